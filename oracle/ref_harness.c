@@ -68,6 +68,7 @@ static int load_seq(SeqFastq *sq, const unsigned char *codes, int n, const char 
 {
   int errcode;
   char *s = codes_to_ascii(codes, n);
+  seqFastqBlank(sq); /* resets the code to ASCII (setSeq, sequence.c:780, does not) */
   errcode = seqFastqSetAscii(sq, "s", s, qual ? "s" : NULL, qual);
   free(s);
   if (errcode) return errcode;
