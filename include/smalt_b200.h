@@ -1,0 +1,160 @@
+/* smalt_b200.h - C ABI of the B200-native SMALT hot path (libsmalt_b200.so).
+ *
+ * Plain C: opaque context, plain pointers and sizes, no C++/torch types.
+ * Every entry point returns 0 (SMB_OK) or an error code; codes <  100 are the
+ * reference's own ERRCODE_* values (/root/reference/src/elib.h:49-139) so a
+ * caller that branches on them (rmap.c:730 ERRCODE_SWATEXCEED, rmap.c:748,
+ * rmap.c:1695 ERRCODE_SHORTSEQ ...) keeps working; codes >= 100 are specific
+ * to this library.  smb_last_error() gives a text for the last failure.
+ *
+ * There is no CPU fallback: without a CUDA device smb_ctx_create() fails with
+ * SMB_ERR_NODEVICE and every compute entry point needs a context.
+ *
+ * Sequences cross the ABI as one byte per base holding the reference's 3-bit
+ * alphabet code in the low 3 bits (A0 C1 G2 T3 X4 N5; SEQCOD_ALPHA_MASK,
+ * sequence.h:98) - the reference's SEQCOD_MANGLED bytes can be passed as they
+ * are, only `code & 7` is used (as in swsimd.c:725, alignment.c:876).
+ *
+ * Reference interfaces replaced (file:line under /root/reference/src):
+ *   smb_sw_score_batch    <- swSIMDAlignStriped      swsimd.h:47-55  (swsimd.c:868)
+ *   smb_band_score_batch  <- aliSmiWatInBandFast     alignment.h:147-175 (alignment.c:1603)
+ *   smb_band_align_batch  <- aliSmiWatInBand + aliRsltSetGetSize/FetchData
+ *                                                    alignment.h:67-145 (alignment.c:1548, :1513, :1518)
+ *   smb_index_upload      <- hashTableRead           hashidx.h:186-190 (hashidx.c:1257)
+ *   smb_refseq_upload     <- seqSetReadBinFil        sequence.h:444 (sequence.c:2521)
+ *   smb_seed_batch        <- hashCollectHitInfoShort hashhit.h (hashhit.c:1007) for both strands
+ *                            + hashCalcHitInfoCoverDeficit (:1096) + hashHitInfoCalcHitNumbers (:1200)
+ *                            + hashCalcHitInfoNumberOfHits (:1171)
+ *   smb_hits_batch        <- hashCollectHitsForSegment (hashhit.c:1691) / hashCollectHitsUsingCutoff
+ *                            (:1593) + hashGetHitListData (:1867)
+ * The reference-side binding a maintainer would add is shown in INTEGRATION.md.
+ */
+#ifndef SMALT_B200_H
+#define SMALT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  SMB_OK = 0,
+  /* reference codes (elib.h) */
+  SMB_ERRCODE_FAILURE = -1,
+  SMB_ERRCODE_NOMEM = 2,
+  SMB_ERRCODE_ARGRANGE = 29,
+  SMB_ERRCODE_SHORTSEQ = 30,
+  SMB_ERRCODE_ALLOCBOUNDARY = 32,
+  SMB_ERRCODE_SWATEXCEED = 41,
+  SMB_ERRCODE_SWATSCOR = 44,
+  SMB_ERRCODE_ASSERT = 47,
+  SMB_ERRCODE_OVERFLOW = 48,
+  SMB_ERRCODE_DIFFSTR = 59,
+  /* library codes */
+  SMB_ERR_NODEVICE = 100,   /* no CUDA device / driver: there is no CPU fallback */
+  SMB_ERR_CUDA = 101,       /* a CUDA runtime call failed (see smb_last_error) */
+  SMB_ERR_ARG = 102,        /* invalid argument */
+  SMB_ERR_CAPACITY = 103,   /* per-task output capacity exceeded (results / diffstr / stack) */
+  SMB_ERR_STATE = 104       /* call order: index / reference / reads not uploaded yet */
+};
+
+typedef struct smb_ctx smb_ctx;
+
+/* ----------------------------- context ---------------------------------- */
+int smb_ctx_create(smb_ctx **ctx, int device);
+void smb_ctx_destroy(smb_ctx *ctx);
+const char *smb_last_error(const smb_ctx *ctx);
+/* library version string, e.g. "smalt-b200 0.1 sm_100a" */
+const char *smb_version(void);
+/* Alignment penalties as given to `smalt map -S` (score.c:41-47 defaults
+ * match=1 mismatch=-2 gapopen=-4 gapext=-3); builds the 8x8 matrix of
+ * score.c:138-173 in constant memory. */
+int smb_set_scoring(smb_ctx *ctx, int match, int mismatch, int gapopen, int gapext);
+/* Device time in ms of the kernels launched by the last batch call, measured
+ * with CUDA events on the context's stream (no host copies included), and the
+ * number of kernel launches of that call. */
+float smb_last_kernel_ms(const smb_ctx *ctx);
+int smb_last_kernel_launches(const smb_ctx *ctx);
+/* total kernels launched by this context since creation */
+long long smb_total_kernel_launches(const smb_ctx *ctx);
+
+/* --------------------------- sequence arena ------------------------------ */
+/* Uploads a block of concatenated sequences (reads and, for the *_batch calls
+ * that take explicit windows, reference windows) to HBM.  Tasks address it by
+ * byte offset.  A later upload replaces the previous one. */
+int smb_arena_upload(smb_ctx *ctx, const uint8_t *codes, size_t nbytes);
+
+/* The packed reference of a `.sma` file: 3 bits per base, 10 bases per 32-bit
+ * word, base i in bits 3*(9 - i%10) of word i/10 (sequence.c:1360-1424);
+ * seq_offs[nseq+1] are the base offsets of the sequences in the concatenated
+ * set (each sequence is followed by one terminator, code 7).  Uploaded once per
+ * GPU; tasks flagged SMB_TASK_REF_PACKED address it by base offset. */
+int smb_refseq_upload(smb_ctx *ctx, const uint32_t *words, size_t nwords,
+		      uint64_t nbases, const uint64_t *seq_offs, int nseq);
+
+/* ------------------------------- tasks ----------------------------------- */
+enum {
+  SMB_TASK_READ_REVCOMP = 1, /* profile the reverse complement of the read (rmap.c:682-692) */
+  SMB_TASK_REF_PACKED = 2    /* ref_off/ref_len address the packed reference, not the arena */
+};
+
+typedef struct {
+  uint64_t read_off; /* byte offset of the read in the arena */
+  uint64_t ref_off;  /* offset of the reference window (arena bytes or packed bases) */
+  uint32_t read_len;
+  uint32_t ref_len;
+  uint32_t flags;
+  uint32_t reserved;
+} smb_sw_task;
+
+typedef struct {
+  uint64_t read_off;
+  uint64_t ref_off;
+  uint32_t read_len;
+  uint32_t ref_len;
+  uint32_t flags;
+  int32_t l_edge, r_edge;   /* band on the read axis at window row 0 (alignment.h:96-100) */
+  int32_t p_left, p_right;  /* read sub-range */
+  int32_t u_left, u_right;  /* window sub-range */
+  int32_t minscore;         /* smb_band_align_batch only */
+  int32_t minscorlen;       /* smb_band_align_batch only */
+} smb_band_task;
+
+typedef struct {
+  int32_t score, qs, qe, rs, re; /* ALIRESULT, alignment.c:149-158 (0-based, inclusive) */
+  uint32_t diff_off;             /* offset of the DiffStr in the diffstr output buffer */
+  uint32_t diff_len;             /* bytes including the terminating 0 */
+  uint32_t task;                 /* index of the task that produced it */
+} smb_ali_result;
+
+/* K2: maximum local alignment score of each read x window pair, unbanded,
+ * canonical affine gaps; scores[i] and errs[i] per task (errs[i] is
+ * SMB_ERRCODE_SWATEXCEED where the reference would return it, swsimd.c:644). */
+int smb_sw_score_batch(smb_ctx *ctx, const smb_sw_task *tasks, int ntasks,
+		       int32_t *scores, int32_t *errs);
+
+/* K2': maximum score of the banded "fast" DP (alignment.c:1029-1233);
+ * errs[i] = SMB_ERRCODE_FAILURE where the band misses the read (alignment.c:1622-1627). */
+int smb_band_score_batch(smb_ctx *ctx, const smb_band_task *tasks, int ntasks,
+			 int32_t *scores, int32_t *errs);
+
+/* K3: banded DP with backtrace and recursion (alignment.c:1300-1434).
+ * Results of all tasks are appended to `results` in task order and, within a
+ * task, in the reference's discovery order; first_result[i] .. first_result[i+1]
+ * delimit task i (first_result has ntasks+1 entries).  DiffStr bytes
+ * (diffstr.h:28-105, forward orientation as stored by addALIMETAtoRsltSet,
+ * alignment.c:1294) go to `diffstr`.  Returns SMB_ERR_CAPACITY if the
+ * caller's buffers are too small (nothing partial is hidden: *nresults and
+ * *ndiffbytes then hold the required sizes). */
+int smb_band_align_batch(smb_ctx *ctx, const smb_band_task *tasks, int ntasks,
+			 smb_ali_result *results, size_t max_results, size_t *nresults,
+			 uint32_t *first_result,
+			 uint8_t *diffstr, size_t max_diffbytes, size_t *ndiffbytes,
+			 int32_t *errs, uint64_t *ncells);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMALT_B200_H */

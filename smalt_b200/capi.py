@@ -1,0 +1,194 @@
+"""ctypes binding of include/smalt_b200.h (the reference-facing C ABI)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+SMB_TASK_READ_REVCOMP = 1
+SMB_TASK_REF_PACKED = 2
+SMB_ERR_CAPACITY = 103
+
+
+class SmbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("smalt_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class SwTask(C.Structure):
+    _fields_ = [("read_off", C.c_uint64), ("ref_off", C.c_uint64), ("read_len", C.c_uint32),
+                ("ref_len", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class BandTask(C.Structure):
+    _fields_ = [("read_off", C.c_uint64), ("ref_off", C.c_uint64), ("read_len", C.c_uint32),
+                ("ref_len", C.c_uint32), ("flags", C.c_uint32),
+                ("l_edge", C.c_int32), ("r_edge", C.c_int32), ("p_left", C.c_int32),
+                ("p_right", C.c_int32), ("u_left", C.c_int32), ("u_right", C.c_int32),
+                ("minscore", C.c_int32), ("minscorlen", C.c_int32)]
+
+
+class AliResult(C.Structure):
+    _fields_ = [("score", C.c_int32), ("qs", C.c_int32), ("qe", C.c_int32), ("rs", C.c_int32),
+                ("re", C.c_int32), ("diff_off", C.c_uint32), ("diff_len", C.c_uint32),
+                ("task", C.c_uint32)]
+
+
+SW_TASK_DTYPE = np.dtype([("read_off", "<u8"), ("ref_off", "<u8"), ("read_len", "<u4"),
+                          ("ref_len", "<u4"), ("flags", "<u4"), ("reserved", "<u4")])
+BAND_TASK_DTYPE = np.dtype([("read_off", "<u8"), ("ref_off", "<u8"), ("read_len", "<u4"),
+                            ("ref_len", "<u4"), ("flags", "<u4"), ("l_edge", "<i4"),
+                            ("r_edge", "<i4"), ("p_left", "<i4"), ("p_right", "<i4"),
+                            ("u_left", "<i4"), ("u_right", "<i4"), ("minscore", "<i4"),
+                            ("minscorlen", "<i4"), ("_pad", "<u4")])
+ALI_RESULT_DTYPE = np.dtype([("score", "<i4"), ("qs", "<i4"), ("qe", "<i4"), ("rs", "<i4"),
+                             ("re", "<i4"), ("diff_off", "<u4"), ("diff_len", "<u4"),
+                             ("task", "<u4")])
+assert SW_TASK_DTYPE.itemsize == C.sizeof(SwTask)
+assert BAND_TASK_DTYPE.itemsize == C.sizeof(BandTask), (BAND_TASK_DTYPE.itemsize, C.sizeof(BandTask))
+assert ALI_RESULT_DTYPE.itemsize == C.sizeof(AliResult)
+
+
+def lib_path():
+    return os.path.join(_HERE, "libsmalt_b200.so")
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libsmalt_b200.so; raises if it is missing - the CUDA library IS the product."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise ImportError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C smalt_b200/csrc` (no CPU fallback exists)" % p)
+    lib = C.CDLL(p)
+    lib.smb_version.restype = C.c_char_p
+    lib.smb_last_error.restype = C.c_char_p
+    lib.smb_last_error.argtypes = [C.c_void_p]
+    lib.smb_last_kernel_ms.restype = C.c_float
+    lib.smb_last_kernel_ms.argtypes = [C.c_void_p]
+    lib.smb_last_kernel_launches.argtypes = [C.c_void_p]
+    lib.smb_total_kernel_launches.restype = C.c_longlong
+    lib.smb_total_kernel_launches.argtypes = [C.c_void_p]
+    lib.smb_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+    lib.smb_ctx_destroy.argtypes = [C.c_void_p]
+    lib.smb_ctx_destroy.restype = None
+    lib.smb_set_scoring.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.smb_arena_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.smb_refseq_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_int]
+    lib.smb_sw_score_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.smb_band_score_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.smb_band_align_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
+                                         C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.c_size_t,
+                                         C.POINTER(C.c_size_t), C.c_void_p, C.POINTER(C.c_uint64)]
+    _lib = lib
+    return lib
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One GPU context (one per process / per GPU): smb_ctx of include/smalt_b200.h."""
+
+    def __init__(self, device=0, penalties=(1, -2, -4, -3)):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        rc = self.lib.smb_ctx_create(C.byref(self._h), device)
+        if rc:
+            raise SmbError(rc, "smb_ctx_create failed (no CUDA device? there is no CPU fallback)")
+        self._check(self.lib.smb_set_scoring(self._h, *penalties))
+        self._keep = []
+
+    def close(self):
+        if self._h:
+            self.lib.smb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise SmbError(rc, self.lib.smb_last_error(self._h).decode())
+
+    @property
+    def last_kernel_ms(self):
+        return float(self.lib.smb_last_kernel_ms(self._h))
+
+    @property
+    def last_kernel_launches(self):
+        return int(self.lib.smb_last_kernel_launches(self._h))
+
+    @property
+    def total_kernel_launches(self):
+        return int(self.lib.smb_total_kernel_launches(self._h))
+
+    def arena_upload(self, codes):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        self._check(self.lib.smb_arena_upload(self._h, _vp(codes), codes.size))
+
+    def refseq_upload(self, words, nbases, seq_offs):
+        words = np.ascontiguousarray(words, np.uint32)
+        so = np.ascontiguousarray(seq_offs, np.uint64)
+        self._check(self.lib.smb_refseq_upload(self._h, _vp(words), words.size, int(nbases), _vp(so),
+                                               len(so) - 1))
+
+    def sw_score(self, tasks):
+        tasks = np.ascontiguousarray(tasks, SW_TASK_DTYPE)
+        n = len(tasks)
+        scores = np.zeros(n, np.int32)
+        errs = np.zeros(n, np.int32)
+        self._check(self.lib.smb_sw_score_batch(self._h, _vp(tasks), n, _vp(scores), _vp(errs)))
+        return scores, errs
+
+    def band_score(self, tasks):
+        tasks = np.ascontiguousarray(tasks, BAND_TASK_DTYPE)
+        n = len(tasks)
+        scores = np.zeros(n, np.int32)
+        errs = np.zeros(n, np.int32)
+        self._check(self.lib.smb_band_score_batch(self._h, _vp(tasks), n, _vp(scores), _vp(errs)))
+        return scores, errs
+
+    def band_align(self, tasks, max_results=None, max_diff=None):
+        """-> (results[ALI_RESULT_DTYPE], first_result[n+1], diffstr bytes, errs, ncells)"""
+        tasks = np.ascontiguousarray(tasks, BAND_TASK_DTYPE)
+        n = len(tasks)
+        if max_results is None:
+            max_results = 4 * n + 64
+        if max_diff is None:
+            max_diff = int(tasks["read_len"].sum() // 2 + 64 * n + 4096)
+        while True:
+            res = np.zeros(max_results, ALI_RESULT_DTYPE)
+            first = np.zeros(n + 1, np.uint32)
+            diff = np.zeros(max_diff, np.uint8)
+            errs = np.zeros(n, np.int32)
+            nres, ndiff, cells = C.c_size_t(0), C.c_size_t(0), C.c_uint64(0)
+            rc = self.lib.smb_band_align_batch(self._h, _vp(tasks), n, _vp(res), max_results,
+                                               C.byref(nres), _vp(first), _vp(diff), max_diff,
+                                               C.byref(ndiff), _vp(errs), C.byref(cells))
+            if rc == SMB_ERR_CAPACITY and (nres.value > max_results or ndiff.value > max_diff):
+                max_results = max(max_results, nres.value)
+                max_diff = max(max_diff, ndiff.value)
+                continue
+            self._check(rc)
+            return res[:nres.value], first, diff[:ndiff.value], errs, cells.value
+
+
+def pack_sequences(seqs):
+    """Concatenates code arrays into one arena; returns (arena, offsets)."""
+    offs = np.zeros(len(seqs) + 1, np.uint64)
+    if seqs:
+        offs[1:] = np.cumsum([len(s) for s in seqs])
+    arena = np.concatenate(seqs).astype(np.uint8) if seqs else np.zeros(0, np.uint8)
+    return arena, offs

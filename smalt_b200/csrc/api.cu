@@ -1,0 +1,425 @@
+// api.cu - the C ABI of include/smalt_b200.h: context, device buffers, batch entry points.
+#include "common.cuh"
+#include "band.h"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace smb;
+
+namespace {
+
+struct DevBuf {  // grow-only device buffer
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T *as() const { return (T *)p; }
+};
+
+}  // namespace
+
+struct smb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  Scoring sc;
+  SeqSrc src{nullptr, nullptr, 0};
+  DevBuf arena, packed, tasks, out_a, out_b, scratch, dirs, diff, offs;
+  size_t arena_bytes = 0;
+  std::vector<uint64_t> seq_offs;
+  float last_ms = 0.f;
+  int last_launches = 0;
+  long long total_launches = 0;
+  std::string err;
+};
+
+static int fail(smb_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CU(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(ctx, SMB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+static void make_scoring(Scoring &sc, int match, int mismatch, int gapopen, int gapext) {
+  sc.match = match;
+  sc.mismatch = mismatch;
+  sc.gap_init = -gapopen;
+  sc.gap_ext = -gapext;
+  for (int a = 0; a < 8; ++a)
+    for (int b = 0; b < 8; ++b) {
+      int s;
+      if (a >= 6 || b >= 6 || a == 5 || b == 5) s = 0;  // N / outside the alphabet (score.c:158-161)
+      else if (a == 4 || b == 4) s = mismatch - match;  // X (score.c:162-163)
+      else s = (a == b) ? match : mismatch;
+      sc.S[a * 8 + b] = (signed char)s;
+    }
+}
+
+extern "C" {
+
+const char *smb_version(void) { return "smalt-b200 0.1 (sm_100a)"; }
+
+int smb_ctx_create(smb_ctx **out, int device) {
+  if (!out) return SMB_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) return SMB_ERR_NODEVICE;
+  smb_ctx *ctx = new (std::nothrow) smb_ctx();
+  if (!ctx) return SMB_ERRCODE_NOMEM;
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+    delete ctx;
+    return SMB_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  make_scoring(ctx->sc, 1, -2, -4, -3);
+  *out = ctx;
+  return SMB_OK;
+}
+
+void smb_ctx_destroy(smb_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf *bufs[] = {&ctx->arena, &ctx->packed, &ctx->tasks, &ctx->out_a, &ctx->out_b,
+                    &ctx->scratch, &ctx->dirs, &ctx->diff, &ctx->offs};
+  for (DevBuf *b : bufs) b->release();
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *smb_last_error(const smb_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+float smb_last_kernel_ms(const smb_ctx *ctx) { return ctx ? ctx->last_ms : 0.f; }
+int smb_last_kernel_launches(const smb_ctx *ctx) { return ctx ? ctx->last_launches : 0; }
+long long smb_total_kernel_launches(const smb_ctx *ctx) { return ctx ? ctx->total_launches : 0; }
+
+int smb_set_scoring(smb_ctx *ctx, int match, int mismatch, int gapopen, int gapext) {
+  if (!ctx) return SMB_ERR_ARG;
+  // scoreSetPenalty ranges (score.c:90-112)
+  if (match < 0 || match > 127 || mismatch > 0 || mismatch < -127 || gapopen > 0 || gapopen < -127 ||
+      gapext > 0 || gapext < -127 || mismatch - match < -127)
+    return fail(ctx, SMB_ERRCODE_SWATEXCEED, "penalty out of range");
+  make_scoring(ctx->sc, match, mismatch, gapopen, gapext);
+  return SMB_OK;
+}
+
+int smb_arena_upload(smb_ctx *ctx, const uint8_t *codes, size_t nbytes) {
+  if (!ctx || (!codes && nbytes)) return SMB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  CU(ctx->arena.ensure(nbytes + 16));
+  CU(cudaMemcpyAsync(ctx->arena.p, codes, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->arena_bytes = nbytes;
+  ctx->src.arena = ctx->arena.as<uint8_t>();
+  return SMB_OK;
+}
+
+int smb_refseq_upload(smb_ctx *ctx, const uint32_t *words, size_t nwords, uint64_t nbases,
+                      const uint64_t *seq_offs, int nseq) {
+  if (!ctx || !words || nwords * 10u < nbases) return SMB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  CU(ctx->packed.ensure(nwords * sizeof(uint32_t) + 16));
+  CU(cudaMemcpyAsync(ctx->packed.p, words, nwords * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->src.packed = ctx->packed.as<uint32_t>();
+  ctx->src.packed_nbases = nbases;
+  ctx->seq_offs.clear();
+  if (seq_offs && nseq > 0) ctx->seq_offs.assign(seq_offs, seq_offs + nseq + 1);
+  return SMB_OK;
+}
+
+static int check_seq_ranges(smb_ctx *ctx, uint64_t read_off, uint32_t read_len, uint64_t ref_off,
+                            uint32_t ref_len, uint32_t flags, int i) {
+  if (read_off + read_len > ctx->arena_bytes)
+    return fail(ctx, SMB_ERR_ARG, "task %d: read [%llu,+%u) outside the arena (%zu bytes)", i,
+                (unsigned long long)read_off, read_len, ctx->arena_bytes);
+  if (flags & SMB_TASK_REF_PACKED) {
+    if (!ctx->src.packed) return fail(ctx, SMB_ERR_STATE, "task %d: no packed reference uploaded", i);
+    if (ref_off + ref_len > ctx->src.packed_nbases)
+      return fail(ctx, SMB_ERR_ARG, "task %d: window outside the packed reference", i);
+  } else if (ref_off + ref_len > ctx->arena_bytes) {
+    return fail(ctx, SMB_ERR_ARG, "task %d: window outside the arena", i);
+  }
+  return SMB_OK;
+}
+
+int smb_sw_score_batch(smb_ctx *ctx, const smb_sw_task *tasks, int ntasks, int32_t *scores,
+                       int32_t *errs) {
+  if (!ctx || ntasks < 0 || (ntasks && (!tasks || !scores || !errs))) return SMB_ERR_ARG;
+  ctx->last_ms = 0.f;
+  ctx->last_launches = 0;
+  if (!ntasks) return SMB_OK;
+  if (!ctx->src.arena) return fail(ctx, SMB_ERR_STATE, "smb_arena_upload() first");
+  for (int i = 0; i < ntasks; ++i) {
+    int rcode = check_seq_ranges(ctx, tasks[i].read_off, tasks[i].read_len, tasks[i].ref_off,
+                                 tasks[i].ref_len, tasks[i].flags, i);
+    if (rcode) return rcode;
+  }
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  CU(ctx->tasks.ensure((size_t)ntasks * sizeof(smb_sw_task)));
+  CU(ctx->out_a.ensure((size_t)ntasks * 2 * sizeof(int32_t)));
+  CU(cudaMemcpyAsync(ctx->tasks.p, tasks, (size_t)ntasks * sizeof(smb_sw_task), cudaMemcpyHostToDevice, st));
+  int32_t *d_scores = ctx->out_a.as<int32_t>(), *d_errs = d_scores + ntasks;
+  size_t need = 0;
+  int nl = 0;
+  CU(launch_sw_score(ctx->sc, ctx->src, ctx->tasks.as<smb_sw_task>(), tasks, ntasks, d_scores, d_errs,
+                     nullptr, 0, &need, ctx->sm_count, st, &nl));
+  CU(ctx->scratch.ensure(need));
+  CU(cudaEventRecord(ctx->ev0, st));
+  CU(launch_sw_score(ctx->sc, ctx->src, ctx->tasks.as<smb_sw_task>(), tasks, ntasks, d_scores, d_errs,
+                     ctx->scratch.p, ctx->scratch.cap, &need, ctx->sm_count, st, &nl));
+  CU(cudaEventRecord(ctx->ev1, st));
+  CU(cudaMemcpyAsync(scores, d_scores, (size_t)ntasks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(errs, d_errs, (size_t)ntasks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+  ctx->last_launches = nl;
+  ctx->total_launches += nl;
+  return SMB_OK;
+}
+
+int smb_band_score_batch(smb_ctx *ctx, const smb_band_task *tasks, int ntasks, int32_t *scores,
+                         int32_t *errs) {
+  if (!ctx || ntasks < 0 || (ntasks && (!tasks || !scores || !errs))) return SMB_ERR_ARG;
+  ctx->last_ms = 0.f;
+  ctx->last_launches = 0;
+  if (!ntasks) return SMB_OK;
+  if (!ctx->src.arena) return fail(ctx, SMB_ERR_STATE, "smb_arena_upload() first");
+  for (int i = 0; i < ntasks; ++i) {
+    int rcode = check_seq_ranges(ctx, tasks[i].read_off, tasks[i].read_len, tasks[i].ref_off,
+                                 tasks[i].ref_len, tasks[i].flags, i);
+    if (rcode) return rcode;
+  }
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  CU(ctx->tasks.ensure((size_t)ntasks * sizeof(smb_band_task)));
+  CU(ctx->out_a.ensure((size_t)ntasks * 2 * sizeof(int32_t) + 64));
+  CU(cudaMemcpyAsync(ctx->tasks.p, tasks, (size_t)ntasks * sizeof(smb_band_task), cudaMemcpyHostToDevice, st));
+  int32_t *d_scores = ctx->out_a.as<int32_t>(), *d_errs = d_scores + ntasks;
+  unsigned long long *d_cells = (unsigned long long *)(((uintptr_t)(d_errs + ntasks) + 15) & ~(uintptr_t)15);
+  CU(cudaMemsetAsync(d_cells, 0, sizeof(unsigned long long), st));
+  BandOut bo{nullptr, nullptr, nullptr, d_errs, d_cells};
+  int nl = 0;
+  CU(cudaEventRecord(ctx->ev0, st));
+  CU(launch_band(ctx->sc, ctx->src, ctx->tasks.as<smb_band_task>(), tasks, ntasks, false, d_scores, bo, 0,
+                 nullptr, nullptr, nullptr, nullptr, ctx->sm_count, st, &nl));
+  CU(cudaEventRecord(ctx->ev1, st));
+  CU(cudaMemcpyAsync(scores, d_scores, (size_t)ntasks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(errs, d_errs, (size_t)ntasks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+  ctx->last_launches = nl;
+  ctx->total_launches += nl;
+  return SMB_OK;
+}
+
+// One pass of K3 over `idx` (indices into tasks) with the given per-task capacities.
+static int band_align_pass(smb_ctx *ctx, const smb_band_task *tasks, const std::vector<int> &idx,
+                           int max_res, int diff_scale, std::vector<smb_ali_result> &h_res,
+                           std::vector<uint32_t> &h_nres, std::vector<int32_t> &h_errs,
+                           std::vector<uint8_t> &h_diff, std::vector<uint64_t> &diff_off,
+                           unsigned long long *cells, float *ms, int *nlaunch) {
+  const int n = (int)idx.size();
+  std::vector<smb_band_task> sub((size_t)n);
+  std::vector<uint64_t> dir_off((size_t)n + 1, 0);
+  std::vector<uint32_t> diff_cap((size_t)n);
+  diff_off.assign((size_t)n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    const smb_band_task &t = tasks[idx[(size_t)i]];
+    sub[(size_t)i] = t;
+    Band b;
+    uint64_t words = 2;
+    if (!band_init(b, t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
+                   (int)t.ref_len)) {
+      const int bw0 = t.r_edge - t.l_edge + 1;
+      int w = (bw0 <= 0) ? (b.q_len - b.q_left) : bw0;
+      if (w < 1) w = 1;
+      words = ((uint64_t)w * (uint64_t)t.ref_len) / 16u + 4u;
+    }
+    dir_off[(size_t)i + 1] = dir_off[(size_t)i] + words;
+    const uint32_t cap = (uint32_t)diff_scale * (t.read_len + t.ref_len + 64u);
+    diff_cap[(size_t)i] = cap;
+    diff_off[(size_t)i + 1] = diff_off[(size_t)i] + cap + (t.read_len + t.ref_len + 8u);
+  }
+  cudaStream_t st = ctx->stream;
+  const size_t res_bytes = (size_t)n * max_res * sizeof(smb_ali_result);
+  const size_t outa = res_bytes + (size_t)n * (sizeof(uint32_t) + sizeof(int32_t)) + 64;
+  CU(ctx->tasks.ensure((size_t)n * sizeof(smb_band_task)));
+  CU(ctx->out_b.ensure(outa));
+  CU(ctx->dirs.ensure(dir_off[(size_t)n] * sizeof(uint32_t)));
+  CU(ctx->diff.ensure(diff_off[(size_t)n]));
+  CU(ctx->offs.ensure((size_t)(n + 1) * 2 * sizeof(uint64_t) + (size_t)n * sizeof(uint32_t)));
+  uint64_t *d_dir_off = ctx->offs.as<uint64_t>();
+  uint64_t *d_diff_off = d_dir_off + (n + 1);
+  uint32_t *d_diff_cap = (uint32_t *)(d_diff_off + (n + 1));
+  CU(cudaMemcpyAsync(ctx->tasks.p, sub.data(), (size_t)n * sizeof(smb_band_task), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_dir_off, dir_off.data(), (size_t)(n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_diff_off, diff_off.data(), (size_t)(n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_diff_cap, diff_cap.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  char *ob = ctx->out_b.as<char>();
+  smb_ali_result *d_res = (smb_ali_result *)ob;
+  uint32_t *d_nres = (uint32_t *)(ob + res_bytes);
+  int32_t *d_errs = (int32_t *)(d_nres + n);
+  unsigned long long *d_cells = (unsigned long long *)(((uintptr_t)(d_errs + n) + 15) & ~(uintptr_t)15);
+  CU(cudaMemsetAsync(d_cells, 0, sizeof(unsigned long long), st));
+  BandOut bo{d_res, d_nres, ctx->diff.as<uint8_t>(), d_errs, d_cells};
+  CU(cudaEventRecord(ctx->ev0, st));
+  CU(launch_band(ctx->sc, ctx->src, ctx->tasks.as<smb_band_task>(), sub.data(), n, true, nullptr, bo, max_res,
+                 d_dir_off, ctx->dirs.as<uint32_t>(), d_diff_off, d_diff_cap, ctx->sm_count, st, nlaunch));
+  CU(cudaEventRecord(ctx->ev1, st));
+  h_res.resize((size_t)n * max_res);
+  h_nres.resize((size_t)n);
+  h_errs.resize((size_t)n);
+  h_diff.resize(diff_off[(size_t)n]);
+  unsigned long long c = 0;
+  CU(cudaMemcpyAsync(h_res.data(), d_res, res_bytes, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h_nres.data(), d_nres, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h_errs.data(), d_errs, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h_diff.data(), ctx->diff.p, diff_off[(size_t)n], cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(&c, d_cells, sizeof c, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  float m = 0.f;
+  CU(cudaEventElapsedTime(&m, ctx->ev0, ctx->ev1));
+  *ms += m;
+  *cells += c;
+  return SMB_OK;
+}
+
+int smb_band_align_batch(smb_ctx *ctx, const smb_band_task *tasks, int ntasks, smb_ali_result *results,
+                         size_t max_results, size_t *nresults, uint32_t *first_result, uint8_t *diffstr,
+                         size_t max_diffbytes, size_t *ndiffbytes, int32_t *errs, uint64_t *ncells) {
+  if (!ctx || ntasks < 0 || !nresults || !ndiffbytes || (ntasks && (!tasks || !first_result || !errs)))
+    return SMB_ERR_ARG;
+  ctx->last_ms = 0.f;
+  ctx->last_launches = 0;
+  *nresults = 0;
+  *ndiffbytes = 0;
+  if (ncells) *ncells = 0;
+  if (first_result) first_result[0] = 0;
+  if (!ntasks) return SMB_OK;
+  if (!ctx->src.arena) return fail(ctx, SMB_ERR_STATE, "smb_arena_upload() first");
+  for (int i = 0; i < ntasks; ++i) {
+    int rcode = check_seq_ranges(ctx, tasks[i].read_off, tasks[i].read_len, tasks[i].ref_off,
+                                 tasks[i].ref_len, tasks[i].flags, i);
+    if (rcode) return rcode;
+  }
+  cudaSetDevice(ctx->device);
+
+  // per task: results and diff bytes collected from (possibly several) passes
+  struct TaskOut { std::vector<smb_ali_result> res; std::vector<uint8_t> diff; int32_t err = 0; };
+  std::vector<TaskOut> outs((size_t)ntasks);
+  std::vector<int> todo((size_t)ntasks);
+  for (int i = 0; i < ntasks; ++i) todo[(size_t)i] = i;
+  int max_res = 8, diff_scale = 1, nl = 0;
+  float ms = 0.f;
+  unsigned long long cells = 0;
+  // memory-bounded chunks (direction strips can be large for long reads)
+  const uint64_t DIR_WORDS_MAX = (uint64_t)1 << 30;  // 4 GiB of direction words per pass
+  for (int attempt = 0; attempt < 6 && !todo.empty(); ++attempt) {
+    std::vector<int> retry;
+    size_t pos = 0;
+    while (pos < todo.size()) {
+      std::vector<int> chunk;
+      uint64_t words = 0;
+      while (pos < todo.size()) {
+        const smb_band_task &t = tasks[todo[pos]];
+        const int bw0 = t.r_edge - t.l_edge + 1;
+        const uint64_t w = (uint64_t)(bw0 <= 0 ? t.read_len : (uint32_t)bw0) * t.ref_len / 16u + 4u;
+        if (!chunk.empty() && words + w > DIR_WORDS_MAX) break;
+        words += w;
+        chunk.push_back(todo[pos++]);
+      }
+      std::vector<smb_ali_result> h_res;
+      std::vector<uint32_t> h_nres;
+      std::vector<int32_t> h_errs;
+      std::vector<uint8_t> h_diff;
+      std::vector<uint64_t> doff;
+      const unsigned long long cells_before = cells;
+      int rcode = band_align_pass(ctx, tasks, chunk, max_res, diff_scale, h_res, h_nres, h_errs, h_diff,
+                                  doff, &cells, &ms, &nl);
+      if (rcode) return rcode;
+      (void)cells_before;
+      for (size_t k = 0; k < chunk.size(); ++k) {
+        const int ti = chunk[k];
+        TaskOut &o = outs[(size_t)ti];
+        o.res.clear();
+        o.diff.clear();
+        o.err = h_errs[k];
+        if (o.err == SMB_ERR_CAPACITY && attempt < 5) { retry.push_back(ti); continue; }
+        for (uint32_t r = 0; r < h_nres[k]; ++r) {
+          smb_ali_result rr = h_res[k * (size_t)max_res + r];
+          const uint8_t *src = h_diff.data() + doff[k] + rr.diff_off;
+          rr.diff_off = (uint32_t)o.diff.size();
+          rr.task = (uint32_t)ti;
+          o.diff.insert(o.diff.end(), src, src + rr.diff_len);
+          o.res.push_back(rr);
+        }
+      }
+    }
+    todo.swap(retry);
+    max_res *= 8;
+    diff_scale *= 4;
+  }
+  ctx->last_ms = ms;
+  ctx->last_launches = nl;
+  ctx->total_launches += nl;
+  if (ncells) *ncells = cells;
+  size_t nr = 0, nd = 0;
+  for (int i = 0; i < ntasks; ++i) { nr += outs[(size_t)i].res.size(); nd += outs[(size_t)i].diff.size(); }
+  *nresults = nr;
+  *ndiffbytes = nd;
+  if (nr > max_results || nd > max_diffbytes || (nr && !results) || (nd && !diffstr))
+    return fail(ctx, SMB_ERR_CAPACITY, "need %zu results and %zu diffstr bytes", nr, nd);
+  nr = nd = 0;
+  for (int i = 0; i < ntasks; ++i) {
+    TaskOut &o = outs[(size_t)i];
+    first_result[i] = (uint32_t)nr;
+    errs[i] = o.err;
+    for (smb_ali_result rr : o.res) {
+      rr.diff_off += (uint32_t)nd;
+      results[nr++] = rr;
+    }
+    if (!o.diff.empty()) memcpy(diffstr + nd, o.diff.data(), o.diff.size());
+    nd += o.diff.size();
+  }
+  first_result[ntasks] = (uint32_t)nr;
+  return SMB_OK;
+}
+
+}  // extern "C"

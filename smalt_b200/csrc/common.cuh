@@ -1,0 +1,71 @@
+// common.cuh - shared declarations of the sm_100a kernels behind include/smalt_b200.h
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/smalt_b200.h"
+
+namespace smb {
+
+// 8x8 substitution matrix over the 3-bit alphabet + affine gap costs
+// (score.c:138-173; gap costs positive as returned by scoreGetProfile, score.c:682-683).
+// Passed to kernels by value (lives in the constant bank of the launch parameters).
+struct Scoring {
+  int match, mismatch, gap_init, gap_ext;
+  signed char S[64];  // S[ref*8 + read]
+};
+
+// Where a kernel reads sequences from.
+struct SeqSrc {
+  const uint8_t *arena;     // concatenated code bytes (reads, explicit windows)
+  const uint32_t *packed;   // 3-bit packed reference, 10 bases / word (sequence.c:1360-1424)
+  uint64_t packed_nbases;
+};
+
+// base i of the packed reference: bits 3*(9 - i%10) of word i/10
+__device__ __forceinline__ uint32_t packed_base(const uint32_t *__restrict__ w, uint64_t i) {
+  const uint64_t wi = i / 10u;
+  const uint32_t r = (uint32_t)(i - wi * 10u);
+  return (__ldg(w + wi) >> (3u * (9u - r))) & 7u;
+}
+
+__device__ __forceinline__ uint32_t ref_base(const SeqSrc &s, bool packed, uint64_t off, uint32_t i) {
+  return packed ? packed_base(s.packed, off + i) : (uint32_t)(__ldg(s.arena + off + i) & 7u);
+}
+
+// base j of the profiled sequence: the read, or its reverse complement
+// (complement of the 2-bit codes, everything else unchanged - seqFastqAppendSegment
+// with reverse+codec, sequence.c; codtab_complement sequence.c:305)
+__device__ __forceinline__ uint32_t read_base(const uint8_t *__restrict__ arena, uint64_t off,
+                                              uint32_t len, bool rc, uint32_t j) {
+  uint32_t c = __ldg(arena + off + (rc ? (len - 1u - j) : j)) & 7u;
+  if (rc && c < 4u) c = 3u - c;
+  return c;
+}
+
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+};
+
+// launchers (one per .cu)
+cudaError_t launch_sw_score(const Scoring &sc, const SeqSrc &src, const smb_sw_task *d_tasks,
+                            const smb_sw_task *h_tasks, int ntasks, int32_t *d_scores,
+                            int32_t *d_errs, void *d_scratch, size_t scratch_bytes,
+                            size_t *scratch_needed, int sm_count, cudaStream_t st, int *nlaunch);
+
+struct BandOut {        // device buffers of smb_band_align_batch
+  smb_ali_result *results;  // [ntasks * max_res]
+  uint32_t *nres;           // [ntasks]
+  uint8_t *diff;            // per-task arenas, task i at diff_off[i], capacity diff_cap[i]
+  int32_t *errs;            // [ntasks]
+  unsigned long long *cells;
+};
+
+cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_task *d_tasks,
+                        const smb_band_task *h_tasks, int ntasks, bool align,
+                        int32_t *d_scores, BandOut out, int max_res,
+                        const uint64_t *d_dir_off, uint32_t *d_dirs,
+                        const uint64_t *d_diff_off, const uint32_t *d_diff_cap,
+                        int sm_count, cudaStream_t st, int *nlaunch);
+
+}  // namespace smb

@@ -1,0 +1,246 @@
+// sw_score.cu - K2: batched Smith-Waterman score kernel for sm_100a.
+//
+// Replaces swSIMDAlignStriped (/root/reference/src/swsimd.c:868-933): the maximum local
+// alignment score of a read (profiled sequence) against a reference window, unbanded,
+// canonical affine gaps:
+//     h = max(0, Hdiag + S);  H = max(h, E, F);
+//     E' = max(E - ext, H - init);  F' = max(F - ext, H - init);   result = max H
+// (swsimd.c:745-781; the reference's 8-bit pass / 16-bit retry / lazy-F loop are SSE2
+// mechanics of the same recurrence - the returned integer is the exact maximum, and
+// ERRCODE_SWATEXCEED when it reaches 65535, swsimd.c:644).
+//
+// B200 mapping (not a port of the striped layout, which exists to feed 128-bit SIMD):
+//  * inter-task parallel: ONE WARP PER read x window task, persistent warps pulling tasks
+//    from an atomic counter (grid = multiple of the SM count);
+//  * inside a task the 32 lanes form a systolic array over the read: lane l owns C
+//    consecutive read columns in REGISTERS (H, E, the read bases), reference rows stream
+//    through the lanes one step apart (row i is in lane l at step i+l).  The only
+//    inter-lane traffic is two warp shuffles per step: H of the lane's last column and
+//    (F << 3 | reference base) - no shared memory, no global traffic in the inner loop;
+//  * the recurrence is issued with the DPX integer instructions (VIADDMNMX / VIMNMX3 via
+//    __viaddmax_s32 / __vimax3_s32 / __viaddmax_s32_relu): 5 DPX/ALU ops + a compare-select
+//    for the substitution score per cell;
+//  * reads longer than 32*C columns are processed in column blocks; the block's right
+//    boundary column (H, F per row) goes through a per-warp L2-resident scratch strip;
+//  * the reference window is read straight from the 3-bit packed reference (10 bases per
+//    32-bit word, the .sma layout) or from explicit bytes, 32 rows per coalesced load.
+#include "common.cuh"
+#include <algorithm>
+#include <vector>
+
+namespace smb {
+
+constexpr int SW_WARPS = 4;  // warps per CTA
+
+struct SwClassArgs {
+  const int *order;  // task indices of this class
+  int ntasks;
+  int *counter;      // persistent-scheduler ticket
+};
+
+template <int C>
+__global__ void __launch_bounds__(SW_WARPS * 32)
+sw_score_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restrict__ tasks,
+                const SwClassArgs cls, int32_t *__restrict__ scores, int32_t *__restrict__ errs,
+                int2 *__restrict__ bscratch, const uint32_t bstride) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int gwarp = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
+  int2 *const strip0 = bscratch + (size_t)gwarp * 2u * bstride;
+  const int gi = sc.gap_init, ge = sc.gap_ext, smatch = sc.match;
+
+  for (;;) {
+    int k = 0;
+    if (lane == 0) k = atomicAdd(cls.counter, 1);
+    k = __shfl_sync(FULL, k, 0);
+    if (k >= cls.ntasks) break;
+    const int tix = __ldg(cls.order + k);
+    const smb_sw_task tk = tasks[tix];
+    const int qlen = (int)tk.read_len, rlen = (int)tk.ref_len;
+    const bool rc = (tk.flags & SMB_TASK_READ_REVCOMP) != 0;
+    const bool packed = (tk.flags & SMB_TASK_REF_PACKED) != 0;
+    const int nblk = (qlen + 32 * C - 1) / (32 * C);
+    const int nsteps = rlen + 31;
+    int best = 0;
+
+    for (int b = 0; b < nblk; ++b) {
+      const int j0 = b * 32 * C + lane * C;
+      int qcode[C], smis[C], H[C], E[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int j = j0 + c;
+        int q = 7, sm = -30000;  // padding column: never scores
+        if (j < qlen) {
+          q = (int)read_base(src.arena, tk.read_off, (uint32_t)qlen, rc, (uint32_t)j);
+          sm = (q < 4) ? sc.mismatch : (int)sc.S[q];  // non-standard read base: S[A][q]
+        }
+        qcode[c] = q;
+        smis[c] = sm;
+        H[c] = 0;
+        E[c] = 0;
+      }
+      int hdiag = 0, hout = 0, frout = 0;
+      uint32_t rbuf = 7u;
+      int2 bin = make_int2(0, 0), keep = make_int2(0, 0);
+      const int2 *bin_strip = strip0 + (size_t)((b & 1) ^ 1) * bstride;
+      int2 *bout_strip = strip0 + (size_t)(b & 1) * bstride;
+      const bool has_in = b > 0, has_out = b < nblk - 1;
+
+      for (int t = 0; t < nsteps; ++t) {
+        if ((t & 31) == 0) {
+          const int i = t + lane;
+          rbuf = (i < rlen) ? ref_base(src, packed, tk.ref_off, (uint32_t)i) : 7u;
+          if (has_in) bin = (i < rlen) ? __ldcg(bin_strip + i) : make_int2(0, 0);
+        }
+        int hl = __shfl_up_sync(FULL, hout, 1);
+        const int fr = __shfl_up_sync(FULL, frout, 1);
+        const int r0 = (int)__shfl_sync(FULL, rbuf, t & 31);
+        int r = fr & 7, F = fr >> 3;
+        if (has_in) {
+          const int hb = __shfl_sync(FULL, bin.x, t & 31);
+          const int fb = __shfl_sync(FULL, bin.y, t & 31);
+          if (lane == 0) { hl = hb; F = fb; }
+        } else if (lane == 0) {
+          hl = 0;
+          F = 0;
+        }
+        if (lane == 0) r = r0;
+        const int i = t - lane;
+        if (i >= 0 && i < rlen) {
+          int diag = hdiag;
+          hdiag = hl;
+          if (r < 4) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              const int s = (qcode[c] == r) ? smatch : smis[c];
+              const int h = __viaddmax_s32(diag, s, 0);
+              diag = H[c];
+              const int hn = __vimax3_s32(h, E[c], F);
+              best = max(best, hn);
+              const int tt = hn - gi;
+              E[c] = __viaddmax_s32(E[c], -ge, tt);
+              F = __viaddmax_s32_relu(F, -ge, tt);
+              H[c] = hn;
+            }
+          } else {  // non-standard reference base (N, X, terminator): table row
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+              const int s = (qcode[c] == 7 && smis[c] < -1000) ? smis[c] : (int)sc.S[r * 8 + qcode[c]];
+              const int h = __viaddmax_s32(diag, s, 0);
+              diag = H[c];
+              const int hn = __vimax3_s32(h, E[c], F);
+              best = max(best, hn);
+              const int tt = hn - gi;
+              E[c] = __viaddmax_s32(E[c], -ge, tt);
+              F = __viaddmax_s32_relu(F, -ge, tt);
+              H[c] = hn;
+            }
+          }
+          hout = H[C - 1];
+          frout = (F << 3) | r;
+        }
+        if (has_out) {  // hand the block's last column (lane 31) to the next column block
+          const int ho = __shfl_sync(FULL, hout, 31);
+          const int fo = __shfl_sync(FULL, frout, 31) >> 3;
+          const int i31 = t - 31;
+          if (i31 >= 0) {
+            if (lane == (i31 & 31)) keep = make_int2(ho, fo);
+            if ((i31 & 31) == 31 || i31 == rlen - 1) {
+              const int base = i31 & ~31;
+              if (base + lane <= i31) __stcg(bout_strip + base + lane, keep);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    best = __reduce_max_sync(FULL, best);
+    if (lane == 0) {
+      const bool exceed = best >= 65535;  // swsimd.c:644
+      scores[tix] = exceed ? 0 : best;
+      errs[tix] = exceed ? SMB_ERRCODE_SWATEXCEED : SMB_OK;
+    }
+  }
+}
+
+template <int C>
+static cudaError_t launch_class(const Scoring &sc, const SeqSrc &src, const smb_sw_task *d_tasks,
+                                const SwClassArgs &cls, int32_t *d_scores, int32_t *d_errs,
+                                int2 *bscratch, uint32_t bstride, int grid, cudaStream_t st) {
+  sw_score_kernel<C><<<grid, SW_WARPS * 32, 0, st>>>(sc, src, d_tasks, cls, d_scores, d_errs,
+                                                      bscratch, bstride);
+  return cudaGetLastError();
+}
+
+// scratch layout: [8 counters | order[ntasks] | boundary strips]
+cudaError_t launch_sw_score(const Scoring &sc, const SeqSrc &src, const smb_sw_task *d_tasks,
+                            const smb_sw_task *h_tasks, int ntasks, int32_t *d_scores,
+                            int32_t *d_errs, void *d_scratch, size_t scratch_bytes,
+                            size_t *scratch_needed, int sm_count, cudaStream_t st, int *nlaunch) {
+  constexpr int NCLS = 8;
+  std::vector<int> order((size_t)ntasks);
+  int count[NCLS + 1] = {0}, start[NCLS + 1] = {0};
+  uint32_t max_rlen_multi = 0;
+  auto cls_of = [](uint32_t qlen) {
+    int c = (int)((qlen + 31) / 32);
+    return c < 1 ? 1 : (c > NCLS ? NCLS : c);
+  };
+  for (int i = 0; i < ntasks; ++i) {
+    count[cls_of(h_tasks[i].read_len)]++;
+    if (h_tasks[i].read_len > 32u * NCLS) max_rlen_multi = std::max(max_rlen_multi, h_tasks[i].ref_len);
+  }
+  for (int c = 1; c <= NCLS; ++c) start[c] = start[c - 1] + count[c - 1];
+  {
+    int fill[NCLS + 1];
+    for (int c = 0; c <= NCLS; ++c) fill[c] = start[c];
+    for (int i = 0; i < ntasks; ++i) order[(size_t)fill[cls_of(h_tasks[i].read_len)]++] = i;
+  }
+  // long reads first inside the multi-block class (largest tasks start earliest)
+  if (max_rlen_multi)
+    std::stable_sort(order.begin() + start[NCLS], order.begin() + start[NCLS] + count[NCLS],
+                     [&](int a, int b) {
+                       return (uint64_t)h_tasks[a].read_len * h_tasks[a].ref_len >
+                              (uint64_t)h_tasks[b].read_len * h_tasks[b].ref_len;
+                     });
+  const int blocks_per_sm = 8;
+  const int max_grid = sm_count * blocks_per_sm;
+  const uint32_t bstride = (max_rlen_multi + 31u) & ~31u;
+  const size_t off_order = 256;
+  const size_t off_strip = (off_order + (size_t)ntasks * sizeof(int) + 255) & ~(size_t)255;
+  const size_t need = off_strip + (size_t)max_grid * SW_WARPS * 2u * bstride * sizeof(int2);
+  *scratch_needed = need;
+  if (need > scratch_bytes || d_scratch == nullptr) return cudaSuccess;  // caller grows and retries
+
+  char *base = (char *)d_scratch;
+  int *d_counters = (int *)base;
+  int *d_order = (int *)(base + off_order);
+  int2 *d_strips = (int2 *)(base + off_strip);
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(d_counters, 0, 256, st)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyAsync(d_order, order.data(), (size_t)ntasks * sizeof(int),
+                           cudaMemcpyHostToDevice, st)) != cudaSuccess)
+    return e;
+  // the order vector must outlive the async copy: pageable-memory copies are staged
+  // synchronously by the runtime before cudaMemcpyAsync returns.
+  for (int c = 1; c <= NCLS; ++c) {
+    if (!count[c]) continue;
+    SwClassArgs cls{d_order + start[c], count[c], d_counters + c};
+    int grid = (count[c] + SW_WARPS - 1) / SW_WARPS;
+    if (grid > max_grid) grid = max_grid;
+    switch (c) {
+      case 1: e = launch_class<1>(sc, src, d_tasks, cls, d_scores, d_errs, d_strips, bstride, grid, st); break;
+      case 2: e = launch_class<2>(sc, src, d_tasks, cls, d_scores, d_errs, d_strips, bstride, grid, st); break;
+      case 3: e = launch_class<3>(sc, src, d_tasks, cls, d_scores, d_errs, d_strips, bstride, grid, st); break;
+      case 4: e = launch_class<4>(sc, src, d_tasks, cls, d_scores, d_errs, d_strips, bstride, grid, st); break;
+      case 5: e = launch_class<5>(sc, src, d_tasks, cls, d_scores, d_errs, d_strips, bstride, grid, st); break;
+      case 6: e = launch_class<6>(sc, src, d_tasks, cls, d_scores, d_errs, d_strips, bstride, grid, st); break;
+      case 7: e = launch_class<7>(sc, src, d_tasks, cls, d_scores, d_errs, d_strips, bstride, grid, st); break;
+      default: e = launch_class<8>(sc, src, d_tasks, cls, d_scores, d_errs, d_strips, bstride, grid, st); break;
+    }
+    if (e != cudaSuccess) return e;
+    ++*nlaunch;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace smb

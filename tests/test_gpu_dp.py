@@ -1,0 +1,243 @@
+"""Parity of the CUDA DP kernels (through the C ABI, libsmalt_b200.so) with the oracle:
+K2 smb_sw_score_batch, K2' smb_band_score_batch, K3 smb_band_align_batch.
+Bit-exact: scores, coordinates, DiffStr bytes, result order, error codes."""
+import numpy as np
+import pytest
+
+from golden_io import load_bam_cigar, load_trace, parse_record
+from oracle_lib import Oracle
+from seqgen import random_seq, read_window_pair, revcomp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import smalt_b200
+    c = smalt_b200.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return Oracle()
+
+
+def _arena(pairs):
+    from smalt_b200.capi import pack_sequences
+    seqs = []
+    for rd, win in pairs:
+        seqs += [rd, win]
+    arena, offs = pack_sequences(seqs)
+    return arena, offs
+
+
+def _sw_tasks(pairs, offs, flags=None):
+    from smalt_b200.capi import SW_TASK_DTYPE
+    t = np.zeros(len(pairs), SW_TASK_DTYPE)
+    for i, (rd, win) in enumerate(pairs):
+        t[i] = (offs[2 * i], offs[2 * i + 1], len(rd), len(win), 0 if flags is None else flags[i], 0)
+    return t
+
+
+def _band_tasks(pairs, offs, args, minscore=None, minscorlen=None):
+    from smalt_b200.capi import BAND_TASK_DTYPE
+    t = np.zeros(len(pairs), BAND_TASK_DTYPE)
+    for i, (rd, win) in enumerate(pairs):
+        t[i]["read_off"], t[i]["ref_off"] = offs[2 * i], offs[2 * i + 1]
+        t[i]["read_len"], t[i]["ref_len"] = len(rd), len(win)
+        (t[i]["l_edge"], t[i]["r_edge"], t[i]["p_left"], t[i]["p_right"], t[i]["u_left"],
+         t[i]["u_right"]) = args[i]
+        if minscore is not None:
+            t[i]["minscore"], t[i]["minscorlen"] = minscore[i], minscorlen[i]
+    return t
+
+
+def _unpack(res, first, diff, i):
+    out = []
+    for r in res[first[i]:first[i + 1]]:
+        d = bytes(diff[r["diff_off"]:r["diff_off"] + r["diff_len"]])
+        out.append(((int(r["score"]), int(r["qs"]), int(r["qe"]), int(r["rs"]), int(r["re"])), d))
+    return out
+
+
+def _rand_pairs(rng, n, qmin, qmax, nonstd=True):
+    pairs = []
+    for it in range(n):
+        qlen = int(rng.integers(qmin, qmax))
+        mut = [dict(p_sub=0.02, p_ins=0.005, p_del=0.005), dict(p_sub=0.1, p_ins=0.04, p_del=0.04),
+               dict(p_sub=0.0, p_ins=0.0, p_del=0.0)][it % 3]
+        rd, win, lf = read_window_pair(rng, qlen, with_flank=True, **mut)
+        if nonstd and it % 6 == 5:
+            rd[rng.integers(0, len(rd))] = 5
+            win[rng.integers(0, len(win))] = 5
+            win[rng.integers(0, len(win))] = 4
+            rd[rng.integers(0, len(rd))] = 4
+        if it % 9 == 8:
+            win = random_seq(rng, len(win))  # unrelated
+        pairs.append((rd, win, lf))
+    return pairs
+
+
+def _band_args(rng, qlen, rlen, lf):
+    style = rng.integers(0, 6)
+    if style == 0 or style > 3:
+        off = -lf + int(rng.integers(-6, 7))
+        w = int(rng.integers(2, 40))
+        return off - w, off + w, 0, qlen - 1, 0, rlen - 1
+    if style == 1:
+        pl, pr = int(rng.integers(0, qlen // 2)), int(rng.integers(qlen // 2, qlen + 3))
+        ul, ur = int(rng.integers(0, rlen // 2)), int(rng.integers(rlen // 2, rlen + 3))
+        l = int(rng.integers(-rlen, qlen))
+        return l, l + int(rng.integers(0, 60)), pl, pr, ul, ur
+    if style == 2:
+        l = int(rng.integers(-50, 50))
+        return l, l - int(rng.integers(0, 5)), 0, qlen - 1, 0, rlen - 1
+    l = int(rng.integers(-2 * rlen, 2 * qlen))
+    return (l, l + int(rng.integers(0, 2 * qlen)), int(rng.integers(-2, qlen)), int(rng.integers(-2, qlen + 2)),
+            int(rng.integers(-2, rlen)), int(rng.integers(-2, rlen + 2)))
+
+
+def test_sw_score_vs_oracle(ctx, orc):
+    rng = np.random.default_rng(101)
+    # every columns-per-lane class (1..8), the multi-block path (> 256), ragged lengths
+    trip = _rand_pairs(rng, 400, 8, 300) + _rand_pairs(rng, 40, 257, 1200) + _rand_pairs(rng, 6, 2000, 4000)
+    pairs = [(a, b) for a, b, _ in trip]
+    arena, offs = _arena(pairs)
+    ctx.arena_upload(arena)
+    scores, errs = ctx.sw_score(_sw_tasks(pairs, offs))
+    assert ctx.last_kernel_launches >= 8
+    for i, (rd, win) in enumerate(pairs):
+        e, s = orc.sw_striped(rd, win)
+        assert (int(errs[i]), int(scores[i])) == (e, s), (i, len(rd), len(win))
+    # reverse-complement flag == profiling the reverse complement
+    flags = [1] * len(pairs)
+    scores_rc, _ = ctx.sw_score(_sw_tasks(pairs, offs, flags))
+    for i in range(0, len(pairs), 7):
+        rd, win = pairs[i]
+        assert int(scores_rc[i]) == orc.sw_striped(revcomp(rd), win)[1]
+
+
+def test_sw_score_packed_reference(ctx, orc):
+    """windows read from the 3-bit packed reference store (the .sma layout)"""
+    from smalt_b200.capi import SW_TASK_DTYPE, pack_sequences
+    from smalt_b200.seqpack import concat_set, pack3
+    rng = np.random.default_rng(102)
+    genome = [random_seq(rng, 5000, p_n=0.002), random_seq(rng, 3333)]
+    codes, soffs = concat_set(genome)
+    ctx.refseq_upload(pack3(codes), len(codes), soffs)
+    reads, tasks = [], []
+    for i in range(200):
+        s = int(rng.integers(0, 2))
+        qlen = int(rng.integers(30, 200))
+        st = int(rng.integers(0, len(genome[s]) - qlen - 40))
+        rd = genome[s][st + 10:st + 10 + qlen].copy()
+        rd[rng.integers(0, qlen, 3)] = rng.integers(0, 4, 3)
+        reads.append(rd)
+        tasks.append((st, qlen + 30, s))
+    arena, offs = pack_sequences(reads)
+    ctx.arena_upload(arena)
+    t = np.zeros(len(reads), SW_TASK_DTYPE)
+    for i, (st, wl, s) in enumerate(tasks):
+        t[i] = (offs[i], int(soffs[s]) + st, len(reads[i]), wl, 2, 0)
+    scores, errs = ctx.sw_score(t)
+    for i, (st, wl, s) in enumerate(tasks):
+        assert (int(errs[i]), int(scores[i])) == orc.sw_striped(reads[i], np.ascontiguousarray(genome[s][st:st + wl]))
+
+
+def test_sw_score_edge_cases(ctx, orc):
+    from smalt_b200.capi import SW_TASK_DTYPE
+    scores, errs = ctx.sw_score(np.zeros(0, SW_TASK_DTYPE))
+    assert len(scores) == 0
+    pairs = [(np.array([0], np.uint8), np.array([0], np.uint8)),
+             (np.array([0, 1, 2], np.uint8), np.array([3], np.uint8)),
+             (np.full(40, 5, np.uint8), np.full(50, 5, np.uint8)),
+             (np.full(33, 2, np.uint8), np.full(70, 2, np.uint8))]
+    arena, offs = _arena(pairs)
+    ctx.arena_upload(arena)
+    scores, errs = ctx.sw_score(_sw_tasks(pairs, offs))
+    for i, (rd, win) in enumerate(pairs):
+        assert (int(errs[i]), int(scores[i])) == orc.sw_striped(rd, win)
+
+
+def test_band_score_vs_oracle(ctx, orc):
+    rng = np.random.default_rng(103)
+    trip = _rand_pairs(rng, 500, 12, 220)
+    pairs = [(a, b) for a, b, _ in trip]
+    args = [_band_args(rng, len(a), len(b), lf) for a, b, lf in trip]
+    arena, offs = _arena(pairs)
+    ctx.arena_upload(arena)
+    scores, errs = ctx.band_score(_band_tasks(pairs, offs, args))
+    nok = 0
+    for i, (rd, win) in enumerate(pairs):
+        e, s, _ = orc.band_fast(rd, win, *args[i])
+        assert int(errs[i]) == e, (i, args[i])
+        if e == 0:
+            assert int(scores[i]) == s, (i, args[i])
+            nok += 1
+    assert nok > 200
+
+
+def test_band_align_vs_oracle(ctx, orc):
+    rng = np.random.default_rng(104)
+    trip = _rand_pairs(rng, 600, 20, 260)
+    pairs, args = [], []
+    for k, (a, b, lf) in enumerate(trip):
+        if k % 7 == 0:  # two copies of the target -> recursion produces several results
+            b = np.concatenate([b, random_seq(rng, 9), b])
+        pairs.append((a, b))
+        args.append(_band_args(rng, len(a), len(b), lf))
+    minscore = [int(x) for x in rng.integers(1, 40, len(pairs))]
+    minscorlen = [int(x) for x in rng.integers(5, 30, len(pairs))]
+    arena, offs = _arena(pairs)
+    ctx.arena_upload(arena)
+    res, first, diff, errs, cells = ctx.band_align(_band_tasks(pairs, offs, args, minscore, minscorlen))
+    tot, ocells = 0, 0
+    for i, (rd, win) in enumerate(pairs):
+        e, want, c = orc.band_align(rd, win, *args[i], minscore[i], minscorlen[i])
+        ocells += c
+        assert int(errs[i]) == e, (i, args[i])
+        assert _unpack(res, first, diff, i) == want, (i, args[i], minscore[i], minscorlen[i])
+        tot += len(want)
+    assert tot > 300
+    assert cells == ocells
+
+
+@pytest.mark.parametrize("name", ["dp_trace_c1.txt", "dp_trace_hard.txt"])
+def test_golden_traces(ctx, name):
+    """DP boundary calls recorded from the reference's own `smalt map` runs"""
+    recs = load_trace(name)
+    _run_records(ctx, recs)
+
+
+def test_reference_known_answers(ctx):
+    g = load_bam_cigar()
+    _run_records(ctx, [parse_record(l) for l in g["trace"]["cigar"]])
+
+
+def _run_records(ctx, recs):
+    for kind in ("SW", "BF", "BA"):
+        sel = [r for r in recs if r["kind"] == kind]
+        if not sel:
+            continue
+        pairs = [(r["read"], r["ref"]) for r in sel]
+        arena, offs = _arena(pairs)
+        ctx.arena_upload(arena)
+        if kind == "SW":
+            scores, errs = ctx.sw_score(_sw_tasks(pairs, offs))
+            for i, r in enumerate(sel):
+                assert (int(errs[i]), int(scores[i])) == (r["err"], r["score"])
+        elif kind == "BF":
+            scores, errs = ctx.band_score(_band_tasks(pairs, offs, [r["args"] for r in sel]))
+            for i, r in enumerate(sel):
+                assert int(errs[i]) == r["err"]
+                if r["err"] == 0:
+                    assert int(scores[i]) == r["score"]
+        else:
+            t = _band_tasks(pairs, offs, [r["args"] for r in sel], [r["minscore"] for r in sel],
+                            [r["minscorlen"] for r in sel])
+            res, first, diff, errs, _ = ctx.band_align(t)
+            for i, r in enumerate(sel):
+                assert int(errs[i]) == r["err"]
+                assert _unpack(res, first, diff, i) == r["results"], i
