@@ -48,6 +48,9 @@ static ScoreProfile *g_prof;
 static AliBuffer *g_abuf;
 static AliRsltSet *g_rset;
 static SeqFastq *g_read, *g_ref, *g_tmp;
+/* reads as smalt.c:744 creates them (SEQTYP_UNKNOWN): the quality container only exists
+ * once qualities were loaded, so FASTA-like and FASTQ-like reads use separate objects */
+static SeqFastq *g_read_q, *g_read_nq;
 static HashTable *g_ht;
 static SeqSet *g_ss;
 static HashHitInfo *g_hhi[2];
@@ -95,6 +98,8 @@ int refh_init(int match, int mismatch, int gapopen, int gapext)
   g_read = seqFastqCreate(0, SEQTYP_FASTQ);
   g_ref = seqFastqCreate(0, SEQTYP_FASTQ);
   g_tmp = seqFastqCreate(0, SEQTYP_FASTQ);
+  g_read_q = seqFastqCreate(0, SEQTYP_UNKNOWN);
+  g_read_nq = seqFastqCreate(0, SEQTYP_UNKNOWN);
   if (!g_mtx || !g_prof || !g_abuf || !g_rset || !g_read || !g_ref || !g_tmp)
     return ERRCODE_NOMEM;
   return 0;
@@ -263,14 +268,15 @@ int refh_hitinfo(const unsigned char *read, int qlen, const char *qual,
   int errcode;
   HashHitInfo *hip;
   if (!g_ht) return ERRCODE_ASSERT;
+  SeqFastq *rd = qual ? g_read_q : g_read_nq;
   hip = g_hhi[is_reverse ? 1 : 0];
-  if ((errcode = load_seq(g_read, read, qlen, qual))) return errcode;
+  if ((errcode = load_seq(rd, read, qlen, qual))) return errcode;
   if (is_short)
     errcode = hashCollectHitInfoShort(hip, (unsigned char) is_reverse, maxhit_per_tuple,
-				      maxhit_total, (unsigned char) basq_thresh, g_read, g_ht);
+				      maxhit_total, (unsigned char) basq_thresh, rd, g_ht);
   else
     errcode = hashCollectHitInfo(hip, (unsigned char) is_reverse,
-				 (unsigned char) basq_thresh, 0, 0, g_read, g_ht);
+				 (unsigned char) basq_thresh, 0, 0, rd, g_ht);
   if (errcode) return errcode;
   *cover_deficit = hashCalcHitInfoCoverDeficit(hip);
   *nhit_tot = hashHitInfoCalcHitNumbers(hip, nhit_rank);
