@@ -154,6 +154,42 @@ int smb_band_align_batch(smb_ctx *ctx, const smb_band_task *tasks, int ntasks,
 			 uint8_t *diffstr, size_t max_diffbytes, size_t *ndiffbytes,
 			 int32_t *errs, uint64_t *ncells);
 
+/* ------------------------------ K1: seeds -------------------------------- */
+/* Hash index as stored in `.smi` (hashidx.c:1214-1255) and as hashTableRead
+ * leaves it in memory (posidx[nwords] is NOT read from the file and stays 0,
+ * hashidx.c:1334 - pass the arrays exactly as read).  typ 0 = perfect, 1 =
+ * with collisions.  Uploaded once per GPU. */
+int smb_index_upload(smb_ctx *ctx, int typ, int wordlen, int nskip, int nbits_key,
+		     int nbits_lo, uint32_t npos, uint32_t nwords,
+		     const uint32_t *idx, const uint32_t *pos,
+		     const uint32_t *wordidx, const uint32_t *posidx);
+
+/* Per read x strand seed table (HashHitInfo, hashhit.c:164-213) in SoA form. */
+typedef struct {
+  uint32_t n_seeds;       /* number of seeds (k-mers with 1..maxhit hits) */
+  uint32_t seed_rank;     /* hashhit.c:769-891 */
+  uint32_t cover_deficit; /* hashCalcHitInfoCoverDeficit */
+  uint32_t nhit_rank;     /* hashHitInfoCalcHitNumbers: hits of the seeds below seed_rank */
+  uint32_t nhit_tot;      /*   ... and of all seeds */
+  uint32_t nhit_all;      /* hashCalcHitInfoNumberOfHits(maxhit_per_tuple) */
+  uint32_t status;        /* HITINFO_STATUS_FLAGS */
+  int32_t err;            /* 0 or SMB_ERRCODE_SHORTSEQ */
+} smb_seed_info;
+
+/* Seeds of `nreads` reads (arena offsets/lengths), both strands: entry
+ * 2*r+s is read r, strand s (0 forward, 1 reverse).  Per-seed arrays are
+ * written at seed_off[2*r+s] = (read offset counted in bases over all previous
+ * reads + strand*read_len) - i.e. each strand of each read owns read_len slots:
+ *   seed_posidx/nhits/qoffs: SEED fields in discovery order,
+ *   sortkey/sidx: nhitqual_sortkeyp / sidxp after the reference's quicksort,
+ *   qmask: HITQUAL codes per read offset (hashhit.h:57-65).
+ * qual may be NULL (FASTA); basq_thresh as `smalt map -q`. */
+int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_len,
+		   int nreads, const uint8_t *qual, uint32_t maxhit_per_tuple,
+		   uint32_t maxhit_total, int basq_thresh,
+		   smb_seed_info *info, uint32_t *seed_posidx, uint32_t *seed_nhits,
+		   uint32_t *seed_qoffs, uint32_t *sortkey, uint32_t *sidx, uint8_t *qmask);
+
 #ifdef __cplusplus
 }
 #endif

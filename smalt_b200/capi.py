@@ -43,6 +43,9 @@ BAND_TASK_DTYPE = np.dtype([("read_off", "<u8"), ("ref_off", "<u8"), ("read_len"
                             ("r_edge", "<i4"), ("p_left", "<i4"), ("p_right", "<i4"),
                             ("u_left", "<i4"), ("u_right", "<i4"), ("minscore", "<i4"),
                             ("minscorlen", "<i4"), ("_pad", "<u4")])
+SEED_INFO_DTYPE = np.dtype([("n_seeds", "<u4"), ("seed_rank", "<u4"), ("cover_deficit", "<u4"),
+                            ("nhit_rank", "<u4"), ("nhit_tot", "<u4"), ("nhit_all", "<u4"),
+                            ("status", "<u4"), ("err", "<i4")])
 ALI_RESULT_DTYPE = np.dtype([("score", "<i4"), ("qs", "<i4"), ("qe", "<i4"), ("rs", "<i4"),
                              ("re", "<i4"), ("diff_off", "<u4"), ("diff_len", "<u4"),
                              ("task", "<u4")])
@@ -87,6 +90,10 @@ def load_library():
     lib.smb_band_align_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
                                          C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.c_size_t,
                                          C.POINTER(C.c_size_t), C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.smb_index_upload.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
+                                     C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.smb_seed_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32,
+                                   C.c_uint32, C.c_int] + [C.c_void_p] * 7
     _lib = lib
     return lib
 
@@ -143,6 +150,37 @@ class Context:
         so = np.ascontiguousarray(seq_offs, np.uint64)
         self._check(self.lib.smb_refseq_upload(self._h, _vp(words), words.size, int(nbases), _vp(so),
                                                len(so) - 1))
+
+    def index_upload(self, ix):
+        """ix: dict as returned by smifile.read_smi / indexer.as_loaded(build_index(...))"""
+        z = np.zeros(1, np.uint32)
+        widx = ix["wordidx"] if ix["wordidx"] is not None else z
+        pidx = ix["posidx"] if ix["posidx"] is not None else z
+        self._check(self.lib.smb_index_upload(
+            self._h, ix["typ"], ix["wordlen"], ix["nskip"], ix["nbits_key"], ix["nbits_lo"], ix["npos"],
+            ix["nwords"], _vp(np.ascontiguousarray(ix["idx"], np.uint32)),
+            _vp(np.ascontiguousarray(ix["pos"], np.uint32)), _vp(np.ascontiguousarray(widx, np.uint32)),
+            _vp(np.ascontiguousarray(pidx, np.uint32))))
+
+    def seed_batch(self, read_off, read_len, qual=None, maxhit_per_tuple=10000, maxhit_total=16384,
+                   basq_thresh=0, full=True):
+        """-> (info[2*n] SEED_INFO_DTYPE, tables dict or None).  Table arrays have 2*sum(read_len)
+        slots; read r strand s starts at 2*sum(read_len[:r]) + s*read_len[r]."""
+        read_off = np.ascontiguousarray(read_off, np.uint64)
+        read_len = np.ascontiguousarray(read_len, np.uint32)
+        n = len(read_len)
+        nslots = 2 * int(read_len.astype(np.int64).sum())
+        info = np.zeros(2 * n, SEED_INFO_DTYPE)
+        tabs = None
+        ptrs = [None] * 6
+        if full:
+            tabs = {k: np.zeros(nslots, np.uint32) for k in ("posidx", "nhits", "qoffs", "sortkey", "sidx")}
+            tabs["qmask"] = np.zeros(nslots, np.uint8)
+            ptrs = [_vp(tabs[k]) for k in ("posidx", "nhits", "qoffs", "sortkey", "sidx", "qmask")]
+        q = None if qual is None else _vp(np.ascontiguousarray(qual, np.uint8))
+        self._check(self.lib.smb_seed_batch(self._h, _vp(read_off), _vp(read_len), n, q, maxhit_per_tuple,
+                                            maxhit_total, basq_thresh, _vp(info), *ptrs))
+        return info, tabs
 
     def sw_score(self, tasks):
         tasks = np.ascontiguousarray(tasks, SW_TASK_DTYPE)

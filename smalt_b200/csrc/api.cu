@@ -43,6 +43,12 @@ struct smb_ctx {
   Scoring sc;
   SeqSrc src{nullptr, nullptr, 0};
   DevBuf arena, packed, tasks, out_a, out_b, scratch, dirs, diff, offs;
+  DevBuf index, qualbuf, seed_meta, seed_u32, seed_u8;
+  Index ix{};
+  bool have_index = false;
+  // device-resident seed tables of the last smb_seed_batch (consumed by smb_hits_batch)
+  int seed_nreads = 0;
+  uint64_t seed_slots = 0;
   size_t arena_bytes = 0;
   std::vector<uint64_t> seq_offs;
   float last_ms = 0.f;
@@ -115,7 +121,8 @@ void smb_ctx_destroy(smb_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf *bufs[] = {&ctx->arena, &ctx->packed, &ctx->tasks, &ctx->out_a, &ctx->out_b,
-                    &ctx->scratch, &ctx->dirs, &ctx->diff, &ctx->offs};
+                    &ctx->scratch, &ctx->dirs, &ctx->diff, &ctx->offs, &ctx->index, &ctx->qualbuf,
+                    &ctx->seed_meta, &ctx->seed_u32, &ctx->seed_u8};
   for (DevBuf *b : bufs) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -419,6 +426,114 @@ int smb_band_align_batch(smb_ctx *ctx, const smb_band_task *tasks, int ntasks, s
     nd += o.diff.size();
   }
   first_result[ntasks] = (uint32_t)nr;
+  return SMB_OK;
+}
+
+// ------------------------------------ K1 ------------------------------------------
+
+int smb_index_upload(smb_ctx *ctx, int typ, int wordlen, int nskip, int nbits_key, int nbits_lo,
+                     uint32_t npos, uint32_t nwords, const uint32_t *idx, const uint32_t *pos,
+                     const uint32_t *wordidx, const uint32_t *posidx) {
+  if (!ctx || !idx || (npos && !pos) || (typ != 0 && (!wordidx || !posidx))) return SMB_ERR_ARG;
+  if (wordlen < 1 || wordlen > 31 || nskip < 1 || nskip > 32 || nbits_key > 32 || (typ != 0 && nbits_lo >= nbits_key))
+    return fail(ctx, SMB_ERR_ARG, "index parameters out of range (k=%d nskip=%d)", wordlen, nskip);
+  cudaSetDevice(ctx->device);
+  Index ix{};
+  ix.typ = typ; ix.wordlen = wordlen; ix.nskip = nskip; ix.nbits_key = nbits_key; ix.nbits_lo = nbits_lo;
+  ix.npos = npos; ix.nwords = nwords;
+  ix.wordmask = (wordlen >= 32) ? ~0ull : ((1ull << (2 * wordlen)) - 1ull);   // hashTableCreate, hashidx.c:781-787
+  if (typ == 0) {
+    ix.nkeys = 1u << (2 * wordlen);
+  } else {
+    ix.nkeys = 1u << nbits_key;
+    ix.wordmask_lo = (1ull << nbits_lo) - 1ull;
+    ix.wordmask_hi = ix.wordmask & ~ix.wordmask_lo;
+    ix.keymod = 1u << (nbits_key - nbits_lo);
+  }
+  const size_t n_idx = (size_t)ix.nkeys + 1, n_pos = npos, n_w = typ ? (size_t)nwords + 1 : 0;
+  auto al = [](size_t n) { return (n + 63) & ~(size_t)63; };
+  const size_t total = al(n_idx) + al(n_pos + 1) + 2 * al(n_w + 1);
+  CU(ctx->index.ensure(total * sizeof(uint32_t)));
+  uint32_t *base = ctx->index.as<uint32_t>();
+  uint32_t *d_idx = base, *d_pos = d_idx + al(n_idx), *d_w = d_pos + al(n_pos + 1), *d_p = d_w + al(n_w + 1);
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(d_idx, idx, n_idx * 4, cudaMemcpyHostToDevice, st));
+  if (n_pos) CU(cudaMemcpyAsync(d_pos, pos, n_pos * 4, cudaMemcpyHostToDevice, st));
+  if (typ) {
+    CU(cudaMemcpyAsync(d_w, wordidx, n_w * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_p, posidx, n_w * 4, cudaMemcpyHostToDevice, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  ix.idx = d_idx; ix.pos = d_pos; ix.wordidx = d_w; ix.posidx = d_p;
+  ctx->ix = ix;
+  ctx->have_index = true;
+  return SMB_OK;
+}
+
+int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_len, int nreads,
+                   const uint8_t *qual, uint32_t maxhit_per_tuple, uint32_t maxhit_total, int basq_thresh,
+                   smb_seed_info *info, uint32_t *seed_posidx, uint32_t *seed_nhits, uint32_t *seed_qoffs,
+                   uint32_t *sortkey, uint32_t *sidx, uint8_t *qmask) {
+  if (!ctx || nreads < 0 || (nreads && (!read_off || !read_len || !info))) return SMB_ERR_ARG;
+  ctx->last_ms = 0.f;
+  ctx->last_launches = 0;
+  if (!nreads) return SMB_OK;
+  if (!ctx->have_index) return fail(ctx, SMB_ERR_STATE, "smb_index_upload() first");
+  if (!ctx->src.arena) return fail(ctx, SMB_ERR_STATE, "smb_arena_upload() first");
+  if (basq_thresh < 0 || basq_thresh + 0x21 > 255) return fail(ctx, 67 /* ERRCODE_QUALVAL */, "quality threshold");
+  std::vector<uint64_t> slot((size_t)nreads + 1, 0);
+  for (int i = 0; i < nreads; ++i) {
+    if (read_off[i] + read_len[i] > ctx->arena_bytes)
+      return fail(ctx, SMB_ERR_ARG, "read %d outside the arena", i);
+    slot[(size_t)i + 1] = slot[(size_t)i] + 2ull * read_len[i];
+  }
+  const uint64_t nslots = slot[(size_t)nreads];
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const size_t meta_bytes = (size_t)nreads * (8 + 4 + 8) + (size_t)2 * nreads * sizeof(smb_seed_info) + 256;
+  CU(ctx->seed_meta.ensure(meta_bytes));
+  CU(ctx->seed_u32.ensure((size_t)(nslots + 64) * 6 * sizeof(uint32_t)));
+  CU(ctx->seed_u8.ensure((size_t)(nslots + 64) * 2));
+  char *mb = ctx->seed_meta.as<char>();
+  uint64_t *d_off = (uint64_t *)mb;
+  uint64_t *d_slot = d_off + nreads;
+  smb_seed_info *d_info = (smb_seed_info *)(d_slot + nreads);
+  uint32_t *d_len = (uint32_t *)(d_info + 2 * (size_t)nreads);
+  CU(cudaMemcpyAsync(d_off, read_off, (size_t)nreads * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_slot, slot.data(), (size_t)nreads * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_len, read_len, (size_t)nreads * 4, cudaMemcpyHostToDevice, st));
+  const uint8_t *d_qual = nullptr;
+  if (qual) {
+    CU(ctx->qualbuf.ensure(ctx->arena_bytes + 16));
+    CU(cudaMemcpyAsync(ctx->qualbuf.p, qual, ctx->arena_bytes, cudaMemcpyHostToDevice, st));
+    d_qual = ctx->qualbuf.as<uint8_t>();
+  }
+  const size_t S = (size_t)nslots + 64;
+  uint32_t *u = ctx->seed_u32.as<uint32_t>();
+  uint8_t *b = ctx->seed_u8.as<uint8_t>();
+  SeedArgs a{};
+  a.read_off = d_off; a.read_len = d_len; a.slot_off = d_slot; a.qual = d_qual; a.nreads = nreads;
+  a.maxhit_per_tuple = maxhit_per_tuple; a.maxhit_total = maxhit_total; a.basq_thresh = basq_thresh;
+  a.is_short = 1;
+  a.info = d_info;
+  a.posidx = u; a.nhits = u + S; a.qoffs = u + 2 * S; a.sortkey = u + 3 * S; a.sidx = u + 4 * S; a.frame = u + 5 * S;
+  a.qmask = b; a.qbuf = b + S;
+  int nl = 0;
+  CU(cudaEventRecord(ctx->ev0, st));
+  CU(launch_seed(ctx->ix, ctx->src.arena, a, st, &nl));
+  CU(cudaEventRecord(ctx->ev1, st));
+  CU(cudaMemcpyAsync(info, d_info, (size_t)2 * nreads * sizeof(smb_seed_info), cudaMemcpyDeviceToHost, st));
+  struct { uint32_t *h; uint32_t *d; } cp[] = {{seed_posidx, a.posidx}, {seed_nhits, a.nhits}, {seed_qoffs, a.qoffs},
+                                                {sortkey, a.sortkey}, {sidx, a.sidx}};
+  for (auto &c : cp)
+    if (c.h) CU(cudaMemcpyAsync(c.h, c.d, (size_t)nslots * 4, cudaMemcpyDeviceToHost, st));
+  if (qmask) CU(cudaMemcpyAsync(qmask, a.qmask, (size_t)nslots, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+  ctx->seed_nreads = nreads;
+  ctx->seed_slots = nslots;
+  ctx->last_launches = nl;
+  ctx->total_launches += nl;
   return SMB_OK;
 }
 

@@ -68,4 +68,28 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
                         const uint64_t *d_diff_off, const uint32_t *d_diff_cap,
                         int sm_count, cudaStream_t st, int *nlaunch);
 
+// ---- K1 ----
+struct Index {
+  int typ, wordlen, nskip, nbits_key, nbits_lo;
+  uint32_t nkeys, npos, nwords, keymod;
+  uint64_t wordmask, wordmask_lo, wordmask_hi;
+  const uint32_t *idx, *pos, *wordidx, *posidx;
+};
+
+struct SeedArgs {
+  const uint64_t *read_off;   // [nreads] arena offsets
+  const uint32_t *read_len;   // [nreads]
+  const uint64_t *slot_off;   // [nreads] first slot of the read (forward strand); reverse at +read_len
+  const uint8_t *qual;        // arena-parallel quality bytes or nullptr
+  int nreads;
+  uint32_t maxhit_per_tuple, maxhit_total;
+  int basq_thresh, is_short;
+  smb_seed_info *info;        // [2*nreads]
+  uint32_t *posidx, *nhits, *qoffs, *sortkey, *sidx, *frame;  // slot arrays
+  uint8_t *qmask, *qbuf;
+};
+
+cudaError_t launch_seed(const Index &ix, const uint8_t *arena, const SeedArgs &a, cudaStream_t st,
+                        int *nlaunch);
+
 }  // namespace smb
