@@ -190,6 +190,31 @@ int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_
 		   smb_seed_info *info, uint32_t *seed_posidx, uint32_t *seed_nhits,
 		   uint32_t *seed_qoffs, uint32_t *sortkey, uint32_t *sidx, uint8_t *qmask);
 
+/* One hit list to build from the seed tables left on the device by the last
+ * smb_seed_batch: the hits of read `read`, strand `strand`, that fall into the
+ * reference segment [lo, hi) given as base offsets in the concatenated set -
+ * what collectHits (rmap.c:283-318) asks hashCollectHitsForSegment for with
+ * lo = soffs[s], hi = soffs[s+1], nhit_max = ktuple_maxhit, use_short = 1. */
+typedef struct {
+  uint64_t lo, hi;
+  uint32_t read;
+  uint32_t nhit_max;
+  uint8_t strand;
+  uint8_t use_short;
+  uint8_t reserved[6];
+} smb_hit_req;
+
+/* Builds and sorts the requested hit lists (HashHitList.sqdat, hashhit.c:215-236:
+ * shift << 31 | read offset, ascending).  list_first[i]..list_first[i+1]
+ * delimit list i in sqdat (list_first has nreq+1 entries).  nhits_alloc is the
+ * reference's allocation bound of the hit list (16384-blocks >= qlen*ln(qlen)*32,
+ * hashhit.c:1262-1296); 0 = derive it from the longest read of the batch.
+ * Returns SMB_ERR_CAPACITY with *nhits_total = required size if max_hits is
+ * too small. */
+int smb_hits_batch(smb_ctx *ctx, const smb_hit_req *req, int nreq, uint32_t nhits_alloc,
+		   uint64_t *sqdat, size_t max_hits, size_t *nhits_total,
+		   uint64_t *list_first, int32_t *errs);
+
 #ifdef __cplusplus
 }
 #endif

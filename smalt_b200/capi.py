@@ -46,6 +46,8 @@ BAND_TASK_DTYPE = np.dtype([("read_off", "<u8"), ("ref_off", "<u8"), ("read_len"
 SEED_INFO_DTYPE = np.dtype([("n_seeds", "<u4"), ("seed_rank", "<u4"), ("cover_deficit", "<u4"),
                             ("nhit_rank", "<u4"), ("nhit_tot", "<u4"), ("nhit_all", "<u4"),
                             ("status", "<u4"), ("err", "<i4")])
+HIT_REQ_DTYPE = np.dtype([("lo", "<u8"), ("hi", "<u8"), ("read", "<u4"), ("nhit_max", "<u4"),
+                          ("strand", "u1"), ("use_short", "u1"), ("reserved", "u1", (6,))])
 ALI_RESULT_DTYPE = np.dtype([("score", "<i4"), ("qs", "<i4"), ("qe", "<i4"), ("rs", "<i4"),
                              ("re", "<i4"), ("diff_off", "<u4"), ("diff_len", "<u4"),
                              ("task", "<u4")])
@@ -94,6 +96,8 @@ def load_library():
                                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.smb_seed_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32,
                                    C.c_uint32, C.c_int] + [C.c_void_p] * 7
+    lib.smb_hits_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_size_t,
+                                   C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 
@@ -181,6 +185,25 @@ class Context:
         self._check(self.lib.smb_seed_batch(self._h, _vp(read_off), _vp(read_len), n, q, maxhit_per_tuple,
                                             maxhit_total, basq_thresh, _vp(info), *ptrs))
         return info, tabs
+
+    def hits_batch(self, req, nhits_alloc=0, max_hits=None):
+        """-> (sqdat uint64, list_first[nreq+1], errs) for HIT_REQ_DTYPE requests"""
+        req = np.ascontiguousarray(req, HIT_REQ_DTYPE)
+        n = len(req)
+        if max_hits is None:
+            max_hits = 64 * n + 4096
+        while True:
+            sq = np.zeros(max_hits, np.uint64)
+            first = np.zeros(n + 1, np.uint64)
+            errs = np.zeros(n, np.int32)
+            tot = C.c_size_t(0)
+            rc = self.lib.smb_hits_batch(self._h, _vp(req), n, nhits_alloc, _vp(sq), max_hits, C.byref(tot),
+                                         _vp(first), _vp(errs))
+            if rc == SMB_ERR_CAPACITY and tot.value > max_hits:
+                max_hits = tot.value
+                continue
+            self._check(rc)
+            return sq[:tot.value], first, errs
 
     def sw_score(self, tasks):
         tasks = np.ascontiguousarray(tasks, SW_TASK_DTYPE)

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cmath>
 #include <new>
 #include <string>
 #include <vector>
@@ -48,6 +49,9 @@ struct smb_ctx {
   bool have_index = false;
   // device-resident seed tables of the last smb_seed_batch (consumed by smb_hits_batch)
   int seed_nreads = 0;
+  SeedArgs seed_args{};
+  uint32_t seed_maxlen = 0;
+  DevBuf hit_meta, hit_data;
   uint64_t seed_slots = 0;
   size_t arena_bytes = 0;
   std::vector<uint64_t> seq_offs;
@@ -122,7 +126,7 @@ void smb_ctx_destroy(smb_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf *bufs[] = {&ctx->arena, &ctx->packed, &ctx->tasks, &ctx->out_a, &ctx->out_b,
                     &ctx->scratch, &ctx->dirs, &ctx->diff, &ctx->offs, &ctx->index, &ctx->qualbuf,
-                    &ctx->seed_meta, &ctx->seed_u32, &ctx->seed_u8};
+                    &ctx->seed_meta, &ctx->seed_u32, &ctx->seed_u8, &ctx->hit_meta, &ctx->hit_data};
   for (DevBuf *b : bufs) b->release();
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -531,7 +535,82 @@ int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_
   CU(cudaStreamSynchronize(st));
   CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
   ctx->seed_nreads = nreads;
+  ctx->seed_args = a;
+  ctx->seed_maxlen = 0;
+  for (int i = 0; i < nreads; ++i) if (read_len[i] > ctx->seed_maxlen) ctx->seed_maxlen = read_len[i];
   ctx->seed_slots = nslots;
+  ctx->last_launches = nl;
+  ctx->total_launches += nl;
+  return SMB_OK;
+}
+
+int smb_hits_batch(smb_ctx *ctx, const smb_hit_req *req, int nreq, uint32_t nhits_alloc, uint64_t *sqdat,
+                   size_t max_hits, size_t *nhits_total, uint64_t *list_first, int32_t *errs) {
+  if (!ctx || nreq < 0 || !nhits_total || (nreq && (!req || !list_first || !errs))) return SMB_ERR_ARG;
+  ctx->last_ms = 0.f;
+  ctx->last_launches = 0;
+  *nhits_total = 0;
+  if (list_first) list_first[0] = 0;
+  if (!nreq) return SMB_OK;
+  if (!ctx->seed_nreads) return fail(ctx, SMB_ERR_STATE, "smb_seed_batch() first");
+  for (int i = 0; i < nreq; ++i)
+    if (req[i].read >= (uint32_t)ctx->seed_nreads || req[i].strand > 1)
+      return fail(ctx, SMB_ERR_ARG, "request %d: read %u / strand %u out of range", i, req[i].read, req[i].strand);
+  if (!nhits_alloc) {  // initHitList / reallocHitList (hashhit.c:1262-1296, :1232-1248), starting from
+                       // hashCreateHitList(HASH_MAXNHITS = 16384) (rmap.c:50, :1123)
+    const double ql = (double)ctx->seed_maxlen;
+    double target = ql > 1 ? ql * log(ql) * 32.0 : 0.0;
+    if (target > 2147483647.0) target = 2147483647.0;
+    if (target < 8192.0) target = 8192.0;
+    size_t t = (size_t)target;
+    nhits_alloc = 16384;
+    if (t > nhits_alloc) nhits_alloc = (uint32_t)((t + 16383) / 16384 * 16384);
+  }
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const size_t n = (size_t)nreq;
+  CU(ctx->hit_meta.ensure(n * (sizeof(smb_hit_req) + 4 + 4 + 4 + 8) + 256));
+  char *mb = ctx->hit_meta.as<char>();
+  smb_hit_req *d_req = (smb_hit_req *)mb;
+  uint64_t *d_off = (uint64_t *)(d_req + n);
+  uint32_t *d_count = (uint32_t *)(d_off + n);
+  uint32_t *d_used = d_count + n;
+  int32_t *d_errs = (int32_t *)(d_used + n);
+  CU(cudaMemcpyAsync(d_req, req, n * sizeof(smb_hit_req), cudaMemcpyHostToDevice, st));
+  HitArgs ha{};
+  ha.seed = ctx->seed_args; ha.req = d_req; ha.nreq = nreq; ha.nhits_alloc = nhits_alloc;
+  ha.count = d_count; ha.maxhit_used = d_used; ha.errs = d_errs; ha.offset = d_off; ha.sqdat = nullptr;
+  int nl = 0;
+  float ms0 = 0.f, ms1 = 0.f;
+  CU(cudaEventRecord(ctx->ev0, st));
+  CU(launch_hits(ctx->ix, ha, false, st, &nl));
+  CU(cudaEventRecord(ctx->ev1, st));
+  std::vector<uint32_t> count(n);
+  CU(cudaMemcpyAsync(count.data(), d_count, n * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(errs, d_errs, n * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaEventElapsedTime(&ms0, ctx->ev0, ctx->ev1));
+  std::vector<uint64_t> off(n + 1, 0);
+  for (size_t i = 0; i < n; ++i) off[i + 1] = off[i] + count[i];
+  const uint64_t total = off[n];
+  for (size_t i = 0; i <= n; ++i) list_first[i] = off[i];
+  *nhits_total = (size_t)total;
+  if (total > max_hits || (total && !sqdat)) {
+    ctx->last_ms = ms0;
+    ctx->last_launches = nl;
+    ctx->total_launches += nl;
+    return fail(ctx, SMB_ERR_CAPACITY, "need room for %llu hits", (unsigned long long)total);
+  }
+  CU(ctx->hit_data.ensure((size_t)(total + 1) * 8));
+  CU(cudaMemcpyAsync(d_off, off.data(), n * 8, cudaMemcpyHostToDevice, st));
+  ha.sqdat = ctx->hit_data.as<uint64_t>();
+  CU(cudaEventRecord(ctx->ev0, st));
+  CU(launch_hits(ctx->ix, ha, true, st, &nl));
+  CU(cudaEventRecord(ctx->ev1, st));
+  if (total) CU(cudaMemcpyAsync(sqdat, ha.sqdat, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaEventElapsedTime(&ms1, ctx->ev0, ctx->ev1));
+  ctx->last_ms = ms0 + ms1;
   ctx->last_launches = nl;
   ctx->total_launches += nl;
   return SMB_OK;

@@ -106,7 +106,7 @@ __device__ __forceinline__ void band_dp(const Scoring &sc, const Band &b, const 
         ++ci;
       }
     }
-    ncell += (unsigned long long)(jlen - jstart);
+    if (jlen > jstart) ncell += (unsigned long long)(jlen - jstart);
     if (dstart > 0) {
       currH = 0;
       if (ALIGN) ci += --dstart;  // the fast variant never releases the clipped start (:1213-1218)

@@ -89,6 +89,19 @@ struct SeedArgs {
   uint8_t *qmask, *qbuf;
 };
 
+struct HitArgs {
+  SeedArgs seed;              // the device-resident seed tables of the last smb_seed_batch
+  const smb_hit_req *req;     // [nreq]
+  int nreq;
+  uint32_t nhits_alloc;       // HashHitList.nhits_alloc (hashhit.c:1497)
+  uint32_t *count;            // [nreq] hits per list
+  uint32_t *maxhit_used;      // [nreq] per-seed cut-off that finally succeeded
+  int32_t *errs;              // [nreq]
+  const uint64_t *offset;     // [nreq] start of each list in sqdat (FILL pass)
+  uint64_t *sqdat;
+};
+cudaError_t launch_hits(const Index &ix, const HitArgs &a, bool fill, cudaStream_t st, int *nlaunch);
+
 cudaError_t launch_seed(const Index &ix, const uint8_t *arena, const SeedArgs &a, cudaStream_t st,
                         int *nlaunch);
 

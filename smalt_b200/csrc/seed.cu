@@ -289,3 +289,175 @@ cudaError_t launch_seed(const Index &ix, const uint8_t *arena, const SeedArgs &a
 }
 
 }  // namespace smb
+
+// ------------------------------------------------------------------------------------
+// Hit lists: fillHitListFromHitInfoSegment (hashhit.c:1416-1546, unfiltered branch) with the
+// retry loop of hashCollectHitsForSegment (:1739-1741), and hashCollectHitsUsingCutoff
+// (:1593-1689).  Two passes: COUNT (sizes every list, resolves the halving of the per-seed
+// cut-off) and FILL (writes the packed hits and sorts them ascending).
+// The reference's resume pointer SEED.cix only accelerates the scan for the first position
+// >= lo (positions of a word are ascending); a binary search gives the same element.
+// ------------------------------------------------------------------------------------
+namespace smb {
+
+__device__ __forceinline__ uint32_t lower_bound_pos(const uint32_t *p, uint32_t n, uint32_t v) {
+  uint32_t a = 0, b = n;
+  while (a < b) {
+    const uint32_t m = (a + b) >> 1;
+    if (__ldg(p + m) < v) a = m + 1; else b = m;
+  }
+  return a;
+}
+
+__device__ __forceinline__ uint64_t pack_hit(bool is_reverse, uint32_t pos, uint32_t q, uint32_t nskip) {
+  // SET_NEXT_SHIFT (hashhit.c:283-288), HASHHIT_HALFBIT = 31
+  if (is_reverse) return (((uint64_t)pos + q / nskip) << 31) + q;
+  return ((((uint64_t)pos | (1ull << 32)) - q / nskip) << 31) + q;
+}
+
+// one pass over the seeds of a request; FILL writes hits, otherwise only counts
+template <bool FILL>
+__device__ int hits_segment_pass(const Index &ix, const HitArgs &a, const smb_hit_req &rq, uint64_t slot,
+                                 uint32_t n_seeds_tot, uint32_t seed_rank, uint32_t maxhit,
+                                 uint32_t pos_lo, uint32_t pos_hi, uint64_t *out, uint32_t &total) {
+  const uint32_t *posidx = a.seed.posidx + slot, *qoffs = a.seed.qoffs + slot;
+  const uint32_t *sortkey = a.seed.sortkey + slot, *sidx = a.seed.sidx + slot;
+  uint8_t *qmask = a.seed.qmask + slot;
+  const bool use_short = rq.use_short != 0;
+  const uint32_t n_seeds = (use_short && seed_rank > 0) ? seed_rank : n_seeds_tot;
+  const bool is_reverse = rq.strand != 0;
+  uint32_t nh_tot = 0;
+  for (uint32_t n = 0; n < n_seeds; ++n) {
+    const uint32_t sd = use_short ? sidx[n] : n;
+    if (maxhit > 0 && sortkey[n] > maxhit) {
+      if (FILL) qmask[qoffs[sd]] = HQ_MULTIHIT;
+      continue;
+    }
+    const uint32_t *posp;
+    const uint32_t nhits = fetch_positions(ix, posidx[sd], posp);
+    if (!posp || nhits == 0) continue;
+    const uint32_t first = lower_bound_pos(posp, nhits, pos_lo);
+    if (first >= nhits) continue;  // all positions below the segment
+    const uint32_t nh = nhits - first;
+    if (nh_tot + nh > a.nhits_alloc) {
+      if (maxhit > 0) { total = nh_tot; return SMB_ERRCODE_ALLOCBOUNDARY; }
+      if (FILL) qmask[qoffs[sd]] = HQ_MULTIHIT;
+      continue;
+    }
+    const uint32_t q = qoffs[sd];
+    uint32_t i = 0;
+    for (; i < nh; ++i) {
+      const uint32_t p = __ldg(posp + first + i);
+      if (p >= pos_hi) break;
+      if (FILL) out[nh_tot + i] = pack_hit(is_reverse, p, q, (uint32_t)ix.nskip);
+    }
+    nh_tot += i;
+  }
+  total = nh_tot;
+  return 0;
+}
+
+// in-place ascending sort of one list by a single thread (keys are unique)
+__device__ void sort_u64(uint64_t *a, int n) {
+  if (n < 2) return;
+  if (n <= 24) {
+    for (int j = 1; j < n; ++j) {
+      const uint64_t k = a[j];
+      int i = j - 1;
+      for (; i >= 0 && a[i] > k; --i) a[i + 1] = a[i];
+      a[i + 1] = k;
+    }
+    return;
+  }
+  // heapsort: O(n log n) worst case, no stack
+  for (int start = n / 2 - 1; start >= 0; --start) {
+    int root = start;
+    const uint64_t v = a[root];
+    for (;;) {
+      int child = 2 * root + 1;
+      if (child >= n) break;
+      if (child + 1 < n && a[child + 1] > a[child]) ++child;
+      if (a[child] <= v) break;
+      a[root] = a[child];
+      root = child;
+    }
+    a[root] = v;
+  }
+  for (int end = n - 1; end > 0; --end) {
+    const uint64_t v = a[end];
+    a[end] = a[0];
+    int root = 0;
+    for (;;) {
+      int child = 2 * root + 1;
+      if (child >= end) break;
+      if (child + 1 < end && a[child + 1] > a[child]) ++child;
+      if (a[child] <= v) break;
+      a[root] = a[child];
+      root = child;
+    }
+    a[root] = v;
+  }
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) hits_kernel(const Index ix, const HitArgs a) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.nreq) return;
+  const smb_hit_req rq = a.req[g];
+  const uint32_t rd = rq.read;
+  const uint32_t qlen = a.seed.read_len[rd];
+  const uint64_t slot = a.seed.slot_off[rd] + (rq.strand ? qlen : 0u);
+  const smb_seed_info inf = a.seed.info[2 * rd + (rq.strand ? 1 : 0)];
+  uint64_t lo = rq.lo / (uint64_t)ix.nskip, hi = rq.hi / (uint64_t)ix.nskip;
+  if (inf.err || lo > 0xFFFFFFFFull) {
+    if (!FILL) { a.count[g] = 0; a.maxhit_used[g] = 0; a.errs[g] = inf.err ? inf.err : SMB_ERRCODE_ARGRANGE; }
+    return;
+  }
+  if (hi > 0xFFFFFFFFull) hi = 0xFFFFFFFFull;
+  if (!FILL) {
+    uint32_t maxhit = rq.nhit_max, total = 0, used = 0;
+    int err;
+    do {  // hashCollectHitsForSegment retry loop (hashhit.c:1730-1741)
+      used = maxhit;
+      err = hits_segment_pass<false>(ix, a, rq, slot, inf.n_seeds, inf.seed_rank, maxhit, (uint32_t)lo,
+                                     (uint32_t)hi, nullptr, total);
+      maxhit /= 2;
+    } while (err == SMB_ERRCODE_ALLOCBOUNDARY && maxhit > 16u);  // MINHIT_PER_TUPLE
+    // if the last attempt still overflowed the reference keeps what that attempt collected
+    // before the overflow; reproduce by counting that partial pass
+    if (err == SMB_ERRCODE_ALLOCBOUNDARY) {
+      a.errs[g] = SMB_ERRCODE_ALLOCBOUNDARY;
+    } else {
+      a.errs[g] = 0;
+    }
+    a.count[g] = total;
+    a.maxhit_used[g] = used;
+  } else {
+    uint64_t *out = a.sqdat + a.offset[g];
+    uint32_t total = 0;
+    // earlier (failed) attempts of the retry loop marked MULTIHIT seeds in the read's qmask
+    // as a side effect; replay them so the mask ends up identical
+    uint32_t maxhit = rq.nhit_max;
+    const uint32_t used = a.maxhit_used[g];
+    while (maxhit != used && maxhit > 16u) {
+      uint32_t t2 = 0;
+      hits_segment_pass<true>(ix, a, rq, slot, inf.n_seeds, inf.seed_rank, maxhit, (uint32_t)lo, (uint32_t)hi,
+                              out, t2);
+      maxhit /= 2;
+    }
+    hits_segment_pass<true>(ix, a, rq, slot, inf.n_seeds, inf.seed_rank, used, (uint32_t)lo, (uint32_t)hi, out,
+                            total);
+    sort_u64(out, (int)a.count[g]);
+  }
+}
+
+cudaError_t launch_hits(const Index &ix, const HitArgs &a, bool fill, cudaStream_t st, int *nlaunch) {
+  if (a.nreq <= 0) return cudaSuccess;
+  const int grid = (a.nreq + 127) / 128;
+  if (fill) hits_kernel<true><<<grid, 128, 0, st>>>(ix, a);
+  else hits_kernel<false><<<grid, 128, 0, st>>>(ix, a);
+  ++*nlaunch;
+  return cudaGetLastError();
+}
+
+}  // namespace smb

@@ -58,3 +58,69 @@ def test_seed_batch_vs_oracle(ctx, k, nskip, lens):
                         assert np.array_equal(tabs[key][slot:slot + n], want[key]), (key, r, s)
                     assert np.array_equal(tabs["qmask"][slot:slot + len(rd)], want["qmask"]), (r, s)
                 slot += len(rd)
+
+
+def _repeat_genome(rng):
+    """300 diverged copies of a 400 bp unit: reads from it collect > 32768 hits, which
+    exercises the ALLOCBOUNDARY retry of hashCollectHitsForSegment (hashhit.c:1739-1741)."""
+    from seqgen import mutate
+    unit = random_seq(rng, 400)
+    parts = []
+    for _ in range(300):
+        parts.append(mutate(rng, unit, p_sub=0.01, p_ins=0, p_del=0)[:400])
+        parts.append(random_seq(rng, 50))
+    return [np.concatenate(parts), random_seq(rng, 20000)], unit
+
+
+@pytest.mark.parametrize("k,nskip,kind", [(13, 6, "plain"), (11, 3, "multi"), (11, 3, "repeat")])
+def test_hits_batch_vs_oracle(ctx, k, nskip, kind):
+    from smalt_b200.capi import HIT_REQ_DTYPE, pack_sequences
+    rng = np.random.default_rng(2000 + k + len(kind))
+    unit = None
+    if kind == "plain":
+        seqs = make_genome(rng, [150000])
+    elif kind == "multi":
+        seqs = make_genome(rng, [30011, 20007, 999])
+    else:
+        seqs, unit = _repeat_genome(rng)
+    ix = indexer.as_loaded(indexer.build_index(seqs, k, nskip))
+    orc = Oracle()
+    oix = orc.make_index(ix)
+    ctx.index_upload(ix)
+    reads = [sample_read(rng, seqs, 150) for _ in range(150)]
+    if unit is not None:
+        reads += [np.ascontiguousarray(unit[i:i + 150]) for i in range(0, 200, 20)]
+    arena, offs = pack_sequences(reads)
+    lens_r = np.array([len(r) for r in reads], np.uint32)
+    ctx.arena_upload(arena)
+    soffs = np.concatenate([[0], np.cumsum([len(x) for x in seqs])])
+    for nhit_max in (10000, 40, 0):
+        info, tabs = ctx.seed_batch(offs[:-1], lens_r, None, 10000, 16384, 0)
+        req = np.zeros(len(reads) * 2 * len(seqs), HIT_REQ_DTYPE)
+        n = 0
+        for r in range(len(reads)):
+            for s in (0, 1):
+                for sx in range(len(seqs)):
+                    req[n]["lo"], req[n]["hi"] = soffs[sx], soffs[sx + 1]
+                    req[n]["read"], req[n]["nhit_max"], req[n]["strand"], req[n]["use_short"] = r, nhit_max, s, 1
+                    n += 1
+        sq, first, errs = ctx.hits_batch(req, nhits_alloc=32768)
+        assert ctx.last_kernel_launches == 2
+        n = 0
+        big = 0
+        for r, rd in enumerate(reads):
+            for s in (0, 1):
+                e, _, h = orc.hitinfo(oix, rd, None, s, 1, 10000, 16384, 0)
+                hl = orc.lib.so_hitlist_create(32768)
+                for sx in range(len(seqs)):
+                    if e == 0:
+                        e2, want, hl = orc.hitlist_segment(oix, h, soffs[sx], soffs[sx + 1], nhit_max, 1, hl)
+                        got = sq[int(first[n]):int(first[n + 1])]
+                        assert e2 == 0
+                        assert np.array_equal(got, want), (r, s, sx, nhit_max, len(got), len(want))
+                        big = max(big, len(want))
+                    n += 1
+                orc.lib.so_hitlist_delete(hl)
+                orc.lib.so_hitinfo_delete(h)
+        if kind == "repeat" and nhit_max == 0:
+            assert big > 10000
