@@ -80,6 +80,11 @@ int smb_last_kernel_launches(const smb_ctx *ctx);
 /* total kernels launched by this context since creation */
 long long smb_total_kernel_launches(const smb_ctx *ctx);
 
+/* Integer-issue micro-benchmark used as the roofline denominator of the DP kernels:
+ * sustained giga thread-operations per second of (0) VIADDMNMX  max(a+b,c),
+ * (1) VIMNMX3 max(a,b,c) and (2) plain IADD+IMNMX pairs, measured on this device. */
+int smb_int_peak(smb_ctx *ctx, double gops[3]);
+
 /* --------------------------- sequence arena ------------------------------ */
 /* Uploads a block of concatenated sequences (reads and, for the *_batch calls
  * that take explicit windows, reference windows) to HBM.  Tasks address it by

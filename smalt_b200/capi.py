@@ -85,6 +85,7 @@ def load_library():
     lib.smb_ctx_destroy.argtypes = [C.c_void_p]
     lib.smb_ctx_destroy.restype = None
     lib.smb_set_scoring.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.smb_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     lib.smb_arena_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     lib.smb_refseq_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_void_p, C.c_int]
     lib.smb_sw_score_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -144,6 +145,12 @@ class Context:
     @property
     def total_kernel_launches(self):
         return int(self.lib.smb_total_kernel_launches(self._h))
+
+    def int_peak(self):
+        """-> (viaddmax, vimax3, add+max) giga thread-ops/s measured on this device"""
+        g = (C.c_double * 3)()
+        self._check(self.lib.smb_int_peak(self._h, g))
+        return tuple(g)
 
     def arena_upload(self, codes):
         codes = np.ascontiguousarray(codes, np.uint8)

@@ -149,6 +149,29 @@ int smb_set_scoring(smb_ctx *ctx, int match, int mismatch, int gapopen, int gape
   return SMB_OK;
 }
 
+int smb_int_peak(smb_ctx *ctx, double gops[3]) {
+  if (!ctx || !gops) return SMB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  CU(ctx->scratch.ensure((size_t)ctx->sm_count * 8 * 256 * sizeof(int)));
+  const int iters = 4096;
+  for (int mode = 0; mode < 3; ++mode) {
+    double ops = 0, best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+      CU(cudaEventRecord(ctx->ev0, st));
+      CU(run_int_peak(mode, ctx->sm_count, ctx->scratch.as<int>(), iters, st, &ops));
+      CU(cudaEventRecord(ctx->ev1, st));
+      CU(cudaStreamSynchronize(st));
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+      ++ctx->total_launches;
+      if (rep > 0 && ms > 0.f && ops / ms * 1e-6 > best) best = ops / ms * 1e-6;
+    }
+    gops[mode] = best;
+  }
+  return SMB_OK;
+}
+
 int smb_arena_upload(smb_ctx *ctx, const uint8_t *codes, size_t nbytes) {
   if (!ctx || (!codes && nbytes)) return SMB_ERR_ARG;
   cudaSetDevice(ctx->device);
