@@ -80,6 +80,11 @@ int smb_last_kernel_launches(const smb_ctx *ctx);
 /* total kernels launched by this context since creation */
 long long smb_total_kernel_launches(const smb_ctx *ctx);
 
+/* Makes `dst` use the index and packed reference already uploaded to `src`
+ * (same device) instead of holding its own copy: one resident copy per GPU,
+ * one context (stream + scratch buffers) per host worker thread. */
+int smb_ctx_share_index(smb_ctx *dst, const smb_ctx *src);
+
 /* Integer-issue micro-benchmark used as the roofline denominator of the DP kernels:
  * sustained giga thread-operations per second of (0) VIADDMNMX  max(a+b,c),
  * (1) VIMNMX3 max(a,b,c) and (2) plain IADD+IMNMX pairs, measured on this device. */
@@ -188,10 +193,12 @@ typedef struct {
  *   seed_posidx/nhits/qoffs: SEED fields in discovery order,
  *   sortkey/sidx: nhitqual_sortkeyp / sidxp after the reference's quicksort,
  *   qmask: HITQUAL codes per read offset (hashhit.h:57-65).
- * qual may be NULL (FASTA); basq_thresh as `smalt map -q`. */
+ * qual may be NULL (FASTA); basq_thresh as `smalt map -q`.  short_info != 0:
+ * hashCollectHitInfoShort (sorted + ranked, the default mode of rmap.c:1686);
+ * short_info == 0: hashCollectHitInfo (unsorted, no per-seed cut, `smalt map -x`). */
 int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_len,
 		   int nreads, const uint8_t *qual, uint32_t maxhit_per_tuple,
-		   uint32_t maxhit_total, int basq_thresh,
+		   uint32_t maxhit_total, int basq_thresh, int short_info,
 		   smb_seed_info *info, uint32_t *seed_posidx, uint32_t *seed_nhits,
 		   uint32_t *seed_qoffs, uint32_t *sortkey, uint32_t *sidx, uint8_t *qmask);
 

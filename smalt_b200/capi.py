@@ -96,7 +96,7 @@ def load_library():
     lib.smb_index_upload.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
                                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.smb_seed_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_uint32,
-                                   C.c_uint32, C.c_int] + [C.c_void_p] * 7
+                                   C.c_uint32, C.c_int, C.c_int] + [C.c_void_p] * 7
     lib.smb_hits_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_size_t,
                                    C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p]
     _lib = lib
@@ -174,7 +174,7 @@ class Context:
             _vp(np.ascontiguousarray(pidx, np.uint32))))
 
     def seed_batch(self, read_off, read_len, qual=None, maxhit_per_tuple=10000, maxhit_total=16384,
-                   basq_thresh=0, full=True):
+                   basq_thresh=0, full=True, short_info=True):
         """-> (info[2*n] SEED_INFO_DTYPE, tables dict or None).  Table arrays have 2*sum(read_len)
         slots; read r strand s starts at 2*sum(read_len[:r]) + s*read_len[r]."""
         read_off = np.ascontiguousarray(read_off, np.uint64)
@@ -190,7 +190,7 @@ class Context:
             ptrs = [_vp(tabs[k]) for k in ("posidx", "nhits", "qoffs", "sortkey", "sidx", "qmask")]
         q = None if qual is None else _vp(np.ascontiguousarray(qual, np.uint8))
         self._check(self.lib.smb_seed_batch(self._h, _vp(read_off), _vp(read_len), n, q, maxhit_per_tuple,
-                                            maxhit_total, basq_thresh, _vp(info), *ptrs))
+                                            maxhit_total, basq_thresh, int(short_info), _vp(info), *ptrs))
         return info, tabs
 
     def hits_batch(self, req, nhits_alloc=0, max_hits=None):

@@ -149,6 +149,16 @@ int smb_set_scoring(smb_ctx *ctx, int match, int mismatch, int gapopen, int gape
   return SMB_OK;
 }
 
+int smb_ctx_share_index(smb_ctx *dst, const smb_ctx *src) {
+  if (!dst || !src || dst->device != src->device) return SMB_ERR_ARG;
+  dst->ix = src->ix;
+  dst->have_index = src->have_index;
+  dst->src.packed = src->src.packed;
+  dst->src.packed_nbases = src->src.packed_nbases;
+  dst->seq_offs = src->seq_offs;
+  return SMB_OK;
+}
+
 int smb_int_peak(smb_ctx *ctx, double gops[3]) {
   if (!ctx || !gops) return SMB_ERR_ARG;
   cudaSetDevice(ctx->device);
@@ -230,14 +240,16 @@ int smb_sw_score_batch(smb_ctx *ctx, const smb_sw_task *tasks, int ntasks, int32
   CU(ctx->out_a.ensure((size_t)ntasks * 2 * sizeof(int32_t)));
   CU(cudaMemcpyAsync(ctx->tasks.p, tasks, (size_t)ntasks * sizeof(smb_sw_task), cudaMemcpyHostToDevice, st));
   int32_t *d_scores = ctx->out_a.as<int32_t>(), *d_errs = d_scores + ntasks;
-  size_t need = 0;
   int nl = 0;
-  CU(launch_sw_score(ctx->sc, ctx->src, ctx->tasks.as<smb_sw_task>(), tasks, ntasks, d_scores, d_errs,
-                     nullptr, 0, &need, ctx->sm_count, st, &nl));
-  CU(ctx->scratch.ensure(need));
+  SwPlan plan;
+  plan_sw(tasks, ntasks, ctx->sm_count, plan);   // host planning happens before the timed events
+  const size_t off_order = 256, off_strip = (off_order + (size_t)ntasks * sizeof(int) + 255) & ~(size_t)255;
+  CU(ctx->scratch.ensure(off_strip + plan.strip_bytes + 256));
+  char *sb = ctx->scratch.as<char>();
+  CU(cudaMemcpyAsync(sb + off_order, plan.order.data(), (size_t)ntasks * sizeof(int), cudaMemcpyHostToDevice, st));
   CU(cudaEventRecord(ctx->ev0, st));
-  CU(launch_sw_score(ctx->sc, ctx->src, ctx->tasks.as<smb_sw_task>(), tasks, ntasks, d_scores, d_errs,
-                     ctx->scratch.p, ctx->scratch.cap, &need, ctx->sm_count, st, &nl));
+  CU(launch_sw_score(ctx->sc, ctx->src, ctx->tasks.as<smb_sw_task>(), plan, (int *)sb, (const int *)(sb + off_order),
+                     sb + off_strip, d_scores, d_errs, st, &nl));
   CU(cudaEventRecord(ctx->ev1, st));
   CU(cudaMemcpyAsync(scores, d_scores, (size_t)ntasks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(errs, d_errs, (size_t)ntasks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -270,9 +282,16 @@ int smb_band_score_batch(smb_ctx *ctx, const smb_band_task *tasks, int ntasks, i
   CU(cudaMemsetAsync(d_cells, 0, sizeof(unsigned long long), st));
   BandOut bo{nullptr, nullptr, nullptr, d_errs, d_cells};
   int nl = 0;
+  BandPlan plan;
+  plan_band(tasks, ntasks, false, plan);
+  const size_t gring_words = band_gring_words(plan);
+  CU(ctx->scratch.ensure((size_t)ntasks * sizeof(int) + gring_words * sizeof(uint32_t) + 512));
+  int *d_order = ctx->scratch.as<int>();
+  uint32_t *d_gring = (uint32_t *)(ctx->scratch.as<char>() + (((size_t)ntasks * sizeof(int) + 255) & ~(size_t)255));
+  CU(cudaMemcpyAsync(d_order, plan.order.data(), (size_t)ntasks * sizeof(int), cudaMemcpyHostToDevice, st));
   CU(cudaEventRecord(ctx->ev0, st));
-  CU(launch_band(ctx->sc, ctx->src, ctx->tasks.as<smb_band_task>(), tasks, ntasks, false, d_scores, bo, 0,
-                 nullptr, nullptr, nullptr, nullptr, ctx->sm_count, st, &nl));
+  CU(launch_band(ctx->sc, ctx->src, ctx->tasks.as<smb_band_task>(), plan, d_order, false, d_scores, bo, 0,
+                 nullptr, nullptr, nullptr, nullptr, d_gring, st, &nl));
   CU(cudaEventRecord(ctx->ev1, st));
   CU(cudaMemcpyAsync(scores, d_scores, (size_t)ntasks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(errs, d_errs, (size_t)ntasks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -333,9 +352,16 @@ static int band_align_pass(smb_ctx *ctx, const smb_band_task *tasks, const std::
   unsigned long long *d_cells = (unsigned long long *)(((uintptr_t)(d_errs + n) + 15) & ~(uintptr_t)15);
   CU(cudaMemsetAsync(d_cells, 0, sizeof(unsigned long long), st));
   BandOut bo{d_res, d_nres, ctx->diff.as<uint8_t>(), d_errs, d_cells};
+  BandPlan plan;
+  plan_band(sub.data(), n, true, plan);
+  const size_t gring_words = band_gring_words(plan);
+  CU(ctx->scratch.ensure((size_t)n * sizeof(int) + gring_words * sizeof(uint32_t) + 512));
+  int *d_order = ctx->scratch.as<int>();
+  uint32_t *d_gring = (uint32_t *)(ctx->scratch.as<char>() + (((size_t)n * sizeof(int) + 255) & ~(size_t)255));
+  CU(cudaMemcpyAsync(d_order, plan.order.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
   CU(cudaEventRecord(ctx->ev0, st));
-  CU(launch_band(ctx->sc, ctx->src, ctx->tasks.as<smb_band_task>(), sub.data(), n, true, nullptr, bo, max_res,
-                 d_dir_off, ctx->dirs.as<uint32_t>(), d_diff_off, d_diff_cap, ctx->sm_count, st, nlaunch));
+  CU(launch_band(ctx->sc, ctx->src, ctx->tasks.as<smb_band_task>(), plan, d_order, true, nullptr, bo, max_res,
+                 d_dir_off, ctx->dirs.as<uint32_t>(), d_diff_off, d_diff_cap, d_gring, st, nlaunch));
   CU(cudaEventRecord(ctx->ev1, st));
   h_res.resize((size_t)n * max_res);
   h_nres.resize((size_t)n);
@@ -499,7 +525,7 @@ int smb_index_upload(smb_ctx *ctx, int typ, int wordlen, int nskip, int nbits_ke
 
 int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_len, int nreads,
                    const uint8_t *qual, uint32_t maxhit_per_tuple, uint32_t maxhit_total, int basq_thresh,
-                   smb_seed_info *info, uint32_t *seed_posidx, uint32_t *seed_nhits, uint32_t *seed_qoffs,
+                   int short_info, smb_seed_info *info, uint32_t *seed_posidx, uint32_t *seed_nhits, uint32_t *seed_qoffs,
                    uint32_t *sortkey, uint32_t *sidx, uint8_t *qmask) {
   if (!ctx || nreads < 0 || (nreads && (!read_off || !read_len || !info))) return SMB_ERR_ARG;
   ctx->last_ms = 0.f;
@@ -541,7 +567,7 @@ int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_
   SeedArgs a{};
   a.read_off = d_off; a.read_len = d_len; a.slot_off = d_slot; a.qual = d_qual; a.nreads = nreads;
   a.maxhit_per_tuple = maxhit_per_tuple; a.maxhit_total = maxhit_total; a.basq_thresh = basq_thresh;
-  a.is_short = 1;
+  a.is_short = short_info ? 1 : 0;
   a.info = d_info;
   a.posidx = u; a.nhits = u + S; a.qoffs = u + 2 * S; a.sortkey = u + 3 * S; a.sidx = u + 4 * S; a.frame = u + 5 * S;
   a.qmask = b; a.qbuf = b + S;

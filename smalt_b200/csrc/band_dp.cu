@@ -318,56 +318,49 @@ static int pow2_at_least(int v) {
   return p;
 }
 
+// Host-side plan: tasks bucketed by ring capacity (one launch per class), input order kept
+// inside a class (neighbouring tasks come from the same read / candidate list and have
+// similar geometry, so the threads of a warp stay balanced without a full sort).
+void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, BandPlan &plan) {
+  plan.order.resize((size_t)ntasks);
+  plan.classes.clear();
+  std::vector<int> wc((size_t)ntasks);
+  int count[32] = {0};
+  auto cls = [](int wcap) { int c = 0; while ((32 << c) < wcap) ++c; return c; };
+  for (int i = 0; i < ntasks; ++i) {
+    const int need = ring_need(h_tasks[i], !align);
+    wc[(size_t)i] = cls(pow2_at_least(need + 1));
+    count[wc[(size_t)i]]++;
+  }
+  int start[33];
+  start[0] = 0;
+  for (int c = 0; c < 32; ++c) start[c + 1] = start[c] + count[c];
+  int fill[32];
+  for (int c = 0; c < 32; ++c) fill[c] = start[c];
+  for (int i = 0; i < ntasks; ++i) plan.order[(size_t)fill[wc[(size_t)i]]++] = i;
+  for (int c = 0; c < 32; ++c)
+    if (count[c]) plan.classes.push_back(BandPlan::Class{32 << c, start[c], count[c]});
+}
+
 cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_task *d_tasks,
-                        const smb_band_task *h_tasks, int ntasks, bool align,
+                        const BandPlan &plan, const int *d_order, bool align,
                         int32_t *d_scores, BandOut out, int max_res,
                         const uint64_t *d_dir_off, uint32_t *d_dirs,
                         const uint64_t *d_diff_off, const uint32_t *d_diff_cap,
-                        int sm_count, cudaStream_t st, int *nlaunch) {
-  (void)sm_count;
-  struct Key { int wcap; long long size; int idx; };
-  std::vector<Key> keys((size_t)ntasks);
-  for (int i = 0; i < ntasks; ++i) {
-    const int need = ring_need(h_tasks[i], !align);
-    keys[(size_t)i] = Key{pow2_at_least(need + 1), (long long)need * h_tasks[i].ref_len, i};
-  }
-  std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) {
-    if (a.wcap != b.wcap) return a.wcap < b.wcap;
-    if (a.size != b.size) return a.size > b.size;
-    return a.idx < b.idx;
-  });
-  std::vector<int> order((size_t)ntasks);
-  for (int i = 0; i < ntasks; ++i) order[(size_t)i] = keys[(size_t)i].idx;
-  int *d_order = nullptr;
-  cudaError_t e;
-  if ((e = cudaMallocAsync((void **)&d_order, (size_t)ntasks * sizeof(int), st)) != cudaSuccess) return e;
-  if ((e = cudaMemcpyAsync(d_order, order.data(), (size_t)ntasks * sizeof(int), cudaMemcpyHostToDevice,
-                           st)) != cudaSuccess)
-    return e;
+                        uint32_t *d_gring, cudaStream_t st, int *nlaunch) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(band_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(band_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
-  const int SMEM_WCAP_MAX = 512;  // 512 slots * 64 threads * 4 B = 128 KB
-  int pos = 0;
-  std::vector<uint32_t *> grings;
-  while (pos < ntasks) {
-    const int wcap = keys[(size_t)pos].wcap;
-    int end = pos;
-    while (end < ntasks && keys[(size_t)end].wcap == wcap) ++end;
-    const int n = end - pos;
-    const int grid = (n + BAND_THREADS - 1) / BAND_THREADS;
-    BandArgs a{d_order + pos, n, wcap, nullptr, max_res};
-    size_t smem = (size_t)wcap * BAND_THREADS * sizeof(uint32_t);
-    if (wcap > SMEM_WCAP_MAX) {
-      uint32_t *gr = nullptr;
-      if ((e = cudaMallocAsync((void **)&gr, (size_t)grid * BAND_THREADS * wcap * sizeof(uint32_t), st)) !=
-          cudaSuccess)
-        return e;
-      grings.push_back(gr);
-      a.gring = gr;
+  cudaError_t e;
+  for (const BandPlan::Class &c : plan.classes) {
+    const int grid = (c.count + BAND_THREADS - 1) / BAND_THREADS;
+    BandArgs a{d_order + c.start, c.count, c.wcap, nullptr, max_res};
+    size_t smem = (size_t)c.wcap * BAND_THREADS * sizeof(uint32_t);
+    if (c.wcap > BAND_SMEM_WCAP_MAX) {  // long-read bands: ring in an HBM strip
+      a.gring = d_gring;
       smem = 0;
     }
     if (align)
@@ -378,11 +371,18 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
                                                            d_dirs, d_diff_off, d_diff_cap);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++*nlaunch;
-    pos = end;
   }
-  for (uint32_t *gr : grings) cudaFreeAsync(gr, st);
-  cudaFreeAsync(d_order, st);
   return cudaSuccess;
+}
+
+size_t band_gring_words(const BandPlan &plan) {
+  size_t need = 0;
+  for (const BandPlan::Class &c : plan.classes)
+    if (c.wcap > BAND_SMEM_WCAP_MAX) {
+      const size_t grid = (size_t)(c.count + BAND_THREADS - 1) / BAND_THREADS;
+      need = std::max(need, grid * BAND_THREADS * (size_t)c.wcap);
+    }
+  return need;
 }
 
 }  // namespace smb

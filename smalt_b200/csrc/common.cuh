@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <vector>
 #include "../../include/smalt_b200.h"
 
 namespace smb {
@@ -47,11 +48,18 @@ struct Timer {
   cudaEvent_t a = nullptr, b = nullptr;
 };
 
-// launchers (one per .cu)
+// ---- K2 ----
+struct SwPlan {
+  std::vector<int> order;   // task indices grouped by columns-per-lane class
+  int count[9], start[9];
+  int max_grid;
+  uint32_t bstride;         // rows of the boundary strips (multi-block reads), 0 if none
+  size_t strip_bytes;
+};
+void plan_sw(const smb_sw_task *h_tasks, int ntasks, int sm_count, SwPlan &plan);
 cudaError_t launch_sw_score(const Scoring &sc, const SeqSrc &src, const smb_sw_task *d_tasks,
-                            const smb_sw_task *h_tasks, int ntasks, int32_t *d_scores,
-                            int32_t *d_errs, void *d_scratch, size_t scratch_bytes,
-                            size_t *scratch_needed, int sm_count, cudaStream_t st, int *nlaunch);
+                            const SwPlan &plan, int *d_counters, const int *d_order, void *d_strips,
+                            int32_t *d_scores, int32_t *d_errs, cudaStream_t st, int *nlaunch);
 
 struct BandOut {        // device buffers of smb_band_align_batch
   smb_ali_result *results;  // [ntasks * max_res]
@@ -61,12 +69,20 @@ struct BandOut {        // device buffers of smb_band_align_batch
   unsigned long long *cells;
 };
 
+constexpr int BAND_SMEM_WCAP_MAX = 512;  // 512 slots * 64 threads * 4 B = 128 KB of shared memory
+struct BandPlan {
+  struct Class { int wcap, start, count; };
+  std::vector<int> order;
+  std::vector<Class> classes;
+};
+void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, BandPlan &plan);
+size_t band_gring_words(const BandPlan &plan);
 cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_task *d_tasks,
-                        const smb_band_task *h_tasks, int ntasks, bool align,
+                        const BandPlan &plan, const int *d_order, bool align,
                         int32_t *d_scores, BandOut out, int max_res,
                         const uint64_t *d_dir_off, uint32_t *d_dirs,
                         const uint64_t *d_diff_off, const uint32_t *d_diff_cap,
-                        int sm_count, cudaStream_t st, int *nlaunch);
+                        uint32_t *d_gring, cudaStream_t st, int *nlaunch);
 
 // ---- K1 ----
 struct Index {

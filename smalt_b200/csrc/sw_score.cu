@@ -172,70 +172,59 @@ static cudaError_t launch_class(const Scoring &sc, const SeqSrc &src, const smb_
   return cudaGetLastError();
 }
 
-// scratch layout: [8 counters | order[ntasks] | boundary strips]
-cudaError_t launch_sw_score(const Scoring &sc, const SeqSrc &src, const smb_sw_task *d_tasks,
-                            const smb_sw_task *h_tasks, int ntasks, int32_t *d_scores,
-                            int32_t *d_errs, void *d_scratch, size_t scratch_bytes,
-                            size_t *scratch_needed, int sm_count, cudaStream_t st, int *nlaunch) {
+// Host-side plan: tasks bucketed by columns-per-lane class (one launch per class).
+void plan_sw(const smb_sw_task *h_tasks, int ntasks, int sm_count, SwPlan &plan) {
   constexpr int NCLS = 8;
-  std::vector<int> order((size_t)ntasks);
-  int count[NCLS + 1] = {0}, start[NCLS + 1] = {0};
+  plan.order.resize((size_t)ntasks);
   uint32_t max_rlen_multi = 0;
   auto cls_of = [](uint32_t qlen) {
     int c = (int)((qlen + 31) / 32);
     return c < 1 ? 1 : (c > NCLS ? NCLS : c);
   };
+  for (int c = 0; c <= NCLS; ++c) plan.count[c] = plan.start[c] = 0;
   for (int i = 0; i < ntasks; ++i) {
-    count[cls_of(h_tasks[i].read_len)]++;
+    plan.count[cls_of(h_tasks[i].read_len)]++;
     if (h_tasks[i].read_len > 32u * NCLS) max_rlen_multi = std::max(max_rlen_multi, h_tasks[i].ref_len);
   }
-  for (int c = 1; c <= NCLS; ++c) start[c] = start[c - 1] + count[c - 1];
-  {
-    int fill[NCLS + 1];
-    for (int c = 0; c <= NCLS; ++c) fill[c] = start[c];
-    for (int i = 0; i < ntasks; ++i) order[(size_t)fill[cls_of(h_tasks[i].read_len)]++] = i;
-  }
+  for (int c = 1; c <= NCLS; ++c) plan.start[c] = plan.start[c - 1] + plan.count[c - 1];
+  int fill[NCLS + 1];
+  for (int c = 0; c <= NCLS; ++c) fill[c] = plan.start[c];
+  for (int i = 0; i < ntasks; ++i) plan.order[(size_t)fill[cls_of(h_tasks[i].read_len)]++] = i;
   // long reads first inside the multi-block class (largest tasks start earliest)
   if (max_rlen_multi)
-    std::stable_sort(order.begin() + start[NCLS], order.begin() + start[NCLS] + count[NCLS],
+    std::stable_sort(plan.order.begin() + plan.start[NCLS], plan.order.begin() + plan.start[NCLS] + plan.count[NCLS],
                      [&](int a, int b) {
                        return (uint64_t)h_tasks[a].read_len * h_tasks[a].ref_len >
                               (uint64_t)h_tasks[b].read_len * h_tasks[b].ref_len;
                      });
-  const int blocks_per_sm = 8;
-  const int max_grid = sm_count * blocks_per_sm;
-  const uint32_t bstride = (max_rlen_multi + 31u) & ~31u;
-  const size_t off_order = 256;
-  const size_t off_strip = (off_order + (size_t)ntasks * sizeof(int) + 255) & ~(size_t)255;
-  const size_t need = off_strip + (size_t)max_grid * SW_WARPS * 2u * bstride * sizeof(int2);
-  *scratch_needed = need;
-  if (need > scratch_bytes || d_scratch == nullptr) return cudaSuccess;  // caller grows and retries
+  plan.max_grid = sm_count * 8;
+  plan.bstride = (max_rlen_multi + 31u) & ~31u;
+  plan.strip_bytes = (size_t)plan.max_grid * SW_WARPS * 2u * plan.bstride * sizeof(int2);
+}
 
-  char *base = (char *)d_scratch;
-  int *d_counters = (int *)base;
-  int *d_order = (int *)(base + off_order);
-  int2 *d_strips = (int2 *)(base + off_strip);
+// d_counters: 16 ints (zeroed here); d_order: plan.order on the device; d_strips: plan.strip_bytes
+cudaError_t launch_sw_score(const Scoring &sc, const SeqSrc &src, const smb_sw_task *d_tasks,
+                            const SwPlan &plan, int *d_counters, const int *d_order, void *d_strips,
+                            int32_t *d_scores, int32_t *d_errs, cudaStream_t st, int *nlaunch) {
+  constexpr int NCLS = 8;
   cudaError_t e;
-  if ((e = cudaMemsetAsync(d_counters, 0, 256, st)) != cudaSuccess) return e;
-  if ((e = cudaMemcpyAsync(d_order, order.data(), (size_t)ntasks * sizeof(int),
-                           cudaMemcpyHostToDevice, st)) != cudaSuccess)
-    return e;
-  // the order vector must outlive the async copy: pageable-memory copies are staged
-  // synchronously by the runtime before cudaMemcpyAsync returns.
+  if ((e = cudaMemsetAsync(d_counters, 0, 16 * sizeof(int), st)) != cudaSuccess) return e;
   for (int c = 1; c <= NCLS; ++c) {
-    if (!count[c]) continue;
-    SwClassArgs cls{d_order + start[c], count[c], d_counters + c};
-    int grid = (count[c] + SW_WARPS - 1) / SW_WARPS;
-    if (grid > max_grid) grid = max_grid;
+    if (!plan.count[c]) continue;
+    SwClassArgs cls{d_order + plan.start[c], plan.count[c], d_counters + c};
+    int grid = (plan.count[c] + SW_WARPS - 1) / SW_WARPS;
+    if (grid > plan.max_grid) grid = plan.max_grid;
+    int2 *strips = (int2 *)d_strips;
+    const uint32_t bstride = plan.bstride;
     switch (c) {
-      case 1: e = launch_class<1>(sc, src, d_tasks, cls, d_scores, d_errs, d_strips, bstride, grid, st); break;
-      case 2: e = launch_class<2>(sc, src, d_tasks, cls, d_scores, d_errs, d_strips, bstride, grid, st); break;
-      case 3: e = launch_class<3>(sc, src, d_tasks, cls, d_scores, d_errs, d_strips, bstride, grid, st); break;
-      case 4: e = launch_class<4>(sc, src, d_tasks, cls, d_scores, d_errs, d_strips, bstride, grid, st); break;
-      case 5: e = launch_class<5>(sc, src, d_tasks, cls, d_scores, d_errs, d_strips, bstride, grid, st); break;
-      case 6: e = launch_class<6>(sc, src, d_tasks, cls, d_scores, d_errs, d_strips, bstride, grid, st); break;
-      case 7: e = launch_class<7>(sc, src, d_tasks, cls, d_scores, d_errs, d_strips, bstride, grid, st); break;
-      default: e = launch_class<8>(sc, src, d_tasks, cls, d_scores, d_errs, d_strips, bstride, grid, st); break;
+      case 1: e = launch_class<1>(sc, src, d_tasks, cls, d_scores, d_errs, strips, bstride, grid, st); break;
+      case 2: e = launch_class<2>(sc, src, d_tasks, cls, d_scores, d_errs, strips, bstride, grid, st); break;
+      case 3: e = launch_class<3>(sc, src, d_tasks, cls, d_scores, d_errs, strips, bstride, grid, st); break;
+      case 4: e = launch_class<4>(sc, src, d_tasks, cls, d_scores, d_errs, strips, bstride, grid, st); break;
+      case 5: e = launch_class<5>(sc, src, d_tasks, cls, d_scores, d_errs, strips, bstride, grid, st); break;
+      case 6: e = launch_class<6>(sc, src, d_tasks, cls, d_scores, d_errs, strips, bstride, grid, st); break;
+      case 7: e = launch_class<7>(sc, src, d_tasks, cls, d_scores, d_errs, strips, bstride, grid, st); break;
+      default: e = launch_class<8>(sc, src, d_tasks, cls, d_scores, d_errs, strips, bstride, grid, st); break;
     }
     if (e != cudaSuccess) return e;
     ++*nlaunch;

@@ -1,0 +1,625 @@
+/* rmap_wave.c - batched ("wave") single-end read mapping for the smalt_b200 driver build.
+ *
+ * The reference maps one read at a time (rmapSingle, /root/reference/src/rmap.c:1648) and
+ * calls the hot-path functions once per read x strand (seed lookup), once per reference
+ * sequence (hit list) and once per candidate segment (SW score, banded alignment).  One
+ * synchronous GPU call per such function call would serialise the device, so this file
+ * replays the same per-read logic in WAVES over a whole block of reads:
+ *
+ *   wave 1  GPU  K1  seed tables of all reads, both strands        (smb_seed_batch)
+ *           GPU  K1  hit lists for every read x strand x sequence  (smb_hits_batch)
+ *           host     candidate selection per read: the reference's own segment.c
+ *                    (segLstFillHits, segAliCandsAddFast, segAliCandsStats,
+ *                    segAliCandsCalcSegmentOffsets) on the GPU hit lists
+ *   wave 2  GPU  K2/K2'  score of EVERY candidate of every read    (smb_sw_score_batch,
+ *                    smb_band_score_batch) - the reference stops scoring early
+ *                    (rmap.c:756-783); the early exits are replayed on the host afterwards,
+ *                    so over-computed scores are simply never looked at
+ *           host     replay of scoreRMAPCAND (rmap.c:660-786) and of the threshold logic of
+ *                    mapSingleRead (rmap.c:1379-1400)
+ *   wave 3  GPU  K3  banded alignment + backtrace of every candidate that passes the
+ *                    INITIAL score threshold                        (smb_band_align_batch)
+ *           host     replay of alignRMAPCANDFull (rmap.c:790-928): in BEST mode the
+ *                    threshold rises while results are added (rmap.c:881-885); a K3 task
+ *                    computed with the initial threshold contains the result tree of any
+ *                    higher threshold as a prefix-closed subtree, which prune_results()
+ *                    extracts exactly ("threshold replay")
+ *           host     the reference's results.c / report.c produce MAPQ and SAM as before.
+ *
+ * This translation unit compiles the reference's rmap.c in place (from the read-only tree on
+ * the include path; nothing is copied) so that the reference's own RMap buffers and static
+ * helpers are reused and rmapCreate/rmapSingle/rmapPair keep working through the shim
+ * (one GPU call per function call: slow, but still no CPU hot path).
+ */
+#include "rmap.c"
+#include "shim.h"
+#include "rmap_wave.h"
+
+typedef struct {
+  RMAPCAND c;
+  COVERAGE cover;
+  uint32_t reflen;   /* length of the (clipped) reference window */
+  uint64_t refoff;   /* offset of the window in the packed reference */
+  int32_t task;      /* index into the K2 / K2' task list */
+  int32_t k3task;    /* index into the K3 task list or -1 */
+  uint8_t simd;
+} WCAND;
+
+typedef struct {
+  uint32_t qlen;
+  int errcode;           /* error that ends the mapping of this read */
+  uint8_t reached_stats; /* mapSingleRead got as far as resultSetAlignmentStats */
+  uint8_t do_align;      /* max1scor >= 1 */
+  int nseg, nseg_tot;
+  uint32_t nhit, nhit_tot;
+  uint32_t cand_first, ncand, nscored;
+  COVERAGE curr_min_cover, cover_deficit[2];
+  SWATSCOR max1scor, max2scor;
+  int min_swatscor, scorlen_min, bandwidth_min;
+} WREAD;
+
+struct RmapWave_ {
+  smb_ctx *ctx;
+  /* host staging, grown on demand */
+  uint8_t *arena, *qual;
+  size_t arena_alloc;
+  uint64_t *read_off;
+  uint32_t *read_len;
+  smb_seed_info *info;
+  WREAD *rd;
+  size_t n_alloc;
+  smb_hit_req *req;
+  uint64_t *list_first;
+  int32_t *req_err;
+  size_t req_alloc;
+  uint64_t *sqdat;
+  size_t sqdat_alloc;
+  WCAND *cand;
+  size_t cand_alloc, ncand;
+  smb_sw_task *swt;
+  int32_t *sw_score, *sw_err;
+  size_t swt_alloc;
+  smb_band_task *bft, *bat;
+  int32_t *bf_score, *bf_err, *ba_err;
+  size_t bft_alloc, bat_alloc;
+  smb_ali_result *res;
+  uint32_t *res_first;
+  uint8_t *diff;
+  size_t res_alloc, diff_alloc;
+  ScoreProfile *prof, *profRC;
+  SeqFastq *readRC;
+  /* statistics */
+  double ms_k1, ms_k2, ms_k3;
+  uint64_t cells_k2, cells_k3, n_k2, n_k3, n_reads;
+};
+
+#define WGROW(ptr, alloc, need, type)						\
+  do { if ((size_t) (need) > (alloc)) {						\
+      size_t na_ = (size_t) (need) + (size_t) (need) / 2 + 64;			\
+      void *hp_ = realloc((ptr), na_ * sizeof(type));				\
+      if (!hp_) return ERRCODE_NOMEM;						\
+      (ptr) = (type *) hp_; (alloc) = na_; } } while (0)
+
+RmapWave *rmapWaveCreate(const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
+			 const ScoreMatrix *scormtxp)
+{
+  RmapWave *w;
+  if (smbShimInit(htp, ssp, codecp, scormtxp)) return NULL;
+  w = (RmapWave *) calloc(1, sizeof(*w));
+  if (!w) return NULL;
+  if (smbShimWorkerCtx(&w->ctx, scormtxp)) { free(w); return NULL; }
+  w->prof = scoreCreateProfile(0, codecp, SCORPROF_SCALAR);
+  w->profRC = scoreCreateProfile(0, codecp, SCORPROF_SCALAR);
+  w->readRC = seqFastqCreate(0, SEQTYP_FASTQ);
+  if (!w->prof || !w->profRC || !w->readRC) { free(w); return NULL; }
+  return w;
+}
+
+void rmapWaveDelete(RmapWave *w)
+{
+  if (!w) return;
+  smb_ctx_destroy(w->ctx);
+  free(w->arena); free(w->qual); free(w->read_off); free(w->read_len); free(w->info); free(w->rd);
+  free(w->req); free(w->list_first); free(w->req_err); free(w->sqdat); free(w->cand); free(w->swt);
+  free(w->sw_score); free(w->sw_err); free(w->bft); free(w->bat); free(w->bf_score); free(w->bf_err);
+  free(w->ba_err); free(w->res); free(w->res_first); free(w->diff);
+  scoreDeleteProfile(w->prof); scoreDeleteProfile(w->profRC); seqFastqDelete(w->readRC);
+  free(w);
+}
+
+void rmapWaveGetStats(const RmapWave *w, double ms[3], uint64_t counts[5])
+{
+  ms[0] = w->ms_k1; ms[1] = w->ms_k2; ms[2] = w->ms_k3;
+  counts[0] = w->n_reads; counts[1] = w->n_k2; counts[2] = w->cells_k2; counts[3] = w->n_k3;
+  counts[4] = w->cells_k3;
+}
+
+static int gpu_fail(ErrMsg *errmsgp, const RmapWave *w, int rc)
+{
+  fprintf(stderr, "smalt_b200: GPU call failed (%d): %s\n", rc, smb_last_error(w->ctx));
+  ERRMSGNO(errmsgp, ERRCODE_FAILURE);
+  return ERRCODE_FAILURE;
+}
+
+/* The results of a K3 task computed with thresholds (ms0, msl0), in the reference's
+ * discovery (pre-)order, contain the results for any (ms >= ms0, msl >= msl0): walk the
+ * recursion tree of alignSmiWatBandRecursive (alignment.c:1300-1434) implied by the row
+ * ranges and apply the cuts the reference would apply with the higher thresholds. */
+static int prune_results(AliRsltSet *out, const smb_ali_result *res, const uint8_t *diff,
+			 uint32_t *pos, uint32_t end, int s_left, int s_right,
+			 int minscore, int minscorlen, int keep)
+{
+  int errcode = 0;
+  const smb_ali_result *r;
+  int s_start, s_end, k;
+  if (*pos >= end) return 0;
+  r = res + *pos;
+  if (r->rs < s_left || r->re > s_right) return 0; /* nothing was found in this row range */
+  ++*pos;
+  s_start = r->rs; s_end = r->re;
+  k = keep && r->score >= minscore && !(r->qs + minscorlen > r->qe + 1);
+  if (k && (errcode = smbShimAliRsltSetAdd(out, r->score, r->qs, r->qe, r->rs, r->re,
+					   diff + r->diff_off, (int) r->diff_len)))
+    return errcode;
+  /* children exist in the list iff the initial thresholds explored them; they are kept only
+   * if this node survives and the (possibly longer) minimum length still allows the range */
+  if ((errcode = prune_results(out, res, diff, pos, end, s_left, s_start - 1, minscore, minscorlen,
+			       k && (s_left + minscorlen < s_start))))
+    return errcode;
+  return prune_results(out, res, diff, pos, end, s_end + 1, s_right, minscore, minscorlen,
+		       k && (s_right > s_end + minscorlen));
+}
+
+int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **reads,
+		   const uint32_t *min_cover_arr, int ktuple_maxhit, int min_swatscor_arg,
+		   int min_swatscor_below_max_arg, UCHAR min_basqval, short target_depth, short max_depth,
+		   RMAPFLG_t rmapflg, const ScoreMatrix *scormtxp, const ResultFilter *rsfp,
+		   const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
+		   RMAPWAVE_EMITF *emitf, void *user)
+{
+  int errcode = ERRCODE_SUCCESS, rc, i;
+  UCHAR nskip;
+  const UCHAR ktup = hashTableGetKtupLen(htp, &nskip);
+  const SETSIZ_t *soffs;
+  const SEQNUM_t nseq = seqSetGetOffsets(ssp, &soffs);
+  RMAPBUFF *bufp = rmp->bfp;
+  size_t tot = 0, nreq = 0, nsw = 0, nbf = 0, nba = 0;
+  int any_qual = 0, have_pen = 0;
+  short matchscor = 0, mismatchscor = 0, gapinitscor = 0, gapextscor = 0;
+  size_t nres = 0, ndiff = 0;
+  uint64_t cells = 0;
+  
+  if (n < 1) return ERRCODE_SUCCESS;
+  if (!(rmapflg & RMAPFLG_SEQBYSEQ) || (rmapflg & (RMAPFLG_NOSHRTINFO | RMAPFLG_SPLIT | RMAPFLG_CMPLXW)))
+    return ERRCODE_ARGINVAL; /* caller falls back to the one-call path (still GPU) */
+
+  /* ------------------------------ wave 1: seeds -------------------------------------- */
+  WGROW(w->read_off, w->n_alloc, n, uint64_t);
+  w->n_alloc = 0; WGROW(w->read_len, w->n_alloc, n, uint32_t);
+  w->n_alloc = 0; WGROW(w->rd, w->n_alloc, n, WREAD);
+  w->n_alloc = 0; WGROW(w->info, w->n_alloc, 2 * (size_t) n, smb_seed_info);
+  w->n_alloc = (size_t) n;
+  for (i = 0; i < n; i++) {
+    SEQLEN_t len;
+    char cod;
+    seqFastqGetConstSequence(reads[i], &len, &cod);
+    if (cod != SEQCOD_MANGLED) return ERRCODE_SEQCODE;
+    w->read_off[i] = tot;
+    w->read_len[i] = len;
+    tot += len;
+    if (seqFastqGetConstQualityFactors(reads[i], NULL, NULL)) any_qual = 1;
+  }
+  if (tot + 16 > w->arena_alloc) {
+    size_t na = tot + tot / 2 + 4096;
+    w->arena = (uint8_t *) realloc(w->arena, na);
+    w->qual = (uint8_t *) realloc(w->qual, na);
+    if (!w->arena || !w->qual) return ERRCODE_NOMEM;
+    w->arena_alloc = na;
+  }
+  for (i = 0; i < n; i++) {
+    SEQLEN_t len;
+    const char *p = seqFastqGetConstSequence(reads[i], &len, NULL);
+    const char *q = seqFastqGetConstQualityFactors(reads[i], NULL, NULL);
+    memcpy(w->arena + w->read_off[i], p, len);
+    if (any_qual) {
+      if (q) memcpy(w->qual + w->read_off[i], q, len);
+      else memset(w->qual + w->read_off[i], 0xff, len); /* FASTA read: never below the threshold */
+    }
+  }
+  if ((rc = smb_arena_upload(w->ctx, w->arena, tot))) return gpu_fail(errmsgp, w, rc);
+  if ((rc = smb_seed_batch(w->ctx, w->read_off, w->read_len, n, any_qual ? w->qual : NULL,
+			   (uint32_t) ktuple_maxhit, HASH_MAXNHITS, min_basqval, 1, w->info,
+			   NULL, NULL, NULL, NULL, NULL, NULL)))
+    return gpu_fail(errmsgp, w, rc);
+  w->ms_k1 += smb_last_kernel_ms(w->ctx);
+
+  /* hit lists: every read x strand x reference sequence (collectHits, rmap.c:283-318) */
+  WGROW(w->req, w->req_alloc, 2 * (size_t) n * (size_t) nseq + 1, smb_hit_req);
+  w->req_alloc = 0; WGROW(w->list_first, w->req_alloc, 2 * (size_t) n * (size_t) nseq + 2, uint64_t);
+  w->req_alloc = 0; WGROW(w->req_err, w->req_alloc, 2 * (size_t) n * (size_t) nseq + 1, int32_t);
+  for (i = 0; i < n; i++) {
+    WREAD *rd = w->rd + i;
+    int st;
+    SEQNUM_t s;
+    memset(rd, 0, sizeof(*rd));
+    rd->qlen = w->read_len[i];
+    rd->errcode = w->info[2 * i].err ? w->info[2 * i].err : w->info[2 * i + 1].err;
+    rd->cand_first = 0;
+    if (rd->errcode) continue;
+    for (st = 0; st < 2; st++)
+      for (s = 0; s < nseq; s++) {
+	smb_hit_req *rq = w->req + nreq++;
+	memset(rq, 0, sizeof(*rq));
+	rq->lo = soffs[s]; rq->hi = soffs[s + 1];
+	rq->read = (uint32_t) i; rq->nhit_max = (uint32_t) ktuple_maxhit;
+	rq->strand = (uint8_t) st; rq->use_short = 1;
+      }
+  }
+  for (;;) {
+    size_t need = 0;
+    rc = smb_hits_batch(w->ctx, w->req, (int) nreq, 0, w->sqdat, w->sqdat_alloc, &need, w->list_first,
+			w->req_err);
+    if (rc == SMB_ERR_CAPACITY && need > w->sqdat_alloc) {
+      free(w->sqdat);
+      w->sqdat_alloc = need + need / 4 + 1024;
+      if (!(w->sqdat = (uint64_t *) malloc(w->sqdat_alloc * sizeof(uint64_t)))) return ERRCODE_NOMEM;
+      continue;
+    }
+    if (rc) return gpu_fail(errmsgp, w, rc);
+    break;
+  }
+  w->ms_k1 += smb_last_kernel_ms(w->ctx);
+
+  /* host: candidate selection with the reference's segment.c, per read */
+  w->ncand = 0;
+  nreq = 0;
+  for (i = 0; i < n; i++) {
+    WREAD *rd = w->rd + i;
+    uint32_t min_cover = min_cover_arr[i], mincov_below_max, min_ktup, n_candseg, c;
+    int st;
+    SEQNUM_t s;
+    short mismatchdiff;
+    rd->cand_first = (uint32_t) w->ncand;
+    if (rd->errcode) continue;
+    /* prelude of mapSingleRead (rmap.c:1258-1290) */
+    if (!have_pen) { /* penalties are those of the score matrix, identical for every read */
+      if ((errcode = scoreMakeProfileFromSequence(w->prof, reads[i], scormtxp))) return errcode;
+      matchscor = scoreProfileGetAvgPenalties(&mismatchscor, &gapinitscor, &gapextscor, w->prof);
+      if ((rc = smbShimSetScoring(w->ctx, w->prof))) return gpu_fail(errmsgp, w, rc);
+      have_pen = 1;
+    }
+    mismatchdiff = (short) (matchscor - mismatchscor);
+    if (mismatchdiff < 0 || gapextscor >= 0 || mismatchscor >= 0) return ERRCODE_ASSERT;
+    min_ktup = calcMinKtup(&min_cover, htp);
+    if (min_swatscor_below_max_arg < 0) {
+      mincov_below_max = rd->qlen - 1;
+    } else {
+      mincov_below_max = ((uint32_t) (min_swatscor_below_max_arg / mismatchdiff)) * nskip;
+      if (mincov_below_max < ktup || (rmapflg & RMAPFLG_BEST))
+	mincov_below_max = ktup + 2 * (nskip - 1);
+    }
+    smbShimHitInfoSet(rmp->mrp->hhiFp, w->info + 2 * i);
+    smbShimHitInfoSet(rmp->mrp->hhiRp, w->info + 2 * i + 1);
+    blankRMAPBUFF(bufp);
+    for (st = 0; st < 2; st++)
+      for (s = 0; s < nseq; s++, nreq++) {
+	const uint64_t f0 = w->list_first[nreq], f1 = w->list_first[nreq + 1];
+	if (rd->errcode) continue;
+	if (w->req_err[nreq] && w->req_err[nreq] != SMB_ERRCODE_ALLOCBOUNDARY) { rd->errcode = w->req_err[nreq]; continue; }
+	hashBlankHitList(bufp->hhlp);
+	if ((errcode = smbShimHitListSet(bufp->hhlp, w->sqdat + f0, (int) (f1 - f0), st, rd->qlen, ktup, nskip)))
+	  return errcode;
+	segLstBlank(bufp->sglp);
+	if ((errcode = segLstFillHits(bufp->sglp, min_ktup, bufp->hhlp)) ||
+	    (errcode = segAliCandsAddFast(bufp->sacp, bufp->qmp, bufp->sglp, min_cover, (int) s)))
+	  rd->errcode = errcode;
+      }
+    if (rd->errcode) { ERRMSGNO(errmsgp, rd->errcode); continue; }
+    if ((errcode = segAliCandsStats(bufp->sacp, mincov_below_max, rmp->mrp->hhiFp, rmp->mrp->hhiRp,
+				    target_depth, max_depth, (uint8_t) (rmapflg & RMAPFLG_SENSITIVE)))) {
+      rd->errcode = errcode;
+      ERRMSGNO(errmsgp, errcode);
+      continue;
+    }
+    {
+      uint32_t nseg_tot;
+      const uint32_t nseg = segAliCandsGetNumberOfSegments(bufp->sacp, NULL, NULL, NULL, NULL, &nseg_tot);
+      if (nseg > INT_MAX || nseg_tot > INT_MAX) { rd->errcode = ERRCODE_ASSERT; continue; }
+      rd->nseg = (int) nseg;
+      rd->nseg_tot = (int) nseg_tot;
+      rd->nhit = calcTotalHitNumStats(rmp->mrp, &rd->nhit_tot);
+      rd->reached_stats = 1;
+    }
+    /* candidate windows: what scoreRMAPCAND would fetch one by one (rmap.c:660-692) */
+    n_candseg = segAliCandsGetNumberOfSegments(bufp->sacp, &rd->curr_min_cover, NULL,
+					       rd->cover_deficit, rd->cover_deficit + 1, NULL);
+    WGROW(w->cand, w->cand_alloc, w->ncand + n_candseg + 1, WCAND);
+    for (c = 0; c < n_candseg; c++) {
+      WCAND *wc = w->cand + w->ncand;
+      RMAPCAND *cp = &wc->c;
+      uint8_t bitflags;
+      SEQLEN_t slen;
+      memset(wc, 0, sizeof(*wc));
+      errcode = segAliCandsCalcSegmentOffsets(&cp->qs, &cp->qe, &cp->rs, &cp->re, &cp->band_l, &cp->band_r,
+					      &cp->dqo, &cp->dro, &cp->sqidx, &bitflags, &wc->cover,
+					      0, rd->qlen, ssp, c, bufp->sacp);
+      if (!errcode && (cp->qe > INT_MAX || cp->re < cp->rs || cp->re - cp->rs > INT_MAX))
+	errcode = ERRCODE_OVERFLOW;
+      if (!errcode && (cp->sqidx < 0 || cp->sqidx >= nseq)) errcode = ERRCODE_ARGRANGE;
+      if (!errcode) {
+	slen = (SEQLEN_t) (soffs[cp->sqidx + 1] - soffs[cp->sqidx]);
+	if (cp->rs >= slen) errcode = ERRCODE_SEQOFFS; /* seqSetFetchSegmentBySequence, sequence.c:2756 */
+	else {
+	  uint64_t len = cp->re - cp->rs + 1;
+	  if (cp->rs + len > slen) len = slen - cp->rs;
+	  wc->reflen = (uint32_t) len;
+	  wc->refoff = soffs[cp->sqidx] + cp->rs;
+	}
+      }
+      if (errcode) { rd->errcode = errcode; ERRMSGNO(errmsgp, errcode); break; }
+      cp->flags = (RMAPFLG_t) ((bitflags & SEGCANDFLG_REVERSE) ? RMAPCANDFLG_REVERSE : 0);
+      cp->swscor = 0;
+      wc->k3task = -1;
+      wc->simd = (uint8_t) (rd->qlen >= MINLEN_QUERY_STRIPED &&
+			    ((SEQLEN_t) (cp->band_r - cp->band_l) * BWSCAL_QLEN) > rd->qlen &&
+			    cp->qs == 0 && cp->qe >= rd->qlen - 1);
+      w->ncand++;
+      rd->ncand++;
+    }
+    if (rd->errcode) { w->ncand = rd->cand_first; rd->ncand = 0; }
+  }
+
+  /* ------------------------------ wave 2: scores ------------------------------------- */
+  WGROW(w->swt, w->swt_alloc, w->ncand + 1, smb_sw_task);
+  w->swt_alloc = 0; WGROW(w->sw_score, w->swt_alloc, w->ncand + 1, int32_t);
+  w->swt_alloc = 0; WGROW(w->sw_err, w->swt_alloc, w->ncand + 1, int32_t);
+  WGROW(w->bft, w->bft_alloc, w->ncand + 1, smb_band_task);
+  w->bft_alloc = 0; WGROW(w->bf_score, w->bft_alloc, w->ncand + 1, int32_t);
+  w->bft_alloc = 0; WGROW(w->bf_err, w->bft_alloc, w->ncand + 1, int32_t);
+  for (i = 0; i < n; i++) {
+    WREAD *rd = w->rd + i;
+    uint32_t c;
+    for (c = 0; c < rd->ncand; c++) {
+      WCAND *wc = w->cand + rd->cand_first + c;
+      const uint32_t flags = SMB_TASK_REF_PACKED | ((wc->c.flags & RMAPCANDFLG_REVERSE) ? SMB_TASK_READ_REVCOMP : 0);
+      if (wc->simd) {
+	smb_sw_task *t = w->swt + nsw;
+	memset(t, 0, sizeof(*t));
+	t->read_off = w->read_off[i]; t->read_len = rd->qlen;
+	t->ref_off = wc->refoff; t->ref_len = wc->reflen; t->flags = flags;
+	wc->task = (int32_t) nsw++;
+	w->cells_k2 += (uint64_t) rd->qlen * wc->reflen;
+      } else {
+	smb_band_task *t = w->bft + nbf;
+	memset(t, 0, sizeof(*t));
+	t->read_off = w->read_off[i]; t->read_len = rd->qlen;
+	t->ref_off = wc->refoff; t->ref_len = wc->reflen; t->flags = flags;
+	t->l_edge = wc->c.band_l; t->r_edge = wc->c.band_r;
+	t->p_left = (int) wc->c.qs; t->p_right = (int) wc->c.qe;
+	t->u_left = 0; t->u_right = (int) wc->reflen - 1;
+	wc->task = (int32_t) nbf++;
+      }
+    }
+  }
+  if (nsw) {
+    if ((rc = smb_sw_score_batch(w->ctx, w->swt, (int) nsw, w->sw_score, w->sw_err))) return gpu_fail(errmsgp, w, rc);
+    w->ms_k2 += smb_last_kernel_ms(w->ctx);
+    w->n_k2 += nsw;
+    /* ERRCODE_SWATEXCEED -> banded fast variant (rmap.c:730-744) */
+    for (i = 0; i < n; i++) {
+      WREAD *rd = w->rd + i;
+      uint32_t c;
+      for (c = 0; c < rd->ncand; c++) {
+	WCAND *wc = w->cand + rd->cand_first + c;
+	if (wc->simd && w->sw_err[wc->task] == ERRCODE_SWATEXCEED) {
+	  smb_band_task *t = w->bft + nbf;
+	  memset(t, 0, sizeof(*t));
+	  t->read_off = w->read_off[i]; t->read_len = rd->qlen;
+	  t->ref_off = wc->refoff; t->ref_len = wc->reflen;
+	  t->flags = SMB_TASK_REF_PACKED | ((wc->c.flags & RMAPCANDFLG_REVERSE) ? SMB_TASK_READ_REVCOMP : 0);
+	  t->l_edge = wc->c.band_l; t->r_edge = wc->c.band_r;
+	  t->p_left = (int) wc->c.qs; t->p_right = (int) wc->c.qe;
+	  t->u_left = 0; t->u_right = (int) wc->reflen - 1;
+	  wc->simd = 0;
+	  wc->task = (int32_t) nbf++;
+	}
+      }
+    }
+  }
+  if (nbf) {
+    if ((rc = smb_band_score_batch(w->ctx, w->bft, (int) nbf, w->bf_score, w->bf_err))) return gpu_fail(errmsgp, w, rc);
+    w->ms_k2 += smb_last_kernel_ms(w->ctx);
+  }
+
+  /* host: replay of scoreRMAPCAND (rmap.c:646-786) and of mapSingleRead (rmap.c:1366-1400) */
+  WGROW(w->bat, w->bat_alloc, w->ncand + 1, smb_band_task);
+  w->bat_alloc = 0; WGROW(w->ba_err, w->bat_alloc, w->ncand + 1, int32_t);
+  for (i = 0; i < n; i++) {
+    WREAD *rd = w->rd + i;
+    const short mmscordiff = (short) (matchscor - mismatchscor), gapscordiff = (short) (matchscor - gapinitscor);
+    COVERAGE curr_min_cover = rd->curr_min_cover, max_cover = 0, min_cover = 0, dcov, cdf;
+    SWATSCOR max1 = 0, max2 = 0;
+    const SWATSCOR max_possible_swscor = (SWATSCOR) (rd->qlen * matchscor);
+    uint32_t cover_rank = 0, cover_rank_break = rd->ncand, c;
+    int min_swatscor = min_swatscor_arg, min_swatscor_below_max = min_swatscor_below_max_arg;
+    if (rd->errcode || !rd->reached_stats) continue;
+    if (mmscordiff < 1 || gapscordiff < 1) return ERRCODE_ASSERT;
+    for (c = 0; c < rd->ncand; c++) {
+      WCAND *wc = w->cand + rd->cand_first + c;
+      RMAPCAND *cp = &wc->c;
+      const COVERAGE cover = wc->cover;
+      int e;
+      if (cover < curr_min_cover) { curr_min_cover = cover; cover_rank++; }
+      if (cover_rank > cover_rank_break) break;
+      if (wc->simd) { e = w->sw_err[wc->task]; cp->swscor = w->sw_score[wc->task]; }
+      else { e = w->bf_err[wc->task]; cp->swscor = w->bf_score[wc->task]; }
+      if (e) { rd->errcode = e; break; }
+      cp->flags |= RMAPCANDFLG_SCORED;
+      cdf = rd->cover_deficit[(cp->flags & RMAPCANDFLG_REVERSE) ? 1 : 0];
+      if ((rmapflg & RMAPFLG_BEST) && (cover + cdf < min_cover)) break;
+      if (cp->swscor > max2) {
+	if (cp->swscor > max1) {
+	  max2 = max1;
+	  max1 = cp->swscor;
+	  if (rmapflg & RMAPFLG_BEST) {
+	    if (max1 + gapscordiff > max_possible_swscor)
+	      cover_rank_break = (max1 + mmscordiff > max_possible_swscor) ? 1 : 2;
+	  }
+	  if (cover + cdf > max_cover) max_cover = (cover > cdf) ? cover - cdf : 0;
+	} else {
+	  max2 = cp->swscor;
+	}
+	dcov = ((int) ((max1 - max2) / mmscordiff) + 1) * nskip;
+	if (dcov + cdf + min_cover < max_cover) min_cover = max_cover - dcov;
+      }
+    }
+    rd->nscored = c;
+    rd->max1scor = max1;
+    rd->max2scor = max2;
+    if (rd->errcode) { ERRMSGNO(errmsgp, rd->errcode); continue; }
+    if (max1 > max_possible_swscor) { rd->errcode = ERRCODE_ASSERT; ERRMSGNO(errmsgp, ERRCODE_ASSERT); continue; }
+    if (max1 < 1) continue;
+    rd->do_align = 1;
+    rd->scorlen_min = ktup + nskip;
+    rd->bandwidth_min = (max_possible_swscor - max1) / (-1 * gapextscor);
+    if (min_swatscor_below_max >= max1) min_swatscor_below_max = max1;
+    if (min_swatscor > max2 && max2 > 0) min_swatscor = max2;
+    if (min_swatscor_below_max >= 0) {
+      const SWATSCOR minswc = (max2 > 0) ? max2 : max1;
+      if (rmapflg & RMAPFLG_BEST) {
+	if (minswc > min_swatscor) min_swatscor = minswc;
+      } else if (min_swatscor + min_swatscor_below_max < max1) {
+	min_swatscor = max1 - min_swatscor_below_max;
+	if (min_swatscor > minswc) min_swatscor = minswc;
+      }
+    }
+    if (min_swatscor > rd->scorlen_min * matchscor && matchscor > 0) rd->scorlen_min = min_swatscor / matchscor;
+    rd->min_swatscor = min_swatscor;
+    /* K3 tasks: every scored candidate that passes the INITIAL threshold (rmap.c:833-835) */
+    for (c = 0; c < rd->nscored; c++) {
+      WCAND *wc = w->cand + rd->cand_first + c;
+      const RMAPCAND *cp = &wc->c;
+      smb_band_task *t;
+      int bw, band_l, band_r;
+      if ((cp->flags & RMAPCANDFLG_SCORED) && cp->swscor < min_swatscor) continue;
+      bw = cp->band_r - cp->band_l;
+      if (bw < rd->bandwidth_min) {
+	bw = (rd->bandwidth_min - bw + 1) / 2;
+	band_l = cp->band_l - bw;
+	band_r = cp->band_r + bw;
+      } else {
+	band_l = cp->band_l;
+	band_r = cp->band_r;
+      }
+      t = w->bat + nba;
+      memset(t, 0, sizeof(*t));
+      t->read_off = w->read_off[i]; t->read_len = rd->qlen;
+      t->ref_off = wc->refoff; t->ref_len = wc->reflen;
+      t->flags = SMB_TASK_REF_PACKED | ((cp->flags & RMAPCANDFLG_REVERSE) ? SMB_TASK_READ_REVCOMP : 0);
+      t->l_edge = band_l; t->r_edge = band_r;
+      t->p_left = (int) cp->qs; t->p_right = (int) cp->qe;
+      t->u_left = 0; t->u_right = (int) wc->reflen - 1;
+      t->minscore = min_swatscor; t->minscorlen = rd->scorlen_min;
+      wc->k3task = (int32_t) nba++;
+    }
+  }
+
+  /* ------------------------------ wave 3: alignments --------------------------------- */
+  if (nba) {
+    for (;;) {
+      if (w->res_alloc < nba + 16) {
+	free(w->res); free(w->res_first);
+	w->res_alloc = nba + nba / 2 + 64;
+	w->res = (smb_ali_result *) malloc(w->res_alloc * sizeof(smb_ali_result));
+	w->res_first = (uint32_t *) malloc((w->res_alloc + 2) * sizeof(uint32_t));
+	if (!w->res || !w->res_first) return ERRCODE_NOMEM;
+      }
+      if (w->diff_alloc < 32 * nba) {
+	free(w->diff);
+	w->diff_alloc = 48 * nba + 4096;
+	if (!(w->diff = (uint8_t *) malloc(w->diff_alloc))) return ERRCODE_NOMEM;
+      }
+      rc = smb_band_align_batch(w->ctx, w->bat, (int) nba, w->res, w->res_alloc, &nres, w->res_first,
+				w->diff, w->diff_alloc, &ndiff, w->ba_err, &cells);
+      if (rc == SMB_ERR_CAPACITY && (nres > w->res_alloc || ndiff > w->diff_alloc)) {
+	if (nres > w->res_alloc) {
+	  free(w->res);
+	  w->res_alloc = nres + 64;
+	  if (!(w->res = (smb_ali_result *) malloc(w->res_alloc * sizeof(smb_ali_result)))) return ERRCODE_NOMEM;
+	}
+	if (ndiff > w->diff_alloc) {
+	  free(w->diff);
+	  w->diff_alloc = ndiff + 4096;
+	  if (!(w->diff = (uint8_t *) malloc(w->diff_alloc))) return ERRCODE_NOMEM;
+	}
+	continue;
+      }
+      if (rc) return gpu_fail(errmsgp, w, rc);
+      break;
+    }
+    w->ms_k3 += smb_last_kernel_ms(w->ctx);
+    w->n_k3 += nba;
+    w->cells_k3 += cells;
+  }
+
+  /* host: replay of alignRMAPCANDFull (rmap.c:820-926), then results.c as in the reference */
+  for (i = 0; i < n; i++) {
+    WREAD *rd = w->rd + i;
+    ResultSet *rsp = rmp->rsrp;
+    uint32_t c;
+    resultSetBlank(rsp);
+    if (rd->errcode == ERRCODE_SHORTSEQ) { /* rmapSingle: too short to be hashed -> empty result set */
+      if ((errcode = (*emitf)(user, i, rsp))) return errcode;
+      continue;
+    }
+    if (rd->reached_stats)
+      resultSetAlignmentStats(rsp, rd->nseg, rd->nseg_tot, max_depth, rd->nhit, rd->nhit_tot);
+    if (!rd->errcode && rd->do_align) {
+      int min_swatscor = rd->min_swatscor;
+      SWATSCOR swatscor_2ndmax = 0;
+      for (c = 0; c < rd->nscored && !rd->errcode; c++) {
+	WCAND *wc = w->cand + rd->cand_first + c;
+	const RMAPCAND *cp = &wc->c;
+	int minscorlen = rd->scorlen_min;
+	uint32_t pos, end;
+	if ((cp->flags & RMAPCANDFLG_SCORED) && cp->swscor < min_swatscor) continue;
+	if (rmapflg & RMAPFLG_BEST) {
+	  resultSetGetMaxSwat(rsp, &swatscor_2ndmax);
+	  if (swatscor_2ndmax > min_swatscor) min_swatscor = swatscor_2ndmax;
+	}
+	if (wc->k3task < 0) { rd->errcode = ERRCODE_ASSERT; break; }
+	if (w->ba_err[wc->k3task]) { rd->errcode = w->ba_err[wc->k3task]; break; }
+	aliRsltSetReset(bufp->alirsltp);
+	/* aliSmiWatInBand (alignment.c:1569-1575) with the current threshold */
+	if (min_swatscor < 1 || matchscor <= 0) { rd->errcode = ERRCODE_ASSERT; break; }
+	if (minscorlen * matchscor < min_swatscor) minscorlen = min_swatscor / matchscor;
+	if (minscorlen < 5) { rd->errcode = ERRCODE_ASSERT; break; }
+	pos = w->res_first[wc->k3task];
+	end = w->res_first[wc->k3task + 1];
+	if ((errcode = prune_results(bufp->alirsltp, w->res, w->diff, &pos, end, 0, (int) wc->reflen - 1,
+				     min_swatscor, minscorlen, 1)))
+	  return errcode;
+	errcode = resultSetAddFromAli(rsp, bufp->alirsltp, cp->rs, 0, rd->qlen,
+				      (cp->sqidx == SEGCAND_UNKNOWN_SEQIDX) ? RESULTSET_UNKNOWN_SEQIDX : cp->sqidx,
+				      (char) (cp->flags & RMAPCANDFLG_REVERSE));
+	if (errcode) { rd->errcode = errcode; break; }
+      }
+      if (rd->errcode) ERRMSGNO(errmsgp, rd->errcode);
+      else {
+	/* profiles of this read for resultSetSortAndAssignSequence (rmap.c:1419-1428) */
+	seqFastqBlank(w->readRC);
+	if ((errcode = seqFastqAppendSegment(w->readRC, reads[i], 0, 0, 1, codecp)) ||
+	    (errcode = scoreMakeProfileFromSequence(w->prof, reads[i], scormtxp)) ||
+	    (errcode = scoreMakeProfileFromSequence(w->profRC, w->readRC, scormtxp)))
+	  return errcode;
+	errcode = resultSetSortAndAssignSequence(rsp, bufp->sqbfp, 0, reads[i], w->prof, w->profRC, ssp, codecp);
+	if (errcode) { rd->errcode = errcode; ERRMSGNO(errmsgp, errcode); }
+      }
+    }
+    if (!rd->errcode && (errcode = resultSetFilterResults(rsp, rsfp, reads[i])))
+      ERRMSGNO(errmsgp, errcode);
+    if ((errcode = (*emitf)(user, i, rsp))) return errcode;
+  }
+  w->n_reads += (uint64_t) n;
+  return ERRCODE_SUCCESS;
+}

@@ -1,0 +1,21 @@
+/* rmap_wave.h - batched single-end mapping (rmap_wave.c) */
+#ifndef SMALT_B200_RMAP_WAVE_H
+#define SMALT_B200_RMAP_WAVE_H
+#include "rmap.h"
+typedef struct RmapWave_ RmapWave;
+typedef int (RMAPWAVE_EMITF)(void *user, int i, const ResultSet *rsltp);
+RmapWave *rmapWaveCreate(const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
+			 const ScoreMatrix *scormtxp);
+void rmapWaveDelete(RmapWave *w);
+/* ms: device time of K1, K2(+K2'), K3; counts: reads, K2 tasks, K2 cells, K3 tasks, K3 cells */
+void rmapWaveGetStats(const RmapWave *w, double ms[3], uint64_t counts[5]);
+/* Maps reads[0..n) (SEQCOD_MANGLED) like n calls of rmapSingle (rmap.c:1648) would and calls
+ * emitf(user, i, result set) for i = 0..n-1 in order.  Returns ERRCODE_ARGINVAL if the flag
+ * combination is not handled by the wave path (the caller then uses rmapSingle per read). */
+int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **reads,
+		   const uint32_t *min_cover_arr, int ktuple_maxhit, int min_swatscor,
+		   int min_swatscor_below_max, unsigned char min_basqval, short target_depth, short max_depth,
+		   RMAPFLG_t rmapflg, const ScoreMatrix *scormtxp, const ResultFilter *rsfp,
+		   const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
+		   RMAPWAVE_EMITF *emitf, void *user);
+#endif

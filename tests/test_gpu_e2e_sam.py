@@ -1,0 +1,97 @@
+"""End to end: `smalt_b200 map` (reference driver + candidate selection + results/SAM writer,
+hot path on the GPU in waves) must print the same SAM as the reference's own CPU `smalt map`
+on the same index and reads - every line except the @PG command-line header."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle_lib import ROOT, ref_binary
+from seqgen import mutate, random_seq, revcomp
+from smalt_b200 import indexer
+
+pytestmark = pytest.mark.gpu
+B200 = os.path.join(ROOT, "smalt_b200", "bin", "smalt_b200")
+LET = np.frombuffer(b"ACGTNN", np.uint8)
+
+
+def _write_fastq(path, reads, fasta=False):
+    with open(path, "w") as f:
+        for i, r in enumerate(reads):
+            s = LET[r].tobytes().decode()
+            if fasta:
+                f.write(">r%d\n%s\n" % (i, s))
+            else:
+                f.write("@r%d\n%s\n+\n%s\n" % (i, s, "".join(chr(33 + 20 + (7 * i + j) % 21) for j in range(len(s)))))
+
+
+def _genome(rng, lens, repeats):
+    seqs = [random_seq(rng, n, p_n=0.0003) for n in lens]
+    if repeats:
+        unit = random_seq(rng, 500)
+        for s in seqs:
+            for _ in range(max(2, len(s) // 20000)):
+                p = int(rng.integers(0, len(s) - 500))
+                s[p:p + 500] = mutate(rng, unit, p_sub=0.02, p_ins=0, p_del=0)[:500]
+    return seqs
+
+
+def _reads(rng, seqs, n, qlen, err):
+    out = []
+    for i in range(n):
+        s = seqs[int(rng.integers(0, len(seqs)))]
+        L = qlen if isinstance(qlen, int) else int(rng.integers(qlen[0], qlen[1]))
+        L = min(L, len(s) - 1)
+        st = int(rng.integers(0, len(s) - L))
+        rd = mutate(rng, s[st:st + L].copy(), p_sub=err, p_ins=err / 8, p_del=err / 8)
+        if i % 2:
+            rd = revcomp(rd)
+        if i % 17 == 0:
+            rd[int(rng.integers(0, len(rd)))] = 5
+        if i % 50 == 0:
+            rd = random_seq(rng, len(rd))          # unmappable
+        if i % 97 == 0:
+            rd = rd[:int(rng.integers(5, 14))]     # shorter than k
+        out.append(np.ascontiguousarray(rd))
+    return out
+
+
+def _sam(path):
+    return [l for l in open(path).read().splitlines() if not l.startswith("@PG")]
+
+
+CASES = [
+    # name, seed, lens, k, s, nreads, qlen, err, repeats, fasta, threads
+    ("c1_like", 1, [1_000_000], 13, 6, 3000, 100, 0.01, False, False, 0),
+    ("c2_like_threads", 2, [400_000], 13, 6, 4000, 150, 0.02, True, False, 4),
+    ("multi_seq", 3, [60_011, 45_007, 30_000, 999], 11, 3, 2500, (40, 260), 0.03, True, False, 2),
+    ("fasta_noisy", 4, [150_000, 120_000], 13, 6, 2000, (60, 400), 0.08, True, True, 0),
+    ("short_reads", 5, [200_000], 11, 2, 2000, (20, 45), 0.02, False, False, 0),
+]
+
+
+@pytest.mark.skipif(ref_binary("smalt") is None or not os.path.exists(B200), reason="needs oracle/_ref and smalt_b200/bin")
+@pytest.mark.parametrize("name,seed,lens,k,s,nreads,qlen,err,repeats,fasta,threads", CASES)
+def test_sam_identical_to_reference(tmp_path, name, seed, lens, k, s, nreads, qlen, err, repeats, fasta, threads):
+    rng = np.random.default_rng(seed)
+    seqs = _genome(rng, lens, repeats)
+    pref = str(tmp_path / "idx")
+    indexer.write_smi(pref, indexer.build_index(seqs, k, s))
+    indexer.write_sma(pref, ["chr%d" % i for i in range(len(seqs))], seqs)
+    reads = _reads(rng, seqs, nreads, qlen, err)
+    fq = str(tmp_path / ("reads.fa" if fasta else "reads.fq"))
+    _write_fastq(fq, reads, fasta)
+    outs = {}
+    for tag, exe in (("ref", ref_binary("smalt")), ("b200", B200)):
+        out = str(tmp_path / (tag + ".sam"))
+        cmd = [exe, "map"] + (["-n", str(threads), "-O"] if threads else []) + ["-o", out, pref, fq]
+        env = dict(os.environ, SMALT_B200_BLOCK="1024")
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[tag] = _sam(out)
+    assert len(outs["ref"]) == len(outs["b200"])
+    diff = [(a, b) for a, b in zip(outs["ref"], outs["b200"]) if a != b]
+    assert not diff, "%d differing SAM lines, first:\n%s\n%s" % (len(diff), diff[0][0], diff[0][1])
+    mapped = sum(1 for l in outs["ref"] if not l.startswith("@") and not int(l.split("\t")[1]) & 4)
+    assert mapped > 0.8 * nreads * (0.5 if name == "short_reads" else 1)
