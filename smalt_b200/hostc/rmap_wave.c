@@ -437,10 +437,10 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
   for (i = 0; i < n; i++) {
     WREAD *rd = w->rd + i;
     const short mmscordiff = (short) (matchscor - mismatchscor), gapscordiff = (short) (matchscor - gapinitscor);
-    COVERAGE curr_min_cover = rd->curr_min_cover, max_cover = 0, min_cover = 0, dcov, cdf;
+    COVERAGE max_cover = 0, min_cover = 0, dcov, cdf;
     SWATSCOR max1 = 0, max2 = 0;
     const SWATSCOR max_possible_swscor = (SWATSCOR) (rd->qlen * matchscor);
-    uint32_t cover_rank = 0, cover_rank_break = rd->ncand, c;
+    uint32_t c;
     int min_swatscor = min_swatscor_arg, min_swatscor_below_max = min_swatscor_below_max_arg;
     if (rd->errcode || !rd->reached_stats) continue;
     if (mmscordiff < 1 || gapscordiff < 1) return ERRCODE_ASSERT;
@@ -449,8 +449,8 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
       RMAPCAND *cp = &wc->c;
       const COVERAGE cover = wc->cover;
       int e;
-      if (cover < curr_min_cover) { curr_min_cover = cover; cover_rank++; }
-      if (cover_rank > cover_rank_break) break;
+      /* (the cover-rank early stop of rmap.c:673-679 is compiled out in the reference:
+       * rmap_stop_candlist_early is not defined, rmap.h:39) */
       if (wc->simd) { e = w->sw_err[wc->task]; cp->swscor = w->sw_score[wc->task]; }
       else { e = w->bf_err[wc->task]; cp->swscor = w->bf_score[wc->task]; }
       if (e) { rd->errcode = e; break; }
@@ -461,10 +461,6 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
 	if (cp->swscor > max1) {
 	  max2 = max1;
 	  max1 = cp->swscor;
-	  if (rmapflg & RMAPFLG_BEST) {
-	    if (max1 + gapscordiff > max_possible_swscor)
-	      cover_rank_break = (max1 + mmscordiff > max_possible_swscor) ? 1 : 2;
-	  }
 	  if (cover + cdf > max_cover) max_cover = (cover > cdf) ? cover - cdf : 0;
 	} else {
 	  max2 = cp->swscor;
@@ -495,6 +491,10 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
     }
     if (min_swatscor > rd->scorlen_min * matchscor && matchscor > 0) rd->scorlen_min = min_swatscor / matchscor;
     rd->min_swatscor = min_swatscor;
+    if (getenv("SMALT_B200_DEBUG"))
+      fprintf(stderr, "DBG read %d ncand %u nscored %u max1 %d max2 %d min_swatscor %d scorlen_min %d bw_min %d nseg %d/%d nhit %u/%u\n",
+	      i, rd->ncand, rd->nscored, max1, max2, min_swatscor, rd->scorlen_min, rd->bandwidth_min, rd->nseg,
+	      rd->nseg_tot, rd->nhit, rd->nhit_tot);
     /* K3 tasks: every scored candidate that passes the INITIAL threshold (rmap.c:833-835) */
     for (c = 0; c < rd->nscored; c++) {
       WCAND *wc = w->cand + rd->cand_first + c;
@@ -599,6 +599,19 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
 	if ((errcode = prune_results(bufp->alirsltp, w->res, w->diff, &pos, end, 0, (int) wc->reflen - 1,
 				     min_swatscor, minscorlen, 1)))
 	  return errcode;
+	if (getenv("SMALT_B200_DEBUG")) {
+	  short k_, n_ = aliRsltSetGetSize(bufp->alirsltp);
+	  fprintf(stderr, "DBG  cand %u swscor %d cover %u rev %d rs %llu band %d %d minscore %d minscorlen %d raw %u kept %d:",
+		  c, cp->swscor, wc->cover, (int) (cp->flags & RMAPCANDFLG_REVERSE), (unsigned long long) cp->rs,
+		  w->bat[wc->k3task].l_edge, w->bat[wc->k3task].r_edge, min_swatscor, minscorlen,
+		  w->res_first[wc->k3task + 1] - w->res_first[wc->k3task], (int) n_);
+	  for (k_ = 0; k_ < n_; k_++) {
+	    int sc_, a_, b_, c_, d_;
+	    aliRsltSetFetchData(bufp->alirsltp, k_, &sc_, &a_, &b_, &c_, &d_, NULL);
+	    fprintf(stderr, " (%d q%d-%d r%d-%d)", sc_, a_, b_, c_, d_);
+	  }
+	  fputc('\n', stderr);
+	}
 	errcode = resultSetAddFromAli(rsp, bufp->alirsltp, cp->rs, 0, rd->qlen,
 				      (cp->sqidx == SEGCAND_UNKNOWN_SEQIDX) ? RESULTSET_UNKNOWN_SEQIDX : cp->sqidx,
 				      (char) (cp->flags & RMAPCANDFLG_REVERSE));
