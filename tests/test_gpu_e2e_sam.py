@@ -65,7 +65,8 @@ CASES = [
     # name, seed, lens, k, s, nreads, qlen, err, repeats, fasta, threads
     ("c1_like", 1, [1_000_000], 13, 6, 3000, 100, 0.01, False, False, 0),
     ("c2_like_threads", 2, [400_000], 13, 6, 4000, 150, 0.02, True, False, 4),
-    ("multi_seq", 3, [60_011, 45_007, 30_000, 999], 11, 3, 2500, (40, 260), 0.03, True, False, 2),
+    ("multi_seq", 3, [60_011, 45_007, 30_000, 999], 11, 3, 2500, (40, 260), 0.03, True, False, 0),
+    ("multi_seq_threads", 3, [60_011, 45_007, 30_000, 999], 11, 3, 2500, (40, 260), 0.03, True, False, 2),
     ("fasta_noisy", 4, [150_000, 120_000], 13, 6, 2000, (60, 400), 0.08, True, True, 0),
     ("short_reads", 5, [200_000], 11, 2, 2000, (20, 45), 0.02, False, False, 0),
 ]
@@ -92,6 +93,12 @@ def test_sam_identical_to_reference(tmp_path, name, seed, lens, k, s, nreads, ql
         outs[tag] = _sam(out)
     assert len(outs["ref"]) == len(outs["b200"])
     diff = [(a, b) for a, b in zip(outs["ref"], outs["b200"]) if a != b]
+    if threads:
+        # With worker threads the reference itself is not reproducible for reads with several
+        # equally good hits: the reported one is drawn with the process-wide drand48 stream, whose
+        # order depends on thread scheduling (two `smalt map -n 2 -O` runs differ from each other).
+        # Like the reference's own test/mthread_test.py:40-101 compare where MAPQ > 6.
+        diff = [(a, b) for a, b in diff if a.startswith("@") or int(a.split("\t")[4]) > 6 or int(b.split("\t")[4]) > 6]
     assert not diff, "%d differing SAM lines, first:\n%s\n%s" % (len(diff), diff[0][0], diff[0][1])
     mapped = sum(1 for l in outs["ref"] if not l.startswith("@") and not int(l.split("\t")[1]) & 4)
     assert mapped > 0.8 * nreads * (0.5 if name == "short_reads" else 1)
