@@ -31,6 +31,7 @@
  * helpers are reused and rmapCreate/rmapSingle/rmapPair keep working through the shim
  * (one GPU call per function call: slow, but still no CPU hot path).
  */
+#include <time.h>
 #include "rmap.c"
 #include "shim.h"
 #include "rmap_wave.h"
@@ -90,6 +91,7 @@ struct RmapWave_ {
   SeqFastq *readRC;
   /* statistics */
   double ms_k1, ms_k2, ms_k3;
+  double wall[8]; /* host wall seconds: stage, seed, hits, candidates, score, replay, align, results */
   uint64_t cells_k2, cells_k3, n_k2, n_k3, n_reads;
 };
 
@@ -127,12 +129,22 @@ void rmapWaveDelete(RmapWave *w)
   free(w);
 }
 
+void rmapWaveGetWall(const RmapWave *w, double wall[8]) { memcpy(wall, w->wall, sizeof(w->wall)); }
+
 void rmapWaveGetStats(const RmapWave *w, double ms[3], uint64_t counts[5])
 {
   ms[0] = w->ms_k1; ms[1] = w->ms_k2; ms[2] = w->ms_k3;
   counts[0] = w->n_reads; counts[1] = w->n_k2; counts[2] = w->cells_k2; counts[3] = w->n_k3;
   counts[4] = w->cells_k3;
 }
+
+static double wnow(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+#define WTICK(k) do { const double t_ = wnow(); w->wall[k] += t_ - tw; tw = t_; } while (0)
 
 static int gpu_fail(ErrMsg *errmsgp, const RmapWave *w, int rc)
 {
@@ -188,6 +200,7 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
   short matchscor = 0, mismatchscor = 0, gapinitscor = 0, gapextscor = 0;
   size_t nres = 0, ndiff = 0;
   uint64_t cells = 0;
+  double tw = wnow();
   
   if (n < 1) return ERRCODE_SUCCESS;
   if (!(rmapflg & RMAPFLG_SEQBYSEQ) || (rmapflg & (RMAPFLG_NOSHRTINFO | RMAPFLG_SPLIT | RMAPFLG_CMPLXW)))
@@ -226,12 +239,14 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
       else memset(w->qual + w->read_off[i], 0xff, len); /* FASTA read: never below the threshold */
     }
   }
+  WTICK(0);
   if ((rc = smb_arena_upload(w->ctx, w->arena, tot))) return gpu_fail(errmsgp, w, rc);
   if ((rc = smb_seed_batch(w->ctx, w->read_off, w->read_len, n, any_qual ? w->qual : NULL,
 			   (uint32_t) ktuple_maxhit, HASH_MAXNHITS, min_basqval, 1, w->info,
 			   NULL, NULL, NULL, NULL, NULL, NULL)))
     return gpu_fail(errmsgp, w, rc);
   w->ms_k1 += smb_last_kernel_ms(w->ctx);
+  WTICK(1);
 
   /* hit lists: every read x strand x reference sequence (collectHits, rmap.c:283-318) */
   WGROW(w->req, w->req_alloc, 2 * (size_t) n * (size_t) nseq + 1, smb_hit_req);
@@ -269,6 +284,7 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
     break;
   }
   w->ms_k1 += smb_last_kernel_ms(w->ctx);
+  WTICK(2);
 
   /* host: candidate selection with the reference's segment.c, per read */
   w->ncand = 0;
@@ -369,6 +385,7 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
     if (rd->errcode) { w->ncand = rd->cand_first; rd->ncand = 0; }
   }
 
+  WTICK(3);
   /* ------------------------------ wave 2: scores ------------------------------------- */
   WGROW(w->swt, w->swt_alloc, w->ncand + 1, smb_sw_task);
   w->swt_alloc = 0; WGROW(w->sw_score, w->swt_alloc, w->ncand + 1, int32_t);
@@ -431,6 +448,7 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
     w->ms_k2 += smb_last_kernel_ms(w->ctx);
   }
 
+  WTICK(4);
   /* host: replay of scoreRMAPCAND (rmap.c:646-786) and of mapSingleRead (rmap.c:1366-1400) */
   WGROW(w->bat, w->bat_alloc, w->ncand + 1, smb_band_task);
   w->bat_alloc = 0; WGROW(w->ba_err, w->bat_alloc, w->ncand + 1, int32_t);
@@ -524,6 +542,7 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
     }
   }
 
+  WTICK(5);
   /* ------------------------------ wave 3: alignments --------------------------------- */
   if (nba) {
     for (;;) {
@@ -562,6 +581,7 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
     w->cells_k3 += cells;
   }
 
+  WTICK(6);
   /* host: replay of alignRMAPCANDFull (rmap.c:820-926), then results.c as in the reference */
   for (i = 0; i < n; i++) {
     WREAD *rd = w->rd + i;
@@ -633,6 +653,7 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
       ERRMSGNO(errmsgp, errcode);
     if ((errcode = (*emitf)(user, i, rsp))) return errcode;
   }
+  WTICK(7);
   w->n_reads += (uint64_t) n;
   return ERRCODE_SUCCESS;
 }

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
+#include <time.h>
 
 #include "elib.h"
 #include "sequence.h"
@@ -42,6 +43,14 @@ static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 static smb_ctx *g_root;             /* owns index + packed reference */
 static const HashTable *g_root_htp; /* table uploaded to g_root */
 static int g_device = -1;
+
+static double shim_now(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+#define SHIM_TIMING(what, t0) do { if (getenv("SMALT_B200_TIMING")) fprintf(stderr, "smalt_b200 timing: %s %.3f s\n", what, shim_now() - (t0)); } while (0)
 
 static void shim_die(const char *what)
 {
@@ -119,7 +128,10 @@ int smbShimInit(const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
   int errcode = 0;
   pthread_mutex_lock(&g_lock);
   if (!g_root) {
-    if ((errcode = smb_ctx_create(&g_root, shim_device()))) {
+    const double t0 = shim_now();
+    errcode = smb_ctx_create(&g_root, shim_device());
+    SHIM_TIMING("root context (CUDA init)", t0);
+    if (errcode) {
       pthread_mutex_unlock(&g_lock);
       fprintf(stderr, "smalt_b200: cannot create a CUDA context on device %d (error %d); "
 	      "there is no CPU fallback\n", shim_device(), errcode);
@@ -128,8 +140,12 @@ int smbShimInit(const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
     (void) scormtxp;
   }
   if (htp && g_root_htp != htp) {
+    double t0 = shim_now();
     if (!(errcode = upload_index(g_root, htp))) g_root_htp = htp;
+    SHIM_TIMING("index upload", t0);
+    t0 = shim_now();
     if (!errcode && ssp) errcode = upload_refseq(g_root, ssp, codecp);
+    SHIM_TIMING("reference pack + upload", t0);
   }
   pthread_mutex_unlock(&g_lock);
   if (errcode) fprintf(stderr, "smalt_b200: GPU upload failed: %s\n", smb_last_error(g_root));
@@ -142,7 +158,12 @@ int smbShimWorkerCtx(smb_ctx **ctxp, const ScoreMatrix *scormtxp)
 {
   int errcode;
   if (!g_root) return ERRCODE_ASSERT;
-  if ((errcode = smb_ctx_create(ctxp, shim_device()))) return ERRCODE_FAILURE;
+  {
+    const double t0 = shim_now();
+    errcode = smb_ctx_create(ctxp, shim_device());
+    SHIM_TIMING("worker context", t0);
+  }
+  if (errcode) return ERRCODE_FAILURE;
   if ((errcode = smb_ctx_share_index(*ctxp, g_root))) return errcode;
   (void) scormtxp; /* penalties are set per block from the read profiles (smbShimSetScoring) */
   return ERRCODE_SUCCESS;
