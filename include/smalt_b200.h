@@ -80,6 +80,17 @@ int smb_last_kernel_launches(const smb_ctx *ctx);
 /* total kernels launched by this context since creation */
 long long smb_total_kernel_launches(const smb_ctx *ctx);
 
+/* process-wide totals over all contexts: kernels launched, bytes copied host->device and
+ * device->host by this library */
+void smb_process_counters(unsigned long long *launches, unsigned long long *h2d_bytes,
+			  unsigned long long *d2h_bytes);
+
+/* Page-locked host memory for the buffers that cross this ABI (reads, task lists, outputs).
+ * Any host pointer is accepted by every entry point; buffers from smb_host_alloc make the
+ * host<->device copies asynchronous DMA transfers instead of staged copies.  NULL on failure. */
+void *smb_host_alloc(size_t nbytes);
+void smb_host_free(void *p);
+
 /* Makes `dst` use the index and packed reference already uploaded to `src`
  * (same device) instead of holding its own copy: one resident copy per GPU,
  * one context (stream + scratch buffers) per host worker thread. */

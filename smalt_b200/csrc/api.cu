@@ -1,6 +1,7 @@
 // api.cu - the C ABI of include/smalt_b200.h: context, device buffers, batch entry points.
 #include "common.cuh"
 #include "band.h"
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -34,6 +35,27 @@ struct DevBuf {  // grow-only device buffer
   template <class T> T *as() const { return (T *)p; }
 };
 
+struct HostBuf {  // grow-only pinned host staging buffer
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T *as() const { return (T *)p; }
+};
+
 }  // namespace
 
 struct smb_ctx {
@@ -41,6 +63,9 @@ struct smb_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_done = nullptr;  // blocking-sync event: waiting host threads sleep instead of spinning
+  HostBuf stage;                  // pinned staging for the library's own host-side arrays
+  DevBuf cmp;                     // K3 output compaction scratch
   Scoring sc;
   SeqSrc src{nullptr, nullptr, 0};
   DevBuf arena, packed, tasks, out_a, out_b, scratch, dirs, diff, offs;
@@ -61,6 +86,19 @@ struct smb_ctx {
   std::string err;
 };
 
+// process-wide traffic counters (all contexts): what bench.py reports as h2d/d2h bytes and launches
+static std::atomic<unsigned long long> g_h2d_bytes{0}, g_d2h_bytes{0};
+static std::atomic<long long> g_launches{0};
+
+static inline cudaError_t h2d(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+  g_h2d_bytes += bytes;
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+}
+static inline cudaError_t d2h(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+  g_d2h_bytes += bytes;
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+}
+
 static int fail(smb_ctx *c, int code, const char *fmt, ...) {
   char buf[512];
   va_list ap;
@@ -78,6 +116,14 @@ static int fail(smb_ctx *c, int code, const char *fmt, ...) {
       return fail(ctx, SMB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
                   __FILE__, __LINE__);                                                   \
   } while (0)
+
+// Waits for the context's stream.  Uses a blocking-sync event so that a host worker thread
+// yields its core while the GPU works (one context per host thread, more threads than cores).
+static cudaError_t ctx_sync(smb_ctx *ctx) {
+  cudaError_t e = cudaEventRecord(ctx->ev_done, ctx->stream);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ctx->ev_done);
+}
 
 static void make_scoring(Scoring &sc, int match, int mismatch, int gapopen, int gapext) {
   sc.match = match;
@@ -109,7 +155,8 @@ int smb_ctx_create(smb_ctx **out, int device) {
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_done, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return SMB_ERR_CUDA;
   }
@@ -126,8 +173,10 @@ void smb_ctx_destroy(smb_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf *bufs[] = {&ctx->arena, &ctx->packed, &ctx->tasks, &ctx->out_a, &ctx->out_b,
                     &ctx->scratch, &ctx->dirs, &ctx->diff, &ctx->offs, &ctx->index, &ctx->qualbuf,
-                    &ctx->seed_meta, &ctx->seed_u32, &ctx->seed_u8, &ctx->hit_meta, &ctx->hit_data};
+                    &ctx->seed_meta, &ctx->seed_u32, &ctx->seed_u8, &ctx->hit_meta, &ctx->hit_data, &ctx->cmp};
   for (DevBuf *b : bufs) b->release();
+  ctx->stage.release();
+  if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -138,6 +187,24 @@ const char *smb_last_error(const smb_ctx *ctx) { return ctx ? ctx->err.c_str() :
 float smb_last_kernel_ms(const smb_ctx *ctx) { return ctx ? ctx->last_ms : 0.f; }
 int smb_last_kernel_launches(const smb_ctx *ctx) { return ctx ? ctx->last_launches : 0; }
 long long smb_total_kernel_launches(const smb_ctx *ctx) { return ctx ? ctx->total_launches : 0; }
+void smb_process_counters(unsigned long long *launches, unsigned long long *h2d_bytes, unsigned long long *d2h_bytes) {
+  if (launches) *launches = (unsigned long long)g_launches.load();
+  if (h2d_bytes) *h2d_bytes = g_h2d_bytes.load();
+  if (d2h_bytes) *d2h_bytes = g_d2h_bytes.load();
+}
+
+void *smb_host_alloc(size_t nbytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, nbytes ? nbytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void smb_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
 
 int smb_set_scoring(smb_ctx *ctx, int match, int mismatch, int gapopen, int gapext) {
   if (!ctx) return SMB_ERR_ARG;
@@ -171,7 +238,7 @@ int smb_int_peak(smb_ctx *ctx, double gops[3]) {
       CU(cudaEventRecord(ctx->ev0, st));
       CU(run_int_peak(mode, ctx->sm_count, ctx->scratch.as<int>(), iters, st, &ops));
       CU(cudaEventRecord(ctx->ev1, st));
-      CU(cudaStreamSynchronize(st));
+      CU(ctx_sync(ctx));
       float ms = 0.f;
       CU(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
       ++ctx->total_launches;
@@ -186,8 +253,8 @@ int smb_arena_upload(smb_ctx *ctx, const uint8_t *codes, size_t nbytes) {
   if (!ctx || (!codes && nbytes)) return SMB_ERR_ARG;
   cudaSetDevice(ctx->device);
   CU(ctx->arena.ensure(nbytes + 16));
-  CU(cudaMemcpyAsync(ctx->arena.p, codes, nbytes, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(h2d(ctx->arena.p, codes, nbytes, ctx->stream));
+  CU(ctx_sync(ctx));
   ctx->arena_bytes = nbytes;
   ctx->src.arena = ctx->arena.as<uint8_t>();
   return SMB_OK;
@@ -198,8 +265,8 @@ int smb_refseq_upload(smb_ctx *ctx, const uint32_t *words, size_t nwords, uint64
   if (!ctx || !words || nwords * 10u < nbases) return SMB_ERR_ARG;
   cudaSetDevice(ctx->device);
   CU(ctx->packed.ensure(nwords * sizeof(uint32_t) + 16));
-  CU(cudaMemcpyAsync(ctx->packed.p, words, nwords * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(h2d(ctx->packed.p, words, nwords * sizeof(uint32_t), ctx->stream));
+  CU(ctx_sync(ctx));
   ctx->src.packed = ctx->packed.as<uint32_t>();
   ctx->src.packed_nbases = nbases;
   ctx->seq_offs.clear();
@@ -238,7 +305,7 @@ int smb_sw_score_batch(smb_ctx *ctx, const smb_sw_task *tasks, int ntasks, int32
   cudaStream_t st = ctx->stream;
   CU(ctx->tasks.ensure((size_t)ntasks * sizeof(smb_sw_task)));
   CU(ctx->out_a.ensure((size_t)ntasks * 2 * sizeof(int32_t)));
-  CU(cudaMemcpyAsync(ctx->tasks.p, tasks, (size_t)ntasks * sizeof(smb_sw_task), cudaMemcpyHostToDevice, st));
+  CU(h2d(ctx->tasks.p, tasks, (size_t)ntasks * sizeof(smb_sw_task), st));
   int32_t *d_scores = ctx->out_a.as<int32_t>(), *d_errs = d_scores + ntasks;
   int nl = 0;
   SwPlan plan;
@@ -246,17 +313,18 @@ int smb_sw_score_batch(smb_ctx *ctx, const smb_sw_task *tasks, int ntasks, int32
   const size_t off_order = 256, off_strip = (off_order + (size_t)ntasks * sizeof(int) + 255) & ~(size_t)255;
   CU(ctx->scratch.ensure(off_strip + plan.strip_bytes + 256));
   char *sb = ctx->scratch.as<char>();
-  CU(cudaMemcpyAsync(sb + off_order, plan.order.data(), (size_t)ntasks * sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(h2d(sb + off_order, plan.order.data(), (size_t)ntasks * sizeof(int), st));
   CU(cudaEventRecord(ctx->ev0, st));
   CU(launch_sw_score(ctx->sc, ctx->src, ctx->tasks.as<smb_sw_task>(), plan, (int *)sb, (const int *)(sb + off_order),
                      sb + off_strip, d_scores, d_errs, st, &nl));
   CU(cudaEventRecord(ctx->ev1, st));
-  CU(cudaMemcpyAsync(scores, d_scores, (size_t)ntasks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(errs, d_errs, (size_t)ntasks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CU(d2h(scores, d_scores, (size_t)ntasks * sizeof(int32_t), st));
+  CU(d2h(errs, d_errs, (size_t)ntasks * sizeof(int32_t), st));
+  CU(ctx_sync(ctx));
   CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
   ctx->last_launches = nl;
   ctx->total_launches += nl;
+  g_launches += nl;
   return SMB_OK;
 }
 
@@ -276,11 +344,11 @@ int smb_band_score_batch(smb_ctx *ctx, const smb_band_task *tasks, int ntasks, i
   cudaStream_t st = ctx->stream;
   CU(ctx->tasks.ensure((size_t)ntasks * sizeof(smb_band_task)));
   CU(ctx->out_a.ensure((size_t)ntasks * 2 * sizeof(int32_t) + 64));
-  CU(cudaMemcpyAsync(ctx->tasks.p, tasks, (size_t)ntasks * sizeof(smb_band_task), cudaMemcpyHostToDevice, st));
+  CU(h2d(ctx->tasks.p, tasks, (size_t)ntasks * sizeof(smb_band_task), st));
   int32_t *d_scores = ctx->out_a.as<int32_t>(), *d_errs = d_scores + ntasks;
   unsigned long long *d_cells = (unsigned long long *)(((uintptr_t)(d_errs + ntasks) + 15) & ~(uintptr_t)15);
   CU(cudaMemsetAsync(d_cells, 0, sizeof(unsigned long long), st));
-  BandOut bo{nullptr, nullptr, nullptr, d_errs, d_cells};
+  BandOut bo{nullptr, nullptr, nullptr, d_errs, d_cells, nullptr};
   int nl = 0;
   BandPlan plan;
   plan_band(tasks, ntasks, false, plan);
@@ -288,17 +356,18 @@ int smb_band_score_batch(smb_ctx *ctx, const smb_band_task *tasks, int ntasks, i
   CU(ctx->scratch.ensure((size_t)ntasks * sizeof(int) + gring_words * sizeof(uint32_t) + 512));
   int *d_order = ctx->scratch.as<int>();
   uint32_t *d_gring = (uint32_t *)(ctx->scratch.as<char>() + (((size_t)ntasks * sizeof(int) + 255) & ~(size_t)255));
-  CU(cudaMemcpyAsync(d_order, plan.order.data(), (size_t)ntasks * sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(h2d(d_order, plan.order.data(), (size_t)ntasks * sizeof(int), st));
   CU(cudaEventRecord(ctx->ev0, st));
   CU(launch_band(ctx->sc, ctx->src, ctx->tasks.as<smb_band_task>(), plan, d_order, false, d_scores, bo, 0,
                  nullptr, nullptr, nullptr, nullptr, d_gring, st, &nl));
   CU(cudaEventRecord(ctx->ev1, st));
-  CU(cudaMemcpyAsync(scores, d_scores, (size_t)ntasks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(errs, d_errs, (size_t)ntasks * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CU(d2h(scores, d_scores, (size_t)ntasks * sizeof(int32_t), st));
+  CU(d2h(errs, d_errs, (size_t)ntasks * sizeof(int32_t), st));
+  CU(ctx_sync(ctx));
   CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
   ctx->last_launches = nl;
   ctx->total_launches += nl;
+  g_launches += nl;
   return SMB_OK;
 }
 
@@ -341,24 +410,24 @@ static int band_align_pass(smb_ctx *ctx, const smb_band_task *tasks, const std::
   uint64_t *d_dir_off = ctx->offs.as<uint64_t>();
   uint64_t *d_diff_off = d_dir_off + (n + 1);
   uint32_t *d_diff_cap = (uint32_t *)(d_diff_off + (n + 1));
-  CU(cudaMemcpyAsync(ctx->tasks.p, sub.data(), (size_t)n * sizeof(smb_band_task), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_dir_off, dir_off.data(), (size_t)(n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_diff_off, diff_off.data(), (size_t)(n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_diff_cap, diff_cap.data(), (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  CU(h2d(ctx->tasks.p, sub.data(), (size_t)n * sizeof(smb_band_task), st));
+  CU(h2d(d_dir_off, dir_off.data(), (size_t)(n + 1) * sizeof(uint64_t), st));
+  CU(h2d(d_diff_off, diff_off.data(), (size_t)(n + 1) * sizeof(uint64_t), st));
+  CU(h2d(d_diff_cap, diff_cap.data(), (size_t)n * sizeof(uint32_t), st));
   char *ob = ctx->out_b.as<char>();
   smb_ali_result *d_res = (smb_ali_result *)ob;
   uint32_t *d_nres = (uint32_t *)(ob + res_bytes);
   int32_t *d_errs = (int32_t *)(d_nres + n);
   unsigned long long *d_cells = (unsigned long long *)(((uintptr_t)(d_errs + n) + 15) & ~(uintptr_t)15);
   CU(cudaMemsetAsync(d_cells, 0, sizeof(unsigned long long), st));
-  BandOut bo{d_res, d_nres, ctx->diff.as<uint8_t>(), d_errs, d_cells};
+  BandOut bo{d_res, d_nres, ctx->diff.as<uint8_t>(), d_errs, d_cells, nullptr};
   BandPlan plan;
   plan_band(sub.data(), n, true, plan);
   const size_t gring_words = band_gring_words(plan);
   CU(ctx->scratch.ensure((size_t)n * sizeof(int) + gring_words * sizeof(uint32_t) + 512));
   int *d_order = ctx->scratch.as<int>();
   uint32_t *d_gring = (uint32_t *)(ctx->scratch.as<char>() + (((size_t)n * sizeof(int) + 255) & ~(size_t)255));
-  CU(cudaMemcpyAsync(d_order, plan.order.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  CU(h2d(d_order, plan.order.data(), (size_t)n * sizeof(int), st));
   CU(cudaEventRecord(ctx->ev0, st));
   CU(launch_band(ctx->sc, ctx->src, ctx->tasks.as<smb_band_task>(), plan, d_order, true, nullptr, bo, max_res,
                  d_dir_off, ctx->dirs.as<uint32_t>(), d_diff_off, d_diff_cap, d_gring, st, nlaunch));
@@ -368,16 +437,135 @@ static int band_align_pass(smb_ctx *ctx, const smb_band_task *tasks, const std::
   h_errs.resize((size_t)n);
   h_diff.resize(diff_off[(size_t)n]);
   unsigned long long c = 0;
-  CU(cudaMemcpyAsync(h_res.data(), d_res, res_bytes, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(h_nres.data(), d_nres, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(h_errs.data(), d_errs, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(h_diff.data(), ctx->diff.p, diff_off[(size_t)n], cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(&c, d_cells, sizeof c, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CU(d2h(h_res.data(), d_res, res_bytes, st));
+  CU(d2h(h_nres.data(), d_nres, (size_t)n * sizeof(uint32_t), st));
+  CU(d2h(h_errs.data(), d_errs, (size_t)n * sizeof(int32_t), st));
+  CU(d2h(h_diff.data(), ctx->diff.p, diff_off[(size_t)n], st));
+  CU(d2h(&c, d_cells, sizeof c, st));
+  CU(ctx_sync(ctx));
   float m = 0.f;
   CU(cudaEventElapsedTime(&m, ctx->ev0, ctx->ev1));
   *ms += m;
   *cells += c;
+  return SMB_OK;
+}
+
+// Fast path of smb_band_align_batch: one kernel pass with the default slot capacities, dense
+// output assembled on the device (compact.cu).  Returns 1 (and leaves the outputs untouched)
+// when a task ran out of slot capacity - the caller then takes the multi-pass path.
+static int band_align_fast(smb_ctx *ctx, const smb_band_task *tasks, int ntasks, smb_ali_result *results,
+                           size_t max_results, size_t *nresults, uint32_t *first_result, uint8_t *diffstr,
+                           size_t max_diffbytes, size_t *ndiffbytes, int32_t *errs, uint64_t *ncells) {
+  const int n = ntasks, max_res = 4;
+  cudaStream_t st = ctx->stream;
+  // host-side geometry: direction strip and DiffStr slot of every task
+  const size_t stage_bytes = (size_t)(n + 1) * 2 * sizeof(uint64_t) + (size_t)n * 2 * sizeof(uint32_t) + 64;
+  const size_t stage_tail = (stage_bytes + 63) & ~(size_t)63;  // totals read back behind the arrays
+  CU(ctx->stage.ensure(stage_tail + 64));
+  uint64_t *dir_off = ctx->stage.as<uint64_t>();
+  uint64_t *diff_off = dir_off + (n + 1);
+  uint32_t *diff_cap = (uint32_t *)(diff_off + (n + 1));
+  int *h_order = (int *)(diff_cap + n);
+  dir_off[0] = diff_off[0] = 0;
+  for (int i = 0; i < n; ++i) {
+    const smb_band_task &t = tasks[i];
+    Band b;
+    uint64_t words = 2;
+    if (!band_init(b, t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
+                   (int)t.ref_len)) {
+      const int bw0 = t.r_edge - t.l_edge + 1;
+      int w = (bw0 <= 0) ? (b.q_len - b.q_left) : bw0;
+      if (w < 1) w = 1;
+      words = ((uint64_t)w * (uint64_t)t.ref_len) / 16u + 4u;
+    }
+    dir_off[i + 1] = dir_off[i] + words;
+    // final DiffStr area: one byte per aligned column at most, plus slack for several results
+    const uint32_t cap = t.read_len + t.ref_len + 64u;
+    diff_cap[i] = cap;
+    diff_off[i + 1] = diff_off[i] + cap + (t.read_len + t.ref_len + 8u);
+  }
+  if (dir_off[n] > ((uint64_t)1 << 30)) return 1;  // long-read sized batch: chunked multi-pass path
+  BandPlan plan;
+  plan_band(tasks, n, true, plan);
+  memcpy(h_order, plan.order.data(), (size_t)n * sizeof(int));
+
+  const size_t res_bytes = (size_t)n * max_res * sizeof(smb_ali_result);
+  const size_t outa = res_bytes + (size_t)n * (2 * sizeof(uint32_t) + sizeof(int32_t)) + 64;
+  CU(ctx->tasks.ensure((size_t)n * sizeof(smb_band_task)));
+  CU(ctx->out_b.ensure(outa));
+  CU(ctx->dirs.ensure(dir_off[n] * sizeof(uint32_t)));
+  CU(ctx->diff.ensure(diff_off[n]));
+  CU(ctx->offs.ensure(stage_bytes));
+  CU(h2d(ctx->tasks.p, tasks, (size_t)n * sizeof(smb_band_task), st));
+  CU(h2d(ctx->offs.p, ctx->stage.p, stage_bytes, st));
+  uint64_t *d_dir_off = ctx->offs.as<uint64_t>();
+  uint64_t *d_diff_off = d_dir_off + (n + 1);
+  uint32_t *d_diff_cap = (uint32_t *)(d_diff_off + (n + 1));
+  int *d_order = (int *)(d_diff_cap + n);
+  char *ob = ctx->out_b.as<char>();
+  smb_ali_result *d_res = (smb_ali_result *)ob;
+  uint32_t *d_nres = (uint32_t *)(ob + res_bytes);
+  uint32_t *d_dused = d_nres + n;
+  int32_t *d_errs = (int32_t *)(d_dused + n);
+  unsigned long long *d_cells = (unsigned long long *)(((uintptr_t)(d_errs + n) + 15) & ~(uintptr_t)15);
+  CU(cudaMemsetAsync(d_cells, 0, sizeof(unsigned long long), st));
+  BandOut bo{d_res, d_nres, ctx->diff.as<uint8_t>(), d_errs, d_cells, d_dused};
+  const size_t gring_words = band_gring_words(plan);
+  CU(ctx->scratch.ensure(gring_words * sizeof(uint32_t) + 512));
+  // compaction scratch: tile sums, totals, per-task offsets
+  const int ntiles = compact_tiles(n);
+  const size_t cmp_bytes = (size_t)ntiles * 2 * 8 + 64 + (size_t)(n + 1) * 4 + 64 + (size_t)n * 8 + 64;
+  CU(ctx->cmp.ensure(cmp_bytes));
+  char *cb = ctx->cmp.as<char>();
+  unsigned long long *d_tile_res = (unsigned long long *)cb;
+  unsigned long long *d_tile_diff = d_tile_res + ntiles;
+  CompactTotals *d_tot = (CompactTotals *)(d_tile_diff + ntiles);
+  unsigned long long *d_diff_first = (unsigned long long *)(((uintptr_t)(d_tot + 1) + 63) & ~(uintptr_t)63);
+  uint32_t *d_first = (uint32_t *)(d_diff_first + n);
+  int nl = 0;
+  CU(cudaEventRecord(ctx->ev0, st));
+  CU(launch_band(ctx->sc, ctx->src, ctx->tasks.as<smb_band_task>(), plan, d_order, true, nullptr, bo, max_res,
+                 d_dir_off, ctx->dirs.as<uint32_t>(), d_diff_off, d_diff_cap, ctx->scratch.as<uint32_t>(), st, &nl));
+  CU(launch_compact_scan(d_nres, d_dused, d_errs, n, d_tile_res, d_tile_diff, d_tot, d_first, d_diff_first, st, &nl));
+  CU(cudaEventRecord(ctx->ev1, st));
+  CompactTotals *h_tot = (CompactTotals *)((char *)ctx->stage.p + stage_tail);
+  unsigned long long *h_cells = (unsigned long long *)(h_tot + 1);
+  CU(d2h(h_tot, d_tot, sizeof(CompactTotals), st));
+  CU(d2h(h_cells, d_cells, sizeof(unsigned long long), st));
+  CU(ctx_sync(ctx));
+  float ms0 = 0.f, ms1 = 0.f;
+  CU(cudaEventElapsedTime(&ms0, ctx->ev0, ctx->ev1));
+  ctx->last_ms += ms0;
+  ctx->last_launches += nl;
+  ctx->total_launches += nl;
+  g_launches += nl;
+  if (h_tot->capacity_flag) return 1;
+  const size_t nr = (size_t)h_tot->nresults, nd = (size_t)h_tot->ndiff;
+  if (ncells) *ncells = *h_cells;
+  *nresults = nr;
+  *ndiffbytes = nd;
+  if (nr > max_results || nd > max_diffbytes || (nr && !results) || (nd && !diffstr) || nd > 0xffffffffull)
+    return fail(ctx, SMB_ERR_CAPACITY, "need %zu results and %zu diffstr bytes", nr, nd);
+  // dense arrays reuse the direction-strip buffer (no longer needed)
+  const size_t dense_bytes = nr * sizeof(smb_ali_result) + nd + 64;
+  CU(ctx->dirs.ensure(dense_bytes));
+  smb_ali_result *d_dense = ctx->dirs.as<smb_ali_result>();
+  uint8_t *d_ddiff = (uint8_t *)(d_dense + nr);
+  nl = 0;
+  CU(cudaEventRecord(ctx->ev0, st));
+  CU(launch_compact_gather(d_res, d_nres, ctx->diff.as<uint8_t>(), d_diff_off, d_dused, n, max_res, d_first,
+                           d_diff_first, d_dense, d_ddiff, st, &nl));
+  CU(cudaEventRecord(ctx->ev1, st));
+  if (nr) CU(d2h(results, d_dense, nr * sizeof(smb_ali_result), st));
+  if (nd) CU(d2h(diffstr, d_ddiff, nd, st));
+  CU(d2h(first_result, d_first, (size_t)(n + 1) * sizeof(uint32_t), st));
+  CU(d2h(errs, d_errs, (size_t)n * sizeof(int32_t), st));
+  CU(ctx_sync(ctx));
+  CU(cudaEventElapsedTime(&ms1, ctx->ev0, ctx->ev1));
+  ctx->last_ms += ms1;
+  ctx->last_launches += nl;
+  ctx->total_launches += nl;
+  g_launches += nl;
   return SMB_OK;
 }
 
@@ -400,6 +588,15 @@ int smb_band_align_batch(smb_ctx *ctx, const smb_band_task *tasks, int ntasks, s
     if (rcode) return rcode;
   }
   cudaSetDevice(ctx->device);
+  {
+    const int rcode = band_align_fast(ctx, tasks, ntasks, results, max_results, nresults, first_result, diffstr,
+                                      max_diffbytes, ndiffbytes, errs, ncells);
+    if (rcode != 1) return rcode;
+    *nresults = 0;
+    *ndiffbytes = 0;
+    if (ncells) *ncells = 0;
+    first_result[0] = 0;
+  }
 
   // per task: results and diff bytes collected from (possibly several) passes
   struct TaskOut { std::vector<smb_ali_result> res; std::vector<uint8_t> diff; int32_t err = 0; };
@@ -456,9 +653,10 @@ int smb_band_align_batch(smb_ctx *ctx, const smb_band_task *tasks, int ntasks, s
     max_res *= 8;
     diff_scale *= 4;
   }
-  ctx->last_ms = ms;
-  ctx->last_launches = nl;
+  ctx->last_ms += ms;
+  ctx->last_launches += nl;
   ctx->total_launches += nl;
+  g_launches += nl;
   if (ncells) *ncells = cells;
   size_t nr = 0, nd = 0;
   for (int i = 0; i < ntasks; ++i) { nr += outs[(size_t)i].res.size(); nd += outs[(size_t)i].diff.size(); }
@@ -510,13 +708,13 @@ int smb_index_upload(smb_ctx *ctx, int typ, int wordlen, int nskip, int nbits_ke
   uint32_t *base = ctx->index.as<uint32_t>();
   uint32_t *d_idx = base, *d_pos = d_idx + al(n_idx), *d_w = d_pos + al(n_pos + 1), *d_p = d_w + al(n_w + 1);
   cudaStream_t st = ctx->stream;
-  CU(cudaMemcpyAsync(d_idx, idx, n_idx * 4, cudaMemcpyHostToDevice, st));
-  if (n_pos) CU(cudaMemcpyAsync(d_pos, pos, n_pos * 4, cudaMemcpyHostToDevice, st));
+  CU(h2d(d_idx, idx, n_idx * 4, st));
+  if (n_pos) CU(h2d(d_pos, pos, n_pos * 4, st));
   if (typ) {
-    CU(cudaMemcpyAsync(d_w, wordidx, n_w * 4, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(d_p, posidx, n_w * 4, cudaMemcpyHostToDevice, st));
+    CU(h2d(d_w, wordidx, n_w * 4, st));
+    CU(h2d(d_p, posidx, n_w * 4, st));
   }
-  CU(cudaStreamSynchronize(st));
+  CU(ctx_sync(ctx));
   ix.idx = d_idx; ix.pos = d_pos; ix.wordidx = d_w; ix.posidx = d_p;
   ctx->ix = ix;
   ctx->have_index = true;
@@ -552,13 +750,13 @@ int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_
   uint64_t *d_slot = d_off + nreads;
   smb_seed_info *d_info = (smb_seed_info *)(d_slot + nreads);
   uint32_t *d_len = (uint32_t *)(d_info + 2 * (size_t)nreads);
-  CU(cudaMemcpyAsync(d_off, read_off, (size_t)nreads * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_slot, slot.data(), (size_t)nreads * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_len, read_len, (size_t)nreads * 4, cudaMemcpyHostToDevice, st));
+  CU(h2d(d_off, read_off, (size_t)nreads * 8, st));
+  CU(h2d(d_slot, slot.data(), (size_t)nreads * 8, st));
+  CU(h2d(d_len, read_len, (size_t)nreads * 4, st));
   const uint8_t *d_qual = nullptr;
   if (qual) {
     CU(ctx->qualbuf.ensure(ctx->arena_bytes + 16));
-    CU(cudaMemcpyAsync(ctx->qualbuf.p, qual, ctx->arena_bytes, cudaMemcpyHostToDevice, st));
+    CU(h2d(ctx->qualbuf.p, qual, ctx->arena_bytes, st));
     d_qual = ctx->qualbuf.as<uint8_t>();
   }
   const size_t S = (size_t)nslots + 64;
@@ -575,13 +773,13 @@ int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_
   CU(cudaEventRecord(ctx->ev0, st));
   CU(launch_seed(ctx->ix, ctx->src.arena, a, st, &nl));
   CU(cudaEventRecord(ctx->ev1, st));
-  CU(cudaMemcpyAsync(info, d_info, (size_t)2 * nreads * sizeof(smb_seed_info), cudaMemcpyDeviceToHost, st));
+  CU(d2h(info, d_info, (size_t)2 * nreads * sizeof(smb_seed_info), st));
   struct { uint32_t *h; uint32_t *d; } cp[] = {{seed_posidx, a.posidx}, {seed_nhits, a.nhits}, {seed_qoffs, a.qoffs},
                                                 {sortkey, a.sortkey}, {sidx, a.sidx}};
   for (auto &c : cp)
-    if (c.h) CU(cudaMemcpyAsync(c.h, c.d, (size_t)nslots * 4, cudaMemcpyDeviceToHost, st));
-  if (qmask) CU(cudaMemcpyAsync(qmask, a.qmask, (size_t)nslots, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+    if (c.h) CU(d2h(c.h, c.d, (size_t)nslots * 4, st));
+  if (qmask) CU(d2h(qmask, a.qmask, (size_t)nslots, st));
+  CU(ctx_sync(ctx));
   CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
   ctx->seed_nreads = nreads;
   ctx->seed_args = a;
@@ -590,6 +788,7 @@ int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_
   ctx->seed_slots = nslots;
   ctx->last_launches = nl;
   ctx->total_launches += nl;
+  g_launches += nl;
   return SMB_OK;
 }
 
@@ -625,7 +824,7 @@ int smb_hits_batch(smb_ctx *ctx, const smb_hit_req *req, int nreq, uint32_t nhit
   uint32_t *d_count = (uint32_t *)(d_off + n);
   uint32_t *d_used = d_count + n;
   int32_t *d_errs = (int32_t *)(d_used + n);
-  CU(cudaMemcpyAsync(d_req, req, n * sizeof(smb_hit_req), cudaMemcpyHostToDevice, st));
+  CU(h2d(d_req, req, n * sizeof(smb_hit_req), st));
   HitArgs ha{};
   ha.seed = ctx->seed_args; ha.req = d_req; ha.nreq = nreq; ha.nhits_alloc = nhits_alloc;
   ha.count = d_count; ha.maxhit_used = d_used; ha.errs = d_errs; ha.offset = d_off; ha.sqdat = nullptr;
@@ -635,9 +834,9 @@ int smb_hits_batch(smb_ctx *ctx, const smb_hit_req *req, int nreq, uint32_t nhit
   CU(launch_hits(ctx->ix, ha, false, st, &nl));
   CU(cudaEventRecord(ctx->ev1, st));
   std::vector<uint32_t> count(n);
-  CU(cudaMemcpyAsync(count.data(), d_count, n * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(errs, d_errs, n * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  CU(d2h(count.data(), d_count, n * 4, st));
+  CU(d2h(errs, d_errs, n * 4, st));
+  CU(ctx_sync(ctx));
   CU(cudaEventElapsedTime(&ms0, ctx->ev0, ctx->ev1));
   std::vector<uint64_t> off(n + 1, 0);
   for (size_t i = 0; i < n; ++i) off[i + 1] = off[i] + count[i];
@@ -648,20 +847,22 @@ int smb_hits_batch(smb_ctx *ctx, const smb_hit_req *req, int nreq, uint32_t nhit
     ctx->last_ms = ms0;
     ctx->last_launches = nl;
     ctx->total_launches += nl;
+  g_launches += nl;
     return fail(ctx, SMB_ERR_CAPACITY, "need room for %llu hits", (unsigned long long)total);
   }
   CU(ctx->hit_data.ensure((size_t)(total + 1) * 8));
-  CU(cudaMemcpyAsync(d_off, off.data(), n * 8, cudaMemcpyHostToDevice, st));
+  CU(h2d(d_off, off.data(), n * 8, st));
   ha.sqdat = ctx->hit_data.as<uint64_t>();
   CU(cudaEventRecord(ctx->ev0, st));
   CU(launch_hits(ctx->ix, ha, true, st, &nl));
   CU(cudaEventRecord(ctx->ev1, st));
-  if (total) CU(cudaMemcpyAsync(sqdat, ha.sqdat, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  if (total) CU(d2h(sqdat, ha.sqdat, (size_t)total * 8, st));
+  CU(ctx_sync(ctx));
   CU(cudaEventElapsedTime(&ms1, ctx->ev0, ctx->ev1));
   ctx->last_ms = ms0 + ms1;
   ctx->last_launches = nl;
   ctx->total_launches += nl;
+  g_launches += nl;
   return SMB_OK;
 }
 

@@ -294,6 +294,7 @@ band_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__restrict_
   }
   out.nres[tix] = nres;
   out.errs[tix] = err;
+  if (out.dused) out.dused[tix] = diff_used;
   if (ncell) atomicAdd(out.cells, ncell);
 }
 

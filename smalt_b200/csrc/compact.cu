@@ -1,0 +1,164 @@
+// compact.cu - device-side compaction of the K3 outputs.
+//
+// band_kernel<true> writes the results of task t into fixed slots (max_res results, a
+// per-task DiffStr area).  Shipping those slots to the host costs ~1 KB per task although a
+// typical task produces one 32-byte result and a DiffStr of a dozen bytes, so the dense
+// arrays of the C ABI (smb_band_align_batch: results in task order, first_result[], one
+// diffstr buffer) are assembled on the device: two exclusive scans (results, DiffStr bytes)
+// and one gather kernel; only the dense arrays cross PCIe.
+#include "common.cuh"
+
+namespace smb {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 4;                       // per thread
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ unsigned long long block_sum(unsigned long long v, unsigned long long *sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned long long w = (threadIdx.x < SCAN_THREADS / 32) ? sh[threadIdx.x] : 0ull;
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_down_sync(0xffffffffu, w, o);
+    if (threadIdx.x == 0) sh[0] = w;
+  }
+  __syncthreads();
+  const unsigned long long r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+// phase 1: per-tile sums of nres[] and dused[]; flags tasks that ran out of slot capacity
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_tiles(const uint32_t *__restrict__ nres, const uint32_t *__restrict__ dused,
+           const int32_t *__restrict__ errs, int n, unsigned long long *__restrict__ tile_res,
+           unsigned long long *__restrict__ tile_diff, CompactTotals *__restrict__ tot) {
+  __shared__ unsigned long long sh[32];
+  const int base = blockIdx.x * SCAN_TILE;
+  unsigned long long a = 0, b = 0;
+  bool cap = false;
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    const int i = base + k * SCAN_THREADS + threadIdx.x;
+    if (i < n) {
+      a += nres[i];
+      b += dused[i];
+      cap |= errs[i] == SMB_ERR_CAPACITY;
+    }
+  }
+  a = block_sum(a, sh);
+  b = block_sum(b, sh);
+  if (threadIdx.x == 0) { tile_res[blockIdx.x] = a; tile_diff[blockIdx.x] = b; }
+  if (cap) tot->capacity_flag = 1;
+}
+
+// phase 2: exclusive scan of the tile sums (a few thousand values: one warp, serial chunks)
+__global__ void scan_top(unsigned long long *tile_res, unsigned long long *tile_diff, int ntiles,
+                         CompactTotals *tot) {
+  const int lane = threadIdx.x;
+  unsigned long long carry_a = 0, carry_b = 0;
+  for (int base = 0; base < ntiles; base += 32) {
+    const int i = base + lane;
+    unsigned long long a = (i < ntiles) ? tile_res[i] : 0ull, b = (i < ntiles) ? tile_diff[i] : 0ull;
+    unsigned long long ia = a, ib = b;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+      if (lane >= o) { ia += ta; ib += tb; }
+    }
+    if (i < ntiles) { tile_res[i] = carry_a + ia - a; tile_diff[i] = carry_b + ib - b; }
+    carry_a += __shfl_sync(0xffffffffu, ia, 31);
+    carry_b += __shfl_sync(0xffffffffu, ib, 31);
+  }
+  if (lane == 0) { tot->nresults = carry_a; tot->ndiff = carry_b; }
+}
+
+// phase 3: per-task exclusive offsets
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_apply(const uint32_t *__restrict__ nres, const uint32_t *__restrict__ dused, int n,
+           const unsigned long long *__restrict__ tile_res, const unsigned long long *__restrict__ tile_diff,
+           uint32_t *__restrict__ first_result, unsigned long long *__restrict__ diff_first) {
+  __shared__ unsigned long long sa[SCAN_THREADS], sb[SCAN_THREADS];
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t va[SCAN_ITEMS], vb[SCAN_ITEMS];
+  unsigned long long a = 0, b = 0;
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    const int i = base + k;
+    va[k] = (i < n) ? nres[i] : 0u;
+    vb[k] = (i < n) ? dused[i] : 0u;
+    a += va[k];
+    b += vb[k];
+  }
+  sa[threadIdx.x] = a;
+  sb[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 1; o < SCAN_THREADS; o <<= 1) {   // Hillis-Steele inclusive scan of the thread sums
+    unsigned long long ta = 0, tb = 0;
+    if ((int)threadIdx.x >= o) { ta = sa[threadIdx.x - o]; tb = sb[threadIdx.x - o]; }
+    __syncthreads();
+    sa[threadIdx.x] += ta;
+    sb[threadIdx.x] += tb;
+    __syncthreads();
+  }
+  unsigned long long oa = tile_res[blockIdx.x] + sa[threadIdx.x] - a;
+  unsigned long long ob = tile_diff[blockIdx.x] + sb[threadIdx.x] - b;
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    const int i = base + k;
+    if (i < n) { first_result[i] = (uint32_t)oa; diff_first[i] = ob; }
+    oa += va[k];
+    ob += vb[k];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) first_result[n] = (uint32_t)oa;
+}
+
+// gather: results and DiffStr bytes of task t -> dense arrays
+__global__ void __launch_bounds__(128)
+gather_results(const smb_ali_result *__restrict__ slots, const uint32_t *__restrict__ nres,
+               const uint8_t *__restrict__ diff_slots, const uint64_t *__restrict__ diff_off,
+               const uint32_t *__restrict__ dused, int n, int max_res,
+               const uint32_t *__restrict__ first_result, const unsigned long long *__restrict__ diff_first,
+               smb_ali_result *__restrict__ out_res, uint8_t *__restrict__ out_diff) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const uint32_t nr = nres[t];
+  const unsigned long long dbase = diff_first[t];
+  const smb_ali_result *src = slots + (size_t)t * max_res;
+  smb_ali_result *dst = out_res + first_result[t];
+  for (uint32_t k = 0; k < nr; ++k) {
+    smb_ali_result r = src[k];
+    r.diff_off += (uint32_t)dbase;
+    r.task = (uint32_t)t;
+    dst[k] = r;
+  }
+  const uint8_t *ds = diff_slots + diff_off[t];
+  uint8_t *dd = out_diff + dbase;
+  const uint32_t nb = dused[t];
+  for (uint32_t k = 0; k < nb; ++k) dd[k] = ds[k];
+}
+
+int compact_tiles(int n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+
+cudaError_t launch_compact_scan(const uint32_t *nres, const uint32_t *dused, const int32_t *errs, int n,
+                                unsigned long long *tile_res, unsigned long long *tile_diff,
+                                CompactTotals *tot, uint32_t *first_result,
+                                unsigned long long *diff_first, cudaStream_t st, int *nlaunch) {
+  const int ntiles = compact_tiles(n);
+  cudaError_t e;
+  if ((e = cudaMemsetAsync(tot, 0, sizeof(CompactTotals), st)) != cudaSuccess) return e;
+  scan_tiles<<<ntiles, SCAN_THREADS, 0, st>>>(nres, dused, errs, n, tile_res, tile_diff, tot);
+  scan_top<<<1, 32, 0, st>>>(tile_res, tile_diff, ntiles, tot);
+  scan_apply<<<ntiles, SCAN_THREADS, 0, st>>>(nres, dused, n, tile_res, tile_diff, first_result, diff_first);
+  *nlaunch += 3;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compact_gather(const smb_ali_result *slots, const uint32_t *nres, const uint8_t *diff_slots,
+                                  const uint64_t *diff_off, const uint32_t *dused, int n, int max_res,
+                                  const uint32_t *first_result, const unsigned long long *diff_first,
+                                  smb_ali_result *out_res, uint8_t *out_diff, cudaStream_t st, int *nlaunch) {
+  gather_results<<<(n + 127) / 128, 128, 0, st>>>(slots, nres, diff_slots, diff_off, dused, n, max_res,
+                                                  first_result, diff_first, out_res, out_diff);
+  ++*nlaunch;
+  return cudaGetLastError();
+}
+
+}  // namespace smb

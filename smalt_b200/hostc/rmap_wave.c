@@ -32,6 +32,7 @@
  * (one GPU call per function call: slow, but still no CPU hot path).
  */
 #include <time.h>
+#include <string.h>
 #include "rmap.c"
 #include "shim.h"
 #include "rmap_wave.h"
@@ -59,8 +60,15 @@ typedef struct {
   int min_swatscor, scorlen_min, bandwidth_min;
 } WREAD;
 
+/* page-locked staging buffers (smb_host_alloc): what crosses the C ABI is copied by DMA */
+typedef struct { void *p; size_t cap; } WBUF;
+enum { WB_ARENA, WB_QUAL, WB_READ_OFF, WB_READ_LEN, WB_INFO, WB_REQ, WB_LIST_FIRST, WB_REQ_ERR, WB_SQDAT,
+       WB_SWT, WB_SW_SCORE, WB_SW_ERR, WB_BFT, WB_BF_SCORE, WB_BF_ERR, WB_BAT, WB_BA_ERR, WB_RES,
+       WB_RES_FIRST, WB_DIFF, WB_COUNT };
+
 struct RmapWave_ {
   smb_ctx *ctx;
+  WBUF wb[WB_COUNT];
   /* host staging, grown on demand */
   uint8_t *arena, *qual;
   size_t arena_alloc;
@@ -95,6 +103,18 @@ struct RmapWave_ {
   uint64_t cells_k2, cells_k3, n_k2, n_k3, n_reads;
 };
 
+static void *wbuf_need(WBUF *b, size_t bytes)
+{
+  if (bytes > b->cap) {
+    smb_host_free(b->p);
+    b->cap = bytes + bytes / 2 + 4096;
+    if (!(b->p = smb_host_alloc(b->cap))) b->cap = 0;
+  }
+  return b->p;
+}
+#define WPIN(ptr, which, need, type)						\
+  do { if (!((ptr) = (type *) wbuf_need(&w->wb[which], (size_t) (need) * sizeof(type)))) return ERRCODE_NOMEM; } while (0)
+
 #define WGROW(ptr, alloc, need, type)						\
   do { if ((size_t) (need) > (alloc)) {						\
       size_t na_ = (size_t) (need) + (size_t) (need) / 2 + 64;			\
@@ -120,11 +140,12 @@ RmapWave *rmapWaveCreate(const HashTable *htp, const SeqSet *ssp, const SeqCodec
 void rmapWaveDelete(RmapWave *w)
 {
   if (!w) return;
+  {
+    int k;
+    for (k = 0; k < WB_COUNT; k++) smb_host_free(w->wb[k].p);
+  }
   smb_ctx_destroy(w->ctx);
-  free(w->arena); free(w->qual); free(w->read_off); free(w->read_len); free(w->info); free(w->rd);
-  free(w->req); free(w->list_first); free(w->req_err); free(w->sqdat); free(w->cand); free(w->swt);
-  free(w->sw_score); free(w->sw_err); free(w->bft); free(w->bat); free(w->bf_score); free(w->bf_err);
-  free(w->ba_err); free(w->res); free(w->res_first); free(w->diff);
+  free(w->rd); free(w->cand);
   scoreDeleteProfile(w->prof); scoreDeleteProfile(w->profRC); seqFastqDelete(w->readRC);
   free(w);
 }
@@ -207,11 +228,10 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
     return ERRCODE_ARGINVAL; /* caller falls back to the one-call path (still GPU) */
 
   /* ------------------------------ wave 1: seeds -------------------------------------- */
-  WGROW(w->read_off, w->n_alloc, n, uint64_t);
-  w->n_alloc = 0; WGROW(w->read_len, w->n_alloc, n, uint32_t);
-  w->n_alloc = 0; WGROW(w->rd, w->n_alloc, n, WREAD);
-  w->n_alloc = 0; WGROW(w->info, w->n_alloc, 2 * (size_t) n, smb_seed_info);
-  w->n_alloc = (size_t) n;
+  WPIN(w->read_off, WB_READ_OFF, n, uint64_t);
+  WPIN(w->read_len, WB_READ_LEN, n, uint32_t);
+  WPIN(w->info, WB_INFO, 2 * (size_t) n, smb_seed_info);
+  WGROW(w->rd, w->n_alloc, n, WREAD);
   for (i = 0; i < n; i++) {
     SEQLEN_t len;
     char cod;
@@ -222,13 +242,8 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
     tot += len;
     if (seqFastqGetConstQualityFactors(reads[i], NULL, NULL)) any_qual = 1;
   }
-  if (tot + 16 > w->arena_alloc) {
-    size_t na = tot + tot / 2 + 4096;
-    w->arena = (uint8_t *) realloc(w->arena, na);
-    w->qual = (uint8_t *) realloc(w->qual, na);
-    if (!w->arena || !w->qual) return ERRCODE_NOMEM;
-    w->arena_alloc = na;
-  }
+  WPIN(w->arena, WB_ARENA, tot + 16, uint8_t);
+  WPIN(w->qual, WB_QUAL, tot + 16, uint8_t);
   for (i = 0; i < n; i++) {
     SEQLEN_t len;
     const char *p = seqFastqGetConstSequence(reads[i], &len, NULL);
@@ -249,9 +264,9 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
   WTICK(1);
 
   /* hit lists: every read x strand x reference sequence (collectHits, rmap.c:283-318) */
-  WGROW(w->req, w->req_alloc, 2 * (size_t) n * (size_t) nseq + 1, smb_hit_req);
-  w->req_alloc = 0; WGROW(w->list_first, w->req_alloc, 2 * (size_t) n * (size_t) nseq + 2, uint64_t);
-  w->req_alloc = 0; WGROW(w->req_err, w->req_alloc, 2 * (size_t) n * (size_t) nseq + 1, int32_t);
+  WPIN(w->req, WB_REQ, 2 * (size_t) n * (size_t) nseq + 1, smb_hit_req);
+  WPIN(w->list_first, WB_LIST_FIRST, 2 * (size_t) n * (size_t) nseq + 2, uint64_t);
+  WPIN(w->req_err, WB_REQ_ERR, 2 * (size_t) n * (size_t) nseq + 1, int32_t);
   for (i = 0; i < n; i++) {
     WREAD *rd = w->rd + i;
     int st;
@@ -270,14 +285,17 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
 	rq->strand = (uint8_t) st; rq->use_short = 1;
       }
   }
+  if (w->sqdat_alloc < 32 * (size_t) n) { /* typical short-read blocks need no second counting pass */
+    WPIN(w->sqdat, WB_SQDAT, 48 * (size_t) n + 1024, uint64_t);
+    w->sqdat_alloc = w->wb[WB_SQDAT].cap / sizeof(uint64_t);
+  }
   for (;;) {
     size_t need = 0;
     rc = smb_hits_batch(w->ctx, w->req, (int) nreq, 0, w->sqdat, w->sqdat_alloc, &need, w->list_first,
 			w->req_err);
     if (rc == SMB_ERR_CAPACITY && need > w->sqdat_alloc) {
-      free(w->sqdat);
-      w->sqdat_alloc = need + need / 4 + 1024;
-      if (!(w->sqdat = (uint64_t *) malloc(w->sqdat_alloc * sizeof(uint64_t)))) return ERRCODE_NOMEM;
+      WPIN(w->sqdat, WB_SQDAT, need + need / 4 + 1024, uint64_t);
+      w->sqdat_alloc = w->wb[WB_SQDAT].cap / sizeof(uint64_t);
       continue;
     }
     if (rc) return gpu_fail(errmsgp, w, rc);
@@ -387,12 +405,12 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
 
   WTICK(3);
   /* ------------------------------ wave 2: scores ------------------------------------- */
-  WGROW(w->swt, w->swt_alloc, w->ncand + 1, smb_sw_task);
-  w->swt_alloc = 0; WGROW(w->sw_score, w->swt_alloc, w->ncand + 1, int32_t);
-  w->swt_alloc = 0; WGROW(w->sw_err, w->swt_alloc, w->ncand + 1, int32_t);
-  WGROW(w->bft, w->bft_alloc, w->ncand + 1, smb_band_task);
-  w->bft_alloc = 0; WGROW(w->bf_score, w->bft_alloc, w->ncand + 1, int32_t);
-  w->bft_alloc = 0; WGROW(w->bf_err, w->bft_alloc, w->ncand + 1, int32_t);
+  WPIN(w->swt, WB_SWT, w->ncand + 1, smb_sw_task);
+  WPIN(w->sw_score, WB_SW_SCORE, w->ncand + 1, int32_t);
+  WPIN(w->sw_err, WB_SW_ERR, w->ncand + 1, int32_t);
+  WPIN(w->bft, WB_BFT, w->ncand + 1, smb_band_task);
+  WPIN(w->bf_score, WB_BF_SCORE, w->ncand + 1, int32_t);
+  WPIN(w->bf_err, WB_BF_ERR, w->ncand + 1, int32_t);
   for (i = 0; i < n; i++) {
     WREAD *rd = w->rd + i;
     uint32_t c;
@@ -450,8 +468,8 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
 
   WTICK(4);
   /* host: replay of scoreRMAPCAND (rmap.c:646-786) and of mapSingleRead (rmap.c:1366-1400) */
-  WGROW(w->bat, w->bat_alloc, w->ncand + 1, smb_band_task);
-  w->bat_alloc = 0; WGROW(w->ba_err, w->bat_alloc, w->ncand + 1, int32_t);
+  WPIN(w->bat, WB_BAT, w->ncand + 1, smb_band_task);
+  WPIN(w->ba_err, WB_BA_ERR, w->ncand + 1, int32_t);
   for (i = 0; i < n; i++) {
     WREAD *rd = w->rd + i;
     const short mmscordiff = (short) (matchscor - mismatchscor), gapscordiff = (short) (matchscor - gapinitscor);
@@ -546,30 +564,25 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
   /* ------------------------------ wave 3: alignments --------------------------------- */
   if (nba) {
     for (;;) {
+      WPIN(w->res_first, WB_RES_FIRST, nba + 2, uint32_t);
       if (w->res_alloc < nba + 16) {
-	free(w->res); free(w->res_first);
-	w->res_alloc = nba + nba / 2 + 64;
-	w->res = (smb_ali_result *) malloc(w->res_alloc * sizeof(smb_ali_result));
-	w->res_first = (uint32_t *) malloc((w->res_alloc + 2) * sizeof(uint32_t));
-	if (!w->res || !w->res_first) return ERRCODE_NOMEM;
+	WPIN(w->res, WB_RES, nba + nba / 2 + 64, smb_ali_result);
+	w->res_alloc = w->wb[WB_RES].cap / sizeof(smb_ali_result);
       }
       if (w->diff_alloc < 32 * nba) {
-	free(w->diff);
-	w->diff_alloc = 48 * nba + 4096;
-	if (!(w->diff = (uint8_t *) malloc(w->diff_alloc))) return ERRCODE_NOMEM;
+	WPIN(w->diff, WB_DIFF, 48 * nba + 4096, uint8_t);
+	w->diff_alloc = w->wb[WB_DIFF].cap;
       }
       rc = smb_band_align_batch(w->ctx, w->bat, (int) nba, w->res, w->res_alloc, &nres, w->res_first,
 				w->diff, w->diff_alloc, &ndiff, w->ba_err, &cells);
       if (rc == SMB_ERR_CAPACITY && (nres > w->res_alloc || ndiff > w->diff_alloc)) {
 	if (nres > w->res_alloc) {
-	  free(w->res);
-	  w->res_alloc = nres + 64;
-	  if (!(w->res = (smb_ali_result *) malloc(w->res_alloc * sizeof(smb_ali_result)))) return ERRCODE_NOMEM;
+	  WPIN(w->res, WB_RES, nres + 64, smb_ali_result);
+	  w->res_alloc = w->wb[WB_RES].cap / sizeof(smb_ali_result);
 	}
 	if (ndiff > w->diff_alloc) {
-	  free(w->diff);
-	  w->diff_alloc = ndiff + 4096;
-	  if (!(w->diff = (uint8_t *) malloc(w->diff_alloc))) return ERRCODE_NOMEM;
+	  WPIN(w->diff, WB_DIFF, ndiff + 4096, uint8_t);
+	  w->diff_alloc = w->wb[WB_DIFF].cap;
 	}
 	continue;
       }

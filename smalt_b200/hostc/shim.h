@@ -22,4 +22,12 @@ int smbShimHitListSet(HashHitList *p, const uint64_t *sqdat, int nhits, int is_r
 		      unsigned char ktup, unsigned char nskip);
 int smbShimAliRsltSetAdd(AliRsltSet *p, int score, int qs, int qe, int rs, int re,
 			 const unsigned char *diffstr, int difflen);
+
+/* per-worker report writers of the block-parallel driver (shim_report.c) */
+#include "report.h"
+ReportWriter *smbShimReportWriterClone(const ReportWriter *proto);
+void smbShimReportWriterSetStream(ReportWriter *p, FILE *fp);
+void smbShimReportWriterDelete(ReportWriter *p);
+int smbShimWriteSAMHeader(FILE *fp, const SeqSet *ssp, const char *prognam, const char *progversion,
+			  int narg, char * const *argv);
 #endif

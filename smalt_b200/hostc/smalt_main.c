@@ -1,34 +1,47 @@
 /* smalt_main.c - the `smalt_b200` driver: the reference's own driver with the hot path on a B200.
  *
- * The reference driver (command line, FASTQ reader, work queue, SAM writer;
- * /root/reference/src/smalt.c, menu.c, threads.c, infmt.c, report.c) is used UNCHANGED: this
- * translation unit compiles smalt.c in place (read-only tree on the include path, nothing is
- * copied) with its main() renamed, and hooks in at exactly one point - the registration of the
- * PROC task of the work queue (smalt.c:1369-1375):
- *   * the per-read-block worker processArgBlock (smalt.c:1221) is replaced by
- *     smb_processArgBlock below, which maps the single-end reads of a block in GPU waves
- *     (rmap_wave.c) instead of one rmapSingle call per read, and
- *   * the block size (smalt.c:466, 32 reads per thread) is raised so that a block is a useful
- *     GPU batch.
+ * The reference driver (command line, index loading, work queue; /root/reference/src/smalt.c,
+ * menu.c, threads.c, infmt.c, report.c) is used UNCHANGED: this translation unit compiles
+ * smalt.c in place (read-only tree on the include path, nothing is copied) with its main()
+ * renamed, and hooks in with linker wraps at the work-queue interface (threads.h):
+ *   threadsSetTask  - the per-read-block worker processArgBlock (smalt.c:1221) is replaced by
+ *                     smb_processArgBlock below, which maps the single-end reads of a block in
+ *                     GPU waves (rmap_wave.c) instead of one rmapSingle call per read;
+ *   threadsRun      - for the common case (one plain-text FASTQ/FASTA file, text output) the
+ *                     whole INPUT -> PROC -> OUTPUT queue is replaced by the block-parallel
+ *                     pipeline of fastmap.inc.c (parallel parsing and formatting with the
+ *                     reference's own parser and report writer);
+ *   infmtCreateReader - only records the input file names for that pipeline.
  * Paired reads and modes the wave path does not cover are passed to the reference's own
  * processArgBlock, whose hot-path calls then go through the shim one call at a time (GPU
  * batches of one - slow, but never a CPU hot path).
  * `smalt_b200 index` is the reference's CPU index builder (not on the hot path).
+ *
+ * The same code is also built as a library (libsmalt_b200_map.so, include/smalt_b200_map.h):
+ * smbm_open() runs the reference's `map` set-up (option parsing, index loading) on a session
+ * thread and parks it inside threadsRun, smbm_map_fastq() maps a FASTQ text buffer to a SAM
+ * text buffer with the same pipeline.
  */
+#define _GNU_SOURCE /* memfd_create */
 #include <pthread.h>
 #include <time.h>
+#include <ctype.h>
 #define main ref_smalt_main
 #include "smalt.c"
 #undef main
 
 #include "rmap_wave.h"
+#include "shim.h"
+#include "../../include/smalt_b200_map.h"
 
 static THREAD_PROCF *g_ref_procf;
-static short g_blocksz = 8192;
+static int fastmap_eligible(const SmaltMapConst *macop, const char **reason);
+static short g_blocksz = 2048;  /* reads per block of the reference queue path */
 static pthread_mutex_t g_stats_lock = PTHREAD_MUTEX_INITIALIZER;
 static double g_ms[3];
 static uint64_t g_counts[5];
 static double g_wall[8], g_wall_enc, g_t0;
+static double g_fm_parse_s, g_fm_format_s;
 
 typedef struct {
   RmapWave *wave;
@@ -66,6 +79,7 @@ static void flushStats(void)
   fprintf(fp, "{\"host_wall_s\": {\"staging\": %.3f, \"seed\": %.3f, \"hits\": %.3f, \"candidates\": %.3f, "
 	  "\"score\": %.3f, \"replay\": %.3f, \"align\": %.3f, \"results\": %.3f, \"encode\": %.3f}}\n",
 	  g_wall[0], g_wall[1], g_wall[2], g_wall[3], g_wall[4], g_wall[5], g_wall[6], g_wall[7], g_wall_enc);
+  fprintf(fp, "{\"parse_s\": %.3f}\n", g_fm_parse_s);
   fclose(fp);
 }
 
@@ -88,19 +102,9 @@ static int smb_processArgBlock(ErrMsg *errmsgp, void *targp, void *bufargp)
       return (*g_ref_procf)(errmsgp, targp, bufargp);
   if (macop->tupcovmin < 0)
     return ERRCODE_ASSERT;
-  if (getenv("SMALT_B200_TIMING")) {
-    struct timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    fprintf(stderr, "smalt_b200 timing: block of %d reads enters PROC at %.3f s\n", (int) n, ts.tv_sec + 1e-9 * ts.tv_nsec - g_t0);
-  }
-  if (!t_ws.wave) {
+  if (!t_ws.wave && !getenv("SMALT_B200_IOTEST")) {
     t_ws.wave = rmapWaveCreate(macop->htp, macop->ssp, macop->codecp, macop->scormtxp);
-    if (getenv("SMALT_B200_TIMING")) {
-    struct timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    fprintf(stderr, "smalt_b200 timing: block of %d reads enters PROC at %.3f s\n", (int) n, ts.tv_sec + 1e-9 * ts.tv_nsec - g_t0);
-  }
-  if (!t_ws.wave) {
+    if (!t_ws.wave) {
       fprintf(stderr, "smalt_b200: cannot set up the GPU context of a worker thread\n");
       return ERRCODE_FAILURE;
     }
@@ -162,29 +166,305 @@ static int smb_processArgBlock(ErrMsg *errmsgp, void *targp, void *bufargp)
   return errcode;
 }
 
+#include "fastmap.inc.c"
+
+/* ------------------------------------------------------------------------------------ */
+/* hooks into the reference's work queue                                                  */
+/* ------------------------------------------------------------------------------------ */
 int __real_threadsSetTask(uint8_t task_typ, short n_threads, THREAD_INITF *initf, const void *initargp,
 			  THREAD_PROCF *procf, THREAD_CLEANF *cleanf, THREAD_CHECKF *checkf,
 			  THREAD_CMPF *cmpf, size_t argsz);
+int __real_threadsRun(void);
+InFmtReader *__real_infmtCreateReader(int *errcode, const char *filnamA, const char *filnamB, const INFMT_t fmt);
+
+static const SmaltMapConst *g_macop;
+static short g_nthreads;
+static char *g_filnamA, *g_filnamB;
+static INFMT_t g_infmt;
+
+InFmtReader *__wrap_infmtCreateReader(int *errcode, const char *filnamA, const char *filnamB, const INFMT_t fmt)
+{
+  free(g_filnamA); free(g_filnamB);
+  g_filnamA = filnamA ? strdup(filnamA) : NULL;
+  g_filnamB = filnamB ? strdup(filnamB) : NULL;
+  g_infmt = fmt;
+  return __real_infmtCreateReader(errcode, filnamA, filnamB, fmt);
+}
 
 int __wrap_threadsSetTask(uint8_t task_typ, short n_threads, THREAD_INITF *initf, const void *initargp,
 			  THREAD_PROCF *procf, THREAD_CLEANF *cleanf, THREAD_CHECKF *checkf,
 			  THREAD_CMPF *cmpf, size_t argsz)
 {
   if (task_typ == THRTASK_ARGBUF && argsz == sizeof(SmaltArgBlock)) {
-    /* a block of reads is the GPU batch: raise smalt.c:466's 32 reads per thread */
+    /* a block of reads is the GPU batch of the queue path: raise smalt.c:466's 32 reads per
+     * thread (only when that path will be used: the block buffers are allocated up front) */
     const char *e = getenv("SMALT_B200_BLOCK");
     long b = e ? atol(e) : g_blocksz;
+    g_macop = (const SmaltMapConst *) initargp;
     if (b < 1) b = 1;
     if (b > 32000) b = 32000;
-    ((SmaltMapConst *) initargp)->threadblksz = (short) b;
+    if (!fastmap_eligible(g_macop, NULL))
+      ((SmaltMapConst *) initargp)->threadblksz = (short) b;
   } else if (task_typ == THRTASK_PROC && argsz == sizeof(SmaltMapArgs)) {
     g_ref_procf = procf;
+    g_nthreads = n_threads;
     procf = smb_processArgBlock;
   }
   return __real_threadsSetTask(task_typ, n_threads, initf, initargp, procf, cleanf, checkf, cmpf, argsz);
 }
 
-int main(int argc, char *argv[])
+/* library mode (smbm_*): one mapper per process (the reference driver keeps global state) */
+struct smbm_mapper {
+  pthread_t th;
+  pthread_mutex_t lock;
+  pthread_cond_t cond;
+  int state;                 /* 0 starting, 1 ready, 2 request pending, 3 closing, 4 ended */
+  int argc;
+  char **argv;
+  const char *req_data;
+  size_t req_len;
+  char *out;
+  size_t out_len, out_alloc;
+  int req_err;
+  smbm_stats stats;
+};
+static smbm_mapper *g_lib;
+
+static int fm_sink_file(void *user, const char *buf, size_t len)
+{
+  return (fwrite(buf, 1, len, (FILE *) user) == len) ? ERRCODE_SUCCESS : ERRCODE_WRITEERR;
+}
+
+static int fm_sink_mem(void *user, const char *buf, size_t len)
+{
+  smbm_mapper *m = (smbm_mapper *) user;
+  if (m->out_len + len + 1 > m->out_alloc) {
+    size_t na = m->out_alloc ? m->out_alloc : (size_t) 1 << 20;
+    char *hp;
+    while (na < m->out_len + len + 1) na *= 2;
+    if (!(hp = (char *) realloc(m->out, na))) return ERRCODE_NOMEM;
+    m->out = hp;
+    m->out_alloc = na;
+  }
+  memcpy(m->out + m->out_len, buf, len);
+  m->out_len += len;
+  m->out[m->out_len] = '\0';
+  return ERRCODE_SUCCESS;
+}
+
+/* can the block-parallel pipeline run this job?  *reason gets a short text when not */
+static int fastmap_eligible(const SmaltMapConst *macop, const char **reason)
+{
+  const char *why = NULL;
+  if (getenv("SMALT_B200_REFIO")) why = "SMALT_B200_REFIO is set";
+  else if (!macop || macop->subprogtyp != MENU_MAP) why = "not the map subprogram";
+  else if ((macop->rmapflg & RMAPFLG_PAIRED) || g_filnamB) why = "paired reads";
+  else if (!(macop->rmapflg & RMAPFLG_SEQBYSEQ) || (macop->rmapflg & (RMAPFLG_NOSHRTINFO | RMAPFLG_SPLIT | RMAPFLG_CMPLXW)))
+    why = "mapping mode not covered by the wave path";
+  else if (macop->outform == REPORTFMT_BAM || macop->outform == REPORTFMT_GFF2) why = "output format";
+  else if (macop->inform != MENU_INFORM_FASTQ && macop->inform != MENU_INFORM_UNKNOWN) why = "input format";
+  else if (macop->tupcovmin < 0) why = "tuple cover";
+  if (reason) *reason = why;
+  return why == NULL;
+}
+
+static void fm_stats_reset(void)
+{
+  memset(g_ms, 0, sizeof(g_ms));
+  memset(g_counts, 0, sizeof(g_counts));
+  memset(g_wall, 0, sizeof(g_wall));
+  g_fm_parse_s = g_fm_format_s = 0;
+}
+
+int __wrap_threadsRun(void)
+{
+  const SmaltMapConst *macop = g_macop;
+  SmaltMapArgs *maps = (SmaltMapArgs *) threadsGetMem(THRTASK_PROC);
+  SmaltOutput *dop = (SmaltOutput *) threadsGetMem(THRTASK_OUTPUT);
+  const int nworkers = (g_nthreads > 0) ? g_nthreads : 1;
+  const char *why = NULL;
+  int errcode;
+
+  if (g_lib) { /* library mode: serve smbm_map_fastq requests until smbm_close */
+    smbm_mapper *m = g_lib;
+    if (!fastmap_eligible(macop, &why) || !maps || !dop) {
+      fprintf(stderr, "smalt_b200: smbm_open: options not supported by the block-parallel pipeline (%s)\n",
+	      why ? why : "set-up failed");
+      return ERRCODE_FAILURE;
+    }
+    pthread_mutex_lock(&m->lock);
+    m->state = 1;
+    pthread_cond_broadcast(&m->cond);
+    for (;;) {
+      while (m->state == 1) pthread_cond_wait(&m->cond, &m->lock);
+      if (m->state == 3) break;
+      pthread_mutex_unlock(&m->lock);
+      {
+	struct timespec t0, t1;
+	uint64_t nr = 0;
+	fm_stats_reset();
+	m->out_len = 0;
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+	errcode = fastmap_run(macop, maps, nworkers, dop->writerp, m->req_data, m->req_len, fm_sink_mem, m, &nr);
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	m->stats.n_reads = nr;
+	m->stats.wall_s = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+	m->stats.k1_ms = g_ms[0]; m->stats.k2_ms = g_ms[1]; m->stats.k3_ms = g_ms[2];
+	m->stats.k2_tasks = g_counts[1]; m->stats.k2_cells = g_counts[2];
+	m->stats.k3_tasks = g_counts[3]; m->stats.k3_cells = g_counts[4];
+	{
+	  unsigned long long nl, hb, db;
+	  smb_process_counters(&nl, &hb, &db);
+	  m->stats.gpu_launches = nl; m->stats.h2d_bytes = hb; m->stats.d2h_bytes = db;
+	}
+	memcpy(m->stats.host_stage_s, g_wall, sizeof(g_wall));
+	m->stats.host_stage_s[8] = g_fm_parse_s;
+      }
+      pthread_mutex_lock(&m->lock);
+      m->req_err = errcode;
+      m->state = 1;
+      pthread_cond_broadcast(&m->cond);
+    }
+    pthread_mutex_unlock(&m->lock);
+    fastmap_cleanup();
+    return ERRCODE_SUCCESS;
+  }
+
+  if (fastmap_eligible(macop, &why) && maps && dop && g_filnamA && strcmp(g_filnamA, "-")) {
+    int fd = open(g_filnamA, O_RDONLY);
+    struct stat sb;
+    if (fd >= 0 && !fstat(fd, &sb) && S_ISREG(sb.st_mode)) {
+      const char *data = sb.st_size ? (const char *) mmap(NULL, (size_t) sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0) : "";
+      if (data != MAP_FAILED && (!sb.st_size || data[0] == '@' || data[0] == '>' || isspace((unsigned char) data[0]))) {
+	FILE *oufp = reportGetWriterStream(dop->writerp);
+	uint64_t nr = 0;
+	if (sb.st_size) madvise((void *) data, (size_t) sb.st_size, MADV_SEQUENTIAL);
+	errcode = fastmap_run(macop, maps, nworkers, dop->writerp, data, (size_t) sb.st_size, fm_sink_file, oufp, &nr);
+	if (macop->menuflg & MENUFLAG_VERBOSE)
+	  fprintf(stderr, "# Processed %llu single reads.\n", (unsigned long long) nr);
+	fastmap_cleanup();
+	if (sb.st_size) munmap((void *) data, (size_t) sb.st_size);
+	close(fd);
+	return errcode ? errcode : ERRCODE_EOF;
+      }
+      if (data != MAP_FAILED && sb.st_size) munmap((void *) data, (size_t) sb.st_size);
+      why = "compressed or unrecognised read file";
+    }
+    if (fd >= 0) close(fd);
+  }
+  if (getenv("SMALT_B200_TIMING"))
+    fprintf(stderr, "smalt_b200: reference work queue in use (%s)\n", why ? why : "input is not a regular file");
+  return __real_threadsRun();
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* library API (include/smalt_b200_map.h)                                                 */
+/* ------------------------------------------------------------------------------------ */
+static void *smbm_session(void *arg)
+{
+  smbm_mapper *m = (smbm_mapper *) arg;
+  ref_smalt_main(m->argc, m->argv);
+  pthread_mutex_lock(&m->lock);
+  m->state = 4;
+  pthread_cond_broadcast(&m->cond);
+  pthread_mutex_unlock(&m->lock);
+  return NULL;
+}
+
+int smbm_open(smbm_mapper **mp, const char *index_prefix, int nthreads, int noptions, const char *const *options)
+{
+  smbm_mapper *m;
+  char nbuf[32], stub[64] = "/tmp/smalt_b200_stub_XXXXXX";
+  int i, k = 0, sfd;
+  if (!mp || !index_prefix || nthreads < 0 || noptions < 0) return SMB_ERR_ARG;
+  *mp = NULL;
+  if (g_lib) return SMB_ERR_STATE; /* one mapper per process */
+  if (!(m = (smbm_mapper *) calloc(1, sizeof(*m)))) return SMB_ERRCODE_NOMEM;
+  m->argv = (char **) calloc((size_t) noptions + 12, sizeof(char *));
+  snprintf(nbuf, sizeof(nbuf), "%d", nthreads);
+  m->argv[k++] = strdup("smalt_b200");
+  m->argv[k++] = strdup("map");
+  m->argv[k++] = strdup("-n"); m->argv[k++] = strdup(nbuf);
+  m->argv[k++] = strdup("-O");
+  m->argv[k++] = strdup("-o"); m->argv[k++] = strdup("/dev/null");
+  for (i = 0; i < noptions; i++) m->argv[k++] = strdup(options[i]);
+  m->argv[k++] = strdup(index_prefix);
+  /* the reference's set-up insists on opening a read file (smalt.c:582): a one-record stub */
+  if ((sfd = mkstemp(stub)) < 0 || write(sfd, "@stub\nA\n+\nI\n", 13) != 13) { free(m); return SMB_ERRCODE_FAILURE; }
+  close(sfd);
+  m->argv[k++] = strdup(stub);
+  m->argc = k;
+  pthread_mutex_init(&m->lock, NULL);
+  pthread_cond_init(&m->cond, NULL);
+  g_lib = m;
+  if (pthread_create(&m->th, NULL, smbm_session, m)) { g_lib = NULL; unlink(stub); free(m); return SMB_ERRCODE_FAILURE; }
+  pthread_mutex_lock(&m->lock);
+  while (m->state == 0) pthread_cond_wait(&m->cond, &m->lock);
+  i = m->state;
+  pthread_mutex_unlock(&m->lock);
+  unlink(stub);
+  if (i != 1) { /* set-up ended without reaching the work queue (bad index name, bad option) */
+    pthread_join(m->th, NULL);
+    g_lib = NULL;
+    return SMB_ERRCODE_FAILURE;
+  }
+  *mp = m;
+  return SMB_OK;
+}
+
+int smbm_map_fastq(smbm_mapper *m, const char *fastq, size_t nbytes, const char **sam, size_t *sam_len,
+		   smbm_stats *stats)
+{
+  int rc;
+  if (!m || m != g_lib || (!fastq && nbytes) || !sam || !sam_len) return SMB_ERR_ARG;
+  pthread_mutex_lock(&m->lock);
+  if (m->state != 1) { pthread_mutex_unlock(&m->lock); return SMB_ERR_STATE; }
+  m->req_data = fastq;
+  m->req_len = nbytes;
+  m->state = 2;
+  pthread_cond_broadcast(&m->cond);
+  while (m->state == 2) pthread_cond_wait(&m->cond, &m->lock);
+  rc = (m->state == 1) ? m->req_err : SMB_ERRCODE_FAILURE;
+  pthread_mutex_unlock(&m->lock);
+  *sam = m->out ? m->out : "";
+  *sam_len = m->out_len;
+  if (stats) *stats = m->stats;
+  return rc;
+}
+
+int smbm_sam_header(smbm_mapper *m, char **text, size_t *len)
+{
+  FILE *fp;
+  int errcode;
+  if (!m || m != g_lib || !text || !len || !g_macop) return SMB_ERR_ARG;
+  if (!(fp = open_memstream(text, len))) return SMB_ERRCODE_NOMEM;
+  errcode = smbShimWriteSAMHeader(fp, g_macop->ssp, g_macop->prognam, g_macop->progversion,
+				  g_macop->cmdlin_narg, g_macop->cmdlin_argv);
+  fclose(fp);
+  return errcode;
+}
+
+void smbm_free(void *p) { free(p); }
+
+int smbm_close(smbm_mapper *m)
+{
+  int i;
+  if (!m || m != g_lib) return SMB_ERR_ARG;
+  pthread_mutex_lock(&m->lock);
+  if (m->state == 1) { m->state = 3; pthread_cond_broadcast(&m->cond); }
+  pthread_mutex_unlock(&m->lock);
+  pthread_join(m->th, NULL);
+  g_lib = NULL;
+  for (i = 0; i < m->argc; i++) free(m->argv[i]);
+  free(m->argv);
+  free(m->out);
+  pthread_mutex_destroy(&m->lock);
+  pthread_cond_destroy(&m->cond);
+  free(m);
+  return SMB_OK;
+}
+
+int smalt_b200_cli_main(int argc, char *argv[])
 {
   struct timespec ts;
   int rv;

@@ -1,0 +1,108 @@
+"""ctypes binding of include/smalt_b200_map.h: the in-process `smalt_b200 map` driver
+(libsmalt_b200_map.so = the reference's unmodified driver / candidate selection / results /
+SAM writer objects around the B200 hot path of libsmalt_b200.so)."""
+import ctypes as C
+import os
+
+from .capi import SmbError, load_library
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+class MapStats(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("wall_s", C.c_double),
+                ("k1_ms", C.c_double), ("k2_ms", C.c_double), ("k3_ms", C.c_double),
+                ("k2_tasks", C.c_uint64), ("k2_cells", C.c_uint64),
+                ("k3_tasks", C.c_uint64), ("k3_cells", C.c_uint64),
+                ("gpu_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("host_stage_s", C.c_double * 12)]
+
+    STAGES = ("staging", "seed", "hits", "candidates", "score", "replay", "align", "results", "parse")
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "host_stage_s"}
+        d["host_stage_s"] = {k: self.host_stage_s[i] for i, k in enumerate(self.STAGES)}
+        return d
+
+
+def map_lib_path():
+    return os.path.join(_HERE, "libsmalt_b200_map.so")
+
+
+def load_map_library():
+    """Loads libsmalt_b200_map.so (and libsmalt_b200.so); raises if missing - no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    load_library()
+    p = map_lib_path()
+    if not os.path.exists(p):
+        raise ImportError("%s not built: `make -C smalt_b200/hostc` needs the reference tree; on the GPU box "
+                          "the prebuilt library travels with the repo snapshot" % p)
+    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    lib.smbm_open.argtypes = [C.POINTER(C.c_void_p), C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_char_p)]
+    lib.smbm_map_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_size_t), C.POINTER(MapStats)]
+    lib.smbm_sam_header.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    lib.smbm_free.argtypes = [C.c_void_p]
+    lib.smbm_free.restype = None
+    lib.smbm_close.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+class Mapper:
+    """`smalt map -n nthreads -O [options] index_prefix` held open in this process."""
+
+    def __init__(self, index_prefix, nthreads=1, options=()):
+        self.lib = load_map_library()
+        self._h = C.c_void_p()
+        opts = (C.c_char_p * max(1, len(options)))(*[o.encode() for o in options])
+        rc = self.lib.smbm_open(C.byref(self._h), index_prefix.encode(), int(nthreads), len(options), opts)
+        if rc:
+            raise SmbError(rc, "smbm_open(%s) failed (index missing, unsupported option or no CUDA device; "
+                               "there is no CPU fallback)" % index_prefix)
+        self.stats = MapStats()
+
+    def map_fastq(self, text):
+        """text: bytes-like FASTQ/FASTA -> SAM records (bytes, no header) in input order."""
+        buf = (C.c_char * len(text)).from_buffer_copy(text) if not isinstance(text, (bytes, bytearray)) else text
+        sam = C.c_void_p()
+        n = C.c_size_t(0)
+        p = C.cast(C.c_char_p(bytes(buf)) if isinstance(buf, bytearray) else C.c_char_p(buf), C.c_void_p)
+        rc = self.lib.smbm_map_fastq(self._h, p, len(text), C.byref(sam), C.byref(n), C.byref(self.stats))
+        if rc:
+            raise SmbError(rc, "smbm_map_fastq failed")
+        return C.string_at(sam, n.value)
+
+    def map_fastq_nocopy(self, text):
+        """like map_fastq but returns only the length of the SAM text (bench: no Python copy)"""
+        sam = C.c_void_p()
+        n = C.c_size_t(0)
+        rc = self.lib.smbm_map_fastq(self._h, C.cast(C.c_char_p(text), C.c_void_p), len(text), C.byref(sam),
+                                     C.byref(n), C.byref(self.stats))
+        if rc:
+            raise SmbError(rc, "smbm_map_fastq failed")
+        return n.value
+
+    def sam_header(self):
+        t = C.c_void_p()
+        n = C.c_size_t(0)
+        rc = self.lib.smbm_sam_header(self._h, C.byref(t), C.byref(n))
+        if rc:
+            raise SmbError(rc, "smbm_sam_header failed")
+        s = C.string_at(t, n.value)
+        self.lib.smbm_free(t)
+        return s
+
+    def close(self):
+        if self._h:
+            self.lib.smbm_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
