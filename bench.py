@@ -1,20 +1,28 @@
 #!/usr/bin/env python
 """bench.py - headline benchmark of the B200-native SMALT hot path.
 
-Metric (BASELINE.json): mapped reads/s (and SW GCUPS) on config C2 - 5 Mb synthetic
-genome, 1 M single-end 150 bp reads, k=13 s=6 - next to the reference's own CPU `smalt`
+Metric (BASELINE.json): mapped reads/s (and SW GCUPS) on config C2 - 5 Mb synthetic genome,
+1 M single-end 150 bp reads, smalt index -k 13 -s 6 - next to the reference's own CPU `smalt`
 timed on this box's host cores.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R]
-  python bench.py --impl reference ...      # the reference CPU arm (oracle/_ref/smalt)
+  python bench.py --impl reference ...      # the reference CPU arm (oracle/_ref/smalt map)
 
-One "step" = one pass of the hot path over one batch of R reads (default 1 M per GPU):
-K1 seed lookup + ranking + hit lists, K2 SW score, K3 banded DP + backtrace.
-`value` is reads/s with inputs resident in HBM (sum of CUDA-event kernel times);
-`e2e` is reads/s through the C ABI with host buffers (H2D of reads/tasks and D2H of every
-result inside the timed region, wall clock between device synchronisations).
-Multi-GPU: one process per GPU (torchrun), reads sharded, index + reference replicated,
-no collective on the data path (weak scaling).
+One "step" = one pass of the mapping path over one batch of R reads per GPU (default 1 M):
+FASTQ text in host memory -> SAM text in host memory through the in-process driver
+(include/smalt_b200_map.h: the reference's unmodified candidate selection / results / SAM
+writer around K1 seed lookup + hit lists, K2 SW score, K3 banded DP + backtrace on the GPU).
+
+  e2e    reads/s of that call, wall clock (host buffers in, host buffers out; every H2D/D2H
+         copy and all host stages inside the timed region) - the headline;
+  value  reads/s with inputs resident in HBM: reads / sum of the device times of all kernels
+         of a step (CUDA events on the launching stream, measured in a pass with ONE host
+         worker so that no two streams overlap);
+  roofline / roofline_k2 / roofline_k1: per kernel, against the measured integer-issue peak
+         (DP kernels; no tensor/HBM bound applies) or the measured HBM bandwidth (seed lookup).
+
+Multi-GPU: one process per GPU (torchrun), reads sharded by rank, index + reference
+replicated, no collective on the data path (weak scaling); host cores are split between ranks.
 """
 import argparse
 import json
@@ -34,9 +42,9 @@ GENOME_LEN = 5_000_000
 READ_LEN = 150
 K, NSKIP = 13, 6
 ERR = 0.02
-WINDOW_PAD = 21            # reference window = read + band margins (150 x 171)
-K2_DECOYS, K3_DECOYS = 3.42, 1.55   # reference-measured calls/read beyond the true locus
-OPS_PER_CELL = 7.5         # algorithmic integer ops per DP cell of K2
+# algorithmic integer operations per DP cell ("rooflines")
+K2_OPS_PER_CELL = 7.5
+K3_OPS_PER_CELL = 19.0
 
 
 def make_genome(seed=2, n=GENOME_LEN):
@@ -70,42 +78,20 @@ def simulate_reads(genome, n, seed, qlen=READ_LEN, err=ERR):
     return np.ascontiguousarray(reads), pos, strand, span
 
 
-def plan_tasks(reads_pos, strand, n, seed, qlen=READ_LEN, G=GENOME_LEN):
-    """PLACEHOLDER task planner (round 1): the true-locus window of every read plus random
-    decoy windows at the per-read rates the reference executes on this workload.  It is
-    replaced by the real candidate selection once that stage is built."""
-    from smalt_b200.capi import BAND_TASK_DTYPE, SW_TASK_DTYPE
-    rng = np.random.default_rng(seed)
-    wl = qlen + WINDOW_PAD
-    wstart = np.clip(reads_pos - 10, 0, G - wl)
-    nd2 = rng.poisson(K2_DECOYS, n)
-    nd3 = rng.poisson(K3_DECOYS, n)
-    def build(nd):
-        owner = np.concatenate([np.arange(n), np.repeat(np.arange(n), nd)])
-        ws = np.concatenate([wstart, rng.integers(0, G - wl, int(nd.sum()))])
-        st = np.concatenate([strand, rng.integers(0, 2, int(nd.sum())).astype(np.uint8)])
-        return owner, ws, st
-    o2, w2, s2 = build(nd2)
-    sw = np.zeros(len(o2), SW_TASK_DTYPE)
-    sw["read_off"] = o2.astype(np.uint64) * qlen
-    sw["ref_off"] = w2
-    sw["read_len"] = qlen
-    sw["ref_len"] = wl
-    sw["flags"] = 2 | s2
-    o3, w3, s3 = build(nd3)
-    bt = np.zeros(len(o3), BAND_TASK_DTYPE)
-    bt["read_off"] = o3.astype(np.uint64) * qlen
-    bt["ref_off"] = w3
-    bt["read_len"] = qlen
-    bt["ref_len"] = wl
-    bt["flags"] = 2 | s3
-    off = np.concatenate([reads_pos - wstart, np.full(len(o3) - n, 10)])
-    bt["l_edge"] = -off - 9
-    bt["r_edge"] = -off + 9
-    bt["p_left"], bt["p_right"] = 0, qlen - 1
-    bt["u_left"], bt["u_right"] = 0, wl - 1
-    bt["minscore"], bt["minscorlen"] = 50, 30
-    return sw, bt
+def fastq_text(reads, first=0):
+    """4-line FASTQ text of the code matrix reads[n, qlen] (names r<first+i>, quality 'I')."""
+    n, qlen = reads.shape
+    let = np.frombuffer(b"ACGT", np.uint8)
+    names = np.char.add("@r", np.arange(first, first + n).astype(str)).astype("S")
+    w = names.dtype.itemsize
+    rec = np.full((n, w + 1 + qlen + 3 + qlen + 1), ord("\n"), np.uint8)
+    nm = np.frombuffer(names.tobytes(), np.uint8).reshape(n, w)
+    rec[:, :w] = nm                       # padded with NULs, removed below
+    rec[:, w + 1:w + 1 + qlen] = let[reads]
+    rec[:, w + 2 + qlen] = ord("+")
+    rec[:, w + 4 + qlen:w + 4 + 2 * qlen] = ord("I")
+    flat = rec.reshape(-1)
+    return flat[flat != 0].tobytes()
 
 
 class ClockSampler:
@@ -152,41 +138,44 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def write_workload_files(tmp, genome, reads):
-    """index files (own builder, byte-identical to `smalt index`) + FASTQ for the CPU arm"""
+def write_index_files(tmp, genome):
+    """index files (own builder, byte-identical to `smalt index -k 13 -s 6`)"""
     from smalt_b200 import indexer
     pref = os.path.join(tmp, "c2")
     ix = indexer.build_index([genome], K, NSKIP)
     indexer.write_smi(pref, ix)
     indexer.write_sma(pref, ["chr1"], [genome])
-    let = np.frombuffer(b"ACGT", np.uint8)
+    return pref, ix
+
+
+def write_workload_files(tmp, genome, reads):
+    pref, ix = write_index_files(tmp, genome)
     fq = os.path.join(tmp, "reads.fq")
-    qual = "I" * reads.shape[1]
-    with open(fq, "w") as f:
-        for i in range(len(reads)):
-            f.write("@r%d\n%s\n+\n%s\n" % (i, let[reads[i]].tobytes().decode(), qual))
+    with open(fq, "wb") as f:
+        f.write(fastq_text(reads))
     return pref, fq, ix
 
 
-def cpu_reference_rate(genome, reads, threads):
-    """reads/s of the UNMODIFIED reference (`oracle/_ref/smalt map -n threads -O`) on `reads`."""
-    smalt = os.path.join(ROOT, "oracle", "_ref", "smalt")
-    if not os.path.exists(smalt):
-        return None, "oracle/_ref/smalt not built"
-    with tempfile.TemporaryDirectory() as tmp:
-        pref, fq, _ = write_workload_files(tmp, genome, reads)
-        cmd = [smalt, "map", "-n", str(threads), "-O", "-o", os.path.join(tmp, "out.sam"), pref, fq]
-        t0 = time.time()
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
-        dt = time.time() - t0
-        if r.returncode != 0:
-            return None, "smalt map failed: " + r.stderr.decode()[-200:]
-        mapped = 0
-        with open(os.path.join(tmp, "out.sam")) as f:
-            for ln in f:
-                if ln[0] != "@" and not (int(ln.split("\t", 2)[1]) & 4):
-                    mapped += 1
-    return dict(rate=len(reads) / dt, seconds=dt, mapped=mapped), None
+def count_mapped(sam_path_or_bytes):
+    data = sam_path_or_bytes if isinstance(sam_path_or_bytes, bytes) else open(sam_path_or_bytes, "rb").read()
+    mapped = total = 0
+    for ln in data.split(b"\n"):
+        if not ln or ln[:1] == b"@":
+            continue
+        total += 1
+        if not int(ln.split(b"\t", 2)[1]) & 4:
+            mapped += 1
+    return mapped, total
+
+
+def run_cli(exe, threads, pref, fq, out, env=None):
+    cmd = [exe, "map", "-n", str(threads), "-O", "-o", out, pref, fq]
+    t0 = time.time()
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    dt = time.time() - t0
+    if r.returncode != 0:
+        return None, "%s failed: %s" % (os.path.basename(exe), r.stderr.decode()[-200:])
+    return dt, None
 
 
 def host_threads():
@@ -196,7 +185,7 @@ def host_threads():
         return max(1, min(os.cpu_count() or 1, 64))
 
 
-def dist_setup(n_gpus):
+def dist_setup():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -210,25 +199,41 @@ def dist_setup(n_gpus):
     return rank, world, local, dist
 
 
+def workload_config(nreads, world=1):
+    return {"workload": "C2: 5 Mb synthetic genome (uniform ACGT, seed 2), %d single-end %d bp reads per GPU, "
+                        "%.0f%% error, smalt index -k %d -s %d" % (nreads, READ_LEN, ERR * 100, K, NSKIP),
+            "reads_per_gpu": nreads, "gpus": world,
+            "l2": "inputs larger than L2 (FASTQ text, task lists and outputs of a step are > 126 MB)"}
+
+
 def run_reference_arm(args):
+    """the reference's own CPU `smalt map` on this box's host cores (rank 0 only)"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    smalt = os.path.join(ROOT, "oracle", "_ref", "smalt")
+    if not os.path.exists(smalt):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/smalt not built"}))
         return
     genome = make_genome()
     nsample = args.ref_sample
     reads, _, _, _ = simulate_reads(genome, nsample, seed=43)
     threads = host_threads()
     rates, mapped = [], 0
-    for it in range(args.warmup + args.steps):
-        res, err = cpu_reference_rate(genome, reads, threads)
-        if res is None:
-            print(json.dumps({"impl": "reference", "unavailable": err}))
-            return
-        if it >= args.warmup:
-            rates.append(res["rate"])
-            mapped = res["mapped"]
+    with tempfile.TemporaryDirectory() as tmp:
+        pref, fq, _ = write_workload_files(tmp, genome, reads)
+        out = os.path.join(tmp, "out.sam")
+        for it in range(args.warmup + args.steps):
+            dt, err = run_cli(smalt, threads, pref, fq, out)
+            if dt is None:
+                print(json.dumps({"impl": "reference", "unavailable": err}))
+                return
+            if it >= args.warmup:
+                rates.append(nsample / dt)
+        mapped, _ = count_mapped(out)
     v = float(np.mean(rates))
-    sample = "first %d reads of the C2 read set per step, smalt map -n %d -O incl. index load" % (nsample, threads)
+    sample = ("first %d reads of the C2 read set per step; whole `smalt map -n %d -O` program (index load, FASTQ "
+              "parsing, SAM output)" % (nsample, threads))
     print(json.dumps({
         "impl": "reference", "metric": "mapped reads/sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * nsample / v, "higher_is_better": True,
@@ -239,14 +244,6 @@ def run_reference_arm(args):
         "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def workload_config(nreads):
-    return {"workload": "C2: 5 Mb synthetic genome (uniform ACGT, seed 2), %d single-end %d bp reads, %.0f%% error, "
-                        "smalt index -k %d -s %d" % (nreads, READ_LEN, ERR * 100, K, NSKIP),
-            "reads_per_gpu": nreads, "l2": "inputs larger than L2 (reads + task lists + outputs > 126 MB)",
-            "tasks": "PLACEHOLDER planner: true-locus window + decoys at the reference's measured call rates "
-                     "(K2 4.42/read, K3 2.55/read); K1 runs on every read x strand"}
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -254,77 +251,63 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-sample", type=int, default=100_000)
-    ap.add_argument("--cpu-sample", type=int, default=100_000)
+    ap.add_argument("--ref-sample", type=int, default=250_000)
+    ap.add_argument("--cpu-sample", type=int, default=250_000)
+    ap.add_argument("--threads", type=int, default=0, help="host worker threads per GPU (0: cores/GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
         return
 
-    rank, world, local, dist = dist_setup(args.gpus)
-    import smalt_b200
-    from smalt_b200 import indexer
-    from smalt_b200.capi import HIT_REQ_DTYPE
-    from smalt_b200.seqpack import pack3
+    rank, world, local, dist = dist_setup()
+    from smalt_b200.capi import Context
+    from smalt_b200.mapper import Mapper
 
     n = args.reads
+    cores = host_threads()
+    threads = args.threads or max(1, int(round(1.5 * cores / world)))
     genome = make_genome()
+    # reads are sharded by rank: rank r maps reads [r*n, (r+1)*n) of the job
     reads, pos, strand, span = simulate_reads(genome, n, seed=43 + 1000 * rank)
-    ix = indexer.as_loaded(indexer.build_index([genome], K, NSKIP))
-    ctx = smalt_b200.Context(local)
-    ctx.index_upload(ix)
-    words = pack3(np.concatenate([genome, np.array([7], np.uint8)]))
-    ctx.refseq_upload(words, len(genome) + 1, np.array([0, len(genome)], np.uint64))
-    sw, bt = plan_tasks(pos, strand, n, seed=7 + rank)
-    arena = reads.reshape(-1)
-    read_off = np.arange(n, dtype=np.uint64) * READ_LEN
-    read_len = np.full(n, READ_LEN, np.uint32)
-    req = np.zeros(2 * n, HIT_REQ_DTYPE)
-    req["lo"], req["hi"] = 0, len(genome)
-    req["read"] = np.repeat(np.arange(n, dtype=np.uint32), 2)
-    req["strand"] = np.tile(np.array([0, 1], np.uint8), n)
-    req["nhit_max"], req["use_short"] = 10000, 1
-    k2_cells = float((sw["read_len"].astype(np.float64) * sw["ref_len"]).sum())
+    text = fastq_text(reads, first=rank * n)
+    tmpdir = tempfile.TemporaryDirectory()
+    tmp = tmpdir.name
+    pref, ix = write_index_files(tmp, genome)
 
     def barrier():
         if dist is not None:
             dist.barrier()
 
-    def step():
-        """one pass of the hot path through the C ABI with host buffers"""
-        kms = {}
-        ctx.arena_upload(arena)
-        info, _ = ctx.seed_batch(read_off, read_len, None, 10000, 16384, 0, full=False)
-        kms["k1_seed"] = ctx.last_kernel_ms
-        sq, first, herr = ctx.hits_batch(req, max_hits=48 * n)
-        kms["k1_hits"] = ctx.last_kernel_ms
-        scores, serr = ctx.sw_score(sw)
-        kms["k2"] = ctx.last_kernel_ms
-        res, rfirst, diff, berr, cells = ctx.band_align(bt, max_results=2 * len(bt), max_diff=24 * len(bt))
-        kms["k3"] = ctx.last_kernel_ms
-        d2h = info.nbytes + sq.nbytes + first.nbytes + scores.nbytes + serr.nbytes + res.nbytes + diff.nbytes + \
-            rfirst.nbytes + berr.nbytes
-        h2d = arena.nbytes + read_off.nbytes + read_len.nbytes + req.nbytes + sw.nbytes + bt.nbytes
-        out = dict(kms=kms, cells=cells, nhits=len(sq), h2d=h2d, d2h=d2h, nres=len(res),
-                   mapped=int((scores[:n] >= 50).sum()))
-        return out
+    # ---- pass 1: device-resident kernel times, ONE host worker (no overlapping streams) ----
+    m = Mapper(pref, 1)
+    m.map_fastq_nocopy(fastq_text(reads[:max(1, n // 8)]))   # warm-up of this mapper
+    m.map_fastq_nocopy(text)
+    s1 = m.stats.as_dict()
+    m.close()
+    dev_ms = s1["k1_ms"] + s1["k2_ms"] + s1["k3_ms"]
 
+    # ---- pass 2: e2e through the in-process driver, all host workers ----
+    m = Mapper(pref, threads)
     for _ in range(args.warmup):
-        step()
-    launches0 = ctx.total_kernel_launches
+        m.map_fastq_nocopy(text)
+    c0 = m.stats.as_dict()
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     t0 = time.perf_counter()
-    outs = [step() for _ in range(args.steps)]
+    sam_bytes = 0
+    for _ in range(args.steps):
+        sam_bytes = m.map_fastq_nocopy(text)
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
-    launches = ctx.total_kernel_launches - launches0
+    c1 = m.stats.as_dict()
+    sam = m.map_fastq(fastq_text(reads[:max(1, n // 50)]))
+    mapped, total = count_mapped(sam)
+    m.close()
 
-    kms_tot = {k: float(np.mean([o["kms"][k] for o in outs])) for k in outs[0]["kms"]}
-    dev_ms = sum(kms_tot.values())           # device time of the kernels of one step (CUDA events)
     wall_ms = 1e3 * wall / args.steps
     if dist is not None:
         import torch
@@ -333,55 +316,87 @@ def main():
         dev_ms, wall_ms = float(t[0]), float(t[1])
     if rank != 0:
         return
-    o = outs[-1]
+
     value = world * n / (dev_ms * 1e-3)
     e2e = world * n / (wall_ms * 1e-3)
-    k2_gcups = k2_cells / (kms_tot["k2"] * 1e-3) / 1e9
-    k3_gcups = o["cells"] / (kms_tot["k3"] * 1e-3) / 1e9
-    peaks = ctx.int_peak()
-    peak_gcups = peaks[0] / OPS_PER_CELL
+    launches = (c1["gpu_launches"] - c0["gpu_launches"]) // args.steps
+    h2d = (c1["h2d_bytes"] - c0["h2d_bytes"]) // args.steps
+    d2h = (c1["d2h_bytes"] - c0["d2h_bytes"]) // args.steps
+    k2_gcups = s1["k2_cells"] / (s1["k2_ms"] * 1e-3) / 1e9
+    k3_gcups = s1["k3_cells"] / (s1["k3_ms"] * 1e-3) / 1e9
+    ctx = Context(local)
+    peaks = ctx.int_peak()          # giga thread-ops/s: VIADDMNMX, VIMNMX3, IADD+IMNMX
+    ctx.close()
+    k2_peak = peaks[0] / K2_OPS_PER_CELL
+    k3_peak = peaks[2] / K3_OPS_PER_CELL
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         peak_src = "MEASURED_PEAKS.json"
     except Exception:
-        hbm_peak, peak_src = 6650.0, "fallback"
-    # K1 algorithmic bytes: per lookup 8 (idx pair) + 4*ceil(log2(bucket+1)) + 8 (posidx pair);
-    # per hit 4 (pos) + 8 (sqdat) + 16 (sort)
+        hbm_peak, peak_src = 6650.0, "fallback of B200_PROFILING.md"
+    # K1 algorithmic bytes: per lookup 8 (idx pair) + 4*ceil(log2(bucket+1)) (wordidx probes) +
+    # 8 (posidx pair); per hit 4 (pos) + 8 (sqdat) + 16 (sort)
     nlook = 2 * n * (READ_LEN - K + 1)
     bucket = max(1.0, ix["nwords"] / ix["nkeys"])
-    k1_bytes = nlook * (8 + 4 * np.ceil(np.log2(bucket + 1)) + 8) + o["nhits"] * 28.0
-    k1_gbs = k1_bytes / ((kms_tot["k1_seed"] + kms_tot["k1_hits"]) * 1e-3) / 1e9
+    k1_bytes = nlook * (8 + 4 * np.ceil(np.log2(bucket + 1)) + 8)
+    k1_gbs = k1_bytes / (s1["k1_ms"] * 1e-3) / 1e9
+    kernel_ms = {"k1_seed_hits": s1["k1_ms"], "k2_sw_score": s1["k2_ms"], "k3_band_align": s1["k3_ms"]}
+    roof_k3 = {"kernel": "band_kernel<true> (K3: banded DP + backtrace)", "bound": "alu", "achieved": k3_gcups,
+               "peak": k3_peak, "unit": "GCUPS", "frac": k3_gcups / k3_peak if k3_peak else None, "traffic": None,
+               "note": "integer-issue bound (no tensor/HBM bound applies to this DP): peak = measured IADD+IMNMX "
+                       "rate %.0f Gop/s / %.1f algorithmic ops per cell" % (peaks[2], K3_OPS_PER_CELL)}
+    roof_k2 = {"kernel": "sw_score_kernel (K2: SW score)", "bound": "alu", "achieved": k2_gcups, "peak": k2_peak,
+               "unit": "GCUPS", "frac": k2_gcups / k2_peak if k2_peak else None, "traffic": None,
+               "note": "DPX issue bound: peak = measured VIADDMNMX rate %.0f Gop/s / %.1f ops per cell"
+                       % (peaks[0], K2_OPS_PER_CELL)}
+    roof_k1 = {"kernel": "seed_kernel + hits_kernel (K1)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak,
+               "unit": "GB/s", "frac": k1_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+               "note": "dependent 4-byte index probes (latency bound); the 5 Mb index (11 MB) is L2 resident"}
+    dominant = max(kernel_ms, key=kernel_ms.get)
     line = {
         "metric": "mapped reads/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": wall_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "i32 DPX (K2), i16x2 (K3), u32/u64 (K1)", "data": "synthetic",
-        "config": workload_config(n),
-        "timing": "value: CUDA events around the kernels of a step (inputs resident); e2e: wall clock between "
-                  "synchronisations incl. H2D/D2H through the C ABI; max over ranks",
-        "kernel_ms": kms_tot, "sw_gcups": k2_gcups, "band_gcups": k3_gcups,
-        "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(o["h2d"]),
-                "d2h_bytes_per_step": int(o["d2h"]), "ms_per_step": wall_ms},
+        "config": dict(workload_config(n, world), host_workers_per_gpu=threads, host_cores=cores),
+        "timing": "value: reads / sum of CUDA-event kernel times of a step (one host worker, inputs resident); "
+                  "e2e: wall clock of smbm_map_fastq (FASTQ text in host memory -> SAM text in host memory), "
+                  "max over ranks",
+        "device_ms_per_step": dev_ms, "kernel_ms": kernel_ms, "sw_gcups": k2_gcups, "band_gcups": k3_gcups,
+        "tasks_per_step": {"k2_tasks": s1["k2_tasks"], "k2_cells": s1["k2_cells"], "k3_tasks": s1["k3_tasks"],
+                           "k3_cells": s1["k3_cells"]},
+        "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": wall_ms, "sam_bytes_per_step": int(sam_bytes),
+                "host_stage_core_s": c1["host_stage_s"]},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"kernel": "sw_score_kernel (K2)", "bound": "alu", "achieved": k2_gcups, "peak": peak_gcups,
-                     "unit": "GCUPS", "frac": k2_gcups / peak_gcups if peak_gcups else None, "traffic": None,
-                     "note": "no tensor/HBM bound applies: integer DPX issue bound; peak = measured VIADDMNMX "
-                             "rate %.0f Gop/s / %.1f ops per cell" % (peaks[0], OPS_PER_CELL)},
-        "roofline_hbm": {"kernel": "seed_kernel + hits_kernel (K1)", "bound": "hbm", "achieved": k1_gbs,
-                         "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak, "traffic": None,
-                         "peak_source": peak_src,
-                         "note": "latency bound dependent 4-byte loads; the 5 Mb index is L2 resident"},
-        "mapped_fraction": o["mapped"] / n,
+        "roofline": roof_k3 if dominant == "k3_band_align" else roof_k2,
+        "roofline_k2": roof_k2, "roofline_k3": roof_k3, "roofline_k1": roof_k1,
+        "mapped_fraction": mapped / max(total, 1),
     }
-    if not args.no_cpu_baseline and world == 1:
+    if world == 1 and not args.no_cli:
+        # the same job as a whole program, like the reference arm runs it (process start, CUDA
+        # start-up, index load, file I/O included)
+        fq = os.path.join(tmp, "reads.fq")
+        with open(fq, "wb") as f:
+            f.write(text)
+        exe = os.path.join(ROOT, "smalt_b200", "bin", "smalt_b200")
+        dt, err = run_cli(exe, cores, pref, fq, os.path.join(tmp, "cli.sam"))
+        line["e2e_cli"] = ({"value": n / dt, "unit": "reads/s", "seconds": dt,
+                            "what": "whole `smalt_b200 map -n %d -O` program on the same %d reads" % (cores, n)}
+                           if dt else {"value": None, "unavailable": err})
+    if world == 1 and not args.no_cpu_baseline:
         ns = min(args.cpu_sample, n)
-        threads = host_threads()
-        res, err = cpu_reference_rate(genome, reads[:ns], threads)
-        if res is not None:
-            line["cpu_baseline"] = {"value": res["rate"], "unit": "reads/s", "cores": threads, "kind": "reference",
-                                    "sample": "first %d reads of this workload, oracle/_ref/smalt map -n %d -O "
-                                              "(whole program incl. index load, %.1f s)" % (ns, threads, res["seconds"])}
+        smalt = os.path.join(ROOT, "oracle", "_ref", "smalt")
+        fq = os.path.join(tmp, "sample.fq")
+        with open(fq, "wb") as f:
+            f.write(fastq_text(reads[:ns]))
+        dt, err = run_cli(smalt, cores, pref, fq, os.path.join(tmp, "ref.sam")) if os.path.exists(smalt) else \
+            (None, "oracle/_ref/smalt not built")
+        if dt:
+            line["cpu_baseline"] = {"value": ns / dt, "unit": "reads/s", "cores": cores, "kind": "reference",
+                                    "sample": "first %d reads of this workload, whole `oracle/_ref/smalt map -n %d "
+                                              "-O` program (%.1f s)" % (ns, cores, dt)}
         else:
-            line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": threads, "kind": "reference",
+            line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": cores, "kind": "reference",
                                     "sample": "unavailable: " + err}
     print(json.dumps(line))
 

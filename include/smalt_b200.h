@@ -64,6 +64,9 @@ typedef struct smb_ctx smb_ctx;
 
 /* ----------------------------- context ---------------------------------- */
 int smb_ctx_create(smb_ctx **ctx, int device);
+/* Optional: initialises CUDA on `device` and loads the kernels.  A driver calls it from a helper
+ * thread at program start so that the ~0.7 s of CUDA start-up overlap its own index loading. */
+int smb_device_warmup(int device);
 void smb_ctx_destroy(smb_ctx *ctx);
 const char *smb_last_error(const smb_ctx *ctx);
 /* library version string, e.g. "smalt-b200 0.1 sm_100a" */

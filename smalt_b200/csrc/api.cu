@@ -144,6 +144,16 @@ extern "C" {
 
 const char *smb_version(void) { return "smalt-b200 0.1 (sm_100a)"; }
 
+int smb_device_warmup(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return SMB_ERR_NODEVICE;
+  if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) return SMB_ERR_CUDA;
+  if (warm_sw() != cudaSuccess || warm_band() != cudaSuccess || warm_seed() != cudaSuccess ||
+      warm_compact() != cudaSuccess)
+    return SMB_ERR_CUDA;
+  return SMB_OK;
+}
+
 int smb_ctx_create(smb_ctx **out, int device) {
   if (!out) return SMB_ERR_ARG;
   *out = nullptr;

@@ -386,4 +386,11 @@ size_t band_gring_words(const BandPlan &plan) {
   return need;
 }
 
+cudaError_t warm_band() {
+  cudaFuncAttributes a;
+  cudaError_t e = cudaFuncGetAttributes(&a, band_kernel<true>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, band_kernel<false>);
+  return e;
+}
+
 }  // namespace smb

@@ -137,6 +137,12 @@ cudaError_t launch_hits(const Index &ix, const HitArgs &a, bool fill, cudaStream
 cudaError_t launch_seed(const Index &ix, const uint8_t *arena, const SeedArgs &a, cudaStream_t st,
                         int *nlaunch);
 
+// forces the (lazily loaded) kernels of the library onto the device
+cudaError_t warm_sw();
+cudaError_t warm_band();
+cudaError_t warm_seed();
+cudaError_t warm_compact();
+
 cudaError_t run_int_peak(int mode, int sm_count, int *d_out, int iters, cudaStream_t st, double *ops);
 
 }  // namespace smb

@@ -161,4 +161,11 @@ cudaError_t launch_compact_gather(const smb_ali_result *slots, const uint32_t *n
   return cudaGetLastError();
 }
 
+cudaError_t warm_compact() {
+  cudaFuncAttributes a;
+  cudaError_t e = cudaFuncGetAttributes(&a, scan_tiles);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, gather_results);
+  return e;
+}
+
 }  // namespace smb

@@ -460,4 +460,12 @@ cudaError_t launch_hits(const Index &ix, const HitArgs &a, bool fill, cudaStream
   return cudaGetLastError();
 }
 
+cudaError_t warm_seed() {
+  cudaFuncAttributes a;
+  cudaError_t e = cudaFuncGetAttributes(&a, seed_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, hits_kernel<true>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, hits_kernel<false>);
+  return e;
+}
+
 }  // namespace smb

@@ -232,4 +232,11 @@ cudaError_t launch_sw_score(const Scoring &sc, const SeqSrc &src, const smb_sw_t
   return cudaSuccess;
 }
 
+cudaError_t warm_sw() {
+  cudaFuncAttributes a;
+  cudaError_t e = cudaFuncGetAttributes(&a, sw_score_kernel<5>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, sw_score_kernel<4>);
+  return e;
+}
+
 }  // namespace smb

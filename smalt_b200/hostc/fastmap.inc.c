@@ -309,6 +309,13 @@ static void *fm_worker_main(void *arg)
 {
   FmWorker *w = (FmWorker *) arg;
   FastMap *fm = w->fm;
+  int rc = fm_worker_setup(w, fm, w->id);
+  if (rc) {
+    pthread_mutex_lock(&fm->lock);
+    if (!fm->errcode) fm->errcode = rc;
+    pthread_mutex_unlock(&fm->lock);
+    return NULL;
+  }
   for (;;) {
     size_t c;
     int stop;
@@ -393,7 +400,10 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
     struct timespec ts;
     double t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &ts); t0 = ts.tv_sec + 1e-9 * ts.tv_nsec;
-    for (i = 0; i < nworkers && !errcode; i++) errcode = fm_worker_setup(g_fm_workers + i, &fm, i);
+    /* the process-wide part (CUDA context, index + reference upload) once, the per-worker part
+     * (stream, report writer, memfd) by the workers themselves */
+    if (smbShimInit(macop->htp, macop->ssp, macop->codecp, macop->scormtxp)) errcode = ERRCODE_FAILURE;
+    for (i = 0; i < nworkers; i++) { g_fm_workers[i].fm = &fm; g_fm_workers[i].id = i; }
     clock_gettime(CLOCK_MONOTONIC, &ts); t1 = ts.tv_sec + 1e-9 * ts.tv_nsec;
     if (getenv("SMALT_B200_TIMING"))
       fprintf(stderr, "smalt_b200 timing: fastmap set-up of %d workers %.3f s (at %.3f s); %zu blocks of ~%zu reads\n",

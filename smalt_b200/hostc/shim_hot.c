@@ -68,6 +68,8 @@ static int shim_device(void)
   return g_device;
 }
 
+int smbShimDevice(void) { return shim_device(); }
+
 extern void smbShimHashTableArrays(const HashTable *htp, int *typ, int *wordlen, int *nskip,
 				   int *nbits_key, int *nbits_lo, uint32_t *npos, uint32_t *nwords,
 				   const uint32_t **idx, const uint32_t **pos,

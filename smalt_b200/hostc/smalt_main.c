@@ -464,17 +464,33 @@ int smbm_close(smbm_mapper *m)
   return SMB_OK;
 }
 
+static void *gpu_warmup_main(void *arg)
+{
+  (void) arg;
+  smb_device_warmup(smbShimDevice());
+  return NULL;
+}
+
 int smalt_b200_cli_main(int argc, char *argv[])
 {
   struct timespec ts;
-  int rv;
+  pthread_t warm;
+  int rv, warming = 0;
   clock_gettime(CLOCK_MONOTONIC, &ts);
   g_t0 = ts.tv_sec + 1e-9 * ts.tv_nsec;
   atexit(flushStats);
+  /* CUDA start-up (~0.7 s) overlaps the reference's option parsing and index loading */
+  if (argc > 1 && (!strcmp(argv[1], "map") || !strcmp(argv[1], "sample")))
+    warming = !pthread_create(&warm, NULL, gpu_warmup_main, NULL);
   rv = ref_smalt_main(argc, argv);
+  if (warming) pthread_join(warm, NULL);
   if (getenv("SMALT_B200_TIMING")) {
     clock_gettime(CLOCK_MONOTONIC, &ts);
     fprintf(stderr, "smalt_b200 timing: main %.3f s\n", ts.tv_sec + 1e-9 * ts.tv_nsec - g_t0);
   }
-  return rv;
+  /* everything is written and closed by the reference's own clean-up; skip the CUDA runtime's
+   * atexit tear-down (~0.3 s) */
+  flushStats();
+  fflush(NULL);
+  _exit(rv);
 }
