@@ -34,7 +34,7 @@ typedef struct {
   uint64_t gpu_launches;     /* kernels launched by this process so far */
   uint64_t h2d_bytes, d2h_bytes; /* bytes copied host->device / device->host by this process so far */
   double host_stage_s[12];   /* summed over worker threads: staging, seed, hits, candidates, score,
-				replay, align, results, parse, (reserved) */
+				replay, align, results, parse, and inside results: add, sort+filter, emit */
 } smbm_stats;
 
 /* Loads <index_prefix>.smi/.sma (hashTableRead hashidx.c:1257, seqSetReadBinFil sequence.c:2521),

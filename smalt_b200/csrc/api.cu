@@ -66,6 +66,7 @@ struct smb_ctx {
   cudaEvent_t ev_done = nullptr;  // blocking-sync event: waiting host threads sleep instead of spinning
   HostBuf stage;                  // pinned staging for the library's own host-side arrays
   DevBuf cmp;                     // K3 output compaction scratch
+  DevBuf ticket;                  // work counters of persistent kernels
   Scoring sc;
   SeqSrc src{nullptr, nullptr, 0};
   DevBuf arena, packed, tasks, out_a, out_b, scratch, dirs, diff, offs;
@@ -148,7 +149,8 @@ int smb_device_warmup(int device) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return SMB_ERR_NODEVICE;
   if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) return SMB_ERR_CUDA;
-  if (warm_sw() != cudaSuccess || warm_band() != cudaSuccess || warm_seed() != cudaSuccess ||
+  if (warm_sw() != cudaSuccess || warm_band() != cudaSuccess || warm_band_warp() != cudaSuccess ||
+      warm_seed() != cudaSuccess ||
       warm_compact() != cudaSuccess)
     return SMB_ERR_CUDA;
   return SMB_OK;
@@ -173,6 +175,10 @@ int smb_ctx_create(smb_ctx **out, int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   make_scoring(ctx->sc, 1, -2, -4, -3);
+  if (ctx->ticket.ensure(256) != cudaSuccess) {
+    smb_ctx_destroy(ctx);
+    return SMB_ERR_CUDA;
+  }
   *out = ctx;
   return SMB_OK;
 }
@@ -183,7 +189,7 @@ void smb_ctx_destroy(smb_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf *bufs[] = {&ctx->arena, &ctx->packed, &ctx->tasks, &ctx->out_a, &ctx->out_b,
                     &ctx->scratch, &ctx->dirs, &ctx->diff, &ctx->offs, &ctx->index, &ctx->qualbuf,
-                    &ctx->seed_meta, &ctx->seed_u32, &ctx->seed_u8, &ctx->hit_meta, &ctx->hit_data, &ctx->cmp};
+                    &ctx->seed_meta, &ctx->seed_u32, &ctx->seed_u8, &ctx->hit_meta, &ctx->hit_data, &ctx->cmp, &ctx->ticket};
   for (DevBuf *b : bufs) b->release();
   ctx->stage.release();
   if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
@@ -369,7 +375,7 @@ int smb_band_score_batch(smb_ctx *ctx, const smb_band_task *tasks, int ntasks, i
   CU(h2d(d_order, plan.order.data(), (size_t)ntasks * sizeof(int), st));
   CU(cudaEventRecord(ctx->ev0, st));
   CU(launch_band(ctx->sc, ctx->src, ctx->tasks.as<smb_band_task>(), plan, d_order, false, d_scores, bo, 0,
-                 nullptr, nullptr, nullptr, nullptr, d_gring, st, &nl));
+                 nullptr, nullptr, nullptr, nullptr, d_gring, ctx->ticket.as<int>(), ctx->sm_count, st, &nl));
   CU(cudaEventRecord(ctx->ev1, st));
   CU(d2h(scores, d_scores, (size_t)ntasks * sizeof(int32_t), st));
   CU(d2h(errs, d_errs, (size_t)ntasks * sizeof(int32_t), st));
@@ -440,7 +446,7 @@ static int band_align_pass(smb_ctx *ctx, const smb_band_task *tasks, const std::
   CU(h2d(d_order, plan.order.data(), (size_t)n * sizeof(int), st));
   CU(cudaEventRecord(ctx->ev0, st));
   CU(launch_band(ctx->sc, ctx->src, ctx->tasks.as<smb_band_task>(), plan, d_order, true, nullptr, bo, max_res,
-                 d_dir_off, ctx->dirs.as<uint32_t>(), d_diff_off, d_diff_cap, d_gring, st, nlaunch));
+                 d_dir_off, ctx->dirs.as<uint32_t>(), d_diff_off, d_diff_cap, d_gring, ctx->ticket.as<int>(), ctx->sm_count, st, nlaunch));
   CU(cudaEventRecord(ctx->ev1, st));
   h_res.resize((size_t)n * max_res);
   h_nres.resize((size_t)n);
@@ -481,7 +487,9 @@ static int band_align_fast(smb_ctx *ctx, const smb_band_task *tasks, int ntasks,
     const smb_band_task &t = tasks[i];
     Band b;
     uint64_t words = 2;
-    if (!band_init(b, t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
+    if (!band_warp_eligible(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
+                            (int)t.ref_len) &&
+        !band_init(b, t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
                    (int)t.ref_len)) {
       const int bw0 = t.r_edge - t.l_edge + 1;
       int w = (bw0 <= 0) ? (b.q_len - b.q_left) : bw0;
@@ -535,7 +543,8 @@ static int band_align_fast(smb_ctx *ctx, const smb_band_task *tasks, int ntasks,
   int nl = 0;
   CU(cudaEventRecord(ctx->ev0, st));
   CU(launch_band(ctx->sc, ctx->src, ctx->tasks.as<smb_band_task>(), plan, d_order, true, nullptr, bo, max_res,
-                 d_dir_off, ctx->dirs.as<uint32_t>(), d_diff_off, d_diff_cap, ctx->scratch.as<uint32_t>(), st, &nl));
+                 d_dir_off, ctx->dirs.as<uint32_t>(), d_diff_off, d_diff_cap, ctx->scratch.as<uint32_t>(), ctx->ticket.as<int>(),
+                 ctx->sm_count, st, &nl));
   CU(launch_compact_scan(d_nres, d_dused, d_errs, n, d_tile_res, d_tile_diff, d_tot, d_first, d_diff_first, st, &nl));
   CU(cudaEventRecord(ctx->ev1, st));
   CompactTotals *h_tot = (CompactTotals *)((char *)ctx->stage.p + stage_tail);

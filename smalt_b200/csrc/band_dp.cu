@@ -328,9 +328,16 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, BandPlan &p
   std::vector<int> wc((size_t)ntasks);
   int count[32] = {0};
   auto cls = [](int wcap) { int c = 0; while ((32 << c) < wcap) ++c; return c; };
+  constexpr int WARP_CLS = 31;  // pseudo class of the warp-per-task kernel (always last in `order`)
   for (int i = 0; i < ntasks; ++i) {
-    const int need = ring_need(h_tasks[i], !align);
-    wc[(size_t)i] = cls(pow2_at_least(need + 1));
+    const smb_band_task &t = h_tasks[i];
+    if (align && band_warp_eligible(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
+                                    (int)t.ref_len)) {
+      wc[(size_t)i] = WARP_CLS;
+    } else {
+      const int need = ring_need(t, !align);
+      wc[(size_t)i] = cls(pow2_at_least(need + 1));
+    }
     count[wc[(size_t)i]]++;
   }
   int start[33];
@@ -339,8 +346,10 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, BandPlan &p
   int fill[32];
   for (int c = 0; c < 32; ++c) fill[c] = start[c];
   for (int i = 0; i < ntasks; ++i) plan.order[(size_t)fill[wc[(size_t)i]]++] = i;
-  for (int c = 0; c < 32; ++c)
+  for (int c = 0; c < WARP_CLS; ++c)
     if (count[c]) plan.classes.push_back(BandPlan::Class{32 << c, start[c], count[c]});
+  plan.warp_start = start[WARP_CLS];
+  plan.warp_count = count[WARP_CLS];
 }
 
 cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_task *d_tasks,
@@ -348,7 +357,7 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
                         int32_t *d_scores, BandOut out, int max_res,
                         const uint64_t *d_dir_off, uint32_t *d_dirs,
                         const uint64_t *d_diff_off, const uint32_t *d_diff_cap,
-                        uint32_t *d_gring, cudaStream_t st, int *nlaunch) {
+                        uint32_t *d_gring, int *d_ticket, int sm_count, cudaStream_t st, int *nlaunch) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(band_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -373,6 +382,9 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++*nlaunch;
   }
+  if (align && plan.warp_count)
+    return launch_band_warp(sc, src, d_tasks, d_order + plan.warp_start, plan.warp_count, d_ticket, out, max_res,
+                            d_diff_off, d_diff_cap, sm_count, st, nlaunch);
   return cudaSuccess;
 }
 

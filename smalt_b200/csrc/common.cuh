@@ -88,8 +88,9 @@ cudaError_t launch_compact_gather(const smb_ali_result *slots, const uint32_t *n
 constexpr int BAND_SMEM_WCAP_MAX = 512;  // 512 slots * 64 threads * 4 B = 128 KB of shared memory
 struct BandPlan {
   struct Class { int wcap, start, count; };
-  std::vector<int> order;
+  std::vector<int> order;       // thread-per-task classes first, then the warp-per-task tasks
   std::vector<Class> classes;
+  int warp_start = 0, warp_count = 0;   // K3 tasks of band_warp_kernel (band_warp.cu)
 };
 void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, BandPlan &plan);
 size_t band_gring_words(const BandPlan &plan);
@@ -98,7 +99,12 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
                         int32_t *d_scores, BandOut out, int max_res,
                         const uint64_t *d_dir_off, uint32_t *d_dirs,
                         const uint64_t *d_diff_off, const uint32_t *d_diff_cap,
-                        uint32_t *d_gring, cudaStream_t st, int *nlaunch);
+                        uint32_t *d_gring, int *d_ticket, int sm_count, cudaStream_t st, int *nlaunch);
+cudaError_t launch_band_warp(const Scoring &sc, const SeqSrc &src, const smb_band_task *d_tasks,
+                             const int *d_order, int ntasks, int *d_ticket, BandOut out, int max_res,
+                             const uint64_t *d_diff_off, const uint32_t *d_diff_cap, int sm_count,
+                             cudaStream_t st, int *nlaunch);
+cudaError_t warm_band_warp();
 
 // ---- K1 ----
 struct Index {

@@ -62,7 +62,7 @@ typedef struct {
   int memfd;
   char fdpath[64];
   ErrMsg *errmsgp;
-  double ms_prev[3], wall_prev[8];
+  double ms_prev[3], wall_prev[11];
   uint64_t counts_prev[5];
 } FmWorker;
 
@@ -333,14 +333,14 @@ static void *fm_worker_main(void *arg)
 
 static void fm_collect_stats(FmWorker *w)
 {
-  double ms[3], wall[8];
+  double ms[3], wall[11];
   uint64_t counts[5];
   int i;
   if (!w->wave) return;
   rmapWaveGetStats(w->wave, ms, counts);
   rmapWaveGetWall(w->wave, wall);
   pthread_mutex_lock(&g_stats_lock);
-  for (i = 0; i < 8; i++) { g_wall[i] += wall[i] - w->wall_prev[i]; w->wall_prev[i] = wall[i]; }
+  for (i = 0; i < 11; i++) { g_wall[i] += wall[i] - w->wall_prev[i]; w->wall_prev[i] = wall[i]; }
   for (i = 0; i < 3; i++) { g_ms[i] += ms[i] - w->ms_prev[i]; w->ms_prev[i] = ms[i]; }
   for (i = 0; i < 5; i++) { g_counts[i] += counts[i] - w->counts_prev[i]; w->counts_prev[i] = counts[i]; }
   pthread_mutex_unlock(&g_stats_lock);

@@ -100,6 +100,7 @@ struct RmapWave_ {
   /* statistics */
   double ms_k1, ms_k2, ms_k3;
   double wall[8]; /* host wall seconds: stage, seed, hits, candidates, score, replay, align, results */
+  double wall_res[3]; /* inside results: add alignments, sort/MAPQ/filter, emit (report + format) */
   uint64_t cells_k2, cells_k3, n_k2, n_k3, n_reads;
 };
 
@@ -150,7 +151,7 @@ void rmapWaveDelete(RmapWave *w)
   free(w);
 }
 
-void rmapWaveGetWall(const RmapWave *w, double wall[8]) { memcpy(wall, w->wall, sizeof(w->wall)); }
+void rmapWaveGetWall(const RmapWave *w, double wall[11]) { memcpy(wall, w->wall, sizeof(w->wall)); memcpy(wall + 8, w->wall_res, sizeof(w->wall_res)); }
 
 void rmapWaveGetStats(const RmapWave *w, double ms[3], uint64_t counts[5])
 {
@@ -221,7 +222,7 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
   short matchscor = 0, mismatchscor = 0, gapinitscor = 0, gapextscor = 0;
   size_t nres = 0, ndiff = 0;
   uint64_t cells = 0;
-  double tw = wnow();
+  double tw = wnow(), tres;
   
   if (n < 1) return ERRCODE_SUCCESS;
   if (!(rmapflg & RMAPFLG_SEQBYSEQ) || (rmapflg & (RMAPFLG_NOSHRTINFO | RMAPFLG_SPLIT | RMAPFLG_CMPLXW)))
@@ -596,6 +597,7 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
 
   WTICK(6);
   /* host: replay of alignRMAPCANDFull (rmap.c:820-926), then results.c as in the reference */
+  tres = wnow();
   for (i = 0; i < n; i++) {
     WREAD *rd = w->rd + i;
     ResultSet *rsp = rmp->rsrp;
@@ -610,6 +612,7 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
     if (!rd->errcode && rd->do_align) {
       int min_swatscor = rd->min_swatscor;
       SWATSCOR swatscor_2ndmax = 0;
+      int need_profiles = 0;
       for (c = 0; c < rd->nscored && !rd->errcode; c++) {
 	WCAND *wc = w->cand + rd->cand_first + c;
 	const RMAPCAND *cp = &wc->c;
@@ -645,26 +648,40 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
 	  }
 	  fputc('\n', stderr);
 	}
+	if (cp->sqidx == SEGCAND_UNKNOWN_SEQIDX) need_profiles = 1;
 	errcode = resultSetAddFromAli(rsp, bufp->alirsltp, cp->rs, 0, rd->qlen,
 				      (cp->sqidx == SEGCAND_UNKNOWN_SEQIDX) ? RESULTSET_UNKNOWN_SEQIDX : cp->sqidx,
 				      (char) (cp->flags & RMAPCANDFLG_REVERSE));
 	if (errcode) { rd->errcode = errcode; break; }
       }
+      { const double t_ = wnow(); w->wall_res[0] += t_ - tres; tres = t_; }
       if (rd->errcode) ERRMSGNO(errmsgp, rd->errcode);
       else {
-	/* profiles of this read for resultSetSortAndAssignSequence (rmap.c:1419-1428) */
-	seqFastqBlank(w->readRC);
-	if ((errcode = seqFastqAppendSegment(w->readRC, reads[i], 0, 0, 1, codecp)) ||
-	    (errcode = scoreMakeProfileFromSequence(w->prof, reads[i], scormtxp)) ||
-	    (errcode = scoreMakeProfileFromSequence(w->profRC, w->readRC, scormtxp)))
-	  return errcode;
+	/* The profiles of the read (rmap.c:1419-1428) are only dereferenced by
+	 * resultSetSortAndAssignSequence for results without a sequence index (results.c:1715,
+	 * :1742-1756: alignments spanning reference sequences in the lumped mode) - never in the
+	 * sequence-by-sequence mode this path runs in; they are built only if such a result exists. */
+	if (need_profiles) {
+	  seqFastqBlank(w->readRC);
+	  if ((errcode = seqFastqAppendSegment(w->readRC, reads[i], 0, 0, 1, codecp)) ||
+	      (errcode = scoreMakeProfileFromSequence(w->prof, reads[i], scormtxp)) ||
+	      (errcode = scoreMakeProfileFromSequence(w->profRC, w->readRC, scormtxp)))
+	    return errcode;
+	}
 	errcode = resultSetSortAndAssignSequence(rsp, bufp->sqbfp, 0, reads[i], w->prof, w->profRC, ssp, codecp);
 	if (errcode) { rd->errcode = errcode; ERRMSGNO(errmsgp, errcode); }
       }
     }
-    if (!rd->errcode && (errcode = resultSetFilterResults(rsp, rsfp, reads[i])))
-      ERRMSGNO(errmsgp, errcode);
-    if ((errcode = (*emitf)(user, i, rsp))) return errcode;
+    {
+      double tr2;
+      if (!rd->errcode && (errcode = resultSetFilterResults(rsp, rsfp, reads[i])))
+	ERRMSGNO(errmsgp, errcode);
+      tr2 = wnow();
+      w->wall_res[1] += tr2 - tres;
+      if ((errcode = (*emitf)(user, i, rsp))) return errcode;
+      tres = wnow();
+      w->wall_res[2] += tres - tr2;
+    }
   }
   WTICK(7);
   w->n_reads += (uint64_t) n;

@@ -10,7 +10,7 @@ void rmapWaveDelete(RmapWave *w);
 /* ms: device time of K1, K2(+K2'), K3; counts: reads, K2 tasks, K2 cells, K3 tasks, K3 cells */
 void rmapWaveGetStats(const RmapWave *w, double ms[3], uint64_t counts[5]);
 /* host wall-clock seconds per stage: staging, seed, hits, candidates, score, replay, align, results */
-void rmapWaveGetWall(const RmapWave *w, double wall[8]);
+void rmapWaveGetWall(const RmapWave *w, double wall[11]);
 /* Maps reads[0..n) (SEQCOD_MANGLED) like n calls of rmapSingle (rmap.c:1648) would and calls
  * emitf(user, i, result set) for i = 0..n-1 in order.  Returns ERRCODE_ARGINVAL if the flag
  * combination is not handled by the wave path (the caller then uses rmapSingle per read). */

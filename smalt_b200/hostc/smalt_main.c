@@ -40,7 +40,7 @@ static short g_blocksz = 2048;  /* reads per block of the reference queue path *
 static pthread_mutex_t g_stats_lock = PTHREAD_MUTEX_INITIALIZER;
 static double g_ms[3];
 static uint64_t g_counts[5];
-static double g_wall[8], g_wall_enc, g_t0;
+static double g_wall[11], g_wall_enc, g_t0;
 static double g_fm_parse_s, g_fm_format_s;
 
 typedef struct {
@@ -48,7 +48,7 @@ typedef struct {
   SeqFastq **reads;
   uint32_t *mincov;
   short n_alloc;
-  double ms_prev[3], wall_prev[8];
+  double ms_prev[3], wall_prev[11];
   uint64_t counts_prev[5];
 } WorkerState;
 
@@ -93,7 +93,7 @@ static int smb_processArgBlock(ErrMsg *errmsgp, void *targp, void *bufargp)
   const SmaltMapConst *macop = map->smconstp;
   const short n = blockp->n_iobf;
   EmitArg ea;
-  double ms[3], wall[8], t_enc;
+  double ms[3], wall[11], t_enc;
   uint64_t counts[5];
   struct timespec ts0, ts1;
 
@@ -159,7 +159,7 @@ static int smb_processArgBlock(ErrMsg *errmsgp, void *targp, void *bufargp)
   rmapWaveGetWall(t_ws.wave, wall);
   pthread_mutex_lock(&g_stats_lock);
   g_wall_enc += t_enc;
-  for (i = 0; i < 8; i++) { g_wall[i] += wall[i] - t_ws.wall_prev[i]; t_ws.wall_prev[i] = wall[i]; }
+  for (i = 0; i < 11; i++) { g_wall[i] += wall[i] - t_ws.wall_prev[i]; t_ws.wall_prev[i] = wall[i]; }
   for (i = 0; i < 3; i++) { g_ms[i] += ms[i] - t_ws.ms_prev[i]; t_ws.ms_prev[i] = ms[i]; }
   for (i = 0; i < 5; i++) { g_counts[i] += counts[i] - t_ws.counts_prev[i]; t_ws.counts_prev[i] = counts[i]; }
   pthread_mutex_unlock(&g_stats_lock);
@@ -317,8 +317,9 @@ int __wrap_threadsRun(void)
 	  smb_process_counters(&nl, &hb, &db);
 	  m->stats.gpu_launches = nl; m->stats.h2d_bytes = hb; m->stats.d2h_bytes = db;
 	}
-	memcpy(m->stats.host_stage_s, g_wall, sizeof(g_wall));
+	memcpy(m->stats.host_stage_s, g_wall, 8 * sizeof(double));
 	m->stats.host_stage_s[8] = g_fm_parse_s;
+	memcpy(m->stats.host_stage_s + 9, g_wall + 8, 3 * sizeof(double));
       }
       pthread_mutex_lock(&m->lock);
       m->req_err = errcode;

@@ -18,7 +18,8 @@ class MapStats(C.Structure):
                 ("gpu_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("host_stage_s", C.c_double * 12)]
 
-    STAGES = ("staging", "seed", "hits", "candidates", "score", "replay", "align", "results", "parse")
+    STAGES = ("staging", "seed", "hits", "candidates", "score", "replay", "align", "results", "parse",
+              "results.add", "results.sort_filter", "results.emit")
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "host_stage_s"}
