@@ -54,6 +54,13 @@ void smbm_free(void *p);
 
 int smbm_close(smbm_mapper *m);
 
+/* Host-only helper (no GPU, no mapper): the byte offsets at which the block-parallel pipeline
+ * would cut `text` into blocks of about chunk_bytes - every offset is the start of a record
+ * (4-line FASTQ or FASTA).  Returns ERRCODE_FASTA (6) if the text is not whole 4-line FASTQ
+ * records.  Used by the tests and by the multi-GPU read sharding. */
+int smbm_split_blocks(const char *text, size_t nbytes, size_t chunk_bytes, size_t *starts,
+		      size_t max_starts, size_t *nstarts, size_t *nrecords);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@ int smbShimInit(const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
 		const ScoreMatrix *scormtxp);
 smb_ctx *smbShimRootCtx(void);
 int smbShimDevice(void);
+void smbShimForgetIndex(void);
 /* a per-thread context (own stream and scratch) that shares the root's index/reference */
 int smbShimWorkerCtx(smb_ctx **ctxp, const ScoreMatrix *scormtxp);
 int smbShimSetScoring(smb_ctx *ctx, const ScoreProfile *profp);

@@ -156,6 +156,16 @@ int smbShimInit(const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
 
 smb_ctx *smbShimRootCtx(void) { return g_root; }
 
+/* The uploaded index is identified by the HashTable pointer; a driver that deletes the table
+ * (end of a mapping session) must say so, or a new table allocated at the same address would
+ * be taken for the one already on the device. */
+void smbShimForgetIndex(void)
+{
+  pthread_mutex_lock(&g_lock);
+  g_root_htp = NULL;
+  pthread_mutex_unlock(&g_lock);
+}
+
 int smbShimWorkerCtx(smb_ctx **ctxp, const ScoreMatrix *scormtxp)
 {
   int errcode;

@@ -328,6 +328,7 @@ int __wrap_threadsRun(void)
     }
     pthread_mutex_unlock(&m->lock);
     fastmap_cleanup();
+    smbShimForgetIndex(); /* the reference deletes its HashTable next (cleanupMapConst) */
     return ERRCODE_SUCCESS;
   }
 
@@ -446,6 +447,36 @@ int smbm_sam_header(smbm_mapper *m, char **text, size_t *len)
 }
 
 void smbm_free(void *p) { free(p); }
+
+/* test hook (no GPU needed): the block boundaries fastmap would use for this text */
+int smbm_split_blocks(const char *text, size_t nbytes, size_t chunk_bytes, size_t *starts, size_t max_starts,
+		      size_t *nstarts, size_t *nrecords)
+{
+  FastMap fm;
+  size_t c, n = 0, nrec_tot = 0, p = 0;
+  if (!text || !chunk_bytes || !starts || !nstarts) return SMB_ERR_ARG;
+  memset(&fm, 0, sizeof(fm));
+  while (p < nbytes && isspace((unsigned char) text[p])) p++;
+  fm.data = text + p; fm.len = nbytes - p;
+  fm.is_fasta = fm.len && fm.data[0] == '>';
+  fm.chunk_bytes = chunk_bytes;
+  fm.nchunks = (fm.len + chunk_bytes - 1) / chunk_bytes;
+  for (c = 0; c < fm.nchunks; c++) {
+    const size_t start = fm_record_start(&fm, c * chunk_bytes);
+    const size_t end = (c + 1 == fm.nchunks) ? fm.len : fm_record_start(&fm, (c + 1) * chunk_bytes);
+    size_t nrec = 0;
+    if (n < max_starts) starts[n] = start + p;
+    n++;
+    if (!fm.is_fasta && end > start) {
+      const int rc = fm_check_fastq(fm.data, start, end, &nrec);
+      if (rc) return rc;
+      nrec_tot += nrec;
+    }
+  }
+  *nstarts = n;
+  if (nrecords) *nrecords = nrec_tot;
+  return (n > max_starts) ? SMB_ERR_CAPACITY : SMB_OK;
+}
 
 int smbm_close(smbm_mapper *m)
 {

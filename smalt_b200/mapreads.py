@@ -1,0 +1,47 @@
+"""`python -m smalt_b200.mapreads` - multi-GPU `smalt map` of a FASTQ file: one process per
+GPU (launch with torchrun), reads sharded by rank, SAM merged in input order on rank 0.
+
+  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 -m smalt_b200.mapreads \
+      [-n threads_per_gpu] -o out.sam <index_prefix> <reads.fq>
+"""
+import argparse
+import os
+import sys
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("-n", type=int, default=0, help="host worker threads per GPU (0: cores / GPUs * 1.5)")
+    ap.add_argument("-o", required=True)
+    ap.add_argument("--backend", default=None, help="torch.distributed backend (default nccl; gloo for tests)")
+    ap.add_argument("index")
+    ap.add_argument("reads")
+    args = ap.parse_args(argv)
+    from .mapper import Mapper
+    from .shard import gather_in_order, shard_of
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(args.backend or "nccl")
+    text = open(args.reads, "rb").read()
+    mine = shard_of(text, rank, world)
+    cores = len(os.sched_getaffinity(0))
+    m = Mapper(args.index, args.n or max(1, int(1.5 * cores / world)))
+    header = m.sam_header() if rank == 0 else b""
+    sam = m.map_fastq(mine)
+    m.close()
+    out = gather_in_order(dist, sam) if dist is not None else sam
+    if rank == 0:
+        with open(args.o, "wb") as f:
+            f.write(header)
+            f.write(out)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
