@@ -44,7 +44,7 @@ K, NSKIP = 13, 6
 ERR = 0.02
 # algorithmic integer operations per DP cell ("rooflines")
 K2_OPS_PER_CELL = 7.5
-K3_OPS_PER_CELL = 19.0
+K3_OPS_PER_CELL = 20.0
 
 
 def make_genome(seed=2, n=GENOME_LEN):
