@@ -366,7 +366,7 @@ def main():
                            "k3_cells": s1["k3_cells"]},
         "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": wall_ms, "sam_bytes_per_step": int(sam_bytes),
-                "host_stage_core_s": c1["host_stage_s"]},
+                "host_stage_wall_s": c1["host_stage_s"], "host_stage_cpu_s": c1["host_cpu_s"]},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roof_k3 if dominant == "k3_band_align" else roof_k2,
         "roofline_k2": roof_k2, "roofline_k3": roof_k3, "roofline_k1": roof_k1,

@@ -35,6 +35,7 @@ typedef struct {
   uint64_t h2d_bytes, d2h_bytes; /* bytes copied host->device / device->host by this process so far */
   double host_stage_s[12];   /* summed over worker threads: staging, seed, hits, candidates, score,
 				replay, align, results, parse, and inside results: add, sort+filter, emit */
+  double host_cpu_s[8];      /* thread CPU seconds of the first eight stages (no waiting for the GPU) */
 } smbm_stats;
 
 /* Loads <index_prefix>.smi/.sma (hashTableRead hashidx.c:1257, seqSetReadBinFil sequence.c:2521),

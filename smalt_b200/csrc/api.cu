@@ -785,6 +785,8 @@ int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_
   a.read_off = d_off; a.read_len = d_len; a.slot_off = d_slot; a.qual = d_qual; a.nreads = nreads;
   a.maxhit_per_tuple = maxhit_per_tuple; a.maxhit_total = maxhit_total; a.basq_thresh = basq_thresh;
   a.is_short = short_info ? 1 : 0;
+  a.maxlen = 0;
+  for (int i = 0; i < nreads; ++i) if (read_len[i] > a.maxlen) a.maxlen = read_len[i];
   a.info = d_info;
   a.posidx = u; a.nhits = u + S; a.qoffs = u + 2 * S; a.sortkey = u + 3 * S; a.sidx = u + 4 * S; a.frame = u + 5 * S;
   a.qmask = b; a.qbuf = b + S;

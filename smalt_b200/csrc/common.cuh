@@ -122,6 +122,7 @@ struct SeedArgs {
   int nreads;
   uint32_t maxhit_per_tuple, maxhit_total;
   int basq_thresh, is_short;
+  uint32_t maxlen;            // longest read of the batch
   smb_seed_info *info;        // [2*nreads]
   uint32_t *posidx, *nhits, *qoffs, *sortkey, *sidx, *frame;  // slot arrays
   uint8_t *qmask, *qbuf;

@@ -279,11 +279,299 @@ seed_kernel(const Index ix, const uint8_t *__restrict__ arena, const SeedArgs a)
   a.info[g] = inf;
 }
 
+
+// ------------------------------------------------------------------------------------
+// seed_warp_kernel: the same function as seed_kernel (hashCollectHitInfoShort of one read x
+// strand), ONE WARP per read x strand.  A block of a few thousand reads gives only ~16 k
+// read-strands: one thread each leaves the GPU at 6 % occupancy and serialises 32 divergent
+// quicksorts per warp (profiles/r1_ncu_full_k1_*).  Here
+//   * the k-mer words of all read offsets are formed by the lanes in parallel from the read
+//     staged in shared memory; validity (non-standard base / low quality inside the word),
+//     the 4-deep repeat filter (previous four VALID words, hashhit.c:342-346, :584-600) and the
+//     seed compaction are warp ballots / prefix sums - same decisions, order-preserving;
+//   * the index probes of 32 words are in flight at once (the dependent idx -> wordidx ->
+//     posidx chains of different words are independent);
+//   * the reference's unstable quicksort (sort.c:233-330) runs unchanged in lane 0 on shared
+//     memory (its exchange sequence decides the tie order, so it is not parallelised);
+//   * the per-frame coverage scans of getHitInfoMaxRank / hashCalcHitInfoCoverDeficit run one
+//     frame per lane on bit masks.
+// Reads longer than the shared-memory staging or nskip > 32 stay with seed_kernel.
+// ------------------------------------------------------------------------------------
+constexpr int SEEDW_WARPS = 4;
+
+struct SeedWarpLayout {   // per-warp shared memory carve-up for reads of at most qmax bases
+  int qmax;
+  __host__ __device__ size_t words_off() const { return 0; }                       // u64[qmax]
+  __host__ __device__ size_t sortkey_off() const { return (size_t)qmax * 8; }      // u32[qmax+1]
+  __host__ __device__ size_t sidx_off() const { return sortkey_off() + ((size_t)qmax + 1) * 4; }  // u32[qmax]
+  __host__ __device__ size_t cov_off() const { return sidx_off() + (size_t)qmax * 4; }   // u32[32 * covw]
+  __host__ __device__ int covw() const { return (qmax + 31) / 32; }
+  __host__ __device__ size_t qoffs_off() const { return cov_off() + (size_t)32 * covw() * 4; }  // u16[qmax]
+  __host__ __device__ size_t frame_off() const { return qoffs_off() + (size_t)qmax * 2; }       // u16[qmax]
+  __host__ __device__ size_t vt_off() const { return frame_off() + (size_t)qmax * 2; }          // u16[qmax]
+  __host__ __device__ size_t codes_off() const { return vt_off() + (size_t)qmax * 2; }          // u8[qmax]
+  __host__ __device__ size_t qmask_off() const { return codes_off() + (size_t)qmax; }           // u8[qmax]
+  __host__ __device__ size_t bytes() const { return (qmask_off() + (size_t)qmax + 15) & ~(size_t)15; }
+};
+
+__global__ void __launch_bounds__(SEEDW_WARPS * 32)
+seed_warp_kernel(const Index ix, const uint8_t *__restrict__ arena, const SeedArgs a, const SeedWarpLayout lay) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * SEEDW_WARPS + (threadIdx.x >> 5);
+  if (g >= 2 * a.nreads) return;
+  unsigned char *base = s_raw + (size_t)(threadIdx.x >> 5) * lay.bytes();
+  unsigned long long *s_word = (unsigned long long *)(base + lay.words_off());
+  uint32_t *s_key = (uint32_t *)(base + lay.sortkey_off());
+  uint32_t *s_sidx = (uint32_t *)(base + lay.sidx_off());
+  uint32_t *s_cov = (uint32_t *)(base + lay.cov_off());
+  unsigned short *s_qoffs = (unsigned short *)(base + lay.qoffs_off());
+  unsigned short *s_frame = (unsigned short *)(base + lay.frame_off());
+  unsigned short *s_vt = (unsigned short *)(base + lay.vt_off());
+  uint8_t *s_code = base + lay.codes_off();
+  uint8_t *s_qmask = base + lay.qmask_off();
+
+  const int rd = g >> 1, is_reverse = g & 1;
+  const uint32_t qlen = a.read_len[rd];
+  const uint8_t *read = arena + a.read_off[rd];
+  const uint8_t *qual = a.qual ? a.qual + a.read_off[rd] : nullptr;
+  const uint64_t slot = a.slot_off[rd] + (is_reverse ? qlen : 0u);
+  uint32_t *g_posidx = a.posidx + slot, *g_nhits = a.nhits + slot, *g_qoffs = a.qoffs + slot;
+  uint32_t *g_sortkey = a.sortkey + slot, *g_sidx = a.sidx + slot;
+  uint8_t *g_qmask = a.qmask + slot;
+  const int ktup = ix.wordlen, nskip = ix.nskip;
+  smb_seed_info inf;
+  inf.n_seeds = inf.seed_rank = inf.cover_deficit = inf.nhit_rank = inf.nhit_tot = inf.nhit_all = 0;
+  inf.status = is_reverse ? HI_REVERSE : 0;
+  inf.err = 0;
+  if (qlen < (uint32_t)ktup) {
+    inf.err = SMB_ERRCODE_SHORTSEQ;
+    if (lane == 0) a.info[g] = inf;
+    return;
+  }
+  // ---- stage the read: code in bits 0-2, bit 7 = base that invalidates its k-mers ----
+  const uint8_t minqval = (uint8_t)(a.basq_thresh + 0x21);
+  for (uint32_t s = lane; s < qlen; s += 32) {
+    const uint32_t c = __ldg(read + s);
+    const bool bad = (c & 4u) || (qual && __ldg(qual + s) < minqval);
+    s_code[s] = (uint8_t)((c & 7u) | (bad ? 0x80u : 0u));
+  }
+  __syncwarp();
+  // ---- k-mer word of every read offset (collectHitInfo, hashhit.c:559-587) ----
+  const uint32_t ntup = qlen - (uint32_t)ktup + 1u;
+  for (uint32_t t = lane; t < ntup; t += 32) {
+    unsigned long long w = 0;
+    uint32_t bad = 0;
+    if (is_reverse) {
+      for (int m = 0; m < ktup; ++m) {
+        const uint32_t c = s_code[t + m];
+        bad |= c;
+        w |= (unsigned long long)((c ^ 3u) & 3u) << (2 * m);
+      }
+    } else {
+      for (int m = 0; m < ktup; ++m) {
+        const uint32_t c = s_code[t + m];
+        bad |= c;
+        w = (w << 2) | (c & 3u);
+      }
+    }
+    s_word[t] = (bad & 0x80u) ? ~0ull : w;   // 2k <= 62 bits: ~0 is never a word
+  }
+  __syncwarp();
+  // ---- compaction of the valid words, in read order ----
+  uint32_t nvalid = 0;
+  for (uint32_t t0 = 0; t0 < ntup; t0 += 32) {
+    const uint32_t t = t0 + lane;
+    const bool v = t < ntup && s_word[t] != ~0ull;
+    const unsigned m = __ballot_sync(FULL, v);
+    if (v) s_vt[nvalid + __popc(m & ((1u << lane) - 1u))] = (unsigned short)t;
+    if (t < ntup && !v) s_qmask[t] = HQ_NONSTDNT;
+    nvalid += __popc(m);
+  }
+  for (uint32_t t = ntup + lane; t < qlen; t += 32) s_qmask[t] = HQ_TERM;
+  __syncwarp();
+  // ---- repeat filter, index probes, seed compaction: 32 valid words per round ----
+  const uint32_t maxhit = a.maxhit_per_tuple;   // is_short
+  uint32_t n_seeds = 0;
+  for (uint32_t v0 = 0; v0 < nvalid; v0 += 32) {
+    const uint32_t vi = v0 + lane;
+    bool seed = false;
+    uint32_t nh = 0, px = 0, t = 0;
+    if (vi < nvalid) {
+      t = s_vt[vi];
+      const unsigned long long w = s_word[t];
+      bool rep = false;
+      for (uint32_t j = 1; j <= 4u && j <= vi; ++j) rep |= (s_word[s_vt[vi - j]] == w);
+      uint8_t code;
+      if (rep) code = HQ_REPEAT;
+      else {
+        nh = lookup(ix, w, px);
+        if (nh < 1) code = HQ_NOHIT;
+        else if (maxhit > 0 && nh > maxhit) code = HQ_MULTIHIT;
+        else { code = HQ_NORMHIT; seed = true; }
+      }
+      s_qmask[t] = code;
+    }
+    const unsigned m = __ballot_sync(FULL, seed);
+    if (seed) {
+      const uint32_t k = n_seeds + __popc(m & ((1u << lane) - 1u));
+      s_key[k] = nh;
+      s_sidx[k] = k;
+      s_qoffs[k] = (unsigned short)t;
+      g_posidx[k] = px;
+      g_nhits[k] = nh;
+      g_qoffs[k] = t;
+    }
+    n_seeds += __popc(m);
+  }
+  __syncwarp();
+  for (uint32_t t = lane; t < qlen; t += 32) g_qmask[t] = s_qmask[t];
+  inf.n_seeds = n_seeds;
+
+  // ---- hashCollectHitInfoShort: sort + rank ----
+  int fcnt = 0, fstart = 0;   // lane f: seeds in frame f, start of its rank list
+  if (n_seeds <= 1) {
+    inf.status |= HI_SORTED;
+    inf.seed_rank = n_seeds;
+  } else {
+    int e = 0;
+    if (lane == 0) e = sort2((int)n_seeds, s_key, s_sidx);
+    e = __shfl_sync(FULL, e, 0);
+    if (e) inf.err = e;
+    inf.status |= HI_SORTED;
+    __syncwarp();
+    uint32_t mincover = 2u * (uint32_t)ktup + (uint32_t)nskip;
+    uint32_t maxcover = qlen * 80u / 100u;
+    if (maxcover < (uint32_t)(ktup + nskip)) maxcover = (uint32_t)(ktup + nskip);
+    else if (maxcover > qlen - (uint32_t)nskip) maxcover = qlen - (uint32_t)nskip;
+    if (mincover > maxcover) { mincover = 0; maxcover = qlen; }
+    // getHitInfoMaxRank (hashhit.c:769-891): rank lists of the frames, one frame per lane
+    if (lane < nskip)
+      for (uint32_t i = 0; i < n_seeds; ++i) fcnt += (s_qoffs[s_sidx[i]] % (uint32_t)nskip) == (uint32_t)lane;
+    int incl = fcnt;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    fstart = incl - fcnt;
+    if (lane < nskip) {
+      int c = 0;
+      for (uint32_t i = 0; i < n_seeds; ++i)
+        if ((s_qoffs[s_sidx[i]] % (uint32_t)nskip) == (uint32_t)lane) s_frame[fstart + c++] = (unsigned short)i;
+    }
+    // seeds whose hits sum up to at most maxhit_total (the reference reads one element past the
+    // end here, hashhit.c:823; its value cannot change the result)
+    uint32_t n = 0;
+    if (lane == 0) {
+      uint32_t ntot = s_key[0], i;
+      for (i = 1; i <= n_seeds && ntot <= a.maxhit_total; ++i) ntot += (i < n_seeds) ? s_key[i] : 0u;
+      n = i - 1;
+    }
+    n = __shfl_sync(FULL, n, 0);
+    __syncwarp();
+    uint32_t nmax = n;
+    const int covw = lay.covw();
+    uint32_t *cov = s_cov + lane * covw;
+    if (lane < nskip && fcnt > 0) {
+      for (int wq = 0; wq < covw; ++wq) cov[wq] = 0;
+      uint32_t cover = 0;
+      int i = 0;
+      for (; i < fcnt && cover <= maxcover && (cover < mincover || s_frame[fstart + i] <= n); ++i) {
+        const uint32_t q0 = s_qoffs[s_sidx[s_frame[fstart + i]]];
+        for (uint32_t q = q0; q < q0 + (uint32_t)ktup - 1u; ++q) {
+          const uint32_t bit = 1u << (q & 31u);
+          if (!(cov[q >> 5] & bit)) { cov[q >> 5] |= bit; ++cover; }
+        }
+      }
+      if (i > 0 && s_frame[fstart + i - 1] > nmax) nmax = s_frame[fstart + i - 1];
+    }
+    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULL, nmax, o));
+    inf.seed_rank = (nmax < 3u) ? (3u < n_seeds ? 3u : n_seeds) : nmax;  // HITINFO_MINSEEDNUM
+    inf.status |= HI_RANK;
+  }
+  // ---- hashCalcHitInfoCoverDeficit (hashhit.c:1096-1169) ----
+  if (inf.status & HI_RANK) {
+    uint32_t dmin = 0xffffffffu, maxc = 0;
+    const int covw = lay.covw();
+    uint32_t *cov = s_cov + lane * covw;
+    if (lane < nskip && fcnt > 0) {
+      for (int wq = 0; wq < covw; ++wq) cov[wq] = 0;
+      uint32_t cover = 0;
+      for (int i = 0; i < fcnt && s_frame[fstart + i] < inf.seed_rank; ++i) {
+        const uint32_t q0 = s_qoffs[s_sidx[s_frame[fstart + i]]];
+        for (uint32_t q = q0; q < q0 + (uint32_t)ktup; ++q) {
+          const uint32_t bit = 1u << (q & 31u);
+          if (!(cov[q >> 5] & bit)) { cov[q >> 5] |= bit; ++cover; }
+        }
+      }
+      dmin = cover;
+      maxc = cover;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      dmin = min(dmin, __shfl_xor_sync(FULL, dmin, o));
+      maxc = max(maxc, __shfl_xor_sync(FULL, maxc, o));
+    }
+    if (dmin > qlen) dmin = qlen;
+    inf.cover_deficit = maxc - dmin + 1u;
+  } else {
+    uint32_t k = (uint32_t)(ktup / nskip), deficit = 0;
+    if (k > 0) --k;
+    k &= 0xffu;
+    if (lane < nskip) {
+      uint32_t d = 0, ctr = 0;
+      for (uint32_t i = (uint32_t)lane; i < qlen; i += (uint32_t)nskip) {
+        if (s_qmask[i] == HQ_NORMHIT) ctr = k;
+        else if (ctr) --ctr;
+        else d += (uint32_t)nskip;
+      }
+      deficit = d;
+    }
+    for (int o = 16; o > 0; o >>= 1) deficit = max(deficit, __shfl_xor_sync(FULL, deficit, o));
+    inf.cover_deficit = deficit;
+  }
+  // ---- hashHitInfoCalcHitNumbers (:1200) / hashCalcHitInfoNumberOfHits (:1171), outputs ----
+  {
+    const uint32_t ns = inf.seed_rank > 0 ? inf.seed_rank : n_seeds;
+    uint32_t nr = 0, nt = 0, hnum = 0;
+    for (uint32_t i = lane; i < n_seeds; i += 32) {
+      const uint32_t kx = s_key[i];
+      if (i < ns) nr += kx;
+      nt += kx;
+      if (a.maxhit_per_tuple < 1u || kx <= a.maxhit_per_tuple) hnum += kx;
+      g_sortkey[i] = kx;
+      g_sidx[i] = s_sidx[i];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      nr += __shfl_xor_sync(FULL, nr, o);
+      nt += __shfl_xor_sync(FULL, nt, o);
+      hnum += __shfl_xor_sync(FULL, hnum, o);
+    }
+    inf.nhit_rank = nr;
+    inf.nhit_tot = nt;
+    inf.nhit_all = hnum;
+  }
+  if (lane == 0) a.info[g] = inf;
+}
+
 cudaError_t launch_seed(const Index &ix, const uint8_t *arena, const SeedArgs &a, cudaStream_t st,
                         int *nlaunch) {
   const int n = 2 * a.nreads;
   if (n <= 0) return cudaSuccess;
-  seed_kernel<<<(n + 127) / 128, 128, 0, st>>>(ix, arena, a);
+  // warp per read x strand when the reads fit the shared-memory staging (a.maxlen), the
+  // ranked short mode is asked for and a frame fits a lane
+  SeedWarpLayout lay{(int)((a.maxlen + 63u) & ~63u)};
+  const size_t smem = lay.bytes() * SEEDW_WARPS;
+  if (a.is_short && a.maxlen > 0 && a.maxlen <= 2048u && ix.nskip <= 32 && ix.wordlen <= 31 && smem <= 200 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(seed_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_set = true;
+    }
+    seed_warp_kernel<<<(n + SEEDW_WARPS - 1) / SEEDW_WARPS, SEEDW_WARPS * 32, smem, st>>>(ix, arena, a, lay);
+  } else {
+    seed_kernel<<<(n + 127) / 128, 128, 0, st>>>(ix, arena, a);
+  }
   ++*nlaunch;
   return cudaGetLastError();
 }
@@ -463,6 +751,7 @@ cudaError_t launch_hits(const Index &ix, const HitArgs &a, bool fill, cudaStream
 cudaError_t warm_seed() {
   cudaFuncAttributes a;
   cudaError_t e = cudaFuncGetAttributes(&a, seed_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, seed_warp_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, hits_kernel<true>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, hits_kernel<false>);
   return e;

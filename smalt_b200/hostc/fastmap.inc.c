@@ -62,7 +62,7 @@ typedef struct {
   int memfd;
   char fdpath[64];
   ErrMsg *errmsgp;
-  double ms_prev[3], wall_prev[11];
+  double ms_prev[3], wall_prev[11], cpu_prev[8];
   uint64_t counts_prev[5];
 } FmWorker;
 
@@ -339,6 +339,13 @@ static void fm_collect_stats(FmWorker *w)
   if (!w->wave) return;
   rmapWaveGetStats(w->wave, ms, counts);
   rmapWaveGetWall(w->wave, wall);
+  {
+    double cpu[8];
+    rmapWaveGetCpu(w->wave, cpu);
+    pthread_mutex_lock(&g_stats_lock);
+    for (i = 0; i < 8; i++) { g_cpu[i] += cpu[i] - w->cpu_prev[i]; w->cpu_prev[i] = cpu[i]; }
+    pthread_mutex_unlock(&g_stats_lock);
+  }
   pthread_mutex_lock(&g_stats_lock);
   for (i = 0; i < 11; i++) { g_wall[i] += wall[i] - w->wall_prev[i]; w->wall_prev[i] = wall[i]; }
   for (i = 0; i < 3; i++) { g_ms[i] += ms[i] - w->ms_prev[i]; w->ms_prev[i] = ms[i]; }

@@ -101,6 +101,7 @@ struct RmapWave_ {
   double ms_k1, ms_k2, ms_k3;
   double wall[8]; /* host wall seconds: stage, seed, hits, candidates, score, replay, align, results */
   double wall_res[3]; /* inside results: add alignments, sort/MAPQ/filter, emit (report + format) */
+  double cpu[8];      /* thread CPU seconds of the same eight stages (wall minus waiting for the GPU) */
   uint64_t cells_k2, cells_k3, n_k2, n_k3, n_reads;
 };
 
@@ -166,7 +167,15 @@ static double wnow(void)
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
-#define WTICK(k) do { const double t_ = wnow(); w->wall[k] += t_ - tw; tw = t_; } while (0)
+static double cnow(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+#define WTICK(k) do { const double t_ = wnow(), c_ = cnow(); w->wall[k] += t_ - tw; tw = t_; \
+    w->cpu[k] += c_ - tc; tc = c_; } while (0)
+void rmapWaveGetCpu(const RmapWave *w, double cpu[8]) { memcpy(cpu, w->cpu, sizeof(w->cpu)); }
 
 static int gpu_fail(ErrMsg *errmsgp, const RmapWave *w, int rc)
 {
@@ -222,7 +231,7 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
   short matchscor = 0, mismatchscor = 0, gapinitscor = 0, gapextscor = 0;
   size_t nres = 0, ndiff = 0;
   uint64_t cells = 0;
-  double tw = wnow(), tres;
+  double tw = wnow(), tc = cnow(), tres;
   
   if (n < 1) return ERRCODE_SUCCESS;
   if (!(rmapflg & RMAPFLG_SEQBYSEQ) || (rmapflg & (RMAPFLG_NOSHRTINFO | RMAPFLG_SPLIT | RMAPFLG_CMPLXW)))

@@ -40,7 +40,7 @@ static short g_blocksz = 2048;  /* reads per block of the reference queue path *
 static pthread_mutex_t g_stats_lock = PTHREAD_MUTEX_INITIALIZER;
 static double g_ms[3];
 static uint64_t g_counts[5];
-static double g_wall[11], g_wall_enc, g_t0;
+static double g_wall[11], g_cpu[8], g_wall_enc, g_t0;
 static double g_fm_parse_s, g_fm_format_s;
 
 typedef struct {
@@ -273,6 +273,7 @@ static void fm_stats_reset(void)
   memset(g_ms, 0, sizeof(g_ms));
   memset(g_counts, 0, sizeof(g_counts));
   memset(g_wall, 0, sizeof(g_wall));
+  memset(g_cpu, 0, sizeof(g_cpu));
   g_fm_parse_s = g_fm_format_s = 0;
 }
 
@@ -320,6 +321,7 @@ int __wrap_threadsRun(void)
 	memcpy(m->stats.host_stage_s, g_wall, 8 * sizeof(double));
 	m->stats.host_stage_s[8] = g_fm_parse_s;
 	memcpy(m->stats.host_stage_s + 9, g_wall + 8, 3 * sizeof(double));
+	memcpy(m->stats.host_cpu_s, g_cpu, sizeof(g_cpu));
       }
       pthread_mutex_lock(&m->lock);
       m->req_err = errcode;

@@ -16,13 +16,14 @@ class MapStats(C.Structure):
                 ("k2_tasks", C.c_uint64), ("k2_cells", C.c_uint64),
                 ("k3_tasks", C.c_uint64), ("k3_cells", C.c_uint64),
                 ("gpu_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("host_stage_s", C.c_double * 12)]
+                ("host_stage_s", C.c_double * 12), ("host_cpu_s", C.c_double * 8)]
 
     STAGES = ("staging", "seed", "hits", "candidates", "score", "replay", "align", "results", "parse",
               "results.add", "results.sort_filter", "results.emit")
 
     def as_dict(self):
-        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "host_stage_s"}
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("host_stage_s", "host_cpu_s")}
+        d["host_cpu_s"] = {k: self.host_cpu_s[i] for i, k in enumerate(self.STAGES[:8])}
         d["host_stage_s"] = {k: self.host_stage_s[i] for i, k in enumerate(self.STAGES)}
         return d
 
