@@ -101,8 +101,10 @@ int smb_ctx_share_index(smb_ctx *dst, const smb_ctx *src);
 
 /* Integer-issue micro-benchmark used as the roofline denominator of the DP kernels:
  * sustained giga thread-operations per second of (0) VIADDMNMX  max(a+b,c),
- * (1) VIMNMX3 max(a,b,c) and (2) plain IADD+IMNMX pairs, measured on this device. */
-int smb_int_peak(smb_ctx *ctx, double gops[3]);
+ * (1) VIMNMX3 max(a,b,c), (2) plain IADD+IMNMX pairs, (3) VIADDMNMX on two 16-bit halves
+ * (instructions, i.e. two cell-operations each) and (4) VIMNMX3 on two 16-bit halves,
+ * measured on this device. */
+int smb_int_peak(smb_ctx *ctx, double gops[5]);
 
 /* --------------------------- sequence arena ------------------------------ */
 /* Uploads a block of concatenated sequences (reads and, for the *_batch calls

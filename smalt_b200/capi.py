@@ -147,8 +147,9 @@ class Context:
         return int(self.lib.smb_total_kernel_launches(self._h))
 
     def int_peak(self):
-        """-> (viaddmax, vimax3, add+max) giga thread-ops/s measured on this device"""
-        g = (C.c_double * 3)()
+        """-> (viaddmax, vimax3, add+max, viaddmax_s16x2, vimax3_s16x2) giga thread-instructions/s
+        measured on this device"""
+        g = (C.c_double * 5)()
         self._check(self.lib.smb_int_peak(self._h, g))
         return tuple(g)
 

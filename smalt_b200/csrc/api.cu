@@ -242,13 +242,13 @@ int smb_ctx_share_index(smb_ctx *dst, const smb_ctx *src) {
   return SMB_OK;
 }
 
-int smb_int_peak(smb_ctx *ctx, double gops[3]) {
+int smb_int_peak(smb_ctx *ctx, double gops[5]) {
   if (!ctx || !gops) return SMB_ERR_ARG;
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
   CU(ctx->scratch.ensure((size_t)ctx->sm_count * 8 * 256 * sizeof(int)));
   const int iters = 4096;
-  for (int mode = 0; mode < 3; ++mode) {
+  for (int mode = 0; mode < 5; ++mode) {
     double ops = 0, best = 0;
     for (int rep = 0; rep < 4; ++rep) {
       CU(cudaEventRecord(ctx->ev0, st));
@@ -325,7 +325,7 @@ int smb_sw_score_batch(smb_ctx *ctx, const smb_sw_task *tasks, int ntasks, int32
   int32_t *d_scores = ctx->out_a.as<int32_t>(), *d_errs = d_scores + ntasks;
   int nl = 0;
   SwPlan plan;
-  plan_sw(tasks, ntasks, ctx->sm_count, plan);   // host planning happens before the timed events
+  plan_sw(tasks, ntasks, ctx->sm_count, ctx->sc, plan);   // host planning happens before the timed events
   const size_t off_order = 256, off_strip = (off_order + (size_t)ntasks * sizeof(int) + 255) & ~(size_t)255;
   CU(ctx->scratch.ensure(off_strip + plan.strip_bytes + 256));
   char *sb = ctx->scratch.as<char>();

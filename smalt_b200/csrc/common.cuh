@@ -51,12 +51,12 @@ struct Timer {
 // ---- K2 ----
 struct SwPlan {
   std::vector<int> order;   // task indices grouped by columns-per-lane class
-  int count[9], start[9];
+  int count[17], start[17]; // [1..8] 32-bit classes, [9..16] paired 16-bit classes
   int max_grid;
   uint32_t bstride;         // rows of the boundary strips (multi-block reads), 0 if none
   size_t strip_bytes;
 };
-void plan_sw(const smb_sw_task *h_tasks, int ntasks, int sm_count, SwPlan &plan);
+void plan_sw(const smb_sw_task *h_tasks, int ntasks, int sm_count, const Scoring &sc, SwPlan &plan);
 cudaError_t launch_sw_score(const Scoring &sc, const SeqSrc &src, const smb_sw_task *d_tasks,
                             const SwPlan &plan, int *d_counters, const int *d_order, void *d_strips,
                             int32_t *d_scores, int32_t *d_errs, cudaStream_t st, int *nlaunch);

@@ -172,8 +172,151 @@ static cudaError_t launch_class(const Scoring &sc, const SeqSrc &src, const smb_
   return cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------------------------
+// sw_score2_kernel: the same recurrence with TWO TASKS PER WARP in the two 16-bit halves of
+// every register (DPX VIADDMNMX.S16x2 / VIMNMX3.S16x2): short reads cannot exceed a score of
+// qlen * match, so 15 bits are enough and every integer instruction advances two cells.
+//   * task A lives in the low, task B in the high half-words of H, E, F, best;
+//   * the substitution score of both cells comes from ONE byte permute: an 8-byte table
+//     T = {match, mismatch x3, 0 x4} indexed by (read code ^ window code) for A,C,G,T and by
+//     4..7 for N / padding columns (PRMT sign-replication widens the byte to 16 bits), with the
+//     selector nibbles of the read precomputed per column and the window's per row;
+//   * window codes of both tasks are staged interleaved in shared memory (one 16-bit load per
+//     row instead of a shuffle); H and F still travel by one shuffle each per step;
+//   * rows with a non-standard window base (N, X, terminator / padding behind the shorter
+//     window) and task pairs with an X in the read take the general per-cell table path.
+// Padding columns and padding rows score 0: values there never exceed the maximum already
+// recorded (h = Hdiag + s <= Hdiag), so they cannot change the result.
+// ------------------------------------------------------------------------------------
+constexpr int SW2_MAXROWS = 1024;   // staged window rows per task
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+template <int C>
+__global__ void __launch_bounds__(SW_WARPS * 32)
+sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restrict__ tasks,
+                 const SwClassArgs cls, int32_t *__restrict__ scores, int32_t *__restrict__ errs) {
+  __shared__ unsigned short s_ref[SW_WARPS][SW2_MAXROWS + 32];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  unsigned short *const sref = s_ref[threadIdx.x >> 5];
+  const uint32_t ngi2 = (uint32_t)((-sc.gap_init) & 0xffff) * 0x10001u;
+  const uint32_t nge2 = (uint32_t)((-sc.gap_ext) & 0xffff) * 0x10001u;
+  const uint32_t T0 = (uint32_t)(sc.match & 0xff) | ((uint32_t)(sc.mismatch & 0xff) * 0x01010100u), T1 = 0u;
+  const int npairs = (cls.ntasks + 1) >> 1;
+
+  for (;;) {
+    int k = 0;
+    if (lane == 0) k = atomicAdd(cls.counter, 1);
+    k = __shfl_sync(FULL, k, 0);
+    if (k >= npairs) break;
+    const int tixA = __ldg(cls.order + 2 * k);
+    const bool haveB = 2 * k + 1 < cls.ntasks;
+    const int tixB = haveB ? __ldg(cls.order + 2 * k + 1) : tixA;
+    const smb_sw_task ta = tasks[tixA], tb = tasks[tixB];
+    const int qlenA = (int)ta.read_len, qlenB = (int)tb.read_len;
+    const int rlenA = (int)ta.ref_len, rlenB = (int)tb.ref_len;
+    const int rlen = max(rlenA, rlenB);
+    const bool rcA = (ta.flags & SMB_TASK_READ_REVCOMP) != 0, rcB = (tb.flags & SMB_TASK_READ_REVCOMP) != 0;
+    const bool pkA = (ta.flags & SMB_TASK_REF_PACKED) != 0, pkB = (tb.flags & SMB_TASK_REF_PACKED) != 0;
+    __syncwarp();
+    for (int i = lane; i < rlen + 32; i += 32) {
+      const uint32_t a = (i < rlenA) ? ref_base(src, pkA, ta.ref_off, (uint32_t)i) : 7u;
+      const uint32_t b = (i < rlenB) ? ref_base(src, pkB, tb.ref_off, (uint32_t)i) : 7u;
+      sref[i] = (unsigned short)(a | (b << 8));
+    }
+    // per column: PRMT selector nibbles of the read bases {qA, qA|8, qB, qB|8} (N, padding: 4) and
+    // the raw codes for the general path
+    uint32_t qsel[C], qraw[C], H[C], E[C];
+    bool hasX = false;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int j = lane * C + c;
+      const uint32_t qa = (j < qlenA) ? read_base(src.arena, ta.read_off, (uint32_t)qlenA, rcA, (uint32_t)j) : 7u;
+      const uint32_t qb = (j < qlenB) ? read_base(src.arena, tb.read_off, (uint32_t)qlenB, rcB, (uint32_t)j) : 7u;
+      hasX |= (qa == 4u) | (qb == 4u);
+      const uint32_t ia = qa < 4u ? qa : 4u, ib = qb < 4u ? qb : 4u;
+      qsel[c] = ia | ((ia | 8u) << 4) | (ib << 8) | ((ib | 8u) << 12);
+      qraw[c] = qa | (qb << 8);
+      H[c] = 0u;
+      E[c] = 0u;
+    }
+    const bool general = __any_sync(FULL, hasX);
+    __syncwarp();
+    uint32_t hdiag = 0u, hout = 0u, fout = 0u, best = 0u;
+    const int nsteps = rlen + 31;
+    for (int t = 0; t < nsteps; ++t) {
+      uint32_t hl = __shfl_up_sync(FULL, hout, 1);
+      uint32_t F = __shfl_up_sync(FULL, fout, 1);
+      if (lane == 0) { hl = 0u; F = 0u; }
+      const int i = t - lane;
+      const bool active = i >= 0 && i < rlen;
+      const uint32_t r2 = active ? (uint32_t)sref[i] : 0x0707u;
+      const bool slow = general || __any_sync(FULL, active && (r2 & 0x0404u) != 0u);
+      if (active) {
+        uint32_t diag = hdiag;
+        hdiag = hl;
+        if (!slow) {
+          const uint32_t rsel = (r2 & 0xffu) * 0x11u | (r2 >> 8) * 0x1100u;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const uint32_t s2 = prmt(T0, T1, qsel[c] ^ rsel);
+            const uint32_t h = __viaddmax_s16x2_relu(diag, s2, 0u);
+            diag = H[c];
+            const uint32_t hn = __vimax3_s16x2(h, E[c], F);
+            best = __vmaxs2(best, hn);
+            const uint32_t tt = __viaddmax_s16x2(hn, ngi2, 0x80008000u);
+            E[c] = __viaddmax_s16x2(E[c], nge2, tt);
+            F = __viaddmax_s16x2_relu(F, nge2, tt);
+            H[c] = hn;
+          }
+        } else {
+          const uint32_t ra = r2 & 0xffu, rb = r2 >> 8;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const uint32_t qa = qraw[c] & 0xffu, qb = qraw[c] >> 8;
+            const int sa = (int)sc.S[ra * 8u + qa], sb = (int)sc.S[rb * 8u + qb];
+            const uint32_t s2 = ((uint32_t)sa & 0xffffu) | ((uint32_t)sb << 16);
+            const uint32_t h = __viaddmax_s16x2_relu(diag, s2, 0u);
+            diag = H[c];
+            const uint32_t hn = __vimax3_s16x2(h, E[c], F);
+            best = __vmaxs2(best, hn);
+            const uint32_t tt = __viaddmax_s16x2(hn, ngi2, 0x80008000u);
+            E[c] = __viaddmax_s16x2(E[c], nge2, tt);
+            F = __viaddmax_s16x2_relu(F, nge2, tt);
+            H[c] = hn;
+          }
+        }
+        hout = H[C - 1];
+        fout = F;
+      }
+    }
+    int bA = (int)(short)(best & 0xffffu), bB = (int)(short)(best >> 16);
+    bA = __reduce_max_sync(FULL, bA);
+    bB = __reduce_max_sync(FULL, bB);
+    if (lane == 0) {
+      scores[tixA] = bA;
+      errs[tixA] = SMB_OK;
+      if (haveB) { scores[tixB] = bB; errs[tixB] = SMB_OK; }
+    }
+  }
+}
+
+template <int C>
+static cudaError_t launch_class2(const Scoring &sc, const SeqSrc &src, const smb_sw_task *d_tasks,
+                                 const SwClassArgs &cls, int32_t *d_scores, int32_t *d_errs, int grid,
+                                 cudaStream_t st) {
+  sw_score2_kernel<C><<<grid, SW_WARPS * 32, 0, st>>>(sc, src, d_tasks, cls, d_scores, d_errs);
+  return cudaGetLastError();
+}
+
 // Host-side plan: tasks bucketed by columns-per-lane class (one launch per class).
-void plan_sw(const smb_sw_task *h_tasks, int ntasks, int sm_count, SwPlan &plan) {
+void plan_sw(const smb_sw_task *h_tasks, int ntasks, int sm_count, const Scoring &sc, SwPlan &plan) {
   constexpr int NCLS = 8;
   plan.order.resize((size_t)ntasks);
   uint32_t max_rlen_multi = 0;
@@ -181,15 +324,27 @@ void plan_sw(const smb_sw_task *h_tasks, int ntasks, int sm_count, SwPlan &plan)
     int c = (int)((qlen + 31) / 32);
     return c < 1 ? 1 : (c > NCLS ? NCLS : c);
   };
-  for (int c = 0; c <= NCLS; ++c) plan.count[c] = plan.start[c] = 0;
+  // two-tasks-per-warp 16-bit kernel: single column block, staged window, scores that fit
+  const bool pen16 = sc.match > 0 && sc.match < 128 && sc.mismatch <= 0 && sc.mismatch > -128 && sc.gap_init >= 0 &&
+                     sc.gap_init < 8000 && sc.gap_ext >= 0 && sc.gap_ext < 8000 && sc.S[5] == 0 && sc.S[5 * 8] == 0;
+  auto pair16 = [&](const smb_sw_task &t) {
+    return pen16 && t.read_len <= 32u * NCLS && t.ref_len <= (uint32_t)SW2_MAXROWS &&
+           (long long)t.read_len * sc.match <= 16000;
+  };
+  // slots 1..8: 32-bit classes, 9..16: paired 16-bit classes
+  for (int c = 0; c <= 2 * NCLS; ++c) plan.count[c] = plan.start[c] = 0;
   for (int i = 0; i < ntasks; ++i) {
-    plan.count[cls_of(h_tasks[i].read_len)]++;
+    const int c = cls_of(h_tasks[i].read_len);
+    plan.count[pair16(h_tasks[i]) ? c + NCLS : c]++;
     if (h_tasks[i].read_len > 32u * NCLS) max_rlen_multi = std::max(max_rlen_multi, h_tasks[i].ref_len);
   }
-  for (int c = 1; c <= NCLS; ++c) plan.start[c] = plan.start[c - 1] + plan.count[c - 1];
-  int fill[NCLS + 1];
-  for (int c = 0; c <= NCLS; ++c) fill[c] = plan.start[c];
-  for (int i = 0; i < ntasks; ++i) plan.order[(size_t)fill[cls_of(h_tasks[i].read_len)]++] = i;
+  for (int c = 1; c <= 2 * NCLS; ++c) plan.start[c] = plan.start[c - 1] + plan.count[c - 1];
+  int fill[2 * NCLS + 1];
+  for (int c = 0; c <= 2 * NCLS; ++c) fill[c] = plan.start[c];
+  for (int i = 0; i < ntasks; ++i) {
+    const int c = cls_of(h_tasks[i].read_len);
+    plan.order[(size_t)fill[pair16(h_tasks[i]) ? c + NCLS : c]++] = i;
+  }
   // long reads first inside the multi-block class (largest tasks start earliest)
   if (max_rlen_multi)
     std::stable_sort(plan.order.begin() + plan.start[NCLS], plan.order.begin() + plan.start[NCLS] + plan.count[NCLS],
@@ -208,7 +363,26 @@ cudaError_t launch_sw_score(const Scoring &sc, const SeqSrc &src, const smb_sw_t
                             int32_t *d_scores, int32_t *d_errs, cudaStream_t st, int *nlaunch) {
   constexpr int NCLS = 8;
   cudaError_t e;
-  if ((e = cudaMemsetAsync(d_counters, 0, 16 * sizeof(int), st)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(d_counters, 0, 32 * sizeof(int), st)) != cudaSuccess) return e;
+  for (int c = 1; c <= NCLS; ++c) {   // paired 16-bit classes
+    const int n = plan.count[c + NCLS];
+    if (!n) continue;
+    SwClassArgs cls{d_order + plan.start[c + NCLS], n, d_counters + c + NCLS};
+    int grid = ((n + 1) / 2 + SW_WARPS - 1) / SW_WARPS;
+    if (grid > plan.max_grid) grid = plan.max_grid;
+    switch (c) {
+      case 1: e = launch_class2<1>(sc, src, d_tasks, cls, d_scores, d_errs, grid, st); break;
+      case 2: e = launch_class2<2>(sc, src, d_tasks, cls, d_scores, d_errs, grid, st); break;
+      case 3: e = launch_class2<3>(sc, src, d_tasks, cls, d_scores, d_errs, grid, st); break;
+      case 4: e = launch_class2<4>(sc, src, d_tasks, cls, d_scores, d_errs, grid, st); break;
+      case 5: e = launch_class2<5>(sc, src, d_tasks, cls, d_scores, d_errs, grid, st); break;
+      case 6: e = launch_class2<6>(sc, src, d_tasks, cls, d_scores, d_errs, grid, st); break;
+      case 7: e = launch_class2<7>(sc, src, d_tasks, cls, d_scores, d_errs, grid, st); break;
+      default: e = launch_class2<8>(sc, src, d_tasks, cls, d_scores, d_errs, grid, st); break;
+    }
+    if (e != cudaSuccess) return e;
+    ++*nlaunch;
+  }
   for (int c = 1; c <= NCLS; ++c) {
     if (!plan.count[c]) continue;
     SwClassArgs cls{d_order + plan.start[c], plan.count[c], d_counters + c};
