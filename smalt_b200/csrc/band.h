@@ -56,15 +56,20 @@ constexpr int BW_MAXDIAG = 64;    // band diagonals: two per lane
 // The wavefront kernel handles a task when its window, read and band fit the per-warp
 // shared-memory staging.  Recursion sub-ranges only shrink rows and band, so the test on the
 // initial geometry covers every DP pass of the task.
-SMB_HD bool band_warp_eligible(int l_edge, int r_edge, int p_left, int p_right, int read_len,
-                               int u_left, int u_right, int ref_len) {
-  if (ref_len > BW_MAXROWS || read_len > BW_MAXREAD || ref_len < 1 || read_len < 1) return false;
+// returns 0 (not eligible), 16 (half a warp per task: band <= 32 diagonals) or 32
+SMB_HD int band_warp_lanes(int l_edge, int r_edge, int p_left, int p_right, int read_len,
+                           int u_left, int u_right, int ref_len) {
+  if (ref_len > BW_MAXROWS || read_len > BW_MAXREAD || ref_len < 1 || read_len < 1) return 0;
   Band b;
-  if (band_init(b, l_edge, r_edge, p_left, p_right, read_len, u_left, u_right, ref_len)) return true;
+  if (band_init(b, l_edge, r_edge, p_left, p_right, read_len, u_left, u_right, ref_len)) return 16;
   // the clipped width can grow by at most the rows skipped when a sub-range starts further down:
   // bound it by the unclipped width
   const int bw0 = r_edge - l_edge + 1;
   const int bw = (bw0 <= 0) ? (b.q_len - b.q_left) : bw0;
-  return bw <= BW_MAXDIAG;
+  return bw <= BW_MAXDIAG / 2 ? 16 : (bw <= BW_MAXDIAG ? 32 : 0);
+}
+SMB_HD bool band_warp_eligible(int l_edge, int r_edge, int p_left, int p_right, int read_len,
+                               int u_left, int u_right, int ref_len) {
+  return band_warp_lanes(l_edge, r_edge, p_left, p_right, read_len, u_left, u_right, ref_len) != 0;
 }
 }  // namespace smb

@@ -328,12 +328,13 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, BandPlan &p
   std::vector<int> wc((size_t)ntasks);
   int count[32] = {0};
   auto cls = [](int wcap) { int c = 0; while ((32 << c) < wcap) ++c; return c; };
-  constexpr int WARP_CLS = 31;  // pseudo class of the warp-per-task kernel (always last in `order`)
+  constexpr int WARP_CLS = 31, HALF_CLS = 30;  // pseudo classes of the warp / half-warp kernels (last in `order`)
   for (int i = 0; i < ntasks; ++i) {
     const smb_band_task &t = h_tasks[i];
-    if (align && band_warp_eligible(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
-                                    (int)t.ref_len)) {
-      wc[(size_t)i] = WARP_CLS;
+    const int wl = align ? band_warp_lanes(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left,
+                                           t.u_right, (int)t.ref_len) : 0;
+    if (wl) {
+      wc[(size_t)i] = wl == 16 ? HALF_CLS : WARP_CLS;
     } else {
       const int need = ring_need(t, !align);
       wc[(size_t)i] = cls(pow2_at_least(need + 1));
@@ -346,8 +347,10 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, BandPlan &p
   int fill[32];
   for (int c = 0; c < 32; ++c) fill[c] = start[c];
   for (int i = 0; i < ntasks; ++i) plan.order[(size_t)fill[wc[(size_t)i]]++] = i;
-  for (int c = 0; c < WARP_CLS; ++c)
+  for (int c = 0; c < HALF_CLS; ++c)
     if (count[c]) plan.classes.push_back(BandPlan::Class{32 << c, start[c], count[c]});
+  plan.half_start = start[HALF_CLS];
+  plan.half_count = count[HALF_CLS];
   plan.warp_start = start[WARP_CLS];
   plan.warp_count = count[WARP_CLS];
 }
@@ -382,9 +385,13 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++*nlaunch;
   }
+  if (align && plan.half_count &&
+      (e = launch_band_warp(sc, src, d_tasks, d_order + plan.half_start, plan.half_count, 16, d_ticket, out, max_res,
+                            d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)
+    return e;
   if (align && plan.warp_count)
-    return launch_band_warp(sc, src, d_tasks, d_order + plan.warp_start, plan.warp_count, d_ticket, out, max_res,
-                            d_diff_off, d_diff_cap, sm_count, st, nlaunch);
+    return launch_band_warp(sc, src, d_tasks, d_order + plan.warp_start, plan.warp_count, 32, d_ticket + 1, out,
+                            max_res, d_diff_off, d_diff_cap, sm_count, st, nlaunch);
   return cudaSuccess;
 }
 

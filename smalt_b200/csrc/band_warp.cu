@@ -21,7 +21,11 @@
 //    the warp then takes the maximum score with ties broken towards the smaller (row, column);
 //  * backtrace, DiffStr reversal, result emission and the pre-order recursion are executed by
 //    lane 0 out of shared memory, exactly as in band_dp.cu.
-// Tasks whose window/read/band exceed the staging (long reads) stay with band_kernel<true>.
+// Bands of at most 32 diagonals (every C1-C4 short-read task) use HALF a warp per task
+// (template LANES = 16): the two halves of a warp are independent 16-lane groups with their
+// own task, shared-memory slice, shuffle width and sync mask, which doubles the busy lanes at
+// band width ~20.  Tasks whose window/read/band exceed the staging (long reads) stay with
+// band_kernel<true>.
 #include "common.cuh"
 #include "band.h"
 
@@ -32,8 +36,9 @@ constexpr int BWK_ROWW = BW_MAXROWS / 16;
 constexpr int BWK_STACK = 48;
 constexpr int BWK_REV = BW_MAXROWS + BW_MAXREAD + 16;
 
-struct WarpSmem {
-  uint32_t dirs[BW_MAXDIAG * BWK_ROWW];
+template <int LANES>
+struct WarpSmem {   // one per task group (LANES lanes, 2*LANES diagonals)
+  uint32_t dirs[2 * LANES * BWK_ROWW];
   uint8_t ref[BW_MAXROWS];
   uint8_t read[BW_MAXREAD];
   uint8_t rev[BWK_REV];
@@ -42,40 +47,44 @@ struct WarpSmem {
 
 #define DIFFB(count, typ) ((uint8_t)((count) + ((typ) << 6)))
 
+template <int LANES>
 __global__ void __launch_bounds__(BWK_WARPS * 32)
 band_warp_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__restrict__ tasks,
                  const int *__restrict__ order, const int ntasks, int *__restrict__ ticket,
                  BandOut out, const int max_res, const uint64_t *__restrict__ diff_off,
                  const uint32_t *__restrict__ diff_cap) {
-  __shared__ WarpSmem s_w[BWK_WARPS];
+  constexpr int GROUPS = 32 / LANES;          // task groups per warp
+  constexpr int MAXDIAG = 2 * LANES;
+  __shared__ WarpSmem<LANES> s_w[BWK_WARPS * GROUPS];
   __shared__ unsigned long long s_S64[8];
-  const unsigned FULL = 0xffffffffu;
   if (threadIdx.x < 8) {
     unsigned long long v = 0;
     for (int q = 0; q < 8; ++q) v |= (unsigned long long)(unsigned char)sc.S[threadIdx.x * 8 + q] << (q * 8);
     s_S64[threadIdx.x] = v;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  WarpSmem &sm = s_w[threadIdx.x >> 5];
+  // a group is an independent LANES-wide "warp": own mask for shuffles and syncs
+  const int lane = threadIdx.x & (LANES - 1);
+  const unsigned FULL = (LANES == 32) ? 0xffffffffu : (0xffffu << (threadIdx.x & 16));
+  WarpSmem<LANES> &sm = s_w[threadIdx.x / LANES];
   const int gi = sc.gap_init, ge = sc.gap_ext;
   unsigned long long ncell_tot = 0;
 
   for (;;) {
     int k = 0;
     if (lane == 0) k = atomicAdd(ticket, 1);
-    k = __shfl_sync(FULL, k, 0);
+    k = __shfl_sync(FULL, k, 0, LANES);
     if (k >= ntasks) break;
     const int tix = __ldg(order + k);
     const smb_band_task tk = tasks[tix];
     const bool rc = (tk.flags & SMB_TASK_READ_REVCOMP) != 0;
     const bool packed = (tk.flags & SMB_TASK_REF_PACKED) != 0;
     const int qlen = (int)tk.read_len, rlen = (int)tk.ref_len;
-    __syncwarp();
-    for (int x = lane; x < rlen; x += 32) sm.ref[x] = (uint8_t)ref_base(src, packed, tk.ref_off, (uint32_t)x);
-    for (int x = lane; x < qlen; x += 32)
+    __syncwarp(FULL);
+    for (int x = lane; x < rlen; x += LANES) sm.ref[x] = (uint8_t)ref_base(src, packed, tk.ref_off, (uint32_t)x);
+    for (int x = lane; x < qlen; x += LANES)
       sm.read[x] = (uint8_t)read_base(src.arena, tk.read_off, tk.read_len, rc, (uint32_t)x);
-    __syncwarp();
+    __syncwarp(FULL);
 
     int err = SMB_OK;
     uint32_t nres = 0, diff_used = 0;
@@ -95,14 +104,14 @@ band_warp_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
     }
     while (sp > 0 && !err) {   // every variable tested here is warp-uniform
       --sp;
-      __syncwarp();
+      __syncwarp(FULL);
       const int s_left = sm.stk_l[sp], s_right = sm.stk_r[sp];
       Band b;
       if (band_init(b, tk.l_edge, tk.r_edge, tk.p_left, tk.p_right, qlen, s_left, s_right, rlen))
         continue;                                                          // :1333-1338
       if (b.s_left >= b.s_len || b.band_width < 0) { err = SMB_ERRCODE_ASSERT; break; }  // :459
       const int nrows = b.s_len - b.s_left, bw = b.band_width;
-      if (bw > BW_MAXDIAG || nrows > BW_MAXROWS) { err = SMB_ERR_ARG; break; }  // host planner bug
+      if (bw > MAXDIAG || nrows > BW_MAXROWS) { err = SMB_ERR_ARG; break; }  // host planner bug
 
       // ---------------- wavefront DP ----------------
       const int dA = 2 * lane, dB = dA + 1;
@@ -116,7 +125,7 @@ band_warp_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
       for (int it = 0; it < iters; ++it) {
         const int r = it - lane;
         const bool rowok = r >= 0 && r < nrows;
-        const int Fin = __shfl_up_sync(FULL, FB, 1);    // F(r, dA-1) from the left neighbour's last step
+        const int Fin = __shfl_up_sync(FULL, FB, 1, LANES);    // F(r, dA-1) from the left neighbour's last step
         int jA = b.l_edge + r + dA;
         unsigned long long srow = 0;
         if (rowok) srow = s_S64[sm.ref[b.s_left + r]];
@@ -150,7 +159,7 @@ band_warp_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
             if ((r & 15) == 15 || r == nrows - 1) { sm.dirs[dA * BWK_ROWW + (r >> 4)] = wA; wA = 0; }
           }
         }
-        const int Ein = __shfl_down_sync(FULL, eA, 1);   // E(r-1, dB+1) from the right neighbour, this iteration
+        const int Ein = __shfl_down_sync(FULL, eA, 1, LANES);   // E(r-1, dB+1) from the right neighbour, this iteration
         // ---- diagonal B ----
         {
           const int jB = jA + 1;
@@ -160,7 +169,7 @@ band_warp_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
           if (ok) {
             const int q = sm.read[jB];
             const int h = HB + (int)(signed char)(srow >> (q << 3));
-            e = (lane == 31) ? 0 : Ein;
+            e = (lane == LANES - 1) ? 0 : Ein;
             F = FA;                                   // F(r, dA): just computed
             const int ep = max(e, 0), fp = max(F, 0), m = max(ep, fp);
             const bool dia = h > m;
@@ -191,15 +200,15 @@ band_warp_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
       if (best > 0)
         key = ((unsigned long long)(unsigned)best << 32) | ((unsigned long long)(0xffffu - (unsigned)bestr) << 16) |
               (unsigned long long)(0xffffu - (unsigned)(b.l_edge + bestr + bestd - b.q_left));
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(FULL, key, o);
+      for (int o = LANES / 2; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(FULL, key, o, LANES);
         key = other > key ? other : key;
       }
       const int max_scor = (int)(key >> 32);
       const int max_r = (int)(0xffffu - (unsigned)((key >> 16) & 0xffffu));
       const int max_j = (int)(0xffffu - (unsigned)(key & 0xffffu)) + b.q_left;
       const int max_i = b.s_left + max_r;
-      __syncwarp();
+      __syncwarp(FULL);
       if (max_scor < minscore) continue;                                   // :1364
 
       // ---------------- makeMetaFromTrack (alignment.c:628-781), lane 0 ----------------
@@ -245,11 +254,11 @@ band_warp_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
         if (ovf) flag = SMB_ERR_CAPACITY;
         else if (checksum != max_scor) flag = SMB_ERRCODE_SWATSCOR;        // :767
       }
-      flag = __shfl_sync(FULL, flag, 0);
+      flag = __shfl_sync(FULL, flag, 0, LANES);
       if (flag) { err = flag; break; }
-      i = __shfl_sync(FULL, i, 0);
-      j = __shfl_sync(FULL, j, 0);
-      n = __shfl_sync(FULL, n, 0);
+      i = __shfl_sync(FULL, i, 0, LANES);
+      j = __shfl_sync(FULL, j, 0, LANES);
+      n = __shfl_sync(FULL, n, 0, LANES);
       const int prof_start = j + 1, prof_end = max_j, np_start = i + 1, np_end = max_i;
       if (prof_start + minscorlen > prof_end + 1) continue;                // :1379
       if (max_scor >= minscore) {                                          // :1384 addALIMETAtoRsltSet
@@ -287,16 +296,16 @@ band_warp_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
             }
           }
         }
-        f2 = __shfl_sync(FULL, f2, 0);
+        f2 = __shfl_sync(FULL, f2, 0, LANES);
         if (f2) { err = f2; break; }
-        diff_used = __shfl_sync(FULL, u, 0);
+        diff_used = __shfl_sync(FULL, u, 0, LANES);
         ++nres;
       }
       // pre-order recursion: left part first, so push right then left (:1389, :1411)
       const bool go_left = s_left + minscorlen < np_start;
       const bool go_right = s_right > np_end + minscorlen;
       if (sp + 2 > BWK_STACK && (go_left || go_right)) { err = SMB_ERR_CAPACITY; break; }
-      __syncwarp();
+      __syncwarp(FULL);
       if (go_right) { if (lane == 0) { sm.stk_l[sp] = np_end + 1; sm.stk_r[sp] = s_right; } ++sp; }
       if (go_left) { if (lane == 0) { sm.stk_l[sp] = s_left; sm.stk_r[sp] = np_start - 1; } ++sp; }
     }
@@ -306,29 +315,36 @@ band_warp_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
       if (out.dused) out.dused[tix] = diff_used;
     }
   }
-  for (int o = 16; o > 0; o >>= 1) ncell_tot += __shfl_down_sync(FULL, ncell_tot, o);
+  for (int o = LANES / 2; o > 0; o >>= 1) ncell_tot += __shfl_down_sync(FULL, ncell_tot, o, LANES);
   if (lane == 0 && ncell_tot) atomicAdd(out.cells, ncell_tot);
 }
 
 cudaError_t launch_band_warp(const Scoring &sc, const SeqSrc &src, const smb_band_task *d_tasks,
-                             const int *d_order, int ntasks, int *d_ticket, BandOut out, int max_res,
+                             const int *d_order, int ntasks, int lanes, int *d_ticket, BandOut out, int max_res,
                              const uint64_t *d_diff_off, const uint32_t *d_diff_cap, int sm_count,
                              cudaStream_t st, int *nlaunch) {
   if (ntasks <= 0) return cudaSuccess;
   cudaError_t e = cudaMemsetAsync(d_ticket, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
-  int grid = (ntasks + BWK_WARPS - 1) / BWK_WARPS;
-  const int cap = sm_count * 10;
+  const int per_cta = BWK_WARPS * (32 / lanes);
+  int grid = (ntasks + per_cta - 1) / per_cta;
+  const int cap = sm_count * 8;
   if (grid > cap) grid = cap;
-  band_warp_kernel<<<grid, BWK_WARPS * 32, 0, st>>>(sc, src, d_tasks, d_order, ntasks, d_ticket, out, max_res,
-                                                    d_diff_off, d_diff_cap);
+  if (lanes == 16)
+    band_warp_kernel<16><<<grid, BWK_WARPS * 32, 0, st>>>(sc, src, d_tasks, d_order, ntasks, d_ticket, out, max_res,
+                                                          d_diff_off, d_diff_cap);
+  else
+    band_warp_kernel<32><<<grid, BWK_WARPS * 32, 0, st>>>(sc, src, d_tasks, d_order, ntasks, d_ticket, out, max_res,
+                                                          d_diff_off, d_diff_cap);
   ++*nlaunch;
   return cudaGetLastError();
 }
 
 cudaError_t warm_band_warp() {
   cudaFuncAttributes a;
-  return cudaFuncGetAttributes(&a, band_warp_kernel);
+  cudaError_t e = cudaFuncGetAttributes(&a, band_warp_kernel<16>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, band_warp_kernel<32>);
+  return e;
 }
 
 }  // namespace smb

@@ -90,7 +90,8 @@ struct BandPlan {
   struct Class { int wcap, start, count; };
   std::vector<int> order;       // thread-per-task classes first, then the warp-per-task tasks
   std::vector<Class> classes;
-  int warp_start = 0, warp_count = 0;   // K3 tasks of band_warp_kernel (band_warp.cu)
+  int warp_start = 0, warp_count = 0;   // K3 tasks of band_warp_kernel<32> (band_warp.cu)
+  int half_start = 0, half_count = 0;   // ... and of band_warp_kernel<16> (two tasks per warp)
 };
 void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, BandPlan &plan);
 size_t band_gring_words(const BandPlan &plan);
@@ -101,7 +102,7 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
                         const uint64_t *d_diff_off, const uint32_t *d_diff_cap,
                         uint32_t *d_gring, int *d_ticket, int sm_count, cudaStream_t st, int *nlaunch);
 cudaError_t launch_band_warp(const Scoring &sc, const SeqSrc &src, const smb_band_task *d_tasks,
-                             const int *d_order, int ntasks, int *d_ticket, BandOut out, int max_res,
+                             const int *d_order, int ntasks, int lanes, int *d_ticket, BandOut out, int max_res,
                              const uint64_t *d_diff_off, const uint32_t *d_diff_cap, int sm_count,
                              cudaStream_t st, int *nlaunch);
 cudaError_t warm_band_warp();
