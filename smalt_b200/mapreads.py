@@ -24,8 +24,15 @@ def main(argv=None):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     dist = None
     if world > 1:
+        import torch
         import torch.distributed as dist
-        dist.init_process_group(args.backend or "nccl")
+        backend = args.backend or "nccl"
+        if backend == "nccl":
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
     text = open(args.reads, "rb").read()
     mine = shard_of(text, rank, world)
     cores = len(os.sched_getaffinity(0))

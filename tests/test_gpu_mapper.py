@@ -121,3 +121,23 @@ def test_mapreads_entry_point(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     got = [l for l in open(out).read().splitlines() if not l.startswith("@")]
     assert got == want
+
+
+@needs
+def test_mapreads_two_gpus(tmp_path):
+    """two ranks, two GPUs: reads sharded by rank, SAM merged in input order == reference"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    pref, fq, text = _workload(tmp_path, 14, [400_000], 13, 6, 20000, (150, 151), 0.02)
+    _, want = _ref_sam(tmp_path, pref, fq)
+    out = str(tmp_path / "b200.sam")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29561", "-m", "smalt_b200.mapreads",
+                        "-n", "1", "-r", "7", "-o", out, pref, fq], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = [l for l in open(out).read().splitlines() if not l.startswith("@")]
+    # each rank draws from its own drand48 stream: compare like the reference's threaded test
+    assert len(got) == len(want)
+    diff = [(a, b) for a, b in zip(got, want) if a != b and (int(a.split("\t")[4]) > 6 or int(b.split("\t")[4]) > 6)]
+    assert not diff, diff[0]
