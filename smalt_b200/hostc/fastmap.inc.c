@@ -22,6 +22,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include "fastprintf.h"
 
 typedef int (FASTMAP_SINKF)(void *user, const char *buf, size_t len);
 
@@ -61,6 +62,11 @@ typedef struct {
   size_t n_alloc;
   int memfd;
   char fdpath[64];
+  char *scratch;             /* NUL-terminated copies of the lines of one record */
+  size_t scratch_alloc;
+  FILE *keyfp;               /* stream handed to the report writer while its output is captured */
+  char *keybuf;
+  size_t keylen;
   ErrMsg *errmsgp;
   double ms_prev[3], wall_prev[11], cpu_prev[8];
   uint64_t counts_prev[5];
@@ -196,6 +202,111 @@ static int fm_worker_setup(FmWorker *w, FastMap *fm, int id)
   return ERRCODE_SUCCESS;
 }
 
+
+/* header line -> name, the rule of readHeader (sequence.c:1056-1140): the prompt is dropped,
+ * leading white space skipped, of every later run of white space the first character is kept,
+ * one trailing white-space character is removed */
+static size_t fm_header_name(char *dst, const char *line, size_t len)
+{
+  size_t i, n = 0;
+  int was_space = 1;
+  for (i = 1; i < len; i++) { /* line[0] is the prompt */
+    const unsigned char c = (unsigned char) line[i];
+    const int sp = (c == ' ' || (c >= 9 && c <= 13));
+    if (was_space) {
+      if (sp) continue;
+      was_space = 0;
+    } else if (sp) {
+      was_space = 1;
+    }
+    dst[n++] = (char) c;
+  }
+  if (was_space && n > 0) n--;
+  dst[n] = '\0';
+  return n;
+}
+
+static int fm_has_space(const char *p, size_t len)
+{
+  size_t i;
+  unsigned acc = 0;
+  for (i = 0; i < len; i++) {
+    const unsigned char c = (unsigned char) p[i];
+    acc |= (unsigned) (c == ' ') | (unsigned) (c - 9u <= 4u);
+  }
+  return acc != 0;
+}
+
+static int fm_reads_reserve(FmWorker *w, size_t n)
+{
+  if (n >= w->n_alloc) {
+    const size_t na = w->n_alloc ? 2 * w->n_alloc : 1024;
+    SeqFastq **hp = (SeqFastq **) realloc(w->reads, na * sizeof(SeqFastq *));
+    uint32_t *mp = (uint32_t *) realloc(w->mincov, na * sizeof(uint32_t));
+    if (hp) w->reads = hp;
+    if (mp) w->mincov = mp;
+    if (!hp || !mp) return ERRCODE_NOMEM;
+    memset(w->reads + w->n_alloc, 0, (na - w->n_alloc) * sizeof(SeqFastq *));
+    w->n_alloc = na;
+  }
+  if (!w->reads[n] && !(w->reads[n] = seqFastqCreate(0, SEQTYP_UNKNOWN))) return ERRCODE_NOMEM;
+  return ERRCODE_SUCCESS;
+}
+
+/* Plain 4-line FASTQ records without white space inside the sequence / quality lines are
+ * loaded straight from the text with seqFastqSetAscii (what infmtRead does for SAM/BAM input,
+ * infmt.c:250-263), reproducing readHeader's name rule.  Returns 1 when the block contains
+ * anything else (blank lines, CR, wrapped or ragged records): the caller then uses the
+ * reference's own parser for the whole block. */
+static int fm_parse_block_fast(FmWorker *w, size_t start, size_t end, size_t *nreads)
+{
+  const char *d = w->fm->data;
+  size_t p = start, n = 0;
+  int errcode;
+  *nreads = 0;
+  while (p < end) {
+    const char *l[4];
+    size_t ll[4], need;
+    int k;
+    char *name, *seq, *qnam, *qual;
+    for (k = 0; k < 4; k++) {
+      const char *nl = (p < end) ? (const char *) memchr(d + p, '\n', end - p) : NULL;
+      if (!nl) return 1;
+      l[k] = d + p;
+      ll[k] = (size_t) (nl - (d + p));
+      p = (size_t) (nl - d) + 1;
+    }
+    if (ll[0] < 1 || l[0][0] != '@' || ll[2] < 1 || l[2][0] != '+' || ll[1] < 1 || ll[1] != ll[3] ||
+	fm_has_space(l[1], ll[1]) || fm_has_space(l[3], ll[3]))
+      return 1;
+    need = ll[0] + ll[1] + ll[2] + ll[3] + 8;
+    if (need > w->scratch_alloc) {
+      char *hp = (char *) realloc(w->scratch, 2 * need);
+      if (!hp) return ERRCODE_NOMEM;
+      w->scratch = hp;
+      w->scratch_alloc = 2 * need;
+    }
+    name = w->scratch;
+    seq = name + ll[0] + 1;
+    qnam = seq + ll[1] + 1;
+    qual = qnam + ll[2] + 1;
+    {
+      size_t nl_ = fm_header_name(name, l[0], ll[0]), ql_ = fm_header_name(qnam, l[2], ll[2]);
+      /* setSeq (sequence.c:780-803) also strips white space at both ends of what it is given */
+      while (nl_ > 0 && isspace((unsigned char) name[nl_ - 1])) nl_--;
+      while (ql_ > 0 && isspace((unsigned char) qnam[ql_ - 1])) ql_--;
+      (void) seq; (void) qual;
+      if ((errcode = fm_reads_reserve(w, n))) return errcode;
+      seqFastqBlank(w->reads[n]);
+      if ((errcode = smbShimSeqFastqLoad(w->reads[n], name, nl_, l[1], ll[1], qnam, ql_, l[3], ll[3])))
+	return errcode;
+    }
+    n++;
+  }
+  *nreads = n;
+  return ERRCODE_SUCCESS;
+}
+
 static int fm_parse_block(FmWorker *w, size_t start, size_t end, size_t *nreads)
 {
   FastMap *fm = w->fm;
@@ -209,6 +320,16 @@ static int fm_parse_block(FmWorker *w, size_t start, size_t end, size_t *nreads)
 	    "rerun with SMALT_B200_REFIO=1 (the reference's own reader)\n", start);
     return errcode;
   }
+  if (!fm->is_fasta && !getenv("SMALT_B200_REFPARSE")) {
+    errcode = fm_parse_block_fast(w, start, end, &n);
+    if (errcode != 1) {
+      if (!errcode && n != nrec_expect) errcode = ERRCODE_FASTA;
+      *nreads = n;
+      return errcode;
+    }
+    errcode = ERRCODE_SUCCESS;
+    n = 0;
+  }
   if (ftruncate(w->memfd, 0)) return ERRCODE_FILEIO;
   for (off = start; off < end;) {
     const ssize_t k = pwrite(w->memfd, fm->data + off, end - off, (off_t) (off - start));
@@ -218,17 +339,7 @@ static int fm_parse_block(FmWorker *w, size_t start, size_t end, size_t *nreads)
   sio = seqIOopen(&errcode, w->fdpath, SEQIO_READ, 0);
   if (!sio) return errcode ? errcode : ERRCODE_NOFILE;
   while (!seqIOstatus(sio)) { /* loadIOBuffArg / infmtRead (smalt.c:795-830, infmt.c:197-240) */
-    if (n >= w->n_alloc) {
-      const size_t na = w->n_alloc ? 2 * w->n_alloc : 1024;
-      SeqFastq **hp = (SeqFastq **) realloc(w->reads, na * sizeof(SeqFastq *));
-      uint32_t *mp = (uint32_t *) realloc(w->mincov, na * sizeof(uint32_t));
-      if (hp) w->reads = hp;
-      if (mp) w->mincov = mp;
-      if (!hp || !mp) { errcode = ERRCODE_NOMEM; break; }
-      memset(w->reads + w->n_alloc, 0, (na - w->n_alloc) * sizeof(SeqFastq *));
-      w->n_alloc = na;
-    }
-    if (!w->reads[n] && !(w->reads[n] = seqFastqCreate(0, SEQTYP_UNKNOWN))) { errcode = ERRCODE_NOMEM; break; }
+    if ((errcode = fm_reads_reserve(w, n))) break;
     seqFastqBlank(w->reads[n]);
     if ((errcode = seqFastqRead(w->reads[n], sio))) break;
     n++;
@@ -277,8 +388,25 @@ static int fm_map_block(FmWorker *w, size_t c)
   }
   if (errcode) { fm_publish(fm, c, NULL, 0, errcode); return errcode; }
 
-  if (!(fp = open_memstream(&buf, &buflen))) { fm_publish(fm, c, NULL, 0, ERRCODE_NOMEM); return ERRCODE_NOMEM; }
-  smbShimReportWriterSetStream(w->writer, fp);
+  /* Formatted records are captured from the reference's fprintf calls (fastprintf.h) for the
+   * line-oriented formats; explicit alignment output (-a) also writes by other means and
+   * goes through a memory stream. */
+  {
+    const int capture = !(macop->oumodflg & REPORTMODIF_ALIOUT) &&
+      (macop->outform == REPORTFMT_SAM || macop->outform == REPORTFMT_CIGAR || macop->outform == REPORTFMT_SSAHA);
+    if (capture) {
+      if (!w->keyfp && !(w->keyfp = open_memstream(&w->keybuf, &w->keylen))) {
+	fm_publish(fm, c, NULL, 0, ERRCODE_NOMEM);
+	return ERRCODE_NOMEM;
+      }
+      fp = NULL;
+      smbFastCaptureBegin(w->keyfp);
+      smbShimReportWriterSetStream(w->writer, w->keyfp);
+    } else {
+      if (!(fp = open_memstream(&buf, &buflen))) { fm_publish(fm, c, NULL, 0, ERRCODE_NOMEM); return ERRCODE_NOMEM; }
+      smbShimReportWriterSetStream(w->writer, fp);
+    }
+  }
   em.w = w; em.fp = fp; em.n = n;
   /* rmapSingleWave takes at most INT_MAX reads; blocks are far smaller */
   for (pos = 0; pos < n && !errcode; pos += 32000) {
@@ -292,7 +420,13 @@ static int fm_map_block(FmWorker *w, size_t c)
     w->reads = save;
   }
   smbShimReportWriterSetStream(w->writer, NULL);
-  if (fclose(fp) && !errcode) errcode = ERRCODE_FILEIO;
+  if (fp) {
+    if (fclose(fp) && !errcode) errcode = ERRCODE_FILEIO;
+  } else {
+    if (smbFastCaptureEnd(&buf, &buflen) && !errcode) errcode = ERRCODE_NOMEM;
+    /* nothing may have reached the key stream itself (it would be out of order) */
+    if (fflush(w->keyfp) || w->keylen != 0) { if (!errcode) errcode = ERRCODE_ASSERT; }
+  }
   pthread_mutex_lock(&g_stats_lock);
   fm->n_reads += n;
   pthread_mutex_unlock(&g_stats_lock);
@@ -448,6 +582,8 @@ static void fastmap_cleanup(void)
     free(w->reads);
     free(w->mincov);
     if (w->memfd > 0) close(w->memfd);
+    if (w->keyfp) { fclose(w->keyfp); free(w->keybuf); }
+    free(w->scratch);
     if (w->errmsgp) { ERRMSG_END(w->errmsgp); }
   }
   free(g_fm_workers);

@@ -25,6 +25,10 @@ int smbShimHitListSet(HashHitList *p, const uint64_t *sqdat, int nhits, int is_r
 int smbShimAliRsltSetAdd(AliRsltSet *p, int score, int qs, int qe, int rs, int re,
 			 const unsigned char *diffstr, int difflen);
 
+/* FASTQ record -> SeqFastq by memcpy (shim_sequence.c) */
+int smbShimSeqFastqLoad(SeqFastq *sqp, const char *name, size_t nlen, const char *seq, size_t slen,
+			const char *qnam, size_t qnlen, const char *qual, size_t qlen);
+
 /* per-worker report writers of the block-parallel driver (shim_report.c) */
 #include "report.h"
 ReportWriter *smbShimReportWriterClone(const ReportWriter *proto);

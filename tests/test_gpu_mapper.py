@@ -141,3 +141,44 @@ def test_mapreads_two_gpus(tmp_path):
     assert len(got) == len(want)
     diff = [(a, b) for a, b in zip(got, want) if a != b and (int(a.split("\t")[4]) > 6 or int(b.split("\t")[4]) > 6)]
     assert not diff, diff[0]
+
+
+@needs
+def test_fast_record_loader_equals_reference_parser(tmp_path):
+    """read names with comments, tabs and runs of blanks, '+name' separator lines, quality lines
+    that start with '@' or '+', CRLF records (those fall back to the reference parser)"""
+    from smalt_b200.mapper import Mapper
+    rng = np.random.default_rng(31)
+    g = random_seq(rng, 80_000)
+    pref = str(tmp_path / "idx")
+    indexer.write_smi(pref, indexer.build_index([g], 13, 6))
+    indexer.write_sma(pref, ["chrT"], [g])
+    recs = []
+    for i in range(1500):
+        L = int(rng.integers(40, 130))
+        st = int(rng.integers(0, len(g) - L))
+        sq = LET[mutate(rng, g[st:st + L].copy(), p_sub=0.02, p_ins=0.002, p_del=0.002)].tobytes().decode()
+        q = "".join(chr(int(x)) for x in rng.integers(40, 74, len(sq)))
+        if i % 3 == 0:
+            q = "@" + q[1:]
+        if i % 4 == 0:
+            q = "+" + q[1:]
+        name = ["r%d", "r%d  two  blanks ", "r%d\tafter tab", " r%d lead", "r%d/1 comment:x=1"][i % 5] % i
+        eol = "\r\n" if 700 <= i < 720 else "\n"
+        recs.append("@%s%s%s%s+%s%s%s%s" % (name, eol, sq, eol, ("r%d" % i) if i % 2 else "", eol, q, eol))
+    text = "".join(recs).encode()
+    fq = str(tmp_path / "t.fq")
+    open(fq, "wb").write(text)
+    _, want = _ref_sam(tmp_path, pref, fq)
+    m = Mapper(pref, 1, ["-r", "7"])
+    try:
+        os.environ["SMALT_B200_BLOCK"] = "200"
+        fast = m.map_fastq(text).decode().splitlines()
+        os.environ["SMALT_B200_REFPARSE"] = "1"
+        slow = m.map_fastq(text).decode().splitlines()
+    finally:
+        os.environ.pop("SMALT_B200_REFPARSE", None)
+        os.environ.pop("SMALT_B200_BLOCK", None)
+        m.close()
+    assert slow == want
+    assert fast == want
