@@ -253,7 +253,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-sample", type=int, default=250_000)
     ap.add_argument("--cpu-sample", type=int, default=250_000)
-    ap.add_argument("--threads", type=int, default=0, help="host worker threads per GPU (0: cores/GPUs)")
+    ap.add_argument("--threads", type=int, default=0, help="host worker threads per GPU (0: 2 x cores / GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cli", action="store_true")
     args = ap.parse_args()
@@ -267,7 +267,7 @@ def main():
 
     n = args.reads
     cores = host_threads()
-    threads = args.threads or max(1, int(round(1.5 * cores / world)))
+    threads = args.threads or max(1, int(round(2.0 * cores / world)))
     genome = make_genome()
     # reads are sharded by rank: rank r maps reads [r*n, (r+1)*n) of the job
     reads, pos, strand, span = simulate_reads(genome, n, seed=43 + 1000 * rank)

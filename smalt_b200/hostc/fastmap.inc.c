@@ -179,7 +179,7 @@ static int fm_emit(void *user, int i, const ResultSet *rsltp)
   if ((macop->menuflg & MENUFLAG_RELSCOR) &&
       (macop->outform == REPORTFMT_SAM || macop->outform == REPORTFMT_BAM))
     reportFixMultiplePrimary(w->rep);
-  return reportWrite(w->writer, w->reads[i], NULL, macop->ssp, macop->codecp, w->rep);
+  return smbShimReportWriteSAM(w->writer, w->reads[i], macop->ssp, macop->codecp, w->rep);
 }
 
 static int fm_worker_setup(FmWorker *w, FastMap *fm, int id)

@@ -34,6 +34,9 @@ int smbShimSeqFastqLoad(SeqFastq *sqp, const char *name, size_t nlen, const char
 ReportWriter *smbShimReportWriterClone(const ReportWriter *proto);
 void smbShimReportWriterSetStream(ReportWriter *p, FILE *fp);
 void smbShimReportWriterDelete(ReportWriter *p);
+/* reportWrite for single-end SAM records with the read decoded once (falls back to reportWrite) */
+int smbShimReportWriteSAM(const ReportWriter *wrp, const SeqFastq *readp, const SeqSet *ssp,
+			  const SeqCodec *codecp, const Report *rep);
 int smbShimWriteSAMHeader(FILE *fp, const SeqSet *ssp, const char *prognam, const char *progversion,
 			  int narg, char * const *argv);
 #endif

@@ -50,3 +50,123 @@ int smbShimWriteSAMHeader(FILE *fp, const SeqSet *ssp, const char *prognam, cons
 {
   return writeSAMHeaderf(fp, ssp, prognam, progversion, narg, argv);
 }
+
+/* ------------------------------------------------------------------------------------
+ * Single-end SAM records without the per-character copies of fprintREPALIsam.
+ *
+ * reportWrite (report.c:1758) -> writeReportForRead -> writeREPALI -> fprintREPALIsam
+ * (:763-905) copies the read into a scratch SeqFastq (seqFastqAppendSegment), decodes it in
+ * place (seqFastqDecode) and prints it with "%s".  smbShimReportWriteSAM prints the same
+ * record with the read decoded once, straight into a thread-local line buffer
+ * (smbShimSeqFastqDecodeSegment).  It covers what the block-parallel driver emits for
+ * single-end reads - SAM format, no mate, no explicit alignment output; for anything else,
+ * and whenever a precondition does not hold, it calls the reference's reportWrite.
+ * ------------------------------------------------------------------------------------ */
+extern int smbShimSeqFastqDecodeSegment(char *seq, char *qual, int *has_qual, const SeqFastq *sqp,
+					SEQLEN_t start, SEQLEN_t len, int reverse, const SeqCodec *codep);
+
+static __thread char *t_seqbuf;
+static __thread size_t t_seqbuf_alloc;
+
+static int samRecordSingle(const ReportWriter *wrp, const REPALI *rrp, const DiffStr *rdfsp,
+			   const SeqFastq *q_sqp, const SeqSet *ssp, const SeqCodec *codecp)
+{
+  int errcode = ERRCODE_SUCCESS;
+  FILE *fp = wrp->oufp;
+  const REPMODIFLG_t oumodiflg = wrp->modflg;
+  const BOOL_t is_mapped = (BOOL_t) ((rrp->status & REPMATEFLG_MAPPED) != 0);
+  const char *s_nam = OUFMT_SAM_NULLSTR, *seqstr, *qualstr;
+  const DIFFSTR_T *diffstr = NULL;
+  int editdist = 0, clip_start = 0, clip_end = 0, swatscor = 0, has_qual = 0;
+  SAMFLAG_t samflg = 0;
+  SEQLEN_t qlen, pos = 0, qseg_start = 0, qseg_len = 0;
+  char cod, *seqbuf, *qualbuf;
+  BOOL_t isReverse = 0, want_seq;
+
+  if (is_mapped) {
+    seqSetGetSeqDatByIndex(NULL, &s_nam, rrp->s_idx, ssp);
+    diffstr = rdfsp->dstrp + rrp->dfo;
+  }
+  if ((errcode = copyReadNamStrToREPSTR(&wrp->nambufp->ref_nam, 0, s_nam)) ||
+      (errcode = copyReadNameToREPSTR(&wrp->nambufp->q_nam, 1, q_sqp)))
+    return errcode;
+  seqFastqGetConstSequence(q_sqp, &qlen, &cod);
+
+  if (is_mapped) {
+    isReverse = (BOOL_t) ((rrp->status & REPMATEFLG_REVERSE) ? 1 : 0);
+    if (oumodiflg & REPORTMODIF_SOFTCLIP) { qseg_start = 0; qseg_len = qlen; }
+    else { qseg_start = rrp->q_start - 1; qseg_len = rrp->q_end - rrp->q_start + 1; }
+    want_seq = 1;
+    pos = (SEQLEN_t) rrp->s_start;
+    if (rrp->q_end > qlen) return ERRCODE_ASSERT;
+    if (isReverse) {
+      samflg |= SAMFLAG_STRAND;
+      clip_start = qlen - rrp->q_end;
+      clip_end = rrp->q_start - 1;
+    } else {
+      clip_start = rrp->q_start - 1;
+      clip_end = qlen - rrp->q_end;
+    }
+    if (rrp->status & REPMATEFLG_PARTIAL) samflg |= SAMFLAG_NOTPRIMARY;
+    swatscor = rrp->swatscor;
+  } else {
+    want_seq = (BOOL_t) ((oumodiflg & REPORTMODIF_SOFTCLIP) != 0);
+    qseg_start = 0;
+    qseg_len = qlen;
+    samflg |= SAMFLAG_NOMAP;
+  }
+  if (want_seq) {
+    /* appendSeqSegment: a zero length means "to the end of the sequence" */
+    if (!qseg_len || qseg_start + qseg_len > qlen) qseg_len = qlen - qseg_start;
+    if (2 * ((size_t) qseg_len + 1) > t_seqbuf_alloc) {
+      char *hp = (char *) realloc(t_seqbuf, 4 * ((size_t) qseg_len + 1));
+      if (!hp) return ERRCODE_NOMEM;
+      t_seqbuf = hp;
+      t_seqbuf_alloc = 4 * ((size_t) qseg_len + 1);
+    }
+    seqbuf = t_seqbuf;
+    qualbuf = t_seqbuf + qseg_len + 1;
+    if ((errcode = smbShimSeqFastqDecodeSegment(seqbuf, qualbuf, &has_qual, q_sqp, qseg_start, qseg_len,
+						is_mapped && isReverse, codecp)))
+      return errcode;
+    seqstr = seqbuf;
+    qualstr = has_qual ? qualbuf : OUFMT_SAM_NULLSTR;
+  } else {
+    seqstr = OUFMT_SAM_NULLSTR;
+    qualstr = OUFMT_SAM_NULLSTR;
+  }
+  if (!qualstr[0]) qualstr = OUFMT_SAM_NULLSTR;
+
+  fprintf(fp, OUFMT_SAM_BEFORE, wrp->nambufp->q_nam.strp, samflg, is_mapped ? wrp->nambufp->ref_nam.strp : OUFMT_SAM_NULLSTR,
+	  pos, rrp->mapscor);
+  if (is_mapped) {
+    errcode = diffStrPrintf(fp, diffstr,
+			    (char) ((oumodiflg & REPORTMODIF_XMISMATCH) ? DIFFSTRFORM_CIGEXT_XMISMATCH : DIFFSTRFORM_CIGEXT),
+			    clip_start, clip_end, (char) ((oumodiflg & REPORTMODIF_SOFTCLIP) != 0));
+    if (!errcode) editdist = diffStrGetLevenshteinDistance(diffstr);
+  } else {
+    fprintf(fp, OUFMT_SAM_NULLSTR);
+  }
+  fprintf(fp, OUFMT_SAM_AFTER, OUFMT_SAM_NULLSTR, 0, 0, seqstr, qualstr, editdist, swatscor);
+  return errcode;
+}
+
+int smbShimReportWriteSAM(const ReportWriter *wrp, const SeqFastq *readp, const SeqSet *ssp,
+			  const SeqCodec *codecp, const Report *rep)
+{
+  int errcode = ERRCODE_SUCCESS, n;
+  const int na = ARRLEN(rep->arAr);
+  char cod;
+  seqFastqGetConstSequence(readp, NULL, &cod);
+  if (wrp->oufmt != REPORTFMT_SAM || (wrp->modflg & REPORTMODIF_ALIOUT) || ARRLEN(rep->arBr) > 0 ||
+      ARRLEN(rep->pairr) > 0 || cod != SEQCOD_MANGLED)
+    return reportWrite(wrp, readp, NULL, ssp, codecp, rep);
+  for (n = 0; n < na; n++)
+    if (rep->arAr[n].status & REPMATEFLG_PAIRED)
+      return reportWrite(wrp, readp, NULL, ssp, codecp, rep);
+  for (n = 0; n < na && !errcode; n++) {
+    rep->arAr[n].was_output = 0;
+    errcode = samRecordSingle(wrp, rep->arAr + n, &rep->dfs, readp, ssp, codecp);
+  }
+  return errcode;
+}

@@ -36,3 +36,42 @@ int smbShimSeqFastqLoad(SeqFastq *sqp, const char *name, size_t nlen, const char
   sqp->type = SEQTYP_FASTQ;
   return ERRCODE_SUCCESS;
 }
+
+/* Decoded (ASCII) bases and quality characters of read segment [start, start+len) in one pass,
+ * as fprintREPALIsam obtains them with seqFastqAppendSegment (reverse complement for reads
+ * mapped to the reverse strand, appendSeqSegment sequence.c:878-892) + seqFastqDecode
+ * (decodeSeq :1552-1563).  seq/qual get len characters and a terminating 0; *has_qual = 0 when
+ * the read carries no qualities.  Returns ERRCODE_SEQCODE if the read is not in the mangled
+ * encoding (the caller then uses the reference's own functions). */
+int smbShimSeqFastqDecodeSegment(char *seq, char *qual, int *has_qual, const SeqFastq *sqp,
+				 SEQLEN_t start, SEQLEN_t len, int reverse, const SeqCodec *codep)
+{
+  const SEQSEQ *dp = sqp->datap, *qp = sqp->qualp;
+  const unsigned char *cp;
+  SEQLEN_t i;
+  if (dp->code != SEQCOD_MANGLED) return ERRCODE_SEQCODE;
+  if (start > dp->size || start + len > dp->size) return ERRCODE_ARGRANGE;
+  cp = (const unsigned char *) dp->basep + start;
+  if (reverse) {
+    for (i = 0; i < len; i++) {
+      const unsigned char c = cp[len - 1 - i];
+      seq[i] = (char) codep->decodtab[(c & SEQCOD_STDNT_TESTBIT) ? c :
+				      (unsigned char) codep->codtab_complement[c & SEQCOD_STDNT_MASK]];
+    }
+  } else {
+    for (i = 0; i < len; i++) seq[i] = (char) codep->decodtab[cp[i]];
+  }
+  seq[len] = '\0';
+  /* seqFastqAppendSegment (sequence.c:1934-1949) copies qualities whenever there are any */
+  *has_qual = qp != NULL && qp->size >= 1;
+  if (*has_qual && qp->size != dp->size) return ERRCODE_QUALLEN;
+  if (*has_qual) {
+    const char *qc = qp->basep + start;
+    if (reverse) for (i = 0; i < len; i++) qual[i] = qc[len - 1 - i];
+    else memcpy(qual, qc, len);
+    qual[len] = '\0';
+  } else {
+    qual[0] = '\0';
+  }
+  return ERRCODE_SUCCESS;
+}

@@ -11,7 +11,7 @@ import sys
 
 def main(argv=None):
     ap = argparse.ArgumentParser()
-    ap.add_argument("-n", type=int, default=0, help="host worker threads per GPU (0: cores / GPUs * 1.5)")
+    ap.add_argument("-n", type=int, default=0, help="host worker threads per GPU (0: 2 x cores / GPUs)")
     ap.add_argument("-o", required=True)
     ap.add_argument("-r", type=int, default=None, help="seed of the draw among equally good hits (smalt map -r)")
     ap.add_argument("--backend", default=None, help="torch.distributed backend (default nccl; gloo for tests)")
@@ -37,7 +37,7 @@ def main(argv=None):
     mine = shard_of(text, rank, world)
     cores = len(os.sched_getaffinity(0))
     opts = [] if args.r is None else ["-r", str(args.r)]
-    m = Mapper(args.index, args.n or max(1, int(1.5 * cores / world)), opts)
+    m = Mapper(args.index, args.n or max(1, int(2 * cores / world)), opts)
     header = m.sam_header() if rank == 0 else b""
     sam = m.map_fastq(mine)
     m.close()
