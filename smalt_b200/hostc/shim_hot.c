@@ -69,6 +69,7 @@ static int shim_device(void)
 }
 
 int smbShimDevice(void) { return shim_device(); }
+double smbShimNow(void) { return shim_now(); }
 
 extern void smbShimHashTableArrays(const HashTable *htp, int *typ, int *wordlen, int *nskip,
 				   int *nbits_key, int *nbits_lo, uint32_t *npos, uint32_t *nwords,

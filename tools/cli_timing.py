@@ -12,10 +12,11 @@ with tempfile.TemporaryDirectory() as tmp:
     for rep in range(2):
         t0 = time.time()
         r = subprocess.run([exe, "map", "-n", str(threads), "-O", "-o", os.path.join(tmp, "b.sam"), pref, fq], capture_output=True, text=True,
-                           env=dict(os.environ, SMALT_B200_TIMING="1", **({"SMALT_B200_BLOCK": sys.argv[3]} if len(sys.argv) > 3 else {})))
+                           env=dict(os.environ, SMALT_B200_TIMING="1", SMALT_B200_STATS=os.path.join(tmp, "st.json"), **({"SMALT_B200_BLOCK": sys.argv[3]} if len(sys.argv) > 3 else {})))
         dt = time.time() - t0
         print("cli -n %d: rc %d %.2f s %.0f reads/s" % (threads, r.returncode, dt, n / dt))
         lines = [l for l in r.stderr.splitlines() if "timing" in l]
         print("\n".join(lines[:40]))
         print("...")
         print("\n".join(lines[-6:]))
+        print(open(os.path.join(tmp, "st.json")).read())
