@@ -14,17 +14,19 @@
 //    bubbles) and the exchange is two warp shuffles per iteration (F to the right neighbour, E
 //    to the left one).  H, E, F live in registers; nothing but the direction bits leaves them;
 //  * window and read bytes of the task are staged once in shared memory; direction codes are
-//    accumulated 2 bits/cell in a register word per diagonal and stored to shared memory every
-//    16 rows ([diagonal][row/16] layout, private to this kernel);
+//    accumulated 2 bits/cell in a register word per lane and stored to shared memory every
+//    8 rows ([lane][row/8] layout, private to this kernel);
 //  * the reference's "first strict maximum in row-major order" (alignment.c:826-830) is kept
 //    exactly: every diagonal records its first strict maximum (rows ascend along a diagonal),
 //    the warp then takes the maximum score with ties broken towards the smaller (row, column);
 //  * backtrace, DiffStr reversal, result emission and the pre-order recursion are executed by
 //    lane 0 out of shared memory, exactly as in band_dp.cu.
 // Bands of at most 32 diagonals (every C1-C4 short-read task) use HALF a warp per task
-// (template LANES = 16): the two halves of a warp are independent 16-lane groups with their
-// own task, shared-memory slice, shuffle width and sync mask, which doubles the busy lanes at
-// band width ~20.  Tasks whose window/read/band exceed the staging (long reads) stay with
+// (template LANES = 16): the two halves of a warp hold one task each and run in lockstep
+// (full-warp shuffles of width 16, trip counts = maximum over the halves, a half with nothing
+// to do in a phase predicated off), which doubles the busy lanes at band width ~20.  The cell
+// update is branch free; the direction codes of a lane's two diagonals share one word
+// (4 bits per row).  Tasks whose window/read/band exceed the staging (long reads) stay with
 // band_kernel<true>.
 #include "common.cuh"
 #include "band.h"
@@ -38,7 +40,7 @@ constexpr int BWK_REV = BW_MAXROWS + BW_MAXREAD + 16;
 
 template <int LANES>
 struct WarpSmem {   // one per task group (LANES lanes, 2*LANES diagonals)
-  uint32_t dirs[2 * LANES * BWK_ROWW];
+  uint32_t dirs[LANES * (BW_MAXROWS / 8)];   // [lane][row/8]: 4 bits per row (2 per diagonal of the lane)
   uint8_t ref[BW_MAXROWS];
   uint8_t read[BW_MAXREAD];
   uint8_t rev[BWK_REV];
@@ -46,6 +48,31 @@ struct WarpSmem {   // one per task group (LANES lanes, 2*LANES diagonals)
 };
 
 #define DIFFB(count, typ) ((uint8_t)((count) + ((typ) << 6)))
+
+// One cell of the restricted recurrence (alignment.c:885-982), branch free.  `ok` = the cell
+// exists (inside the band, the read segment and the row range); a cell that does not exist
+// passes H = E = F = 0 on, exactly like the reference's zeroed row buffers.
+#define BAND_CELL(ok, diag, ein, fin, s, Hout, Eout, Fout, best, bestr, r, dcode)                 \
+  do {                                                                                             \
+    const int h_ = (diag) + (s);                                                                   \
+    const int m_ = __vimax3_s32((ein), (fin), 0);                                                  \
+    const bool dia_ = h_ > m_;                                                                     \
+    const int hn_ = max(h_, m_);                                                                   \
+    int e_ = (ein) - (((ein) > 0) ? ge : 0);                                                       \
+    int f_ = (fin) - (((fin) > 0) ? ge : 0);                                                       \
+    const bool open_ = dia_ && h_ > gi;                                                            \
+    const int t_ = open_ ? h_ - gi : (int)0x80000000;                                              \
+    e_ = max(e_, t_);                                                                              \
+    f_ = max(f_, t_);                                                                              \
+    if ((ok) && open_ && h_ > (best)) { (best) = h_; (bestr) = (r); }                              \
+    /* DIA 3, COL 1 (E >= F: whenever the maximum is positive max(E,0) >= max(F,0) <=> E >= F), */ \
+    /* ROW 2, stop 0                                                                          */ \
+    const uint32_t d_ = dia_ ? 3u : (m_ == 0 ? 0u : ((ein) >= (fin) ? 1u : 2u));                   \
+    (Hout) = (ok) ? hn_ : 0;                                                                       \
+    (Eout) = (ok) ? e_ : 0;                                                                        \
+    (Fout) = (ok) ? f_ : 0;                                                                        \
+    (dcode) = (ok) ? d_ : 0u;                                                                      \
+  } while (0)
 
 template <int LANES>
 __global__ void __launch_bounds__(BWK_WARPS * 32)
@@ -55,6 +82,8 @@ band_warp_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
                  const uint32_t *__restrict__ diff_cap) {
   constexpr int GROUPS = 32 / LANES;          // task groups per warp
   constexpr int MAXDIAG = 2 * LANES;
+  constexpr int DIRW = BW_MAXROWS / 8;
+  constexpr unsigned ALL = 0xffffffffu;
   __shared__ WarpSmem<LANES> s_w[BWK_WARPS * GROUPS];
   __shared__ unsigned long long s_S64[8];
   if (threadIdx.x < 8) {
@@ -63,9 +92,10 @@ band_warp_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
     s_S64[threadIdx.x] = v;
   }
   __syncthreads();
-  // a group is an independent LANES-wide "warp": own mask for shuffles and syncs
+  // The groups of a warp (two half-warps for LANES = 16) work in LOCKSTEP on one task each:
+  // every shuffle and vote is a full-warp operation of width LANES, loop trip counts are the
+  // maximum over the groups and a group that has nothing to do in a phase is predicated off.
   const int lane = threadIdx.x & (LANES - 1);
-  const unsigned FULL = (LANES == 32) ? 0xffffffffu : (0xffffu << (threadIdx.x & 16));
   WarpSmem<LANES> &sm = s_w[threadIdx.x / LANES];
   const int gi = sc.gap_init, ge = sc.gap_ext;
   unsigned long long ncell_tot = 0;
@@ -73,24 +103,25 @@ band_warp_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
   for (;;) {
     int k = 0;
     if (lane == 0) k = atomicAdd(ticket, 1);
-    k = __shfl_sync(FULL, k, 0, LANES);
-    if (k >= ntasks) break;
-    const int tix = __ldg(order + k);
-    const smb_band_task tk = tasks[tix];
+    k = __shfl_sync(ALL, k, 0, LANES);
+    const bool alive = k < ntasks;
+    if (!__any_sync(ALL, alive)) break;
+    const int tix = alive ? __ldg(order + k) : 0;
+    smb_band_task tk = tasks[tix];
     const bool rc = (tk.flags & SMB_TASK_READ_REVCOMP) != 0;
     const bool packed = (tk.flags & SMB_TASK_REF_PACKED) != 0;
     const int qlen = (int)tk.read_len, rlen = (int)tk.ref_len;
-    __syncwarp(FULL);
-    for (int x = lane; x < rlen; x += LANES) sm.ref[x] = (uint8_t)ref_base(src, packed, tk.ref_off, (uint32_t)x);
-    for (int x = lane; x < qlen; x += LANES)
-      sm.read[x] = (uint8_t)read_base(src.arena, tk.read_off, tk.read_len, rc, (uint32_t)x);
-    __syncwarp(FULL);
-
+    __syncwarp();
+    if (alive) {
+      for (int x = lane; x < rlen; x += LANES) sm.ref[x] = (uint8_t)ref_base(src, packed, tk.ref_off, (uint32_t)x);
+      for (int x = lane; x < qlen; x += LANES)
+        sm.read[x] = (uint8_t)read_base(src.arena, tk.read_off, tk.read_len, rc, (uint32_t)x);
+    }
     int err = SMB_OK;
     uint32_t nres = 0, diff_used = 0;
     int minscore = tk.minscore, minscorlen = tk.minscorlen;
-    uint8_t *dfinal = out.diff + diff_off[tix];
-    const uint32_t dcap = diff_cap[tix];
+    uint8_t *dfinal = out.diff + (alive ? diff_off[tix] : 0);
+    const uint32_t dcap = alive ? diff_cap[tix] : 0u;
     smb_ali_result *res = out.results + (size_t)tix * max_res;
     if (minscore < 1 || sc.match <= 0) err = SMB_ERRCODE_ASSERT;         // alignment.c:1569
     else {
@@ -98,98 +129,71 @@ band_warp_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
       if (minscorlen < 5) err = SMB_ERRCODE_ASSERT;                       // ALILEN_MIN :1574
     }
     int sp = 0;
-    if (!err) {
+    if (alive && !err) {
       if (lane == 0) { sm.stk_l[0] = tk.u_left; sm.stk_r[0] = tk.u_right; }
       sp = 1;
     }
-    while (sp > 0 && !err) {   // every variable tested here is warp-uniform
-      --sp;
-      __syncwarp(FULL);
-      const int s_left = sm.stk_l[sp], s_right = sm.stk_r[sp];
+    __syncwarp();
+
+    // one round = one DP pass of every group that still has a row range on its stack
+    while (__any_sync(ALL, alive && sp > 0 && !err)) {
+      bool on = alive && sp > 0 && !err;          // group-uniform
+      int s_left = 0, s_right = 0;
       Band b;
-      if (band_init(b, tk.l_edge, tk.r_edge, tk.p_left, tk.p_right, qlen, s_left, s_right, rlen))
-        continue;                                                          // :1333-1338
-      if (b.s_left >= b.s_len || b.band_width < 0) { err = SMB_ERRCODE_ASSERT; break; }  // :459
-      const int nrows = b.s_len - b.s_left, bw = b.band_width;
-      if (bw > MAXDIAG || nrows > BW_MAXROWS) { err = SMB_ERR_ARG; break; }  // host planner bug
+      b.band_width = 0; b.l_edge = 0; b.r_edge = 0; b.l_edge_orig = 0; b.r_edge_orig = 0;
+      b.s_left = 0; b.s_len = 0; b.q_left = 0; b.q_len = 0;
+      if (on) {
+        --sp;
+        s_left = sm.stk_l[sp];
+        s_right = sm.stk_r[sp];
+        if (band_init(b, tk.l_edge, tk.r_edge, tk.p_left, tk.p_right, qlen, s_left, s_right, rlen))
+          on = false;                                                      // :1333-1338
+        else if (b.s_left >= b.s_len || b.band_width < 0) { err = SMB_ERRCODE_ASSERT; on = false; }  // :459
+        else if (b.band_width > MAXDIAG || b.s_len - b.s_left > BW_MAXROWS) { err = SMB_ERR_ARG; on = false; }
+      }
+      const int nrows = on ? b.s_len - b.s_left : 0, bw = on ? b.band_width : 0;
 
       // ---------------- wavefront DP ----------------
       const int dA = 2 * lane, dB = dA + 1;
       const bool hasA = dA < bw, hasB = dB < bw;
       int HA = 0, HB = 0, eA = 0, eB = 0, FA = 0, FB = 0;
       int bestA = 0, bestB = 0, bestAr = 0, bestBr = 0;
-      uint32_t wA = 0, wB = 0;
+      uint32_t wdir = 0;
       unsigned ncell = 0;
-      const int nlanes = (bw + 1) >> 1;
-      const int iters = nrows + nlanes - 1;
+      int iters = on ? nrows + ((bw + 1) >> 1) - 1 : 0;
+      if (GROUPS > 1) iters = max(iters, __shfl_xor_sync(ALL, iters, 16));
+      // column of diagonal A in row r = it - lane: j = l_edge + it + lane (advances with it)
+      const int jbase = b.l_edge + lane;
+      int qnext = 0;   // read base of column jA of the next iteration (= column jB of this one)
+      {
+        const int j0 = jbase;
+        qnext = (on && j0 >= 0 && j0 < qlen) ? (int)sm.read[j0] : 0;
+      }
+      uint32_t *const dirp = sm.dirs + lane * DIRW;
       for (int it = 0; it < iters; ++it) {
         const int r = it - lane;
-        const bool rowok = r >= 0 && r < nrows;
-        const int Fin = __shfl_up_sync(FULL, FB, 1, LANES);    // F(r, dA-1) from the left neighbour's last step
-        int jA = b.l_edge + r + dA;
-        unsigned long long srow = 0;
-        if (rowok) srow = s_S64[sm.ref[b.s_left + r]];
-        // ---- diagonal A ----
-        {
-          const bool ok = rowok && hasA && jA >= b.q_left && jA < b.q_len;
-          int hn = 0, e = 0, F = 0;
-          uint32_t d = 0;
-          if (ok) {
-            const int q = sm.read[jA];
-            const int h = HA + (int)(signed char)(srow >> (q << 3));
-            e = eB;                                   // E(r-1, dA+1): own diagonal B, previous iteration
-            F = (lane == 0) ? 0 : Fin;
-            const int ep = max(e, 0), fp = max(F, 0), m = max(ep, fp);
-            const bool dia = h > m;
-            hn = dia ? h : m;
-            e -= (e > 0) ? ge : 0;
-            F -= (F > 0) ? ge : 0;
-            if (dia && h > gi) {
-              const int t = h - gi;
-              if (h > bestA) { bestA = h; bestAr = r; }
-              e = max(e, t);
-              F = max(F, t);
-            }
-            d = dia ? 3u : (m == 0 ? 0u : (ep >= fp ? 1u : 2u));
-            ++ncell;
-          }
-          HA = hn; eA = e; FA = F;
-          if (rowok && hasA) {
-            wA |= d << ((uint32_t)(r & 15) * 2u);
-            if ((r & 15) == 15 || r == nrows - 1) { sm.dirs[dA * BWK_ROWW + (r >> 4)] = wA; wA = 0; }
-          }
-        }
-        const int Ein = __shfl_down_sync(FULL, eA, 1, LANES);   // E(r-1, dB+1) from the right neighbour, this iteration
-        // ---- diagonal B ----
-        {
-          const int jB = jA + 1;
-          const bool ok = rowok && hasB && jB >= b.q_left && jB < b.q_len;
-          int hn = 0, e = 0, F = 0;
-          uint32_t d = 0;
-          if (ok) {
-            const int q = sm.read[jB];
-            const int h = HB + (int)(signed char)(srow >> (q << 3));
-            e = (lane == LANES - 1) ? 0 : Ein;
-            F = FA;                                   // F(r, dA): just computed
-            const int ep = max(e, 0), fp = max(F, 0), m = max(ep, fp);
-            const bool dia = h > m;
-            hn = dia ? h : m;
-            e -= (e > 0) ? ge : 0;
-            F -= (F > 0) ? ge : 0;
-            if (dia && h > gi) {
-              const int t = h - gi;
-              if (h > bestB) { bestB = h; bestBr = r; }
-              e = max(e, t);
-              F = max(F, t);
-            }
-            d = dia ? 3u : (m == 0 ? 0u : (ep >= fp ? 1u : 2u));
-            ++ncell;
-          }
-          HB = hn; eB = e; FB = F;
-          if (rowok && hasB) {
-            wB |= d << ((uint32_t)(r & 15) * 2u);
-            if ((r & 15) == 15 || r == nrows - 1) { sm.dirs[dB * BWK_ROWW + (r >> 4)] = wB; wB = 0; }
-          }
+        const bool rowok = on && r >= 0 && r < nrows;
+        const int Fin = __shfl_up_sync(ALL, FB, 1, LANES);     // F(r, dA-1): left neighbour's last step
+        const int jA = jbase + it, jB = jA + 1;
+        const int refc = rowok ? (int)sm.ref[b.s_left + r] : 0;
+        const unsigned long long srow = s_S64[refc];
+        const int qA = qnext;
+        const int qB = (on && jB >= 0 && jB < qlen) ? (int)sm.read[jB] : 0;
+        qnext = qB;
+        const bool okA = rowok && hasA && jA >= b.q_left && jA < b.q_len;
+        const bool okB = rowok && hasB && jB >= b.q_left && jB < b.q_len;
+        const int sA = (int)(signed char)(srow >> (qA << 3));
+        const int sB = (int)(signed char)(srow >> (qB << 3));
+        uint32_t dcA, dcB;
+        // diagonal A: E(r-1, dA+1) is this lane's diagonal B of the previous iteration
+        BAND_CELL(okA, HA, eB, (lane == 0 ? 0 : Fin), sA, HA, eA, FA, bestA, bestAr, r, dcA);
+        const int Ein = __shfl_down_sync(ALL, eA, 1, LANES);   // E(r-1, dB+1): right neighbour, this iteration
+        // diagonal B: F(r, dA) was just computed
+        BAND_CELL(okB, HB, (lane == LANES - 1 ? 0 : Ein), FA, sB, HB, eB, FB, bestB, bestBr, r, dcB);
+        ncell += (unsigned)okA + (unsigned)okB;
+        if (rowok) {
+          wdir |= (dcA | (dcB << 2)) << ((uint32_t)(r & 7) << 2);
+          if ((r & 7) == 7 || r == nrows - 1) { dirp[r >> 3] = wdir; wdir = 0; }
         }
       }
       ncell_tot += ncell;
@@ -197,30 +201,31 @@ band_warp_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
       int best = bestA, bestr = bestAr, bestd = dA;
       if (bestB > best || (bestB == best && bestB > 0 && bestBr < bestr)) { best = bestB; bestr = bestBr; bestd = dB; }
       unsigned long long key = 0;
-      if (best > 0)
+      if (on && best > 0)
         key = ((unsigned long long)(unsigned)best << 32) | ((unsigned long long)(0xffffu - (unsigned)bestr) << 16) |
               (unsigned long long)(0xffffu - (unsigned)(b.l_edge + bestr + bestd - b.q_left));
       for (int o = LANES / 2; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(FULL, key, o, LANES);
+        const unsigned long long other = __shfl_xor_sync(ALL, key, o, LANES);
         key = other > key ? other : key;
       }
       const int max_scor = (int)(key >> 32);
       const int max_r = (int)(0xffffu - (unsigned)((key >> 16) & 0xffffu));
       const int max_j = (int)(0xffffu - (unsigned)(key & 0xffffu)) + b.q_left;
       const int max_i = b.s_left + max_r;
-      __syncwarp(FULL);
-      if (max_scor < minscore) continue;                                   // :1364
+      __syncwarp();
+      if (max_scor < minscore) on = false;                                  // :1364
 
-      // ---------------- makeMetaFromTrack (alignment.c:628-781), lane 0 ----------------
-      int i = max_i, j = max_j, checksum = 0, flag = 0;
+      // ---------------- makeMetaFromTrack (alignment.c:628-781), lane 0 of the group ----------------
+      int i = max_i, j = max_j, flag = 0;
       uint32_t n = 0;
-      if (lane == 0) {
+      if (on && lane == 0) {
         bool gap_open = false, ovf = false;
         unsigned nmatch = 0;
+        int checksum = 0;
         int r = max_r, d = max_j - b.l_edge - max_r;
 #define EMIT(c, t) do { if (n < (uint32_t)BWK_REV) sm.rev[n] = DIFFB(c, t); else ovf = true; ++n; } while (0)
         while (i >= b.s_left && j >= b.q_left) {
-          const uint32_t dir = (sm.dirs[d * BWK_ROWW + (r >> 4)] >> ((uint32_t)(r & 15) * 2u)) & 3u;
+          const uint32_t dir = (sm.dirs[(d >> 1) * DIRW + (r >> 3)] >> (((uint32_t)(r & 7) << 2) + ((uint32_t)(d & 1) << 1))) & 3u;
           if (!dir) break;
           if (dir == 3u) {
             const int s = (int)(signed char)(s_S64[sm.ref[i]] >> ((int)sm.read[j] << 3));
@@ -254,68 +259,72 @@ band_warp_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
         if (ovf) flag = SMB_ERR_CAPACITY;
         else if (checksum != max_scor) flag = SMB_ERRCODE_SWATSCOR;        // :767
       }
-      flag = __shfl_sync(FULL, flag, 0, LANES);
-      if (flag) { err = flag; break; }
-      i = __shfl_sync(FULL, i, 0, LANES);
-      j = __shfl_sync(FULL, j, 0, LANES);
-      n = __shfl_sync(FULL, n, 0, LANES);
+      flag = __shfl_sync(ALL, flag, 0, LANES);
+      i = __shfl_sync(ALL, i, 0, LANES);
+      j = __shfl_sync(ALL, j, 0, LANES);
+      n = __shfl_sync(ALL, n, 0, LANES);
+      if (on && flag) { err = flag; on = false; }
       const int prof_start = j + 1, prof_end = max_j, np_start = i + 1, np_end = max_i;
-      if (prof_start + minscorlen > prof_end + 1) continue;                // :1379
-      if (max_scor >= minscore) {                                          // :1384 addALIMETAtoRsltSet
-        if ((int)nres >= max_res) { err = SMB_ERR_CAPACITY; break; }
-        int f2 = 0;
-        uint32_t u = diff_used;
-        if (lane == 0) {
-          // diffStrReverse (diffstr.c:850-896)
-          int l = (int)n - 2;
-          if (l >= 32767) f2 = SMB_ERRCODE_OVERFLOW;
-          else if ((sm.rev[l] >> 6) != 3u) f2 = SMB_ERRCODE_DIFFSTR;
-          else {
-            unsigned count_prev = sm.rev[l] & 0x3Fu;
-            bool dovf = false;
+      if (on && prof_start + minscorlen > prof_end + 1) on = false;        // :1379
+      // :1384 addALIMETAtoRsltSet (max_scor >= minscore holds here)
+      if (on && (int)nres >= max_res) { err = SMB_ERR_CAPACITY; on = false; }
+      int f2 = 0;
+      uint32_t u = diff_used;
+      if (on && lane == 0) {
+        // diffStrReverse (diffstr.c:850-896)
+        int l = (int)n - 2;
+        if (l >= 32767) f2 = SMB_ERRCODE_OVERFLOW;
+        else if ((sm.rev[l] >> 6) != 3u) f2 = SMB_ERRCODE_DIFFSTR;
+        else {
+          unsigned count_prev = sm.rev[l] & 0x3Fu;
+          bool dovf = false;
 #define PUT(v) do { if (u < dcap) dfinal[u] = (v); else dovf = true; ++u; } while (0)
-            for (--l; l >= 0; --l) {
-              const unsigned count = sm.rev[l] & 0x3Fu, typ = sm.rev[l] >> 6;
-              if (typ == 0u) {
-                count_prev = (count_prev + count + 1u) & 0xffu;
-                if (count_prev > 61u) { PUT(DIFFB(61u, 0u)); count_prev -= 62u; }
-              } else {
-                PUT(DIFFB(count_prev, typ));
-                count_prev = count;
-              }
-            }
-            PUT(DIFFB(count_prev, 3u));
-            PUT(DIFFB(0u, 0u));
-#undef PUT
-            if (dovf) f2 = SMB_ERR_CAPACITY;
-            else {
-              smb_ali_result rr;
-              rr.score = max_scor; rr.qs = prof_start; rr.qe = prof_end; rr.rs = np_start; rr.re = np_end;
-              rr.diff_off = diff_used; rr.diff_len = u - diff_used; rr.task = (uint32_t)tix;
-              res[nres] = rr;
+          for (--l; l >= 0; --l) {
+            const unsigned count = sm.rev[l] & 0x3Fu, typ = sm.rev[l] >> 6;
+            if (typ == 0u) {
+              count_prev = (count_prev + count + 1u) & 0xffu;
+              if (count_prev > 61u) { PUT(DIFFB(61u, 0u)); count_prev -= 62u; }
+            } else {
+              PUT(DIFFB(count_prev, typ));
+              count_prev = count;
             }
           }
+          PUT(DIFFB(count_prev, 3u));
+          PUT(DIFFB(0u, 0u));
+#undef PUT
+          if (dovf) f2 = SMB_ERR_CAPACITY;
+          else {
+            smb_ali_result rr;
+            rr.score = max_scor; rr.qs = prof_start; rr.qe = prof_end; rr.rs = np_start; rr.re = np_end;
+            rr.diff_off = diff_used; rr.diff_len = u - diff_used; rr.task = (uint32_t)tix;
+            res[nres] = rr;
+          }
         }
-        f2 = __shfl_sync(FULL, f2, 0, LANES);
-        if (f2) { err = f2; break; }
-        diff_used = __shfl_sync(FULL, u, 0, LANES);
-        ++nres;
       }
-      // pre-order recursion: left part first, so push right then left (:1389, :1411)
-      const bool go_left = s_left + minscorlen < np_start;
-      const bool go_right = s_right > np_end + minscorlen;
-      if (sp + 2 > BWK_STACK && (go_left || go_right)) { err = SMB_ERR_CAPACITY; break; }
-      __syncwarp(FULL);
-      if (go_right) { if (lane == 0) { sm.stk_l[sp] = np_end + 1; sm.stk_r[sp] = s_right; } ++sp; }
-      if (go_left) { if (lane == 0) { sm.stk_l[sp] = s_left; sm.stk_r[sp] = np_start - 1; } ++sp; }
+      f2 = __shfl_sync(ALL, f2, 0, LANES);
+      u = __shfl_sync(ALL, u, 0, LANES);
+      if (on && f2) { err = f2; on = false; }
+      if (on) {
+        diff_used = u;
+        ++nres;
+        // pre-order recursion: left part first, so push right then left (:1389, :1411)
+        const bool go_left = s_left + minscorlen < np_start;
+        const bool go_right = s_right > np_end + minscorlen;
+        if (sp + 2 > BWK_STACK && (go_left || go_right)) err = SMB_ERR_CAPACITY;
+        else {
+          if (go_right) { if (lane == 0) { sm.stk_l[sp] = np_end + 1; sm.stk_r[sp] = s_right; } ++sp; }
+          if (go_left) { if (lane == 0) { sm.stk_l[sp] = s_left; sm.stk_r[sp] = np_start - 1; } ++sp; }
+        }
+      }
+      __syncwarp();
     }
-    if (lane == 0) {
+    if (alive && lane == 0) {
       out.nres[tix] = nres;
       out.errs[tix] = err;
       if (out.dused) out.dused[tix] = diff_used;
     }
   }
-  for (int o = LANES / 2; o > 0; o >>= 1) ncell_tot += __shfl_down_sync(FULL, ncell_tot, o, LANES);
+  for (int o = LANES / 2; o > 0; o >>= 1) ncell_tot += __shfl_down_sync(ALL, ncell_tot, o, LANES);
   if (lane == 0 && ncell_tot) atomicAdd(out.cells, ncell_tot);
 }
 
