@@ -838,11 +838,13 @@ int smb_hits_batch(smb_ctx *ctx, const smb_hit_req *req, int nreq, uint32_t nhit
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
   const size_t n = (size_t)nreq;
-  CU(ctx->hit_meta.ensure(n * (sizeof(smb_hit_req) + 4 + 4 + 4 + 8) + 256));
+  const int ntiles = compact_tiles(nreq);
+  CU(ctx->hit_meta.ensure(n * (sizeof(smb_hit_req) + 4 + 4 + 4) + (n + 1 + (size_t)ntiles) * 8 + 512));
   char *mb = ctx->hit_meta.as<char>();
   smb_hit_req *d_req = (smb_hit_req *)mb;
-  uint64_t *d_off = (uint64_t *)(d_req + n);
-  uint32_t *d_count = (uint32_t *)(d_off + n);
+  uint64_t *d_off = (uint64_t *)(d_req + n);                 // n + 1 offsets
+  unsigned long long *d_tile = (unsigned long long *)(d_off + n + 1);
+  uint32_t *d_count = (uint32_t *)(d_tile + ntiles);
   uint32_t *d_used = d_count + n;
   int32_t *d_errs = (int32_t *)(d_used + n);
   CU(h2d(d_req, req, n * sizeof(smb_hit_req), st));
@@ -851,28 +853,25 @@ int smb_hits_batch(smb_ctx *ctx, const smb_hit_req *req, int nreq, uint32_t nhit
   ha.count = d_count; ha.maxhit_used = d_used; ha.errs = d_errs; ha.offset = d_off; ha.sqdat = nullptr;
   int nl = 0;
   float ms0 = 0.f, ms1 = 0.f;
+  // pass 1: list sizes, then their offsets by a device scan (only the offsets travel to the host)
   CU(cudaEventRecord(ctx->ev0, st));
   CU(launch_hits(ctx->ix, ha, false, st, &nl));
+  CU(launch_scan_counts(d_count, nreq, (unsigned long long *)d_off, d_tile, st, &nl));
   CU(cudaEventRecord(ctx->ev1, st));
-  std::vector<uint32_t> count(n);
-  CU(d2h(count.data(), d_count, n * 4, st));
+  CU(d2h(list_first, d_off, (n + 1) * 8, st));
   CU(d2h(errs, d_errs, n * 4, st));
   CU(ctx_sync(ctx));
   CU(cudaEventElapsedTime(&ms0, ctx->ev0, ctx->ev1));
-  std::vector<uint64_t> off(n + 1, 0);
-  for (size_t i = 0; i < n; ++i) off[i + 1] = off[i] + count[i];
-  const uint64_t total = off[n];
-  for (size_t i = 0; i <= n; ++i) list_first[i] = off[i];
+  const uint64_t total = list_first[n];
   *nhits_total = (size_t)total;
   if (total > max_hits || (total && !sqdat)) {
     ctx->last_ms = ms0;
     ctx->last_launches = nl;
     ctx->total_launches += nl;
-  g_launches += nl;
+    g_launches += nl;
     return fail(ctx, SMB_ERR_CAPACITY, "need room for %llu hits", (unsigned long long)total);
   }
   CU(ctx->hit_data.ensure((size_t)(total + 1) * 8));
-  CU(h2d(d_off, off.data(), n * 8, st));
   ha.sqdat = ctx->hit_data.as<uint64_t>();
   CU(cudaEventRecord(ctx->ev0, st));
   CU(launch_hits(ctx->ix, ha, true, st, &nl));

@@ -80,6 +80,8 @@ cudaError_t launch_compact_scan(const uint32_t *nres, const uint32_t *dused, con
                                 unsigned long long *tile_res, unsigned long long *tile_diff,
                                 CompactTotals *tot, uint32_t *first_result,
                                 unsigned long long *diff_first, cudaStream_t st, int *nlaunch);
+cudaError_t launch_scan_counts(const uint32_t *in, int n, unsigned long long *out, unsigned long long *tile,
+                               cudaStream_t st, int *nlaunch);
 cudaError_t launch_compact_gather(const smb_ali_result *slots, const uint32_t *nres, const uint8_t *diff_slots,
                                   const uint64_t *diff_off, const uint32_t *dused, int n, int max_res,
                                   const uint32_t *first_result, const unsigned long long *diff_first,

@@ -135,7 +135,78 @@ gather_results(const smb_ali_result *__restrict__ slots, const uint32_t *__restr
   for (uint32_t k = 0; k < nb; ++k) dd[k] = ds[k];
 }
 
+
 int compact_tiles(int n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+
+// ---- exclusive scan of u32 counts into u64 offsets (hit-list offsets of smb_hits_batch) ----
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan1_tiles(const uint32_t *__restrict__ in, int n, unsigned long long *__restrict__ tile) {
+  __shared__ unsigned long long sh[32];
+  const int base = blockIdx.x * SCAN_TILE;
+  unsigned long long a = 0;
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    const int i = base + k * SCAN_THREADS + threadIdx.x;
+    if (i < n) a += in[i];
+  }
+  a = block_sum(a, sh);
+  if (threadIdx.x == 0) tile[blockIdx.x] = a;
+}
+
+__global__ void scan1_top(unsigned long long *tile, int ntiles) {
+  const int lane = threadIdx.x;
+  unsigned long long carry = 0;
+  for (int base = 0; base < ntiles; base += 32) {
+    const int i = base + lane;
+    const unsigned long long a = (i < ntiles) ? tile[i] : 0ull;
+    unsigned long long ia = a;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, ia, o);
+      if (lane >= o) ia += t;
+    }
+    if (i < ntiles) tile[i] = carry + ia - a;
+    carry += __shfl_sync(0xffffffffu, ia, 31);
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan1_apply(const uint32_t *__restrict__ in, int n, const unsigned long long *__restrict__ tile,
+            unsigned long long *__restrict__ out) {
+  __shared__ unsigned long long sa[SCAN_THREADS];
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  unsigned long long a = 0;
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0u;
+    a += v[k];
+  }
+  sa[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 1; o < SCAN_THREADS; o <<= 1) {
+    unsigned long long t = 0;
+    if ((int)threadIdx.x >= o) t = sa[threadIdx.x - o];
+    __syncthreads();
+    sa[threadIdx.x] += t;
+    __syncthreads();
+  }
+  unsigned long long o = tile[blockIdx.x] + sa[threadIdx.x] - a;
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) out[base + k] = o;
+    o += v[k];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) out[n] = o;
+}
+
+// out has n + 1 entries (out[n] = total); tile: compact_tiles(n) scratch words
+cudaError_t launch_scan_counts(const uint32_t *in, int n, unsigned long long *out, unsigned long long *tile,
+                               cudaStream_t st, int *nlaunch) {
+  const int ntiles = compact_tiles(n);
+  scan1_tiles<<<ntiles, SCAN_THREADS, 0, st>>>(in, n, tile);
+  scan1_top<<<1, 32, 0, st>>>(tile, ntiles);
+  scan1_apply<<<ntiles, SCAN_THREADS, 0, st>>>(in, n, tile, out);
+  *nlaunch += 3;
+  return cudaGetLastError();
+}
+
 
 cudaError_t launch_compact_scan(const uint32_t *nres, const uint32_t *dused, const int32_t *errs, int n,
                                 unsigned long long *tile_res, unsigned long long *tile_diff,

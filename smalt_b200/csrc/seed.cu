@@ -687,10 +687,38 @@ __device__ void sort_u64(uint64_t *a, int n) {
   }
 }
 
+// ------------------------------------------------------------------------------------
+// hits_warp_kernel: ONE WARP PER REQUEST (read x strand x reference segment).  The lanes take
+// the seeds of the request in parallel (position-range search of each seed is independent),
+// list offsets come from a warp prefix sum, and the final ascending sort of the (unique)
+// packed hits is a bitonic sort in shared memory.  The reference's sequential overflow
+// handling (list longer than nhits_alloc: halve the per-seed cut-off and retry,
+// hashhit.c:1730-1741) cannot trigger when even the sum over ALL seeds of the hits at or
+// beyond the segment start fits nhits_alloc - the test that selects this path; otherwise
+// lane 0 runs the sequential code (hits_segment_pass): COUNT resolves the halving of the
+// per-seed cut-off, FILL replays the failed attempts (they mark MULTIHIT seeds in the read's
+// qmask as a side effect) and the final one.
+// ------------------------------------------------------------------------------------
+constexpr int HITW_WARPS = 4;
+constexpr int HITW_SORTCAP = 512;   // hits sorted in shared memory (larger lists: heapsort by lane 0)
+
+__device__ __forceinline__ uint32_t upper_bound_pos(const uint32_t *p, uint32_t n, uint32_t from, uint32_t v) {
+  uint32_t a = from, b = n;   // first index >= from with p[index] >= v
+  while (a < b) {
+    const uint32_t m = (a + b) >> 1;
+    if (__ldg(p + m) < v) a = m + 1; else b = m;
+  }
+  return a;
+}
+
 template <bool FILL>
-__global__ void __launch_bounds__(128) hits_kernel(const Index ix, const HitArgs a) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(HITW_WARPS * 32) hits_warp_kernel(const Index ix, const HitArgs a) {
+  __shared__ unsigned long long s_sort[HITW_WARPS][HITW_SORTCAP];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * HITW_WARPS + (threadIdx.x >> 5);
   if (g >= a.nreq) return;
+  unsigned long long *srt = s_sort[threadIdx.x >> 5];
   const smb_hit_req rq = a.req[g];
   const uint32_t rd = rq.read;
   const uint32_t qlen = a.seed.read_len[rd];
@@ -698,52 +726,140 @@ __global__ void __launch_bounds__(128) hits_kernel(const Index ix, const HitArgs
   const smb_seed_info inf = a.seed.info[2 * rd + (rq.strand ? 1 : 0)];
   uint64_t lo = rq.lo / (uint64_t)ix.nskip, hi = rq.hi / (uint64_t)ix.nskip;
   if (inf.err || lo > 0xFFFFFFFFull) {
-    if (!FILL) { a.count[g] = 0; a.maxhit_used[g] = 0; a.errs[g] = inf.err ? inf.err : SMB_ERRCODE_ARGRANGE; }
+    if (!FILL && lane == 0) { a.count[g] = 0; a.maxhit_used[g] = 0; a.errs[g] = inf.err ? inf.err : SMB_ERRCODE_ARGRANGE; }
     return;
   }
   if (hi > 0xFFFFFFFFull) hi = 0xFFFFFFFFull;
+  const uint32_t pos_lo = (uint32_t)lo, pos_hi = (uint32_t)hi;
+  const uint32_t *posidx = a.seed.posidx + slot, *qoffs = a.seed.qoffs + slot;
+  const uint32_t *sortkey = a.seed.sortkey + slot, *sidx = a.seed.sidx + slot;
+  uint8_t *qmask = a.seed.qmask + slot;
+  const bool use_short = rq.use_short != 0;
+  const uint32_t n_seeds = (use_short && inf.seed_rank > 0) ? inf.seed_rank : inf.n_seeds;
+  const bool is_reverse = rq.strand != 0;
+  const uint32_t maxhit = rq.nhit_max;
+  constexpr uint32_t FASTFLAG = 0x80000000u;
+
+  bool fast;
   if (!FILL) {
-    uint32_t maxhit = rq.nhit_max, total = 0, used = 0;
-    int err;
-    do {  // hashCollectHitsForSegment retry loop (hashhit.c:1730-1741)
-      used = maxhit;
-      err = hits_segment_pass<false>(ix, a, rq, slot, inf.n_seeds, inf.seed_rank, maxhit, (uint32_t)lo,
-                                     (uint32_t)hi, nullptr, total);
-      maxhit /= 2;
-    } while (err == SMB_ERRCODE_ALLOCBOUNDARY && maxhit > 16u);  // MINHIT_PER_TUPLE
-    // if the last attempt still overflowed the reference keeps what that attempt collected
-    // before the overflow; reproduce by counting that partial pass
-    if (err == SMB_ERRCODE_ALLOCBOUNDARY) {
-      a.errs[g] = SMB_ERRCODE_ALLOCBOUNDARY;
-    } else {
-      a.errs[g] = 0;
-    }
-    a.count[g] = total;
-    a.maxhit_used[g] = used;
-  } else {
-    uint64_t *out = a.sqdat + a.offset[g];
+    // can the sequential overflow logic trigger at all?  bound: hits at or beyond the segment start
+    unsigned long long bound = 0;
     uint32_t total = 0;
-    // earlier (failed) attempts of the retry loop marked MULTIHIT seeds in the read's qmask
-    // as a side effect; replay them so the mask ends up identical
-    uint32_t maxhit = rq.nhit_max;
-    const uint32_t used = a.maxhit_used[g];
-    while (maxhit != used && maxhit > 16u) {
-      uint32_t t2 = 0;
-      hits_segment_pass<true>(ix, a, rq, slot, inf.n_seeds, inf.seed_rank, maxhit, (uint32_t)lo, (uint32_t)hi,
-                              out, t2);
-      maxhit /= 2;
+    for (uint32_t n = lane; n < n_seeds; n += 32) {
+      if (maxhit > 0 && sortkey[n] > maxhit) continue;
+      const uint32_t sd = use_short ? sidx[n] : n;
+      const uint32_t *posp;
+      const uint32_t nhits = fetch_positions(ix, posidx[sd], posp);
+      if (!posp || nhits == 0) continue;
+      const uint32_t first = lower_bound_pos(posp, nhits, pos_lo);
+      bound += nhits - first;
+      total += upper_bound_pos(posp, nhits, first, pos_hi) - first;
     }
-    hits_segment_pass<true>(ix, a, rq, slot, inf.n_seeds, inf.seed_rank, used, (uint32_t)lo, (uint32_t)hi, out,
-                            total);
-    sort_u64(out, (int)a.count[g]);
+    for (int o = 16; o > 0; o >>= 1) {
+      bound += __shfl_xor_sync(FULL, bound, o);
+      total += __shfl_xor_sync(FULL, total, o);
+    }
+    fast = bound <= (unsigned long long)a.nhits_alloc;
+    if (fast) {
+      if (lane == 0) { a.count[g] = total; a.maxhit_used[g] = maxhit | FASTFLAG; a.errs[g] = 0; }
+      return;
+    }
+    if (lane == 0) {   // sequential path: hashCollectHitsForSegment retry loop (hashhit.c:1730-1741)
+      uint32_t mh = maxhit, tot = 0, used = 0;
+      int err;
+      do {
+        used = mh;
+        err = hits_segment_pass<false>(ix, a, rq, slot, inf.n_seeds, inf.seed_rank, mh, pos_lo, pos_hi, nullptr, tot);
+        mh /= 2;
+      } while (err == SMB_ERRCODE_ALLOCBOUNDARY && mh > 16u);
+      a.errs[g] = (err == SMB_ERRCODE_ALLOCBOUNDARY) ? SMB_ERRCODE_ALLOCBOUNDARY : 0;
+      a.count[g] = tot;
+      a.maxhit_used[g] = used & ~FASTFLAG;
+    }
+    return;
   }
+
+  // ---- FILL ----
+  const uint32_t usedflag = a.maxhit_used[g];
+  uint64_t *out = a.sqdat + a.offset[g];
+  const int count = (int)a.count[g];
+  fast = (usedflag & FASTFLAG) != 0;
+  if (!fast) {
+    if (lane == 0) {   // sequential path
+      uint32_t mh = maxhit, total = 0;
+      const uint32_t used = usedflag;
+      while (mh != used && mh > 16u) {
+        uint32_t t2 = 0;
+        hits_segment_pass<true>(ix, a, rq, slot, inf.n_seeds, inf.seed_rank, mh, pos_lo, pos_hi, out, t2);
+        mh /= 2;
+      }
+      hits_segment_pass<true>(ix, a, rq, slot, inf.n_seeds, inf.seed_rank, used, pos_lo, pos_hi, out, total);
+      sort_u64(out, count);
+    }
+    return;
+  }
+  const bool in_smem = count <= HITW_SORTCAP;
+  uint32_t base = 0;
+  for (uint32_t n0 = 0; n0 < n_seeds; n0 += 32) {
+    const uint32_t n = n0 + lane;
+    uint32_t cnt = 0, first = 0, q = 0;
+    const uint32_t *posp = nullptr;
+    if (n < n_seeds) {
+      const uint32_t sd = use_short ? sidx[n] : n;
+      q = qoffs[sd];
+      if (maxhit > 0 && sortkey[n] > maxhit) {
+        qmask[q] = HQ_MULTIHIT;
+      } else {
+        const uint32_t nhits = fetch_positions(ix, posidx[sd], posp);
+        if (posp && nhits) {
+          first = lower_bound_pos(posp, nhits, pos_lo);
+          cnt = upper_bound_pos(posp, nhits, first, pos_hi) - first;
+        }
+      }
+    }
+    uint32_t incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const uint32_t off = base + incl - cnt;
+    for (uint32_t i = 0; i < cnt; ++i) {
+      const unsigned long long h = pack_hit(is_reverse, __ldg(posp + first + i), q, (uint32_t)ix.nskip);
+      if (in_smem) srt[off + i] = h; else out[off + i] = h;
+    }
+    base += __shfl_sync(FULL, incl, 31);
+  }
+  __syncwarp();
+  if (!in_smem) {
+    if (lane == 0) sort_u64(out, count);
+    return;
+  }
+  // bitonic sort of `count` keys padded to a power of two
+  int np2 = 1;
+  while (np2 < count) np2 <<= 1;
+  for (int i = count + lane; i < np2; i += 32) srt[i] = ~0ull;
+  __syncwarp();
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = lane; i < np2; i += 32) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long x = srt[i], y = srt[l];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { srt[i] = y; srt[l] = x; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < count; i += 32) out[i] = srt[i];
 }
 
 cudaError_t launch_hits(const Index &ix, const HitArgs &a, bool fill, cudaStream_t st, int *nlaunch) {
   if (a.nreq <= 0) return cudaSuccess;
-  const int grid = (a.nreq + 127) / 128;
-  if (fill) hits_kernel<true><<<grid, 128, 0, st>>>(ix, a);
-  else hits_kernel<false><<<grid, 128, 0, st>>>(ix, a);
+  const int grid = (a.nreq + HITW_WARPS - 1) / HITW_WARPS;
+  if (fill) hits_warp_kernel<true><<<grid, HITW_WARPS * 32, 0, st>>>(ix, a);
+  else hits_warp_kernel<false><<<grid, HITW_WARPS * 32, 0, st>>>(ix, a);
   ++*nlaunch;
   return cudaGetLastError();
 }
@@ -752,8 +868,8 @@ cudaError_t warm_seed() {
   cudaFuncAttributes a;
   cudaError_t e = cudaFuncGetAttributes(&a, seed_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, seed_warp_kernel);
-  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, hits_kernel<true>);
-  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, hits_kernel<false>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, hits_warp_kernel<true>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, hits_warp_kernel<false>);
   return e;
 }
 
