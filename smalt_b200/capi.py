@@ -72,7 +72,7 @@ def load_library():
     if not os.path.exists(p):
         raise ImportError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "or `make -C smalt_b200/csrc` (no CPU fallback exists)" % p)
-    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(p)
     lib.smb_version.restype = C.c_char_p
     lib.smb_last_error.restype = C.c_char_p
     lib.smb_last_error.argtypes = [C.c_void_p]

@@ -42,7 +42,7 @@ def load_map_library():
     if not os.path.exists(p):
         raise ImportError("%s not built: `make -C smalt_b200/hostc` needs the reference tree; on the GPU box "
                           "the prebuilt library travels with the repo snapshot" % p)
-    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(p)
     lib.smbm_open.argtypes = [C.POINTER(C.c_void_p), C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_char_p)]
     lib.smbm_map_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p),
                                    C.POINTER(C.c_size_t), C.POINTER(MapStats)]
