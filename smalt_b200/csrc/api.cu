@@ -149,7 +149,7 @@ int smb_device_warmup(int device) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return SMB_ERR_NODEVICE;
   if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) return SMB_ERR_CUDA;
-  if (warm_sw() != cudaSuccess || warm_band() != cudaSuccess || warm_band_warp() != cudaSuccess ||
+  if (warm_sw() != cudaSuccess || warm_band() != cudaSuccess || warm_band_warp() != cudaSuccess || warm_band_pack() != cudaSuccess ||
       warm_seed() != cudaSuccess ||
       warm_compact() != cudaSuccess)
     return SMB_ERR_CUDA;
@@ -367,7 +367,7 @@ int smb_band_score_batch(smb_ctx *ctx, const smb_band_task *tasks, int ntasks, i
   BandOut bo{nullptr, nullptr, nullptr, d_errs, d_cells, nullptr};
   int nl = 0;
   BandPlan plan;
-  plan_band(tasks, ntasks, false, plan);
+  plan_band(tasks, ntasks, false, ctx->sc, plan);
   const size_t gring_words = band_gring_words(plan);
   CU(ctx->scratch.ensure((size_t)ntasks * sizeof(int) + gring_words * sizeof(uint32_t) + 512));
   int *d_order = ctx->scratch.as<int>();
@@ -438,7 +438,7 @@ static int band_align_pass(smb_ctx *ctx, const smb_band_task *tasks, const std::
   CU(cudaMemsetAsync(d_cells, 0, sizeof(unsigned long long), st));
   BandOut bo{d_res, d_nres, ctx->diff.as<uint8_t>(), d_errs, d_cells, nullptr};
   BandPlan plan;
-  plan_band(sub.data(), n, true, plan);
+  plan_band(sub.data(), n, true, ctx->sc, plan);
   const size_t gring_words = band_gring_words(plan);
   CU(ctx->scratch.ensure((size_t)n * sizeof(int) + gring_words * sizeof(uint32_t) + 512));
   int *d_order = ctx->scratch.as<int>();
@@ -504,7 +504,7 @@ static int band_align_fast(smb_ctx *ctx, const smb_band_task *tasks, int ntasks,
   }
   if (dir_off[n] > ((uint64_t)1 << 30)) return 1;  // long-read sized batch: chunked multi-pass path
   BandPlan plan;
-  plan_band(tasks, n, true, plan);
+  plan_band(tasks, n, true, ctx->sc, plan);
   memcpy(h_order, plan.order.data(), (size_t)n * sizeof(int));
 
   const size_t res_bytes = (size_t)n * max_res * sizeof(smb_ali_result);

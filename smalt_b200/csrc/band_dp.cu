@@ -32,6 +32,7 @@
 #include "common.cuh"
 #include "band.h"
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace smb {
@@ -322,18 +323,26 @@ static int pow2_at_least(int v) {
 // Host-side plan: tasks bucketed by ring capacity (one launch per class), input order kept
 // inside a class (neighbouring tasks come from the same read / candidate list and have
 // similar geometry, so the threads of a warp stay balanced without a full sort).
-void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, BandPlan &plan) {
+void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, const Scoring &sc, BandPlan &plan) {
   plan.order.resize((size_t)ntasks);
   plan.classes.clear();
   std::vector<int> wc((size_t)ntasks);
   int count[32] = {0};
   auto cls = [](int wcap) { int c = 0; while ((32 << c) < wcap) ++c; return c; };
-  constexpr int WARP_CLS = 31, HALF_CLS = 30;  // pseudo classes of the warp / half-warp kernels (last in `order`)
+  constexpr int WARP_CLS = 31, HALF_CLS = 30, PACK_CLS = 29;  // pseudo classes of the warp kernels (last in `order`)
+  // packed 16-bit kernel: scores must stay far below 2^15 (band_pack.cu)
+  const bool pen16 = sc.match > 0 && sc.match < 128 && sc.mismatch <= 0 && sc.mismatch > -128 && sc.gap_init >= 0 &&
+                     sc.gap_init < 4000 && sc.gap_ext >= 0 && sc.gap_ext < 4000 && sc.S[5] == 0 && sc.S[5 * 8] == 0 &&
+                     !getenv("SMB_NO_PACK");
+  plan.pack_maxrows = 0;
   for (int i = 0; i < ntasks; ++i) {
     const smb_band_task &t = h_tasks[i];
     const int wl = align ? band_warp_lanes(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left,
                                            t.u_right, (int)t.ref_len) : 0;
-    if (wl) {
+    if (wl == 16 && pen16 && (long long)t.read_len * sc.match <= 12000) {
+      wc[(size_t)i] = PACK_CLS;
+      plan.pack_maxrows = std::max(plan.pack_maxrows, (int)t.ref_len);
+    } else if (wl) {
       wc[(size_t)i] = wl == 16 ? HALF_CLS : WARP_CLS;
     } else {
       const int need = ring_need(t, !align);
@@ -347,8 +356,10 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, BandPlan &p
   int fill[32];
   for (int c = 0; c < 32; ++c) fill[c] = start[c];
   for (int i = 0; i < ntasks; ++i) plan.order[(size_t)fill[wc[(size_t)i]]++] = i;
-  for (int c = 0; c < HALF_CLS; ++c)
+  for (int c = 0; c < PACK_CLS; ++c)
     if (count[c]) plan.classes.push_back(BandPlan::Class{32 << c, start[c], count[c]});
+  plan.pack_start = start[PACK_CLS];
+  plan.pack_count = count[PACK_CLS];
   plan.half_start = start[HALF_CLS];
   plan.half_count = count[HALF_CLS];
   plan.warp_start = start[WARP_CLS];
@@ -385,6 +396,10 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++*nlaunch;
   }
+  if (align && plan.pack_count &&
+      (e = launch_band_pack(sc, src, d_tasks, d_order + plan.pack_start, plan.pack_count, plan.pack_maxrows, d_ticket + 2,
+                            out, max_res, d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)
+    return e;
   if (align && plan.half_count &&
       (e = launch_band_warp(sc, src, d_tasks, d_order + plan.half_start, plan.half_count, 16, d_ticket, out, max_res,
                             d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)

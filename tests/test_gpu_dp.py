@@ -241,3 +241,50 @@ def _run_records(ctx, recs):
             for i, r in enumerate(sel):
                 assert int(errs[i]) == r["err"]
                 assert _unpack(res, first, diff, i) == r["results"], i
+
+
+def test_band_align_packed_kernel_geometry(ctx, orc):
+    """Geometries at the limits of the four-tasks-per-warp kernel (band_pack.cu): window lengths
+    around multiples of 32 up to 256 rows, bands of 1..32 diagonals, very different task sizes
+    paired in one half-warp, odd task counts and batches of one."""
+    rng = np.random.default_rng(105)
+    pairs, args = [], []
+    for rows in (31, 32, 33, 63, 64, 65, 159, 160, 161, 191, 192, 193, 223, 224, 255, 256):
+        for bw in (1, 2, 7, 16, 19, 31, 32):
+            qlen = int(rng.integers(20, min(rows, 250) + 1))
+            rd = random_seq(rng, qlen)
+            off = int(rng.integers(0, max(1, rows - qlen)))
+            win = random_seq(rng, rows)
+            from seqgen import mutate
+            m = mutate(rng, rd.copy(), p_sub=0.03, p_ins=0.01, p_del=0.01)[:rows - off]
+            win[off:off + len(m)] = m
+            if (rows + bw) % 5 == 0:
+                win[int(rng.integers(0, rows))] = 5
+                rd[int(rng.integers(0, qlen))] = 5
+            if (rows + bw) % 11 == 0:
+                win[int(rng.integers(0, rows))] = 4
+            pairs.append((rd, win))
+            l = -off - bw // 2
+            args.append((l, l + bw - 1, 0, qlen - 1, 0, rows - 1))
+    order = rng.permutation(len(pairs))          # unlike sizes next to each other
+    pairs = [pairs[i] for i in order]
+    args = [args[i] for i in order]
+    minscore = [int(x) for x in rng.integers(1, 25, len(pairs))]
+    minscorlen = [int(x) for x in rng.integers(5, 20, len(pairs))]
+    arena, offs = _arena(pairs)
+    ctx.arena_upload(arena)
+    for sel in (slice(None), slice(0, 1), slice(1, 4), slice(0, len(pairs) - 1)):
+        idx = list(range(len(pairs)))[sel]
+        sub_pairs = [pairs[i] for i in idx]
+        sub_offs = np.concatenate([[offs[2 * i], offs[2 * i + 1]] for i in idx] + [[0]])
+        t = _band_tasks(sub_pairs, sub_offs, [args[i] for i in idx], [minscore[i] for i in idx],
+                        [minscorlen[i] for i in idx])
+        res, first, diff, errs, cells = ctx.band_align(t)
+        ocells = 0
+        for k, i in enumerate(idx):
+            rd, win = pairs[i]
+            e, want, c = orc.band_align(rd, win, *args[i], minscore[i], minscorlen[i])
+            ocells += c
+            assert int(errs[k]) == e, (i, args[i])
+            assert _unpack(res, first, diff, k) == want, (i, len(rd), len(win), args[i], minscore[i], minscorlen[i])
+        assert cells == ocells
