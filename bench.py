@@ -42,9 +42,10 @@ GENOME_LEN = 5_000_000
 READ_LEN = 150
 K, NSKIP = 13, 6
 ERR = 0.02
-# algorithmic integer operations per DP cell ("rooflines")
-K2_OPS_PER_CELL = 7.5
-K3_OPS_PER_CELL = 20.0
+# integer instructions per DP cell of the recurrences as restated for two 16-bit lanes per
+# register ("rooflines"): K2 8 per cell pair, K3 30 per cell pair
+K2_OPS_PER_CELL = 4.0
+K3_OPS_PER_CELL = 15.0
 
 
 def make_genome(seed=2, n=GENOME_LEN):
@@ -325,10 +326,11 @@ def main():
     k2_gcups = s1["k2_cells"] / (s1["k2_ms"] * 1e-3) / 1e9
     k3_gcups = s1["k3_cells"] / (s1["k3_ms"] * 1e-3) / 1e9
     ctx = Context(local)
-    peaks = ctx.int_peak()          # giga thread-ops/s: VIADDMNMX, VIMNMX3, IADD+IMNMX
+    # giga thread-instructions/s: VIADDMNMX, VIMNMX3, IADD+IMNMX pairs (ops), VIADDMNMX.S16x2, VIMNMX3.S16x2
+    peaks = ctx.int_peak()
     ctx.close()
-    k2_peak = peaks[0] / K2_OPS_PER_CELL
-    k3_peak = peaks[2] / K3_OPS_PER_CELL
+    k2_peak = peaks[3] / K2_OPS_PER_CELL
+    k3_peak = peaks[3] / K3_OPS_PER_CELL
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         peak_src = "MEASURED_PEAKS.json"
@@ -341,14 +343,16 @@ def main():
     k1_bytes = nlook * (8 + 4 * np.ceil(np.log2(bucket + 1)) + 8)
     k1_gbs = k1_bytes / (s1["k1_ms"] * 1e-3) / 1e9
     kernel_ms = {"k1_seed_hits": s1["k1_ms"], "k2_sw_score": s1["k2_ms"], "k3_band_align": s1["k3_ms"]}
-    roof_k3 = {"kernel": "band_kernel<true> (K3: banded DP + backtrace)", "bound": "alu", "achieved": k3_gcups,
-               "peak": k3_peak, "unit": "GCUPS", "frac": k3_gcups / k3_peak if k3_peak else None, "traffic": None,
-               "note": "integer-issue bound (no tensor/HBM bound applies to this DP): peak = measured IADD+IMNMX "
-                       "rate %.0f Gop/s / %.1f algorithmic ops per cell" % (peaks[2], K3_OPS_PER_CELL)}
-    roof_k2 = {"kernel": "sw_score_kernel (K2: SW score)", "bound": "alu", "achieved": k2_gcups, "peak": k2_peak,
-               "unit": "GCUPS", "frac": k2_gcups / k2_peak if k2_peak else None, "traffic": None,
-               "note": "DPX issue bound: peak = measured VIADDMNMX rate %.0f Gop/s / %.1f ops per cell"
-                       % (peaks[0], K2_OPS_PER_CELL)}
+    roof_k3 = {"kernel": "band_pack_kernel (K3: banded DP + backtrace, 4 tasks per warp)", "bound": "alu",
+               "achieved": k3_gcups, "peak": k3_peak, "unit": "GCUPS", "frac": k3_gcups / k3_peak if k3_peak else None,
+               "traffic": None,
+               "note": "integer-issue bound (no tensor/HBM bound applies to this DP): peak = measured VIADDMNMX.S16x2 "
+                       "issue rate %.0f G thread-instr/s / %.1f instructions per cell (30 per packed cell pair); "
+                       "cells include the serial backtrace time" % (peaks[3], K3_OPS_PER_CELL)}
+    roof_k2 = {"kernel": "sw_score2_kernel (K2: SW score, 2 tasks per warp)", "bound": "alu", "achieved": k2_gcups,
+               "peak": k2_peak, "unit": "GCUPS", "frac": k2_gcups / k2_peak if k2_peak else None, "traffic": None,
+               "note": "DPX issue bound: peak = measured VIADDMNMX.S16x2 issue rate %.0f G thread-instr/s / %.1f "
+                       "instructions per cell (8 per packed cell pair)" % (peaks[3], K2_OPS_PER_CELL)}
     roof_k1 = {"kernel": "seed_kernel + hits_kernel (K1)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak,
                "unit": "GB/s", "frac": k1_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                "note": "dependent 4-byte index probes (latency bound); the 5 Mb index (11 MB) is L2 resident"}
@@ -356,7 +360,7 @@ def main():
     line = {
         "metric": "mapped reads/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": wall_ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "i32 DPX (K2), i16x2 (K3), u32/u64 (K1)", "data": "synthetic",
+        "vs_baseline": None, "dtype": "i16x2 DPX (K2, K3), u32/u64 (K1)", "data": "synthetic",
         "config": dict(workload_config(n, world), host_workers_per_gpu=threads, host_cores=cores),
         "timing": "value: reads / sum of CUDA-event kernel times of a step (one host worker, inputs resident); "
                   "e2e: wall clock of smbm_map_fastq (FASTQ text in host memory -> SAM text in host memory), "
@@ -368,7 +372,9 @@ def main():
                 "ms_per_step": wall_ms, "sam_bytes_per_step": int(sam_bytes),
                 "host_stage_wall_s": c1["host_stage_s"], "host_stage_cpu_s": c1["host_cpu_s"]},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": roof_k3 if dominant == "k3_band_align" else roof_k2,
+        "int_peaks_ginstr": {"viaddmnmx": peaks[0], "vimnmx3": peaks[1], "iadd_imnmx_ops": peaks[2],
+                             "viaddmnmx_s16x2": peaks[3], "vimnmx3_s16x2": peaks[4]},
+        "roofline": {"k3_band_align": roof_k3, "k2_sw_score": roof_k2, "k1_seed_hits": roof_k1}[dominant],
         "roofline_k2": roof_k2, "roofline_k3": roof_k3, "roofline_k1": roof_k1,
         "mapped_fraction": mapped / max(total, 1),
     }
