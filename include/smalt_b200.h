@@ -224,12 +224,16 @@ int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_
  * what collectHits (rmap.c:283-318) asks hashCollectHitsForSegment for with
  * lo = soffs[s], hi = soffs[s+1], nhit_max = ktuple_maxhit, use_short = 1. */
 typedef struct {
-  uint64_t lo, hi;
+  uint64_t lo, hi;       /* segment [lo, hi) in bases of the concatenated set (ignored for mode 2) */
   uint32_t read;
-  uint32_t nhit_max;
+  uint32_t nhit_max;     /* per-seed cut-off (ktuple_maxhit) */
   uint8_t strand;
-  uint8_t use_short;
-  uint8_t reserved[6];
+  uint8_t use_short;     /* 1: ranked seeds, 0: all seeds unsorted (hashCollectHitsForSegment);
+			    2: whole set with cut-off = hashCollectHitsUsingCutoff (hashhit.c:1593-1689),
+			       the path of rmap.c:320-346 for >= 512 reference sequences */
+  uint8_t reserved[2];
+  uint32_t nhits_max;    /* mode 2: HashHitList.nhits_max of this read, qlen*ln(qlen)*32 clamped to
+			    [8192, INT_MAX] (hashhit.c:1266-1288; 0 = let the library derive it) */
 } smb_hit_req;
 
 /* Builds and sorts the requested hit lists (HashHitList.sqdat, hashhit.c:215-236:
@@ -242,6 +246,12 @@ typedef struct {
 int smb_hits_batch(smb_ctx *ctx, const smb_hit_req *req, int nreq, uint32_t nhits_alloc,
 		   uint64_t *sqdat, size_t max_hits, size_t *nhits_total,
 		   uint64_t *list_first, int32_t *errs);
+
+/* The HITQUAL masks (hashhit.h:57-65) of the hit lists built by the last smb_hits_batch, one
+ * byte per read offset: list i at qmask[qmask_first[i] .. qmask_first[i+1]) (read_len bytes).
+ * Only mode-2 lists mark NORMHIT / MULTIHIT seeds (hashhit.c:1632-1650); segment lists are all
+ * HITQUAL_NOHIT like the reference's.  segLstFillHits (segment.c:782-788) consumes the mask. */
+int smb_hits_qmask(smb_ctx *ctx, uint8_t *qmask, size_t max_bytes, uint64_t *qmask_first);
 
 #ifdef __cplusplus
 }

@@ -47,7 +47,7 @@ SEED_INFO_DTYPE = np.dtype([("n_seeds", "<u4"), ("seed_rank", "<u4"), ("cover_de
                             ("nhit_rank", "<u4"), ("nhit_tot", "<u4"), ("nhit_all", "<u4"),
                             ("status", "<u4"), ("err", "<i4")])
 HIT_REQ_DTYPE = np.dtype([("lo", "<u8"), ("hi", "<u8"), ("read", "<u4"), ("nhit_max", "<u4"),
-                          ("strand", "u1"), ("use_short", "u1"), ("reserved", "u1", (6,))])
+                          ("strand", "u1"), ("use_short", "u1"), ("reserved", "u1", (2,)), ("nhits_max", "<u4")])
 ALI_RESULT_DTYPE = np.dtype([("score", "<i4"), ("qs", "<i4"), ("qe", "<i4"), ("rs", "<i4"),
                              ("re", "<i4"), ("diff_off", "<u4"), ("diff_len", "<u4"),
                              ("task", "<u4")])
@@ -99,6 +99,7 @@ def load_library():
                                    C.c_uint32, C.c_int, C.c_int] + [C.c_void_p] * 7
     lib.smb_hits_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_size_t,
                                    C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p]
+    lib.smb_hits_qmask.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     _lib = lib
     return lib
 
@@ -212,6 +213,13 @@ class Context:
                 continue
             self._check(rc)
             return sq[:tot.value], first, errs
+
+    def hits_qmask(self, nreq, nbytes):
+        """HITQUAL masks of the lists of the last hits_batch -> (qmask bytes, first[nreq+1])"""
+        qm = np.zeros(max(1, nbytes), np.uint8)
+        first = np.zeros(nreq + 1, np.uint64)
+        self._check(self.lib.smb_hits_qmask(self._h, _vp(qm), nbytes, _vp(first)))
+        return qm[:int(first[nreq])], first
 
     def sw_score(self, tasks):
         tasks = np.ascontiguousarray(tasks, SW_TASK_DTYPE)

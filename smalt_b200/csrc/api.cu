@@ -77,7 +77,10 @@ struct smb_ctx {
   int seed_nreads = 0;
   SeedArgs seed_args{};
   uint32_t seed_maxlen = 0;
-  DevBuf hit_meta, hit_data;
+  DevBuf hit_meta, hit_data, hit_qmask;
+  std::vector<uint32_t> seed_len;      // host copy of the read lengths of the last smb_seed_batch
+  std::vector<uint64_t> hit_qmask_first;  // per request of the last smb_hits_batch
+  bool hit_qmask_valid = false;
   uint64_t seed_slots = 0;
   size_t arena_bytes = 0;
   std::vector<uint64_t> seq_offs;
@@ -189,7 +192,7 @@ void smb_ctx_destroy(smb_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf *bufs[] = {&ctx->arena, &ctx->packed, &ctx->tasks, &ctx->out_a, &ctx->out_b,
                     &ctx->scratch, &ctx->dirs, &ctx->diff, &ctx->offs, &ctx->index, &ctx->qualbuf,
-                    &ctx->seed_meta, &ctx->seed_u32, &ctx->seed_u8, &ctx->hit_meta, &ctx->hit_data, &ctx->cmp, &ctx->ticket};
+                    &ctx->seed_meta, &ctx->seed_u32, &ctx->seed_u8, &ctx->hit_meta, &ctx->hit_data, &ctx->cmp, &ctx->ticket, &ctx->hit_qmask};
   for (DevBuf *b : bufs) b->release();
   ctx->stage.release();
   if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
@@ -803,6 +806,7 @@ int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_
   CU(ctx_sync(ctx));
   CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
   ctx->seed_nreads = nreads;
+  ctx->seed_len.assign(read_len, read_len + nreads);
   ctx->seed_args = a;
   ctx->seed_maxlen = 0;
   for (int i = 0; i < nreads; ++i) if (read_len[i] > ctx->seed_maxlen) ctx->seed_maxlen = read_len[i];
@@ -839,6 +843,18 @@ int smb_hits_batch(smb_ctx *ctx, const smb_hit_req *req, int nreq, uint32_t nhit
   cudaStream_t st = ctx->stream;
   const size_t n = (size_t)nreq;
   const int ntiles = compact_tiles(nreq);
+  // list masks (HITQUAL per read offset) are produced when a whole-set (mode 2) list is asked for
+  bool want_qmask = false;
+  for (int i = 0; i < nreq && !want_qmask; ++i) want_qmask = req[i].use_short == 2;
+  ctx->hit_qmask_valid = false;
+  uint64_t *d_qoff = nullptr;
+  if (want_qmask) {
+    ctx->hit_qmask_first.assign(n + 1, 0);
+    for (size_t i = 0; i < n; ++i) ctx->hit_qmask_first[i + 1] = ctx->hit_qmask_first[i] + ctx->seed_len[req[i].read];
+    CU(ctx->hit_qmask.ensure(ctx->hit_qmask_first[n] + (n + 1) * 8 + 64));
+    d_qoff = (uint64_t *)(ctx->hit_qmask.as<char>() + ((ctx->hit_qmask_first[n] + 15) & ~(uint64_t)15));
+    CU(h2d(d_qoff, ctx->hit_qmask_first.data(), (n + 1) * 8, ctx->stream));
+  }
   CU(ctx->hit_meta.ensure(n * (sizeof(smb_hit_req) + 4 + 4 + 4) + (n + 1 + (size_t)ntiles) * 8 + 512));
   char *mb = ctx->hit_meta.as<char>();
   smb_hit_req *d_req = (smb_hit_req *)mb;
@@ -851,6 +867,8 @@ int smb_hits_batch(smb_ctx *ctx, const smb_hit_req *req, int nreq, uint32_t nhit
   HitArgs ha{};
   ha.seed = ctx->seed_args; ha.req = d_req; ha.nreq = nreq; ha.nhits_alloc = nhits_alloc;
   ha.count = d_count; ha.maxhit_used = d_used; ha.errs = d_errs; ha.offset = d_off; ha.sqdat = nullptr;
+  ha.list_qmask = want_qmask ? ctx->hit_qmask.as<uint8_t>() : nullptr;
+  ha.qmask_off = d_qoff;
   int nl = 0;
   float ms0 = 0.f, ms1 = 0.f;
   // pass 1: list sizes, then their offsets by a device scan (only the offsets travel to the host)
@@ -883,6 +901,19 @@ int smb_hits_batch(smb_ctx *ctx, const smb_hit_req *req, int nreq, uint32_t nhit
   ctx->last_launches = nl;
   ctx->total_launches += nl;
   g_launches += nl;
+  ctx->hit_qmask_valid = want_qmask;
+  return SMB_OK;
+}
+
+int smb_hits_qmask(smb_ctx *ctx, uint8_t *qmask, size_t max_bytes, uint64_t *qmask_first) {
+  if (!ctx || !qmask_first) return SMB_ERR_ARG;
+  if (!ctx->hit_qmask_valid) return fail(ctx, SMB_ERR_STATE, "no whole-set (mode 2) hit lists in the last smb_hits_batch");
+  const size_t n = ctx->hit_qmask_first.size() - 1, total = (size_t)ctx->hit_qmask_first[n];
+  memcpy(qmask_first, ctx->hit_qmask_first.data(), (n + 1) * 8);
+  if (total > max_bytes || (total && !qmask)) return fail(ctx, SMB_ERR_CAPACITY, "need %zu mask bytes", total);
+  cudaSetDevice(ctx->device);
+  if (total) CU(d2h(qmask, ctx->hit_qmask.p, total, ctx->stream));
+  CU(ctx_sync(ctx));
   return SMB_OK;
 }
 

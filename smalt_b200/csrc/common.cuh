@@ -147,6 +147,8 @@ struct HitArgs {
   int32_t *errs;              // [nreq]
   const uint64_t *offset;     // [nreq] start of each list in sqdat (FILL pass)
   uint64_t *sqdat;
+  uint8_t *list_qmask;        // HITQUAL mask of every list (read_len bytes each) or nullptr
+  const uint64_t *qmask_off;  // [nreq] start of each list's mask
 };
 cudaError_t launch_hits(const Index &ix, const HitArgs &a, bool fill, cudaStream_t st, int *nlaunch);
 

@@ -740,6 +740,117 @@ __global__ void __launch_bounds__(HITW_WARPS * 32) hits_warp_kernel(const Index 
   const uint32_t maxhit = rq.nhit_max;
   constexpr uint32_t FASTFLAG = 0x80000000u;
 
+  if (rq.use_short == 2) {   // hashCollectHitsUsingCutoff (hashhit.c:1593-1689): whole set, rank order
+    const uint32_t ns = inf.seed_rank ? inf.seed_rank : inf.n_seeds;
+    uint32_t nhits_max = rq.nhits_max;
+    if (!nhits_max) {
+      double t = qlen > 1 ? (double)qlen * log((double)qlen) * 32.0 : 0.0;
+      nhits_max = t > 2147483647.0 ? 2147483647u : (t < 8192.0 ? 8192u : (uint32_t)t);
+    }
+    uint8_t *lq = a.list_qmask ? a.list_qmask + a.qmask_off[g] : nullptr;
+    if (!FILL) {
+      unsigned long long tot = 0;
+      for (uint32_t n = lane; n < ns; n += 32) {
+        const uint32_t nh = sortkey[n];
+        if (nh >= 1 && !(maxhit > 0 && nh > maxhit)) tot += nh;
+      }
+      for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+      if (tot <= (unsigned long long)nhits_max) {   // the ceiling cannot be reached: first attempt, every seed
+        if (lane == 0) { a.count[g] = (uint32_t)tot; a.maxhit_used[g] = maxhit | FASTFLAG; a.errs[g] = 0; }
+        return;
+      }
+      if (lane == 0) {   // the reference's retry loop: halve the cut-off while the ceiling is hit
+        uint32_t mh = maxhit, used, nh_tot;
+        bool ceiling;
+        do {
+          ceiling = false;
+          used = mh;
+          nh_tot = 0;
+          for (uint32_t n = 0; n < ns; ++n) {
+            const uint32_t nh = sortkey[n];
+            if (nh < 1) continue;
+            if (mh > 0 && nh > mh) continue;
+            if (nh_tot + nh > nhits_max) { ceiling = true; break; }
+            nh_tot += nh;
+          }
+          mh /= 2;
+        } while (ceiling && mh > 16u);   // MINHIT_PER_TUPLE
+        a.count[g] = nh_tot;
+        a.maxhit_used[g] = used & ~FASTFLAG;
+        a.errs[g] = 0;
+      }
+      return;
+    }
+    // FILL: the final attempt (cut-off a.maxhit_used), seeds in rank order up to the ceiling
+    const uint32_t usedflag = a.maxhit_used[g];
+    const uint32_t mh = usedflag & ~FASTFLAG;
+    uint64_t *out = a.sqdat + a.offset[g];
+    const uint32_t count = a.count[g];
+    if (lq) for (uint32_t q = lane; q < qlen; q += 32) lq[q] = HQ_NOHIT;
+    __syncwarp();
+    uint32_t base = 0;
+    bool stop = false;
+    for (uint32_t n0 = 0; n0 < ns && !stop; n0 += 32) {
+      const uint32_t n = n0 + lane;
+      uint32_t nh = 0, q = 0, sd = 0;
+      bool multi = false;
+      if (n < ns) {
+        nh = sortkey[n];
+        sd = sidx[n];
+        q = qoffs[sd];
+        if (nh >= 1 && mh > 0 && nh > mh) { multi = true; nh = 0; }
+      }
+      uint32_t incl = nh;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+      }
+      // ceiling: the first seed whose hits would not fit ends the list (nothing after it is looked at)
+      const bool over = nh > 0 && base + incl > nhits_max;
+      const unsigned overm = __ballot_sync(FULL, over);
+      const int firstover = overm ? __ffs(overm) - 1 : 32;
+      if (lane < firstover) {
+        if (multi) { if (lq) lq[q] = HQ_MULTIHIT; }
+        else if (nh > 0) {
+          const uint32_t *posp;
+          const uint32_t nhits = fetch_positions(ix, posidx[sd], posp);
+          const uint32_t off = base + incl - nh;
+          if (lq) lq[q] = HQ_NORMHIT;
+          for (uint32_t i = 0; i < nh && i < nhits && off + i < count; ++i)
+            out[off + i] = pack_hit(is_reverse, __ldg(posp + i), q, (uint32_t)ix.nskip);
+        }
+      }
+      if (overm) stop = true;
+      base += __shfl_sync(FULL, incl, 31);
+    }
+    __syncwarp();
+    if (count <= (uint32_t)HITW_SORTCAP) {
+      for (uint32_t i = lane; i < count; i += 32) srt[i] = out[i];
+      int np2 = 1;
+      while (np2 < (int)count) np2 <<= 1;
+      for (int i = (int)count + lane; i < np2; i += 32) srt[i] = ~0ull;
+      __syncwarp();
+      for (int k = 2; k <= np2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = lane; i < np2; i += 32) {
+            const int l = i ^ j;
+            if (l > i) {
+              const unsigned long long x = srt[i], y = srt[l];
+              const bool up = (i & k) == 0;
+              if ((x > y) == up) { srt[i] = y; srt[l] = x; }
+            }
+          }
+          __syncwarp();
+        }
+      for (uint32_t i = lane; i < count; i += 32) out[i] = srt[i];
+    } else if (lane == 0) {
+      sort_u64(out, (int)count);
+    }
+    return;
+  }
+  if (FILL && a.list_qmask)   // segment lists never mark seeds: all NOHIT (hashhit.c:1224-1231)
+    for (uint32_t q = lane; q < qlen; q += 32) a.list_qmask[a.qmask_off[g] + q] = HQ_NOHIT;
+
   bool fast;
   if (!FILL) {
     // can the sequential overflow logic trigger at all?  bound: hits at or beyond the segment start

@@ -124,3 +124,51 @@ def test_hits_batch_vs_oracle(ctx, k, nskip, kind):
                 orc.lib.so_hitinfo_delete(h)
         if kind == "repeat" and nhit_max == 0:
             assert big > 10000
+
+
+@pytest.mark.parametrize("kind", ["multi", "repeat"])
+def test_hits_cutoff_vs_oracle(ctx, kind):
+    """whole-set hit lists (mode 2 = hashCollectHitsUsingCutoff, the path for >= 512 reference
+    sequences): packed hits, the list's HITQUAL mask, the ceiling / halving retry"""
+    from smalt_b200.capi import HIT_REQ_DTYPE, pack_sequences
+    rng = np.random.default_rng(3000 + len(kind))
+    unit = None
+    if kind == "multi":
+        seqs = make_genome(rng, [30011, 20007, 999])
+    else:
+        seqs, unit = _repeat_genome(rng)
+    k, nskip = 11, 3
+    ix = indexer.as_loaded(indexer.build_index(seqs, k, nskip))
+    orc = Oracle()
+    oix = orc.make_index(ix)
+    ctx.index_upload(ix)
+    reads = [sample_read(rng, seqs, int(rng.integers(40, 200))) for _ in range(120)]
+    if unit is not None:
+        reads += [np.ascontiguousarray(unit[i:i + 150]) for i in range(0, 200, 20)]
+    arena, offs = pack_sequences(reads)
+    lens_r = np.array([len(r) for r in reads], np.uint32)
+    ctx.arena_upload(arena)
+    for nhit_max in (10000, 40, 0):
+        info, tabs = ctx.seed_batch(offs[:-1], lens_r, None, 10000, 16384, 0)
+        req = np.zeros(len(reads) * 2, HIT_REQ_DTYPE)
+        req["read"] = np.repeat(np.arange(len(reads), dtype=np.uint32), 2)
+        req["strand"] = np.tile(np.array([0, 1], np.uint8), len(reads))
+        req["nhit_max"], req["use_short"] = nhit_max, 2
+        sq, first, errs = ctx.hits_batch(req)
+        qm, qfirst = ctx.hits_qmask(len(req), int(2 * lens_r.sum()))
+        n, big = 0, 0
+        for r, rd in enumerate(reads):
+            for s in (0, 1):
+                e, _, h = orc.hitinfo(oix, rd, None, s, 1, 10000, 16384, 0)
+                if e == 0:
+                    e2, want, wantmask, hl = orc.hitlist_cutoff(oix, h, nhit_max)
+                    assert e2 == 0 and int(errs[n]) == 0
+                    got = sq[int(first[n]):int(first[n + 1])]
+                    assert np.array_equal(got, want), (r, s, nhit_max, len(got), len(want))
+                    assert np.array_equal(qm[int(qfirst[n]):int(qfirst[n + 1])], wantmask), (r, s, nhit_max)
+                    big = max(big, len(want))
+                    orc.lib.so_hitlist_delete(hl)
+                orc.lib.so_hitinfo_delete(h)
+                n += 1
+        if kind == "repeat" and nhit_max == 0:
+            assert big > 5000
