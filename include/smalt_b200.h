@@ -218,6 +218,24 @@ int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_
 		   smb_seed_info *info, uint32_t *seed_posidx, uint32_t *seed_nhits,
 		   uint32_t *seed_qoffs, uint32_t *sortkey, uint32_t *sidx, uint8_t *qmask);
 
+/* Seed tables against per-read SMALL indexes: the reference builds a k=5, s=1 perfect-hash
+ * table on the fly from the insert-size intervals around a mapped mate (setupFineHashTable,
+ * rmap.c:495-517: hashTableSetUp with an InterVal, hashidx.c:549-575, :829-998) and collects
+ * the seeds of the other mate in it (initRMAPINFO on rmp->htflyp, rmap.c:2026-2030).  One such
+ * table exists per pair, so a batch carries `ntables` tables (HASHIDXTYP_PERFECT only: idx has
+ * 4^wordlen + 1 entries, pos has npos; all tables share wordlen and nskip) and read_table[r]
+ * names the table of read r.  Reads are addressed in the arena like in smb_seed_batch; the
+ * seed tables stay on the device for smb_hits_batch, which then reads the per-read tables. */
+typedef struct {
+  const uint32_t *idx;
+  const uint32_t *pos;
+  uint32_t npos;
+} smb_small_index;
+int smb_seed_batch_tables(smb_ctx *ctx, int wordlen, int nskip, const smb_small_index *tables, int ntables,
+			  const uint32_t *read_table, const uint64_t *read_off, const uint32_t *read_len, int nreads,
+			  const uint8_t *qual, uint32_t maxhit_per_tuple, uint32_t maxhit_total, int basq_thresh,
+			  int short_info, smb_seed_info *info);
+
 /* One hit list to build from the seed tables left on the device by the last
  * smb_seed_batch: the hits of read `read`, strand `strand`, that fall into the
  * reference segment [lo, hi) given as base offsets in the concatenated set -

@@ -77,7 +77,8 @@ struct smb_ctx {
   int seed_nreads = 0;
   SeedArgs seed_args{};
   uint32_t seed_maxlen = 0;
-  DevBuf hit_meta, hit_data, hit_qmask;
+  DevBuf hit_meta, hit_data, hit_qmask, aux_index;
+  Index seed_ix{};                     // index (template) of the last seed batch: what smb_hits_batch reads
   std::vector<uint32_t> seed_len;      // host copy of the read lengths of the last smb_seed_batch
   std::vector<uint64_t> hit_qmask_first;  // per request of the last smb_hits_batch
   bool hit_qmask_valid = false;
@@ -192,7 +193,7 @@ void smb_ctx_destroy(smb_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf *bufs[] = {&ctx->arena, &ctx->packed, &ctx->tasks, &ctx->out_a, &ctx->out_b,
                     &ctx->scratch, &ctx->dirs, &ctx->diff, &ctx->offs, &ctx->index, &ctx->qualbuf,
-                    &ctx->seed_meta, &ctx->seed_u32, &ctx->seed_u8, &ctx->hit_meta, &ctx->hit_data, &ctx->cmp, &ctx->ticket, &ctx->hit_qmask};
+                    &ctx->seed_meta, &ctx->seed_u32, &ctx->seed_u8, &ctx->hit_meta, &ctx->hit_data, &ctx->cmp, &ctx->ticket, &ctx->hit_qmask, &ctx->aux_index};
   for (DevBuf *b : bufs) b->release();
   ctx->stage.release();
   if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
@@ -743,15 +744,16 @@ int smb_index_upload(smb_ctx *ctx, int typ, int wordlen, int nskip, int nbits_ke
   return SMB_OK;
 }
 
-int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_len, int nreads,
-                   const uint8_t *qual, uint32_t maxhit_per_tuple, uint32_t maxhit_total, int basq_thresh,
-                   int short_info, smb_seed_info *info, uint32_t *seed_posidx, uint32_t *seed_nhits, uint32_t *seed_qoffs,
-                   uint32_t *sortkey, uint32_t *sidx, uint8_t *qmask) {
+static int seed_batch_impl(smb_ctx *ctx, const Index &ixt, const IndexTab *d_tab, const uint32_t *read_tab,
+                           const uint64_t *read_off, const uint32_t *read_len, int nreads,
+                           const uint8_t *qual, uint32_t maxhit_per_tuple, uint32_t maxhit_total, int basq_thresh,
+                           int short_info, smb_seed_info *info, uint32_t *seed_posidx, uint32_t *seed_nhits, uint32_t *seed_qoffs,
+                           uint32_t *sortkey, uint32_t *sidx, uint8_t *qmask) {
   if (!ctx || nreads < 0 || (nreads && (!read_off || !read_len || !info))) return SMB_ERR_ARG;
   ctx->last_ms = 0.f;
   ctx->last_launches = 0;
   if (!nreads) return SMB_OK;
-  if (!ctx->have_index) return fail(ctx, SMB_ERR_STATE, "smb_index_upload() first");
+  if (!d_tab && !ctx->have_index) return fail(ctx, SMB_ERR_STATE, "smb_index_upload() first");
   if (!ctx->src.arena) return fail(ctx, SMB_ERR_STATE, "smb_arena_upload() first");
   if (basq_thresh < 0 || basq_thresh + 0x21 > 255) return fail(ctx, 67 /* ERRCODE_QUALVAL */, "quality threshold");
   std::vector<uint64_t> slot((size_t)nreads + 1, 0);
@@ -763,7 +765,7 @@ int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_
   const uint64_t nslots = slot[(size_t)nreads];
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
-  const size_t meta_bytes = (size_t)nreads * (8 + 4 + 8) + (size_t)2 * nreads * sizeof(smb_seed_info) + 256;
+  const size_t meta_bytes = (size_t)nreads * (8 + 4 + 8 + 4) + (size_t)2 * nreads * sizeof(smb_seed_info) + 256;
   CU(ctx->seed_meta.ensure(meta_bytes));
   CU(ctx->seed_u32.ensure((size_t)(nslots + 64) * 6 * sizeof(uint32_t)));
   CU(ctx->seed_u8.ensure((size_t)(nslots + 64) * 2));
@@ -772,6 +774,8 @@ int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_
   uint64_t *d_slot = d_off + nreads;
   smb_seed_info *d_info = (smb_seed_info *)(d_slot + nreads);
   uint32_t *d_len = (uint32_t *)(d_info + 2 * (size_t)nreads);
+  uint32_t *d_rtab = d_len + nreads;
+  if (d_tab) CU(h2d(d_rtab, read_tab, (size_t)nreads * 4, st));
   CU(h2d(d_off, read_off, (size_t)nreads * 8, st));
   CU(h2d(d_slot, slot.data(), (size_t)nreads * 8, st));
   CU(h2d(d_len, read_len, (size_t)nreads * 4, st));
@@ -785,6 +789,7 @@ int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_
   uint32_t *u = ctx->seed_u32.as<uint32_t>();
   uint8_t *b = ctx->seed_u8.as<uint8_t>();
   SeedArgs a{};
+  a.tab = d_tab; a.read_tab = d_tab ? d_rtab : nullptr;
   a.read_off = d_off; a.read_len = d_len; a.slot_off = d_slot; a.qual = d_qual; a.nreads = nreads;
   a.maxhit_per_tuple = maxhit_per_tuple; a.maxhit_total = maxhit_total; a.basq_thresh = basq_thresh;
   a.is_short = short_info ? 1 : 0;
@@ -795,7 +800,7 @@ int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_
   a.qmask = b; a.qbuf = b + S;
   int nl = 0;
   CU(cudaEventRecord(ctx->ev0, st));
-  CU(launch_seed(ctx->ix, ctx->src.arena, a, st, &nl));
+  CU(launch_seed(ixt, ctx->src.arena, a, st, &nl));
   CU(cudaEventRecord(ctx->ev1, st));
   CU(d2h(info, d_info, (size_t)2 * nreads * sizeof(smb_seed_info), st));
   struct { uint32_t *h; uint32_t *d; } cp[] = {{seed_posidx, a.posidx}, {seed_nhits, a.nhits}, {seed_qoffs, a.qoffs},
@@ -808,6 +813,7 @@ int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_
   ctx->seed_nreads = nreads;
   ctx->seed_len.assign(read_len, read_len + nreads);
   ctx->seed_args = a;
+  ctx->seed_ix = ixt;
   ctx->seed_maxlen = 0;
   for (int i = 0; i < nreads; ++i) if (read_len[i] > ctx->seed_maxlen) ctx->seed_maxlen = read_len[i];
   ctx->seed_slots = nslots;
@@ -815,6 +821,57 @@ int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_
   ctx->total_launches += nl;
   g_launches += nl;
   return SMB_OK;
+}
+
+int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_len, int nreads,
+                   const uint8_t *qual, uint32_t maxhit_per_tuple, uint32_t maxhit_total, int basq_thresh,
+                   int short_info, smb_seed_info *info, uint32_t *seed_posidx, uint32_t *seed_nhits, uint32_t *seed_qoffs,
+                   uint32_t *sortkey, uint32_t *sidx, uint8_t *qmask) {
+  if (!ctx) return SMB_ERR_ARG;
+  return seed_batch_impl(ctx, ctx->ix, nullptr, nullptr, read_off, read_len, nreads, qual, maxhit_per_tuple, maxhit_total,
+                         basq_thresh, short_info, info, seed_posidx, seed_nhits, seed_qoffs, sortkey, sidx, qmask);
+}
+
+int smb_seed_batch_tables(smb_ctx *ctx, int wordlen, int nskip, const smb_small_index *tables, int ntables,
+                          const uint32_t *read_table, const uint64_t *read_off, const uint32_t *read_len, int nreads,
+                          const uint8_t *qual, uint32_t maxhit_per_tuple, uint32_t maxhit_total, int basq_thresh,
+                          int short_info, smb_seed_info *info) {
+  if (!ctx || ntables < 0 || nreads < 0 || (nreads && (!tables || !read_table || ntables < 1))) return SMB_ERR_ARG;
+  if (wordlen < 1 || wordlen > 12 || nskip < 1 || nskip > 32)
+    return fail(ctx, SMB_ERR_ARG, "small index parameters out of range (k=%d nskip=%d)", wordlen, nskip);
+  ctx->last_ms = 0.f;
+  ctx->last_launches = 0;
+  if (!nreads) return SMB_OK;
+  for (int i = 0; i < nreads; ++i)
+    if (read_table[i] >= (uint32_t)ntables) return fail(ctx, SMB_ERR_ARG, "read %d: table %u out of range", i, read_table[i]);
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  const size_t nkeys = (size_t)1 << (2 * wordlen), n_idx = nkeys + 1;
+  auto al = [](size_t n) { return (n + 63) & ~(size_t)63; };
+  size_t words = al((size_t)ntables * sizeof(IndexTab) / 4 + 16);
+  std::vector<size_t> off((size_t)ntables);
+  for (int t = 0; t < ntables; ++t) {
+    if (!tables[t].idx || (tables[t].npos && !tables[t].pos)) return SMB_ERR_ARG;
+    off[(size_t)t] = words;
+    words += al(n_idx) + al((size_t)tables[t].npos + 1);
+  }
+  CU(ctx->aux_index.ensure(words * sizeof(uint32_t)));
+  uint32_t *base = ctx->aux_index.as<uint32_t>();
+  std::vector<IndexTab> tab((size_t)ntables);
+  for (int t = 0; t < ntables; ++t) {
+    uint32_t *d_idx = base + off[(size_t)t], *d_pos = d_idx + al(n_idx);
+    CU(h2d(d_idx, tables[t].idx, n_idx * 4, st));
+    if (tables[t].npos) CU(h2d(d_pos, tables[t].pos, (size_t)tables[t].npos * 4, st));
+    tab[(size_t)t] = IndexTab{d_idx, d_pos, tables[t].npos, 0};
+  }
+  CU(h2d(base, tab.data(), (size_t)ntables * sizeof(IndexTab), st));
+  CU(ctx_sync(ctx));   // the host vectors above go out of scope
+  Index ixt{};
+  ixt.typ = 0; ixt.wordlen = wordlen; ixt.nskip = nskip;
+  ixt.wordmask = (1ull << (2 * wordlen)) - 1ull;
+  ixt.nkeys = (uint32_t)nkeys;
+  return seed_batch_impl(ctx, ixt, (const IndexTab *)base, read_table, read_off, read_len, nreads, qual, maxhit_per_tuple,
+                         maxhit_total, basq_thresh, short_info, info, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
 int smb_hits_batch(smb_ctx *ctx, const smb_hit_req *req, int nreq, uint32_t nhits_alloc, uint64_t *sqdat,
@@ -873,7 +930,7 @@ int smb_hits_batch(smb_ctx *ctx, const smb_hit_req *req, int nreq, uint32_t nhit
   float ms0 = 0.f, ms1 = 0.f;
   // pass 1: list sizes, then their offsets by a device scan (only the offsets travel to the host)
   CU(cudaEventRecord(ctx->ev0, st));
-  CU(launch_hits(ctx->ix, ha, false, st, &nl));
+  CU(launch_hits(ctx->seed_ix, ha, false, st, &nl));
   CU(launch_scan_counts(d_count, nreq, (unsigned long long *)d_off, d_tile, st, &nl));
   CU(cudaEventRecord(ctx->ev1, st));
   CU(d2h(list_first, d_off, (n + 1) * 8, st));
@@ -892,7 +949,7 @@ int smb_hits_batch(smb_ctx *ctx, const smb_hit_req *req, int nreq, uint32_t nhit
   CU(ctx->hit_data.ensure((size_t)(total + 1) * 8));
   ha.sqdat = ctx->hit_data.as<uint64_t>();
   CU(cudaEventRecord(ctx->ev0, st));
-  CU(launch_hits(ctx->ix, ha, true, st, &nl));
+  CU(launch_hits(ctx->seed_ix, ha, true, st, &nl));
   CU(cudaEventRecord(ctx->ev1, st));
   if (total) CU(d2h(sqdat, ha.sqdat, (size_t)total * 8, st));
   CU(ctx_sync(ctx));

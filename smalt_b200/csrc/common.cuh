@@ -123,7 +123,16 @@ struct Index {
   const uint32_t *idx, *pos, *wordidx, *posidx;
 };
 
+// per-read tables of a multi-table seed batch (smb_seed_batch_tables): perfect-hash indexes that
+// share word length and sampling step and differ in their arrays only
+struct IndexTab {
+  const uint32_t *idx, *pos;
+  uint32_t npos, reserved;
+};
+
 struct SeedArgs {
+  const IndexTab *tab;        // nullptr: every read uses the kernel's Index argument
+  const uint32_t *read_tab;   // [nreads] table of each read
   const uint64_t *read_off;   // [nreads] arena offsets
   const uint32_t *read_len;   // [nreads]
   const uint64_t *slot_off;   // [nreads] first slot of the read (forward strand); reverse at +read_len

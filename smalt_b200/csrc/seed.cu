@@ -121,10 +121,12 @@ enum { HQ_TERM = 0, HQ_NORMHIT = 1, HQ_MULTIHIT = 2, HQ_REPEAT = 3, HQ_NOHIT = 4
 enum { HI_REVERSE = 1, HI_SORTED = 2, HI_RANK = 4 };
 
 __global__ void __launch_bounds__(128)
-seed_kernel(const Index ix, const uint8_t *__restrict__ arena, const SeedArgs a) {
+seed_kernel(const Index ix0, const uint8_t *__restrict__ arena, const SeedArgs a) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= 2 * a.nreads) return;
   const int rd = g >> 1, is_reverse = g & 1;
+  Index ix = ix0;
+  if (a.tab) { const IndexTab t = a.tab[a.read_tab[rd]]; ix.idx = t.idx; ix.pos = t.pos; ix.npos = t.npos; }
   const uint32_t qlen = a.read_len[rd];
   const uint8_t *read = arena + a.read_off[rd];
   const uint8_t *qual = a.qual ? a.qual + a.read_off[rd] : nullptr;
@@ -315,7 +317,7 @@ struct SeedWarpLayout {   // per-warp shared memory carve-up for reads of at mos
 };
 
 __global__ void __launch_bounds__(SEEDW_WARPS * 32)
-seed_warp_kernel(const Index ix, const uint8_t *__restrict__ arena, const SeedArgs a, const SeedWarpLayout lay) {
+seed_warp_kernel(const Index ix0, const uint8_t *__restrict__ arena, const SeedArgs a, const SeedWarpLayout lay) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -333,6 +335,8 @@ seed_warp_kernel(const Index ix, const uint8_t *__restrict__ arena, const SeedAr
   uint8_t *s_qmask = base + lay.qmask_off();
 
   const int rd = g >> 1, is_reverse = g & 1;
+  Index ix = ix0;
+  if (a.tab) { const IndexTab t = a.tab[a.read_tab[rd]]; ix.idx = t.idx; ix.pos = t.pos; ix.npos = t.npos; }
   const uint32_t qlen = a.read_len[rd];
   const uint8_t *read = arena + a.read_off[rd];
   const uint8_t *qual = a.qual ? a.qual + a.read_off[rd] : nullptr;
@@ -712,7 +716,7 @@ __device__ __forceinline__ uint32_t upper_bound_pos(const uint32_t *p, uint32_t 
 }
 
 template <bool FILL>
-__global__ void __launch_bounds__(HITW_WARPS * 32) hits_warp_kernel(const Index ix, const HitArgs a) {
+__global__ void __launch_bounds__(HITW_WARPS * 32) hits_warp_kernel(const Index ix0, const HitArgs a) {
   __shared__ unsigned long long s_sort[HITW_WARPS][HITW_SORTCAP];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -721,6 +725,8 @@ __global__ void __launch_bounds__(HITW_WARPS * 32) hits_warp_kernel(const Index 
   unsigned long long *srt = s_sort[threadIdx.x >> 5];
   const smb_hit_req rq = a.req[g];
   const uint32_t rd = rq.read;
+  Index ix = ix0;
+  if (a.seed.tab) { const IndexTab t = a.seed.tab[a.seed.read_tab[rd]]; ix.idx = t.idx; ix.pos = t.pos; ix.npos = t.npos; }
   const uint32_t qlen = a.seed.read_len[rd];
   const uint64_t slot = a.seed.slot_off[rd] + (rq.strand ? qlen : 0u);
   const smb_seed_info inf = a.seed.info[2 * rd + (rq.strand ? 1 : 0)];

@@ -47,6 +47,21 @@ typedef struct {
   uint8_t simd;
 } WCAND;
 
+/* one mapSingleRead pass (rmap.c:1228-1433) of one read of the block */
+typedef struct {
+  uint32_t read;         /* index of the read in the block (arena) */
+  uint32_t seed_read;    /* index of the read in the seed batch that is on the device */
+  uint32_t min_cover;
+  int min_swatscor;      /* absolute score threshold argument */
+  SeqFastq *readp;
+  ResultSet *rsp;        /* results are ADDED to this set */
+  int niv;               /* < 0: unrestricted search; else number of intervals (rmap.c:438-493) */
+  uint32_t iv_first;     /* first interval in RmapWave.iv */
+  uint8_t blank;         /* blank rsp first (rmapSingle) */
+} WJOB;
+typedef struct { uint64_t lo, hi; int32_t sx; } WIVAL;   /* [lo, hi) in bases of the concatenated set */
+typedef int (WAVE_DONEF)(void *user, int job, int errcode, ResultSet *rsp);
+
 typedef struct {
   uint32_t qlen;
   int errcode;           /* error that ends the mapping of this read */
@@ -60,9 +75,19 @@ typedef struct {
   int min_swatscor, scorlen_min, bandwidth_min;
 } WREAD;
 
+/* paired mode (rmapPairWave): what is kept of a pair between the passes */
+struct PairState_ {
+  ResultSet *rs[2];      /* [0] results of the read, [1] of its mate */
+  unsigned char status, rare_mate;
+  RSLTPAIRFLG_t pairflg;
+  int mapq1, swscor1, swscor2_restricted, n_proper, swscor1_2ndbest;
+  unsigned char stage;   /* PST_* */
+};
+enum { PST_END = 0, PST_SECOND_UNRESTRICTED = 3, PST_RESCUE_MAIN = 4, PST_RESCUE_FINE = 5 };
+
 /* page-locked staging buffers (smb_host_alloc): what crosses the C ABI is copied by DMA */
 typedef struct { void *p; size_t cap; } WBUF;
-enum { WB_ARENA, WB_QUAL, WB_READ_OFF, WB_READ_LEN, WB_INFO, WB_REQ, WB_LIST_FIRST, WB_REQ_ERR, WB_SQDAT,
+enum { WB_ARENA, WB_QUAL, WB_READ_OFF, WB_READ_LEN, WB_INFO, WB_INFO4, WB_REQ, WB_LIST_FIRST, WB_REQ_ERR, WB_SQDAT,
        WB_SWT, WB_SW_SCORE, WB_SW_ERR, WB_BFT, WB_BF_SCORE, WB_BF_ERR, WB_BAT, WB_BA_ERR, WB_RES,
        WB_RES_FIRST, WB_DIFF, WB_COUNT };
 
@@ -97,6 +122,25 @@ struct RmapWave_ {
   size_t res_alloc, diff_alloc;
   ScoreProfile *prof, *profRC;
   SeqFastq *readRC;
+  WJOB *jobs, *pjob;
+  size_t jobs_alloc, pjob_alloc;
+  uint64_t n_pairs_pass3, n_pairs_pass4;
+  WIVAL *iv;
+  size_t iv_alloc, niv;
+  int nreads;            /* reads of the seed batch on the device */
+  int any_qual;
+  smb_seed_info *info4;  /* seed tables against the on-the-fly indexes (pass 4) */
+  uint32_t *ftab;        /* arrays of the on-the-fly indexes of a block: idx[nkeys+1], pos[npos] each */
+  size_t ftab_alloc, nftab;
+  smb_small_index *ftabs;
+  size_t *ftab_off;
+  uint32_t *ftab_read;
+  uint64_t *f_off;
+  uint32_t *f_len;
+  size_t ftabs_alloc;
+  struct PairState_ *ps; /* paired mode: per-pair result sets of the block */
+  size_t ps_alloc;
+  uint64_t n_pairs, n_pairs_fallback;
   /* statistics */
   double ms_k1, ms_k2, ms_k3;
   double wall[8]; /* host wall seconds: stage, seed, hits, candidates, score, replay, align, results */
@@ -147,7 +191,13 @@ void rmapWaveDelete(RmapWave *w)
     for (k = 0; k < WB_COUNT; k++) smb_host_free(w->wb[k].p);
   }
   smb_ctx_destroy(w->ctx);
-  free(w->rd); free(w->cand);
+  free(w->rd); free(w->cand); free(w->jobs); free(w->pjob); free(w->iv);
+  free(w->ftab); free(w->ftabs); free(w->ftab_off); free(w->ftab_read); free(w->f_off); free(w->f_len);
+  if (w->ps) {
+    size_t k;
+    for (k = 0; k < w->ps_alloc; k++) { resultSetDelete(w->ps[k].rs[0]); resultSetDelete(w->ps[k].rs[1]); }
+    free(w->ps);
+  }
   scoreDeleteProfile(w->prof); scoreDeleteProfile(w->profRC); seqFastqDelete(w->readRC);
   free(w);
 }
@@ -213,35 +263,16 @@ static int prune_results(AliRsltSet *out, const smb_ali_result *res, const uint8
 		       k && (s_right > s_end + minscorlen));
 }
 
-int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **reads,
-		   const uint32_t *min_cover_arr, int ktuple_maxhit, int min_swatscor_arg,
-		   int min_swatscor_below_max_arg, UCHAR min_basqval, short target_depth, short max_depth,
-		   RMAPFLG_t rmapflg, const ScoreMatrix *scormtxp, const ResultFilter *rsfp,
-		   const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
-		   RMAPWAVE_EMITF *emitf, void *user)
+/* wave 1a: seed tables of all reads of a block, both strands (one K1 batch) */
+static int wave_seed(ErrMsg *errmsgp, RmapWave *w, int n, SeqFastq **reads, int ktuple_maxhit, UCHAR min_basqval)
 {
-  int errcode = ERRCODE_SUCCESS, rc, i;
-  UCHAR nskip;
-  const UCHAR ktup = hashTableGetKtupLen(htp, &nskip);
-  const SETSIZ_t *soffs;
-  const SEQNUM_t nseq = seqSetGetOffsets(ssp, &soffs);
-  RMAPBUFF *bufp = rmp->bfp;
-  size_t tot = 0, nreq = 0, nsw = 0, nbf = 0, nba = 0;
-  int any_qual = 0, have_pen = 0;
-  short matchscor = 0, mismatchscor = 0, gapinitscor = 0, gapextscor = 0;
-  size_t nres = 0, ndiff = 0;
-  uint64_t cells = 0;
-  double tw = wnow(), tc = cnow(), tres;
-  
-  if (n < 1) return ERRCODE_SUCCESS;
-  if (!(rmapflg & RMAPFLG_SEQBYSEQ) || (rmapflg & (RMAPFLG_NOSHRTINFO | RMAPFLG_SPLIT | RMAPFLG_CMPLXW)))
-    return ERRCODE_ARGINVAL; /* caller falls back to the one-call path (still GPU) */
-
-  /* ------------------------------ wave 1: seeds -------------------------------------- */
+  int rc, i, any_qual = 0;
+  size_t tot = 0;
+  double tw = wnow(), tc = cnow();
+  w->nreads = 0;
   WPIN(w->read_off, WB_READ_OFF, n, uint64_t);
   WPIN(w->read_len, WB_READ_LEN, n, uint32_t);
   WPIN(w->info, WB_INFO, 2 * (size_t) n, smb_seed_info);
-  WGROW(w->rd, w->n_alloc, n, WREAD);
   for (i = 0; i < n; i++) {
     SEQLEN_t len;
     char cod;
@@ -272,28 +303,72 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
     return gpu_fail(errmsgp, w, rc);
   w->ms_k1 += smb_last_kernel_ms(w->ctx);
   WTICK(1);
+  w->nreads = n;
+  w->any_qual = any_qual;
+  return ERRCODE_SUCCESS;
+}
+
+/* waves 1b-3 for a list of jobs on the reads of the current seed batch */
+static int wave_pass(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, const WJOB *jobs, const smb_seed_info *info,
+		     int ktuple_maxhit, int min_swatscor_below_max_arg, short target_depth, short max_depth,
+		     RMAPFLG_t rmapflg, const ScoreMatrix *scormtxp,
+		     const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
+		     WAVE_DONEF *donef, void *user)
+{
+  int errcode = ERRCODE_SUCCESS, rc, i;
+  UCHAR nskip;
+  const UCHAR ktup = hashTableGetKtupLen(htp, &nskip);
+  const SETSIZ_t *soffs;
+  const SEQNUM_t nseq = seqSetGetOffsets(ssp, &soffs);
+  RMAPBUFF *bufp = rmp->bfp;
+  size_t nreq = 0, nreq_max = 0, nsw = 0, nbf = 0, nba = 0;
+  int have_pen = 0;
+  short matchscor = 0, mismatchscor = 0, gapinitscor = 0, gapextscor = 0;
+  size_t nres = 0, ndiff = 0;
+  uint64_t cells = 0;
+  double tw = wnow(), tc = cnow(), tres;
+
+  if (n < 1) return ERRCODE_SUCCESS;
+  WGROW(w->rd, w->n_alloc, n, WREAD);
+  for (i = 0; i < n; i++) nreq_max += 2 * (size_t) (jobs[i].niv < 0 ? nseq : jobs[i].niv);
 
   /* hit lists: every read x strand x reference sequence (collectHits, rmap.c:283-318) */
-  WPIN(w->req, WB_REQ, 2 * (size_t) n * (size_t) nseq + 1, smb_hit_req);
-  WPIN(w->list_first, WB_LIST_FIRST, 2 * (size_t) n * (size_t) nseq + 2, uint64_t);
-  WPIN(w->req_err, WB_REQ_ERR, 2 * (size_t) n * (size_t) nseq + 1, int32_t);
+  /* or, restricted: read x strand x interval with the full seed table (collectHitsFromInterVal,
+   * rmap.c:438-493) */
+  WPIN(w->req, WB_REQ, nreq_max + 1, smb_hit_req);
+  WPIN(w->list_first, WB_LIST_FIRST, nreq_max + 2, uint64_t);
+  WPIN(w->req_err, WB_REQ_ERR, nreq_max + 1, int32_t);
   for (i = 0; i < n; i++) {
     WREAD *rd = w->rd + i;
-    int st;
+    const WJOB *jb = jobs + i;
+    const uint32_t r = jb->seed_read;
+    int st, k;
     SEQNUM_t s;
     memset(rd, 0, sizeof(*rd));
-    rd->qlen = w->read_len[i];
-    rd->errcode = w->info[2 * i].err ? w->info[2 * i].err : w->info[2 * i + 1].err;
+    rd->qlen = w->read_len[jb->read];
+    rd->errcode = info[2 * r].err ? info[2 * r].err : info[2 * r + 1].err;
     rd->cand_first = 0;
     if (rd->errcode) continue;
-    for (st = 0; st < 2; st++)
-      for (s = 0; s < nseq; s++) {
-	smb_hit_req *rq = w->req + nreq++;
-	memset(rq, 0, sizeof(*rq));
-	rq->lo = soffs[s]; rq->hi = soffs[s + 1];
-	rq->read = (uint32_t) i; rq->nhit_max = (uint32_t) ktuple_maxhit;
-	rq->strand = (uint8_t) st; rq->use_short = 1;
+    for (st = 0; st < 2; st++) {
+      if (jb->niv < 0) {
+	for (s = 0; s < nseq; s++) {
+	  smb_hit_req *rq = w->req + nreq++;
+	  memset(rq, 0, sizeof(*rq));
+	  rq->lo = soffs[s]; rq->hi = soffs[s + 1];
+	  rq->read = r; rq->nhit_max = (uint32_t) ktuple_maxhit;
+	  rq->strand = (uint8_t) st; rq->use_short = 1;
+	}
+      } else {
+	for (k = 0; k < jb->niv; k++) {
+	  const WIVAL *iv = w->iv + jb->iv_first + k;
+	  smb_hit_req *rq = w->req + nreq++;
+	  memset(rq, 0, sizeof(*rq));
+	  rq->lo = iv->lo; rq->hi = iv->hi;
+	  rq->read = r; rq->nhit_max = (uint32_t) ktuple_maxhit;
+	  rq->strand = (uint8_t) st; rq->use_short = 0;
+	}
       }
+    }
   }
   if (w->sqdat_alloc < 32 * (size_t) n) { /* typical short-read blocks need no second counting pass */
     WPIN(w->sqdat, WB_SQDAT, 48 * (size_t) n + 1024, uint64_t);
@@ -319,15 +394,15 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
   nreq = 0;
   for (i = 0; i < n; i++) {
     WREAD *rd = w->rd + i;
-    uint32_t min_cover = min_cover_arr[i], mincov_below_max, min_ktup, n_candseg, c;
-    int st;
-    SEQNUM_t s;
+    const WJOB *jb = jobs + i;
+    uint32_t min_cover = jb->min_cover, mincov_below_max, min_ktup, n_candseg, c;
+    int st, nlist;
     short mismatchdiff;
     rd->cand_first = (uint32_t) w->ncand;
     if (rd->errcode) continue;
     /* prelude of mapSingleRead (rmap.c:1258-1290) */
     if (!have_pen) { /* penalties are those of the score matrix, identical for every read */
-      if ((errcode = scoreMakeProfileFromSequence(w->prof, reads[i], scormtxp))) return errcode;
+      if ((errcode = scoreMakeProfileFromSequence(w->prof, jb->readp, scormtxp))) return errcode;
       matchscor = scoreProfileGetAvgPenalties(&mismatchscor, &gapinitscor, &gapextscor, w->prof);
       if ((rc = smbShimSetScoring(w->ctx, w->prof))) return gpu_fail(errmsgp, w, rc);
       have_pen = 1;
@@ -342,12 +417,14 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
       if (mincov_below_max < ktup || (rmapflg & RMAPFLG_BEST))
 	mincov_below_max = ktup + 2 * (nskip - 1);
     }
-    smbShimHitInfoSet(rmp->mrp->hhiFp, w->info + 2 * i);
-    smbShimHitInfoSet(rmp->mrp->hhiRp, w->info + 2 * i + 1);
+    smbShimHitInfoSet(rmp->mrp->hhiFp, info + 2 * jb->seed_read);
+    smbShimHitInfoSet(rmp->mrp->hhiRp, info + 2 * jb->seed_read + 1);
     blankRMAPBUFF(bufp);
+    nlist = (jb->niv < 0) ? (int) nseq : jb->niv;
     for (st = 0; st < 2; st++)
-      for (s = 0; s < nseq; s++, nreq++) {
+      for (c = 0; c < (uint32_t) nlist; c++, nreq++) {
 	const uint64_t f0 = w->list_first[nreq], f1 = w->list_first[nreq + 1];
+	const SEQNUM_t s = (jb->niv < 0) ? (SEQNUM_t) c : (SEQNUM_t) w->iv[jb->iv_first + c].sx;
 	if (rd->errcode) continue;
 	if (w->req_err[nreq] && w->req_err[nreq] != SMB_ERRCODE_ALLOCBOUNDARY) { rd->errcode = w->req_err[nreq]; continue; }
 	hashBlankHitList(bufp->hhlp);
@@ -430,14 +507,14 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
       if (wc->simd) {
 	smb_sw_task *t = w->swt + nsw;
 	memset(t, 0, sizeof(*t));
-	t->read_off = w->read_off[i]; t->read_len = rd->qlen;
+	t->read_off = w->read_off[jobs[i].read]; t->read_len = rd->qlen;
 	t->ref_off = wc->refoff; t->ref_len = wc->reflen; t->flags = flags;
 	wc->task = (int32_t) nsw++;
 	w->cells_k2 += (uint64_t) rd->qlen * wc->reflen;
       } else {
 	smb_band_task *t = w->bft + nbf;
 	memset(t, 0, sizeof(*t));
-	t->read_off = w->read_off[i]; t->read_len = rd->qlen;
+	t->read_off = w->read_off[jobs[i].read]; t->read_len = rd->qlen;
 	t->ref_off = wc->refoff; t->ref_len = wc->reflen; t->flags = flags;
 	t->l_edge = wc->c.band_l; t->r_edge = wc->c.band_r;
 	t->p_left = (int) wc->c.qs; t->p_right = (int) wc->c.qe;
@@ -459,7 +536,7 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
 	if (wc->simd && w->sw_err[wc->task] == ERRCODE_SWATEXCEED) {
 	  smb_band_task *t = w->bft + nbf;
 	  memset(t, 0, sizeof(*t));
-	  t->read_off = w->read_off[i]; t->read_len = rd->qlen;
+	  t->read_off = w->read_off[jobs[i].read]; t->read_len = rd->qlen;
 	  t->ref_off = wc->refoff; t->ref_len = wc->reflen;
 	  t->flags = SMB_TASK_REF_PACKED | ((wc->c.flags & RMAPCANDFLG_REVERSE) ? SMB_TASK_READ_REVCOMP : 0);
 	  t->l_edge = wc->c.band_l; t->r_edge = wc->c.band_r;
@@ -487,7 +564,7 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
     SWATSCOR max1 = 0, max2 = 0;
     const SWATSCOR max_possible_swscor = (SWATSCOR) (rd->qlen * matchscor);
     uint32_t c;
-    int min_swatscor = min_swatscor_arg, min_swatscor_below_max = min_swatscor_below_max_arg;
+    int min_swatscor = jobs[i].min_swatscor, min_swatscor_below_max = min_swatscor_below_max_arg;
     if (rd->errcode || !rd->reached_stats) continue;
     if (mmscordiff < 1 || gapscordiff < 1) return ERRCODE_ASSERT;
     for (c = 0; c < rd->ncand; c++) {
@@ -559,7 +636,7 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
       }
       t = w->bat + nba;
       memset(t, 0, sizeof(*t));
-      t->read_off = w->read_off[i]; t->read_len = rd->qlen;
+      t->read_off = w->read_off[jobs[i].read]; t->read_len = rd->qlen;
       t->ref_off = wc->refoff; t->ref_len = wc->reflen;
       t->flags = SMB_TASK_REF_PACKED | ((cp->flags & RMAPCANDFLG_REVERSE) ? SMB_TASK_READ_REVCOMP : 0);
       t->l_edge = band_l; t->r_edge = band_r;
@@ -609,11 +686,12 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
   tres = wnow();
   for (i = 0; i < n; i++) {
     WREAD *rd = w->rd + i;
-    ResultSet *rsp = rmp->rsrp;
+    ResultSet *rsp = jobs[i].rsp;
+    SeqFastq *readp = jobs[i].readp;
     uint32_t c;
-    resultSetBlank(rsp);
-    if (rd->errcode == ERRCODE_SHORTSEQ) { /* rmapSingle: too short to be hashed -> empty result set */
-      if ((errcode = (*emitf)(user, i, rsp))) return errcode;
+    if (jobs[i].blank) resultSetBlank(rsp);
+    if (rd->errcode == ERRCODE_SHORTSEQ) { /* too short to be hashed (rmap.c:1273-1275) */
+      if (donef && (errcode = (*donef)(user, i, ERRCODE_SHORTSEQ, rsp))) return errcode;
       continue;
     }
     if (rd->reached_stats)
@@ -672,27 +750,370 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
 	 * sequence-by-sequence mode this path runs in; they are built only if such a result exists. */
 	if (need_profiles) {
 	  seqFastqBlank(w->readRC);
-	  if ((errcode = seqFastqAppendSegment(w->readRC, reads[i], 0, 0, 1, codecp)) ||
-	      (errcode = scoreMakeProfileFromSequence(w->prof, reads[i], scormtxp)) ||
+	  if ((errcode = seqFastqAppendSegment(w->readRC, readp, 0, 0, 1, codecp)) ||
+	      (errcode = scoreMakeProfileFromSequence(w->prof, readp, scormtxp)) ||
 	      (errcode = scoreMakeProfileFromSequence(w->profRC, w->readRC, scormtxp)))
 	    return errcode;
 	}
-	errcode = resultSetSortAndAssignSequence(rsp, bufp->sqbfp, 0, reads[i], w->prof, w->profRC, ssp, codecp);
+	errcode = resultSetSortAndAssignSequence(rsp, bufp->sqbfp, 0, readp, w->prof, w->profRC, ssp, codecp);
 	if (errcode) { rd->errcode = errcode; ERRMSGNO(errmsgp, errcode); }
       }
     }
-    {
-      double tr2;
-      if (!rd->errcode && (errcode = resultSetFilterResults(rsp, rsfp, reads[i])))
-	ERRMSGNO(errmsgp, errcode);
-      tr2 = wnow();
-      w->wall_res[1] += tr2 - tres;
-      if ((errcode = (*emitf)(user, i, rsp))) return errcode;
-      tres = wnow();
-      w->wall_res[2] += tres - tr2;
-    }
+    if (donef && (errcode = (*donef)(user, i, rd->errcode, rsp))) return errcode;
+    tres = wnow();
   }
   WTICK(7);
   w->n_reads += (uint64_t) n;
   return ERRCODE_SUCCESS;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* single-end blocks                                                                      */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+  RmapWave *w;
+  ErrMsg *errmsgp;
+  const ResultFilter *rsfp;
+  const WJOB *jobs;
+  RMAPWAVE_EMITF *emitf;
+  void *user;
+} SINGLEDONE;
+
+static int single_done(void *user, int i, int errcode, ResultSet *rsp)
+{
+  SINGLEDONE *sd = (SINGLEDONE *) user;
+  double t0 = wnow(), t1;
+  int e;
+  if (errcode != ERRCODE_SHORTSEQ && !errcode && (e = resultSetFilterResults(rsp, sd->rsfp, sd->jobs[i].readp)))
+    ERRMSGNO(sd->errmsgp, e);
+  t1 = wnow();
+  sd->w->wall_res[1] += t1 - t0;
+  e = (*sd->emitf)(sd->user, i, rsp);
+  sd->w->wall_res[2] += wnow() - t1;
+  return e;
+}
+
+int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **reads,
+		   const uint32_t *min_cover_arr, int ktuple_maxhit, int min_swatscor_arg,
+		   int min_swatscor_below_max_arg, UCHAR min_basqval, short target_depth, short max_depth,
+		   RMAPFLG_t rmapflg, const ScoreMatrix *scormtxp, const ResultFilter *rsfp,
+		   const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
+		   RMAPWAVE_EMITF *emitf, void *user)
+{
+  int errcode, i;
+  SINGLEDONE sd;
+  if (n < 1) return ERRCODE_SUCCESS;
+  if (!(rmapflg & RMAPFLG_SEQBYSEQ) || (rmapflg & (RMAPFLG_NOSHRTINFO | RMAPFLG_SPLIT | RMAPFLG_CMPLXW)))
+    return ERRCODE_ARGINVAL; /* caller runs the reference's own per-read code on fibers (still GPU) */
+  if ((errcode = wave_seed(errmsgp, w, n, reads, ktuple_maxhit, min_basqval))) return errcode;
+  WGROW(w->jobs, w->jobs_alloc, n, WJOB);
+  for (i = 0; i < n; i++) {
+    WJOB *jb = w->jobs + i;
+    jb->read = jb->seed_read = (uint32_t) i; jb->min_cover = min_cover_arr[i]; jb->min_swatscor = min_swatscor_arg;
+    jb->readp = reads[i]; jb->rsp = rmp->rsrp; jb->niv = -1; jb->iv_first = 0; jb->blank = 1;
+  }
+  sd.w = w; sd.errmsgp = errmsgp; sd.rsfp = rsfp; sd.jobs = w->jobs; sd.emitf = emitf; sd.user = user;
+  return wave_pass(errmsgp, rmp, w, n, w->jobs, w->info, ktuple_maxhit, min_swatscor_below_max_arg, target_depth, max_depth,
+		   rmapflg, scormtxp, htp, ssp, codecp, single_done, &sd);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* paired-end blocks                                                                      */
+/* ------------------------------------------------------------------------------------ */
+/* rmapPair (rmap.c:1744-2112) for a block of pairs.  The common course of a pair -
+ *   seeds of both mates; the mate with fewer seed hits ("mate 1") mapped without restriction;
+ *   insert-size intervals from its best hits (setupInterValFromResultSet, rmap.c:354-436);
+ *   the other mate mapped inside those intervals; proper pairs found, mate 1 confidently
+ *   placed (rmap.c:1950-1969)
+ * - runs as two wave passes over all pairs of the block (the same K1/K2/K3 batches as
+ * single-end reads, hit lists restricted to the intervals in the second pass).  A pair that
+ * leaves that course (no proper pair, weak mate 1: unrestricted second search and the rescue
+ * with the on-the-fly k=5 index, rmap.c:1970-2061; a mate too short to be hashed) is marked
+ * RMAPPAIR_FALLBACK and mapped from scratch by the reference's own rmapPair on a fiber
+ * (shim_fiber.inc.c) - the course of a pair is a deterministic function of the pair, so the
+ * replay gives the reference's result.  Every decision is made by the reference's own
+ * functions (results.c / resultpairs.c / interval.c); nothing of their logic is restated. */
+
+void rmapWaveGetPairStats(const RmapWave *w, uint64_t counts[4])
+{
+  counts[0] = w->n_pairs; counts[1] = w->n_pairs_fallback; counts[2] = w->n_pairs_pass3; counts[3] = w->n_pairs_pass4;
+}
+
+/* job of a restricted search (intervals copied from ivr): job slot j >= 0 in w->jobs, or the
+ * per-pair slot of pair -1-j in w->pjob */
+static int pair_job_restricted(RmapWave *w, int j, int read, int seed_read, uint32_t min_cover, int min_swatscor,
+			       SeqFastq *readp, ResultSet *rsp, const InterVal *ivr, const SETSIZ_t *soffs)
+{
+  const int niv = interValNum(ivr);
+  WJOB *jb = (j >= 0) ? w->jobs + j : w->pjob + (-1 - j);
+  int k;
+  WGROW(w->iv, w->iv_alloc, w->niv + (size_t) niv + 1, WIVAL);
+  jb->read = (uint32_t) read; jb->seed_read = (uint32_t) seed_read;
+  jb->min_cover = min_cover; jb->min_swatscor = min_swatscor;
+  jb->readp = readp; jb->rsp = rsp;
+  jb->niv = niv; jb->iv_first = (uint32_t) w->niv; jb->blank = 0;
+  for (k = 0; k < niv; k++) {
+    SEQLEN_t lo, hi;
+    SEQNUM_t sx;
+    WIVAL *iv = w->iv + w->niv++;
+    if (interValGet(&lo, &hi, &sx, NULL, k, ivr)) return ERRCODE_ASSERT;
+    iv->lo = soffs[sx] + lo; iv->hi = soffs[sx] + hi + 1; iv->sx = (int32_t) sx;
+  }
+  return ERRCODE_SUCCESS;
+}
+
+int rmapPairWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int npairs, SeqFastq **reads, const uint32_t *mincov,
+		 int d_min, int d_max, RSLTPAIRLIB_t pairlibcode, int ktuple_maxhit, int min_swatscor,
+		 UCHAR min_basqval, short target_depth, short max_depth, RMAPFLG_t rmapflg,
+		 const ScoreMatrix *scormtxp, const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
+		 unsigned char *status)
+{
+  int errcode, p, nj;
+  const SETSIZ_t *soffs;
+  seqSetGetOffsets(ssp, &soffs);
+  if (npairs < 1) return ERRCODE_SUCCESS;
+  if (!(rmapflg & RMAPFLG_SEQBYSEQ) ||
+      (rmapflg & (RMAPFLG_NOSHRTINFO | RMAPFLG_SPLIT | RMAPFLG_CMPLXW | RMAPFLG_ALLPAIR)) ||
+      !rmp->mmp || !rmp->ivr || !rmp->pairp)
+    return ERRCODE_ARGINVAL;
+  if ((size_t) npairs > w->ps_alloc) {
+    const size_t na = (size_t) npairs + 64;
+    struct PairState_ *hp = (struct PairState_ *) realloc(w->ps, na * sizeof(*hp));
+    if (!hp) return ERRCODE_NOMEM;
+    memset(hp + w->ps_alloc, 0, (na - w->ps_alloc) * sizeof(*hp));
+    w->ps = hp;
+    w->ps_alloc = na;
+  }
+  if ((errcode = wave_seed(errmsgp, w, 2 * npairs, reads, ktuple_maxhit, min_basqval))) return errcode;
+  WGROW(w->jobs, w->jobs_alloc, npairs, WJOB);
+  WGROW(w->pjob, w->pjob_alloc, npairs, WJOB);
+
+  /* pass 1: the mate with fewer hits, unrestricted (rmap.c:1870-1919) */
+  for (p = 0, nj = 0; p < npairs; p++) {
+    struct PairState_ *ps = w->ps + p;
+    const smb_seed_info *inf = w->info + 4 * (size_t) p;
+    const int err_read = inf[0].err ? inf[0].err : inf[1].err, err_mate = inf[2].err ? inf[2].err : inf[3].err;
+    WJOB *jb;
+    if (!ps->rs[0] && (!(ps->rs[0] = resultSetCreate(16, 256)) || !(ps->rs[1] = resultSetCreate(16, 256))))
+      return ERRCODE_NOMEM;
+    ps->status = RMAPPAIR_DONE;
+    if (err_read || err_mate) { ps->status = RMAPPAIR_FALLBACK; continue; }
+    resultSetBlank(ps->rs[0]);
+    resultSetBlank(ps->rs[1]);
+    /* calcTotalNumberOfHits (rmap.c:1079-1084) of both mates */
+    ps->rare_mate = (unsigned char) ((uint32_t) (inf[0].nhit_all + inf[1].nhit_all) > (uint32_t) (inf[2].nhit_all + inf[3].nhit_all));
+    ps->pairflg = (RSLTPAIRFLG_t) (RSLTPAIRFLG_PAIRED | (ps->rare_mate ? RSLTPAIRFLG_RAREMATE : 0));
+    jb = w->jobs + nj++;
+    jb->read = jb->seed_read = (uint32_t) (2 * p + ps->rare_mate);
+    jb->min_cover = mincov[jb->read]; jb->min_swatscor = min_swatscor;
+    jb->readp = reads[jb->read]; jb->rsp = ps->rs[ps->rare_mate];
+    jb->niv = -1; jb->iv_first = 0; jb->blank = 0;
+  }
+  if ((errcode = wave_pass(errmsgp, rmp, w, nj, w->jobs, w->info, ktuple_maxhit, MINSCOR_BELOW_MAX_BEST, target_depth,
+			   max_depth, rmapflg, scormtxp, htp, ssp, codecp, NULL, NULL)))
+    return errcode;
+  for (p = 0, nj = 0; p < npairs; p++) /* errors of pass 1 (the reference exits on them) -> reference code */
+    if (w->ps[p].status == RMAPPAIR_DONE && w->rd[nj++].errcode) w->ps[p].status = RMAPPAIR_FALLBACK;
+
+  /* pass 2: the other mate inside the insert-size intervals around mate 1 (rmap.c:1921-1948) */
+  w->niv = 0;
+  for (p = 0, nj = 0; p < npairs; p++) {
+    struct PairState_ *ps = w->ps + p;
+    const int i1 = 2 * p + ps->rare_mate, i2 = 2 * p + !ps->rare_mate;
+    if (ps->status != RMAPPAIR_DONE) continue;
+    ps->mapq1 = resultSetGetMappingScore(ps->rs[ps->rare_mate], &ps->swscor1);
+    if (setupInterValFromResultSet(rmp->ivr, d_min, d_max, reads[i1], reads[i2], htp, ssp, ps->rs[ps->rare_mate])) {
+      ps->status = RMAPPAIR_FALLBACK;
+      continue;
+    }
+    interValPrune(rmp->ivr);
+    if ((errcode = pair_job_restricted(w, nj++, i2, i2, mincov[i2], min_swatscor, reads[i2], ps->rs[!ps->rare_mate],
+				       rmp->ivr, soffs)))
+      return errcode;
+  }
+  if ((errcode = wave_pass(errmsgp, rmp, w, nj, w->jobs, w->info, ktuple_maxhit, MINSCOR_BELOW_MAX_BEST, target_depth,
+			   max_depth, rmapflg, scormtxp, htp, ssp, codecp, NULL, NULL)))
+    return errcode;
+
+  /* does the pair end here? (rmap.c:1950-1969) */
+  for (p = 0, nj = 0; p < npairs; p++) {
+    struct PairState_ *ps = w->ps + p;
+    const int i1 = 2 * p + ps->rare_mate, i2 = 2 * p + !ps->rare_mate;
+    ps->stage = PST_END;
+    if (ps->status != RMAPPAIR_DONE) continue;
+    if (w->rd[nj++].errcode) { ps->status = RMAPPAIR_FALLBACK; continue; }
+    errcode = resultSetFindProperPairs(rmp->pairp, d_min, d_max, MAXNUM_PAIRS_TOTAL, 0, pairlibcode, ps->rs[0], ps->rs[1]);
+    if (errcode && errcode != ERRCODE_PAIRNUM) { ps->status = RMAPPAIR_FALLBACK; continue; }
+    ps->swscor2_restricted = 0;
+    ps->n_proper = 0;
+    resultSetGetMappingScore(ps->rs[!ps->rare_mate], &ps->swscor2_restricted);
+    resultSetGetNumberOfPairs(&ps->n_proper, rmp->pairp);
+    if (ps->n_proper < 1 || ps->mapq1 < MAPSCORE_UNIQUE_MAPPED_1ST ||
+	!scorIsAboveFractMax(ps->swscor2_restricted, ps->swscor1, MINFRACT_MAXSCOR_2ND, reads[i2], reads[i1]))
+      ps->stage = PST_SECOND_UNRESTRICTED;
+    else
+      ps->pairflg = (RSLTPAIRFLG_t) (ps->pairflg | (ps->rare_mate == 0 ? RSLTPAIRFLG_RESTRICT_2nd : RSLTPAIRFLG_RESTRICT_1st));
+  }
+
+  /* pass 3: no proper pair or mate 1 not placed with confidence -> unrestricted search for the
+   * other mate (rmap.c:1970-1996) */
+  for (p = 0, nj = 0; p < npairs; p++) {
+    struct PairState_ *ps = w->ps + p;
+    const int i2 = 2 * p + !ps->rare_mate;
+    WJOB *jb;
+    if (ps->status != RMAPPAIR_DONE || ps->stage != PST_SECOND_UNRESTRICTED) continue;
+    if (ps->n_proper < 1) resultSetBlank(ps->rs[!ps->rare_mate]);
+    jb = w->jobs + nj++;
+    jb->read = jb->seed_read = (uint32_t) i2;
+    jb->min_cover = mincov[i2]; jb->min_swatscor = min_swatscor;
+    jb->readp = reads[i2]; jb->rsp = ps->rs[!ps->rare_mate];
+    jb->niv = -1; jb->iv_first = 0; jb->blank = 0;
+  }
+  w->n_pairs_pass3 += (uint64_t) nj;
+  if (nj && (errcode = wave_pass(errmsgp, rmp, w, nj, w->jobs, w->info, ktuple_maxhit, MINSCOR_BELOW_MAX_BEST,
+				 target_depth, max_depth, rmapflg, scormtxp, htp, ssp, codecp, NULL, NULL)))
+    return errcode;
+
+  /* something better for mate 1 near the new hits of the other mate?  (rmap.c:1998-2061):
+   * intervals around them; the k=5 index of those intervals is built by the reference's own
+   * hashTableSetUp on the host (setupFineHashTable, rmap.c:495-517) and copied out per pair */
+  w->niv = 0;
+  w->nftab = 0;
+  {
+    int n4m = 0, n4f = 0, fine_k = 0, fine_s = 0;
+    UCHAR nskip_main;
+    const UCHAR ktup_main = hashTableGetKtupLen(htp, &nskip_main);
+    for (p = 0, nj = 0; p < npairs; p++) {
+      struct PairState_ *ps = w->ps + p;
+      const int i1 = 2 * p + ps->rare_mate, i2 = 2 * p + !ps->rare_mate;
+      int mapq2, swscor2 = 0;
+      SEQLEN_t rlen;
+      if (ps->status != RMAPPAIR_DONE || ps->stage != PST_SECOND_UNRESTRICTED) continue;
+      ps->stage = PST_END;
+      if (w->rd[nj++].errcode) { ps->status = RMAPPAIR_FALLBACK; continue; }
+      mapq2 = resultSetGetMappingScore(ps->rs[!ps->rare_mate], &swscor2);
+      if (!(mapq2 > MAPSCORE_UNIQUE_MAPPED_1ST || swscor2 > ps->swscor2_restricted || swscor2 > ps->swscor1)) continue;
+      ps->swscor1_2ndbest = 0;
+      resultSetGetScorStats(ps->rs[ps->rare_mate], NULL, NULL, &ps->swscor1_2ndbest, NULL);
+      if (setupInterValFromResultSet(rmp->ivr, d_min, d_max, reads[i2], reads[i1], htp, ssp, ps->rs[!ps->rare_mate])) {
+	ps->status = RMAPPAIR_FALLBACK;
+	continue;
+      }
+      interValPrune(rmp->ivr);
+      seqFastqGetConstSequence(reads[i1], &rlen, NULL);
+      if (ktup_main > rlen) continue;
+      errcode = setupFineHashTable(rmp->htflyp, rmp->bfp->sqbfp, ssp, rmp->ivr, htp, codecp);
+      if (errcode && errcode != ERRCODE_MAXKPOS) { ps->status = RMAPPAIR_FALLBACK; continue; }
+      if (errcode) {
+	ps->stage = PST_RESCUE_MAIN; /* too many positions for the on-the-fly index: main index, restricted */
+	n4m++;
+      } else {
+	int typ, wordlen, nsk, nbk, nbl;
+	uint32_t npos, nwords;
+	const uint32_t *idx, *pos, *widx, *pidx;
+	size_t nkeys, need;
+	smbShimHashTableArrays(rmp->htflyp, &typ, &wordlen, &nsk, &nbk, &nbl, &npos, &nwords, &idx, &pos, &widx, &pidx);
+	if (!fine_k) { fine_k = wordlen; fine_s = nsk; }
+	if (typ != HASHIDXTYP_PERFECT || wordlen != fine_k || nsk != fine_s || wordlen > 12) {
+	  ps->status = RMAPPAIR_FALLBACK; /* (sampling step changed by hashTableReset, rmap.c:503-510) */
+	  continue;
+	}
+	nkeys = (size_t) 1 << (2 * wordlen);
+	need = w->nftab + nkeys + 1 + npos + 2;
+	WGROW(w->ftab, w->ftab_alloc, need, uint32_t);
+	if ((size_t) n4f + 1 > w->ftabs_alloc) {
+	  const size_t na = (size_t) n4f + 256;
+	  w->ftabs = (smb_small_index *) realloc(w->ftabs, na * sizeof(smb_small_index));
+	  w->ftab_off = (size_t *) realloc(w->ftab_off, 2 * na * sizeof(size_t));
+	  w->ftab_read = (uint32_t *) realloc(w->ftab_read, na * sizeof(uint32_t));
+	  w->f_off = (uint64_t *) realloc(w->f_off, na * sizeof(uint64_t));
+	  w->f_len = (uint32_t *) realloc(w->f_len, na * sizeof(uint32_t));
+	  if (!w->ftabs || !w->ftab_off || !w->ftab_read || !w->f_off || !w->f_len) return ERRCODE_NOMEM;
+	  w->ftabs_alloc = na;
+	}
+	memcpy(w->ftab + w->nftab, idx, (nkeys + 1) * sizeof(uint32_t));
+	if (npos) memcpy(w->ftab + w->nftab + nkeys + 1, pos, (size_t) npos * sizeof(uint32_t));
+	w->ftab_off[2 * n4f] = w->nftab; w->ftab_off[2 * n4f + 1] = w->nftab + nkeys + 1;
+	w->ftabs[n4f].npos = npos;
+	w->nftab = need;
+	ps->stage = PST_RESCUE_FINE;
+	n4f++;
+      }
+      /* the job of this pair goes after those of the same kind: intervals are kept per pair */
+      if ((errcode = pair_job_restricted(w, -1 - p, i1, i1, mincov[i1], ps->swscor1_2ndbest, reads[i1],
+					 ps->rs[ps->rare_mate], rmp->ivr, soffs)))
+	return errcode;
+    }
+    /* pass 4 (main index): restricted search for mate 1 with its block seed tables (rmap.c:2048-2060) */
+    if (n4m) {
+      for (p = 0, nj = 0; p < npairs; p++)
+	if (w->ps[p].status == RMAPPAIR_DONE && w->ps[p].stage == PST_RESCUE_MAIN) w->jobs[nj++] = w->pjob[p];
+      if ((errcode = wave_pass(errmsgp, rmp, w, nj, w->jobs, w->info, ktuple_maxhit, MINSCOR_BELOW_MAX_BEST, target_depth,
+			       max_depth, rmapflg, scormtxp, htp, ssp, codecp, NULL, NULL)))
+	return errcode;
+      for (p = 0, nj = 0; p < npairs; p++)
+	if (w->ps[p].status == RMAPPAIR_DONE && w->ps[p].stage == PST_RESCUE_MAIN && w->rd[nj++].errcode)
+	  w->ps[p].status = RMAPPAIR_FALLBACK;
+    }
+    /* pass 4 (on-the-fly indexes): full seed tables of mate 1 against the index of its pair
+     * (initRMAPINFO on htflyp, rmap.c:2026-2030) - one K1 batch with per-read tables - then the
+     * restricted search with those (rmap.c:2032-2046) */
+    if (n4f) {
+      int rc, k = 0;
+      smb_seed_info *info4;
+      WPIN(info4, WB_INFO4, 2 * (size_t) n4f, smb_seed_info);
+      w->info4 = info4;
+      for (p = 0, nj = 0; p < npairs; p++) {
+	struct PairState_ *ps = w->ps + p;
+	if (ps->status != RMAPPAIR_DONE || ps->stage != PST_RESCUE_FINE) continue;
+	w->ftabs[k].idx = w->ftab + w->ftab_off[2 * k];
+	w->ftabs[k].pos = w->ftab + w->ftab_off[2 * k + 1];
+	w->ftab_read[k] = (uint32_t) k;
+	w->jobs[nj] = w->pjob[p];
+	w->jobs[nj].seed_read = (uint32_t) k;
+	w->f_off[k] = w->read_off[w->jobs[nj].read];
+	w->f_len[k] = w->read_len[w->jobs[nj].read];
+	nj++; k++;
+      }
+      if ((rc = smb_seed_batch_tables(w->ctx, fine_k, fine_s, w->ftabs, n4f, w->ftab_read, w->f_off, w->f_len, n4f,
+				      w->any_qual ? w->qual : NULL, 0, 0, min_basqval, 0, info4)))
+	return gpu_fail(errmsgp, w, rc);
+      w->ms_k1 += smb_last_kernel_ms(w->ctx);
+      if ((errcode = wave_pass(errmsgp, rmp, w, nj, w->jobs, info4, ktuple_maxhit, MINSCOR_BELOW_MAX_BEST, target_depth,
+			       max_depth, rmapflg, scormtxp, rmp->htflyp, ssp, codecp, NULL, NULL)))
+	return errcode;
+      for (p = 0, nj = 0; p < npairs; p++)
+	if (w->ps[p].status == RMAPPAIR_DONE && w->ps[p].stage == PST_RESCUE_FINE && w->rd[nj++].errcode)
+	  w->ps[p].status = RMAPPAIR_FALLBACK;
+      w->nreads = 0; /* the block seed tables are gone from the device */
+    }
+    w->n_pairs_pass4 += (uint64_t) (n4m + n4f);
+  }
+  for (p = 0; p < npairs; p++) {
+    status[p] = w->ps[p].status;
+    if (status[p] != RMAPPAIR_DONE) w->n_pairs_fallback++;
+  }
+  w->n_pairs += (uint64_t) npairs;
+  return ERRCODE_SUCCESS;
+}
+
+/* tail of rmapPair (rmap.c:2095-2109) for a pair that rmapPairWave completed; the result sets
+ * stay valid until the next rmapPairWave */
+int rmapPairWaveFinish(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int p, int d_min, int d_max,
+		       RSLTPAIRLIB_t pairlibcode, const ResultFilter *rsfp, SeqFastq *readp, SeqFastq *matep,
+		       const ResultSet **rsltp, const ResultSet **rslt_matep, const ResultPairs **pairp,
+		       RSLTPAIRFLG_t *pairflg)
+{
+  struct PairState_ *ps = w->ps + p;
+  int errcode;
+  if ((size_t) p >= w->ps_alloc || ps->status != RMAPPAIR_DONE) return ERRCODE_ASSERT;
+  /* same sequence of calls on the ResultPairs object as in rmapPair */
+  errcode = resultSetFindProperPairs(rmp->pairp, d_min, d_max, MAXNUM_PAIRS_TOTAL, 0, pairlibcode, ps->rs[0], ps->rs[1]);
+  if (errcode && errcode != ERRCODE_PAIRNUM) ERRMSGNO(errmsgp, errcode);
+  if ((errcode = resultSetFindPairs(rmp->pairp, ps->pairflg, pairlibcode, d_min, d_max, ps->rs[0], ps->rs[1])))
+    ERRMSGNO(errmsgp, errcode);
+  if ((errcode = resultSetFilterResults(ps->rs[0], rsfp, readp))) ERRMSGNO(errmsgp, errcode);
+  if ((errcode = resultSetFilterResults(ps->rs[1], rsfp, matep))) ERRMSGNO(errmsgp, errcode);
+  *rsltp = ps->rs[0]; *rslt_matep = ps->rs[1]; *pairp = rmp->pairp; *pairflg = ps->pairflg;
+  return errcode;
 }

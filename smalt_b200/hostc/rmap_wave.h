@@ -22,4 +22,19 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
 		   RMAPFLG_t rmapflg, const ScoreMatrix *scormtxp, const ResultFilter *rsfp,
 		   const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
 		   RMAPWAVE_EMITF *emitf, void *user);
+/* Paired reads: reads[2p] / reads[2p+1] = read and mate of pair p (mincov likewise).  On return
+ * status[p] is RMAPPAIR_DONE (finish with rmapPairWaveFinish) or RMAPPAIR_FALLBACK (map the pair
+ * with the reference's rmapPair).  ERRCODE_ARGINVAL: flag combination not handled here. */
+enum { RMAPPAIR_DONE = 0, RMAPPAIR_FALLBACK = 1 };
+int rmapPairWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int npairs, SeqFastq **reads, const uint32_t *mincov,
+		 int d_min, int d_max, RSLTPAIRLIB_t pairlibcode, int ktuple_maxhit, int min_swatscor,
+		 unsigned char min_basqval, short target_depth, short max_depth, RMAPFLG_t rmapflg,
+		 const ScoreMatrix *scormtxp, const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
+		 unsigned char *status);
+int rmapPairWaveFinish(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int p, int d_min, int d_max,
+		       RSLTPAIRLIB_t pairlibcode, const ResultFilter *rsfp, SeqFastq *readp, SeqFastq *matep,
+		       const ResultSet **rsltp, const ResultSet **rslt_matep, const ResultPairs **pairp,
+		       RSLTPAIRFLG_t *pairflg);
+/* pairs seen, pairs left to rmapPair, pairs with a third pass, pairs with a fourth pass */
+void rmapWaveGetPairStats(const RmapWave *w, uint64_t counts[4]);
 #endif

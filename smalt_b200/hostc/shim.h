@@ -25,6 +25,34 @@ int smbShimHitListSet(HashHitList *p, const uint64_t *sqdat, int nhits, int is_r
 int smbShimAliRsltSetAdd(AliRsltSet *p, int score, int qs, int qe, int rs, int re,
 			 const unsigned char *diffstr, int difflen);
 
+/* arrays of a hash table (shim_hashidx.c) */
+void smbShimHashTableArrays(const HashTable *htp, int *typ, int *wordlen, int *nskip,
+			    int *nbits_key, int *nbits_lo, uint32_t *npos, uint32_t *nwords,
+			    const uint32_t **idx, const uint32_t **pos,
+			    const uint32_t **wordidx, const uint32_t **posidx);
+
+/* fiber scheduler (shim_fiber.inc.c): runs a per-item function that uses the reference's
+ * one-call hot-path API for many items at once and executes the calls as GPU batches */
+typedef struct SmbFiberPool_ SmbFiberPool;
+typedef void (SMBFIBER_ITEMF)(void *user, int item, int slot);
+typedef struct {
+  uint64_t n_items, n_waves, n_seeded, seeds_served, n_hits, n_sw, n_bandfast, n_bandali, order_waits;
+  uint64_t cells_k2, cells_k3;
+  double ms_k1, ms_k2, ms_k3;
+  double wall_stage, wall_arena, wall_sw, wall_ba;
+  double wall_host, wall_hits, wall_dp, cpu_host;   /* seconds: fibers running, hit-list batches, DP batches */
+} smbFiberStats;
+SmbFiberPool *smbFiberPoolCreate(int nfibers, size_t stack_bytes);
+void smbFiberPoolDelete(SmbFiberPool *p);
+int smbFiberPoolSize(const SmbFiberPool *p);
+void smbFiberPoolGetStats(const SmbFiberPool *p, smbFiberStats *st);
+int smbFiberPoolSeed(SmbFiberPool *p, int nreads, SeqFastq *const *reads, int reads_per_item, int is_short,
+		     uint32_t maxhit_per_tuple, uint32_t maxhit_total, int basq, const HashTable *htp);
+int smbFiberPoolRun(SmbFiberPool *p, int nitems, SMBFIBER_ITEMF *itemf, void *user);
+int smbFiberYield(void);
+void smbFiberWaitOrder(void);
+int smbFiberSelfTest(int nfibers, int nitems, int *order_out, int *draws_out, int *ndraws);
+
 /* FASTQ record -> SeqFastq by memcpy (shim_sequence.c) */
 int smbShimSeqFastqLoad(SeqFastq *sqp, const char *name, size_t nlen, const char *seq, size_t slen,
 			const char *qnam, size_t qnlen, const char *qual, size_t qlen);

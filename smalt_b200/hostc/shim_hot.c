@@ -42,7 +42,20 @@
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
 static smb_ctx *g_root;             /* owns index + packed reference */
 static const HashTable *g_root_htp; /* table uploaded to g_root */
+static smb_ctx *g_aux;              /* one-call context for any OTHER table (the on-the-fly k=5 index of
+				     * rmap.c:495-517): its index is uploaded per seed call, so that the
+				     * arrays shared by the worker contexts are never overwritten */
 static int g_device = -1;
+
+/* fiber scheduler (shim_fiber.inc.c): batches the one-call API over many reads */
+static struct SmbFiberPool_ *fiber_pool_current(void);
+static int fiber_seed_lookup(HashHitInfo *h, int is_reverse, int is_short, uint32_t maxhit_per_tuple,
+			     uint32_t maxhit_total, int basq, const SeqFastq *seqp, const HashTable *htp);
+static int fiber_hits(HashHitList *hlp, uint64_t lo, uint64_t hi, uint32_t nhit_max, int mode, HashHitInfo *h,
+		      int *done);
+static int fiber_dp(int kind, int *score, AliRsltSet *rssp, const ScoreProfile *profp, const char *useq, int uslen,
+		    int l_edge, int r_edge, int pl, int pr, int ul, int ur, int minscore, int minscorlen, int *done);
+enum { FOP_NONE, FOP_NOP, FOP_WAITORDER, FOP_HITS, FOP_SW, FOP_BANDFAST, FOP_BANDALI };
 
 static double shim_now(void)
 {
@@ -142,7 +155,7 @@ int smbShimInit(const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
     }
     (void) scormtxp;
   }
-  if (htp && g_root_htp != htp) {
+  if (htp && g_root_htp != htp && (ssp || !g_root_htp)) {
     double t0 = shim_now();
     if (!(errcode = upload_index(g_root, htp))) g_root_htp = htp;
     SHIM_TIMING("index upload", t0);
@@ -352,6 +365,11 @@ int swSIMDAlignStriped(int *maxscor, const AliBuffer *abp, const ScoreProfile *p
   int errcode;
   (void) abp;
   *maxscor = 0;
+  if (fiber_pool_current()) {
+    int done = 0;
+    errcode = fiber_dp(FOP_SW, maxscor, NULL, profp, unprofiled_seqp, unprofiled_seqlen, 0, 0, 0, 0, 0, 0, 0, 0, &done);
+    if (done) return errcode;
+  }
   if (smbShimInit(NULL, NULL, NULL, NULL)) return ERRCODE_FAILURE;
   pthread_mutex_lock(&g_lock);
   if (!(errcode = single_arena(g_root, profp, unprofiled_seqp, unprofiled_seqlen, &qlen))) {
@@ -383,6 +401,12 @@ int aliSmiWatInBandFast(int *maxswscor, AliBuffer *bufp, const ScoreProfile *pro
   unsigned int qlen;
   int errcode;
   (void) bufp;
+  if (fiber_pool_current()) {
+    int done = 0;
+    errcode = fiber_dp(FOP_BANDFAST, maxswscor, NULL, profp, unprofiled_seqp, unprofiled_seqlen, l_edge, r_edge,
+		       profiled_left, profiled_right, unprofiled_left, unprofiled_right, 0, 0, &done);
+    if (done) return errcode;
+  }
   if (smbShimInit(NULL, NULL, NULL, NULL)) return ERRCODE_FAILURE;
   pthread_mutex_lock(&g_lock);
   if (!(errcode = single_arena(g_root, profp, unprofiled_seqp, unprofiled_seqlen, &qlen))) {
@@ -410,6 +434,12 @@ int aliSmiWatInBand(AliRsltSet *rssp, AliBuffer *bufp, const ScoreProfile *profp
   uint8_t *diff = NULL;
   uint32_t first[2];
   (void) bufp;
+  if (fiber_pool_current()) {
+    int done = 0;
+    errcode = fiber_dp(FOP_BANDALI, NULL, rssp, profp, unprofiled_seqp, unprofiled_seqlen, l_edge, r_edge,
+		       profiled_left, profiled_right, unprofiled_left, unprofiled_right, minscore, minscorlen, &done);
+    if (done) return errcode;
+  }
   if (smbShimInit(NULL, NULL, NULL, NULL)) return ERRCODE_FAILURE;
   pthread_mutex_lock(&g_lock);
   if (!(errcode = single_arena(g_root, profp, unprofiled_seqp, unprofiled_seqlen, &qlen))) {
@@ -450,6 +480,9 @@ struct _HashHitInfo {
   uint32_t maxhit_per_tuple, maxhit_total;
   int basq, is_short, has_qual, is_reverse;
   unsigned long serial;
+  const HashTable *htp;    /* table of the last collecting call */
+  void *pool;              /* fiber pool whose block seed batch holds this read's tables, or NULL */
+  int pool_read;           /* read index in that batch */
 };
 
 struct _HashHitList {
@@ -464,8 +497,9 @@ struct _HashHitList {
   size_t qmask_alloc;
 };
 
-static unsigned long g_serial;          /* id of the read whose tables are on g_root */
-static unsigned long g_resident_serial;
+static unsigned long g_serial;          /* id of the read whose tables are on g_root / g_aux */
+static unsigned long g_resident_serial, g_aux_resident_serial;
+
 
 HashHitInfo *hashCreateHitInfo(int blksz, const HashTable *htp)
 {
@@ -481,7 +515,7 @@ void hashDeleteHitInfo(HashHitInfo *p)
   free(p);
 }
 
-void smbShimHitInfoSet(HashHitInfo *p, const smb_seed_info *info) { p->info = *info; p->serial = 0; }
+void smbShimHitInfoSet(HashHitInfo *p, const smb_seed_info *info) { p->info = *info; p->serial = 0; p->pool = NULL; }
 const smb_seed_info *smbShimHitInfoGet(const HashHitInfo *p) { return &p->info; }
 
 uint32_t hashCalcHitInfoCoverDeficit(const HashHitInfo *hip) { return hip->info.cover_deficit; }
@@ -498,18 +532,32 @@ uint32_t hashHitInfoCalcHitNumbers(const HashHitInfo *hhip, uint32_t *nhit_rank)
   return hhip->info.nhit_tot;
 }
 
+static smb_ctx *hitinfo_ctx(const HashHitInfo *h) { return (h->htp == g_root_htp) ? g_root : g_aux; }
+
+/* (re)builds the device seed tables of one read on the one-call context of its table; g_lock held */
 static int seed_one(HashHitInfo *h)
 {
   uint64_t off = 0;
   smb_seed_info info[2];
   int errcode;
-  if ((errcode = smb_arena_upload(g_root, h->codes, h->qlen))) return ERRCODE_FAILURE;
-  errcode = smb_seed_batch(g_root, &off, &h->qlen, 1, h->has_qual ? h->qual : NULL, h->maxhit_per_tuple,
+  smb_ctx *c;
+  if (h->htp != g_root_htp) {
+    if (!g_aux && smb_ctx_create(&g_aux, shim_device())) return ERRCODE_FAILURE;
+    if (upload_index(g_aux, h->htp)) return ERRCODE_FAILURE;
+    g_aux_resident_serial = 0;
+  }
+  c = hitinfo_ctx(h);
+  if ((errcode = smb_arena_upload(c, h->codes, h->qlen))) return ERRCODE_FAILURE;
+  errcode = smb_seed_batch(c, &off, &h->qlen, 1, h->has_qual ? h->qual : NULL, h->maxhit_per_tuple,
 			   h->maxhit_total, h->basq, h->is_short, info, NULL, NULL, NULL, NULL, NULL, NULL);
   if (errcode) return ERRCODE_FAILURE;
   h->info = info[h->is_reverse ? 1 : 0];
-  g_resident_serial = h->serial;
+  if (c == g_root) g_resident_serial = h->serial; else g_aux_resident_serial = h->serial;
   return 0;
+}
+static int hitinfo_resident(const HashHitInfo *h)
+{
+  return (h->htp == g_root_htp) ? g_resident_serial == h->serial : g_aux_resident_serial == h->serial;
 }
 
 static int collect_info(HashHitInfo *h, int is_reverse, int is_short, uint32_t maxhit_per_tuple,
@@ -522,6 +570,12 @@ static int collect_info(HashHitInfo *h, int is_reverse, int is_short, uint32_t m
   int errcode;
   if (cod != SEQCOD_MANGLED) return ERRCODE_SEQCODE;
   if (smbShimInit(htp, NULL, NULL, NULL)) return ERRCODE_FAILURE;
+  h->htp = htp;
+  h->pool = NULL;
+  h->ktup = hashTableGetKtupLen(htp, &h->nskip);
+  if (fiber_pool_current() &&
+      fiber_seed_lookup(h, is_reverse, is_short, maxhit_per_tuple, maxhit_total, basq, seqp, htp))
+    return h->info.err;
   if (len + 1 > h->n_alloc) {
     h->codes = (unsigned char *) realloc(h->codes, (size_t) len + 64);
     h->qual = (unsigned char *) realloc(h->qual, (size_t) len + 64);
@@ -609,33 +663,37 @@ int smbShimHitListSet(HashHitList *p, const uint64_t *sqdat, int nhits, int is_r
   return 0;
 }
 
-int hashCollectHitsForSegment(HashHitList *hlp, SETSIZ_t segmoffs_lo, SETSIZ_t segmoffs_hi,
-			      HASHNUM_t nhit_max, unsigned char use_short_hitinfo,
-			      const HashHitInfo *hhip, const HashTable *htp, const HashHitFilter *hhfp)
+/* one hit list through the one-call contexts (mode: smb_hit_req.use_short) */
+static int collect_hits(HashHitList *hlp, uint64_t lo, uint64_t hi, uint32_t nhit_max, int mode, HashHitInfo *h)
 {
   smb_hit_req rq;
-  uint64_t first[2];
+  uint64_t first[2], qfirst[2];
   int32_t err = 0;
   size_t tot = 0;
-  int errcode;
-  HashHitInfo *h = (HashHitInfo *) hhip;
-  (void) htp;
-  if (hhfp) shim_die("hit filters (HashHitFilter) are not supported by the B200 path");
-  if (!h->serial) shim_die("hashCollectHitsForSegment on a wave-injected HashHitInfo");
+  int errcode, done = 0;
+  smb_ctx *c;
   if ((errcode = hitlist_qmask(hlp, h->qlen))) return errcode;
+  if (h->pool) {
+    errcode = fiber_hits(hlp, lo, hi, nhit_max, mode, h, &done);
+    if (done) return errcode;
+  }
+  if (!h->serial) shim_die("hit list requested for a HashHitInfo whose seed tables are not on the device");
   memset(&rq, 0, sizeof rq);
-  rq.lo = segmoffs_lo; rq.hi = segmoffs_hi; rq.read = 0; rq.nhit_max = nhit_max;
-  rq.strand = (uint8_t) (h->is_reverse != 0); rq.use_short = use_short_hitinfo;
+  rq.lo = lo; rq.hi = hi; rq.read = 0; rq.nhit_max = nhit_max;
+  rq.strand = (uint8_t) (h->is_reverse != 0); rq.use_short = (uint8_t) mode;
   pthread_mutex_lock(&g_lock);
-  if (g_resident_serial != h->serial) errcode = seed_one(h);
+  if (!hitinfo_resident(h)) errcode = seed_one(h);
+  c = hitinfo_ctx(h);
   if (!errcode) {
-    errcode = smb_hits_batch(g_root, &rq, 1, 0, hlp->own, hlp->own_alloc, &tot, first, &err);
+    errcode = smb_hits_batch(c, &rq, 1, 0, hlp->own, hlp->own_alloc, &tot, first, &err);
     if (errcode == SMB_ERR_CAPACITY && tot > hlp->own_alloc) {
       hlp->own = (uint64_t *) realloc(hlp->own, (tot + 1024) * sizeof(uint64_t));
       hlp->own_alloc = tot + 1024;
-      errcode = hlp->own ? smb_hits_batch(g_root, &rq, 1, 0, hlp->own, hlp->own_alloc, &tot, first, &err)
+      errcode = hlp->own ? smb_hits_batch(c, &rq, 1, 0, hlp->own, hlp->own_alloc, &tot, first, &err)
 	: ERRCODE_NOMEM;
     }
+    if (!errcode && mode == 2) /* seeds marked NORMHIT / MULTIHIT (hashhit.c:1632-1650) */
+      errcode = smb_hits_qmask(c, (uint8_t *) hlp->qmask, h->qlen, qfirst);
   }
   pthread_mutex_unlock(&g_lock);
   if (errcode) return ERRCODE_FAILURE;
@@ -647,13 +705,21 @@ int hashCollectHitsForSegment(HashHitList *hlp, SETSIZ_t segmoffs_lo, SETSIZ_t s
   return (err == SMB_ERRCODE_ALLOCBOUNDARY) ? ERRCODE_SUCCESS : err;
 }
 
+int hashCollectHitsForSegment(HashHitList *hlp, SETSIZ_t segmoffs_lo, SETSIZ_t segmoffs_hi,
+			      HASHNUM_t nhit_max, unsigned char use_short_hitinfo,
+			      const HashHitInfo *hhip, const HashTable *htp, const HashHitFilter *hhfp)
+{
+  (void) htp;
+  if (hhfp) shim_die("hit filters (HashHitFilter) are not supported by the B200 path");
+  return collect_hits(hlp, segmoffs_lo, segmoffs_hi, nhit_max, use_short_hitinfo ? 1 : 0, (HashHitInfo *) hhip);
+}
+
+/* whole-set list (rmap.c:320-346, >= 512 reference sequences): K1 mode 2 */
 int hashCollectHitsUsingCutoff(HashHitList *hlp, HASHNUM_t max_nhit_per_tup, const HashTable *htp,
 			       const HashHitInfo *hip)
 {
-  (void) hlp; (void) max_nhit_per_tup; (void) htp; (void) hip;
-  shim_die("whole-set hit lists (hashCollectHitsUsingCutoff, >= 512 reference sequences) are "
-	   "not supported by the B200 path yet");
-  return ERRCODE_FAILURE;
+  (void) htp;
+  return collect_hits(hlp, 0, 0, max_nhit_per_tup, 2, (HashHitInfo *) hip);
 }
 
 const uint64_t *hashGetHitListData(int *nhits, char *is_reverse, uint32_t *qlen, unsigned char *ktup,
@@ -667,3 +733,5 @@ const uint64_t *hashGetHitListData(int *nhits, char *is_reverse, uint32_t *qlen,
   if (nskip) *nskip = hlp->nskip;
   return hlp->sqdat;
 }
+
+#include "shim_fiber.inc.c"

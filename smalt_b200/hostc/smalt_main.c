@@ -34,6 +34,57 @@
 #include "shim.h"
 #include "../../include/smalt_b200_map.h"
 
+/* diagnostic sampling profiler (SMALT_B200_PROF=<file>): histogram of interrupted program
+ * counters relative to this library, resolved offline with addr2line */
+#include <signal.h>
+#include <sys/time.h>
+#include <dlfcn.h>
+#include <ucontext.h>
+#define PROF_SLOTS (1 << 16)
+static struct { uintptr_t pc; unsigned n; } g_prof[PROF_SLOTS];
+static void prof_handler(int sig, siginfo_t *si, void *ucv)
+{
+#if defined(__x86_64__)
+  const uintptr_t pc = (uintptr_t) ((ucontext_t *) ucv)->uc_mcontext.gregs[REG_RIP];
+  unsigned h = (unsigned) ((pc * 0x9E3779B97F4A7C15ull) >> 48), k;
+  for (k = 0; k < 64; k++, h = (h + 1) & (PROF_SLOTS - 1)) {
+    if (g_prof[h].pc == pc || !g_prof[h].pc) { g_prof[h].pc = pc; g_prof[h].n++; return; }
+  }
+#endif
+  (void) sig; (void) si;
+}
+static void prof_dump(void)
+{
+  const char *fn = getenv("SMALT_B200_PROF");
+  FILE *fp = fn ? fopen(fn, "w") : NULL;
+  Dl_info me;
+  unsigned i;
+  if (!fp) return;
+  dladdr((void *) prof_dump, &me);
+  for (i = 0; i < PROF_SLOTS; i++)
+    if (g_prof[i].n) {
+      Dl_info di;
+      const int ok = dladdr((void *) g_prof[i].pc, &di);
+      fprintf(fp, "%u %s 0x%lx %s\n", g_prof[i].n, (ok && di.dli_fname) ? di.dli_fname : "?",
+	      (unsigned long) (g_prof[i].pc - (ok ? (uintptr_t) di.dli_fbase : 0)), (ok && di.dli_sname) ? di.dli_sname : "?");
+    }
+  fclose(fp);
+}
+static void prof_start(void)
+{
+  struct sigaction sa;
+  struct itimerval it;
+  if (!getenv("SMALT_B200_PROF")) return;
+  memset(&sa, 0, sizeof sa);
+  sa.sa_sigaction = prof_handler;
+  sa.sa_flags = SA_SIGINFO | SA_RESTART;
+  sigaction(SIGPROF, &sa, NULL);
+  it.it_interval.tv_sec = 0; it.it_interval.tv_usec = 1000;
+  it.it_value = it.it_interval;
+  setitimer(ITIMER_PROF, &it, NULL);
+  atexit(prof_dump);
+}
+
 static THREAD_PROCF *g_ref_procf;
 static int fastmap_eligible(const SmaltMapConst *macop, const char **reason);
 static short g_blocksz = 2048;  /* reads per block of the reference queue path */
@@ -42,6 +93,8 @@ static double g_ms[3];
 static uint64_t g_counts[5];
 static double g_wall[11], g_cpu[8], g_wall_enc, g_t0;
 static double g_fm_parse_s, g_fm_format_s;
+static smbFiberStats g_fstats;
+static uint64_t g_pairs, g_pairs_fallback, g_pairs_p3, g_pairs_p4;
 
 typedef struct {
   RmapWave *wave;
@@ -80,7 +133,288 @@ static void flushStats(void)
 	  "\"score\": %.3f, \"replay\": %.3f, \"align\": %.3f, \"results\": %.3f, \"encode\": %.3f}}\n",
 	  g_wall[0], g_wall[1], g_wall[2], g_wall[3], g_wall[4], g_wall[5], g_wall[6], g_wall[7], g_wall_enc);
   fprintf(fp, "{\"parse_s\": %.3f}\n", g_fm_parse_s);
+  fprintf(fp, "{\"pairs\": %llu, \"pairs_by_reference_code\": %llu, \"pairs_third_pass\": %llu, \"pairs_fourth_pass\": %llu}\n",
+	  (unsigned long long) g_pairs, (unsigned long long) g_pairs_fallback, (unsigned long long) g_pairs_p3,
+	  (unsigned long long) g_pairs_p4);
+  fprintf(fp, "{\"fiber\": {\"items\": %llu, \"waves\": %llu, \"seeded\": %llu, \"seeds_served\": %llu, \"hits\": %llu, "
+	  "\"sw\": %llu, \"bandfast\": %llu, \"bandali\": %llu, \"order_waits\": %llu, \"wall_host_s\": %.3f, \"cpu_host_s\": %.3f, "
+	  "\"wall_hits_s\": %.3f, \"wall_dp_s\": %.3f, \"dp_stage_s\": %.3f, \"dp_arena_s\": %.3f, \"dp_sw_s\": %.3f, \"dp_ba_s\": %.3f}}\n",
+	  (unsigned long long) g_fstats.n_items, (unsigned long long) g_fstats.n_waves, (unsigned long long) g_fstats.n_seeded,
+	  (unsigned long long) g_fstats.seeds_served, (unsigned long long) g_fstats.n_hits, (unsigned long long) g_fstats.n_sw,
+	  (unsigned long long) g_fstats.n_bandfast, (unsigned long long) g_fstats.n_bandali,
+	  (unsigned long long) g_fstats.order_waits, g_fstats.wall_host, g_fstats.cpu_host, g_fstats.wall_hits, g_fstats.wall_dp,
+	  g_fstats.wall_stage, g_fstats.wall_arena, g_fstats.wall_sw, g_fstats.wall_ba);
   fclose(fp);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* fiber path: the reference's own per-item function for a whole block at once            */
+/* ------------------------------------------------------------------------------------ */
+/* Paired reads (rmapPair) and the modes the single-end wave path does not restate run the
+ * reference's processMapArgs (smalt.c:1083) unchanged - one fiber and one RMap per item in
+ * flight; the hot-path calls of all fibers are executed as GPU batches (shim_fiber.inc.c). */
+typedef struct {
+  SmbFiberPool *pool;
+  SmaltMapArgs *slot;       /* per fiber: a SmaltMapArgs with its own RMap (created on first use) */
+  SeqFastq **reads;
+  size_t reads_alloc;
+  const SmaltMapConst *macop;
+  ErrMsg *errmsgp;
+  SmaltArgBlock *blockp;
+  short threadno;
+  int errcode;
+  smbFiberStats prev;
+} FiberWorker;
+static __thread FiberWorker t_fw;
+
+static void fiber_item(void *user, int item, int slot)
+{
+  FiberWorker *fw = (FiberWorker *) user;
+  SmaltMapArgs *m = fw->slot + slot;
+  int errcode;
+  if (!m->rmp && (errcode = initMapArgs(m, fw->macop, fw->threadno))) {
+    if (!fw->errcode) fw->errcode = errcode;
+    return;
+  }
+  errcode = processMapArgs(fw->errmsgp, m, fw->blockp->iobfp + item);
+  if (errcode && !fw->errcode) fw->errcode = errcode;
+}
+
+static int fiber_block(ErrMsg *errmsgp, SmaltMapArgs *map, SmaltArgBlock *blockp)
+{
+  const SmaltMapConst *macop = map->smconstp;
+  FiberWorker *fw = &t_fw;
+  const int n = blockp->n_iobf;
+  int i, errcode, rpi = 1, nreads = 0;
+  smbFiberStats st;
+  if (n < 1) return ERRCODE_SUCCESS;
+  if (!fw->pool) {
+    const char *e = getenv("SMALT_B200_FIBERS");
+    long nf = e ? atol(e) : 512;
+    if (nf < 1) nf = 1;
+    if (nf > 16384) nf = 16384;
+    if (smbShimInit(macop->htp, macop->ssp, macop->codecp, macop->scormtxp)) return ERRCODE_FAILURE;
+    fw->pool = smbFiberPoolCreate((int) nf, 256 * 1024);
+    fw->slot = (SmaltMapArgs *) calloc((size_t) nf, sizeof(SmaltMapArgs));
+    if (!fw->pool || !fw->slot) return ERRCODE_NOMEM;
+  }
+  for (i = 0; i < n; i++) if (blockp->iobfp[i].isPaired) rpi = 2;
+  if ((size_t) n * rpi > fw->reads_alloc) {
+    free(fw->reads);
+    fw->reads_alloc = (size_t) n * rpi + 64;
+    if (!(fw->reads = (SeqFastq **) malloc(fw->reads_alloc * sizeof(SeqFastq *)))) return ERRCODE_NOMEM;
+  }
+  /* seed tables of the whole block up front: reads are encoded here (processMapArgs' own
+   * seqFastqEncode is then a no-op, sequence.c:1345) */
+  for (i = 0; i < n; i++) {
+    SmaltIOBuffArg *b = blockp->iobfp + i;
+    if ((errcode = seqFastqEncode(b->readp, macop->codecp))) { ERRMSGNO(errmsgp, errcode); return errcode; }
+    fw->reads[nreads++] = b->readp;
+    if (rpi == 2) {
+      if (b->isPaired) {
+	if ((errcode = seqFastqEncode(b->matep, macop->codecp))) { ERRMSGNO(errmsgp, errcode); return errcode; }
+	fw->reads[nreads++] = b->matep;
+      } else {
+	fw->reads[nreads++] = b->readp;
+      }
+    }
+  }
+  if ((errcode = smbFiberPoolSeed(fw->pool, nreads, fw->reads, rpi, !(macop->rmapflg & RMAPFLG_NOSHRTINFO),
+				  (uint32_t) macop->nhitmax_tuple, 16384 /* HASH_MAXNHITS, rmap.c:50 */, macop->minbasq, macop->htp)))
+    return errcode;
+  fw->macop = macop; fw->errmsgp = errmsgp; fw->blockp = blockp; fw->threadno = map->threadno;
+  fw->errcode = ERRCODE_SUCCESS;
+  if ((errcode = smbFiberPoolRun(fw->pool, n, fiber_item, fw))) return errcode;
+  smbFiberPoolGetStats(fw->pool, &st);
+  pthread_mutex_lock(&g_stats_lock);
+  g_fstats.n_items += st.n_items - fw->prev.n_items; g_fstats.n_waves += st.n_waves - fw->prev.n_waves;
+  g_fstats.n_hits += st.n_hits - fw->prev.n_hits; g_fstats.n_sw += st.n_sw - fw->prev.n_sw;
+  g_fstats.n_bandfast += st.n_bandfast - fw->prev.n_bandfast; g_fstats.n_bandali += st.n_bandali - fw->prev.n_bandali;
+  g_fstats.order_waits += st.order_waits - fw->prev.order_waits;
+  g_fstats.seeds_served += st.seeds_served - fw->prev.seeds_served;
+  g_fstats.n_seeded += st.n_seeded - fw->prev.n_seeded;
+  g_fstats.cells_k2 += st.cells_k2 - fw->prev.cells_k2; g_fstats.cells_k3 += st.cells_k3 - fw->prev.cells_k3;
+  g_fstats.ms_k1 += st.ms_k1 - fw->prev.ms_k1; g_fstats.ms_k2 += st.ms_k2 - fw->prev.ms_k2;
+  g_fstats.ms_k3 += st.ms_k3 - fw->prev.ms_k3;
+  g_fstats.wall_host += st.wall_host - fw->prev.wall_host; g_fstats.wall_hits += st.wall_hits - fw->prev.wall_hits;
+  g_fstats.wall_dp += st.wall_dp - fw->prev.wall_dp; g_fstats.cpu_host += st.cpu_host - fw->prev.cpu_host;
+  g_fstats.wall_stage += st.wall_stage - fw->prev.wall_stage; g_fstats.wall_arena += st.wall_arena - fw->prev.wall_arena;
+  g_fstats.wall_sw += st.wall_sw - fw->prev.wall_sw; g_fstats.wall_ba += st.wall_ba - fw->prev.wall_ba;
+  g_ms[0] += st.ms_k1 - fw->prev.ms_k1; g_ms[1] += st.ms_k2 - fw->prev.ms_k2; g_ms[2] += st.ms_k3 - fw->prev.ms_k3;
+  g_counts[0] += (uint64_t) nreads; g_counts[1] += st.n_sw - fw->prev.n_sw; g_counts[2] += st.cells_k2 - fw->prev.cells_k2;
+  g_counts[3] += st.n_bandali - fw->prev.n_bandali; g_counts[4] += st.cells_k3 - fw->prev.cells_k3;
+  pthread_mutex_unlock(&g_stats_lock);
+  fw->prev = st;
+  return fw->errcode;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* paired reads: wave passes for the common course of a pair, fibers for the rest          */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+  SeqFastq **reads;
+  uint32_t *mincov;
+  unsigned char *status;
+  int *fb_item, *fb_slot;
+  size_t alloc;
+  SmbFiberPool *pool;
+  SmaltMapArgs *slot;
+  int nslot;
+  const SmaltMapConst *macop;
+  ErrMsg *errmsgp;
+  SmaltArgBlock *blockp;
+  short threadno;
+  int errcode;
+  smbFiberStats prev;
+  uint64_t p3_prev, p4_prev;
+} PairWorker;
+static __thread PairWorker t_pw;
+
+static uint32_t covermin_of(const SmaltMapConst *macop, const SeqFastq *sqp, uint32_t cov_read, int is_mate)
+{ /* processMapArgs, smalt.c:1112-1147 */
+  uint32_t len, c;
+  if (!(macop->tupcovmin < 1.01)) return is_mate ? cov_read : (uint32_t) macop->tupcovmin;
+  seqFastqGetConstSequence(sqp, &len, NULL);
+  c = (uint32_t) (macop->tupcovmin * len);
+  return c > len ? len : c;
+}
+
+/* rmapPair exactly as processMapArgs (smalt.c:1149-1167) calls it, on the RMap of a fiber slot */
+static void pair_fallback_item(void *user, int k, int slot)
+{
+  PairWorker *pw = (PairWorker *) user;
+  SmaltMapArgs *m = pw->slot + slot;
+  const SmaltMapConst *macop = pw->macop;
+  SmaltIOBuffArg *brgp = pw->blockp->iobfp + pw->fb_item[k];
+  const int i = pw->fb_item[k];
+  int errcode;
+  pw->fb_slot[k] = slot;
+  if (!m->rmp && (errcode = initMapArgs(m, macop, pw->threadno))) {
+    if (!pw->errcode) pw->errcode = errcode;
+    return;
+  }
+  ERRMSG_READNO(pw->errmsgp, brgp->readno + 1);
+  ERRMSG_READNAM(pw->errmsgp, seqFastqGetSeqName(brgp->readp));
+  rmapPair(pw->errmsgp, m->rmp, brgp->readp, brgp->matep, &brgp->pairflg,
+	   macop->insert_min, macop->insert_max, macop->pairtyp, macop->nhitmax_tuple,
+	   (int) pw->mincov[2 * i], (int) pw->mincov[2 * i + 1], macop->min_swatscor, macop->minbasq,
+	   SMALT_TARGET_DEPTH, SMALT_MAX_DEPTH, (RMAPFLG_t) (macop->rmapflg | RMAPFLG_PAIRED),
+	   macop->scormtxp, macop->rfp, macop->htp, macop->ssp, macop->codecp);
+}
+
+static int pair_block(ErrMsg *errmsgp, SmaltMapArgs *map, SmaltArgBlock *blockp)
+{
+  const SmaltMapConst *macop = map->smconstp;
+  PairWorker *pw = &t_pw;
+  const int n = blockp->n_iobf;
+  int i, k, nfb = 0, errcode;
+  for (i = 0; i < n; i++)
+    if (!blockp->iobfp[i].isPaired) return fiber_block(errmsgp, map, blockp);
+  if (macop->tupcovmin < 0) return ERRCODE_ASSERT;
+  if (!t_ws.wave) {
+    t_ws.wave = rmapWaveCreate(macop->htp, macop->ssp, macop->codecp, macop->scormtxp);
+    if (!t_ws.wave) {
+      fprintf(stderr, "smalt_b200: cannot set up the GPU context of a worker thread\n");
+      return ERRCODE_FAILURE;
+    }
+  }
+  if ((size_t) n > pw->alloc) {
+    const size_t na = (size_t) n + 64;
+    pw->reads = (SeqFastq **) realloc(pw->reads, 2 * na * sizeof(SeqFastq *));
+    pw->mincov = (uint32_t *) realloc(pw->mincov, 2 * na * sizeof(uint32_t));
+    pw->status = (unsigned char *) realloc(pw->status, na);
+    pw->fb_item = (int *) realloc(pw->fb_item, na * sizeof(int));
+    pw->fb_slot = (int *) realloc(pw->fb_slot, na * sizeof(int));
+    if (!pw->reads || !pw->mincov || !pw->status || !pw->fb_item || !pw->fb_slot) return ERRCODE_NOMEM;
+    pw->alloc = na;
+  }
+  for (i = 0; i < n; i++) {
+    SmaltIOBuffArg *b = blockp->iobfp + i;
+    if ((errcode = seqFastqEncode(b->readp, macop->codecp)) || (errcode = seqFastqEncode(b->matep, macop->codecp))) {
+      ERRMSGNO(errmsgp, errcode);
+      return errcode;
+    }
+    pw->reads[2 * i] = b->readp;
+    pw->reads[2 * i + 1] = b->matep;
+    pw->mincov[2 * i] = covermin_of(macop, b->readp, 0, 0);
+    pw->mincov[2 * i + 1] = covermin_of(macop, b->matep, pw->mincov[2 * i], 1);
+  }
+  errcode = rmapPairWave(errmsgp, map->rmp, t_ws.wave, n, pw->reads, pw->mincov, macop->insert_min, macop->insert_max,
+			 macop->pairtyp, macop->nhitmax_tuple, macop->min_swatscor, macop->minbasq,
+			 SMALT_TARGET_DEPTH, SMALT_MAX_DEPTH, (RMAPFLG_t) (macop->rmapflg | RMAPFLG_PAIRED),
+			 macop->scormtxp, macop->htp, macop->ssp, macop->codecp, pw->status);
+  if (errcode == ERRCODE_ARGINVAL) return fiber_block(errmsgp, map, blockp);
+  if (errcode) return errcode;
+  /* pairs that left the common course: the reference's rmapPair, one fiber slot each (the slot's
+   * RMap keeps the results until they are reported below) */
+  for (i = 0; i < n; i++) if (pw->status[i] != RMAPPAIR_DONE) pw->fb_item[nfb++] = i;
+  if (nfb) {
+    if (nfb > pw->nslot) {
+      const int ns = nfb + 64;
+      SmaltMapArgs *hp = (SmaltMapArgs *) realloc(pw->slot, (size_t) ns * sizeof(SmaltMapArgs));
+      if (!hp) return ERRCODE_NOMEM;
+      memset(hp + pw->nslot, 0, (size_t) (ns - pw->nslot) * sizeof(SmaltMapArgs));
+      pw->slot = hp;
+      pw->nslot = ns;
+      smbFiberPoolDelete(pw->pool);
+      if (!(pw->pool = smbFiberPoolCreate(ns, 256 * 1024))) return ERRCODE_NOMEM;
+      memset(&pw->prev, 0, sizeof(pw->prev));
+    }
+    for (k = 0; k < nfb; k++) {
+      pw->reads[2 * k] = blockp->iobfp[pw->fb_item[k]].readp;     /* (the wave is done with the array) */
+      pw->reads[2 * k + 1] = blockp->iobfp[pw->fb_item[k]].matep;
+    }
+    if ((errcode = smbFiberPoolSeed(pw->pool, 2 * nfb, pw->reads, 2, !(macop->rmapflg & RMAPFLG_NOSHRTINFO),
+				    (uint32_t) macop->nhitmax_tuple, 16384 /* HASH_MAXNHITS, rmap.c:50 */,
+				    macop->minbasq, macop->htp)))
+      return errcode;
+    pw->macop = macop; pw->errmsgp = errmsgp; pw->blockp = blockp; pw->threadno = map->threadno;
+    pw->errcode = ERRCODE_SUCCESS;
+    if ((errcode = smbFiberPoolRun(pw->pool, nfb, pair_fallback_item, pw)) || (errcode = pw->errcode)) return errcode;
+  }
+  /* reports in input order (the random draws among equally good placements happen here,
+   * resultpairs.c:896-927): tail of processMapArgs, smalt.c:1168-1184 */
+  for (i = 0, k = 0; i < n; i++) {
+    SmaltIOBuffArg *brgp = blockp->iobfp + i;
+    const ResultSet *rsltp, *rslt_matep;
+    const ResultPairs *pairp;
+    if (pw->status[i] == RMAPPAIR_DONE) {
+      RSLTPAIRFLG_t pairflg;
+      ERRMSG_READNO(errmsgp, brgp->readno + 1);
+      ERRMSG_READNAM(errmsgp, seqFastqGetSeqName(brgp->readp));
+      if ((errcode = rmapPairWaveFinish(errmsgp, map->rmp, t_ws.wave, i, macop->insert_min, macop->insert_max,
+					macop->pairtyp, macop->rfp, brgp->readp, brgp->matep, &rsltp, &rslt_matep,
+					&pairp, &pairflg)))
+	return errcode;
+      brgp->pairflg = pairflg;
+    } else {
+      rmapGetData(&rsltp, &rslt_matep, &pairp, NULL, NULL, pw->slot[pw->fb_slot[k++]].rmp);
+    }
+    errcode = resultSetAddPairToReport(brgp->rep, macop->ihp, pairp, brgp->pairflg, macop->rsltouflg, rsltp, rslt_matep);
+    if (errcode) ERRMSGNO(errmsgp, errcode);
+    if (MENU_SAMPLE == macop->subprogtyp &&
+	ERRCODE_SUCCESS == resultSetInferInsertSize(&brgp->isiz, RSLTSAMSPEC_V1P4, rsltp, rslt_matep))
+      brgp->pairflg |= RSLTPAIRFLG_INSERTSIZ;
+  }
+  {
+    double ms[3], wall[11];
+    uint64_t counts[5];
+    rmapWaveGetStats(t_ws.wave, ms, counts);
+    rmapWaveGetWall(t_ws.wave, wall);
+    pthread_mutex_lock(&g_stats_lock);
+    for (i = 0; i < 11; i++) { g_wall[i] += wall[i] - t_ws.wall_prev[i]; t_ws.wall_prev[i] = wall[i]; }
+    for (i = 0; i < 3; i++) { g_ms[i] += ms[i] - t_ws.ms_prev[i]; t_ws.ms_prev[i] = ms[i]; }
+    for (i = 0; i < 5; i++) { g_counts[i] += counts[i] - t_ws.counts_prev[i]; t_ws.counts_prev[i] = counts[i]; }
+    g_pairs += (uint64_t) n; g_pairs_fallback += (uint64_t) nfb;
+    {
+      uint64_t pc[4];
+      rmapWaveGetPairStats(t_ws.wave, pc);
+      g_pairs_p3 += pc[2] - t_pw.p3_prev; t_pw.p3_prev = pc[2];
+      g_pairs_p4 += pc[3] - t_pw.p4_prev; t_pw.p4_prev = pc[3];
+    }
+    pthread_mutex_unlock(&g_stats_lock);
+  }
+  return ERRCODE_SUCCESS;
 }
 
 /* THREAD_PROCF replacing processArgBlock (smalt.c:1221) */
@@ -99,7 +433,8 @@ static int smb_processArgBlock(ErrMsg *errmsgp, void *targp, void *bufargp)
 
   for (i = 0; i < n; i++)
     if (blockp->iobfp[i].isPaired)
-      return (*g_ref_procf)(errmsgp, targp, bufargp);
+      return getenv("SMALT_B200_ONECALL") ? (*g_ref_procf)(errmsgp, targp, bufargp) :
+	(getenv("SMALT_B200_FIBERS_ONLY") ? fiber_block(errmsgp, map, blockp) : pair_block(errmsgp, map, blockp));
   if (macop->tupcovmin < 0)
     return ERRCODE_ASSERT;
   if (!t_ws.wave && !getenv("SMALT_B200_IOTEST")) {
@@ -153,8 +488,8 @@ static int smb_processArgBlock(ErrMsg *errmsgp, void *targp, void *bufargp)
 			   SMALT_TARGET_DEPTH, SMALT_MAX_DEPTH, (RMAPFLG_t) (macop->rmapflg & ~RMAPFLG_ALLPAIR),
 			   macop->scormtxp, macop->rfp, macop->htp, macop->ssp, macop->codecp,
 			   emitResult, &ea);
-  if (errcode == ERRCODE_ARGINVAL) /* mode not covered by the wave path */
-    return (*g_ref_procf)(errmsgp, targp, bufargp);
+  if (errcode == ERRCODE_ARGINVAL) /* mode not restated by the wave path: the reference's own per-read code on fibers */
+    return getenv("SMALT_B200_ONECALL") ? (*g_ref_procf)(errmsgp, targp, bufargp) : fiber_block(errmsgp, map, blockp);
   rmapWaveGetStats(t_ws.wave, ms, counts);
   rmapWaveGetWall(t_ws.wave, wall);
   pthread_mutex_lock(&g_stats_lock);
@@ -521,6 +856,7 @@ int smalt_b200_cli_main(int argc, char *argv[])
   clock_gettime(CLOCK_MONOTONIC, &ts);
   g_t0 = ts.tv_sec + 1e-9 * ts.tv_nsec;
   atexit(flushStats);
+  prof_start();
   /* CUDA start-up (~0.7 s) overlaps the reference's option parsing and index loading */
   if (argc > 1 && (!strcmp(argv[1], "map") || !strcmp(argv[1], "sample")) && !getenv("SMALT_B200_NOWARM"))
     warming = !pthread_create(&warm, NULL, gpu_warmup_main, NULL);
@@ -533,6 +869,7 @@ int smalt_b200_cli_main(int argc, char *argv[])
   /* everything is written and closed by the reference's own clean-up; skip the CUDA runtime's
    * atexit tear-down (~0.3 s) */
   flushStats();
+  prof_dump();
   fflush(NULL);
   _exit(rv);
 }
