@@ -100,6 +100,9 @@ def load_library():
     lib.smb_hits_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_size_t,
                                    C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p]
     lib.smb_hits_qmask.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.smb_seed_batch_tables.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                          C.c_void_p]
     _lib = lib
     return lib
 
@@ -194,6 +197,31 @@ class Context:
         self._check(self.lib.smb_seed_batch(self._h, _vp(read_off), _vp(read_len), n, q, maxhit_per_tuple,
                                             maxhit_total, basq_thresh, int(short_info), _vp(info), *ptrs))
         return info, tabs
+
+    def seed_batch_tables(self, tables, read_table, read_off, read_len, qual=None, maxhit_per_tuple=0,
+                          maxhit_total=0, basq_thresh=0, short_info=False):
+        """Seed tables against per-read small perfect-hash indexes (dicts as made by indexer.build_index with
+        typ 0, all of one k / nskip): read r uses tables[read_table[r]].  -> info[2*n]"""
+        class Small(C.Structure):
+            _fields_ = [("idx", C.c_void_p), ("pos", C.c_void_p), ("npos", C.c_uint32)]
+        k, s = tables[0]["wordlen"], tables[0]["nskip"]
+        keep, arr = [], (Small * len(tables))()
+        for i, t in enumerate(tables):
+            assert t["typ"] == 0 and t["wordlen"] == k and t["nskip"] == s
+            idx = np.ascontiguousarray(t["idx"], np.uint32)
+            pos = np.ascontiguousarray(t["pos"], np.uint32)
+            keep += [idx, pos]
+            arr[i].idx, arr[i].pos, arr[i].npos = idx.ctypes.data, pos.ctypes.data, int(t["npos"])
+        read_table = np.ascontiguousarray(read_table, np.uint32)
+        read_off = np.ascontiguousarray(read_off, np.uint64)
+        read_len = np.ascontiguousarray(read_len, np.uint32)
+        n = len(read_len)
+        info = np.zeros(2 * n, SEED_INFO_DTYPE)
+        q = None if qual is None else _vp(np.ascontiguousarray(qual, np.uint8))
+        self._check(self.lib.smb_seed_batch_tables(self._h, k, s, C.cast(arr, C.c_void_p), len(tables), _vp(read_table),
+                                                   _vp(read_off), _vp(read_len), n, q, maxhit_per_tuple, maxhit_total,
+                                                   basq_thresh, int(short_info), _vp(info)))
+        return info
 
     def hits_batch(self, req, nhits_alloc=0, max_hits=None):
         """-> (sqdat uint64, list_first[nreq+1], errs) for HIT_REQ_DTYPE requests"""

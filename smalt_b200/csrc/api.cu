@@ -153,7 +153,7 @@ int smb_device_warmup(int device) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return SMB_ERR_NODEVICE;
   if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) return SMB_ERR_CUDA;
-  if (warm_sw() != cudaSuccess || warm_band() != cudaSuccess || warm_band_warp() != cudaSuccess || warm_band_pack() != cudaSuccess ||
+  if (warm_sw() != cudaSuccess || warm_band() != cudaSuccess || warm_band_warp() != cudaSuccess || warm_band_wide() != cudaSuccess || warm_band_pack() != cudaSuccess ||
       warm_seed() != cudaSuccess ||
       warm_compact() != cudaSuccess)
     return SMB_ERR_CUDA;
@@ -493,6 +493,8 @@ static int band_align_fast(smb_ctx *ctx, const smb_band_task *tasks, int ntasks,
     uint64_t words = 2;
     if (!band_warp_eligible(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
                             (int)t.ref_len) &&
+        !band_wide_eligible(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
+                            (int)t.ref_len) &&
         !band_init(b, t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
                    (int)t.ref_len)) {
       const int bw0 = t.r_edge - t.l_edge + 1;
@@ -562,6 +564,18 @@ static int band_align_fast(smb_ctx *ctx, const smb_band_task *tasks, int ntasks,
   ctx->last_launches += nl;
   ctx->total_launches += nl;
   g_launches += nl;
+  if (getenv("SMB_PLAN_DEBUG")) {
+    int mxbw = 0, mxrows = 0, mxread = 0;
+    for (int i = 0; i < n; ++i) {
+      mxbw = std::max(mxbw, tasks[i].r_edge - tasks[i].l_edge + 1);
+      mxrows = std::max(mxrows, (int)tasks[i].ref_len);
+      mxread = std::max(mxread, (int)tasks[i].read_len);
+    }
+    fprintf(stderr, "K3 plan: n %d pack %d half %d warp %d wide %d thread-classes %zu (", n, plan.pack_count, plan.half_count,
+            plan.warp_count, plan.wide_count, plan.classes.size());
+    for (const auto &c : plan.classes) fprintf(stderr, " wcap %d x %d", c.wcap, c.count);
+    fprintf(stderr, " ) max band %d rows %d read %d  %.3f ms\n", mxbw, mxrows, mxread, ms0);
+  }
   if (h_tot->capacity_flag) return 1;
   const size_t nr = (size_t)h_tot->nresults, nd = (size_t)h_tot->ndiff;
   if (ncells) *ncells = *h_cells;

@@ -68,6 +68,19 @@ SMB_HD int band_warp_lanes(int l_edge, int r_edge, int p_left, int p_right, int 
   const int bw = (bw0 <= 0) ? (b.q_len - b.q_left) : bw0;
   return bw <= BW_MAXDIAG / 2 ? 16 : (bw <= BW_MAXDIAG ? 32 : 0);
 }
+// band_wide_kernel (band_wide.cu): four diagonals per lane, longer windows
+constexpr int BWD_MAXROWS = 512;
+constexpr int BWD_MAXREAD = 512;
+constexpr int BWD_MAXDIAG = 128;
+SMB_HD bool band_wide_eligible(int l_edge, int r_edge, int p_left, int p_right, int read_len,
+                               int u_left, int u_right, int ref_len) {
+  if (ref_len > BWD_MAXROWS || read_len > BWD_MAXREAD || ref_len < 1 || read_len < 1) return false;
+  Band b;
+  if (band_init(b, l_edge, r_edge, p_left, p_right, read_len, u_left, u_right, ref_len)) return true;
+  const int bw0 = r_edge - l_edge + 1;
+  const int bw = (bw0 <= 0) ? (b.q_len - b.q_left) : bw0;
+  return bw <= BWD_MAXDIAG;
+}
 SMB_HD bool band_warp_eligible(int l_edge, int r_edge, int p_left, int p_right, int read_len,
                                int u_left, int u_right, int ref_len) {
   return band_warp_lanes(l_edge, r_edge, p_left, p_right, read_len, u_left, u_right, ref_len) != 0;

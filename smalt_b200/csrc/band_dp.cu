@@ -329,11 +329,12 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, const Scori
   std::vector<int> wc((size_t)ntasks);
   int count[32] = {0};
   auto cls = [](int wcap) { int c = 0; while ((32 << c) < wcap) ++c; return c; };
-  constexpr int WARP_CLS = 31, HALF_CLS = 30, PACK_CLS = 29;  // pseudo classes of the warp kernels (last in `order`)
+  constexpr int WARP_CLS = 31, HALF_CLS = 30, PACK_CLS = 29, WIDE_CLS = 28;  // pseudo classes of the warp kernels (last in `order`)
   // packed 16-bit kernel: scores must stay far below 2^15 (band_pack.cu)
   const bool pen16 = sc.match > 0 && sc.match < 128 && sc.mismatch <= 0 && sc.mismatch > -128 && sc.gap_init >= 0 &&
                      sc.gap_init < 4000 && sc.gap_ext >= 0 && sc.gap_ext < 4000 && sc.S[5] == 0 && sc.S[5 * 8] == 0 &&
                      !getenv("SMB_NO_PACK");
+  const bool no_wide = getenv("SMB_NO_WIDE") != nullptr;
   plan.pack_maxrows = 0;
   for (int i = 0; i < ntasks; ++i) {
     const smb_band_task &t = h_tasks[i];
@@ -344,6 +345,10 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, const Scori
       plan.pack_maxrows = std::max(plan.pack_maxrows, (int)t.ref_len);
     } else if (wl) {
       wc[(size_t)i] = wl == 16 ? HALF_CLS : WARP_CLS;
+    } else if (align && !no_wide &&
+               band_wide_eligible(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
+                                  (int)t.ref_len)) {
+      wc[(size_t)i] = WIDE_CLS;
     } else {
       const int need = ring_need(t, !align);
       wc[(size_t)i] = cls(pow2_at_least(need + 1));
@@ -356,8 +361,10 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, const Scori
   int fill[32];
   for (int c = 0; c < 32; ++c) fill[c] = start[c];
   for (int i = 0; i < ntasks; ++i) plan.order[(size_t)fill[wc[(size_t)i]]++] = i;
-  for (int c = 0; c < PACK_CLS; ++c)
+  for (int c = 0; c < WIDE_CLS; ++c)
     if (count[c]) plan.classes.push_back(BandPlan::Class{32 << c, start[c], count[c]});
+  plan.wide_start = start[WIDE_CLS];
+  plan.wide_count = count[WIDE_CLS];
   plan.pack_start = start[PACK_CLS];
   plan.pack_count = count[PACK_CLS];
   plan.half_start = start[HALF_CLS];
@@ -396,6 +403,10 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++*nlaunch;
   }
+  if (align && plan.wide_count &&
+      (e = launch_band_wide(sc, src, d_tasks, d_order + plan.wide_start, plan.wide_count, d_ticket + 3, out, max_res,
+                            d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)
+    return e;
   if (align && plan.pack_count &&
       (e = launch_band_pack(sc, src, d_tasks, d_order + plan.pack_start, plan.pack_count, plan.pack_maxrows, d_ticket + 2,
                             out, max_res, d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)

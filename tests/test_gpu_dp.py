@@ -288,3 +288,56 @@ def test_band_align_packed_kernel_geometry(ctx, orc):
             assert int(errs[k]) == e, (i, args[i])
             assert _unpack(res, first, diff, k) == want, (i, len(rd), len(win), args[i], minscore[i], minscorlen[i])
         assert cells == ocells
+
+
+def test_band_align_wide_kernel_geometry(ctx, orc):
+    """Geometries of the four-diagonals-per-lane kernel (band_wide.cu): bands of 33..128 diagonals
+    (also beyond: thread-per-task kernel), windows of up to 512 rows, reads of up to 512 bases,
+    several local alignments per window (recursion), batches of one."""
+    from seqgen import mutate
+    rng = np.random.default_rng(106)
+    pairs, args = [], []
+    for rows in (120, 255, 256, 257, 300, 383, 384, 385, 500, 511, 512, 513):
+        for bw in (33, 64, 65, 66, 97, 127, 128, 129):
+            qlen = int(rng.integers(60, min(rows, 512) + 1))
+            if rows % 7 == 0:
+                qlen = min(rows, 512)
+            rd = random_seq(rng, qlen)
+            off = int(rng.integers(0, max(1, rows - qlen)))
+            win = random_seq(rng, rows)
+            m = mutate(rng, rd.copy(), p_sub=0.04, p_ins=0.02, p_del=0.02)[:rows - off]
+            win[off:off + len(m)] = m
+            if (rows + bw) % 3 == 0:          # two separate pieces: several results, recursion left/right
+                cut = len(m) // 2
+                win[off + cut:off + cut + 25] = random_seq(rng, min(25, rows - off - cut))
+            if (rows + bw) % 5 == 0:
+                win[int(rng.integers(0, rows))] = 5
+                rd[int(rng.integers(0, qlen))] = 5
+            pairs.append((rd, win))
+            l = -off - bw // 2 + int(rng.integers(-6, 7))
+            args.append((l, l + bw - 1, 0, qlen - 1, 0, rows - 1))
+    order = rng.permutation(len(pairs))
+    pairs = [pairs[i] for i in order]
+    args = [args[i] for i in order]
+    minscore = [int(x) for x in rng.integers(1, 30, len(pairs))]
+    minscorlen = [int(x) for x in rng.integers(5, 25, len(pairs))]
+    arena, offs = _arena(pairs)
+    ctx.arena_upload(arena)
+    nmulti = 0
+    for sel in (slice(None), slice(0, 1), slice(2, 7)):
+        idx = list(range(len(pairs)))[sel]
+        sub_pairs = [pairs[i] for i in idx]
+        sub_offs = np.concatenate([[offs[2 * i], offs[2 * i + 1]] for i in idx] + [[0]])
+        t = _band_tasks(sub_pairs, sub_offs, [args[i] for i in idx], [minscore[i] for i in idx],
+                        [minscorlen[i] for i in idx])
+        res, first, diff, errs, cells = ctx.band_align(t)
+        ocells = 0
+        for k, i in enumerate(idx):
+            rd, win = pairs[i]
+            e, want, c = orc.band_align(rd, win, *args[i], minscore[i], minscorlen[i])
+            ocells += c
+            assert int(errs[k]) == e, (i, args[i])
+            assert _unpack(res, first, diff, k) == want, (i, len(rd), len(win), args[i], minscore[i], minscorlen[i])
+            nmulti += len(want) > 1
+        assert cells == ocells
+    assert nmulti > 5

@@ -1,0 +1,83 @@
+"""Paired-end mapping (rmapPair, rmap.c:1744-2112) through the paired wave scheduler
+(rmap_wave.c: four block-wide passes incl. the rescue with per-pair on-the-fly indexes on the
+device) and through the fiber scheduler (reference per-item code, hot-path calls batched):
+SAM identical to the reference's CPU smalt, line by line, with one worker and a fixed draw seed."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from oracle_lib import ROOT, ref_binary
+
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import paired_check as pc  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+needs = pytest.mark.skipif(ref_binary("smalt") is None or not os.path.exists(pc.B200),
+                           reason="needs oracle/_ref and smalt_b200/bin")
+
+
+def _both(tmp, args, env=None):
+    ref, _ = pc.run(pc.REF, args, os.path.join(tmp, "ref.sam"))
+    stats = os.path.join(tmp, "stats.json")
+    got, _ = pc.run(pc.B200, args, os.path.join(tmp, "b200.sam"), dict(env or {}, SMALT_B200_STATS=stats))
+    st = {}
+    for line in open(stats):
+        st.update(json.loads(line))
+    return ref, got, st
+
+
+def _same(ref, got):
+    assert len(ref) == len(got)
+    diff = [(a, b) for a, b in zip(ref, got) if a != b]
+    assert not diff, "%d differing SAM lines, first:\n%s\n%s" % (len(diff), diff[0][0], diff[0][1])
+
+
+@needs
+def test_pairs_wave_all_passes(tmp_path):
+    """repeats, unmappable mates on either side: every pass of the scheduler is taken"""
+    tmp = str(tmp_path)
+    pref, f1, f2 = pc.make(tmp, 6000, 2.0, 3, seed=11)
+    ref, got, st = _both(tmp, ["-n", "1", "-i", "600", "-j", "200", pref, f1, f2])
+    _same(ref, got)
+    assert st["pairs"] == 6000 and st["pairs_third_pass"] > 100 and st["pairs_fourth_pass"] > 100
+    assert st["pairs_by_reference_code"] < 60
+    proper = sum(1 for l in ref if not l.startswith("@") and int(l.split("\t")[1]) & 2)
+    assert proper > 9000
+
+
+@needs
+def test_pairs_fibers_only(tmp_path):
+    """the same through the fiber scheduler alone (reference rmapPair on fibers)"""
+    tmp = str(tmp_path)
+    pref, f1, f2 = pc.make(tmp, 1500, 1.0, 2, seed=12)
+    ref, got, st = _both(tmp, ["-n", "1", "-i", "600", "-j", "200", pref, f1, f2],
+                         {"SMALT_B200_FIBERS_ONLY": "1", "SMALT_B200_FIBERS": "256"})
+    _same(ref, got)
+    assert st["fiber"]["items"] == 1500 and st["fiber"]["hits"] > 0 and st["fiber"]["bandali"] > 0
+
+
+@needs
+def test_pairs_exhaustive_option(tmp_path):
+    """-x (RMAPFLG_ALLPAIR | NOSHRTINFO: full seed tables, every pair searched both ways) is not
+    restated by the wave passes: fibers"""
+    tmp = str(tmp_path)
+    pref, f1, f2 = pc.make(tmp, 400, 0.5, 2, seed=13)
+    ref, got, st = _both(tmp, ["-n", "1", "-x", "-i", "600", "-j", "200", pref, f1, f2])
+    _same(ref, got)
+    assert st["fiber"]["items"] == 400
+
+
+@needs
+def test_many_reference_sequences(tmp_path):
+    """>= 512 reference sequences: whole-set hit lists (hashCollectHitsUsingCutoff, K1 mode 2),
+    single-end reads through the fibers"""
+    tmp = str(tmp_path)
+    pref, f1, f2 = pc.make(tmp, 1200, 1.2, 600, seed=14, repeats=False)
+    ref, got, st = _both(tmp, ["-n", "1", pref, f1])
+    _same(ref, got)
+    assert st["fiber"]["items"] == 1200
+    mapped = sum(1 for l in ref if not l.startswith("@") and not int(l.split("\t")[1]) & 4)
+    assert mapped > 1000

@@ -172,3 +172,54 @@ def test_hits_cutoff_vs_oracle(ctx, kind):
                 n += 1
         if kind == "repeat" and nhit_max == 0:
             assert big > 5000
+
+
+def test_seed_batch_tables_vs_oracle(ctx):
+    """per-read on-the-fly indexes (k=5 s=1 perfect hash, rmap.c:495-517): seed statistics of every
+    read against its own table, then restricted hit lists (full seed table, hashhit.c:1691-1769)"""
+    from smalt_b200.capi import HIT_REQ_DTYPE, pack_sequences
+    rng = np.random.default_rng(77)
+    orc = Oracle()
+    tables, oixs, gens = [], [], []
+    for t in range(9):
+        g = [random_seq(rng, int(rng.integers(900, 2600)))]
+        ixd = indexer.build_index(g, 5, 1)
+        assert ixd["typ"] == 0
+        tables.append(ixd)
+        oixs.append(orc.make_index(indexer.as_loaded(ixd)))
+        gens.append(g)
+    reads, rt = [], []
+    for r in range(60):
+        t = int(rng.integers(0, len(tables)))
+        reads.append(sample_read(rng, gens[t], int(rng.integers(30, 200))))
+        rt.append(t)
+    reads.append(random_seq(rng, 4)); rt.append(0)     # shorter than k
+    arena, offs = pack_sequences(reads)
+    lens_r = np.array([len(r) for r in reads], np.uint32)
+    ctx.arena_upload(arena)
+    info = ctx.seed_batch_tables(tables, rt, offs[:-1], lens_r)
+    req = np.zeros(2 * len(reads), HIT_REQ_DTYPE)
+    for r in range(len(reads)):
+        L = len(gens[rt[r]][0])
+        for s in (0, 1):
+            req[2 * r + s]["lo"], req[2 * r + s]["hi"] = L // 5, L - L // 7
+            req[2 * r + s]["read"], req[2 * r + s]["strand"] = r, s
+            req[2 * r + s]["nhit_max"], req[2 * r + s]["use_short"] = 10000, 0
+    sq, first, errs = ctx.hits_batch(req)
+    nlists = 0
+    for r, rd in enumerate(reads):
+        for s in (0, 1):
+            e, want, h = orc.hitinfo(oixs[rt[r]], rd, None, s, 0, 0, 0, 0)
+            got = info[2 * r + s]
+            assert int(got["err"]) == e, (r, s)
+            if e == 0:
+                for key in ("n_seeds", "cover_deficit", "nhit_tot", "nhit_all"):
+                    assert int(got[key]) == want[key], (key, r, s)
+                q = req[2 * r + s]
+                e2, wl, hl = orc.hitlist_segment(oixs[rt[r]], h, int(q["lo"]), int(q["hi"]), 10000, 0)
+                assert e2 == 0 and int(errs[2 * r + s]) == 0
+                assert np.array_equal(sq[int(first[2 * r + s]):int(first[2 * r + s + 1])], wl), (r, s)
+                nlists += len(wl) > 0
+                orc.lib.so_hitlist_delete(hl)
+            orc.lib.so_hitinfo_delete(h)
+    assert nlists > 60

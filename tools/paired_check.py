@@ -82,6 +82,8 @@ def main():
     print("-n %d: ref %.2f s (%.0f reads/s)  b200 %.2f s (%.0f reads/s)  differing (MAPQ>6) %d" %
           (ncpu, t_refn, 2 * npairs / t_refn, t_bn, 2 * npairs / t_bn, len(dn)))
     print(open(stats).read())
+    for x, y in dn[:3]:
+        print("REFn ", x[:200]); print("B200n", y[:200])
     return 1 if diff or dn or len(ref) != len(got) else 0
 
 
