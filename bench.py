@@ -139,6 +139,102 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def simulate_at(genome, pos, rc, seed, qlen=READ_LEN, err=ERR):
+    """like simulate_reads, but at given positions / strands (rc[i]: read i is the reverse complement of
+    genome[pos[i] ...]) -> reads[n, qlen]"""
+    rng = np.random.default_rng(seed)
+    n = len(pos)
+    ev = rng.random((n, qlen))
+    p_indel = err * 0.2
+    is_del = ev < p_indel / 2
+    is_ins = (ev >= p_indel / 2) & (ev < p_indel)
+    is_sub = (ev >= p_indel) & (ev < p_indel + err * 0.8)
+    step = np.ones((n, qlen), np.int64)
+    step[is_del] += rng.integers(1, 4, int(is_del.sum()))
+    step[is_ins] = 0
+    step[:, 0] = 0
+    idx = pos[:, None] + np.cumsum(step, axis=1)
+    reads = genome[np.minimum(idx, len(genome) - 1)]
+    rnd = rng.integers(0, 4, (n, qlen)).astype(np.uint8)
+    reads[is_ins] = rnd[is_ins]
+    reads[is_sub] = (reads[is_sub] + 1 + rnd[is_sub] % 3) & 3
+    reads[rc] = 3 - reads[rc][:, ::-1]
+    return np.ascontiguousarray(reads)
+
+
+def paired_workload(tmp, npairs, nseq=4, seqlen=5_000_000, seed=3):
+    """C3 scaled down (BASELINE.json configs[2]: 100 Mb genome, 5 M pairs): nseq x seqlen bases, pairs of
+    2 x 150 bp from fragments of 400 +- 40 bases (forward/reverse), 2 % error, 2 % of the mates random"""
+    from smalt_b200 import indexer
+    rng = np.random.default_rng(seed)
+    seqs = [rng.integers(0, 4, seqlen).astype(np.uint8) for _ in range(nseq)]
+    genome = np.concatenate(seqs)
+    pref = os.path.join(tmp, "c3")
+    indexer.write_smi(pref, indexer.build_index(seqs, K, NSKIP))
+    indexer.write_sma(pref, ["chr%d" % (i + 1) for i in range(nseq)], seqs)
+    ins = np.clip(rng.normal(400, 40, npairs), 200, 600).astype(np.int64)
+    chrom = rng.integers(0, nseq, npairs)
+    start = chrom * seqlen + (rng.random(npairs) * (seqlen - 700)).astype(np.int64)
+    flip = rng.integers(0, 2, npairs).astype(bool)      # which mate is the forward one
+    r_fwd = simulate_at(genome, start, np.zeros(npairs, bool), seed + 1)
+    r_rev = simulate_at(genome, start + ins - READ_LEN - 8, np.ones(npairs, bool), seed + 2)
+    junk = rng.random(npairs) < 0.02
+    r_rev[junk] = rng.integers(0, 4, (int(junk.sum()), READ_LEN)).astype(np.uint8)
+    r1 = np.where(flip[:, None], r_rev, r_fwd)
+    r2 = np.where(flip[:, None], r_fwd, r_rev)
+    return pref, fastq_text(r1), fastq_text(r2)
+
+
+def run_paired(tmp, threads, cores, npairs, ref_pairs, steps, warmup):
+    """paired-end throughput through the in-process driver (smbm_map_fastq_pairs) + the reference's CPU
+    `smalt map` on a sample of the same pairs"""
+    from smalt_b200.mapper import Mapper
+    pref, t1, t2 = paired_workload(tmp, npairs)
+    opts = ["-i", "600", "-j", "200"]
+    m = Mapper(pref, threads, options=opts, paired=True)
+    for _ in range(warmup):
+        m.map_fastq_pairs(t1, t2, copy=False)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        nb = m.map_fastq_pairs(t1, t2, copy=False)
+    wall = (time.perf_counter() - t0) / steps
+    st = m.stats.as_dict()
+    sam = m.map_fastq_pairs(t1[:_nth_record(t1, 20000)], t2[:_nth_record(t2, 20000)])
+    m.close()
+    proper = sum(1 for ln in sam.split(b"\n") if ln and ln[:1] != b"@" and int(ln.split(b"\t", 2)[1]) & 2)
+    out = {"workload": "C3 scaled to 4 x 5 Mb: %d pairs of 2 x %d bp per step, fragments 400 +- 40, %.0f%% error, 2%% random "
+                       "mates, smalt index -k %d -s %d, map -i 600 -j 200" % (npairs, READ_LEN, ERR * 100, K, NSKIP),
+           "e2e": {"value": 2 * npairs / wall, "unit": "reads/s", "ms_per_step": 1e3 * wall, "sam_bytes_per_step": int(nb)},
+           "kernel_ms": {"k1": st["k1_ms"], "k2": st["k2_ms"], "k3": st["k3_ms"]},
+           "proper_pair_fraction_sample": proper / 40000.0, "host_workers": threads}
+    smalt = os.path.join(ROOT, "oracle", "_ref", "smalt")
+    if os.path.exists(smalt):
+        f1, f2 = os.path.join(tmp, "p1.fq"), os.path.join(tmp, "p2.fq")
+        with open(f1, "wb") as f:
+            f.write(t1[:_nth_record(t1, ref_pairs)])
+        with open(f2, "wb") as f:
+            f.write(t2[:_nth_record(t2, ref_pairs)])
+        t0 = time.time()
+        r = subprocess.run([smalt, "map", "-n", str(cores), "-O"] + opts + ["-o", os.path.join(tmp, "pref.sam"), pref, f1, f2],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        dt = time.time() - t0
+        out["cpu_baseline"] = ({"value": 2 * ref_pairs / dt, "unit": "reads/s", "cores": cores, "kind": "reference",
+                                "sample": "first %d pairs, whole `oracle/_ref/smalt map -n %d -O -i 600 -j 200` program "
+                                          "(%.1f s)" % (ref_pairs, cores, dt)}
+                               if r.returncode == 0 else {"value": None, "sample": "unavailable: reference failed"})
+    return out
+
+
+def _nth_record(text, n):
+    """byte offset behind the n-th 4-line record of a FASTQ text"""
+    p = 0
+    for _ in range(4 * n):
+        p = text.find(b"\n", p) + 1
+        if p == 0:
+            return len(text)
+    return p
+
+
 def write_index_files(tmp, genome):
     """index files (own builder, byte-identical to `smalt index -k 13 -s 6`)"""
     from smalt_b200 import indexer
@@ -257,6 +353,8 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="host worker threads per GPU (0: 2 x cores / GPUs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cli", action="store_true")
+    ap.add_argument("--no-paired", action="store_true")
+    ap.add_argument("--pairs", type=int, default=250_000, help="pairs per step of the paired-end section")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -404,6 +502,13 @@ def main():
         else:
             line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": cores, "kind": "reference",
                                     "sample": "unavailable: " + err}
+    if world == 1 and not args.no_paired:
+        # configs[2] of BASELINE.json (paired-end, insert sizes) scaled to one GPU and a few seconds: not the
+        # headline metric, reported next to it
+        try:
+            line["paired"] = run_paired(tmp, threads, cores, args.pairs, min(50_000, args.pairs), 2, 2)
+        except Exception as exc:   # the headline line must not be lost
+            line["paired"] = {"unavailable": repr(exc)[:300]}
     print(json.dumps(line))
 
 

@@ -49,6 +49,15 @@ int smbm_open(smbm_mapper **m, const char *index_prefix, int nthreads, int nopti
 int smbm_map_fastq(smbm_mapper *m, const char *fastq, size_t nbytes, const char **sam, size_t *sam_len,
 		   smbm_stats *stats);
 
+/* Paired-end reads (rmapPair, rmap.c:1744): a mapper opened with smbm_open_paired (the options
+ * carry the insert size range, e.g. {"-i","600","-j","200"}) maps record i of `fastq` with record
+ * i of `fastq_mates` (two plain 4-line FASTQ texts with the same number of records) and returns
+ * both SAM records of every pair, in input order. */
+int smbm_open_paired(smbm_mapper **m, const char *index_prefix, int nthreads, int noptions,
+		     const char *const *options);
+int smbm_map_fastq_pairs(smbm_mapper *m, const char *fastq, size_t nbytes, const char *fastq_mates,
+			 size_t nbytes_mates, const char **sam, size_t *sam_len, smbm_stats *stats);
+
 /* the @HD/@SQ/@PG header lines the reference writes (report.c writeSAMHeaderf); free with smbm_free */
 int smbm_sam_header(smbm_mapper *m, char **text, size_t *len);
 void smbm_free(void *p);

@@ -39,6 +39,11 @@ typedef struct FastMap_ {
   const char *data;
   size_t len;
   int is_fasta;
+  /* paired input: second file, cut at the same record numbers */
+  const char *dataB;
+  size_t lenB;
+  struct FmLines_ *linesA, *linesB;
+  size_t block_recs, nrecs;
   size_t chunk_bytes, nchunks;
   int nworkers;
   FASTMAP_SINKF *sinkf;
@@ -60,6 +65,12 @@ typedef struct {
   SeqFastq **reads;
   uint32_t *mincov;
   size_t n_alloc;
+  SeqFastq **mates;          /* paired input */
+  uint32_t *mincov_m;
+  size_t m_alloc;
+  SeqFastq **pairs;          /* reads[i], mates[i] interleaved for pair_core */
+  size_t pairs_alloc;
+  PairWorker pw;
   int memfd;
   char fdpath[64];
   char *scratch;             /* NUL-terminated copies of the lines of one record */
@@ -258,9 +269,8 @@ static int fm_reads_reserve(FmWorker *w, size_t n)
  * infmt.c:250-263), reproducing readHeader's name rule.  Returns 1 when the block contains
  * anything else (blank lines, CR, wrapped or ragged records): the caller then uses the
  * reference's own parser for the whole block. */
-static int fm_parse_block_fast(FmWorker *w, size_t start, size_t end, size_t *nreads)
+static int fm_parse_block_fast(FmWorker *w, const char *d, size_t start, size_t end, size_t *nreads)
 {
-  const char *d = w->fm->data;
   size_t p = start, n = 0;
   int errcode;
   *nreads = 0;
@@ -307,7 +317,7 @@ static int fm_parse_block_fast(FmWorker *w, size_t start, size_t end, size_t *nr
   return ERRCODE_SUCCESS;
 }
 
-static int fm_parse_block(FmWorker *w, size_t start, size_t end, size_t *nreads)
+static int fm_parse_block(FmWorker *w, const char *data, size_t start, size_t end, size_t *nreads)
 {
   FastMap *fm = w->fm;
   int errcode = ERRCODE_SUCCESS;
@@ -315,13 +325,13 @@ static int fm_parse_block(FmWorker *w, size_t start, size_t end, size_t *nreads)
   SeqIO *sio;
   *nreads = 0;
   if (end <= start) return ERRCODE_SUCCESS;
-  if (!fm->is_fasta && (errcode = fm_check_fastq(fm->data, start, end, &nrec_expect))) {
+  if (!fm->is_fasta && (errcode = fm_check_fastq(data, start, end, &nrec_expect))) {
     fprintf(stderr, "smalt_b200: the read file is not plain 4-line FASTQ near byte %zu; "
 	    "rerun with SMALT_B200_REFIO=1 (the reference's own reader)\n", start);
     return errcode;
   }
   if (!fm->is_fasta && !getenv("SMALT_B200_REFPARSE")) {
-    errcode = fm_parse_block_fast(w, start, end, &n);
+    errcode = fm_parse_block_fast(w, data, start, end, &n);
     if (errcode != 1) {
       if (!errcode && n != nrec_expect) errcode = ERRCODE_FASTA;
       *nreads = n;
@@ -332,7 +342,7 @@ static int fm_parse_block(FmWorker *w, size_t start, size_t end, size_t *nreads)
   }
   if (ftruncate(w->memfd, 0)) return ERRCODE_FILEIO;
   for (off = start; off < end;) {
-    const ssize_t k = pwrite(w->memfd, fm->data + off, end - off, (off_t) (off - start));
+    const ssize_t k = pwrite(w->memfd, data + off, end - off, (off_t) (off - start));
     if (k <= 0) return ERRCODE_FILEIO;
     off += (size_t) k;
   }
@@ -366,7 +376,7 @@ static int fm_map_block(FmWorker *w, size_t c)
   struct timespec t0, t1;
 
   clock_gettime(CLOCK_MONOTONIC, &t0);
-  errcode = fm_parse_block(w, start, end, &n);
+  errcode = fm_parse_block(w, fm->data, start, end, &n);
   clock_gettime(CLOCK_MONOTONIC, &t1);
   pthread_mutex_lock(&g_stats_lock);
   g_fm_parse_s += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
@@ -439,6 +449,186 @@ static int fm_map_block(FmWorker *w, size_t c)
   return errcode;
 }
 
+/* ---- paired input ---------------------------------------------------------------------- */
+/* Two files hold the mates of pair i as their i-th records, so both are cut at the same RECORD
+ * numbers: the newlines of fixed-size segments are counted in parallel once, the byte offset of
+ * a line is then found by a search over the segment sums and a scan inside one segment. */
+typedef struct FmLines_ {
+  const char *d;
+  size_t len, seg_bytes, nseg;
+  uint64_t *cum;        /* cum[s] = newlines in [0, s*seg_bytes), nseg+1 entries */
+  uint64_t nlines;      /* lines of the text (a last line without newline counts) */
+} FmLines;
+
+typedef struct { FmLines *L; size_t s0, s1; } FmCountJob;
+
+static void *fm_count_main(void *arg)
+{
+  FmCountJob *j = (FmCountJob *) arg;
+  FmLines *L = j->L;
+  size_t s;
+  for (s = j->s0; s < j->s1; s++) {
+    const size_t a = s * L->seg_bytes, b = (a + L->seg_bytes < L->len) ? a + L->seg_bytes : L->len;
+    const char *p = L->d + a, *e = L->d + b;
+    uint64_t c = 0;
+    while (p < e && (p = (const char *) memchr(p, '\n', (size_t) (e - p)))) { c++; p++; }
+    L->cum[s + 1] = c;
+  }
+  return NULL;
+}
+
+static FmLines *fm_lines_build(const char *d, size_t len, int nthreads)
+{
+  FmLines *L = (FmLines *) calloc(1, sizeof(*L));
+  pthread_t *tid;
+  FmCountJob *jobs;
+  size_t s;
+  int t;
+  if (!L) return NULL;
+  L->d = d; L->len = len;
+  L->seg_bytes = (size_t) 1 << 18;
+  L->nseg = (len + L->seg_bytes - 1) / L->seg_bytes;
+  if (nthreads < 1) nthreads = 1;
+  if ((size_t) nthreads > L->nseg) nthreads = L->nseg ? (int) L->nseg : 1;
+  L->cum = (uint64_t *) calloc(L->nseg + 2, sizeof(uint64_t));
+  tid = (pthread_t *) calloc((size_t) nthreads, sizeof(pthread_t));
+  jobs = (FmCountJob *) calloc((size_t) nthreads, sizeof(FmCountJob));
+  if (!L->cum || !tid || !jobs) { free(L->cum); free(L); free(tid); free(jobs); return NULL; }
+  for (t = 0; t < nthreads; t++) {
+    jobs[t].L = L;
+    jobs[t].s0 = L->nseg * (size_t) t / (size_t) nthreads;
+    jobs[t].s1 = L->nseg * (size_t) (t + 1) / (size_t) nthreads;
+    if (nthreads == 1) fm_count_main(jobs + t);
+    else pthread_create(tid + t, NULL, fm_count_main, jobs + t);
+  }
+  if (nthreads > 1) for (t = 0; t < nthreads; t++) pthread_join(tid[t], NULL);
+  for (s = 0; s < L->nseg; s++) L->cum[s + 1] += L->cum[s];
+  L->nlines = L->cum[L->nseg] + ((len > 0 && d[len - 1] != '\n') ? 1 : 0);
+  free(tid); free(jobs);
+  return L;
+}
+
+static void fm_lines_free(FmLines *L) { if (L) { free(L->cum); free(L); } }
+
+/* byte offset of the start of line `line` (0-based); len for line >= nlines */
+static size_t fm_line_offset(const FmLines *L, uint64_t line)
+{
+  size_t lo = 0, hi = L->nseg, a, b;
+  const char *p, *e;
+  uint64_t need;
+  if (line == 0) return 0;
+  if (line > L->cum[L->nseg]) return L->len;
+  /* the line starts behind the line-th newline: segment s with cum[s] < line <= cum[s+1] */
+  while (lo + 1 < hi) {
+    const size_t mid = (lo + hi) / 2;
+    if (L->cum[mid] < line) lo = mid; else hi = mid;
+  }
+  a = lo * L->seg_bytes;
+  b = (a + L->seg_bytes < L->len) ? a + L->seg_bytes : L->len;
+  need = line - L->cum[lo];
+  p = L->d + a; e = L->d + b;
+  while (need && p < e && (p = (const char *) memchr(p, '\n', (size_t) (e - p)))) { p++; need--; }
+  return (need || !p) ? L->len : (size_t) (p - L->d);
+}
+
+typedef struct { FmWorker *w; } FmPairEmit;
+
+static int fm_emit_pair(void *user, int i, const ResultSet *rsltp, const ResultSet *rslt_matep,
+			const ResultPairs *pairp, RSLTPAIRFLG_t pairflg)
+{ /* tail of processMapArgs (smalt.c:1168-1176) + outputIOBuffArg (smalt.c:852-866) */
+  FmWorker *w = ((FmPairEmit *) user)->w;
+  const SmaltMapConst *macop = w->fm->macop;
+  int errcode;
+  reportBlank(w->rep);
+  if ((errcode = resultSetAddPairToReport(w->rep, macop->ihp, pairp, pairflg, macop->rsltouflg, rsltp, rslt_matep)))
+    return errcode;
+  if ((macop->menuflg & MENUFLAG_RELSCOR) &&
+      (macop->outform == REPORTFMT_SAM || macop->outform == REPORTFMT_BAM))
+    reportFixMultiplePrimary(w->rep);
+  return reportWrite(w->writer, w->pairs[2 * i], w->pairs[2 * i + 1], macop->ssp, macop->codecp, w->rep);
+}
+
+static int fm_map_block_pairs(FmWorker *w, size_t c)
+{
+  FastMap *fm = w->fm;
+  const SmaltMapConst *macop = fm->macop;
+  const uint64_t r0 = (uint64_t) c * fm->block_recs;
+  const uint64_t r1 = (r0 + fm->block_recs < fm->nrecs) ? r0 + fm->block_recs : fm->nrecs;
+  const size_t sA = fm_line_offset(fm->linesA, 4 * r0), eA = fm_line_offset(fm->linesA, 4 * r1);
+  const size_t sB = fm_line_offset(fm->linesB, 4 * r0), eB = fm_line_offset(fm->linesB, 4 * r1);
+  size_t n = 0, nB = 0, i, buflen = 0;
+  char *buf = NULL;
+  int errcode;
+  FILE *fp = NULL;
+  FmPairEmit em;
+  struct timespec t0, t1;
+
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  errcode = fm_parse_block(w, fm->data, sA, eA, &n);
+  if (!errcode) { /* the mates with the same parser into their own array */
+    SeqFastq **r = w->reads; uint32_t *m = w->mincov; size_t a = w->n_alloc;
+    w->reads = w->mates; w->mincov = w->mincov_m; w->n_alloc = w->m_alloc;
+    errcode = fm_parse_block(w, fm->dataB, sB, eB, &nB);
+    w->mates = w->reads; w->mincov_m = w->mincov; w->m_alloc = w->n_alloc;
+    w->reads = r; w->mincov = m; w->n_alloc = a;
+  }
+  if (!errcode && (n != nB || n != (size_t) (r1 - r0))) {
+    fprintf(stderr, "smalt_b200: the two read files do not hold the same records near pair %llu; "
+	    "rerun with SMALT_B200_REFIO=1 (the reference's own reader)\n", (unsigned long long) r0);
+    errcode = ERRCODE_FASTA;
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  pthread_mutex_lock(&g_stats_lock);
+  g_fm_parse_s += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+  pthread_mutex_unlock(&g_stats_lock);
+  if (errcode || !n) { fm_publish(fm, c, NULL, 0, errcode); return errcode; }
+  if (n > w->pairs_alloc) {
+    free(w->pairs);
+    w->pairs_alloc = n + 256;
+    if (!(w->pairs = (SeqFastq **) malloc(2 * w->pairs_alloc * sizeof(SeqFastq *)))) {
+      w->pairs_alloc = 0;
+      fm_publish(fm, c, NULL, 0, ERRCODE_NOMEM);
+      return ERRCODE_NOMEM;
+    }
+  }
+  for (i = 0; i < n; i++) { w->pairs[2 * i] = w->reads[i]; w->pairs[2 * i + 1] = w->mates[i]; }
+  {
+    const int capture = !(macop->oumodflg & REPORTMODIF_ALIOUT) &&
+      (macop->outform == REPORTFMT_SAM || macop->outform == REPORTFMT_CIGAR || macop->outform == REPORTFMT_SSAHA);
+    if (capture) {
+      if (!w->keyfp && !(w->keyfp = open_memstream(&w->keybuf, &w->keylen))) {
+	fm_publish(fm, c, NULL, 0, ERRCODE_NOMEM);
+	return ERRCODE_NOMEM;
+      }
+      smbFastCaptureBegin(w->keyfp);
+      smbShimReportWriterSetStream(w->writer, w->keyfp);
+    } else {
+      if (!(fp = open_memstream(&buf, &buflen))) { fm_publish(fm, c, NULL, 0, ERRCODE_NOMEM); return ERRCODE_NOMEM; }
+      smbShimReportWriterSetStream(w->writer, fp);
+    }
+  }
+  em.w = w;
+  errcode = pair_core(w->errmsgp, fm->maps[w->id].rmp, w->wave, &w->pw, macop, (short) w->id, (int) n, w->pairs,
+		      fm_emit_pair, &em, 0);
+  smbShimReportWriterSetStream(w->writer, NULL);
+  if (fp) {
+    if (fclose(fp) && !errcode) errcode = ERRCODE_FILEIO;
+  } else {
+    if (smbFastCaptureEnd(&buf, &buflen) && !errcode) errcode = ERRCODE_NOMEM;
+    if (fflush(w->keyfp) || w->keylen != 0) { if (!errcode) errcode = ERRCODE_ASSERT; }
+  }
+  pthread_mutex_lock(&g_stats_lock);
+  fm->n_reads += 2 * n;
+  pthread_mutex_unlock(&g_stats_lock);
+  fm_publish(fm, c, buf, buflen, errcode);
+  if (getenv("SMALT_B200_TIMING")) {
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    fprintf(stderr, "smalt_b200 timing: worker %d block %zu (%zu pairs) %.3f s, done at %.3f s\n", w->id, c, n,
+	    (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec), t1.tv_sec + 1e-9 * t1.tv_nsec - g_t0);
+  }
+  return errcode;
+}
+
 static void *fm_worker_main(void *arg)
 {
   FmWorker *w = (FmWorker *) arg;
@@ -459,7 +649,7 @@ static void *fm_worker_main(void *arg)
     if (!stop) fm->next_chunk++;
     pthread_mutex_unlock(&fm->lock);
     if (stop) break;
-    if (fm_map_block(w, c)) break;
+    if (fm->dataB ? fm_map_block_pairs(w, c) : fm_map_block(w, c)) break;
   }
   /* chunks claimed by nobody after an error must still be marked done for the flusher */
   return NULL;
@@ -489,7 +679,8 @@ static void fm_collect_stats(FmWorker *w)
 
 /* Maps the reads in data[0..len) and hands the formatted output to sinkf in input order. */
 static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nworkers, const ReportWriter *proto,
-		       const char *data, size_t len, FASTMAP_SINKF *sinkf, void *sink_user, uint64_t *n_reads)
+		       const char *data, size_t len, const char *dataB, size_t lenB,
+		       FASTMAP_SINKF *sinkf, void *sink_user, uint64_t *n_reads)
 {
   FastMap fm;
   pthread_t *tid;
@@ -505,6 +696,29 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
   fm.is_fasta = data[p] == '>';
   fm.nworkers = nworkers;
   fm.sinkf = sinkf; fm.sink_user = sink_user;
+  if (dataB) { /* paired: blocks of whole records, the same record numbers in both files */
+    size_t b = 1024;  /* two result sets of >= 24 KB (six 4 KB arrays, array.c:52-76) stay allocated per pair */
+    if (p || fm.is_fasta || data[0] != '@' || !lenB || dataB[0] != '@') return ERRCODE_ARGINVAL;
+    fm.dataB = dataB; fm.lenB = lenB;
+    fm.linesA = fm_lines_build(fm.data, fm.len, nworkers);
+    fm.linesB = fm_lines_build(dataB, lenB, nworkers);
+    if (!fm.linesA || !fm.linesB) { fm_lines_free(fm.linesA); fm_lines_free(fm.linesB); return ERRCODE_NOMEM; }
+    if (fm.linesA->nlines != fm.linesB->nlines || (fm.linesA->nlines & 3)) {
+      fm_lines_free(fm.linesA); fm_lines_free(fm.linesB);
+      return ERRCODE_ARGINVAL; /* not two plain 4-line FASTQ files of equal length: reference reader */
+    }
+    fm.nrecs = (size_t) (fm.linesA->nlines >> 2);
+    if (e && atol(e) > 0) b = (size_t) atol(e);
+    else {
+      const size_t bb = fm.nrecs / ((size_t) nworkers * 6) + 1;
+      if (bb < b) b = bb;
+      if (b < 128) b = 128;
+    }
+    if (b > 16000) b = 16000;
+    fm.block_recs = block = b;
+    fm.nchunks = (fm.nrecs + b - 1) / b;
+    if (!fm.nchunks) { fm_lines_free(fm.linesA); fm_lines_free(fm.linesB); if (n_reads) *n_reads = 0; return ERRCODE_SUCCESS; }
+  } else
   /* block size: reads per block -> bytes per block from the first records */
   {
     size_t q = 0, lines = 0, want = fm.is_fasta ? 128 : 256;
@@ -517,16 +731,19 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
     rec_bytes = q / ((lines + (fm.is_fasta ? 1 : 3)) / (fm.is_fasta ? 2 : 4) + (lines < 4));
     if (rec_bytes < 16) rec_bytes = 16;
   }
-  if (e && atol(e) > 0) block = (size_t) atol(e);
+  if (dataB) ;
+  else if (e && atol(e) > 0) block = (size_t) atol(e);
   else { /* at least ~6 blocks per worker for load balance, at least 512 reads per block */
     const size_t est_reads = fm.len / rec_bytes + 1;
     size_t b = est_reads / ((size_t) nworkers * 6) + 1;
     if (b < 512) b = 512;
     if (b < block) block = b;
   }
-  if (block > 32000) block = 32000;
-  fm.chunk_bytes = block * rec_bytes;
-  fm.nchunks = (fm.len + fm.chunk_bytes - 1) / fm.chunk_bytes;
+  if (!dataB) {
+    if (block > 32000) block = 32000;
+    fm.chunk_bytes = block * rec_bytes;
+    fm.nchunks = (fm.len + fm.chunk_bytes - 1) / fm.chunk_bytes;
+  }
   if (!(fm.out = (FmBlockOut *) calloc(fm.nchunks, sizeof(FmBlockOut)))) return ERRCODE_NOMEM;
   pthread_mutex_init(&fm.lock, NULL);
 
@@ -564,6 +781,8 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
   for (i = 0; i < nworkers; i++) fm_collect_stats(g_fm_workers + i);
   for (p = 0; p < fm.nchunks; p++) free(fm.out[p].buf);
   free(fm.out);
+  fm_lines_free(fm.linesA);
+  fm_lines_free(fm.linesB);
   pthread_mutex_destroy(&fm.lock);
   if (n_reads) *n_reads = fm.n_reads;
   return errcode;
@@ -581,6 +800,10 @@ static void fastmap_cleanup(void)
     for (k = 0; k < w->n_alloc; k++) seqFastqDelete(w->reads[k]);
     free(w->reads);
     free(w->mincov);
+    for (k = 0; k < w->m_alloc; k++) seqFastqDelete(w->mates[k]);
+    free(w->mates);
+    free(w->mincov_m);
+    free(w->pairs);
     if (w->memfd > 0) close(w->memfd);
     if (w->keyfp) { fclose(w->keyfp); free(w->keybuf); }
     free(w->scratch);

@@ -83,6 +83,10 @@ struct PairState_ {
   int mapq1, swscor1, swscor2_restricted, n_proper, swscor1_2ndbest;
   unsigned char stage;   /* PST_* */
 };
+/* Growth step of the per-pair result sets (results.c:1781-1817 takes it as a parameter; the
+ * default of 4096 results = 112 KB per set is meant for one set per thread): most reads have one
+ * or two results, and a block keeps two sets per pair. */
+enum { PAIR_RESULT_BLKSZ = 4 };
 enum { PST_END = 0, PST_SECOND_UNRESTRICTED = 3, PST_RESCUE_MAIN = 4, PST_RESCUE_FINE = 5 };
 
 /* page-locked staging buffers (smb_host_alloc): what crosses the C ABI is copied by DMA */
@@ -894,7 +898,7 @@ int rmapPairWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int npairs, SeqFastq *
     const smb_seed_info *inf = w->info + 4 * (size_t) p;
     const int err_read = inf[0].err ? inf[0].err : inf[1].err, err_mate = inf[2].err ? inf[2].err : inf[3].err;
     WJOB *jb;
-    if (!ps->rs[0] && (!(ps->rs[0] = resultSetCreate(16, 256)) || !(ps->rs[1] = resultSetCreate(16, 256))))
+    if (!ps->rs[0] && (!(ps->rs[0] = resultSetCreate(PAIR_RESULT_BLKSZ, 64)) || !(ps->rs[1] = resultSetCreate(PAIR_RESULT_BLKSZ, 64))))
       return ERRCODE_NOMEM;
     ps->status = RMAPPAIR_DONE;
     if (err_read || err_mate) { ps->status = RMAPPAIR_FALLBACK; continue; }

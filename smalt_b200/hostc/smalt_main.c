@@ -40,12 +40,39 @@
 #include <sys/time.h>
 #include <dlfcn.h>
 #include <ucontext.h>
+#include <execinfo.h>
+#include <link.h>
 #define PROF_SLOTS (1 << 16)
 static struct { uintptr_t pc; unsigned n; } g_prof[PROF_SLOTS];
+static uintptr_t g_prof_lo[2], g_prof_hi[2];   /* text of libsmalt_b200_map.so / libsmalt_b200.so */
+static int g_prof_callers;
+static int prof_phdr(struct dl_phdr_info *info, size_t size, void *data)
+{
+  int k = -1, i;
+  (void) size; (void) data;
+  if (info->dlpi_name && strstr(info->dlpi_name, "libsmalt_b200_map.so")) k = 0;
+  else if (info->dlpi_name && strstr(info->dlpi_name, "libsmalt_b200.so")) k = 1;
+  if (k < 0) return 0;
+  for (i = 0; i < info->dlpi_phnum; i++)
+    if (info->dlpi_phdr[i].p_type == PT_LOAD && (info->dlpi_phdr[i].p_flags & PF_X)) {
+      g_prof_lo[k] = info->dlpi_addr + info->dlpi_phdr[i].p_vaddr;
+      g_prof_hi[k] = g_prof_lo[k] + info->dlpi_phdr[i].p_memsz;
+    }
+  return 0;
+}
 static void prof_handler(int sig, siginfo_t *si, void *ucv)
 {
 #if defined(__x86_64__)
-  const uintptr_t pc = (uintptr_t) ((ucontext_t *) ucv)->uc_mcontext.gregs[REG_RIP];
+  uintptr_t pc = (uintptr_t) ((ucontext_t *) ucv)->uc_mcontext.gregs[REG_RIP];
+  if (g_prof_callers) { /* attribute the sample to the innermost frame inside this driver's libraries */
+    void *bt[24];
+    const int nb = backtrace(bt, 24);
+    int i;
+    for (i = 2; i < nb; i++) {
+      const uintptr_t a = (uintptr_t) bt[i];
+      if ((a >= g_prof_lo[0] && a < g_prof_hi[0]) || (a >= g_prof_lo[1] && a < g_prof_hi[1])) { pc = a; break; }
+    }
+  }
   unsigned h = (unsigned) ((pc * 0x9E3779B97F4A7C15ull) >> 48), k;
   for (k = 0; k < 64; k++, h = (h + 1) & (PROF_SLOTS - 1)) {
     if (g_prof[h].pc == pc || !g_prof[h].pc) { g_prof[h].pc = pc; g_prof[h].n++; return; }
@@ -75,6 +102,12 @@ static void prof_start(void)
   struct sigaction sa;
   struct itimerval it;
   if (!getenv("SMALT_B200_PROF")) return;
+  if (getenv("SMALT_B200_PROF_CALLERS")) {
+    void *bt[4];
+    backtrace(bt, 4);   /* loads the unwinder outside of the signal handler */
+    dl_iterate_phdr(prof_phdr, NULL);
+    g_prof_callers = 1;
+  }
   memset(&sa, 0, sizeof sa);
   sa.sa_sigaction = prof_handler;
   sa.sa_flags = SA_SIGINFO | SA_RESTART;
@@ -85,8 +118,23 @@ static void prof_start(void)
   atexit(prof_dump);
 }
 
+/* Worker threads allocate and free block-sized arrays all the time.  With glibc's defaults a
+ * thread arena gives memory back whenever its top chunk exceeds 128 KB and maps it again for the
+ * next block: mprotect + page faults under the process-wide mmap lock, which made 16 workers
+ * slower than 4 (69 % of the samples of a paired run in __mprotect).  Keep the heaps. */
+#include <malloc.h>
+static void keep_heaps(void)
+{
+  static int done;
+  if (done) return;
+  done = 1;
+  mallopt(M_TRIM_THRESHOLD, 1 << 30);
+  mallopt(M_MMAP_THRESHOLD, 32 << 20);
+}
+
 static THREAD_PROCF *g_ref_procf;
 static int fastmap_eligible(const SmaltMapConst *macop, const char **reason);
+static int g_fm_pairs_ok = 1;   /* paired input may use the block-parallel pipeline (SMALT_B200_PAIRS_REFIO=1: not) */
 static short g_blocksz = 2048;  /* reads per block of the reference queue path */
 static pthread_mutex_t g_stats_lock = PTHREAD_MUTEX_INITIALIZER;
 static double g_ms[3];
@@ -251,10 +299,14 @@ static int fiber_block(ErrMsg *errmsgp, SmaltMapArgs *map, SmaltArgBlock *blockp
 /* ------------------------------------------------------------------------------------ */
 /* paired reads: wave passes for the common course of a pair, fibers for the rest          */
 /* ------------------------------------------------------------------------------------ */
+typedef int (PAIR_EMITF)(void *user, int i, const ResultSet *rsltp, const ResultSet *rslt_matep,
+			 const ResultPairs *pairp, RSLTPAIRFLG_t pairflg);
 typedef struct {
-  SeqFastq **reads;
+  SeqFastq **reads;         /* reads[2i], reads[2i+1]: read and mate of pair i (caller's array) */
+  SeqFastq **fb_reads;
   uint32_t *mincov;
   unsigned char *status;
+  RSLTPAIRFLG_t *pairflg;
   int *fb_item, *fb_slot;
   size_t alloc;
   SmbFiberPool *pool;
@@ -262,11 +314,11 @@ typedef struct {
   int nslot;
   const SmaltMapConst *macop;
   ErrMsg *errmsgp;
-  SmaltArgBlock *blockp;
   short threadno;
   int errcode;
-  smbFiberStats prev;
   uint64_t p3_prev, p4_prev;
+  double ms_prev[3], wall_prev[11];
+  uint64_t counts_prev[5];
 } PairWorker;
 static __thread PairWorker t_pw;
 
@@ -285,7 +337,6 @@ static void pair_fallback_item(void *user, int k, int slot)
   PairWorker *pw = (PairWorker *) user;
   SmaltMapArgs *m = pw->slot + slot;
   const SmaltMapConst *macop = pw->macop;
-  SmaltIOBuffArg *brgp = pw->blockp->iobfp + pw->fb_item[k];
   const int i = pw->fb_item[k];
   int errcode;
   pw->fb_slot[k] = slot;
@@ -293,57 +344,45 @@ static void pair_fallback_item(void *user, int k, int slot)
     if (!pw->errcode) pw->errcode = errcode;
     return;
   }
-  ERRMSG_READNO(pw->errmsgp, brgp->readno + 1);
-  ERRMSG_READNAM(pw->errmsgp, seqFastqGetSeqName(brgp->readp));
-  rmapPair(pw->errmsgp, m->rmp, brgp->readp, brgp->matep, &brgp->pairflg,
+  ERRMSG_READNAM(pw->errmsgp, seqFastqGetSeqName(pw->reads[2 * i]));
+  rmapPair(pw->errmsgp, m->rmp, pw->reads[2 * i], pw->reads[2 * i + 1], pw->pairflg + i,
 	   macop->insert_min, macop->insert_max, macop->pairtyp, macop->nhitmax_tuple,
 	   (int) pw->mincov[2 * i], (int) pw->mincov[2 * i + 1], macop->min_swatscor, macop->minbasq,
 	   SMALT_TARGET_DEPTH, SMALT_MAX_DEPTH, (RMAPFLG_t) (macop->rmapflg | RMAPFLG_PAIRED),
 	   macop->scormtxp, macop->rfp, macop->htp, macop->ssp, macop->codecp);
 }
 
-static int pair_block(ErrMsg *errmsgp, SmaltMapArgs *map, SmaltArgBlock *blockp)
+/* Maps the pairs reads[2i], reads[2i+1] (i < n) and hands the results to emitf in input order.
+ * ERRCODE_ARGINVAL: mode not handled by the paired wave passes (nothing was emitted). */
+static int pair_core(ErrMsg *errmsgp, RMap *rmp, RmapWave *wave, PairWorker *pw, const SmaltMapConst *macop,
+		     short threadno, int n, SeqFastq **reads, PAIR_EMITF *emitf, void *user, int wave_stats)
 {
-  const SmaltMapConst *macop = map->smconstp;
-  PairWorker *pw = &t_pw;
-  const int n = blockp->n_iobf;
   int i, k, nfb = 0, errcode;
-  for (i = 0; i < n; i++)
-    if (!blockp->iobfp[i].isPaired) return fiber_block(errmsgp, map, blockp);
   if (macop->tupcovmin < 0) return ERRCODE_ASSERT;
-  if (!t_ws.wave) {
-    t_ws.wave = rmapWaveCreate(macop->htp, macop->ssp, macop->codecp, macop->scormtxp);
-    if (!t_ws.wave) {
-      fprintf(stderr, "smalt_b200: cannot set up the GPU context of a worker thread\n");
-      return ERRCODE_FAILURE;
-    }
-  }
   if ((size_t) n > pw->alloc) {
     const size_t na = (size_t) n + 64;
-    pw->reads = (SeqFastq **) realloc(pw->reads, 2 * na * sizeof(SeqFastq *));
+    pw->fb_reads = (SeqFastq **) realloc(pw->fb_reads, 2 * na * sizeof(SeqFastq *));
     pw->mincov = (uint32_t *) realloc(pw->mincov, 2 * na * sizeof(uint32_t));
     pw->status = (unsigned char *) realloc(pw->status, na);
+    pw->pairflg = (RSLTPAIRFLG_t *) realloc(pw->pairflg, na * sizeof(RSLTPAIRFLG_t));
     pw->fb_item = (int *) realloc(pw->fb_item, na * sizeof(int));
     pw->fb_slot = (int *) realloc(pw->fb_slot, na * sizeof(int));
-    if (!pw->reads || !pw->mincov || !pw->status || !pw->fb_item || !pw->fb_slot) return ERRCODE_NOMEM;
+    if (!pw->fb_reads || !pw->mincov || !pw->status || !pw->pairflg || !pw->fb_item || !pw->fb_slot) return ERRCODE_NOMEM;
     pw->alloc = na;
   }
+  pw->reads = reads;
   for (i = 0; i < n; i++) {
-    SmaltIOBuffArg *b = blockp->iobfp + i;
-    if ((errcode = seqFastqEncode(b->readp, macop->codecp)) || (errcode = seqFastqEncode(b->matep, macop->codecp))) {
+    if ((errcode = seqFastqEncode(reads[2 * i], macop->codecp)) || (errcode = seqFastqEncode(reads[2 * i + 1], macop->codecp))) {
       ERRMSGNO(errmsgp, errcode);
       return errcode;
     }
-    pw->reads[2 * i] = b->readp;
-    pw->reads[2 * i + 1] = b->matep;
-    pw->mincov[2 * i] = covermin_of(macop, b->readp, 0, 0);
-    pw->mincov[2 * i + 1] = covermin_of(macop, b->matep, pw->mincov[2 * i], 1);
+    pw->mincov[2 * i] = covermin_of(macop, reads[2 * i], 0, 0);
+    pw->mincov[2 * i + 1] = covermin_of(macop, reads[2 * i + 1], pw->mincov[2 * i], 1);
   }
-  errcode = rmapPairWave(errmsgp, map->rmp, t_ws.wave, n, pw->reads, pw->mincov, macop->insert_min, macop->insert_max,
+  errcode = rmapPairWave(errmsgp, rmp, wave, n, reads, pw->mincov, macop->insert_min, macop->insert_max,
 			 macop->pairtyp, macop->nhitmax_tuple, macop->min_swatscor, macop->minbasq,
 			 SMALT_TARGET_DEPTH, SMALT_MAX_DEPTH, (RMAPFLG_t) (macop->rmapflg | RMAPFLG_PAIRED),
 			 macop->scormtxp, macop->htp, macop->ssp, macop->codecp, pw->status);
-  if (errcode == ERRCODE_ARGINVAL) return fiber_block(errmsgp, map, blockp);
   if (errcode) return errcode;
   /* pairs that left the common course: the reference's rmapPair, one fiber slot each (the slot's
    * RMap keeps the results until they are reported below) */
@@ -358,63 +397,101 @@ static int pair_block(ErrMsg *errmsgp, SmaltMapArgs *map, SmaltArgBlock *blockp)
       pw->nslot = ns;
       smbFiberPoolDelete(pw->pool);
       if (!(pw->pool = smbFiberPoolCreate(ns, 256 * 1024))) return ERRCODE_NOMEM;
-      memset(&pw->prev, 0, sizeof(pw->prev));
     }
     for (k = 0; k < nfb; k++) {
-      pw->reads[2 * k] = blockp->iobfp[pw->fb_item[k]].readp;     /* (the wave is done with the array) */
-      pw->reads[2 * k + 1] = blockp->iobfp[pw->fb_item[k]].matep;
+      pw->fb_reads[2 * k] = reads[2 * pw->fb_item[k]];
+      pw->fb_reads[2 * k + 1] = reads[2 * pw->fb_item[k] + 1];
     }
-    if ((errcode = smbFiberPoolSeed(pw->pool, 2 * nfb, pw->reads, 2, !(macop->rmapflg & RMAPFLG_NOSHRTINFO),
+    if ((errcode = smbFiberPoolSeed(pw->pool, 2 * nfb, pw->fb_reads, 2, !(macop->rmapflg & RMAPFLG_NOSHRTINFO),
 				    (uint32_t) macop->nhitmax_tuple, 16384 /* HASH_MAXNHITS, rmap.c:50 */,
 				    macop->minbasq, macop->htp)))
       return errcode;
-    pw->macop = macop; pw->errmsgp = errmsgp; pw->blockp = blockp; pw->threadno = map->threadno;
+    pw->macop = macop; pw->errmsgp = errmsgp; pw->threadno = threadno;
     pw->errcode = ERRCODE_SUCCESS;
     if ((errcode = smbFiberPoolRun(pw->pool, nfb, pair_fallback_item, pw)) || (errcode = pw->errcode)) return errcode;
   }
-  /* reports in input order (the random draws among equally good placements happen here,
-   * resultpairs.c:896-927): tail of processMapArgs, smalt.c:1168-1184 */
+  /* results in input order (the random draws among equally good placements happen when they
+   * are reported, resultpairs.c:896-927) */
   for (i = 0, k = 0; i < n; i++) {
-    SmaltIOBuffArg *brgp = blockp->iobfp + i;
     const ResultSet *rsltp, *rslt_matep;
     const ResultPairs *pairp;
+    RSLTPAIRFLG_t pairflg;
     if (pw->status[i] == RMAPPAIR_DONE) {
-      RSLTPAIRFLG_t pairflg;
-      ERRMSG_READNO(errmsgp, brgp->readno + 1);
-      ERRMSG_READNAM(errmsgp, seqFastqGetSeqName(brgp->readp));
-      if ((errcode = rmapPairWaveFinish(errmsgp, map->rmp, t_ws.wave, i, macop->insert_min, macop->insert_max,
-					macop->pairtyp, macop->rfp, brgp->readp, brgp->matep, &rsltp, &rslt_matep,
+      ERRMSG_READNAM(errmsgp, seqFastqGetSeqName(reads[2 * i]));
+      if ((errcode = rmapPairWaveFinish(errmsgp, rmp, wave, i, macop->insert_min, macop->insert_max,
+					macop->pairtyp, macop->rfp, reads[2 * i], reads[2 * i + 1], &rsltp, &rslt_matep,
 					&pairp, &pairflg)))
 	return errcode;
-      brgp->pairflg = pairflg;
     } else {
       rmapGetData(&rsltp, &rslt_matep, &pairp, NULL, NULL, pw->slot[pw->fb_slot[k++]].rmp);
+      pairflg = pw->pairflg[i];
     }
-    errcode = resultSetAddPairToReport(brgp->rep, macop->ihp, pairp, brgp->pairflg, macop->rsltouflg, rsltp, rslt_matep);
-    if (errcode) ERRMSGNO(errmsgp, errcode);
-    if (MENU_SAMPLE == macop->subprogtyp &&
-	ERRCODE_SUCCESS == resultSetInferInsertSize(&brgp->isiz, RSLTSAMSPEC_V1P4, rsltp, rslt_matep))
-      brgp->pairflg |= RSLTPAIRFLG_INSERTSIZ;
+    if ((errcode = (*emitf)(user, i, rsltp, rslt_matep, pairp, pairflg))) return errcode;
   }
   {
     double ms[3], wall[11];
-    uint64_t counts[5];
-    rmapWaveGetStats(t_ws.wave, ms, counts);
-    rmapWaveGetWall(t_ws.wave, wall);
+    uint64_t counts[5], pc[4];
+    rmapWaveGetStats(wave, ms, counts);
+    rmapWaveGetWall(wave, wall);
+    rmapWaveGetPairStats(wave, pc);
     pthread_mutex_lock(&g_stats_lock);
-    for (i = 0; i < 11; i++) { g_wall[i] += wall[i] - t_ws.wall_prev[i]; t_ws.wall_prev[i] = wall[i]; }
-    for (i = 0; i < 3; i++) { g_ms[i] += ms[i] - t_ws.ms_prev[i]; t_ws.ms_prev[i] = ms[i]; }
-    for (i = 0; i < 5; i++) { g_counts[i] += counts[i] - t_ws.counts_prev[i]; t_ws.counts_prev[i] = counts[i]; }
-    g_pairs += (uint64_t) n; g_pairs_fallback += (uint64_t) nfb;
-    {
-      uint64_t pc[4];
-      rmapWaveGetPairStats(t_ws.wave, pc);
-      g_pairs_p3 += pc[2] - t_pw.p3_prev; t_pw.p3_prev = pc[2];
-      g_pairs_p4 += pc[3] - t_pw.p4_prev; t_pw.p4_prev = pc[3];
+    if (wave_stats) { /* (the block-parallel pipeline collects the wave's own counters itself) */
+      for (i = 0; i < 11; i++) { g_wall[i] += wall[i] - pw->wall_prev[i]; pw->wall_prev[i] = wall[i]; }
+      for (i = 0; i < 3; i++) { g_ms[i] += ms[i] - pw->ms_prev[i]; pw->ms_prev[i] = ms[i]; }
+      for (i = 0; i < 5; i++) { g_counts[i] += counts[i] - pw->counts_prev[i]; pw->counts_prev[i] = counts[i]; }
     }
+    g_pairs += (uint64_t) n; g_pairs_fallback += (uint64_t) nfb;
+    g_pairs_p3 += pc[2] - pw->p3_prev; pw->p3_prev = pc[2];
+    g_pairs_p4 += pc[3] - pw->p4_prev; pw->p4_prev = pc[3];
     pthread_mutex_unlock(&g_stats_lock);
   }
   return ERRCODE_SUCCESS;
+}
+
+typedef struct { const SmaltMapConst *macop; SmaltArgBlock *blockp; ErrMsg *errmsgp; } PairEmitQueue;
+static int pair_emit_queue(void *user, int i, const ResultSet *rsltp, const ResultSet *rslt_matep,
+			   const ResultPairs *pairp, RSLTPAIRFLG_t pairflg)
+{ /* tail of processMapArgs, smalt.c:1168-1184 */
+  PairEmitQueue *pe = (PairEmitQueue *) user;
+  SmaltIOBuffArg *brgp = pe->blockp->iobfp + i;
+  const SmaltMapConst *macop = pe->macop;
+  int errcode;
+  brgp->pairflg = pairflg;
+  errcode = resultSetAddPairToReport(brgp->rep, macop->ihp, pairp, brgp->pairflg, macop->rsltouflg, rsltp, rslt_matep);
+  if (errcode) ERRMSGNO(pe->errmsgp, errcode);
+  if (MENU_SAMPLE == macop->subprogtyp &&
+      ERRCODE_SUCCESS == resultSetInferInsertSize(&brgp->isiz, RSLTSAMSPEC_V1P4, rsltp, rslt_matep))
+    brgp->pairflg |= RSLTPAIRFLG_INSERTSIZ;
+  return ERRCODE_SUCCESS;
+}
+
+static int pair_block(ErrMsg *errmsgp, SmaltMapArgs *map, SmaltArgBlock *blockp)
+{
+  const SmaltMapConst *macop = map->smconstp;
+  const int n = blockp->n_iobf;
+  static __thread SeqFastq **reads;
+  static __thread size_t reads_alloc;
+  PairEmitQueue pe;
+  int i, errcode;
+  for (i = 0; i < n; i++)
+    if (!blockp->iobfp[i].isPaired) return fiber_block(errmsgp, map, blockp);
+  if (!t_ws.wave) {
+    t_ws.wave = rmapWaveCreate(macop->htp, macop->ssp, macop->codecp, macop->scormtxp);
+    if (!t_ws.wave) {
+      fprintf(stderr, "smalt_b200: cannot set up the GPU context of a worker thread\n");
+      return ERRCODE_FAILURE;
+    }
+  }
+  if ((size_t) n > reads_alloc) {
+    free(reads);
+    reads_alloc = (size_t) n + 64;
+    if (!(reads = (SeqFastq **) malloc(2 * reads_alloc * sizeof(SeqFastq *)))) return ERRCODE_NOMEM;
+  }
+  for (i = 0; i < n; i++) { reads[2 * i] = blockp->iobfp[i].readp; reads[2 * i + 1] = blockp->iobfp[i].matep; }
+  pe.macop = macop; pe.blockp = blockp; pe.errmsgp = errmsgp;
+  errcode = pair_core(errmsgp, map->rmp, t_ws.wave, &t_pw, macop, map->threadno, n, reads, pair_emit_queue, &pe, 1);
+  if (errcode == ERRCODE_ARGINVAL) return fiber_block(errmsgp, map, blockp);
+  return errcode;
 }
 
 /* THREAD_PROCF replacing processArgBlock (smalt.c:1221) */
@@ -538,6 +615,7 @@ int __wrap_threadsSetTask(uint8_t task_typ, short n_threads, THREAD_INITF *initf
     g_macop = (const SmaltMapConst *) initargp;
     if (b < 1) b = 1;
     if (b > 32000) b = 32000;
+    if (getenv("SMALT_B200_PAIRS_REFIO")) g_fm_pairs_ok = 0;
     if (!fastmap_eligible(g_macop, NULL))
       ((SmaltMapConst *) initargp)->threadblksz = (short) b;
   } else if (task_typ == THRTASK_PROC && argsz == sizeof(SmaltMapArgs)) {
@@ -556,8 +634,8 @@ struct smbm_mapper {
   int state;                 /* 0 starting, 1 ready, 2 request pending, 3 closing, 4 ended */
   int argc;
   char **argv;
-  const char *req_data;
-  size_t req_len;
+  const char *req_data, *req_dataB;
+  size_t req_len, req_lenB;
   char *out;
   size_t out_len, out_alloc;
   int req_err;
@@ -592,10 +670,13 @@ static int fastmap_eligible(const SmaltMapConst *macop, const char **reason)
 {
   const char *why = NULL;
   if (getenv("SMALT_B200_REFIO")) why = "SMALT_B200_REFIO is set";
+  else if (getenv("SMALT_B200_FIBERS_ONLY") || getenv("SMALT_B200_ONECALL")) why = "diagnostic switch of the queue path is set";
   else if (!macop || macop->subprogtyp != MENU_MAP) why = "not the map subprogram";
-  else if ((macop->rmapflg & RMAPFLG_PAIRED) || g_filnamB) why = "paired reads";
+  else if (!g_fm_pairs_ok && ((macop->rmapflg & RMAPFLG_PAIRED) || g_filnamB)) why = "paired reads";
   else if (!(macop->rmapflg & RMAPFLG_SEQBYSEQ) || (macop->rmapflg & (RMAPFLG_NOSHRTINFO | RMAPFLG_SPLIT | RMAPFLG_CMPLXW)))
     why = "mapping mode not covered by the wave path";
+  else if (((macop->rmapflg & RMAPFLG_PAIRED) || g_filnamB) && (macop->rmapflg & RMAPFLG_ALLPAIR))
+    why = "exhaustive pair search";
   else if (macop->outform == REPORTFMT_BAM || macop->outform == REPORTFMT_GFF2) why = "output format";
   else if (macop->inform != MENU_INFORM_FASTQ && macop->inform != MENU_INFORM_UNKNOWN) why = "input format";
   else if (macop->tupcovmin < 0) why = "tuple cover";
@@ -641,7 +722,8 @@ int __wrap_threadsRun(void)
 	fm_stats_reset();
 	m->out_len = 0;
 	clock_gettime(CLOCK_MONOTONIC, &t0);
-	errcode = fastmap_run(macop, maps, nworkers, dop->writerp, m->req_data, m->req_len, fm_sink_mem, m, &nr);
+	errcode = fastmap_run(macop, maps, nworkers, dop->writerp, m->req_data, m->req_len, m->req_dataB, m->req_lenB,
+			      fm_sink_mem, m, &nr);
 	clock_gettime(CLOCK_MONOTONIC, &t1);
 	m->stats.n_reads = nr;
 	m->stats.wall_s = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
@@ -670,26 +752,48 @@ int __wrap_threadsRun(void)
   }
 
   if (fastmap_eligible(macop, &why) && maps && dop && g_filnamA && strcmp(g_filnamA, "-")) {
-    int fd = open(g_filnamA, O_RDONLY);
-    struct stat sb;
-    if (fd >= 0 && !fstat(fd, &sb) && S_ISREG(sb.st_mode)) {
+    int fd = open(g_filnamA, O_RDONLY), fdB = -1;
+    struct stat sb, sbB;
+    const char *dataB = NULL;
+    int okB = 1;
+    memset(&sbB, 0, sizeof(sbB));
+    if (g_filnamB) { /* mates in a second file */
+      okB = 0;
+      fdB = open(g_filnamB, O_RDONLY);
+      if (fdB >= 0 && !fstat(fdB, &sbB) && S_ISREG(sbB.st_mode) && sbB.st_size) {
+	dataB = (const char *) mmap(NULL, (size_t) sbB.st_size, PROT_READ, MAP_PRIVATE, fdB, 0);
+	if (dataB == MAP_FAILED) dataB = NULL;
+	else if (dataB[0] == '@') okB = 1;
+      }
+      if (!okB) why = "compressed or unrecognised mate file";
+    }
+    if (okB && fd >= 0 && !fstat(fd, &sb) && S_ISREG(sb.st_mode)) {
       const char *data = sb.st_size ? (const char *) mmap(NULL, (size_t) sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0) : "";
       if (data != MAP_FAILED && (!sb.st_size || data[0] == '@' || data[0] == '>' || isspace((unsigned char) data[0]))) {
 	FILE *oufp = reportGetWriterStream(dop->writerp);
 	uint64_t nr = 0;
 	if (sb.st_size) madvise((void *) data, (size_t) sb.st_size, MADV_SEQUENTIAL);
-	errcode = fastmap_run(macop, maps, nworkers, dop->writerp, data, (size_t) sb.st_size, fm_sink_file, oufp, &nr);
-	if (macop->menuflg & MENUFLAG_VERBOSE)
-	  fprintf(stderr, "# Processed %llu single reads.\n", (unsigned long long) nr);
-	fastmap_cleanup();
-	if (sb.st_size) munmap((void *) data, (size_t) sb.st_size);
-	close(fd);
-	return errcode ? errcode : ERRCODE_EOF;
+	errcode = fastmap_run(macop, maps, nworkers, dop->writerp, data, (size_t) sb.st_size, dataB, (size_t) sbB.st_size,
+			      fm_sink_file, oufp, &nr);
+	if (errcode != ERRCODE_ARGINVAL) {
+	  if (macop->menuflg & MENUFLAG_VERBOSE)
+	    fprintf(stderr, "# Processed %llu %s reads.\n", (unsigned long long) nr, dataB ? "paired" : "single");
+	  fastmap_cleanup();
+	  if (sb.st_size) munmap((void *) data, (size_t) sb.st_size);
+	  if (dataB) munmap((void *) dataB, (size_t) sbB.st_size);
+	  close(fd);
+	  if (fdB >= 0) close(fdB);
+	  return errcode ? errcode : ERRCODE_EOF;
+	}
+	why = "read files are not plain 4-line FASTQ with the same number of records";
+      } else {
+	why = "compressed or unrecognised read file";
       }
       if (data != MAP_FAILED && sb.st_size) munmap((void *) data, (size_t) sb.st_size);
-      why = "compressed or unrecognised read file";
     }
+    if (dataB) munmap((void *) dataB, (size_t) sbB.st_size);
     if (fd >= 0) close(fd);
+    if (fdB >= 0) close(fdB);
   }
   if (getenv("SMALT_B200_TIMING"))
     fprintf(stderr, "smalt_b200: reference work queue in use (%s)\n", why ? why : "input is not a regular file");
@@ -710,8 +814,20 @@ static void *smbm_session(void *arg)
   return NULL;
 }
 
+static int smbm_open_impl(smbm_mapper **mp, const char *index_prefix, int nthreads, int noptions,
+			  const char *const *options, int paired);
 int smbm_open(smbm_mapper **mp, const char *index_prefix, int nthreads, int noptions, const char *const *options)
 {
+  return smbm_open_impl(mp, index_prefix, nthreads, noptions, options, 0);
+}
+int smbm_open_paired(smbm_mapper **mp, const char *index_prefix, int nthreads, int noptions, const char *const *options)
+{
+  return smbm_open_impl(mp, index_prefix, nthreads, noptions, options, 1);
+}
+static int smbm_open_impl(smbm_mapper **mp, const char *index_prefix, int nthreads, int noptions,
+			  const char *const *options, int paired)
+{
+  keep_heaps();
   smbm_mapper *m;
   char nbuf[32], stub[64] = "/tmp/smalt_b200_stub_XXXXXX";
   int i, k = 0, sfd;
@@ -732,6 +848,7 @@ int smbm_open(smbm_mapper **mp, const char *index_prefix, int nthreads, int nopt
   if ((sfd = mkstemp(stub)) < 0 || write(sfd, "@stub\nA\n+\nI\n", 13) != 13) { free(m); return SMB_ERRCODE_FAILURE; }
   close(sfd);
   m->argv[k++] = strdup(stub);
+  if (paired) m->argv[k++] = strdup(stub);   /* two read files = paired-end set-up (smalt.c:518) */
   m->argc = k;
   pthread_mutex_init(&m->lock, NULL);
   pthread_cond_init(&m->cond, NULL);
@@ -754,12 +871,20 @@ int smbm_open(smbm_mapper **mp, const char *index_prefix, int nthreads, int nopt
 int smbm_map_fastq(smbm_mapper *m, const char *fastq, size_t nbytes, const char **sam, size_t *sam_len,
 		   smbm_stats *stats)
 {
+  return smbm_map_fastq_pairs(m, fastq, nbytes, NULL, 0, sam, sam_len, stats);
+}
+
+int smbm_map_fastq_pairs(smbm_mapper *m, const char *fastq, size_t nbytes, const char *fastq_mates, size_t nbytes_mates,
+			 const char **sam, size_t *sam_len, smbm_stats *stats)
+{
   int rc;
   if (!m || m != g_lib || (!fastq && nbytes) || !sam || !sam_len) return SMB_ERR_ARG;
   pthread_mutex_lock(&m->lock);
   if (m->state != 1) { pthread_mutex_unlock(&m->lock); return SMB_ERR_STATE; }
   m->req_data = fastq;
   m->req_len = nbytes;
+  m->req_dataB = nbytes_mates ? fastq_mates : NULL;
+  m->req_lenB = nbytes_mates;
   m->state = 2;
   pthread_cond_broadcast(&m->cond);
   while (m->state == 2) pthread_cond_wait(&m->cond, &m->lock);
@@ -857,6 +982,7 @@ int smalt_b200_cli_main(int argc, char *argv[])
   g_t0 = ts.tv_sec + 1e-9 * ts.tv_nsec;
   atexit(flushStats);
   prof_start();
+  keep_heaps();
   /* CUDA start-up (~0.7 s) overlaps the reference's option parsing and index loading */
   if (argc > 1 && (!strcmp(argv[1], "map") || !strcmp(argv[1], "sample")) && !getenv("SMALT_B200_NOWARM"))
     warming = !pthread_create(&warm, NULL, gpu_warmup_main, NULL);

@@ -44,6 +44,9 @@ def load_map_library():
                           "the prebuilt library travels with the repo snapshot" % p)
     lib = C.CDLL(p)
     lib.smbm_open.argtypes = [C.POINTER(C.c_void_p), C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_char_p)]
+    lib.smbm_open_paired.argtypes = lib.smbm_open.argtypes
+    lib.smbm_map_fastq_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(MapStats)]
     lib.smbm_map_fastq.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p),
                                    C.POINTER(C.c_size_t), C.POINTER(MapStats)]
     lib.smbm_sam_header.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
@@ -57,11 +60,12 @@ def load_map_library():
 class Mapper:
     """`smalt map -n nthreads -O [options] index_prefix` held open in this process."""
 
-    def __init__(self, index_prefix, nthreads=1, options=()):
+    def __init__(self, index_prefix, nthreads=1, options=(), paired=False):
         self.lib = load_map_library()
         self._h = C.c_void_p()
         opts = (C.c_char_p * max(1, len(options)))(*[o.encode() for o in options])
-        rc = self.lib.smbm_open(C.byref(self._h), index_prefix.encode(), int(nthreads), len(options), opts)
+        openf = self.lib.smbm_open_paired if paired else self.lib.smbm_open
+        rc = openf(C.byref(self._h), index_prefix.encode(), int(nthreads), len(options), opts)
         if rc:
             raise SmbError(rc, "smbm_open(%s) failed (index missing, unsupported option or no CUDA device; "
                                "there is no CPU fallback)" % index_prefix)
@@ -87,6 +91,18 @@ class Mapper:
         if rc:
             raise SmbError(rc, "smbm_map_fastq failed")
         return n.value
+
+    def map_fastq_pairs(self, text, text_mates, copy=True):
+        """record i of `text` and record i of `text_mates` are a pair (mapper opened with paired=True)
+        -> SAM records of both mates of every pair (bytes), or their total length if not copy"""
+        sam = C.c_void_p()
+        n = C.c_size_t(0)
+        rc = self.lib.smbm_map_fastq_pairs(self._h, C.cast(C.c_char_p(text), C.c_void_p), len(text),
+                                           C.cast(C.c_char_p(text_mates), C.c_void_p), len(text_mates),
+                                           C.byref(sam), C.byref(n), C.byref(self.stats))
+        if rc:
+            raise SmbError(rc, "smbm_map_fastq_pairs failed")
+        return C.string_at(sam, n.value) if copy else n.value
 
     def sam_header(self):
         t = C.c_void_p()

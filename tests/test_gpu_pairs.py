@@ -81,3 +81,29 @@ def test_many_reference_sequences(tmp_path):
     assert st["fiber"]["items"] == 1200
     mapped = sum(1 for l in ref if not l.startswith("@") and not int(l.split("\t")[1]) & 4)
     assert mapped > 1000
+
+
+@needs
+def test_pairs_in_process_mapper(tmp_path):
+    """library API (include/smalt_b200_map.h): smbm_open_paired + smbm_map_fastq_pairs with worker
+    threads - both SAM records of every pair in input order, equal to the reference where the
+    placement is not a random draw among equals (MAPQ > 6 on both mates, cf. mthread_test.py)"""
+    from smalt_b200.mapper import Mapper
+    tmp = str(tmp_path)
+    pref, f1, f2 = pc.make(tmp, 3000, 1.5, 3, seed=15)
+    ref, _ = pc.run(pc.REF, ["-n", "1", "-i", "600", "-j", "200", pref, f1, f2], os.path.join(tmp, "ref.sam"))
+    ref = [l for l in ref if not l.startswith("@")]
+    m = Mapper(pref, nthreads=4, options=["-r", "7", "-i", "600", "-j", "200"], paired=True)
+    try:
+        a, b = open(f1, "rb").read(), open(f2, "rb").read()
+        for rep in range(2):       # worker state persists between calls
+            got = m.map_fastq_pairs(a, b).decode().splitlines()
+            assert len(got) == len(ref) == 6000
+            for k in range(0, 6000, 2):
+                r1, r2, g1, g2 = ref[k].split("\t"), ref[k + 1].split("\t"), got[k].split("\t"), got[k + 1].split("\t")
+                assert r1[0] == g1[0] and r2[0] == g2[0]
+                if min(int(r1[4]), int(r2[4])) > 6:
+                    assert ref[k] == got[k] and ref[k + 1] == got[k + 1], (k, ref[k], got[k])
+        assert m.stats.n_reads == 6000
+    finally:
+        m.close()
