@@ -189,7 +189,8 @@ static cudaError_t launch_class(const Scoring &sc, const SeqSrc &src, const smb_
 // Padding columns and padding rows score 0: values there never exceed the maximum already
 // recorded (h = Hdiag + s <= Hdiag), so they cannot change the result.
 // ------------------------------------------------------------------------------------
-constexpr int SW2_MAXROWS = 1024;   // staged window rows per task
+constexpr int SW2_MAXROWS = 512;    // staged window rows per task
+constexpr int SW2_PAD = 32;         // padding rows staged before and behind the window
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   uint32_t d;
@@ -197,17 +198,53 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return d;
 }
 
+// One systolic step of C packed cell pairs.  The table index (read selector ^ row selector) with the
+// row mask applied is ONE LOP3: rows with N / padding carry selector 0 and mask 4 in their task's
+// nibbles, so that every column reads a zero there (a plain xor would turn N against N into a match).
+#define SW2_STEP(SEL_EXPR)                                                                  \
+  do {                                                                                      \
+    _Pragma("unroll")                                                                       \
+    for (int c = 0; c < C; ++c) {                                                           \
+      const uint32_t s2 = (SEL_EXPR);                                                       \
+      const uint32_t h = __viaddmax_s16x2_relu(diag, s2, zero);                             \
+      diag = H[c];                                                                          \
+      const uint32_t hn = __vimax3_s16x2(h, E[c], F);                                       \
+      best = __vmaxs2(best, hn);                                                            \
+      const uint32_t tt = __viaddmax_s16x2(hn, ngi2, 0x80008000u);                          \
+      E[c] = __viaddmax_s16x2(E[c], nge2, tt);                                              \
+      F = __viaddmax_s16x2_relu(F, nge2, tt);                                               \
+      H[c] = hn;                                                                            \
+    }                                                                                       \
+  } while (0)
+
 template <int C>
 __global__ void __launch_bounds__(SW_WARPS * 32)
 sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restrict__ tasks,
                  const SwClassArgs cls, int32_t *__restrict__ scores, int32_t *__restrict__ errs) {
-  __shared__ unsigned short s_ref[SW_WARPS][SW2_MAXROWS + 32];
+  // per window row (SW2_PAD padding rows on either side): PRMT selector nibbles of both tasks in the
+  // low half, their N / padding masks in the high half; the raw codes for the general path
+  __shared__ uint32_t s_row[SW_WARPS][SW2_MAXROWS + 2 * SW2_PAD];
+  __shared__ unsigned short s_raw[SW_WARPS][SW2_MAXROWS + 2 * SW2_PAD];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  unsigned short *const sref = s_ref[threadIdx.x >> 5];
+  uint32_t *const srow = s_row[threadIdx.x >> 5];
+  unsigned short *const sraw = s_raw[threadIdx.x >> 5];
   const uint32_t ngi2 = (uint32_t)((-sc.gap_init) & 0xffff) * 0x10001u;
   const uint32_t nge2 = (uint32_t)((-sc.gap_ext) & 0xffff) * 0x10001u;
-  const uint32_t T0 = (uint32_t)(sc.match & 0xff) | ((uint32_t)(sc.mismatch & 0xff) * 0x01010100u), T1 = 0u;
+  // The table {match, mismatch x3 | 0 x4} and the constant 0 are read back from shared memory so
+  // that they live in (vector) registers: as kernel-uniform values ptxas keeps them in uniform
+  // registers / as immediates and re-materialises both for every cell (IMAD.U32 from UR + PRMT of
+  // RZ: two extra instructions per cell pair).
+  __shared__ uint32_t s_konst[2];
+  if (threadIdx.x == 0) {
+    s_konst[0] = (uint32_t)(sc.match & 0xff) | ((uint32_t)(sc.mismatch & 0xff) * 0x01010100u);
+    s_konst[1] = 0u;
+  }
+  __syncthreads();
+  const uint32_t T0 = ((volatile uint32_t *)s_konst)[0], zero = ((volatile uint32_t *)s_konst)[1];
+  // PRMT takes the table as its SECOND source (bytes 4..7; the first source is the zero register):
+  // as first source ptxas overwrites it with the result and copies it afresh for every cell.  The
+  // selector nibbles are therefore kept with bit 2 flipped: idx' = ((q ^ 4) ^ r) & ~mask.
   const int npairs = (cls.ntasks + 1) >> 1;
 
   for (;;) {
@@ -224,16 +261,19 @@ sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restri
     const int rlen = max(rlenA, rlenB);
     const bool rcA = (ta.flags & SMB_TASK_READ_REVCOMP) != 0, rcB = (tb.flags & SMB_TASK_READ_REVCOMP) != 0;
     const bool pkA = (ta.flags & SMB_TASK_REF_PACKED) != 0, pkB = (tb.flags & SMB_TASK_REF_PACKED) != 0;
+    bool hasX = false;
     __syncwarp();
-    for (int i = lane; i < rlen + 32; i += 32) {
-      const uint32_t a = (i < rlenA) ? ref_base(src, pkA, ta.ref_off, (uint32_t)i) : 7u;
-      const uint32_t b = (i < rlenB) ? ref_base(src, pkB, tb.ref_off, (uint32_t)i) : 7u;
-      sref[i] = (unsigned short)(a | (b << 8));
+    for (int x = lane; x < rlen + 2 * SW2_PAD; x += 32) {
+      const int i = x - SW2_PAD;
+      const uint32_t a = (i >= 0 && i < rlenA) ? ref_base(src, pkA, ta.ref_off, (uint32_t)i) : 7u;
+      const uint32_t b = (i >= 0 && i < rlenB) ? ref_base(src, pkB, tb.ref_off, (uint32_t)i) : 7u;
+      hasX |= (a == 4u) | (b == 4u);
+      sraw[x] = (unsigned short)(a | (b << 8));
+      srow[x] = (a < 4u ? a * 0x11u : 0x00440000u) | (b < 4u ? b * 0x1100u : 0x44000000u);
     }
     // per column: PRMT selector nibbles of the read bases {qA, qA|8, qB, qB|8} (N, padding: 4) and
     // the raw codes for the general path
     uint32_t qsel[C], qraw[C], H[C], E[C];
-    bool hasX = false;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const int j = lane * C + c;
@@ -241,59 +281,51 @@ sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restri
       const uint32_t qb = (j < qlenB) ? read_base(src.arena, tb.read_off, (uint32_t)qlenB, rcB, (uint32_t)j) : 7u;
       hasX |= (qa == 4u) | (qb == 4u);
       const uint32_t ia = qa < 4u ? qa : 4u, ib = qb < 4u ? qb : 4u;
-      qsel[c] = ia | ((ia | 8u) << 4) | (ib << 8) | ((ib | 8u) << 12);
+      qsel[c] = (ia | ((ia | 8u) << 4) | (ib << 8) | ((ib | 8u) << 12)) ^ 0x4444u;
       qraw[c] = qa | (qb << 8);
       H[c] = 0u;
       E[c] = 0u;
     }
+    // X (the mismatch-against-everything code, score.c:138-173) in a read or a window: the pair
+    // takes the per-cell table path
     const bool general = __any_sync(FULL, hasX);
     __syncwarp();
     uint32_t hdiag = 0u, hout = 0u, fout = 0u, best = 0u;
     const int nsteps = rlen + 31;
-    for (int t = 0; t < nsteps; ++t) {
-      uint32_t hl = __shfl_up_sync(FULL, hout, 1);
-      uint32_t F = __shfl_up_sync(FULL, fout, 1);
-      if (lane == 0) { hl = 0u; F = 0u; }
-      const int i = t - lane;
-      const bool active = i >= 0 && i < rlen;
-      const uint32_t r2 = active ? (uint32_t)sref[i] : 0x0707u;
-      const bool slow = general || __any_sync(FULL, active && (r2 & 0x0404u) != 0u);
-      if (active) {
+    if (!general) {
+      // Every lane computes in every step: before its first and behind its last window row it
+      // runs over the padding rows, which score 0 in every column - H stays 0 in front of the
+      // window and cannot rise behind it, E and F only matter where they are positive - so the
+      // maximum is that of the window rows alone and the loop needs no activity predicate.
+      const uint32_t *rowp = srow + (SW2_PAD - lane);
+      for (int t = 0; t < nsteps; ++t) {
+        uint32_t hl = __shfl_up_sync(FULL, hout, 1);
+        uint32_t F = __shfl_up_sync(FULL, fout, 1);
+        if (lane == 0) { hl = 0u; F = 0u; }
+        const uint32_t w = rowp[t];
+        const uint32_t wm = w >> 16;
         uint32_t diag = hdiag;
         hdiag = hl;
-        if (!slow) {
-          const uint32_t rsel = (r2 & 0xffu) * 0x11u | (r2 >> 8) * 0x1100u;
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const uint32_t s2 = prmt(T0, T1, qsel[c] ^ rsel);
-            const uint32_t h = __viaddmax_s16x2_relu(diag, s2, 0u);
-            diag = H[c];
-            const uint32_t hn = __vimax3_s16x2(h, E[c], F);
-            best = __vmaxs2(best, hn);
-            const uint32_t tt = __viaddmax_s16x2(hn, ngi2, 0x80008000u);
-            E[c] = __viaddmax_s16x2(E[c], nge2, tt);
-            F = __viaddmax_s16x2_relu(F, nge2, tt);
-            H[c] = hn;
-          }
-        } else {
-          const uint32_t ra = r2 & 0xffu, rb = r2 >> 8;
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const uint32_t qa = qraw[c] & 0xffu, qb = qraw[c] >> 8;
-            const int sa = (int)sc.S[ra * 8u + qa], sb = (int)sc.S[rb * 8u + qb];
-            const uint32_t s2 = ((uint32_t)sa & 0xffffu) | ((uint32_t)sb << 16);
-            const uint32_t h = __viaddmax_s16x2_relu(diag, s2, 0u);
-            diag = H[c];
-            const uint32_t hn = __vimax3_s16x2(h, E[c], F);
-            best = __vmaxs2(best, hn);
-            const uint32_t tt = __viaddmax_s16x2(hn, ngi2, 0x80008000u);
-            E[c] = __viaddmax_s16x2(E[c], nge2, tt);
-            F = __viaddmax_s16x2_relu(F, nge2, tt);
-            H[c] = hn;
-          }
-        }
+        SW2_STEP(prmt(0u, T0, (qsel[c] ^ w) & ~wm));
         hout = H[C - 1];
         fout = F;
+      }
+    } else {
+      for (int t = 0; t < nsteps; ++t) {
+        uint32_t hl = __shfl_up_sync(FULL, hout, 1);
+        uint32_t F = __shfl_up_sync(FULL, fout, 1);
+        if (lane == 0) { hl = 0u; F = 0u; }
+        const int i = t - lane;
+        if (i >= 0 && i < rlen) {
+          const uint32_t r2 = (uint32_t)sraw[i + SW2_PAD];
+          const uint32_t ra = r2 & 0xffu, rb = r2 >> 8;
+          uint32_t diag = hdiag;
+          hdiag = hl;
+          SW2_STEP((((uint32_t)(int)sc.S[ra * 8u + (qraw[c] & 0xffu)]) & 0xffffu) |
+                   ((uint32_t)(int)sc.S[rb * 8u + (qraw[c] >> 8)] << 16));
+          hout = H[C - 1];
+          fout = F;
+        }
       }
     }
     int bA = (int)(short)(best & 0xffffu), bB = (int)(short)(best >> 16);

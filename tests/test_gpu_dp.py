@@ -119,6 +119,31 @@ def test_sw_score_vs_oracle(ctx, orc):
         assert int(scores_rc[i]) == orc.sw_striped(revcomp(rd), win)[1]
 
 
+def test_sw_score_n_bases_and_ragged_pairs(ctx, orc):
+    """two-tasks-per-warp kernel: N in reads and windows (no X: stays on the PRMT path, N rows are
+    masked to score 0 against every column, N against N included), tasks of very different window
+    and read lengths sharing a warp (padding rows / columns), windows up to the staging limit"""
+    rng = np.random.default_rng(111)
+    pairs = []
+    for it in range(600):
+        qlen = int(rng.integers(20, 257))
+        rd, win, _ = read_window_pair(rng, qlen, with_flank=True, p_sub=0.03, p_ins=0.01, p_del=0.01)
+        if it % 5 == 0:
+            win = np.concatenate([win, random_seq(rng, int(rng.integers(1, 500 - len(win))))]) if len(win) < 480 else win
+        pn = (0.0, 0.02, 0.15, 0.6)[it % 4]
+        rd[rng.random(len(rd)) < pn] = 5
+        win[rng.random(len(win)) < pn] = 5
+        if it % 50 == 0:
+            rd[:] = 5
+        pairs.append((np.ascontiguousarray(rd), np.ascontiguousarray(win)))
+    arena, offs = _arena(pairs)
+    ctx.arena_upload(arena)
+    scores, errs = ctx.sw_score(_sw_tasks(pairs, offs))
+    for i, (rd, win) in enumerate(pairs):
+        e, s = orc.sw_striped(rd, win)
+        assert (int(errs[i]), int(scores[i])) == (e, s), (i, len(rd), len(win))
+
+
 def test_sw_score_packed_reference(ctx, orc):
     """windows read from the 3-bit packed reference store (the .sma layout)"""
     from smalt_b200.capi import SW_TASK_DTYPE, pack_sequences
