@@ -336,6 +336,7 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, const Scori
                      !getenv("SMB_NO_PACK");
   const bool no_wide = getenv("SMB_NO_WIDE") != nullptr;
   plan.pack_maxrows = 0;
+  plan.pack_maxread = 0;
   for (int i = 0; i < ntasks; ++i) {
     const smb_band_task &t = h_tasks[i];
     const int wl = align ? band_warp_lanes(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left,
@@ -343,6 +344,7 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, const Scori
     if (wl == 16 && pen16 && (long long)t.read_len * sc.match <= 12000) {
       wc[(size_t)i] = PACK_CLS;
       plan.pack_maxrows = std::max(plan.pack_maxrows, (int)t.ref_len);
+      plan.pack_maxread = std::max(plan.pack_maxread, (int)t.read_len);
     } else if (wl) {
       wc[(size_t)i] = wl == 16 ? HALF_CLS : WARP_CLS;
     } else if (align && !no_wide &&
@@ -408,7 +410,7 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
                             d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)
     return e;
   if (align && plan.pack_count &&
-      (e = launch_band_pack(sc, src, d_tasks, d_order + plan.pack_start, plan.pack_count, plan.pack_maxrows, d_ticket + 2,
+      (e = launch_band_pack(sc, src, d_tasks, d_order + plan.pack_start, plan.pack_count, plan.pack_maxrows, plan.pack_maxread, d_ticket + 2,
                             out, max_res, d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)
     return e;
   if (align && plan.half_count &&

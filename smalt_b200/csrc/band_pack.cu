@@ -35,15 +35,20 @@ constexpr int BPK_LANES = 16;
 constexpr int BPK_STACK = 24;
 constexpr int BPK_ROWPAD = 16;        // rowarr index = r + BPK_ROWPAD
 
-struct PackLayout {                   // per-group shared memory for windows of at most R rows
+struct PackLayout {                   // per-group shared memory for windows of at most R rows, reads of at most Q bases
   int R;                              // multiple of 32
+  int Q;                              // multiple of 16
   __host__ __device__ int rowarr_n() const { return R + 64; }
   __host__ __device__ int colarr_n() const { return R + 64; }
   __host__ __device__ int dirw() const { return R / 4; }          // words per lane
-  __host__ __device__ int rev_n() const { return R + BW_MAXREAD + 16; }
+  __host__ __device__ int rev_n() const { return R + Q + 16; }
+  // 32-bit entries {PRMT selector of task 0, of task 1, validity of task 0 (0x80 / 0), of task 1};
+  // the raw codes (general path only) in byte arrays behind them
   __host__ __device__ size_t rowarr_off() const { return 0; }
-  __host__ __device__ size_t colarr_off() const { return (size_t)rowarr_n() * 8; }
-  __host__ __device__ size_t dirs_off() const { return colarr_off() + (size_t)colarr_n() * 8; }
+  __host__ __device__ size_t colarr_off() const { return (size_t)rowarr_n() * 4; }
+  __host__ __device__ size_t rowraw_off() const { return colarr_off() + (size_t)colarr_n() * 4; }
+  __host__ __device__ size_t colraw_off() const { return rowraw_off() + (size_t)rowarr_n(); }
+  __host__ __device__ size_t dirs_off() const { return (colraw_off() + (size_t)colarr_n() + 15) & ~(size_t)15; }
   __host__ __device__ size_t stk_off() const { return dirs_off() + (size_t)BPK_LANES * dirw() * 4; }
   __host__ __device__ size_t rev_off() const { return stk_off() + (size_t)2 * 2 * BPK_STACK * 4; }
   __host__ __device__ size_t bytes() const { return (rev_off() + (size_t)2 * rev_n() + 15) & ~(size_t)15; }
@@ -60,7 +65,9 @@ __device__ __forceinline__ uint32_t bp_neg(uint32_t x) { return bp_prmt(x, 0u, 0
 __device__ __forceinline__ uint32_t bp_gt(uint32_t a, uint32_t b) { return bp_neg(__vsub2(b, a)); }
 
 // PRMT selector byte (two nibbles: low byte, high byte of the 16-bit score) of a read base ...
-__device__ __forceinline__ uint32_t sel_read(uint32_t q) { return q < 4u ? (q | ((q | 8u) << 4)) : 0xC4u; }
+// (bit 2 of both nibbles flipped: the table is the SECOND source of the PRMT, bytes 4..7, because as
+// first source ptxas overwrites it with the result and copies it afresh for every cell)
+__device__ __forceinline__ uint32_t sel_read(uint32_t q) { return (q < 4u ? (q | ((q | 8u) << 4)) : 0xC4u) ^ 0x44u; }
 // ... and of a window base; N / padding: sign-replicate a non-negative table entry -> 0
 __device__ __forceinline__ uint32_t sel_ref(uint32_t r) { return r < 4u ? (r | (r << 4)) : 0x4Cu; }
 
@@ -109,15 +116,16 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
   constexpr int LANES = BPK_LANES;
   const int lane = threadIdx.x & (LANES - 1);
   unsigned char *base = s_raw + (size_t)(threadIdx.x / LANES) * lay.bytes();
-  unsigned long long *rowarr = (unsigned long long *)(base + lay.rowarr_off());
-  unsigned long long *colarr = (unsigned long long *)(base + lay.colarr_off());
+  uint32_t *rowarr = (uint32_t *)(base + lay.rowarr_off());
+  uint32_t *colarr = (uint32_t *)(base + lay.colarr_off());
+  uint8_t *rowraw = base + lay.rowraw_off(), *colraw = base + lay.colraw_off();
   uint32_t *dirs = (uint32_t *)(base + lay.dirs_off());
   int *stk = (int *)(base + lay.stk_off());               // [task][l/r][BPK_STACK]
   uint8_t *revbase = base + lay.rev_off();
   const int DIRW = lay.dirw();
   const uint32_t ngi2 = (uint32_t)((-sc.gap_init) & 0xffff) * 0x10001u;
   const uint32_t nge2 = (uint32_t)((-sc.gap_ext) & 0xffff) * 0x10001u;
-  const uint32_t T0 = (uint32_t)(sc.match & 0xff) | ((uint32_t)(sc.mismatch & 0xff) * 0x01010100u), T1 = 0u;
+  const uint32_t T0 = (uint32_t)(sc.match & 0xff) | ((uint32_t)(sc.mismatch & 0xff) * 0x01010100u);
   const int npairs = (ntasks + 1) >> 1;
   unsigned long long ncell_tot = 0;
 
@@ -197,13 +205,14 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
           uint32_t c = 7u;
           if (on[t] && r >= 0 && r < nr) {
             c = ref_base(src, T[t].packed != 0, T[t].ref_off, (uint32_t)(B[t].s_left + r));
-            mask |= 0xffffu << (16 * t);
+            mask |= 0x800000u << (8 * t);
           }
           hasx |= c == 4u;
           sel |= sel_ref(c) << (8 * t);
           raw |= c << (4 * t);
         }
-        rowarr[e] = (unsigned long long)mask | ((unsigned long long)(sel | (raw << 16)) << 32);
+        rowarr[e] = mask | sel;
+        rowraw[e] = (uint8_t)raw;
       }
       for (int x = lane; x < ncol_e; x += LANES) {
         uint32_t mask = 0, sel = 0, raw = 0;
@@ -213,13 +222,14 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
           uint32_t c = 7u;
           if (on[t] && j >= B[t].q_left && j < B[t].q_len) {
             c = read_base(src.arena, T[t].read_off, (uint32_t)T[t].qlen, T[t].rc != 0, (uint32_t)j);
-            mask |= 0xffffu << (16 * t);
+            mask |= 0x800000u << (8 * t);
           }
           hasx |= c == 4u;
           sel |= sel_read(c) << (8 * t);
           raw |= c << (4 * t);
         }
-        colarr[x] = (unsigned long long)mask | ((unsigned long long)(sel | (raw << 16)) << 32);
+        colarr[x] = mask | sel;
+        colraw[x] = (uint8_t)raw;
       }
       const bool general = __any_sync(ALL, hasx);
       __syncwarp();
@@ -232,23 +242,25 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
       uint32_t bestA = 0, bestB = 0, bestAr = 0, bestBr = 0, wdir = 0, cnt2 = 0;
       uint32_t *const dirp = dirs + lane * DIRW;
       const int maxrows = max(nrows0, nrows1);
-      unsigned long long colA = colarr[lane];
+      // validity bytes -> half-word masks (sign replication of bytes 2 and 3)
+#define BP_VMASK(e) bp_prmt((e), 0u, 0xbbaau)
+      uint32_t colA = colarr[lane], cmaskA = BP_VMASK(colA);
       for (int it = 0; it < iters; ++it) {
         const int r = it - lane;
         const uint32_t Fin = __shfl_up_sync(ALL, FB, 1, LANES);
-        const unsigned long long rw = rowarr[r + BPK_ROWPAD];
-        const unsigned long long colB = colarr[it + lane + 1];
-        const uint32_t rmask = (uint32_t)rw, rhi = (uint32_t)(rw >> 32);
-        const uint32_t okA = rmask & (uint32_t)colA & hasA2, okB = rmask & (uint32_t)colB & hasB2;
-        const uint32_t cAhi = (uint32_t)(colA >> 32), cBhi = (uint32_t)(colB >> 32);
+        const uint32_t rw = rowarr[r + BPK_ROWPAD];
+        const uint32_t colB = colarr[it + lane + 1];
+        const uint32_t rmask = BP_VMASK(rw), cmaskB = BP_VMASK(colB);
+        const uint32_t okA = rmask & cmaskA & hasA2, okB = rmask & cmaskB & hasB2;
         uint32_t sA, sB;
-        if (!general) {
-          sA = bp_prmt(T0, T1, (cAhi ^ rhi) & 0xffffu);
-          sB = bp_prmt(T0, T1, (cBhi ^ rhi) & 0xffffu);
+        if (!general) {   // (PRMT reads the low 16 bits of the selector only)
+          sA = bp_prmt(0u, T0, colA ^ rw);
+          sB = bp_prmt(0u, T0, colB ^ rw);
         } else {   // X bases: per-cell table look-ups
-          const uint32_t r0 = (rhi >> 16) & 7u, r1 = (rhi >> 20) & 7u;
-          const int a0 = sc.S[r0 * 8u + ((cAhi >> 16) & 7u)], a1 = sc.S[r1 * 8u + ((cAhi >> 20) & 7u)];
-          const int b0 = sc.S[r0 * 8u + ((cBhi >> 16) & 7u)], b1 = sc.S[r1 * 8u + ((cBhi >> 20) & 7u)];
+          const uint32_t rr = rowraw[r + BPK_ROWPAD], ca = colraw[it + lane], cb = colraw[it + lane + 1];
+          const uint32_t r0 = rr & 7u, r1 = (rr >> 4) & 7u;
+          const int a0 = sc.S[r0 * 8u + (ca & 7u)], a1 = sc.S[r1 * 8u + ((ca >> 4) & 7u)];
+          const int b0 = sc.S[r0 * 8u + (cb & 7u)], b1 = sc.S[r1 * 8u + ((cb >> 4) & 7u)];
           sA = ((uint32_t)a0 & 0xffffu) | ((uint32_t)a1 << 16);
           sB = ((uint32_t)b0 & 0xffffu) | ((uint32_t)b1 << 16);
         }
@@ -259,6 +271,7 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
         PACK_CELL(okB, HB, (lane == LANES - 1 ? 0u : Ein), FA, sB, HB, eB, FB, bestB, bestBr, r2, dcB);
         cnt2 += (okA & 0x00010001u) + (okB & 0x00010001u);
         colA = colB;
+        cmaskA = cmaskB;
         if (r >= 0 && r < maxrows) {   // (the trip count may exceed this group's rows: never store beyond them)
           wdir |= (dcA | (dcB << 2)) << ((uint32_t)(r & 3) << 2);
           if ((r & 3) == 3) { dirp[r >> 2] = wdir; wdir = 0; }
@@ -319,10 +332,9 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
             const uint32_t dir = (w >> (sh + ((uint32_t)(r & 3) << 2) + ((uint32_t)(d & 1) << 1))) & 3u;
             if (!dir) break;
             if (dir == 3u) {
-              const uint32_t rhi = (uint32_t)(rowarr[r + BPK_ROWPAD] >> 32), chi = (uint32_t)(colarr[j - b.l_edge] >> 32);
               int s;
-              if (!general) s = (int)(short)(bp_prmt(T0, T1, (chi ^ rhi) & 0xffffu) >> sh);
-              else s = (int)sc.S[((rhi >> (16 + 4 * t)) & 7u) * 8u + ((chi >> (16 + 4 * t)) & 7u)];
+              if (!general) s = (int)(short)(bp_prmt(0u, T0, colarr[j - b.l_edge] ^ rowarr[r + BPK_ROWPAD]) >> sh);
+              else s = (int)sc.S[((rowraw[r + BPK_ROWPAD] >> (4 * t)) & 7u) * 8u + ((colraw[j - b.l_edge] >> (4 * t)) & 7u)];
               if (s > 0) {
                 if (nmatch > 61u) { EMIT(61u, 0u); nmatch -= 61u; }
                 else ++nmatch;
@@ -437,8 +449,8 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
 }
 
 cudaError_t launch_band_pack(const Scoring &sc, const SeqSrc &src, const smb_band_task *d_tasks,
-                             const int *d_order, int ntasks, int max_rows, int *d_ticket, BandOut out, int max_res,
-                             const uint64_t *d_diff_off, const uint32_t *d_diff_cap, int sm_count,
+                             const int *d_order, int ntasks, int max_rows, int max_read, int *d_ticket, BandOut out,
+                             int max_res, const uint64_t *d_diff_off, const uint32_t *d_diff_cap, int sm_count,
                              cudaStream_t st, int *nlaunch) {
   if (ntasks <= 0) return cudaSuccess;
   static bool attr_set = false;
@@ -448,12 +460,13 @@ cudaError_t launch_band_pack(const Scoring &sc, const SeqSrc &src, const smb_ban
   }
   cudaError_t e = cudaMemsetAsync(d_ticket, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
-  PackLayout lay{(max_rows + 31) & ~31};
+  PackLayout lay{(max_rows + 31) & ~31, (max_read + 15) & ~15};
   if (lay.R < 32) lay.R = 32;
+  if (lay.Q < 16 || lay.Q > BW_MAXREAD) lay.Q = BW_MAXREAD;
   const size_t smem = lay.bytes() * BPK_WARPS * 2;
   const int per_cta = BPK_WARPS * 4;   // tasks per CTA
   int grid = (ntasks + per_cta - 1) / per_cta;
-  const int cap = sm_count * 12;
+  const int cap = sm_count * 16;
   if (grid > cap) grid = cap;
   band_pack_kernel<<<grid, BPK_WARPS * 32, smem, st>>>(sc, src, d_tasks, d_order, ntasks, d_ticket, out, max_res,
                                                        d_diff_off, d_diff_cap, lay);
