@@ -341,7 +341,7 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, const Scori
     const smb_band_task &t = h_tasks[i];
     const int wl = align ? band_warp_lanes(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left,
                                            t.u_right, (int)t.ref_len) : 0;
-    if (wl == 16 && pen16 && (long long)t.read_len * sc.match <= 12000) {
+    if (wl == 16 && pen16 && (long long)t.read_len * sc.match <= 255) {   // (maximum keys of band_pack.cu: score < 256)
       wc[(size_t)i] = PACK_CLS;
       plan.pack_maxrows = std::max(plan.pack_maxrows, (int)t.ref_len);
       plan.pack_maxread = std::max(plan.pack_maxread, (int)t.read_len);

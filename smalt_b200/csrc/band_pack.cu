@@ -73,26 +73,30 @@ __device__ __forceinline__ uint32_t sel_ref(uint32_t r) { return r < 4u ? (r | (
 
 #define DIFFB(count, typ) ((uint8_t)((count) + ((typ) << 6)))
 
-// two cells (task 0 / task 1) of the restricted recurrence; ok2 = validity mask per half-word
-#define PACK_CELL(ok2, diag, ein, fin, s2, Hout, Eout, Fout, best, bestr, r2, dcode)                 \
+// two cells (task 0 / task 1) of the restricted recurrence; ok2 = validity mask per half-word,
+// ok3 = ok2 & 0x00030003.  There is no packed subtract or compare: a > b is the sign of
+// b + ~a (= b - a - 1), turned into a half-word mask by PRMT sign replication; the complement
+// masks it yields are folded into the LOP3s that consume them.  The running maximum of a
+// diagonal is kept as the key (score << 8 | 255 - row): an unsigned packed max then keeps the
+// FIRST row of the largest score (alignment.c:826-830) - scores and rows are below 256 here.
+#define PACK_CELL(ok2, ok3, diag, ein, fin, s2, Hout, Eout, Fout, best, rinv2, dcode)                \
   do {                                                                                                \
     const uint32_t h_ = __vadd2((diag), (s2));                                                        \
     const uint32_t m_ = __vmaxs2((ein), (fin));               /* E, F >= 0 */                          \
-    const uint32_t dia_ = bp_gt(h_, m_);                                                              \
+    const uint32_t nm_ = ~m_;                                                                         \
+    const uint32_t ndia_ = bp_neg(__vadd2(h_, nm_));          /* h <= m */                             \
     const uint32_t hn_ = __vmaxs2(h_, m_);                                                            \
     const uint32_t x_ = __vadd2(h_, ngi2);                    /* h - gap_init */                       \
-    const uint32_t open_ = dia_ & ~bp_neg(__vadd2(x_, 0xffffffffu)) & (ok2);   /* ... > 0 */          \
+    const uint32_t nx_ = bp_neg(__vadd2(h_, ngi2m1));         /* h - gap_init <= 0 */                  \
+    const uint32_t open_ = ~ndia_ & ~nx_ & (ok2);                                                     \
     const uint32_t t_ = x_ & open_;                                                                   \
     const uint32_t e_ = __viaddmax_s16x2_relu((ein), nge2, t_);                                       \
     const uint32_t f_ = __viaddmax_s16x2_relu((fin), nge2, t_);                                       \
-    const uint32_t hb_ = h_ & open_;                                                                  \
-    const uint32_t gt_ = bp_gt(hb_, (best));                                                          \
-    (best) = __vmaxs2((best), hb_);                                                                   \
-    (bestr) = ((bestr) & ~gt_) | ((r2) & gt_);                                                        \
-    const uint32_t fgt_ = bp_gt((fin), (ein));                /* F > E: ROW, else COL */              \
-    const uint32_t pos_ = bp_neg(__vsub2(0u, m_));            /* m > 0 */                              \
-    const uint32_t b0_ = dia_ | (pos_ & ~fgt_), b1_ = dia_ | (pos_ & fgt_);                           \
-    (dcode) = ((b0_ & 0x00010001u) | (b1_ & 0x00020002u)) & (ok2);                                    \
+    (best) = __vmaxu2((best), ((h_ & open_) << 8) | (rinv2));                                         \
+    const uint32_t nfgt_ = bp_neg(__vadd2((fin), ~(ein)));    /* F <= E: COL, else ROW */              \
+    const uint32_t pos_ = bp_neg(__vadd2(nm_, 0x00010001u));  /* m > 0 */                              \
+    const uint32_t b0_ = (pos_ & nfgt_) | ~ndia_, b1_ = (pos_ & ~nfgt_) | ~ndia_;                     \
+    (dcode) = ((b0_ & 0x00010001u) | (b1_ & ~0x00010001u)) & (ok3);                                   \
     (Hout) = hn_ & (ok2);                                                                             \
     (Eout) = e_ & (ok2);                                                                              \
     (Fout) = f_ & (ok2);                                                                              \
@@ -125,6 +129,7 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
   const int DIRW = lay.dirw();
   const uint32_t ngi2 = (uint32_t)((-sc.gap_init) & 0xffff) * 0x10001u;
   const uint32_t nge2 = (uint32_t)((-sc.gap_ext) & 0xffff) * 0x10001u;
+  const uint32_t ngi2m1 = (uint32_t)((-sc.gap_init - 1) & 0xffff) * 0x10001u;
   const uint32_t T0 = (uint32_t)(sc.match & 0xff) | ((uint32_t)(sc.mismatch & 0xff) * 0x01010100u);
   const int npairs = (ntasks + 1) >> 1;
   unsigned long long ncell_tot = 0;
@@ -239,7 +244,7 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
       const uint32_t hasA2 = (dA < bw0 ? 0xffffu : 0u) | (dA < bw1 ? 0xffff0000u : 0u);
       const uint32_t hasB2 = (dB < bw0 ? 0xffffu : 0u) | (dB < bw1 ? 0xffff0000u : 0u);
       uint32_t HA = 0, HB = 0, eA = 0, eB = 0, FA = 0, FB = 0;
-      uint32_t bestA = 0, bestB = 0, bestAr = 0, bestBr = 0, wdir = 0, cnt2 = 0;
+      uint32_t bestA = 0, bestB = 0, wdir = 0, cnt2 = 0;
       uint32_t *const dirp = dirs + lane * DIRW;
       const int maxrows = max(nrows0, nrows1);
       // validity bytes -> half-word masks (sign replication of bytes 2 and 3)
@@ -252,6 +257,7 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
         const uint32_t colB = colarr[it + lane + 1];
         const uint32_t rmask = BP_VMASK(rw), cmaskB = BP_VMASK(colB);
         const uint32_t okA = rmask & cmaskA & hasA2, okB = rmask & cmaskB & hasB2;
+        const uint32_t okA3 = okA & 0x00030003u, okB3 = okB & 0x00030003u;
         uint32_t sA, sB;
         if (!general) {   // (PRMT reads the low 16 bits of the selector only)
           sA = bp_prmt(0u, T0, colA ^ rw);
@@ -264,11 +270,11 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
           sA = ((uint32_t)a0 & 0xffffu) | ((uint32_t)a1 << 16);
           sB = ((uint32_t)b0 & 0xffffu) | ((uint32_t)b1 << 16);
         }
-        const uint32_t r2 = (uint32_t)(r & 0xffff) * 0x10001u;
+        const uint32_t rinv2 = ((unsigned)r < 256u) ? (uint32_t)(255 - r) * 0x10001u : 0u;
         uint32_t dcA, dcB;
-        PACK_CELL(okA, HA, eB, (lane == 0 ? 0u : Fin), sA, HA, eA, FA, bestA, bestAr, r2, dcA);
+        PACK_CELL(okA, okA3, HA, eB, (lane == 0 ? 0u : Fin), sA, HA, eA, FA, bestA, rinv2, dcA);
         const uint32_t Ein = __shfl_down_sync(ALL, eA, 1, LANES);
-        PACK_CELL(okB, HB, (lane == LANES - 1 ? 0u : Ein), FA, sB, HB, eB, FB, bestB, bestBr, r2, dcB);
+        PACK_CELL(okB, okB3, HB, (lane == LANES - 1 ? 0u : Ein), FA, sB, HB, eB, FB, bestB, rinv2, dcB);
         cnt2 += (okA & 0x00010001u) + (okB & 0x00010001u);
         colA = colB;
         cmaskA = cmaskB;
@@ -290,8 +296,9 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
       for (int t = 0; t < 2; ++t) {
         const Band &b = B[t];
         const int sh = 16 * t;
-        const int bA = (int)(short)(bestA >> sh), bB = (int)(short)(bestB >> sh);
-        const int rA = (int)((bestAr >> sh) & 0xffffu), rB = (int)((bestBr >> sh) & 0xffffu);
+        const uint32_t kA = (bestA >> sh) & 0xffffu, kB = (bestB >> sh) & 0xffffu;
+        const int bA = (int)(kA >> 8), bB = (int)(kB >> 8);
+        const int rA = 255 - (int)(kA & 0xffu), rB = 255 - (int)(kB & 0xffu);
         int best = bA, bestr = rA, bestd = dA;
         if (bB > best || (bB == best && bB > 0 && rB < bestr)) { best = bB; bestr = rB; bestd = dB; }
         unsigned long long key = 0;
