@@ -117,6 +117,74 @@ __device__ int sort2(int n, uint32_t *key, uint32_t *val) {
 #undef XC
 }
 
+// The same sort by all lanes of a warp.  The result of sort2 for a sub-array depends on nothing but
+// the sub-array, and the two parts a partitioning step leaves are disjoint - so they can be sorted
+// in any order, or at the same time, and the arrangement (ties included) stays that of the
+// reference's sequential run.  Level by level: lane i takes the i-th pending range and either
+// finishes it (straight insertion below 7 elements, sort.c:251-262) or partitions it exactly like
+// the reference (sort.c:264-316) and appends the two parts to the next level's list.  The critical
+// path is n + n/2 + n/4 + ... element steps instead of n log n.
+// `ranges`: room for 2 lists of (cap) ranges = 4 * cap ints.
+__device__ void sort2_warp(int n, uint32_t *key, uint32_t *val, int *ranges, int cap, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  int *cur = ranges, *nxt = ranges + 2 * cap;
+  int ncur = 1;
+  if (lane == 0) { cur[0] = 0; cur[1] = n - 1; }
+  __syncwarp();
+#define XC(a, b) do { uint32_t t_ = (a); (a) = (b); (b) = t_; } while (0)
+  while (ncur > 0) {
+    int nnext = 0;
+    for (int base = 0; base < ncur; base += 32) {
+      const int idx = base + lane;
+      int c0lo = 0, c0hi = -1, c1lo = 0, c1hi = -1;
+      if (idx < ncur) {
+        const int lo = cur[2 * idx], hi = cur[2 * idx + 1];
+        if (hi - lo < 7) {
+          for (int j = lo + 1; j <= hi; ++j) {
+            const uint32_t k = key[j], v = val[j];
+            int i;
+            for (i = j - 1; i >= lo && key[i] > k; --i) { key[i + 1] = key[i]; val[i + 1] = val[i]; }
+            key[i + 1] = k; val[i + 1] = v;
+          }
+        } else {
+          const int mid = (lo + hi) >> 1;
+          XC(key[mid], key[lo + 1]); XC(val[mid], val[lo + 1]);
+          if (key[lo] > key[hi]) { XC(key[lo], key[hi]); XC(val[lo], val[hi]); }
+          if (key[lo + 1] > key[hi]) { XC(key[lo + 1], key[hi]); XC(val[lo + 1], val[hi]); }
+          if (key[lo] > key[lo + 1]) { XC(key[lo], key[lo + 1]); XC(val[lo], val[lo + 1]); }
+          int i = lo + 1, j = hi;
+          const uint32_t pk = key[lo + 1], pv = val[lo + 1];
+          for (;;) {
+            do ++i; while (key[i] < pk);
+            do --j; while (key[j] > pk);
+            if (j < i) break;
+            XC(key[i], key[j]); XC(val[i], val[j]);
+          }
+          key[lo + 1] = key[j]; val[lo + 1] = val[j];
+          key[j] = pk; val[j] = pv;
+          c0lo = lo; c0hi = j - 1;      // the two parts (the reference pushes the larger, goes on with the smaller)
+          c1lo = i; c1hi = hi;
+        }
+      }
+      const int n0 = c0hi > c0lo, n1 = c1hi > c1lo;   // parts of fewer than two elements are done
+      int incl = n0 + n1;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+      }
+      int off = nnext + incl - (n0 + n1);
+      if (n0 && off < cap) { nxt[2 * off] = c0lo; nxt[2 * off + 1] = c0hi; }
+      off += n0;
+      if (n1 && off < cap) { nxt[2 * off] = c1lo; nxt[2 * off + 1] = c1hi; }
+      nnext += __shfl_sync(FULL, incl, 31);
+    }
+    __syncwarp();
+    int *t = cur; cur = nxt; nxt = t;
+    ncur = nnext < cap ? nnext : cap;
+  }
+#undef XC
+}
+
 enum { HQ_TERM = 0, HQ_NORMHIT = 1, HQ_MULTIHIT = 2, HQ_REPEAT = 3, HQ_NOHIT = 4, HQ_NONSTDNT = 5 };
 enum { HI_REVERSE = 1, HI_SORTED = 2, HI_RANK = 4 };
 
@@ -439,10 +507,9 @@ seed_warp_kernel(const Index ix0, const uint8_t *__restrict__ arena, const SeedA
     inf.status |= HI_SORTED;
     inf.seed_rank = n_seeds;
   } else {
-    int e = 0;
-    if (lane == 0) e = sort2((int)n_seeds, s_key, s_sidx);
-    e = __shfl_sync(FULL, e, 0);
-    if (e) inf.err = e;
+    // (s_word is free by now: it serves as the range lists; a part has at least two elements, and
+    // the parts of a level are disjoint: never more than n / 2 <= qmax / 2 of them)
+    sort2_warp((int)n_seeds, s_key, s_sidx, (int *)s_word, lay.qmax / 2, lane);
     inf.status |= HI_SORTED;
     __syncwarp();
     uint32_t mincover = 2u * (uint32_t)ktup + (uint32_t)nskip;
