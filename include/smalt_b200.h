@@ -218,6 +218,20 @@ int smb_seed_batch(smb_ctx *ctx, const uint64_t *read_off, const uint32_t *read_
 		   smb_seed_info *info, uint32_t *seed_posidx, uint32_t *seed_nhits,
 		   uint32_t *seed_qoffs, uint32_t *sortkey, uint32_t *sidx, uint8_t *qmask);
 
+/* Index construction on the GPU: the arrays hashTableSetUp (hashidx.c:829-998) builds for a whole
+ * sequence set, byte for byte (the `.smi` file written from them equals `smalt index`'s).  The
+ * 3-bit packed reference must have been uploaded (smb_refseq_upload).  typ / nbits_key / nbits_lo
+ * as selectHashTyp (smalt.c:268-332) chooses them; seqs[i] describes the k-mer grid of sequence i
+ * (doWordsInSeq, hashidx.c:465-531): `start` = offset of the sequence in the concatenated set,
+ * `offs` = offset of its first grid position, `n_k` = grid positions in it, `tup_base` = serial
+ * number of the first one.  smb_index_fetch copies the arrays out (wordidx / posidx: nwords + 1
+ * entries, collision type only; NULL pointers are skipped) and releases the device copy. */
+typedef struct { uint64_t start; uint32_t offs, n_k, tup_base, reserved; } smb_index_seq;
+typedef struct { uint32_t npos, nwords, nkeys; float kernel_ms; } smb_index_info;
+int smb_index_build(smb_ctx *ctx, int wordlen, int nskip, int typ, int nbits_key, int nbits_lo,
+		    const smb_index_seq *seqs, int nseq, smb_index_info *info);
+int smb_index_fetch(smb_ctx *ctx, uint32_t *idx, uint32_t *pos, uint32_t *wordidx, uint32_t *posidx);
+
 /* Seed tables against per-read SMALL indexes: the reference builds a k=5, s=1 perfect-hash
  * table on the fly from the insert-size intervals around a mapped mate (setupFineHashTable,
  * rmap.c:495-517: hashTableSetUp with an InterVal, hashidx.c:549-575, :829-998) and collects

@@ -48,6 +48,8 @@ SEED_INFO_DTYPE = np.dtype([("n_seeds", "<u4"), ("seed_rank", "<u4"), ("cover_de
                             ("status", "<u4"), ("err", "<i4")])
 HIT_REQ_DTYPE = np.dtype([("lo", "<u8"), ("hi", "<u8"), ("read", "<u4"), ("nhit_max", "<u4"),
                           ("strand", "u1"), ("use_short", "u1"), ("reserved", "u1", (2,)), ("nhits_max", "<u4")])
+INDEX_SEQ_DTYPE = np.dtype([("start", "<u8"), ("offs", "<u4"), ("n_k", "<u4"), ("tup_base", "<u4"), ("reserved", "<u4")])
+INDEX_INFO_DTYPE = np.dtype([("npos", "<u4"), ("nwords", "<u4"), ("nkeys", "<u4"), ("kernel_ms", "<f4")])
 ALI_RESULT_DTYPE = np.dtype([("score", "<i4"), ("qs", "<i4"), ("qe", "<i4"), ("rs", "<i4"),
                              ("re", "<i4"), ("diff_off", "<u4"), ("diff_len", "<u4"),
                              ("task", "<u4")])
@@ -100,6 +102,9 @@ def load_library():
     lib.smb_hits_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_size_t,
                                    C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p]
     lib.smb_hits_qmask.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.smb_index_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                    C.c_void_p]
+    lib.smb_index_fetch.argtypes = [C.c_void_p] * 5
     lib.smb_seed_batch_tables.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
                                           C.c_void_p]
@@ -177,6 +182,21 @@ class Context:
             ix["nwords"], _vp(np.ascontiguousarray(ix["idx"], np.uint32)),
             _vp(np.ascontiguousarray(ix["pos"], np.uint32)), _vp(np.ascontiguousarray(widx, np.uint32)),
             _vp(np.ascontiguousarray(pidx, np.uint32))))
+
+    def index_build(self, k, nskip, typ, nbits_key, nbits_lo, grid):
+        """GPU index construction over the uploaded packed reference; grid: INDEX_SEQ_DTYPE array.
+        -> dict(npos, nwords, nkeys, kernel_ms, idx, pos, wordidx, posidx)"""
+        grid = np.ascontiguousarray(grid, INDEX_SEQ_DTYPE)
+        info = np.zeros(1, INDEX_INFO_DTYPE)
+        self._check(self.lib.smb_index_build(self._h, k, nskip, typ, nbits_key, nbits_lo, _vp(grid), len(grid), _vp(info)))
+        npos, nwords, nkeys = int(info["npos"][0]), int(info["nwords"][0]), int(info["nkeys"][0])
+        idx = np.zeros(nkeys + 1, np.uint32)
+        pos = np.zeros(max(npos, 1), np.uint32)
+        widx = np.zeros(nwords + 1, np.uint32)
+        pidx = np.zeros(nwords + 1, np.uint32)
+        self._check(self.lib.smb_index_fetch(self._h, _vp(idx), _vp(pos), _vp(widx), _vp(pidx)))
+        return dict(npos=npos, nwords=nwords, nkeys=nkeys, kernel_ms=float(info["kernel_ms"][0]), idx=idx,
+                    pos=pos[:npos], wordidx=widx if typ else None, posidx=pidx if typ else None)
 
     def seed_batch(self, read_off, read_len, qual=None, maxhit_per_tuple=10000, maxhit_total=16384,
                    basq_thresh=0, full=True, short_info=True):

@@ -78,6 +78,8 @@ struct smb_ctx {
   SeedArgs seed_args{};
   uint32_t seed_maxlen = 0;
   DevBuf hit_meta, hit_data, hit_qmask, aux_index;
+  IndexBuildOut built{};               // arrays left on the device by smb_index_build
+  int built_typ = 0;
   Index seed_ix{};                     // index (template) of the last seed batch: what smb_hits_batch reads
   std::vector<uint32_t> seed_len;      // host copy of the read lengths of the last smb_seed_batch
   std::vector<uint64_t> hit_qmask_first;  // per request of the last smb_hits_batch
@@ -195,6 +197,7 @@ void smb_ctx_destroy(smb_ctx *ctx) {
                     &ctx->scratch, &ctx->dirs, &ctx->diff, &ctx->offs, &ctx->index, &ctx->qualbuf,
                     &ctx->seed_meta, &ctx->seed_u32, &ctx->seed_u8, &ctx->hit_meta, &ctx->hit_data, &ctx->cmp, &ctx->ticket, &ctx->hit_qmask, &ctx->aux_index};
   for (DevBuf *b : bufs) b->release();
+  if (ctx->built.block) cudaFree(ctx->built.block);
   ctx->stage.release();
   if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -755,6 +758,53 @@ int smb_index_upload(smb_ctx *ctx, int typ, int wordlen, int nskip, int nbits_ke
   ix.idx = d_idx; ix.pos = d_pos; ix.wordidx = d_w; ix.posidx = d_p;
   ctx->ix = ix;
   ctx->have_index = true;
+  return SMB_OK;
+}
+
+int smb_index_build(smb_ctx *ctx, int wordlen, int nskip, int typ, int nbits_key, int nbits_lo,
+                    const smb_index_seq *seqs, int nseq, smb_index_info *info) {
+  if (!ctx || !seqs || nseq < 1 || !info) return SMB_ERR_ARG;
+  if (wordlen < 1 || wordlen > 31 || nskip < 1 || (typ == 0 && wordlen > 15) ||
+      (typ != 0 && (nbits_key < 1 || nbits_key > 30 || nbits_lo < 0 || nbits_lo >= nbits_key || 2 * wordlen - nbits_lo > 32)))
+    return fail(ctx, SMB_ERR_ARG, "index parameters out of range (k=%d nskip=%d typ=%d key bits %d/%d)", wordlen, nskip,
+                typ, nbits_key, nbits_lo);
+  if (!ctx->src.packed) return fail(ctx, SMB_ERR_STATE, "smb_refseq_upload() first");
+  for (int i = 0; i < nseq; ++i)
+    if (seqs[i].n_k && seqs[i].start + seqs[i].offs + (uint64_t)(seqs[i].n_k - 1) * nskip + wordlen > ctx->src.packed_nbases)
+      return fail(ctx, SMB_ERR_ARG, "sequence %d: k-mer grid outside the uploaded reference", i);
+  cudaSetDevice(ctx->device);
+  if (ctx->built.block) { cudaFree(ctx->built.block); ctx->built = IndexBuildOut{}; }
+  int nl = 0;
+  static_assert(sizeof(smb_index_seq) == sizeof(IndexBuildSeq), "layout");
+  CU(cudaEventRecord(ctx->ev0, ctx->stream));
+  CU(index_build(ctx->src.packed, (const IndexBuildSeq *)seqs, nseq, wordlen, nskip, typ, nbits_key, nbits_lo,
+                 ctx->stream, &ctx->built, &nl));
+  CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  CU(ctx_sync(ctx));
+  CU(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+  ctx->built_typ = typ;
+  ctx->last_launches = nl;
+  ctx->total_launches += nl;
+  g_launches += nl;
+  info->npos = ctx->built.npos; info->nwords = ctx->built.nwords; info->nkeys = ctx->built.nkeys;
+  info->kernel_ms = ctx->last_ms;
+  return SMB_OK;
+}
+
+int smb_index_fetch(smb_ctx *ctx, uint32_t *idx, uint32_t *pos, uint32_t *wordidx, uint32_t *posidx) {
+  if (!ctx) return SMB_ERR_ARG;
+  if (!ctx->built.block) return fail(ctx, SMB_ERR_STATE, "smb_index_build() first");
+  cudaSetDevice(ctx->device);
+  const IndexBuildOut &b = ctx->built;
+  if (idx) CU(d2h(idx, b.idx, ((size_t)b.nkeys + 1) * 4, ctx->stream));
+  if (pos && b.npos) CU(d2h(pos, b.pos, (size_t)b.npos * 4, ctx->stream));
+  if (ctx->built_typ != 0) {
+    if (wordidx) CU(d2h(wordidx, b.wordidx, ((size_t)b.nwords + 1) * 4, ctx->stream));
+    if (posidx) CU(d2h(posidx, b.posidx, ((size_t)b.nwords + 1) * 4, ctx->stream));
+  }
+  CU(ctx_sync(ctx));
+  cudaFree(ctx->built.block);
+  ctx->built = IndexBuildOut{};
   return SMB_OK;
 }
 

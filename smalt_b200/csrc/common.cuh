@@ -136,6 +136,16 @@ struct IndexTab {
   uint32_t npos, reserved;
 };
 
+// index construction (index_build.cu)
+struct IndexBuildSeq { uint64_t start; uint32_t offs, n_k, tup_base, reserved; };   // == smb_index_seq
+struct IndexBuildOut {
+  uint32_t npos, nwords, nkeys;
+  uint32_t *block;                       // one device allocation holding the four arrays (cudaFree it)
+  uint32_t *idx, *pos, *wordidx, *posidx;
+};
+cudaError_t index_build(const uint32_t *d_packed, const IndexBuildSeq *h_seqs, int nseq, int k, int nskip, int typ,
+                        int nbits_key, int nbits_lo, cudaStream_t st, IndexBuildOut *out, int *nlaunch);
+
 struct SeedArgs {
   const IndexTab *tab;        // nullptr: every read uses the kernel's Index argument
   const uint32_t *read_tab;   // [nreads] table of each read

@@ -8,7 +8,74 @@
  * (hashTableGetKtupleHits, hashTableFetchHitPositions) end up in the object but are never
  * called by the B200 path: all lookups run in seed.cu.
  */
+#include <stdlib.h>
+#define hashTableSetUp hashTableSetUp_cpu
 #include "hashidx.c"
+#undef hashTableSetUp
+
+int smbShimIndexBuild(const SeqSet *ssp, const SeqCodec *codecp, int k, int nskip, int typ, int nbits_key,
+		      int nbits_lo, uint32_t *npos, uint32_t *nwords, uint32_t *tuplectr_out, float *ms);
+int smbShimIndexFetch(uint32_t *idx, uint32_t *pos, uint32_t *wordidx, uint32_t *posidx);
+
+/* hashTableSetUp (hashidx.c:829-998).  The index of a whole sequence set (`smalt index`) is
+ * built on the GPU (csrc/index_build.cu) into the same arrays with the same allocation rules, so
+ * that hashTableWrite produces the same `.smi` bytes; the on-the-fly index of a few intervals
+ * (rmap.c:495-517), a box without a GPU and SMALT_B200_CPU_INDEX=1 use the reference's builder. */
+int hashTableSetUp(HashTable *htp, SeqFastq *sqbufp, const SeqSet *ssp, const InterVal *ivp,
+		   const SeqCodec *codecp, uint32_t *npos_max, char verbose)
+{
+  uint32_t npos = 0, nwords = 0, tuplectr = 0;
+  float ms = 0.f;
+  SETSIZ_t totlen;
+  if (ivp != NULL || getenv("SMALT_B200_CPU_INDEX"))
+    return hashTableSetUp_cpu(htp, sqbufp, ssp, ivp, codecp, npos_max, verbose);
+  seqSetGetSeqNumAndTotLen(&totlen, ssp);
+  if (htp->status == HASHSETUP_EMPTY) {
+    if (htp->nskip < 1 || (totlen + 1) / htp->nskip > HASHPOS_MAX) return ERRCODE_ASSERT;
+  } else {
+    hashTableReset(htp, 0);
+  }
+  if (smbShimIndexBuild(ssp, codecp, htp->wordlen, htp->nskip, htp->typ, htp->nbits_key, htp->nbits_lo,
+			&npos, &nwords, &tuplectr, &ms) < 0) {
+    if (verbose) fprintf(stderr, "# (index construction on the CPU)\n");
+    return hashTableSetUp_cpu(htp, sqbufp, ssp, ivp, codecp, npos_max, verbose);
+  }
+  if (verbose) fprintf(stderr, "# Hash index built on the GPU (%u positions, %u words, %.1f ms).\n", npos, nwords, ms);
+  if (npos_max != NULL) {   /* hashidx.c:881-887 */
+    if (*npos_max > 0 && npos > *npos_max) {
+      *npos_max = npos;
+      return ERRCODE_MAXKPOS;
+    }
+    *npos_max = npos;
+  }
+  if (htp->pos == NULL || npos > htp->npos_alloc) {   /* hashidx.c:889-903 */
+    size_t n_alloc = ((size_t) npos + 1) / BLKSIZ_IDXPOS + 1;
+    n_alloc *= BLKSIZ_IDXPOS;
+    if (htp->pos == NULL) {
+      ECALLOCP(n_alloc, htp->pos);
+      if (!htp->pos) return ERRCODE_NOMEM;
+    } else {
+      void *hp = EREALLOCP(htp->pos, n_alloc);
+      if (!hp) return ERRCODE_NOMEM;
+      htp->pos = hp;
+    }
+    htp->npos_alloc = n_alloc;
+  }
+  htp->npos = npos;
+  if (htp->typ != HASHIDXTYP_PERFECT) {   /* hashidx.c:935-940 */
+    htp->nwords = nwords;
+    free(htp->wordidx);
+    if ((ECALLOCP(2 * ((size_t) nwords + ARRAY_MARGIN), htp->wordidx)) == NULL) return ERRCODE_NOMEM;
+    htp->posidx = htp->wordidx + nwords + ARRAY_MARGIN;
+  }
+  if (smbShimIndexFetch(htp->idx, htp->pos, htp->typ != HASHIDXTYP_PERFECT ? htp->wordidx : NULL,
+			htp->typ != HASHIDXTYP_PERFECT ? htp->posidx : NULL))
+    return ERRCODE_FAILURE;
+  htp->maxpos = (tuplectr > 0) ? tuplectr - 1 : 0;
+  htp->status = HASHSETUP_COMPLETE;
+  if (verbose) fprintf(stderr, "# Hash table is set up.\n");
+  return ERRCODE_SUCCESS;
+}
 
 void smbShimHashTableArrays(const HashTable *htp, int *typ, int *wordlen, int *nskip,
 			    int *nbits_key, int *nbits_lo, uint32_t *npos, uint32_t *nwords,

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
+#include <limits.h>
 #include <time.h>
 
 #include "elib.h"
@@ -136,6 +137,64 @@ static int upload_refseq(smb_ctx *ctx, const SeqSet *ssp, const SeqCodec *codecp
   free(words);
   free(so);
   return errcode;
+}
+
+/* Index construction on the GPU for `smalt_b200 index` (hashTableSetUp of a whole sequence set,
+ * called from shim_hashidx.c): the k-mer grid bookkeeping of doWordsInSeq (hashidx.c:465-531) per
+ * sequence on the host, everything else in csrc/index_build.cu.  Returns < 0 when the GPU path
+ * does not apply (no device, a sequence shorter than k, ...): the caller then runs the
+ * reference's CPU builder - index construction is not the mapping hot path. */
+int smbShimIndexBuild(const SeqSet *ssp, const SeqCodec *codecp, int k, int nskip, int typ, int nbits_key,
+		      int nbits_lo, uint32_t *npos, uint32_t *nwords, uint32_t *tuplectr_out, float *ms)
+{
+  const SETSIZ_t *soffs;
+  const SEQNUM_t nseq = seqSetGetOffsets(ssp, &soffs);
+  smb_index_seq *grid;
+  smb_index_info info;
+  long long tuplectr = 0, offs = 0;
+  SEQNUM_t s;
+  int rc;
+  if (nseq < 1 || nseq > INT_MAX) return -1;
+  if (!(grid = (smb_index_seq *) calloc((size_t) nseq, sizeof(*grid)))) return -1;
+  for (s = 0; s < nseq; s++) {
+    const long long L = (long long) (soffs[s + 1] - soffs[s]);
+    long long n_k, ktup_i, d;
+    if (L < k) { free(grid); return -1; }
+    n_k = (L - k - offs >= 0) ? (L - k - offs) / nskip + 1 : 0;
+    grid[s].start = soffs[s]; grid[s].offs = (uint32_t) offs; grid[s].n_k = (uint32_t) n_k;
+    grid[s].tup_base = (uint32_t) tuplectr;
+    if (n_k > 0) ktup_i = nskip - (L - 1 - (offs + (n_k - 1) * nskip + k - 1));
+    else ktup_i = k + offs - L;
+    tuplectr += n_k;
+    d = k - ktup_i;
+    offs = d % nskip;
+    if (offs) offs = nskip - offs;
+    tuplectr += (k - ktup_i + offs) / nskip;
+    if (tuplectr > 0xFFFFFFFFll || n_k > 0xFFFFFFFFll) { free(grid); return -1; }
+  }
+  pthread_mutex_lock(&g_lock);
+  rc = 0;
+  if (!g_root && smb_ctx_create(&g_root, shim_device())) rc = -1;
+  if (!rc && upload_refseq(g_root, ssp, codecp)) rc = -1;
+  if (!rc && smb_index_build(g_root, k, nskip, typ, nbits_key, nbits_lo, grid, (int) nseq, &info)) {
+    fprintf(stderr, "smalt_b200: GPU index construction failed: %s\n", smb_last_error(g_root));
+    rc = -1;
+  }
+  pthread_mutex_unlock(&g_lock);
+  free(grid);
+  if (rc) return rc;
+  *npos = info.npos; *nwords = info.nwords; *tuplectr_out = (uint32_t) tuplectr;
+  if (ms) *ms = info.kernel_ms;
+  return 0;
+}
+
+int smbShimIndexFetch(uint32_t *idx, uint32_t *pos, uint32_t *wordidx, uint32_t *posidx)
+{
+  int rc;
+  pthread_mutex_lock(&g_lock);
+  rc = g_root ? smb_index_fetch(g_root, idx, pos, wordidx, posidx) : -1;
+  pthread_mutex_unlock(&g_lock);
+  return rc ? ERRCODE_FAILURE : ERRCODE_SUCCESS;
 }
 
 int smbShimInit(const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,

@@ -132,6 +132,52 @@ def build_index(seqs, k=13, nskip=6):
                 wordidx=wordidx, posidx=posidx)
 
 
+def kmer_grid(seqs, k, nskip):
+    """The k-mer grid bookkeeping of doWordsInSeq (hashidx.c:465-531) per sequence, without touching the
+    bases: -> (grid array for smb_index_build, final k-mer counter)."""
+    from .capi import INDEX_SEQ_DTYPE
+    grid = np.zeros(len(seqs), INDEX_SEQ_DTYPE)
+    tuplectr = 0
+    offs = 0
+    start = 0
+    for n, s in enumerate(seqs):
+        L = len(s)
+        if L < k:
+            raise ValueError("sequence shorter than k (ERRCODE_SHORTSEQ)")
+        n_k = (L - k - offs) // nskip + 1 if L - k - offs >= 0 else 0
+        grid[n] = (start, offs, n_k, tuplectr, 0)
+        if n_k > 0:
+            last_end = offs + (n_k - 1) * nskip + k - 1
+            ktup_i = nskip - (L - 1 - last_end)
+        else:
+            ktup_i = k + offs - L
+        tuplectr += n_k
+        d = k - ktup_i
+        offs = int(np.fmod(d, nskip))
+        if offs:
+            offs = nskip - offs
+        tuplectr += int(np.trunc((k - ktup_i + offs) / nskip))
+        start += L
+    return grid, tuplectr
+
+
+def build_index_gpu(ctx, seqs, k=13, nskip=6, upload=True):
+    """build_index on the GPU (csrc/index_build.cu through smb_index_build): same dict, same bytes."""
+    from .seqpack import pack3
+    totlen = int(sum(len(s) for s in seqs))
+    typ, nbits_key, nbits_lo = select_hash_type(k, nskip, totlen)
+    grid, tuplectr = kmer_grid(seqs, k, nskip)
+    if upload:
+        allc = np.concatenate([np.asarray(s, np.uint8) & 7 for s in seqs] + [np.array([7], np.uint8)])
+        offs = np.concatenate([[0], np.cumsum([len(s) for s in seqs])]).astype(np.uint64)
+        ctx.refseq_upload(pack3(allc), totlen, offs)
+    r = ctx.index_build(k, nskip, typ, nbits_key if typ else 2 * k, nbits_lo, grid)
+    maxpos = tuplectr - 1 if tuplectr > 0 else 0
+    return dict(typ=typ, wordlen=k, nskip=nskip, nbits_key=nbits_key if typ else 2 * k, nbits_lo=nbits_lo if typ else 0,
+                npos=r["npos"], nwords=r["nwords"], maxpos=maxpos, nkeys=r["nkeys"], idx=r["idx"], pos=r["pos"],
+                wordidx=r["wordidx"], posidx=r["posidx"], kernel_ms=r["kernel_ms"])
+
+
 def as_loaded(ix):
     """The table as hashTableRead leaves it: posidx[nwords] is not read back (hashidx.c:1334)."""
     out = dict(ix)
