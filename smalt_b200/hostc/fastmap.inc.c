@@ -633,7 +633,7 @@ static void *fm_worker_main(void *arg)
 {
   FmWorker *w = (FmWorker *) arg;
   FastMap *fm = w->fm;
-  int rc = fm_worker_setup(w, fm, w->id);
+  int rc = (pregrow_arena(), fm_worker_setup(w, fm, w->id));
   if (rc) {
     pthread_mutex_lock(&fm->lock);
     if (!fm->errcode) fm->errcode = rc;

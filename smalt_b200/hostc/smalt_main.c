@@ -136,6 +136,20 @@ static void keep_heaps(void)
   mallopt(M_MMAP_THRESHOLD, 32 << 20);
 }
 
+/* ... and let a worker thread grow its arena ONCE: glibc extends a thread arena page by page with
+ * mprotect (arena.c grow_heap) - thousands of calls under the mmap lock while 16-32 workers fill
+ * their first blocks (21 % of the samples of a 1 M read run).  One large request, freed again,
+ * leaves the heap mapped (trimming is off). */
+static void pregrow_arena(void)
+{
+  static __thread int done;
+  if (!done && !(getenv("SMALT_B200_NOPREGROW") && atoi(getenv("SMALT_B200_NOPREGROW")))) {
+    void *p = malloc((size_t) 28 << 20);
+    done = 1;
+    if (p) { *(volatile char *) p = 0; free(p); }
+  }
+}
+
 static THREAD_PROCF *g_ref_procf;
 static int fastmap_eligible(const SmaltMapConst *macop, const char **reason);
 struct smbm_mapper;
@@ -503,7 +517,7 @@ static int pair_block(ErrMsg *errmsgp, SmaltMapArgs *map, SmaltArgBlock *blockp)
 /* THREAD_PROCF replacing processArgBlock (smalt.c:1221) */
 static int smb_processArgBlock(ErrMsg *errmsgp, void *targp, void *bufargp)
 {
-  int errcode = ERRCODE_SUCCESS;
+  int errcode = (pregrow_arena(), ERRCODE_SUCCESS);
   short i;
   SmaltMapArgs *map = (SmaltMapArgs *) targp;
   SmaltArgBlock *blockp = (SmaltArgBlock *) bufargp;
