@@ -107,3 +107,23 @@ def test_pairs_in_process_mapper(tmp_path):
         assert m.stats.n_reads == 6000
     finally:
         m.close()
+
+
+@needs
+def test_sample_and_map_with_histogram(tmp_path):
+    """`smalt sample` (insert-size histogram; RMAPFLG_BEST | ALLPAIR on every readskip-th pair,
+    smalt.c:1397: fibers) writes the reference's histogram, and `map -g <histogram>` (pair scores
+    from the histogram, resultpairs.c) gives the reference's SAM"""
+    tmp = str(tmp_path)
+    pref, f1, f2 = pc.make(tmp, 3000, 1.0, 2, seed=16)
+    hist = {}
+    for tag, exe in (("ref", pc.REF), ("b200", pc.B200)):
+        hist[tag] = os.path.join(tmp, tag + ".hist")
+        r = subprocess.run([exe, "sample", "-u", "10", "-n", "1", "-o", hist[tag], pref, f1, f2],
+                           capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, (tag, r.stderr[-1500:])
+    a, b = open(hist["ref"]).read(), open(hist["b200"]).read()
+    assert a == b and len(a.splitlines()) > 5
+    ref, got, st = _both(tmp, ["-n", "1", "-g", hist["ref"], pref, f1, f2])
+    _same(ref, got)
+    assert st["pairs"] == 3000
