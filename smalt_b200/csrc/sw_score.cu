@@ -217,18 +217,25 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     }                                                                                       \
   } while (0)
 
-template <int C>
+// LANES = 32: one task pair per warp, lane owns C columns.  LANES = 16: TWO task pairs per warp (four
+// tasks), one per half-warp, lane owns C columns of its pair (C = 2 x the 32-lane class): the skew of
+// the systolic array - steps in which a lane runs over padding rows - halves (15 instead of 31 of
+// ~200 steps) and the per-step instructions (two shuffles, two selects, one LDS) are shared by twice as
+// many cells.  The half-warps run in lockstep: full-warp shuffles of width 16, trip counts and staging
+// bounds are the maxima over the two halves.
+template <int C, int LANES>
 __global__ void __launch_bounds__(SW_WARPS * 32)
 sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restrict__ tasks,
                  const SwClassArgs cls, int32_t *__restrict__ scores, int32_t *__restrict__ errs) {
+  constexpr int GROUPS = 32 / LANES;
   // per window row (SW2_PAD padding rows on either side): PRMT selector nibbles of both tasks in the
   // low half, their N / padding masks in the high half; the raw codes for the general path
-  __shared__ uint32_t s_row[SW_WARPS][SW2_MAXROWS + 2 * SW2_PAD];
-  __shared__ unsigned short s_raw[SW_WARPS][SW2_MAXROWS + 2 * SW2_PAD];
+  __shared__ uint32_t s_row[SW_WARPS * GROUPS][SW2_MAXROWS + 2 * SW2_PAD];
+  __shared__ unsigned short s_raw[SW_WARPS * GROUPS][SW2_MAXROWS + 2 * SW2_PAD];
   const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  uint32_t *const srow = s_row[threadIdx.x >> 5];
-  unsigned short *const sraw = s_raw[threadIdx.x >> 5];
+  const int lane = threadIdx.x & (LANES - 1);
+  uint32_t *const srow = s_row[threadIdx.x / LANES];
+  unsigned short *const sraw = s_raw[threadIdx.x / LANES];
   const uint32_t ngi2 = (uint32_t)((-sc.gap_init) & 0xffff) * 0x10001u;
   const uint32_t nge2 = (uint32_t)((-sc.gap_ext) & 0xffff) * 0x10001u;
   // The table {match, mismatch x3 | 0 x4} and the constant 0 are read back from shared memory so
@@ -250,20 +257,22 @@ sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restri
   for (;;) {
     int k = 0;
     if (lane == 0) k = atomicAdd(cls.counter, 1);
-    k = __shfl_sync(FULL, k, 0);
-    if (k >= npairs) break;
-    const int tixA = __ldg(cls.order + 2 * k);
-    const bool haveB = 2 * k + 1 < cls.ntasks;
+    k = __shfl_sync(FULL, k, 0, LANES);
+    const bool alive = k < npairs;
+    if (!__any_sync(FULL, alive)) break;
+    const int tixA = alive ? __ldg(cls.order + 2 * k) : 0;
+    const bool haveB = alive && 2 * k + 1 < cls.ntasks;
     const int tixB = haveB ? __ldg(cls.order + 2 * k + 1) : tixA;
     const smb_sw_task ta = tasks[tixA], tb = tasks[tixB];
-    const int qlenA = (int)ta.read_len, qlenB = (int)tb.read_len;
-    const int rlenA = (int)ta.ref_len, rlenB = (int)tb.ref_len;
-    const int rlen = max(rlenA, rlenB);
+    const int qlenA = alive ? (int)ta.read_len : 0, qlenB = alive ? (int)tb.read_len : 0;
+    const int rlenA = alive ? (int)ta.ref_len : 0, rlenB = alive ? (int)tb.ref_len : 0;
+    int rlen = max(rlenA, rlenB);                                      // of this group
+    if (GROUPS > 1) rlen = max(rlen, __shfl_xor_sync(FULL, rlen, 16)); // ... of the warp: common trip count
     const bool rcA = (ta.flags & SMB_TASK_READ_REVCOMP) != 0, rcB = (tb.flags & SMB_TASK_READ_REVCOMP) != 0;
     const bool pkA = (ta.flags & SMB_TASK_REF_PACKED) != 0, pkB = (tb.flags & SMB_TASK_REF_PACKED) != 0;
     bool hasX = false;
     __syncwarp();
-    for (int x = lane; x < rlen + 2 * SW2_PAD; x += 32) {
+    for (int x = lane; x < rlen + 2 * SW2_PAD; x += LANES) {
       const int i = x - SW2_PAD;
       const uint32_t a = (i >= 0 && i < rlenA) ? ref_base(src, pkA, ta.ref_off, (uint32_t)i) : 7u;
       const uint32_t b = (i >= 0 && i < rlenB) ? ref_base(src, pkB, tb.ref_off, (uint32_t)i) : 7u;
@@ -286,12 +295,12 @@ sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restri
       H[c] = 0u;
       E[c] = 0u;
     }
-    // X (the mismatch-against-everything code, score.c:138-173) in a read or a window: the pair
-    // takes the per-cell table path
+    // X (the mismatch-against-everything code, score.c:138-173) in a read or a window: the warp's
+    // pairs take the per-cell table path
     const bool general = __any_sync(FULL, hasX);
     __syncwarp();
     uint32_t hdiag = 0u, hout = 0u, fout = 0u, best = 0u;
-    const int nsteps = rlen + 31;
+    const int nsteps = rlen + LANES - 1;
     if (!general) {
       // Every lane computes in every step: before its first and behind its last window row it
       // runs over the padding rows, which score 0 in every column - H stays 0 in front of the
@@ -299,8 +308,8 @@ sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restri
       // maximum is that of the window rows alone and the loop needs no activity predicate.
       const uint32_t *rowp = srow + (SW2_PAD - lane);
       for (int t = 0; t < nsteps; ++t) {
-        uint32_t hl = __shfl_up_sync(FULL, hout, 1);
-        uint32_t F = __shfl_up_sync(FULL, fout, 1);
+        uint32_t hl = __shfl_up_sync(FULL, hout, 1, LANES);
+        uint32_t F = __shfl_up_sync(FULL, fout, 1, LANES);
         if (lane == 0) { hl = 0u; F = 0u; }
         const uint32_t w = rowp[t];
         const uint32_t wm = w >> 16;
@@ -312,8 +321,8 @@ sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restri
       }
     } else {
       for (int t = 0; t < nsteps; ++t) {
-        uint32_t hl = __shfl_up_sync(FULL, hout, 1);
-        uint32_t F = __shfl_up_sync(FULL, fout, 1);
+        uint32_t hl = __shfl_up_sync(FULL, hout, 1, LANES);
+        uint32_t F = __shfl_up_sync(FULL, fout, 1, LANES);
         if (lane == 0) { hl = 0u; F = 0u; }
         const int i = t - lane;
         if (i >= 0 && i < rlen) {
@@ -329,9 +338,11 @@ sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restri
       }
     }
     int bA = (int)(short)(best & 0xffffu), bB = (int)(short)(best >> 16);
-    bA = __reduce_max_sync(FULL, bA);
-    bB = __reduce_max_sync(FULL, bB);
-    if (lane == 0) {
+    for (int o = LANES / 2; o > 0; o >>= 1) {
+      bA = max(bA, __shfl_xor_sync(FULL, bA, o, LANES));
+      bB = max(bB, __shfl_xor_sync(FULL, bB, o, LANES));
+    }
+    if (lane == 0 && alive) {
       scores[tixA] = bA;
       errs[tixA] = SMB_OK;
       if (haveB) { scores[tixB] = bB; errs[tixB] = SMB_OK; }
@@ -339,11 +350,14 @@ sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restri
   }
 }
 
+// C: columns per lane of the 32-lane form (ceil(qlen / 32)); the half-warp form owns 2C per lane
 template <int C>
 static cudaError_t launch_class2(const Scoring &sc, const SeqSrc &src, const smb_sw_task *d_tasks,
                                  const SwClassArgs &cls, int32_t *d_scores, int32_t *d_errs, int grid,
                                  cudaStream_t st) {
-  sw_score2_kernel<C><<<grid, SW_WARPS * 32, 0, st>>>(sc, src, d_tasks, cls, d_scores, d_errs);
+  static const bool lanes32 = getenv("SMB_SW_LANES32") != nullptr;
+  if (lanes32) sw_score2_kernel<C, 32><<<grid, SW_WARPS * 32, 0, st>>>(sc, src, d_tasks, cls, d_scores, d_errs);
+  else sw_score2_kernel<2 * C, 16><<<(grid + 1) / 2, SW_WARPS * 32, 0, st>>>(sc, src, d_tasks, cls, d_scores, d_errs);
   return cudaGetLastError();
 }
 
