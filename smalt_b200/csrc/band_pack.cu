@@ -335,12 +335,16 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
           uint32_t n = 0;
 #define EMIT(c, ty) do { if (n < revcap) rev[n] = DIFFB(c, ty); else ovf = true; ++n; } while (0)
           while (i >= b.s_left && j >= b.q_left) {
+            // (the three loads of a step are issued together: the walk is a chain of dependent
+            // shared-memory loads, and the substitution score is needed by the usual DIA move)
             const uint32_t w = dirs[(d >> 1) * DIRW + (r >> 2)];
+            const uint32_t csel = colarr[j - b.l_edge], rsel = rowarr[r + BPK_ROWPAD];
             const uint32_t dir = (w >> (sh + ((uint32_t)(r & 3) << 2) + ((uint32_t)(d & 1) << 1))) & 3u;
+            const int sfast = (int)(short)(bp_prmt(0u, T0, csel ^ rsel) >> sh);
             if (!dir) break;
             if (dir == 3u) {
               int s;
-              if (!general) s = (int)(short)(bp_prmt(0u, T0, colarr[j - b.l_edge] ^ rowarr[r + BPK_ROWPAD]) >> sh);
+              if (!general) s = sfast;
               else s = (int)sc.S[((rowraw[r + BPK_ROWPAD] >> (4 * t)) & 7u) * 8u + ((colraw[j - b.l_edge] >> (4 * t)) & 7u)];
               if (s > 0) {
                 if (nmatch > 61u) { EMIT(61u, 0u); nmatch -= 61u; }
