@@ -2,7 +2,9 @@
 GPU (launch with torchrun), reads sharded by rank, SAM merged in input order on rank 0.
 
   torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 -m smalt_b200.mapreads \
-      [-n threads_per_gpu] -o out.sam <index_prefix> <reads.fq>
+      [-n threads_per_gpu] [-i max_insert -j min_insert] -o out.sam <index_prefix> <reads.fq> [<mates.fq>]
+With a mate file the pairs are sharded (both files cut at the same record numbers) and mapped
+with the paired-end path (rmapPair).
 """
 import argparse
 import os
@@ -15,11 +17,14 @@ def main(argv=None):
     ap.add_argument("-o", required=True)
     ap.add_argument("-r", type=int, default=None, help="seed of the draw among equally good hits (smalt map -r)")
     ap.add_argument("--backend", default=None, help="torch.distributed backend (default nccl; gloo for tests)")
+    ap.add_argument("-i", type=int, default=None, help="maximum insert size (smalt map -i)")
+    ap.add_argument("-j", type=int, default=None, help="minimum insert size (smalt map -j)")
     ap.add_argument("index")
     ap.add_argument("reads")
+    ap.add_argument("mates", nargs="?", default=None)
     args = ap.parse_args(argv)
     from .mapper import Mapper
-    from .shard import gather_in_order, shard_of
+    from .shard import gather_in_order, pair_shard_of, shard_of
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     dist = None
@@ -34,12 +39,22 @@ def main(argv=None):
         else:
             dist.init_process_group(backend)
     text = open(args.reads, "rb").read()
-    mine = shard_of(text, rank, world)
     cores = len(os.sched_getaffinity(0))
     opts = [] if args.r is None else ["-r", str(args.r)]
-    m = Mapper(args.index, args.n or max(1, int(2 * cores / world)), opts)
-    header = m.sam_header() if rank == 0 else b""
-    sam = m.map_fastq(mine)
+    for flag, val in (("-i", args.i), ("-j", args.j)):
+        if val is not None:
+            opts += [flag, str(val)]
+    nthreads = args.n or max(1, int(2 * cores / world))
+    if args.mates is None:
+        mine = shard_of(text, rank, world)
+        m = Mapper(args.index, nthreads, opts)
+        header = m.sam_header() if rank == 0 else b""
+        sam = m.map_fastq(mine)
+    else:
+        mine1, mine2 = pair_shard_of(text, open(args.mates, "rb").read(), rank, world)
+        m = Mapper(args.index, nthreads, opts, paired=True)
+        header = m.sam_header() if rank == 0 else b""
+        sam = m.map_fastq_pairs(mine1, mine2) if mine1 else b""
     m.close()
     out = gather_in_order(dist, sam) if dist is not None else sam
     if rank == 0:

@@ -36,6 +36,36 @@ def shard_of(text, rank, world, lib=None):
     return text[pts[rank]:pts[rank + 1]]
 
 
+def pair_split_points(text1, text2, nparts):
+    """Paired input: both 4-line FASTQ texts are cut at the same RECORD numbers (record i of one file
+    is the mate of record i of the other) -> (offsets in text1, offsets in text2), nparts+1 each."""
+    def line_starts(t):
+        a = np.frombuffer(t, np.uint8)
+        nl = np.flatnonzero(a == 10)
+        starts = np.concatenate([[0], nl + 1])
+        if len(t) and t[-1:] != b"\n":
+            nlines = len(nl) + 1
+        else:
+            nlines = len(nl)
+        return starts, nlines
+    s1, n1 = line_starts(text1)
+    s2, n2 = line_starts(text2)
+    if n1 != n2 or n1 % 4:
+        raise ValueError("mate files are not two 4-line FASTQ texts with the same number of records")
+    nrec = n1 // 4
+    cuts = [min(nrec, (nrec * r + nparts - 1) // nparts) for r in range(nparts + 1)]
+    cuts[-1] = nrec
+    def offs(starts, n, t):
+        return [int(starts[4 * c]) if 4 * c < len(starts) and c < nrec else len(t) for c in cuts]
+    return offs(s1, n1, text1), offs(s2, n2, text2)
+
+
+def pair_shard_of(text1, text2, rank, world):
+    """the pairs rank `rank` of `world` maps: (records of file 1, records of file 2)"""
+    p1, p2 = pair_split_points(text1, text2, world)
+    return text1[p1[rank]:p1[rank + 1]], text2[p2[rank]:p2[rank + 1]]
+
+
 def gather_in_order(dist, local_bytes, dst=0):
     """Concatenates the per-rank outputs in rank order on `dst` (None elsewhere).  Works with any
     torch.distributed backend: sizes by all_gather, payloads as uint8 tensors."""

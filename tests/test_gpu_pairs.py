@@ -127,3 +127,34 @@ def test_sample_and_map_with_histogram(tmp_path):
     ref, got, st = _both(tmp, ["-n", "1", "-g", hist["ref"], pref, f1, f2])
     _same(ref, got)
     assert st["pairs"] == 3000
+
+
+@needs
+def test_mapreads_pairs(tmp_path):
+    """the multi-GPU entry point with a mate file: pairs sharded by rank (both files cut at the same
+    record numbers), paired-end path per rank, SAM merged in input order"""
+    import torch
+    tmp = str(tmp_path)
+    pref, f1, f2 = pc.make(tmp, 4000, 1.5, 3, seed=17)
+    ref, _ = pc.run(pc.REF, ["-n", "1", "-i", "600", "-j", "200", pref, f1, f2], os.path.join(tmp, "ref.sam"))
+    ref = [l for l in ref if not l.startswith("@")]
+    out = os.path.join(tmp, "b200.sam")
+    r = subprocess.run([sys.executable, "-m", "smalt_b200.mapreads", "-n", "1", "-r", "7", "-i", "600", "-j", "200",
+                        "-o", out, pref, f1, f2], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = [l for l in open(out).read().splitlines() if not l.startswith("@")]
+    assert got == ref                      # one rank, one worker: byte for byte
+    if torch.cuda.device_count() < 2:
+        return
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29571", "-m", "smalt_b200.mapreads",
+                        "-n", "2", "-r", "7", "-i", "600", "-j", "200", "-o", out, pref, f1, f2],
+                       capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = [l for l in open(out).read().splitlines() if not l.startswith("@")]
+    assert len(got) == len(ref)
+    for k in range(0, len(ref), 2):        # pairs without a random draw on either side
+        f = [x.split("\t", 5) for x in (ref[k], ref[k + 1], got[k], got[k + 1])]
+        assert f[0][0] == f[2][0]
+        if min(int(x[4]) for x in f) > 6:
+            assert ref[k] == got[k] and ref[k + 1] == got[k + 1], (k, ref[k], got[k])

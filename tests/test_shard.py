@@ -121,3 +121,28 @@ def test_two_rank_gather_in_input_order(tmp_path):
     want = b"".join(rec.split("\n")[0][1:].encode() + b"\t" + str(len(rec.split("\n")[1])).encode() + b"\n"
                     for rec in recs)
     assert out.read_bytes() == want
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8, 50])
+def test_pair_sharding_cuts_both_files_at_the_same_records(world):
+    """paired input: record i of file 1 and record i of file 2 always land on the same rank, every
+    pair on exactly one rank, ranks in input order (also when there are more ranks than pairs)"""
+    from smalt_b200.shard import pair_shard_of
+    rng = np.random.default_rng(world)
+    r1 = _fastq(rng, 37, tricky=True)
+    r2 = _fastq(rng, 37, tricky=True)     # different lengths per record: byte offsets differ between the files
+    t1, t2 = "".join(r1).encode(), "".join(r2).encode()
+    got1, got2, npairs = b"", b"", 0
+    for rank in range(world):
+        a, b = pair_shard_of(t1, t2, rank, world)
+        assert a.count(b"\n") == b.count(b"\n") and a.count(b"\n") % 4 == 0
+        # the k-th record of the shard of file 1 and of file 2 carry the same read number
+        na = [l for l in a.split(b"\n")[0::4] if l]
+        nb = [l for l in b.split(b"\n")[0::4] if l]
+        assert [x.split()[0] for x in na] == [x.split()[0] for x in nb]
+        got1 += a
+        got2 += b
+        npairs += len(na)
+    assert got1 == t1 and got2 == t2 and npairs == 37
+    with pytest.raises(ValueError):
+        pair_shard_of(t1, "".join(r2[:-1]).encode(), 0, 2)
