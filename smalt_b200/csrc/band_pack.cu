@@ -23,7 +23,7 @@
 //    (band, read segment, row range - different for the two tasks) is one AND of three masks;
 //  * direction codes: 4 bits per row and task (two diagonals of the lane), four rows per word;
 //  * argmax, backtrace, DiffStr reversal, result emission and the recursion are per task as in
-//    band_warp.cu (lane t of the half-warp serves task t).
+//    band_warp.cu, except that the eight lanes 8t..8t+7 of the half-warp walk the path of task t together.
 // Tasks with an X base in the read or the window use the general table path for their scores.
 #include "common.cuh"
 #include "band.h"
@@ -315,82 +315,111 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
         max_i[t] = b.s_left + max_r[t];
         if (max_scor[t] < T[t].minscore) on[t] = false;                    // :1364
       }
-      // makeMetaFromTrack (alignment.c:628-781): lane t walks the path of task t
+      // makeMetaFromTrack (alignment.c:628-781): lanes 8t..8t+7 of the group walk the path of task t
+      // together.  Sub-lane L looks at the cell L steps up the current diagonal; the run of cells
+      // that continue as "DIA move onto a match" (ballot) is consumed at once - the reference's
+      // per-match counter (`nmatch > 61 ? emit 61 : ++nmatch`, i.e. 62 rolls over to 1 with one
+      // emission) has the closed form below - and the first cell that is anything else takes the
+      // reference's step, with the values of the sub-lane that looked at it.
       int bi = 0, bj = 0, flag = 0;
       uint32_t bn = 0;
       {
-        const int t = lane & 1;
-        const bool mine = lane < 2 && (t ? on[1] : on[0]);
-        if (mine) {
-          const Band &b = t ? B[1] : B[0];
-          const int mscor = t ? max_scor[1] : max_scor[0];
-          uint8_t *rev = revbase + (size_t)t * lay.rev_n();
-          const uint32_t revcap = (uint32_t)lay.rev_n();
-          const int sh = 16 * t;
-          int i = t ? max_i[1] : max_i[0], j = t ? max_j[1] : max_j[0];
-          int r = t ? max_r[1] : max_r[0], d = j - b.l_edge - r;
-          bool gap_open = false, ovf = false;
-          unsigned nmatch = 0;
-          int checksum = 0;
-          uint32_t n = 0;
-#define EMIT(c, ty) do { if (n < revcap) rev[n] = DIFFB(c, ty); else ovf = true; ++n; } while (0)
-          while (i >= b.s_left && j >= b.q_left) {
-            // (the three loads of a step are issued together: the walk is a chain of dependent
-            // shared-memory loads, and the substitution score is needed by the usual DIA move)
-            const uint32_t w = dirs[(d >> 1) * DIRW + (r >> 2)];
-            const uint32_t csel = colarr[j - b.l_edge], rsel = rowarr[r + BPK_ROWPAD];
-            const uint32_t dir = (w >> (sh + ((uint32_t)(r & 3) << 2) + ((uint32_t)(d & 1) << 1))) & 3u;
-            const int sfast = (int)(short)(bp_prmt(0u, T0, csel ^ rsel) >> sh);
-            if (!dir) break;
-            if (dir == 3u) {
-              int s;
-              if (!general) s = sfast;
-              else s = (int)sc.S[((rowraw[r + BPK_ROWPAD] >> (4 * t)) & 7u) * 8u + ((colraw[j - b.l_edge] >> (4 * t)) & 7u)];
-              if (s > 0) {
-                if (nmatch > 61u) { EMIT(61u, 0u); nmatch -= 61u; }
-                else ++nmatch;
-              } else {
-                EMIT(nmatch, 3u);
-                nmatch = 0;
-              }
-              checksum += s;
-              gap_open = false;
-              --i; --j; --r;
-              continue;
-            }
-            if (gap_open) checksum -= sc.gap_ext;
-            else { checksum -= sc.gap_init; gap_open = true; }
-            if (dir & 1u) {
-              EMIT(nmatch, 1u);
-              nmatch = 0;
-              --i; --r; ++d;
-              continue;
-            }
-            EMIT(nmatch, 2u);
-            nmatch = 0;
-            --j; --d;
+        const int t = (lane >> 3) & 1, L = lane & 7;
+        const int gbase = (int)(threadIdx.x & 24u);          // first lane of this 8-lane team within the warp
+        const Band &b = t ? B[1] : B[0];
+        const int mscor = t ? max_scor[1] : max_scor[0];
+        uint8_t *rev = revbase + (size_t)t * lay.rev_n();
+        const uint32_t revcap = (uint32_t)lay.rev_n();
+        const int sh = 16 * t;
+        int i = t ? max_i[1] : max_i[0], j = t ? max_j[1] : max_j[0];
+        int r = t ? max_r[1] : max_r[0], d = j - b.l_edge - r;
+        bool act = t ? on[1] : on[0];
+        const bool mine = act;
+        bool gap_open = false, ovf = false;
+        unsigned nmatch = 0;
+        int checksum = 0;
+        uint32_t n = 0;
+#define EMIT(c, ty) do { if (n < revcap) { if (L == 0) rev[n] = DIFFB(c, ty); } else ovf = true; ++n; } while (0)
+        while (__any_sync(ALL, act)) {
+          const int rr = r - L;
+          const bool valid = act && i - L >= b.s_left && j - L >= b.q_left;
+          uint32_t w = 0, csel = 0, rsel = 0;
+          if (valid) {
+            w = dirs[(d >> 1) * DIRW + (rr >> 2)];
+            csel = colarr[j - L - b.l_edge];
+            rsel = rowarr[rr + BPK_ROWPAD];
           }
+          const uint32_t dir = (w >> (sh + ((uint32_t)(rr & 3) << 2) + ((uint32_t)(d & 1) << 1))) & 3u;
+          int s = (int)(short)(bp_prmt(0u, T0, csel ^ rsel) >> sh);
+          if (general && valid)
+            s = (int)sc.S[((rowraw[rr + BPK_ROWPAD] >> (4 * t)) & 7u) * 8u + ((colraw[j - L - b.l_edge] >> (4 * t)) & 7u)];
+          const bool fast = valid && dir == 3u && s > 0 && !general;
+          const uint32_t m8 = (__ballot_sync(ALL, fast) >> gbase) & 0xffu;
+          const int run = __ffs((int)(~m8)) - 1;               // 0..8 leading cells of the run
+          const int src = gbase + (run & 7);
+          const uint32_t dir_g = __shfl_sync(ALL, dir, src);
+          const int s_g = __shfl_sync(ALL, s, src);
+          const bool valid_g = __shfl_sync(ALL, (int)valid, src) != 0;
+          if (act) {
+            if (run > 0) {
+              nmatch += (unsigned)run;
+              if (nmatch > 62u) { EMIT(61u, 0u); nmatch -= 62u; }
+              checksum += run * (int)sc.match;
+              gap_open = false;
+              i -= run; j -= run; r -= run;
+            }
+            if (run < 8) {
+              if (!valid_g || !dir_g) act = false;               // left the segment / start of the path
+              else if (dir_g == 3u) {
+                if (s_g > 0) {
+                  if (nmatch > 61u) { EMIT(61u, 0u); nmatch -= 61u; }
+                  else ++nmatch;
+                } else {
+                  EMIT(nmatch, 3u);
+                  nmatch = 0;
+                }
+                checksum += s_g;
+                gap_open = false;
+                --i; --j; --r;
+              } else {
+                if (gap_open) checksum -= sc.gap_ext;
+                else { checksum -= sc.gap_init; gap_open = true; }
+                if (dir_g & 1u) {
+                  EMIT(nmatch, 1u);
+                  nmatch = 0;
+                  --i; --r; ++d;
+                } else {
+                  EMIT(nmatch, 2u);
+                  nmatch = 0;
+                  --j; --d;
+                }
+              }
+            }
+          }
+        }
+        if (mine) {
           EMIT(nmatch, 3u);
           EMIT(0u, 0u);
-#undef EMIT
           if (ovf) flag = SMB_ERR_CAPACITY;
           else if (checksum != mscor) flag = SMB_ERRCODE_SWATSCOR;        // :767
           bi = i; bj = j; bn = n;
         }
+#undef EMIT
       }
+      __syncwarp();
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         PackTask &p = T[t];
-        const int fl = __shfl_sync(ALL, flag, t, LANES);
-        const int i = __shfl_sync(ALL, bi, t, LANES), j = __shfl_sync(ALL, bj, t, LANES);
-        const uint32_t n = __shfl_sync(ALL, bn, t, LANES);
+        const int fl = __shfl_sync(ALL, flag, 8 * t, LANES);
+        const int i = __shfl_sync(ALL, bi, 8 * t, LANES), j = __shfl_sync(ALL, bj, 8 * t, LANES);
+        const uint32_t n = __shfl_sync(ALL, bn, 8 * t, LANES);
         if (on[t] && fl) { p.err = fl; on[t] = false; }
         const int prof_start = j + 1, prof_end = max_j[t], np_start = i + 1, np_end = max_i[t];
         if (on[t] && prof_start + p.minscorlen > prof_end + 1) on[t] = false;        // :1379
         if (on[t] && (int)p.nres >= max_res) { p.err = SMB_ERR_CAPACITY; on[t] = false; }
         int f2 = 0;
         uint32_t u = p.diff_used;
-        if (on[t] && lane == t) {
+        if (on[t] && lane == 8 * t) {
           // diffStrReverse (diffstr.c:850-896) into the task's DiffStr area, then the result record
           const uint8_t *rev = revbase + (size_t)t * lay.rev_n();
           uint8_t *dfinal = out.diff + diff_off[p.tix];
@@ -423,8 +452,8 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
             }
           }
         }
-        f2 = __shfl_sync(ALL, f2, t, LANES);
-        u = __shfl_sync(ALL, u, t, LANES);
+        f2 = __shfl_sync(ALL, f2, 8 * t, LANES);
+        u = __shfl_sync(ALL, u, 8 * t, LANES);
         if (on[t] && f2) { p.err = f2; on[t] = false; }
         if (on[t]) {
           p.diff_used = u;
