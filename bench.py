@@ -43,9 +43,10 @@ READ_LEN = 150
 K, NSKIP = 13, 6
 ERR = 0.02
 # integer instructions per DP cell of the recurrences as restated for two 16-bit lanes per
-# register ("rooflines"): K2 8 per cell pair, K3 30 per cell pair
+# register ("rooflines"): K2 8 per cell pair; K3: ALU-pipe instructions per iteration of the
+# DP loop in the SASS (62, loop overhead included) / 4 cells (two packed cell pairs)
 K2_OPS_PER_CELL = 4.0
-K3_OPS_PER_CELL = 15.0
+K3_OPS_PER_CELL = 15.5
 
 
 def make_genome(seed=2, n=GENOME_LEN):
@@ -351,6 +352,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=250_000)
     ap.add_argument("--cpu-sample", type=int, default=250_000)
     ap.add_argument("--threads", type=int, default=0, help="host worker threads per GPU (0: 2 x cores / GPUs)")
+    ap.add_argument("--device-block", type=int, default=32000, help="reads per launch of the device-time pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cli", action="store_true")
     ap.add_argument("--no-paired", action="store_true")
@@ -380,11 +382,15 @@ def main():
             dist.barrier()
 
     # ---- pass 1: device-resident kernel times, ONE host worker (no overlapping streams) ----
+    # (blocks of DEVICE_BLOCK reads per launch: with one stream nothing else fills the tail of a launch,
+    # which the e2e pass does with the launches of its other workers' streams)
+    os.environ["SMALT_B200_BLOCK"] = str(args.device_block)
     m = Mapper(pref, 1)
     m.map_fastq_nocopy(fastq_text(reads[:max(1, n // 8)]))   # warm-up of this mapper
     m.map_fastq_nocopy(text)
     s1 = m.stats.as_dict()
     m.close()
+    del os.environ["SMALT_B200_BLOCK"]
     dev_ms = s1["k1_ms"] + s1["k2_ms"] + s1["k3_ms"]
 
     # ---- pass 2: e2e through the in-process driver, all host workers ----
@@ -448,8 +454,8 @@ def main():
                "achieved": k3_gcups, "peak": k3_peak, "unit": "GCUPS", "frac": k3_gcups / k3_peak if k3_peak else None,
                "traffic": 4.55e6,
                "note": "integer-issue bound (no tensor/HBM bound applies to this DP): peak = measured VIADDMNMX.S16x2 "
-                       "issue rate %.0f G thread-instr/s / %.1f instructions per cell (30 per packed cell pair); "
-                       "cells include the serial backtrace time" % (peaks[3], K3_OPS_PER_CELL)}
+                       "issue rate %.0f G thread-instr/s / %.1f ALU-pipe instructions per cell (62 per DP-loop iteration "
+                       "of two packed cell pairs in the SASS); cells include staging and backtrace time" % (peaks[3], K3_OPS_PER_CELL)}
     roof_k2 = {"kernel": "sw_score2_kernel (K2: SW score, 2 tasks per warp)", "bound": "alu", "achieved": k2_gcups,
                "peak": k2_peak, "unit": "GCUPS", "frac": k2_gcups / k2_peak if k2_peak else None, "traffic": 4.48e6,
                "note": "DPX issue bound: peak = measured VIADDMNMX.S16x2 issue rate %.0f G thread-instr/s / %.1f "
@@ -463,7 +469,8 @@ def main():
         "warmup": args.warmup, "ms_per_step": wall_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "i16x2 DPX (K2, K3), u32/u64 (K1)", "data": "synthetic",
         "config": dict(workload_config(n, world), host_workers_per_gpu=threads, host_cores=cores),
-        "timing": "value: reads / sum of CUDA-event kernel times of a step (one host worker, inputs resident); "
+        "timing": "value: reads / sum of CUDA-event kernel times of a step (one host worker = one stream, "
+                  "inputs resident, %d reads per launch); " % args.device_block +
                   "e2e: wall clock of smbm_map_fastq (FASTQ text in host memory -> SAM text in host memory), "
                   "max over ranks",
         "device_ms_per_step": dev_ms, "kernel_ms": kernel_ms, "sw_gcups": k2_gcups, "band_gcups": k3_gcups,

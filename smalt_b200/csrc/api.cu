@@ -574,7 +574,7 @@ static int band_align_fast(smb_ctx *ctx, const smb_band_task *tasks, int ntasks,
       mxrows = std::max(mxrows, (int)tasks[i].ref_len);
       mxread = std::max(mxread, (int)tasks[i].read_len);
     }
-    fprintf(stderr, "K3 plan: n %d pack %d half %d warp %d wide %d thread-classes %zu (", n, plan.pack_count, plan.half_count,
+    fprintf(stderr, "K3 plan: n %d pack8 %d pack %d half %d warp %d wide %d thread-classes %zu (", n, plan.pack8_count, plan.pack_count, plan.half_count,
             plan.warp_count, plan.wide_count, plan.classes.size());
     for (const auto &c : plan.classes) fprintf(stderr, " wcap %d x %d", c.wcap, c.count);
     fprintf(stderr, " ) max band %d rows %d read %d  %.3f ms\n", mxbw, mxrows, mxread, ms0);

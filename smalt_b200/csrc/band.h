@@ -68,6 +68,15 @@ SMB_HD int band_warp_lanes(int l_edge, int r_edge, int p_left, int p_right, int 
   const int bw = (bw0 <= 0) ? (b.q_len - b.q_left) : bw0;
   return bw <= BW_MAXDIAG / 2 ? 16 : (bw <= BW_MAXDIAG ? 32 : 0);
 }
+constexpr int BP8_MAXDIAG = 24;   // band_pack_kernel<8, 3>: eight lanes, three diagonals each
+// upper bound of the band width of every DP pass of a task (same bound as band_warp_lanes)
+SMB_HD int band_width_bound(int l_edge, int r_edge, int p_left, int p_right, int read_len,
+                            int u_left, int u_right, int ref_len) {
+  Band b;
+  if (band_init(b, l_edge, r_edge, p_left, p_right, read_len, u_left, u_right, ref_len)) return 0;
+  const int bw0 = r_edge - l_edge + 1;
+  return (bw0 <= 0) ? (b.q_len - b.q_left) : bw0;
+}
 // band_wide_kernel (band_wide.cu): four diagonals per lane, longer windows
 constexpr int BWD_MAXROWS = 512;
 constexpr int BWD_MAXREAD = 512;

@@ -329,22 +329,31 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, const Scori
   std::vector<int> wc((size_t)ntasks);
   int count[32] = {0};
   auto cls = [](int wcap) { int c = 0; while ((32 << c) < wcap) ++c; return c; };
-  constexpr int WARP_CLS = 31, HALF_CLS = 30, PACK_CLS = 29, WIDE_CLS = 28;  // pseudo classes of the warp kernels (last in `order`)
+  constexpr int WARP_CLS = 31, HALF_CLS = 30, PACK_CLS = 29, WIDE_CLS = 28, PACK8_CLS = 27;  // pseudo classes of the warp kernels (last in `order`)
   // packed 16-bit kernel: scores must stay far below 2^15 (band_pack.cu)
   const bool pen16 = sc.match > 0 && sc.match < 128 && sc.mismatch <= 0 && sc.mismatch > -128 && sc.gap_init >= 0 &&
                      sc.gap_init < 4000 && sc.gap_ext >= 0 && sc.gap_ext < 4000 && sc.S[5] == 0 && sc.S[5 * 8] == 0 &&
                      !getenv("SMB_NO_PACK");
   const bool no_wide = getenv("SMB_NO_WIDE") != nullptr;
-  plan.pack_maxrows = 0;
-  plan.pack_maxread = 0;
+  // the eight-tasks-per-warp geometry is measured slower on B200: opt-in
+  const bool no_pack8 = getenv("SMB_PACK8") == nullptr;
+  plan.pack_maxrows = plan.pack8_maxrows = 0;
+  plan.pack_maxread = plan.pack8_maxread = 0;
   for (int i = 0; i < ntasks; ++i) {
     const smb_band_task &t = h_tasks[i];
     const int wl = align ? band_warp_lanes(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left,
                                            t.u_right, (int)t.ref_len) : 0;
     if (wl == 16 && pen16 && (long long)t.read_len * sc.match <= 255) {   // (maximum keys of band_pack.cu: score < 256)
-      wc[(size_t)i] = PACK_CLS;
-      plan.pack_maxrows = std::max(plan.pack_maxrows, (int)t.ref_len);
-      plan.pack_maxread = std::max(plan.pack_maxread, (int)t.read_len);
+      if (!no_pack8 && band_width_bound(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
+                                        (int)t.ref_len) <= BP8_MAXDIAG) {
+        wc[(size_t)i] = PACK8_CLS;
+        plan.pack8_maxrows = std::max(plan.pack8_maxrows, (int)t.ref_len);
+        plan.pack8_maxread = std::max(plan.pack8_maxread, (int)t.read_len);
+      } else {
+        wc[(size_t)i] = PACK_CLS;
+        plan.pack_maxrows = std::max(plan.pack_maxrows, (int)t.ref_len);
+        plan.pack_maxread = std::max(plan.pack_maxread, (int)t.read_len);
+      }
     } else if (wl) {
       wc[(size_t)i] = wl == 16 ? HALF_CLS : WARP_CLS;
     } else if (align && !no_wide &&
@@ -363,10 +372,12 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, const Scori
   int fill[32];
   for (int c = 0; c < 32; ++c) fill[c] = start[c];
   for (int i = 0; i < ntasks; ++i) plan.order[(size_t)fill[wc[(size_t)i]]++] = i;
-  for (int c = 0; c < WIDE_CLS; ++c)
+  for (int c = 0; c < PACK8_CLS; ++c)
     if (count[c]) plan.classes.push_back(BandPlan::Class{32 << c, start[c], count[c]});
   plan.wide_start = start[WIDE_CLS];
   plan.wide_count = count[WIDE_CLS];
+  plan.pack8_start = start[PACK8_CLS];
+  plan.pack8_count = count[PACK8_CLS];
   plan.pack_start = start[PACK_CLS];
   plan.pack_count = count[PACK_CLS];
   plan.half_start = start[HALF_CLS];
@@ -410,7 +421,11 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
                             d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)
     return e;
   if (align && plan.pack_count &&
-      (e = launch_band_pack(sc, src, d_tasks, d_order + plan.pack_start, plan.pack_count, plan.pack_maxrows, plan.pack_maxread, d_ticket + 2,
+      (e = launch_band_pack(sc, src, d_tasks, d_order + plan.pack_start, plan.pack_count, 16, plan.pack_maxrows, plan.pack_maxread, d_ticket + 2,
+                            out, max_res, d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)
+    return e;
+  if (align && plan.pack8_count &&
+      (e = launch_band_pack(sc, src, d_tasks, d_order + plan.pack8_start, plan.pack8_count, 8, plan.pack8_maxrows, plan.pack8_maxread, d_ticket + 4,
                             out, max_res, d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)
     return e;
   if (align && plan.half_count &&

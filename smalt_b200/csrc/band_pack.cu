@@ -31,16 +31,20 @@
 namespace smb {
 
 constexpr int BPK_WARPS = 2;          // warps per CTA (4 half-warp groups, 8 tasks)
-constexpr int BPK_LANES = 16;
+// group geometry: LANES lanes advance two tasks, ND diagonals per lane (bands of at most LANES * ND
+// diagonals): <16, 2> or <8, 3> (eight tasks per warp, for bands of at most 24 diagonals - the
+// usual short-read band of 19 then keeps 7 of 8 lanes busy instead of 10 of 16)
 constexpr int BPK_STACK = 24;
 constexpr int BPK_ROWPAD = 16;        // rowarr index = r + BPK_ROWPAD
 
 struct PackLayout {                   // per-group shared memory for windows of at most R rows, reads of at most Q bases
   int R;                              // multiple of 32
   int Q;                              // multiple of 16
+  int lanes;                          // lanes per group
+  int rpw;                            // rows per direction word (and task): 16 / (2 * ND) = 4 or 2
   __host__ __device__ int rowarr_n() const { return R + 64; }
   __host__ __device__ int colarr_n() const { return R + 64; }
-  __host__ __device__ int dirw() const { return R / 4; }          // words per lane
+  __host__ __device__ int dirw() const { return R / rpw; }        // words per lane
   __host__ __device__ int rev_n() const { return R + Q + 16; }
   // 32-bit entries {PRMT selector of task 0, of task 1, validity of task 0 (0x80 / 0), of task 1};
   // the raw codes (general path only) in byte arrays behind them
@@ -49,7 +53,7 @@ struct PackLayout {                   // per-group shared memory for windows of 
   __host__ __device__ size_t rowraw_off() const { return colarr_off() + (size_t)colarr_n() * 4; }
   __host__ __device__ size_t colraw_off() const { return rowraw_off() + (size_t)rowarr_n(); }
   __host__ __device__ size_t dirs_off() const { return (colraw_off() + (size_t)colarr_n() + 15) & ~(size_t)15; }
-  __host__ __device__ size_t stk_off() const { return dirs_off() + (size_t)BPK_LANES * dirw() * 4; }
+  __host__ __device__ size_t stk_off() const { return dirs_off() + (size_t)lanes * dirw() * 4; }
   __host__ __device__ size_t rev_off() const { return stk_off() + (size_t)2 * 2 * BPK_STACK * 4; }
   __host__ __device__ size_t bytes() const { return (rev_off() + (size_t)2 * rev_n() + 15) & ~(size_t)15; }
 };
@@ -73,33 +77,33 @@ __device__ __forceinline__ uint32_t sel_ref(uint32_t r) { return r < 4u ? (r | (
 
 #define DIFFB(count, typ) ((uint8_t)((count) + ((typ) << 6)))
 
-// two cells (task 0 / task 1) of the restricted recurrence; ok2 = validity mask per half-word,
-// ok3 = ok2 & 0x00030003.  There is no packed subtract or compare: a > b is the sign of
-// b + ~a (= b - a - 1), turned into a half-word mask by PRMT sign replication; the complement
-// masks it yields are folded into the LOP3s that consume them.  The running maximum of a
-// diagonal is kept as the key (score << 8 | 255 - row): an unsigned packed max then keeps the
-// FIRST row of the largest score (alignment.c:826-830) - scores and rows are below 256 here.
-#define PACK_CELL(ok2, ok3, diag, ein, fin, s2, Hout, Eout, Fout, best, rinv2, dcode)                \
+// two cells (task 0 / task 1) of the restricted recurrence; ok2 = validity mask per half-word.
+// The ALU pipe (16 lanes per scheduler) bounds this kernel, so the cell is written for the fewest
+// ALU instructions, with shifts and constant adds as IMADs (FMA pipe):
+//  * there is no packed subtract or compare: h > m is the sign of h + ~m, made a mask by PRMT sign
+//    replication;
+//  * t = (dia && h > gap_init) ? h - gap_init : 0 = relu(h - gap_init) & dia & valid, one VIADDMNMX.RELU;
+//  * only t is masked by the cell's validity.  H, E and F of invalid cells need no masks: padding scores 0,
+//    E moves down a read column, F along a window row, H along a diagonal, and on each of those lines
+//    the invalid cells come first (before the read segment / band) - where nothing but zeros can
+//    arise without a t - or last, where no valid cell reads them;
+//  * the running maximum of a diagonal is kept on t (same order as h, and maxima count only when
+//    h > gap_init anyway, alignment.c:826-830) as the key (t << 8 | 255 - row): an unsigned packed max
+//    keeps the FIRST row of the largest score - scores and rows are below 256 here;
+//  * direction: DIA (3) if h > m, else 0 if m == 0, else COL (1) if E >= F, else ROW (2)
+//    = min(2m, 1 + (m != E)) | (dia ? 3 : 0).  The backtrace reads the codes of valid cells only.
+#define PACK_CELL(ok2, diag, ein, fin, s2, Hout, Eout, Fout, best, rinv2, dcode)                      \
   do {                                                                                                \
     const uint32_t h_ = __vadd2((diag), (s2));                                                        \
     const uint32_t m_ = __vmaxs2((ein), (fin));               /* E, F >= 0 */                          \
-    const uint32_t nm_ = ~m_;                                                                         \
-    const uint32_t ndia_ = bp_neg(__vadd2(h_, nm_));          /* h <= m */                             \
-    const uint32_t hn_ = __vmaxs2(h_, m_);                                                            \
-    const uint32_t x_ = __vadd2(h_, ngi2);                    /* h - gap_init */                       \
-    const uint32_t nx_ = bp_neg(__vadd2(h_, ngi2m1));         /* h - gap_init <= 0 */                  \
-    const uint32_t open_ = ~ndia_ & ~nx_ & (ok2);                                                     \
-    const uint32_t t_ = x_ & open_;                                                                   \
-    const uint32_t e_ = __viaddmax_s16x2_relu((ein), nge2, t_);                                       \
-    const uint32_t f_ = __viaddmax_s16x2_relu((fin), nge2, t_);                                       \
-    (best) = __vmaxu2((best), ((h_ & open_) << 8) | (rinv2));                                         \
-    const uint32_t nfgt_ = bp_neg(__vadd2((fin), ~(ein)));    /* F <= E: COL, else ROW */              \
-    const uint32_t pos_ = bp_neg(__vadd2(nm_, 0x00010001u));  /* m > 0 */                              \
-    const uint32_t b0_ = (pos_ & nfgt_) | ~ndia_, b1_ = (pos_ & ~nfgt_) | ~ndia_;                     \
-    (dcode) = ((b0_ & 0x00010001u) | (b1_ & ~0x00010001u)) & (ok3);                                   \
-    (Hout) = hn_ & (ok2);                                                                             \
-    (Eout) = e_ & (ok2);                                                                              \
-    (Fout) = f_ & (ok2);                                                                              \
+    const uint32_t ndia_ = bp_neg(__vadd2(h_, ~m_));          /* h <= m */                             \
+    const uint32_t t_ = __viaddmax_s16x2_relu(h_, ngi2, 0u) & ~ndia_ & (ok2);                         \
+    const uint32_t q_ = __vminu2(m_ ^ (ein), 0x00010001u);    /* F > E */                              \
+    (Eout) = __viaddmax_s16x2_relu((ein), nge2, t_);                                                  \
+    (Fout) = __viaddmax_s16x2_relu((fin), nge2, t_);                                                  \
+    (best) = __vmaxu2((best), t_ * 256u + (rinv2));                                                   \
+    (dcode) = __vminu2(m_ * 2u, q_ + 0x00010001u) | (~ndia_ & 0x00030003u);                           \
+    (Hout) = __vmaxs2(h_, m_);                                                                        \
   } while (0)
 
 struct PackTask {           // group-uniform state of one of the two tasks of a group
@@ -110,6 +114,7 @@ struct PackTask {           // group-uniform state of one of the two tasks of a 
   int l_edge0, r_edge0, p_left, p_right;
 };
 
+template <int LANES, int ND>
 __global__ void __launch_bounds__(BPK_WARPS * 32)
 band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__restrict__ tasks,
                  const int *__restrict__ order, const int ntasks, int *__restrict__ ticket,
@@ -117,7 +122,9 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
                  const uint32_t *__restrict__ diff_cap, const PackLayout lay) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   constexpr unsigned ALL = 0xffffffffu;
-  constexpr int LANES = BPK_LANES;
+  constexpr int TEAM = LANES / 2;              // lanes walking one task's path
+  constexpr int RPW = 8 / ND, RSH = RPW == 4 ? 2 : 1, BITS = 2 * ND;   // direction words: rows per half-word, bits per row
+  static_assert((LANES == 16 && ND == 2) || (LANES == 8 && ND == 3), "group geometry");
   const int lane = threadIdx.x & (LANES - 1);
   unsigned char *base = s_raw + (size_t)(threadIdx.x / LANES) * lay.bytes();
   uint32_t *rowarr = (uint32_t *)(base + lay.rowarr_off());
@@ -129,7 +136,6 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
   const int DIRW = lay.dirw();
   const uint32_t ngi2 = (uint32_t)((-sc.gap_init) & 0xffff) * 0x10001u;
   const uint32_t nge2 = (uint32_t)((-sc.gap_ext) & 0xffff) * 0x10001u;
-  const uint32_t ngi2m1 = (uint32_t)((-sc.gap_init - 1) & 0xffff) * 0x10001u;
   const uint32_t T0 = (uint32_t)(sc.match & 0xff) | ((uint32_t)(sc.mismatch & 0xff) * 0x01010100u);
   const int npairs = (ntasks + 1) >> 1;
   unsigned long long ncell_tot = 0;
@@ -189,17 +195,18 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
           if (band_init(b, p.l_edge0, p.r_edge0, p.p_left, p.p_right, p.qlen, s_left[t], s_right[t], p.rlen))
             on[t] = false;                                                   // :1333-1338
           else if (b.s_left >= b.s_len || b.band_width < 0) { p.err = SMB_ERRCODE_ASSERT; on[t] = false; }  // :459
-          else if (b.band_width > 2 * LANES || b.s_len - b.s_left > lay.R) { p.err = SMB_ERR_ARG; on[t] = false; }
+          else if (b.band_width > ND * LANES || b.s_len - b.s_left > lay.R) { p.err = SMB_ERR_ARG; on[t] = false; }
         }
       }
       const int nrows0 = on[0] ? B[0].s_len - B[0].s_left : 0, nrows1 = on[1] ? B[1].s_len - B[1].s_left : 0;
       const int bw0 = on[0] ? B[0].band_width : 0, bw1 = on[1] ? B[1].band_width : 0;
-      int iters = max(on[0] ? nrows0 + ((bw0 + 1) >> 1) - 1 : 0, on[1] ? nrows1 + ((bw1 + 1) >> 1) - 1 : 0);
-      iters = max(iters, __shfl_xor_sync(ALL, iters, 16));
+      int iters = max(on[0] ? nrows0 + (bw0 + ND - 1) / ND - 1 : 0, on[1] ? nrows1 + (bw1 + ND - 1) / ND - 1 : 0);
+#pragma unroll
+      for (int o = LANES; o < 32; o <<= 1) iters = max(iters, __shfl_xor_sync(ALL, iters, o));
       // ---- stage rows and columns of both tasks: {mask32, selector16, raw codes} ----
       bool hasx = false;
       // the trip count is the maximum over both half-warps: stage (as invalid) everything it can touch
-      const int nrow_e = iters + 2 * BPK_ROWPAD, ncol_e = min(iters + LANES + 2, lay.colarr_n());
+      const int nrow_e = iters + 2 * BPK_ROWPAD, ncol_e = min(iters + (ND - 1) * LANES + 2, lay.colarr_n());
       __syncwarp();
       for (int e = lane; e < min(nrow_e, lay.rowarr_n()); e += LANES) {
         const int r = e - BPK_ROWPAD;
@@ -240,54 +247,91 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
       __syncwarp();
 
       // ---------------- packed wavefront DP ----------------
-      const int dA = 2 * lane, dB = dA + 1;
-      const uint32_t hasA2 = (dA < bw0 ? 0xffffu : 0u) | (dA < bw1 ? 0xffff0000u : 0u);
-      const uint32_t hasB2 = (dB < bw0 ? 0xffffu : 0u) | (dB < bw1 ? 0xffff0000u : 0u);
-      uint32_t HA = 0, HB = 0, eA = 0, eB = 0, FA = 0, FB = 0;
-      uint32_t bestA = 0, bestB = 0, wdir = 0, cnt2 = 0;
+      // lane l owns diagonals ND*l .. ND*l + ND-1 and computes row it - l of each in iteration it:
+      // cell (r, d) reads H(r-1, d) (own register), E(r-1, d+1) (own previous value of the next diagonal,
+      // or the right neighbour's first diagonal of this iteration) and F(r, d-1) (own value just computed,
+      // or the left neighbour's last diagonal of the previous iteration)
+      uint32_t has[ND], H[ND], E[ND], F[ND], best[ND], col[ND], cmask[ND];
+#pragma unroll
+      for (int x = 0; x < ND; ++x) {
+        const int dx = ND * lane + x;
+        has[x] = (dx < bw0 ? 0xffffu : 0u) | (dx < bw1 ? 0xffff0000u : 0u);
+        H[x] = E[x] = F[x] = best[x] = 0;
+        col[x] = cmask[x] = 0;
+      }
+      uint32_t wdir = 0;
       uint32_t *const dirp = dirs + lane * DIRW;
       const int maxrows = max(nrows0, nrows1);
       // validity bytes -> half-word masks (sign replication of bytes 2 and 3)
 #define BP_VMASK(e) bp_prmt((e), 0u, 0xbbaau)
-      uint32_t colA = colarr[lane], cmaskA = BP_VMASK(colA);
+#pragma unroll
+      for (int x = 0; x + 1 < ND; ++x) {
+        col[x] = colarr[(ND - 1) * lane + x];
+        cmask[x] = BP_VMASK(col[x]);
+      }
       for (int it = 0; it < iters; ++it) {
         const int r = it - lane;
-        const uint32_t Fin = __shfl_up_sync(ALL, FB, 1, LANES);
+        const uint32_t Fin = __shfl_up_sync(ALL, F[ND - 1], 1, LANES);
         const uint32_t rw = rowarr[r + BPK_ROWPAD];
-        const uint32_t colB = colarr[it + lane + 1];
-        const uint32_t rmask = BP_VMASK(rw), cmaskB = BP_VMASK(colB);
-        const uint32_t okA = rmask & cmaskA & hasA2, okB = rmask & cmaskB & hasB2;
-        const uint32_t okA3 = okA & 0x00030003u, okB3 = okB & 0x00030003u;
-        uint32_t sA, sB;
+        col[ND - 1] = colarr[it + (ND - 1) * lane + ND - 1];
+        cmask[ND - 1] = BP_VMASK(col[ND - 1]);
+        const uint32_t rmask = BP_VMASK(rw);
+        uint32_t ok[ND], sx[ND], dc[ND];
+#pragma unroll
+        for (int x = 0; x < ND; ++x) ok[x] = rmask & cmask[x] & has[x];
         if (!general) {   // (PRMT reads the low 16 bits of the selector only)
-          sA = bp_prmt(0u, T0, colA ^ rw);
-          sB = bp_prmt(0u, T0, colB ^ rw);
+#pragma unroll
+          for (int x = 0; x < ND; ++x) sx[x] = bp_prmt(0u, T0, col[x] ^ rw);
         } else {   // X bases: per-cell table look-ups
-          const uint32_t rr = rowraw[r + BPK_ROWPAD], ca = colraw[it + lane], cb = colraw[it + lane + 1];
+          const uint32_t rr = rowraw[r + BPK_ROWPAD];
           const uint32_t r0 = rr & 7u, r1 = (rr >> 4) & 7u;
-          const int a0 = sc.S[r0 * 8u + (ca & 7u)], a1 = sc.S[r1 * 8u + ((ca >> 4) & 7u)];
-          const int b0 = sc.S[r0 * 8u + (cb & 7u)], b1 = sc.S[r1 * 8u + ((cb >> 4) & 7u)];
-          sA = ((uint32_t)a0 & 0xffffu) | ((uint32_t)a1 << 16);
-          sB = ((uint32_t)b0 & 0xffffu) | ((uint32_t)b1 << 16);
+#pragma unroll
+          for (int x = 0; x < ND; ++x) {
+            const uint32_t cx = colraw[it + (ND - 1) * lane + x];
+            const int a0 = sc.S[r0 * 8u + (cx & 7u)], a1 = sc.S[r1 * 8u + ((cx >> 4) & 7u)];
+            sx[x] = ((uint32_t)a0 & 0xffffu) | ((uint32_t)a1 << 16);
+          }
         }
         const uint32_t rinv2 = ((unsigned)r < 256u) ? (uint32_t)(255 - r) * 0x10001u : 0u;
-        uint32_t dcA, dcB;
-        PACK_CELL(okA, okA3, HA, eB, (lane == 0 ? 0u : Fin), sA, HA, eA, FA, bestA, rinv2, dcA);
-        const uint32_t Ein = __shfl_down_sync(ALL, eA, 1, LANES);
-        PACK_CELL(okB, okB3, HB, (lane == LANES - 1 ? 0u : Ein), FA, sB, HB, eB, FB, bestB, rinv2, dcB);
-        cnt2 += (okA & 0x00010001u) + (okB & 0x00010001u);
-        colA = colB;
-        cmaskA = cmaskB;
+#pragma unroll
+        for (int x = 0; x < ND; ++x) {
+          uint32_t ein, fin;
+          if (x + 1 < ND) ein = E[x + 1];
+          else {
+            const uint32_t Ein = __shfl_down_sync(ALL, E[0], 1, LANES);
+            ein = lane == LANES - 1 ? 0u : Ein;
+          }
+          if (x == 0) fin = lane == 0 ? 0u : Fin;
+          else fin = F[x - 1];
+          PACK_CELL(ok[x], H[x], ein, fin, sx[x], H[x], E[x], F[x], best[x], rinv2, dc[x]);
+        }
+#pragma unroll
+        for (int x = 0; x + 1 < ND; ++x) { col[x] = col[x + 1]; cmask[x] = cmask[x + 1]; }
         if (r >= 0 && r < maxrows) {   // (the trip count may exceed this group's rows: never store beyond them)
-          wdir |= (dcA | (dcB << 2)) << ((uint32_t)(r & 3) << 2);
-          if ((r & 3) == 3) { dirp[r >> 2] = wdir; wdir = 0; }
+          uint32_t code = dc[0];
+#pragma unroll
+          for (int x = 1; x < ND; ++x) code |= dc[x] << (2 * x);
+          wdir |= code << ((uint32_t)(r & (RPW - 1)) * BITS);
+          if ((r & (RPW - 1)) == RPW - 1) { dirp[r >> RSH] = wdir; wdir = 0; }
         }
       }
       {
         const int rlast = min(iters - 1 - lane, maxrows - 1);
-        if (rlast >= 0 && (rlast & 3) != 3) dirp[rlast >> 2] = wdir;
+        if (rlast >= 0 && (rlast & (RPW - 1)) != RPW - 1) dirp[rlast >> RSH] = wdir;
       }
-      ncell_tot += (cnt2 & 0xffffu) + (cnt2 >> 16);
+      // cells of this pass (statistics): per diagonal the rows whose read column lies in the segment
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+        if (on[t]) {
+          const Band &b = B[t];
+          const int nr = t ? nrows1 : nrows0;
+#pragma unroll
+          for (int x = 0; x < ND; ++x) {
+            const int dx = ND * lane + x;
+            const int lo = max(0, b.q_left - b.l_edge - dx), hi = min(nr, b.q_len - b.l_edge - dx);
+            if (dx < b.band_width && hi > lo) ncell_tot += (unsigned)(hi - lo);
+          }
+        }
       __syncwarp();
 
       // ---- per task: argmax, backtrace, result, recursion (lane t serves task t) ----
@@ -296,14 +340,16 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
       for (int t = 0; t < 2; ++t) {
         const Band &b = B[t];
         const int sh = 16 * t;
-        const uint32_t kA = (bestA >> sh) & 0xffffu, kB = (bestB >> sh) & 0xffffu;
-        const int bA = (int)(kA >> 8), bB = (int)(kB >> 8);
-        const int rA = 255 - (int)(kA & 0xffu), rB = 255 - (int)(kB & 0xffu);
-        int best = bA, bestr = rA, bestd = dA;
-        if (bB > best || (bB == best && bB > 0 && rB < bestr)) { best = bB; bestr = rB; bestd = dB; }
+        int bsc = 0, bestr = 0, bestd = 0;
+#pragma unroll
+        for (int x = 0; x < ND; ++x) {
+          const uint32_t kx = (best[x] >> sh) & 0xffffu;
+          const int bx = (kx >> 8) ? (int)(kx >> 8) + sc.gap_init : 0, rx = 255 - (int)(kx & 0xffu);
+          if (x == 0 || bx > bsc || (bx == bsc && bx > 0 && rx < bestr)) { bsc = bx; bestr = rx; bestd = ND * lane + x; }
+        }
         unsigned long long key = 0;
-        if (on[t] && best > 0)
-          key = ((unsigned long long)(unsigned)best << 32) | ((unsigned long long)(0xffffu - (unsigned)bestr) << 16) |
+        if (on[t] && bsc > 0)
+          key = ((unsigned long long)(unsigned)bsc << 32) | ((unsigned long long)(0xffffu - (unsigned)bestr) << 16) |
                 (unsigned long long)(0xffffu - (unsigned)(b.l_edge + bestr + bestd - b.q_left));
         for (int o = LANES / 2; o > 0; o >>= 1) {
           const unsigned long long other = __shfl_xor_sync(ALL, key, o, LANES);
@@ -315,7 +361,7 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
         max_i[t] = b.s_left + max_r[t];
         if (max_scor[t] < T[t].minscore) on[t] = false;                    // :1364
       }
-      // makeMetaFromTrack (alignment.c:628-781): lanes 8t..8t+7 of the group walk the path of task t
+      // makeMetaFromTrack (alignment.c:628-781): the TEAM lanes t*TEAM.. of the group walk the path of task t
       // together.  Sub-lane L looks at the cell L steps up the current diagonal; the run of cells
       // that continue as "DIA move onto a match" (ballot) is consumed at once - the reference's
       // per-match counter (`nmatch > 61 ? emit 61 : ++nmatch`, i.e. 62 rolls over to 1 with one
@@ -324,8 +370,8 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
       int bi = 0, bj = 0, flag = 0;
       uint32_t bn = 0;
       {
-        const int t = (lane >> 3) & 1, L = lane & 7;
-        const int gbase = (int)(threadIdx.x & 24u);          // first lane of this 8-lane team within the warp
+        const int t = lane / TEAM, L = lane & (TEAM - 1);
+        const int gbase = (int)(threadIdx.x & 31u & ~(unsigned)(TEAM - 1));   // first lane of this team within the warp
         const Band &b = t ? B[1] : B[0];
         const int mscor = t ? max_scor[1] : max_scor[0];
         uint8_t *rev = revbase + (size_t)t * lay.rev_n();
@@ -345,18 +391,18 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
           const bool valid = act && i - L >= b.s_left && j - L >= b.q_left;
           uint32_t w = 0, csel = 0, rsel = 0;
           if (valid) {
-            w = dirs[(d >> 1) * DIRW + (rr >> 2)];
+            w = dirs[(d / ND) * DIRW + (rr >> RSH)];
             csel = colarr[j - L - b.l_edge];
             rsel = rowarr[rr + BPK_ROWPAD];
           }
-          const uint32_t dir = (w >> (sh + ((uint32_t)(rr & 3) << 2) + ((uint32_t)(d & 1) << 1))) & 3u;
+          const uint32_t dir = (w >> (sh + (uint32_t)(rr & (RPW - 1)) * BITS + ((uint32_t)(d % ND) << 1))) & 3u;
           int s = (int)(short)(bp_prmt(0u, T0, csel ^ rsel) >> sh);
           if (general && valid)
             s = (int)sc.S[((rowraw[rr + BPK_ROWPAD] >> (4 * t)) & 7u) * 8u + ((colraw[j - L - b.l_edge] >> (4 * t)) & 7u)];
           const bool fast = valid && dir == 3u && s > 0 && !general;
-          const uint32_t m8 = (__ballot_sync(ALL, fast) >> gbase) & 0xffu;
-          const int run = __ffs((int)(~m8)) - 1;               // 0..8 leading cells of the run
-          const int src = gbase + (run & 7);
+          const uint32_t m8 = (__ballot_sync(ALL, fast) >> gbase) & ((1u << TEAM) - 1u);
+          const int run = __ffs((int)(~m8)) - 1;               // 0..TEAM leading cells of the run
+          const int src = gbase + (run & (TEAM - 1));
           const uint32_t dir_g = __shfl_sync(ALL, dir, src);
           const int s_g = __shfl_sync(ALL, s, src);
           const bool valid_g = __shfl_sync(ALL, (int)valid, src) != 0;
@@ -368,7 +414,7 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
               gap_open = false;
               i -= run; j -= run; r -= run;
             }
-            if (run < 8) {
+            if (run < TEAM) {
               if (!valid_g || !dir_g) act = false;               // left the segment / start of the path
               else if (dir_g == 3u) {
                 if (s_g > 0) {
@@ -410,16 +456,16 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         PackTask &p = T[t];
-        const int fl = __shfl_sync(ALL, flag, 8 * t, LANES);
-        const int i = __shfl_sync(ALL, bi, 8 * t, LANES), j = __shfl_sync(ALL, bj, 8 * t, LANES);
-        const uint32_t n = __shfl_sync(ALL, bn, 8 * t, LANES);
+        const int fl = __shfl_sync(ALL, flag, TEAM * t, LANES);
+        const int i = __shfl_sync(ALL, bi, TEAM * t, LANES), j = __shfl_sync(ALL, bj, TEAM * t, LANES);
+        const uint32_t n = __shfl_sync(ALL, bn, TEAM * t, LANES);
         if (on[t] && fl) { p.err = fl; on[t] = false; }
         const int prof_start = j + 1, prof_end = max_j[t], np_start = i + 1, np_end = max_i[t];
         if (on[t] && prof_start + p.minscorlen > prof_end + 1) on[t] = false;        // :1379
         if (on[t] && (int)p.nres >= max_res) { p.err = SMB_ERR_CAPACITY; on[t] = false; }
         int f2 = 0;
         uint32_t u = p.diff_used;
-        if (on[t] && lane == 8 * t) {
+        if (on[t] && lane == TEAM * t) {
           // diffStrReverse (diffstr.c:850-896) into the task's DiffStr area, then the result record
           const uint8_t *rev = revbase + (size_t)t * lay.rev_n();
           uint8_t *dfinal = out.diff + diff_off[p.tix];
@@ -452,8 +498,8 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
             }
           }
         }
-        f2 = __shfl_sync(ALL, f2, 8 * t, LANES);
-        u = __shfl_sync(ALL, u, 8 * t, LANES);
+        f2 = __shfl_sync(ALL, f2, TEAM * t, LANES);
+        u = __shfl_sync(ALL, u, TEAM * t, LANES);
         if (on[t] && f2) { p.err = f2; on[t] = false; }
         if (on[t]) {
           p.diff_used = u;
@@ -488,35 +534,51 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
   if (lane == 0 && ncell_tot) atomicAdd(out.cells, ncell_tot);
 }
 
-cudaError_t launch_band_pack(const Scoring &sc, const SeqSrc &src, const smb_band_task *d_tasks,
-                             const int *d_order, int ntasks, int max_rows, int max_read, int *d_ticket, BandOut out,
-                             int max_res, const uint64_t *d_diff_off, const uint32_t *d_diff_cap, int sm_count,
-                             cudaStream_t st, int *nlaunch) {
-  if (ntasks <= 0) return cudaSuccess;
+template <int LANES, int ND>
+static cudaError_t launch_pack_t(const Scoring &sc, const SeqSrc &src, const smb_band_task *d_tasks, const int *d_order,
+                                 int ntasks, int max_rows, int max_read, int *d_ticket, BandOut out, int max_res,
+                                 const uint64_t *d_diff_off, const uint32_t *d_diff_cap, int sm_count, cudaStream_t st,
+                                 int *nlaunch) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(band_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(band_pack_kernel<LANES, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
   cudaError_t e = cudaMemsetAsync(d_ticket, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
-  PackLayout lay{(max_rows + 31) & ~31, (max_read + 15) & ~15};
+  PackLayout lay{(max_rows + 31) & ~31, (max_read + 15) & ~15, LANES, 8 / ND};
   if (lay.R < 32) lay.R = 32;
   if (lay.Q < 16 || lay.Q > BW_MAXREAD) lay.Q = BW_MAXREAD;
-  const size_t smem = lay.bytes() * BPK_WARPS * 2;
-  const int per_cta = BPK_WARPS * 4;   // tasks per CTA
+  constexpr int groups = BPK_WARPS * 32 / LANES;
+  const size_t smem = lay.bytes() * groups;
+  const int per_cta = groups * 2;   // tasks per CTA
   int grid = (ntasks + per_cta - 1) / per_cta;
   const int cap = sm_count * 16;
   if (grid > cap) grid = cap;
-  band_pack_kernel<<<grid, BPK_WARPS * 32, smem, st>>>(sc, src, d_tasks, d_order, ntasks, d_ticket, out, max_res,
-                                                       d_diff_off, d_diff_cap, lay);
+  band_pack_kernel<LANES, ND><<<grid, BPK_WARPS * 32, smem, st>>>(sc, src, d_tasks, d_order, ntasks, d_ticket, out,
+                                                                  max_res, d_diff_off, d_diff_cap, lay);
   ++*nlaunch;
   return cudaGetLastError();
 }
 
+// lanes = 16: bands of at most 32 diagonals, four tasks per warp; lanes = 8: at most 24, eight tasks per warp
+cudaError_t launch_band_pack(const Scoring &sc, const SeqSrc &src, const smb_band_task *d_tasks,
+                             const int *d_order, int ntasks, int lanes, int max_rows, int max_read, int *d_ticket,
+                             BandOut out, int max_res, const uint64_t *d_diff_off, const uint32_t *d_diff_cap,
+                             int sm_count, cudaStream_t st, int *nlaunch) {
+  if (ntasks <= 0) return cudaSuccess;
+  if (lanes == 8)
+    return launch_pack_t<8, 3>(sc, src, d_tasks, d_order, ntasks, max_rows, max_read, d_ticket, out, max_res, d_diff_off,
+                               d_diff_cap, sm_count, st, nlaunch);
+  return launch_pack_t<16, 2>(sc, src, d_tasks, d_order, ntasks, max_rows, max_read, d_ticket, out, max_res, d_diff_off,
+                              d_diff_cap, sm_count, st, nlaunch);
+}
+
 cudaError_t warm_band_pack() {
   cudaFuncAttributes a;
-  return cudaFuncGetAttributes(&a, band_pack_kernel);
+  cudaError_t e = cudaFuncGetAttributes(&a, band_pack_kernel<16, 2>);
+  if (e != cudaSuccess) return e;
+  return cudaFuncGetAttributes(&a, band_pack_kernel<8, 3>);
 }
 
 }  // namespace smb

@@ -94,7 +94,8 @@ struct BandPlan {
   std::vector<Class> classes;
   int warp_start = 0, warp_count = 0;   // K3 tasks of band_warp_kernel<32> (band_warp.cu)
   int half_start = 0, half_count = 0;   // ... and of band_warp_kernel<16> (two tasks per warp)
-  int pack_start = 0, pack_count = 0, pack_maxrows = 0, pack_maxread = 0;   // band_pack_kernel (four tasks per warp, s16x2)
+  int pack_start = 0, pack_count = 0, pack_maxrows = 0, pack_maxread = 0;   // band_pack_kernel<16, 2> (four tasks per warp, s16x2)
+  int pack8_start = 0, pack8_count = 0, pack8_maxrows = 0, pack8_maxread = 0;   // band_pack_kernel<8, 3> (eight tasks per warp)
   int wide_start = 0, wide_count = 0;   // band_wide_kernel (band_wide.cu: bands <= 128 diagonals, windows <= 512 rows)
 };
 void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, const Scoring &sc, BandPlan &plan);
@@ -116,7 +117,7 @@ cudaError_t launch_band_wide(const Scoring &sc, const SeqSrc &src, const smb_ban
                              cudaStream_t st, int *nlaunch);
 cudaError_t warm_band_wide();
 cudaError_t launch_band_pack(const Scoring &sc, const SeqSrc &src, const smb_band_task *d_tasks,
-                             const int *d_order, int ntasks, int max_rows, int max_read, int *d_ticket, BandOut out, int max_res,
+                             const int *d_order, int ntasks, int lanes, int max_rows, int max_read, int *d_ticket, BandOut out, int max_res,
                              const uint64_t *d_diff_off, const uint32_t *d_diff_cap, int sm_count,
                              cudaStream_t st, int *nlaunch);
 cudaError_t warm_band_pack();

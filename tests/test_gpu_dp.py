@@ -268,10 +268,16 @@ def _run_records(ctx, recs):
                 assert _unpack(res, first, diff, i) == r["results"], i
 
 
-def test_band_align_packed_kernel_geometry(ctx, orc):
+@pytest.mark.parametrize("pack8", [False, True])
+def test_band_align_packed_kernel_geometry(ctx, orc, pack8, monkeypatch):
     """Geometries at the limits of the four-tasks-per-warp kernel (band_pack.cu): window lengths
     around multiples of 32 up to 256 rows, bands of 1..32 diagonals, very different task sizes
-    paired in one half-warp, odd task counts and batches of one."""
+    paired in one half-warp, odd task counts and batches of one.  pack8: bands of at most 24
+    diagonals go to the <8 lanes, 3 diagonals> instance of the kernel (opt-in, SMB_PACK8)."""
+    if pack8:
+        monkeypatch.setenv("SMB_PACK8", "1")
+    else:
+        monkeypatch.delenv("SMB_PACK8", raising=False)
     rng = np.random.default_rng(105)
     pairs, args = [], []
     for rows in (31, 32, 33, 63, 64, 65, 159, 160, 161, 191, 192, 193, 223, 224, 255, 256):
