@@ -331,7 +331,7 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, const Scori
   auto cls = [](int wcap) { int c = 0; while ((32 << c) < wcap) ++c; return c; };
   constexpr int WARP_CLS = 31, HALF_CLS = 30, PACK_CLS = 29, WIDE_CLS = 28, PACK8_CLS = 27;  // pseudo classes of the warp kernels (last in `order`)
   // packed 16-bit kernel: scores must stay far below 2^15 (band_pack.cu)
-  const bool pen16 = sc.match > 0 && sc.match < 128 && sc.mismatch <= 0 && sc.mismatch > -128 && sc.gap_init >= 0 &&
+  const bool pen16 = sc.match > 0 && sc.match < 128 && sc.mismatch <= 0 && sc.mismatch > -128 && sc.gap_init > 0 &&
                      sc.gap_init < 4000 && sc.gap_ext >= 0 && sc.gap_ext < 4000 && sc.S[5] == 0 && sc.S[5 * 8] == 0 &&
                      !getenv("SMB_NO_PACK");
   const bool no_wide = getenv("SMB_NO_WIDE") != nullptr;

@@ -19,8 +19,8 @@
 //    {match, mismatch x3, 0 x4}: selector = (read selector) xor (window selector), where N and
 //    padding select a zero entry through the sign-replication mode (see sel_read / sel_ref);
 //  * per DP pass the window rows and read columns of both tasks are staged in shared memory as
-//    64-bit entries {validity mask of the two halves, PRMT selector, raw codes}; cell validity
-//    (band, read segment, row range - different for the two tasks) is one AND of three masks;
+//    PRMT selectors (+ raw codes for the general path); rows and columns outside the window / read
+//    segment are staged as padding (score 0) and need no validity test (see the DP loop);
 //  * direction codes: 4 bits per row and task (two diagonals of the lane), four rows per word;
 //  * argmax, backtrace, DiffStr reversal, result emission and the recursion are per task as in
 //    band_warp.cu, except that the eight lanes 8t..8t+7 of the half-warp walk the path of task t together.
@@ -44,9 +44,9 @@ struct PackLayout {                   // per-group shared memory for windows of 
   int rpw;                            // rows per direction word (and task): 16 / (2 * ND) = 4 or 2
   __host__ __device__ int rowarr_n() const { return R + 64; }
   __host__ __device__ int colarr_n() const { return R + 64; }
-  __host__ __device__ int dirw() const { return R / rpw; }        // words per lane
+  __host__ __device__ int dirw() const { return (R + lanes) / rpw + 1; }   // words per lane: one row per DP iteration
   __host__ __device__ int rev_n() const { return R + Q + 16; }
-  // 32-bit entries {PRMT selector of task 0, of task 1, validity of task 0 (0x80 / 0), of task 1};
+  // 32-bit entries {PRMT selector of task 0, of task 1};
   // the raw codes (general path only) in byte arrays behind them
   __host__ __device__ size_t rowarr_off() const { return 0; }
   __host__ __device__ size_t colarr_off() const { return (size_t)rowarr_n() * 4; }
@@ -77,13 +77,13 @@ __device__ __forceinline__ uint32_t sel_ref(uint32_t r) { return r < 4u ? (r | (
 
 #define DIFFB(count, typ) ((uint8_t)((count) + ((typ) << 6)))
 
-// two cells (task 0 / task 1) of the restricted recurrence; ok2 = validity mask per half-word.
+// two cells (task 0 / task 1) of the restricted recurrence; ok2 = 0xffff per half-word whose diagonal lies in the band.
 // The ALU pipe (16 lanes per scheduler) bounds this kernel, so the cell is written for the fewest
 // ALU instructions, with shifts and constant adds as IMADs (FMA pipe):
 //  * there is no packed subtract or compare: h > m is the sign of h + ~m, made a mask by PRMT sign
 //    replication;
 //  * t = (dia && h > gap_init) ? h - gap_init : 0 = relu(h - gap_init) & dia & valid, one VIADDMNMX.RELU;
-//  * only t is masked by the cell's validity.  H, E and F of invalid cells need no masks: padding scores 0,
+//  * only t is masked (by the band).  H, E and F of cells outside need no masks: padding scores 0,
 //    E moves down a read column, F along a window row, H along a diagonal, and on each of those lines
 //    the invalid cells come first (before the read segment / band) - where nothing but zeros can
 //    arise without a t - or last, where no valid cell reads them;
@@ -97,7 +97,7 @@ __device__ __forceinline__ uint32_t sel_ref(uint32_t r) { return r < 4u ? (r | (
     const uint32_t h_ = __vadd2((diag), (s2));                                                        \
     const uint32_t m_ = __vmaxs2((ein), (fin));               /* E, F >= 0 */                          \
     const uint32_t ndia_ = bp_neg(__vadd2(h_, ~m_));          /* h <= m */                             \
-    const uint32_t t_ = __viaddmax_s16x2_relu(h_, ngi2, 0u) & ~ndia_ & (ok2);                         \
+    const uint32_t t_ = __viaddmax_s16x2_relu(h_, ngi2, ngi2) & ~ndia_ & (ok2);   /* (ngi2 < 0: any operand the RELU removes) */                         \
     const uint32_t q_ = __vminu2(m_ ^ (ein), 0x00010001u);    /* F > E */                              \
     (Eout) = __viaddmax_s16x2_relu((ein), nge2, t_);                                                  \
     (Fout) = __viaddmax_s16x2_relu((fin), nge2, t_);                                                  \
@@ -203,6 +203,7 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
       int iters = max(on[0] ? nrows0 + (bw0 + ND - 1) / ND - 1 : 0, on[1] ? nrows1 + (bw1 + ND - 1) / ND - 1 : 0);
 #pragma unroll
       for (int o = LANES; o < 32; o <<= 1) iters = max(iters, __shfl_xor_sync(ALL, iters, o));
+      iters = (iters + RPW - 1) & ~(RPW - 1);                  // whole direction words (the extra rows are padding)
       // ---- stage rows and columns of both tasks: {mask32, selector16, raw codes} ----
       bool hasx = false;
       // the trip count is the maximum over both half-warps: stage (as invalid) everything it can touch
@@ -210,37 +211,35 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
       __syncwarp();
       for (int e = lane; e < min(nrow_e, lay.rowarr_n()); e += LANES) {
         const int r = e - BPK_ROWPAD;
-        uint32_t mask = 0, sel = 0, raw = 0;
+        uint32_t sel = 0, raw = 0;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const int nr = t ? nrows1 : nrows0;
           uint32_t c = 7u;
           if (on[t] && r >= 0 && r < nr) {
             c = ref_base(src, T[t].packed != 0, T[t].ref_off, (uint32_t)(B[t].s_left + r));
-            mask |= 0x800000u << (8 * t);
           }
           hasx |= c == 4u;
           sel |= sel_ref(c) << (8 * t);
           raw |= c << (4 * t);
         }
-        rowarr[e] = mask | sel;
+        rowarr[e] = sel;
         rowraw[e] = (uint8_t)raw;
       }
       for (int x = lane; x < ncol_e; x += LANES) {
-        uint32_t mask = 0, sel = 0, raw = 0;
+        uint32_t sel = 0, raw = 0;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const int j = B[t].l_edge + x;
           uint32_t c = 7u;
           if (on[t] && j >= B[t].q_left && j < B[t].q_len) {
             c = read_base(src.arena, T[t].read_off, (uint32_t)T[t].qlen, T[t].rc != 0, (uint32_t)j);
-            mask |= 0x800000u << (8 * t);
           }
           hasx |= c == 4u;
           sel |= sel_read(c) << (8 * t);
           raw |= c << (4 * t);
         }
-        colarr[x] = mask | sel;
+        colarr[x] = sel;
         colraw[x] = (uint8_t)raw;
       }
       const bool general = __any_sync(ALL, hasx);
@@ -251,74 +250,70 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
       // cell (r, d) reads H(r-1, d) (own register), E(r-1, d+1) (own previous value of the next diagonal,
       // or the right neighbour's first diagonal of this iteration) and F(r, d-1) (own value just computed,
       // or the left neighbour's last diagonal of the previous iteration)
-      uint32_t has[ND], H[ND], E[ND], F[ND], best[ND], col[ND], cmask[ND];
+      // Cells outside the window rows or the read segment need no masks: they are staged as padding
+      // (score 0).  Above and to the left of the valid cells nothing but zeros can arise (t = relu(0 - gap_init));
+      // below and to the right a t can arise, but E, F and H there only flow on to other such cells, and
+      // their keys lose against the valid cell their score came from (same t at an earlier row of the
+      // same diagonal, or a larger t if a gap lies between: gap_init > 0).  Only the diagonals beyond the
+      // band (has) must not open gaps, because E moves from diagonal d + 1 to d.
+      uint32_t has[ND], H[ND], E[ND], F[ND], best[ND], col[ND];
 #pragma unroll
       for (int x = 0; x < ND; ++x) {
         const int dx = ND * lane + x;
         has[x] = (dx < bw0 ? 0xffffu : 0u) | (dx < bw1 ? 0xffff0000u : 0u);
         H[x] = E[x] = F[x] = best[x] = 0;
-        col[x] = cmask[x] = 0;
+        col[x] = 0;
       }
-      uint32_t wdir = 0;
       uint32_t *const dirp = dirs + lane * DIRW;
-      const int maxrows = max(nrows0, nrows1);
-      // validity bytes -> half-word masks (sign replication of bytes 2 and 3)
-#define BP_VMASK(e) bp_prmt((e), 0u, 0xbbaau)
+      const uint32_t not_first = lane == 0 ? 0u : 0xffffffffu, not_last = lane == LANES - 1 ? 0u : 0xffffffffu;
 #pragma unroll
-      for (int x = 0; x + 1 < ND; ++x) {
-        col[x] = colarr[(ND - 1) * lane + x];
-        cmask[x] = BP_VMASK(col[x]);
-      }
-      for (int it = 0; it < iters; ++it) {
-        const int r = it - lane;
-        const uint32_t Fin = __shfl_up_sync(ALL, F[ND - 1], 1, LANES);
-        const uint32_t rw = rowarr[r + BPK_ROWPAD];
-        col[ND - 1] = colarr[it + (ND - 1) * lane + ND - 1];
-        cmask[ND - 1] = BP_VMASK(col[ND - 1]);
-        const uint32_t rmask = BP_VMASK(rw);
-        uint32_t ok[ND], sx[ND], dc[ND];
+      for (int x = 0; x + 1 < ND; ++x) col[x] = colarr[(ND - 1) * lane + x];
+      // direction words hold the RPW rows of RPW consecutive ITERATIONS (row it - lane): the position of a
+      // row in its word is then the same for all lanes and known at compile time
+      for (int it0 = 0; it0 < iters; it0 += RPW) {
+        uint32_t wdir = 0;
 #pragma unroll
-        for (int x = 0; x < ND; ++x) ok[x] = rmask & cmask[x] & has[x];
-        if (!general) {   // (PRMT reads the low 16 bits of the selector only)
+        for (int k = 0; k < RPW; ++k) {
+          const int it = it0 + k;
+          const int r = it - lane;
+          const uint32_t Fin = __shfl_up_sync(ALL, F[ND - 1], 1, LANES) & not_first;
+          const uint32_t rw = rowarr[r + BPK_ROWPAD];
+          col[ND - 1] = colarr[it + (ND - 1) * lane + ND - 1];
+          uint32_t sx[ND], dc[ND];
+          if (!general) {   // (PRMT reads the low 16 bits of the selector only)
 #pragma unroll
-          for (int x = 0; x < ND; ++x) sx[x] = bp_prmt(0u, T0, col[x] ^ rw);
-        } else {   // X bases: per-cell table look-ups
-          const uint32_t rr = rowraw[r + BPK_ROWPAD];
-          const uint32_t r0 = rr & 7u, r1 = (rr >> 4) & 7u;
+            for (int x = 0; x < ND; ++x) sx[x] = bp_prmt(0u, T0, col[x] ^ rw);
+          } else {   // X bases: per-cell table look-ups
+            const uint32_t rr = rowraw[r + BPK_ROWPAD];
+            const uint32_t r0 = rr & 7u, r1 = (rr >> 4) & 7u;
+#pragma unroll
+            for (int x = 0; x < ND; ++x) {
+              const uint32_t cx = colraw[it + (ND - 1) * lane + x];
+              const int a0 = sc.S[r0 * 8u + (cx & 7u)], a1 = sc.S[r1 * 8u + ((cx >> 4) & 7u)];
+              sx[x] = ((uint32_t)a0 & 0xffffu) | ((uint32_t)a1 << 16);
+            }
+          }
+          // key of the row: 255 - r (rows beyond 255 do not exist; the drain iterations get 0)
+          const uint32_t rinv2 = (uint32_t)min(max(255 - r, 0), 255) * 0x10001u;
 #pragma unroll
           for (int x = 0; x < ND; ++x) {
-            const uint32_t cx = colraw[it + (ND - 1) * lane + x];
-            const int a0 = sc.S[r0 * 8u + (cx & 7u)], a1 = sc.S[r1 * 8u + ((cx >> 4) & 7u)];
-            sx[x] = ((uint32_t)a0 & 0xffffu) | ((uint32_t)a1 << 16);
+            uint32_t ein, fin;
+            if (x + 1 < ND) ein = E[x + 1];
+            else ein = __shfl_down_sync(ALL, E[0], 1, LANES) & not_last;
+            if (x == 0) fin = Fin;
+            else fin = F[x - 1];
+            PACK_CELL(has[x], H[x], ein, fin, sx[x], H[x], E[x], F[x], best[x], rinv2, dc[x]);
           }
-        }
-        const uint32_t rinv2 = ((unsigned)r < 256u) ? (uint32_t)(255 - r) * 0x10001u : 0u;
 #pragma unroll
-        for (int x = 0; x < ND; ++x) {
-          uint32_t ein, fin;
-          if (x + 1 < ND) ein = E[x + 1];
-          else {
-            const uint32_t Ein = __shfl_down_sync(ALL, E[0], 1, LANES);
-            ein = lane == LANES - 1 ? 0u : Ein;
-          }
-          if (x == 0) fin = lane == 0 ? 0u : Fin;
-          else fin = F[x - 1];
-          PACK_CELL(ok[x], H[x], ein, fin, sx[x], H[x], E[x], F[x], best[x], rinv2, dc[x]);
-        }
-#pragma unroll
-        for (int x = 0; x + 1 < ND; ++x) { col[x] = col[x + 1]; cmask[x] = cmask[x + 1]; }
-        if (r >= 0 && r < maxrows) {   // (the trip count may exceed this group's rows: never store beyond them)
+          for (int x = 0; x + 1 < ND; ++x) col[x] = col[x + 1];
           uint32_t code = dc[0];
 #pragma unroll
           for (int x = 1; x < ND; ++x) code |= dc[x] << (2 * x);
-          wdir |= code << ((uint32_t)(r & (RPW - 1)) * BITS);
-          if ((r & (RPW - 1)) == RPW - 1) { dirp[r >> RSH] = wdir; wdir = 0; }
+          wdir |= code << (k * BITS);
         }
+        dirp[it0 >> RSH] = wdir;
       }
-      {
-        const int rlast = min(iters - 1 - lane, maxrows - 1);
-        if (rlast >= 0 && (rlast & (RPW - 1)) != RPW - 1) dirp[rlast >> RSH] = wdir;
-      }
+      __syncwarp();
       // cells of this pass (statistics): per diagonal the rows whose read column lies in the segment
 #pragma unroll
       for (int t = 0; t < 2; ++t)
@@ -387,15 +382,15 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
         uint32_t n = 0;
 #define EMIT(c, ty) do { if (n < revcap) { if (L == 0) rev[n] = DIFFB(c, ty); } else ovf = true; ++n; } while (0)
         while (__any_sync(ALL, act)) {
-          const int rr = r - L;
+          const int rr = r - L, itw = rr + d / ND;          // direction words are laid out by DP iteration
           const bool valid = act && i - L >= b.s_left && j - L >= b.q_left;
           uint32_t w = 0, csel = 0, rsel = 0;
           if (valid) {
-            w = dirs[(d / ND) * DIRW + (rr >> RSH)];
+            w = dirs[(d / ND) * DIRW + (itw >> RSH)];
             csel = colarr[j - L - b.l_edge];
             rsel = rowarr[rr + BPK_ROWPAD];
           }
-          const uint32_t dir = (w >> (sh + (uint32_t)(rr & (RPW - 1)) * BITS + ((uint32_t)(d % ND) << 1))) & 3u;
+          const uint32_t dir = (w >> (sh + (uint32_t)(itw & (RPW - 1)) * BITS + ((uint32_t)(d % ND) << 1))) & 3u;
           int s = (int)(short)(bp_prmt(0u, T0, csel ^ rsel) >> sh);
           if (general && valid)
             s = (int)sc.S[((rowraw[rr + BPK_ROWPAD] >> (4 * t)) & 7u) * 8u + ((colraw[j - L - b.l_edge] >> (4 * t)) & 7u)];
