@@ -19,7 +19,7 @@
 //    {match, mismatch x3, 0 x4}: selector = (read selector) xor (window selector), where N and
 //    padding select a zero entry through the sign-replication mode (see sel_read / sel_ref);
 //  * per DP pass the window rows and read columns of both tasks are staged in shared memory as
-//    PRMT selectors (+ raw codes for the general path); rows and columns outside the window / read
+//    PRMT selectors (decoded from whole source words); rows and columns outside the window / read
 //    segment are staged as padding (score 0) and need no validity test (see the DP loop);
 //  * direction codes: 4 bits per row and task (two diagonals of the lane), four rows per word;
 //  * argmax, backtrace, DiffStr reversal, result emission and the recursion are per task as in
@@ -46,13 +46,10 @@ struct PackLayout {                   // per-group shared memory for windows of 
   __host__ __device__ int colarr_n() const { return R + 64; }
   __host__ __device__ int dirw() const { return (R + lanes) / rpw + 1; }   // words per lane: one row per DP iteration
   __host__ __device__ int rev_n() const { return R + Q + 16; }
-  // 32-bit entries {PRMT selector of task 0, of task 1};
-  // the raw codes (general path only) in byte arrays behind them
+  // 16-bit entries {PRMT selector of task 0, of task 1}
   __host__ __device__ size_t rowarr_off() const { return 0; }
-  __host__ __device__ size_t colarr_off() const { return (size_t)rowarr_n() * 4; }
-  __host__ __device__ size_t rowraw_off() const { return colarr_off() + (size_t)colarr_n() * 4; }
-  __host__ __device__ size_t colraw_off() const { return rowraw_off() + (size_t)rowarr_n(); }
-  __host__ __device__ size_t dirs_off() const { return (colraw_off() + (size_t)colarr_n() + 15) & ~(size_t)15; }
+  __host__ __device__ size_t colarr_off() const { return (size_t)rowarr_n() * 2; }
+  __host__ __device__ size_t dirs_off() const { return (colarr_off() + (size_t)colarr_n() * 2 + 15) & ~(size_t)15; }
   __host__ __device__ size_t stk_off() const { return dirs_off() + (size_t)lanes * dirw() * 4; }
   __host__ __device__ size_t rev_off() const { return stk_off() + (size_t)2 * 2 * BPK_STACK * 4; }
   __host__ __device__ size_t bytes() const { return (rev_off() + (size_t)2 * rev_n() + 15) & ~(size_t)15; }
@@ -71,9 +68,14 @@ __device__ __forceinline__ uint32_t bp_gt(uint32_t a, uint32_t b) { return bp_ne
 // PRMT selector byte (two nibbles: low byte, high byte of the 16-bit score) of a read base ...
 // (bit 2 of both nibbles flipped: the table is the SECOND source of the PRMT, bytes 4..7, because as
 // first source ptxas overwrites it with the result and copies it afresh for every cell)
-__device__ __forceinline__ uint32_t sel_read(uint32_t q) { return (q < 4u ? (q | ((q | 8u) << 4)) : 0xC4u) ^ 0x44u; }
+// (X gets a code of its own, 0x81 / 0x4D: tasks with an X take the table path, which reads the base
+// codes back from the selectors)
+__device__ __forceinline__ uint32_t sel_read(uint32_t q) { return q < 4u ? ((q | ((q | 8u) << 4)) ^ 0x44u) : (q == 4u ? 0x81u : 0x80u); }
 // ... and of a window base; N / padding: sign-replicate a non-negative table entry -> 0
-__device__ __forceinline__ uint32_t sel_ref(uint32_t r) { return r < 4u ? (r | (r << 4)) : 0x4Cu; }
+__device__ __forceinline__ uint32_t sel_ref(uint32_t r) { return r < 4u ? (r | (r << 4)) : (r == 4u ? 0x4Du : 0x4Cu); }
+// base codes from selector bytes (N and padding both come back as 7: the same zero row of the table)
+__device__ __forceinline__ uint32_t code_read(uint32_t s) { return (s & 0x40u) ? (s & 3u) : ((s & 1u) ? 4u : 7u); }
+__device__ __forceinline__ uint32_t code_ref(uint32_t s) { return (s & 0x40u) ? ((s & 1u) ? 4u : 7u) : (s & 3u); }
 
 #define DIFFB(count, typ) ((uint8_t)((count) + ((typ) << 6)))
 
@@ -91,18 +93,18 @@ __device__ __forceinline__ uint32_t sel_ref(uint32_t r) { return r < 4u ? (r | (
 //    h > gap_init anyway, alignment.c:826-830) as the key (t << 8 | 255 - row): an unsigned packed max
 //    keeps the FIRST row of the largest score - scores and rows are below 256 here;
 //  * direction: DIA (3) if h > m, else 0 if m == 0, else COL (1) if E >= F, else ROW (2)
-//    = min(2m, 1 + (m != E)) | (dia ? 3 : 0).  The backtrace reads the codes of valid cells only.
+//    = min(m + m, min((m ^ E) + 1, 2)) | (dia ? 3 : 0), two VIADDMNMX.U16x2.  The backtrace reads the codes of valid cells only.
 #define PACK_CELL(ok2, diag, ein, fin, s2, Hout, Eout, Fout, best, rinv2, dcode)                      \
   do {                                                                                                \
     const uint32_t h_ = __vadd2((diag), (s2));                                                        \
     const uint32_t m_ = __vmaxs2((ein), (fin));               /* E, F >= 0 */                          \
     const uint32_t ndia_ = bp_neg(__vadd2(h_, ~m_));          /* h <= m */                             \
     const uint32_t t_ = __viaddmax_s16x2_relu(h_, ngi2, ngi2) & ~ndia_ & (ok2);   /* (ngi2 < 0: any operand the RELU removes) */                         \
-    const uint32_t q_ = __vminu2(m_ ^ (ein), 0x00010001u);    /* F > E */                              \
+    const uint32_t sel_ = __viaddmin_u16x2(m_ ^ (ein), 0x00010001u, 0x00020002u);  /* E >= F ? 1 : 2 */  \
     (Eout) = __viaddmax_s16x2_relu((ein), nge2, t_);                                                  \
     (Fout) = __viaddmax_s16x2_relu((fin), nge2, t_);                                                  \
     (best) = __vmaxu2((best), t_ * 256u + (rinv2));                                                   \
-    (dcode) = __vminu2(m_ * 2u, q_ + 0x00010001u) | (~ndia_ & 0x00030003u);                           \
+    (dcode) = __viaddmin_u16x2(m_, m_, sel_) | (~ndia_ & 0x00030003u);                                \
     (Hout) = __vmaxs2(h_, m_);                                                                        \
   } while (0)
 
@@ -127,9 +129,8 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
   static_assert((LANES == 16 && ND == 2) || (LANES == 8 && ND == 3), "group geometry");
   const int lane = threadIdx.x & (LANES - 1);
   unsigned char *base = s_raw + (size_t)(threadIdx.x / LANES) * lay.bytes();
-  uint32_t *rowarr = (uint32_t *)(base + lay.rowarr_off());
-  uint32_t *colarr = (uint32_t *)(base + lay.colarr_off());
-  uint8_t *rowraw = base + lay.rowraw_off(), *colraw = base + lay.colraw_off();
+  uint16_t *rowarr = (uint16_t *)(base + lay.rowarr_off());
+  uint16_t *colarr = (uint16_t *)(base + lay.colarr_off());
   uint32_t *dirs = (uint32_t *)(base + lay.dirs_off());
   int *stk = (int *)(base + lay.stk_off());               // [task][l/r][BPK_STACK]
   uint8_t *revbase = base + lay.rev_off();
@@ -204,43 +205,69 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
 #pragma unroll
       for (int o = LANES; o < 32; o <<= 1) iters = max(iters, __shfl_xor_sync(ALL, iters, o));
       iters = (iters + RPW - 1) & ~(RPW - 1);                  // whole direction words (the extra rows are padding)
-      // ---- stage rows and columns of both tasks: {mask32, selector16, raw codes} ----
+      // ---- stage rows and columns: PRMT selectors, task t in byte t of a 16-bit entry ----
+      // Everything the trip count (the maximum over the groups of the warp) can touch is padding first;
+      // then whole source words are decoded: ten window bases per word of the packed reference, four
+      // read bases per aligned word of the arena.
       bool hasx = false;
-      // the trip count is the maximum over both half-warps: stage (as invalid) everything it can touch
-      const int nrow_e = iters + 2 * BPK_ROWPAD, ncol_e = min(iters + (ND - 1) * LANES + 2, lay.colarr_n());
+      const int nrow_e = min(iters + 2 * BPK_ROWPAD, lay.rowarr_n()), ncol_e = min(iters + (ND - 1) * LANES + 2, lay.colarr_n());
+      uint8_t *const rowsel = (uint8_t *)rowarr, *const colsel = (uint8_t *)colarr;
       __syncwarp();
-      for (int e = lane; e < min(nrow_e, lay.rowarr_n()); e += LANES) {
-        const int r = e - BPK_ROWPAD;
-        uint32_t sel = 0, raw = 0;
+      for (int e = lane; e < (nrow_e + 1) >> 1; e += LANES) ((uint32_t *)rowarr)[e] = 0x4C4C4C4Cu;   // sel_ref(7)
+      for (int e = lane; e < (ncol_e + 1) >> 1; e += LANES) ((uint32_t *)colarr)[e] = 0x80808080u;   // sel_read(7)
+      __syncwarp();
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int nr = t ? nrows1 : nrows0;
-          uint32_t c = 7u;
-          if (on[t] && r >= 0 && r < nr) {
-            c = ref_base(src, T[t].packed != 0, T[t].ref_off, (uint32_t)(B[t].s_left + r));
-          }
-          hasx |= c == 4u;
-          sel |= sel_ref(c) << (8 * t);
-          raw |= c << (4 * t);
-        }
-        rowarr[e] = sel;
-        rowraw[e] = (uint8_t)raw;
-      }
-      for (int x = lane; x < ncol_e; x += LANES) {
-        uint32_t sel = 0, raw = 0;
+      for (int t = 0; t < 2; ++t) {
+        if (!on[t]) continue;
+        const PackTask &p = T[t];
+        const Band &b = B[t];
+        const int nr = t ? nrows1 : nrows0;
+        if (p.packed) {
+          const uint64_t b0 = p.ref_off + (uint64_t)b.s_left, w0 = b0 / 10u;
+          const int r0 = (int)(b0 - w0 * 10u);
+          const int nw = (r0 + nr + 9) / 10;
+          for (int k = lane; k < nw; k += LANES) {
+            const uint32_t w = __ldg(src.packed + w0 + (uint64_t)k);
+            const int rb = k * 10 - r0;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int j = B[t].l_edge + x;
-          uint32_t c = 7u;
-          if (on[t] && j >= B[t].q_left && j < B[t].q_len) {
-            c = read_base(src.arena, T[t].read_off, (uint32_t)T[t].qlen, T[t].rc != 0, (uint32_t)j);
+            for (int q = 0; q < 10; ++q) {
+              const uint32_t c = (w >> (27 - 3 * q)) & 7u;
+              if ((unsigned)(rb + q) < (unsigned)nr) {
+                rowsel[2 * (rb + q + BPK_ROWPAD) + t] = (uint8_t)sel_ref(c);
+                hasx |= c == 4u;
+              }
+            }
           }
-          hasx |= c == 4u;
-          sel |= sel_read(c) << (8 * t);
-          raw |= c << (4 * t);
+        } else {
+          for (int r = lane; r < nr; r += LANES) {
+            const uint32_t c = (uint32_t)(__ldg(src.arena + p.ref_off + (uint64_t)(b.s_left + r)) & 7u);
+            rowsel[2 * (r + BPK_ROWPAD) + t] = (uint8_t)sel_ref(c);
+            hasx |= c == 4u;
+          }
         }
-        colarr[x] = sel;
-        colraw[x] = (uint8_t)raw;
+        // read columns j in [jlo, jhi): source bytes s = j, or qlen - 1 - j for the reverse complement
+        const int jlo = max(b.q_left, b.l_edge), jhi = min(b.q_len, b.l_edge + ncol_e);
+        if (jhi > jlo) {
+          const int s_lo = p.rc ? p.qlen - jhi : jlo, s_hi = p.rc ? p.qlen - jlo : jhi;
+          const uint64_t a0 = (p.read_off + (uint64_t)s_lo) & ~(uint64_t)3;
+          const int sb = (int)((long long)a0 - (long long)p.read_off);      // source index of byte 0 of word 0
+          const int nwd = (s_hi - sb + 3) >> 2;
+          const uint32_t *const wp = (const uint32_t *)(src.arena + a0);
+          for (int k = lane; k < nwd; k += LANES) {
+            const uint32_t w = __ldg(wp + k);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int si = sb + 4 * k + q;
+              uint32_t c = (w >> (8 * q)) & 7u;
+              if (si >= s_lo && si < s_hi) {
+                const int j = p.rc ? p.qlen - 1 - si : si;
+                if (p.rc && c < 4u) c = 3u - c;
+                colsel[2 * (j - b.l_edge) + t] = (uint8_t)sel_read(c);
+                hasx |= c == 4u;
+              }
+            }
+          }
+        }
       }
       const bool general = __any_sync(ALL, hasx);
       __syncwarp();
@@ -284,17 +311,15 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
 #pragma unroll
             for (int x = 0; x < ND; ++x) sx[x] = bp_prmt(0u, T0, col[x] ^ rw);
           } else {   // X bases: per-cell table look-ups
-            const uint32_t rr = rowraw[r + BPK_ROWPAD];
-            const uint32_t r0 = rr & 7u, r1 = (rr >> 4) & 7u;
+            const uint32_t r0 = code_ref(rw & 0xffu), r1 = code_ref((rw >> 8) & 0xffu);
 #pragma unroll
             for (int x = 0; x < ND; ++x) {
-              const uint32_t cx = colraw[it + (ND - 1) * lane + x];
-              const int a0 = sc.S[r0 * 8u + (cx & 7u)], a1 = sc.S[r1 * 8u + ((cx >> 4) & 7u)];
+              const int a0 = sc.S[r0 * 8u + code_read(col[x] & 0xffu)], a1 = sc.S[r1 * 8u + code_read((col[x] >> 8) & 0xffu)];
               sx[x] = ((uint32_t)a0 & 0xffffu) | ((uint32_t)a1 << 16);
             }
           }
           // key of the row: 255 - r (rows beyond 255 do not exist; the drain iterations get 0)
-          const uint32_t rinv2 = (uint32_t)min(max(255 - r, 0), 255) * 0x10001u;
+          const uint32_t rinv2 = (uint32_t)__viaddmin_s32_relu(lane + 255 - it0, -k, 255) * 0x10001u;
 #pragma unroll
           for (int x = 0; x < ND; ++x) {
             uint32_t ein, fin;
@@ -393,7 +418,7 @@ band_pack_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
           const uint32_t dir = (w >> (sh + (uint32_t)(itw & (RPW - 1)) * BITS + ((uint32_t)(d % ND) << 1))) & 3u;
           int s = (int)(short)(bp_prmt(0u, T0, csel ^ rsel) >> sh);
           if (general && valid)
-            s = (int)sc.S[((rowraw[rr + BPK_ROWPAD] >> (4 * t)) & 7u) * 8u + ((colraw[j - L - b.l_edge] >> (4 * t)) & 7u)];
+            s = (int)sc.S[code_ref((rsel >> (8 * t)) & 0xffu) * 8u + code_read((csel >> (8 * t)) & 0xffu)];
           const bool fast = valid && dir == 3u && s > 0 && !general;
           const uint32_t m8 = (__ballot_sync(ALL, fast) >> gbase) & ((1u << TEAM) - 1u);
           const int run = __ffs((int)(~m8)) - 1;               // 0..TEAM leading cells of the run
