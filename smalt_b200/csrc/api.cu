@@ -64,6 +64,7 @@ struct smb_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_done = nullptr;  // blocking-sync event: waiting host threads sleep instead of spinning
+  BandSide side;                  // K3: stream of the small launches beside the packed kernel
   HostBuf stage;                  // pinned staging for the library's own host-side arrays
   DevBuf cmp;                     // K3 output compaction scratch
   DevBuf ticket;                  // work counters of persistent kernels
@@ -174,7 +175,10 @@ int smb_ctx_create(smb_ctx **out, int device) {
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_done, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&ctx->ev_done, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->side.stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->side.fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->side.join, cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return SMB_ERR_CUDA;
   }
@@ -202,6 +206,9 @@ void smb_ctx_destroy(smb_ctx *ctx) {
   if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->side.fork) cudaEventDestroy(ctx->side.fork);
+  if (ctx->side.join) cudaEventDestroy(ctx->side.join);
+  if (ctx->side.stream) cudaStreamDestroy(ctx->side.stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -453,7 +460,7 @@ static int band_align_pass(smb_ctx *ctx, const smb_band_task *tasks, const std::
   CU(h2d(d_order, plan.order.data(), (size_t)n * sizeof(int), st));
   CU(cudaEventRecord(ctx->ev0, st));
   CU(launch_band(ctx->sc, ctx->src, ctx->tasks.as<smb_band_task>(), plan, d_order, true, nullptr, bo, max_res,
-                 d_dir_off, ctx->dirs.as<uint32_t>(), d_diff_off, d_diff_cap, d_gring, ctx->ticket.as<int>(), ctx->sm_count, st, nlaunch));
+                 d_dir_off, ctx->dirs.as<uint32_t>(), d_diff_off, d_diff_cap, d_gring, ctx->ticket.as<int>(), ctx->sm_count, st, nlaunch, &ctx->side));
   CU(cudaEventRecord(ctx->ev1, st));
   h_res.resize((size_t)n * max_res);
   h_nres.resize((size_t)n);
@@ -553,7 +560,7 @@ static int band_align_fast(smb_ctx *ctx, const smb_band_task *tasks, int ntasks,
   CU(cudaEventRecord(ctx->ev0, st));
   CU(launch_band(ctx->sc, ctx->src, ctx->tasks.as<smb_band_task>(), plan, d_order, true, nullptr, bo, max_res,
                  d_dir_off, ctx->dirs.as<uint32_t>(), d_diff_off, d_diff_cap, ctx->scratch.as<uint32_t>(), ctx->ticket.as<int>(),
-                 ctx->sm_count, st, &nl));
+                 ctx->sm_count, st, &nl, &ctx->side));
   CU(launch_compact_scan(d_nres, d_dused, d_errs, n, d_tile_res, d_tile_diff, d_tot, d_first, d_diff_first, st, &nl));
   CU(cudaEventRecord(ctx->ev1, st));
   CompactTotals *h_tot = (CompactTotals *)((char *)ctx->stage.p + stage_tail);

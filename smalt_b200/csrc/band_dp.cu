@@ -391,7 +391,8 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
                         int32_t *d_scores, BandOut out, int max_res,
                         const uint64_t *d_dir_off, uint32_t *d_dirs,
                         const uint64_t *d_diff_off, const uint32_t *d_diff_cap,
-                        uint32_t *d_gring, int *d_ticket, int sm_count, cudaStream_t st, int *nlaunch) {
+                        uint32_t *d_gring, int *d_ticket, int sm_count, cudaStream_t main_st, int *nlaunch,
+                        const BandSide *side) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(band_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -399,6 +400,17 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
     attr_set = true;
   }
   cudaError_t e;
+  // the packed kernels take (nearly) all tasks of a short-read batch; whatever else the batch holds goes
+  // to the side stream
+  const bool packed_any = align && (plan.pack_count || plan.pack8_count);
+  const bool other_any = !plan.classes.empty() || (align && (plan.wide_count || plan.half_count || plan.warp_count));
+  const bool fork = side && side->stream && packed_any && other_any;
+  cudaStream_t st = main_st;
+  if (fork) {
+    if ((e = cudaEventRecord(side->fork, main_st)) != cudaSuccess) return e;
+    if ((e = cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return e;
+    st = side->stream;
+  }
   for (const BandPlan::Class &c : plan.classes) {
     const int grid = (c.count + BAND_THREADS - 1) / BAND_THREADS;
     BandArgs a{d_order + c.start, c.count, c.wcap, nullptr, max_res};
@@ -420,6 +432,16 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
       (e = launch_band_wide(sc, src, d_tasks, d_order + plan.wide_start, plan.wide_count, d_ticket + 3, out, max_res,
                             d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)
     return e;
+  if (align && plan.half_count &&
+      (e = launch_band_warp(sc, src, d_tasks, d_order + plan.half_start, plan.half_count, 16, d_ticket, out, max_res,
+                            d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)
+    return e;
+  if (align && plan.warp_count &&
+      (e = launch_band_warp(sc, src, d_tasks, d_order + plan.warp_start, plan.warp_count, 32, d_ticket + 1, out,
+                            max_res, d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)
+    return e;
+  if (fork && (e = cudaEventRecord(side->join, side->stream)) != cudaSuccess) return e;
+  st = main_st;
   if (align && plan.pack_count &&
       (e = launch_band_pack(sc, src, d_tasks, d_order + plan.pack_start, plan.pack_count, 16, plan.pack_maxrows, plan.pack_maxread, d_ticket + 2,
                             out, max_res, d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)
@@ -428,13 +450,7 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
       (e = launch_band_pack(sc, src, d_tasks, d_order + plan.pack8_start, plan.pack8_count, 8, plan.pack8_maxrows, plan.pack8_maxread, d_ticket + 4,
                             out, max_res, d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)
     return e;
-  if (align && plan.half_count &&
-      (e = launch_band_warp(sc, src, d_tasks, d_order + plan.half_start, plan.half_count, 16, d_ticket, out, max_res,
-                            d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)
-    return e;
-  if (align && plan.warp_count)
-    return launch_band_warp(sc, src, d_tasks, d_order + plan.warp_start, plan.warp_count, 32, d_ticket + 1, out,
-                            max_res, d_diff_off, d_diff_cap, sm_count, st, nlaunch);
+  if (fork && (e = cudaStreamWaitEvent(main_st, side->join, 0)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 

@@ -100,12 +100,19 @@ struct BandPlan {
 };
 void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, const Scoring &sc, BandPlan &plan);
 size_t band_gring_words(const BandPlan &plan);
+// side stream for the small launches of a batch (the few tasks the packed kernel does not take): they
+// run beside the packed kernel instead of adding their latency behind it
+struct BandSide {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
 cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_task *d_tasks,
                         const BandPlan &plan, const int *d_order, bool align,
                         int32_t *d_scores, BandOut out, int max_res,
                         const uint64_t *d_dir_off, uint32_t *d_dirs,
                         const uint64_t *d_diff_off, const uint32_t *d_diff_cap,
-                        uint32_t *d_gring, int *d_ticket, int sm_count, cudaStream_t st, int *nlaunch);
+                        uint32_t *d_gring, int *d_ticket, int sm_count, cudaStream_t st, int *nlaunch,
+                        const BandSide *side = nullptr);
 cudaError_t launch_band_warp(const Scoring &sc, const SeqSrc &src, const smb_band_task *d_tasks,
                              const int *d_order, int ntasks, int lanes, int *d_ticket, BandOut out, int max_res,
                              const uint64_t *d_diff_off, const uint32_t *d_diff_cap, int sm_count,
