@@ -384,6 +384,23 @@ struct SeedWarpLayout {   // per-warp shared memory carve-up for reads of at mos
   __host__ __device__ size_t bytes() const { return (qmask_off() + (size_t)qmax + 15) & ~(size_t)15; }
 };
 
+// marks read positions [q0, q0 + len) in a bit mask and returns how many of them were not marked
+// before (the per-base loops of hashhit.c:838-850 and :1120-1131, a word at a time)
+__device__ __forceinline__ uint32_t cov_add(uint32_t *cov, uint32_t q0, uint32_t len) {
+  uint32_t added = 0, w = q0 >> 5, sft = q0 & 31u;
+  while (len) {
+    const uint32_t take = min(len, 32u - sft);
+    const uint32_t m = (take >= 32u ? 0xffffffffu : ((1u << take) - 1u)) << sft;
+    const uint32_t old = cov[w];
+    added += __popc(m & ~old);
+    cov[w] = old | m;
+    len -= take;
+    sft = 0;
+    ++w;
+  }
+  return added;
+}
+
 __global__ void __launch_bounds__(SEEDW_WARPS * 32)
 seed_warp_kernel(const Index ix0, const uint8_t *__restrict__ arena, const SeedArgs a, const SeedWarpLayout lay) {
   extern __shared__ __align__(16) unsigned char s_raw[];
@@ -518,8 +535,12 @@ seed_warp_kernel(const Index ix0, const uint8_t *__restrict__ arena, const SeedA
     else if (maxcover > qlen - (uint32_t)nskip) maxcover = qlen - (uint32_t)nskip;
     if (mincover > maxcover) { mincover = 0; maxcover = qlen; }
     // getHitInfoMaxRank (hashhit.c:769-891): rank lists of the frames, one frame per lane
+    // (frame of every seed once, by all lanes; s_word is free again after the sort)
+    uint8_t *const s_fr = (uint8_t *)s_word;
+    for (uint32_t i = lane; i < n_seeds; i += 32) s_fr[i] = (uint8_t)(s_qoffs[s_sidx[i]] % (uint32_t)nskip);
+    __syncwarp();
     if (lane < nskip)
-      for (uint32_t i = 0; i < n_seeds; ++i) fcnt += (s_qoffs[s_sidx[i]] % (uint32_t)nskip) == (uint32_t)lane;
+      for (uint32_t i = 0; i < n_seeds; ++i) fcnt += s_fr[i] == (uint8_t)lane;
     int incl = fcnt;
     for (int o = 1; o < 32; o <<= 1) {
       const int v = __shfl_up_sync(FULL, incl, o);
@@ -529,7 +550,7 @@ seed_warp_kernel(const Index ix0, const uint8_t *__restrict__ arena, const SeedA
     if (lane < nskip) {
       int c = 0;
       for (uint32_t i = 0; i < n_seeds; ++i)
-        if ((s_qoffs[s_sidx[i]] % (uint32_t)nskip) == (uint32_t)lane) s_frame[fstart + c++] = (unsigned short)i;
+        if (s_fr[i] == (uint8_t)lane) s_frame[fstart + c++] = (unsigned short)i;
     }
     // seeds whose hits sum up to at most maxhit_total (the reference reads one element past the
     // end here, hashhit.c:823; its value cannot change the result)
@@ -550,10 +571,7 @@ seed_warp_kernel(const Index ix0, const uint8_t *__restrict__ arena, const SeedA
       int i = 0;
       for (; i < fcnt && cover <= maxcover && (cover < mincover || s_frame[fstart + i] <= n); ++i) {
         const uint32_t q0 = s_qoffs[s_sidx[s_frame[fstart + i]]];
-        for (uint32_t q = q0; q < q0 + (uint32_t)ktup - 1u; ++q) {
-          const uint32_t bit = 1u << (q & 31u);
-          if (!(cov[q >> 5] & bit)) { cov[q >> 5] |= bit; ++cover; }
-        }
+        cover += cov_add(cov, q0, (uint32_t)ktup - 1u);
       }
       if (i > 0 && s_frame[fstart + i - 1] > nmax) nmax = s_frame[fstart + i - 1];
     }
@@ -571,10 +589,7 @@ seed_warp_kernel(const Index ix0, const uint8_t *__restrict__ arena, const SeedA
       uint32_t cover = 0;
       for (int i = 0; i < fcnt && s_frame[fstart + i] < inf.seed_rank; ++i) {
         const uint32_t q0 = s_qoffs[s_sidx[s_frame[fstart + i]]];
-        for (uint32_t q = q0; q < q0 + (uint32_t)ktup; ++q) {
-          const uint32_t bit = 1u << (q & 31u);
-          if (!(cov[q >> 5] & bit)) { cov[q >> 5] |= bit; ++cover; }
-        }
+        cover += cov_add(cov, q0, (uint32_t)ktup);
       }
       dmin = cover;
       maxc = cover;
