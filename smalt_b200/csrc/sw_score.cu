@@ -209,7 +209,8 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
       const uint32_t h = __viaddmax_s16x2_relu(diag, s2, zero);                             \
       diag = H[c];                                                                          \
       const uint32_t hn = __vimax3_s16x2(h, E[c], F);                                       \
-      best = __vmaxs2(best, hn);                                                            \
+      if (c & 1) best = __vimax3_s16x2(best, H[c - 1], hn);   /* two columns per VIMNMX3 */  \
+      else if (c == C - 1) best = __vmaxs2(best, hn);                                       \
       const uint32_t tt = __viaddmax_s16x2(hn, ngi2, 0x80008000u);                          \
       E[c] = __viaddmax_s16x2(E[c], nge2, tt);                                              \
       F = __viaddmax_s16x2_relu(F, nge2, tt);                                               \
