@@ -447,21 +447,21 @@ def main():
     k1_bytes = nlook * (8 + 4 * np.ceil(np.log2(bucket + 1)) + 8)
     k1_gbs = k1_bytes / (s1["k1_ms"] * 1e-3) / 1e9
     kernel_ms = {"k1_seed_hits": s1["k1_ms"], "k2_sw_score": s1["k2_ms"], "k3_band_align": s1["k3_ms"]}
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch (one block of 8192 reads) from the
-    # ncu --set full captures under profiles/ (r1b_ncu_full_k2/k3_raw_selected.csv) - both kernels are
-    # bound by the integer ALU pipe (sm__pipe_alu_cycles_active 93 % / 69 %), not by memory
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch (one block of 32000 reads) from the
+    # ncu --set full captures under profiles/ (r1c_ncu_full_k1/k2/k3_raw_selected.csv) - K2 and K3 are
+    # bound by the integer ALU pipe (sm__pipe_alu_cycles_active 93 % / 72 %), not by memory
     roof_k3 = {"kernel": "band_pack_kernel (K3: banded DP + backtrace, 4 tasks per warp)", "bound": "alu",
                "achieved": k3_gcups, "peak": k3_peak, "unit": "GCUPS", "frac": k3_gcups / k3_peak if k3_peak else None,
-               "traffic": 4.55e6,
+               "traffic": 13.1e6,
                "note": "integer-issue bound (no tensor/HBM bound applies to this DP): peak = measured VIADDMNMX.S16x2 "
                        "issue rate %.0f G thread-instr/s / %.1f ALU-pipe instructions per cell (62 per DP-loop iteration "
                        "of two packed cell pairs in the SASS); cells include staging and backtrace time" % (peaks[3], K3_OPS_PER_CELL)}
     roof_k2 = {"kernel": "sw_score2_kernel (K2: SW score, 2 tasks per warp)", "bound": "alu", "achieved": k2_gcups,
-               "peak": k2_peak, "unit": "GCUPS", "frac": k2_gcups / k2_peak if k2_peak else None, "traffic": 4.48e6,
+               "peak": k2_peak, "unit": "GCUPS", "frac": k2_gcups / k2_peak if k2_peak else None, "traffic": 11.8e6,
                "note": "DPX issue bound: peak = measured VIADDMNMX.S16x2 issue rate %.0f G thread-instr/s / %.1f "
                        "instructions per cell (8 per packed cell pair)" % (peaks[3], K2_OPS_PER_CELL)}
     roof_k1 = {"kernel": "seed_kernel + hits_kernel (K1)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak,
-               "unit": "GB/s", "frac": k1_gbs / hbm_peak, "traffic": 12.0e6, "peak_source": peak_src,
+               "unit": "GB/s", "frac": k1_gbs / hbm_peak, "traffic": 37.3e6, "peak_source": peak_src,
                "note": "dependent 4-byte index probes (latency bound); the 5 Mb index (11 MB) is L2 resident"}
     dominant = max(kernel_ms, key=kernel_ms.get)
     line = {
