@@ -493,8 +493,17 @@ def main():
         with open(fq, "wb") as f:
             f.write(text)
         exe = os.path.join(ROOT, "smalt_b200", "bin", "smalt_b200")
-        dt, err = run_cli(exe, cores, pref, fq, os.path.join(tmp, "cli.sam"))
-        line["e2e_cli"] = ({"value": n / dt, "unit": "reads/s", "seconds": dt,
+        # (the driver is still tearing down the contexts of the passes above when this process's mappers
+        # are closed: a program started right then waits seconds in CUDA start-up; two runs, the faster)
+        runs = []
+        for _ in range(2):
+            time.sleep(2.0)
+            dt, err = run_cli(exe, cores, pref, fq, os.path.join(tmp, "cli.sam"))
+            if not dt:
+                break
+            runs.append(dt)
+        dt = min(runs) if runs else None
+        line["e2e_cli"] = ({"value": n / dt, "unit": "reads/s", "seconds": dt, "runs_seconds": runs,
                             "what": "whole `smalt_b200 map -n %d -O` program on the same %d reads" % (cores, n)}
                            if dt else {"value": None, "unavailable": err})
     if world == 1 and not args.no_cpu_baseline:
