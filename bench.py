@@ -43,9 +43,10 @@ READ_LEN = 150
 K, NSKIP = 13, 6
 ERR = 0.02
 # integer instructions per DP cell of the recurrences as restated for two 16-bit lanes per
-# register ("rooflines"): K2 8 per cell pair; K3: ALU-pipe instructions per iteration of the
-# DP loop in the SASS (62, loop overhead included) / 4 cells (two packed cell pairs)
-K2_OPS_PER_CELL = 4.0
+# register ("rooflines"): K2 6.5 ALU-pipe instructions per cell pair (LOP3, PRMT, 3 x VIADDMNMX,
+# 1.5 x VIMNMX3; the eighth, H - gap_init, is an IMAD on the FMA pipe); K3: ALU-pipe instructions per
+# iteration of the DP loop in the SASS (62, loop overhead included) / 4 cells (two packed cell pairs)
+K2_OPS_PER_CELL = 3.25
 K3_OPS_PER_CELL = 15.5
 
 
@@ -459,7 +460,7 @@ def main():
     roof_k2 = {"kernel": "sw_score2_kernel (K2: SW score, 2 tasks per warp)", "bound": "alu", "achieved": k2_gcups,
                "peak": k2_peak, "unit": "GCUPS", "frac": k2_gcups / k2_peak if k2_peak else None, "traffic": 11.8e6,
                "note": "DPX issue bound: peak = measured VIADDMNMX.S16x2 issue rate %.0f G thread-instr/s / %.1f "
-                       "instructions per cell (8 per packed cell pair)" % (peaks[3], K2_OPS_PER_CELL)}
+                       "ALU-pipe instructions per cell (6.5 per packed cell pair)" % (peaks[3], K2_OPS_PER_CELL)}
     roof_k1 = {"kernel": "seed_kernel + hits_kernel (K1)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak,
                "unit": "GB/s", "frac": k1_gbs / hbm_peak, "traffic": 37.3e6, "peak_source": peak_src,
                "note": "dependent 4-byte index probes (latency bound); the 5 Mb index (11 MB) is L2 resident"}

@@ -198,6 +198,11 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return d;
 }
 
+// H, E and F are kept BIASED by gap_init (the stored value is the score + gap_init): the floor of H
+// is then gap_init instead of 0, max(E - ext, H - gap_init) becomes max(E' - ext, H' - gap_init) with
+// H' - gap_init = H >= 0 in both half-words - so that one subtraction is an ordinary 32-bit one that
+// cannot borrow across the halves and needs no DPX instruction (it leaves the ALU pipe, which bounds
+// this kernel, for the FMA pipe) - and E', F' >= 0 need no RELU.
 // One systolic step of C packed cell pairs.  The table index (read selector ^ row selector) with the
 // row mask applied is ONE LOP3: rows with N / padding carry selector 0 and mask 4 in their task's
 // nibbles, so that every column reads a zero there (a plain xor would turn N against N into a match).
@@ -206,14 +211,14 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     _Pragma("unroll")                                                                       \
     for (int c = 0; c < C; ++c) {                                                           \
       const uint32_t s2 = (SEL_EXPR);                                                       \
-      const uint32_t h = __viaddmax_s16x2_relu(diag, s2, zero);                             \
+      const uint32_t h = __viaddmax_s16x2(diag, s2, gi2);     /* floor: H = 0 */            \
       diag = H[c];                                                                          \
       const uint32_t hn = __vimax3_s16x2(h, E[c], F);                                       \
       if (c & 1) best = __vimax3_s16x2(best, H[c - 1], hn);   /* two columns per VIMNMX3 */  \
       else if (c == C - 1) best = __vmaxs2(best, hn);                                       \
-      const uint32_t tt = __viaddmax_s16x2(hn, ngi2, 0x80008000u);                          \
+      const uint32_t tt = hn - gi2;   /* plain 32-bit subtract (FMA pipe): no half borrows */ \
       E[c] = __viaddmax_s16x2(E[c], nge2, tt);                                              \
-      F = __viaddmax_s16x2_relu(F, nge2, tt);                                               \
+      F = __viaddmax_s16x2(F, nge2, tt);                                                    \
       H[c] = hn;                                                                            \
     }                                                                                       \
   } while (0)
@@ -237,19 +242,18 @@ sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restri
   const int lane = threadIdx.x & (LANES - 1);
   uint32_t *const srow = s_row[threadIdx.x / LANES];
   unsigned short *const sraw = s_raw[threadIdx.x / LANES];
-  const uint32_t ngi2 = (uint32_t)((-sc.gap_init) & 0xffff) * 0x10001u;
   const uint32_t nge2 = (uint32_t)((-sc.gap_ext) & 0xffff) * 0x10001u;
-  // The table {match, mismatch x3 | 0 x4} and the constant 0 are read back from shared memory so
+  // The table {match, mismatch x3 | 0 x4} and the bias are read back from shared memory so
   // that they live in (vector) registers: as kernel-uniform values ptxas keeps them in uniform
   // registers / as immediates and re-materialises both for every cell (IMAD.U32 from UR + PRMT of
   // RZ: two extra instructions per cell pair).
   __shared__ uint32_t s_konst[2];
   if (threadIdx.x == 0) {
     s_konst[0] = (uint32_t)(sc.match & 0xff) | ((uint32_t)(sc.mismatch & 0xff) * 0x01010100u);
-    s_konst[1] = 0u;
+    s_konst[1] = (uint32_t)(sc.gap_init & 0xffff) * 0x10001u;
   }
   __syncthreads();
-  const uint32_t T0 = ((volatile uint32_t *)s_konst)[0], zero = ((volatile uint32_t *)s_konst)[1];
+  const uint32_t T0 = ((volatile uint32_t *)s_konst)[0], gi2 = ((volatile uint32_t *)s_konst)[1];
   // PRMT takes the table as its SECOND source (bytes 4..7; the first source is the zero register):
   // as first source ptxas overwrites it with the result and copies it afresh for every cell.  The
   // selector nibbles are therefore kept with bit 2 flipped: idx' = ((q ^ 4) ^ r) & ~mask.
@@ -293,14 +297,14 @@ sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restri
       const uint32_t ia = qa < 4u ? qa : 4u, ib = qb < 4u ? qb : 4u;
       qsel[c] = (ia | ((ia | 8u) << 4) | (ib << 8) | ((ib | 8u) << 12)) ^ 0x4444u;
       qraw[c] = qa | (qb << 8);
-      H[c] = 0u;
-      E[c] = 0u;
+      H[c] = gi2;
+      E[c] = gi2;
     }
     // X (the mismatch-against-everything code, score.c:138-173) in a read or a window: the warp's
     // pairs take the per-cell table path
     const bool general = __any_sync(FULL, hasX);
     __syncwarp();
-    uint32_t hdiag = 0u, hout = 0u, fout = 0u, best = 0u;
+    uint32_t hdiag = gi2, hout = gi2, fout = gi2, best = gi2;
     const int nsteps = rlen + LANES - 1;
     if (!general) {
       // Every lane computes in every step: before its first and behind its last window row it
@@ -311,7 +315,7 @@ sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restri
       for (int t = 0; t < nsteps; ++t) {
         uint32_t hl = __shfl_up_sync(FULL, hout, 1, LANES);
         uint32_t F = __shfl_up_sync(FULL, fout, 1, LANES);
-        if (lane == 0) { hl = 0u; F = 0u; }
+        if (lane == 0) { hl = gi2; F = gi2; }
         const uint32_t w = rowp[t];
         const uint32_t wm = w >> 16;
         uint32_t diag = hdiag;
@@ -324,7 +328,7 @@ sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restri
       for (int t = 0; t < nsteps; ++t) {
         uint32_t hl = __shfl_up_sync(FULL, hout, 1, LANES);
         uint32_t F = __shfl_up_sync(FULL, fout, 1, LANES);
-        if (lane == 0) { hl = 0u; F = 0u; }
+        if (lane == 0) { hl = gi2; F = gi2; }
         const int i = t - lane;
         if (i >= 0 && i < rlen) {
           const uint32_t r2 = (uint32_t)sraw[i + SW2_PAD];
@@ -338,7 +342,7 @@ sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restri
         }
       }
     }
-    int bA = (int)(short)(best & 0xffffu), bB = (int)(short)(best >> 16);
+    int bA = (int)(short)(best & 0xffffu) - sc.gap_init, bB = (int)(short)(best >> 16) - sc.gap_init;
     for (int o = LANES / 2; o > 0; o >>= 1) {
       bA = max(bA, __shfl_xor_sync(FULL, bA, o, LANES));
       bB = max(bB, __shfl_xor_sync(FULL, bB, o, LANES));
