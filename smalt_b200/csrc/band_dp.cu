@@ -404,7 +404,8 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
   // to the side stream
   const bool packed_any = align && (plan.pack_count || plan.pack8_count);
   const bool other_any = !plan.classes.empty() || (align && (plan.wide_count || plan.half_count || plan.warp_count));
-  const bool fork = side && side->stream && packed_any && other_any;
+  static const bool no_side = getenv("SMB_NO_SIDE") != nullptr;
+  const bool fork = side && side->stream && packed_any && other_any && !no_side;
   cudaStream_t st = main_st;
   if (fork) {
     if ((e = cudaEventRecord(side->fork, main_st)) != cudaSuccess) return e;
