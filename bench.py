@@ -534,4 +534,10 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    finally:
+        if "torch.distributed" in sys.modules:
+            import torch.distributed as _d
+            if _d.is_available() and _d.is_initialized():
+                _d.destroy_process_group()
