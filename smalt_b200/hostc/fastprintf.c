@@ -60,6 +60,16 @@ static size_t put_i64(char *p, long long v)
   return put_u64(p, (unsigned long long) v);
 }
 
+char *smbFastReserve(FILE *fp, size_t n)
+{
+  if (!fp || fp != t_cap.fp || cap_reserve(n)) return NULL;
+  return t_cap.buf + t_cap.len;
+}
+
+void smbFastCommit(size_t used) { t_cap.len += used; }
+
+size_t smbFastPutInt(char *p, long long v) { return put_i64(p, v); }
+
 int smbFastFprintf(FILE *fp, const char *fmt, ...)
 {
   va_list ap, ap0;
@@ -71,6 +81,17 @@ int smbFastFprintf(FILE *fp, const char *fmt, ...)
     rv = vfprintf(fp, fmt, ap);
     va_end(ap);
     return rv;
+  }
+  /* one CIGAR operation (diffstr.c:65 CIGAR_EXTF): the call that is made most often */
+  if (fmt[0] == '%' && fmt[1] == 'd' && fmt[2] == '%' && fmt[3] == 'c' && !fmt[4]) {
+    const int v = va_arg(ap, int), c = va_arg(ap, int);
+    size_t n;
+    va_end(ap);
+    if (cap_reserve(16)) return -1;
+    n = put_i64(t_cap.buf + t_cap.len, v);
+    t_cap.buf[t_cap.len + n] = (char) c;
+    t_cap.len += n + 1;
+    return (int) n + 1;
   }
   va_copy(ap0, ap);
   start = t_cap.len;

@@ -18,4 +18,10 @@ int smbFastFprintf(FILE *fp, const char *fmt, ...);
 void smbFastCaptureBegin(FILE *key);
 /* ends the capture; *buf is malloc'ed (caller frees), *len its length */
 int smbFastCaptureEnd(char **buf, size_t *len);
+/* direct appends for callers that know what they print (shim_report.c): `n` bytes of room in the
+ * capture buffer of this thread when `fp` is the captured stream, NULL otherwise (or when out of
+ * memory); smbFastCommit makes the first `used` bytes part of the output */
+char *smbFastReserve(FILE *fp, size_t n);
+void smbFastCommit(size_t used);
+size_t smbFastPutInt(char *p, long long v);
 #endif

@@ -137,8 +137,23 @@ static int samRecordSingle(const ReportWriter *wrp, const REPALI *rrp, const Dif
   }
   if (!qualstr[0]) qualstr = OUFMT_SAM_NULLSTR;
 
-  fprintf(fp, OUFMT_SAM_BEFORE, wrp->nambufp->q_nam.strp, samflg, is_mapped ? wrp->nambufp->ref_nam.strp : OUFMT_SAM_NULLSTR,
-	  pos, rrp->mapscor);
+  /* OUFMT_SAM_BEFORE "%s\t%hu\t%s\t%i\t%hi\t" (report.c:192), written field by field when the stream
+   * is this thread's capture buffer */
+  {
+    const char *qn = wrp->nambufp->q_nam.strp, *rn = is_mapped ? wrp->nambufp->ref_nam.strp : OUFMT_SAM_NULLSTR;
+    const size_t lq = strlen(qn), lr = strlen(rn);
+    char *o = smbFastReserve(fp, lq + lr + 64);
+    if (o) {
+      char *p = o;
+      memcpy(p, qn, lq); p += lq; *p++ = '\t';
+      p += smbFastPutInt(p, (unsigned short) samflg); *p++ = '\t';
+      memcpy(p, rn, lr); p += lr; *p++ = '\t';
+      p += smbFastPutInt(p, (int) pos); *p++ = '\t';
+      p += smbFastPutInt(p, (short) rrp->mapscor); *p++ = '\t';
+      smbFastCommit((size_t) (p - o));
+    } else
+      fprintf(fp, OUFMT_SAM_BEFORE, qn, samflg, rn, pos, rrp->mapscor);
+  }
   if (is_mapped) {
     errcode = diffStrPrintf(fp, diffstr,
 			    (char) ((oumodiflg & REPORTMODIF_XMISMATCH) ? DIFFSTRFORM_CIGEXT_XMISMATCH : DIFFSTRFORM_CIGEXT),
@@ -147,7 +162,24 @@ static int samRecordSingle(const ReportWriter *wrp, const REPALI *rrp, const Dif
   } else {
     fprintf(fp, OUFMT_SAM_NULLSTR);
   }
-  fprintf(fp, OUFMT_SAM_AFTER, OUFMT_SAM_NULLSTR, 0, 0, seqstr, qualstr, editdist, swatscor);
+  /* OUFMT_SAM_AFTER "\t%s\t%i\t%i\t%s\t%s\tNM:i:%i\tAS:i:%i\n" (report.c:194) */
+  {
+    const size_t ls = strlen(seqstr), lq = strlen(qualstr);
+    char *o = smbFastReserve(fp, ls + lq + 96);
+    if (o) {
+      char *p = o;
+      memcpy(p, "\t*\t0\t0\t", 7); p += 7;
+      memcpy(p, seqstr, ls); p += ls; *p++ = '\t';
+      memcpy(p, qualstr, lq); p += lq;
+      memcpy(p, "\tNM:i:", 6); p += 6;
+      p += smbFastPutInt(p, editdist);
+      memcpy(p, "\tAS:i:", 6); p += 6;
+      p += smbFastPutInt(p, swatscor);
+      *p++ = '\n';
+      smbFastCommit((size_t) (p - o));
+    } else
+      fprintf(fp, OUFMT_SAM_AFTER, OUFMT_SAM_NULLSTR, 0, 0, seqstr, qualstr, editdist, swatscor);
+  }
   return errcode;
 }
 
