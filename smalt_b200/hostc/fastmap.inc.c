@@ -237,14 +237,20 @@ static size_t fm_header_name(char *dst, const char *line, size_t len)
   return n;
 }
 
+/* white space (' ', 9..13) in a sequence / quality line?  Eight bytes at a time: any byte below '!'
+ * counts (control characters other than white space also send the block to the reference parser,
+ * which is always right). */
 static int fm_has_space(const char *p, size_t len)
 {
-  size_t i;
-  unsigned acc = 0;
-  for (i = 0; i < len; i++) {
-    const unsigned char c = (unsigned char) p[i];
-    acc |= (unsigned) (c == ' ') | (unsigned) (c - 9u <= 4u);
+  size_t i = 0;
+  uint64_t acc = 0;
+  for (; i + 8 <= len; i += 8) {
+    uint64_t w;
+    memcpy(&w, p + i, 8);
+    acc |= (w - 0x2121212121212121ULL) & ~w;
   }
+  acc &= 0x8080808080808080ULL;
+  for (; i < len; i++) acc |= (uint64_t) ((unsigned char) p[i] < 0x21u);
   return acc != 0;
 }
 
