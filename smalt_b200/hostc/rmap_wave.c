@@ -86,6 +86,14 @@ struct PairState_ {
 /* Growth step of the per-pair result sets (results.c:1781-1817 takes it as a parameter; the
  * default of 4096 results = 112 KB per set is meant for one set per thread): most reads have one
  * or two results, and a block keeps two sets per pair. */
+/* SMALT_B200_DEBUG, looked up once (the test sits in per-read and per-candidate loops) */
+static int wave_debug(void)
+{
+  static int state = -1;
+  if (state < 0) state = getenv("SMALT_B200_DEBUG") != NULL;
+  return state;
+}
+
 enum { PAIR_RESULT_BLKSZ = 4 };
 enum { PST_END = 0, PST_SECOND_UNRESTRICTED = 3, PST_RESCUE_MAIN = 4, PST_RESCUE_FINE = 5 };
 
@@ -618,7 +626,7 @@ static int wave_pass(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, const WJOB 
     }
     if (min_swatscor > rd->scorlen_min * matchscor && matchscor > 0) rd->scorlen_min = min_swatscor / matchscor;
     rd->min_swatscor = min_swatscor;
-    if (getenv("SMALT_B200_DEBUG"))
+    if (wave_debug())
       fprintf(stderr, "DBG read %d ncand %u nscored %u max1 %d max2 %d min_swatscor %d scorlen_min %d bw_min %d nseg %d/%d nhit %u/%u\n",
 	      i, rd->ncand, rd->nscored, max1, max2, min_swatscor, rd->scorlen_min, rd->bandwidth_min, rd->nseg,
 	      rd->nseg_tot, rd->nhit, rd->nhit_tot);
@@ -726,7 +734,7 @@ static int wave_pass(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, const WJOB 
 	if ((errcode = prune_results(bufp->alirsltp, w->res, w->diff, &pos, end, 0, (int) wc->reflen - 1,
 				     min_swatscor, minscorlen, 1)))
 	  return errcode;
-	if (getenv("SMALT_B200_DEBUG")) {
+	if (wave_debug()) {
 	  short k_, n_ = aliRsltSetGetSize(bufp->alirsltp);
 	  fprintf(stderr, "DBG  cand %u swscor %d cover %u rev %d rs %llu band %d %d minscore %d minscorlen %d raw %u kept %d:",
 		  c, cp->swscor, wc->cover, (int) (cp->flags & RMAPCANDFLG_REVERSE), (unsigned long long) cp->rs,
