@@ -372,3 +372,43 @@ def test_band_align_wide_kernel_geometry(ctx, orc):
             nmulti += len(want) > 1
         assert cells == ocells
     assert nmulti > 5
+
+
+@pytest.mark.parametrize("pen", [(2, -1, -1, -1), (1, -3, -9, -1), (3, -2, -5, -4), (1, -1, -2, 0)])
+def test_dp_kernels_other_penalties(pen):
+    """K2 and K3 under other penalty sets than the default (match, mismatch, gap open, gap extension):
+    cheap gaps, where gap states reach far into the padding the packed K3 kernel no longer masks and
+    the gap_init bias of the packed K2 kernel is small; expensive ones; a free extension."""
+    import smalt_b200
+    orc = Oracle(pen)
+    ctx = smalt_b200.Context(0, penalties=pen)
+    try:
+        rng = np.random.default_rng(700 + pen[0] * 7 - pen[2])
+        qmax = 255 // pen[0]          # packed kernels: scores < 256
+        trip = _rand_pairs(rng, 240, 20, min(160, qmax))
+        pairs, args = [], []
+        for k, (a, b, lf) in enumerate(trip):
+            if k % 7 == 0:
+                b = np.concatenate([b, random_seq(rng, 9), b])
+            pairs.append((a, b))
+            args.append(_band_args(rng, len(a), len(b), lf))
+        minscore = [int(x) for x in rng.integers(1, 40, len(pairs))]
+        minscorlen = [int(x) for x in rng.integers(5, 30, len(pairs))]
+        arena, offs = _arena(pairs)
+        ctx.arena_upload(arena)
+        scores, errs = ctx.sw_score(_sw_tasks(pairs, offs))
+        for i, (rd, win) in enumerate(pairs):
+            assert (int(errs[i]), int(scores[i])) == orc.sw_striped(rd, win), (i, pen)
+        res, first, diff, errs, cells = ctx.band_align(_band_tasks(pairs, offs, args, minscore, minscorlen))
+        ocells, most = 0, 0
+        for i, (rd, win) in enumerate(pairs):
+            e, want, c = orc.band_align(rd, win, *args[i], minscore[i], minscorlen[i])
+            ocells += c
+            most = max(most, len(want))
+            assert int(errs[i]) == e, (i, pen, args[i])
+            assert _unpack(res, first, diff, i) == want, (i, pen, args[i], minscore[i], minscorlen[i])
+        # (a task with more results than the first attempt has slots for is run again with more slots:
+        # the cell counter then includes the abandoned attempt)
+        assert cells == ocells if most <= 4 else cells >= ocells
+    finally:
+        ctx.close()
