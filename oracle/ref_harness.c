@@ -318,3 +318,82 @@ int refh_hitlist(int is_reverse, long long seqidx, unsigned int maxhit_per_tuple
   for (i = 0; i < (int) qlen && i < maxq; i++) qmask_out[i] = qmask[i];
   return 0;
 }
+
+/* ---------------------- candidate selection (segment.c) ------------------ */
+#include "segment.h"
+
+static SegLst *g_sgl;
+static SegAliCands *g_sac;
+static SegQMask *g_qm;
+
+/* What mapSingleRead does between the seed tables and the scoring (rmap.c:1258-1337 with
+ * fillRMAPBUFF/collectHits, rmap.c:273-318, in the sequence-by-sequence mode): for both strands
+ * and every reference sequence hashCollectHitsForSegment -> segLstFillHits -> segAliCandsAddFast,
+ * then segAliCandsStats and, for every selected candidate, segAliCandsCalcSegmentOffsets with
+ * edgelen 0 (makeRMAPCANDfromSegment, rmap.c:535-556).  Uses the seed tables left by the last
+ * refh_hitinfo() calls of the two strands (same read).  `out` rows: qs qe rs re band_l band_r dqo
+ * dro sqidx flags cover (11 x int64). */
+int refh_candidates(unsigned int maxhit_per_tuple, unsigned int min_cover, int min_swatscor_below_max,
+		    int mismatchdiff, int is_best, int target_depth, int max_depth, int is_sensitive,
+		    unsigned int qlen, int maxcand, unsigned int *stats /* n_sort n_mincover max_cover
+		    max2nd_cover cdF cdR nhit nhit_tot */, long long *out)
+{
+  int errcode = 0, st;
+  uint8_t nskip;
+  const uint8_t ktup = hashTableGetKtupLen(g_ht, &nskip);
+  const SETSIZ_t *soffsp;
+  const SEQNUM_t nseq = seqSetGetOffsets(g_ss, &soffsp);
+  uint32_t min_ktup, mincov_below_max, n, c, r0, r1;
+  SEQNUM_t s;
+  if (!g_ht) return ERRCODE_ASSERT;
+  if (!g_sgl) {
+    g_sgl = segLstCreate(0);
+    g_sac = segAliCandsCreate(0);
+    g_qm = segQMaskCreate(0);
+    if (!g_sgl || !g_sac || !g_qm) return ERRCODE_NOMEM;
+  }
+  /* calcMinKtup, rmap.c:240-247 */
+  min_ktup = (min_cover >= (uint32_t) ktup + nskip) ? (min_cover - ktup) / nskip : 1;
+  min_cover = (min_ktup - 1) * nskip + ktup;
+  if (min_swatscor_below_max < 0) mincov_below_max = qlen - 1;
+  else {
+    mincov_below_max = ((uint32_t) (min_swatscor_below_max / mismatchdiff)) * nskip;
+    if (mincov_below_max < ktup || is_best) mincov_below_max = ktup + 2 * (nskip - 1);
+  }
+  segAliCandsBlank(g_sac);
+  for (st = 0; st < 2 && !errcode; st++)
+    for (s = 0; s < nseq; s++) {
+      hashBlankHitList(g_hhl);
+      if ((errcode = hashCollectHitsForSegment(g_hhl, soffsp[s], soffsp[s + 1], maxhit_per_tuple, 1,
+					       g_hhi[st], g_ht, NULL)))
+	break;
+      segLstBlank(g_sgl);
+      if ((errcode = segLstFillHits(g_sgl, min_ktup, g_hhl))) break;
+      if ((errcode = segAliCandsAddFast(g_sac, g_qm, g_sgl, min_cover, s))) break;
+    }
+  if (errcode) return errcode;
+  if ((errcode = segAliCandsStats(g_sac, mincov_below_max, g_hhi[0], g_hhi[1], (SEGNUM_t) (short) target_depth,
+				  (SEGNUM_t) (short) max_depth, (uint8_t) is_sensitive)))
+    return errcode;
+  n = segAliCandsGetNumberOfSegments(g_sac, &stats[2], &stats[3], &stats[4], &stats[5], &stats[1]);
+  stats[0] = n;
+  r0 = hashHitInfoCalcHitNumbers(g_hhi[0], &c);
+  r1 = hashHitInfoCalcHitNumbers(g_hhi[1], &stats[6]);
+  stats[6] += c;
+  stats[7] = r0 + r1;
+  for (c = 0; c < n && (int) c < maxcand; c++) {
+    SEQLEN_t qs, qe, dqo;
+    SETSIZ_t rs, re;
+    int bl, br, dro;
+    SEQNUM_t sx;
+    SEGBITFLG_t fl;
+    SEGCOV_t cov;
+    if ((errcode = segAliCandsCalcSegmentOffsets(&qs, &qe, &rs, &re, &bl, &br, &dqo, &dro, &sx, &fl, &cov, 0, qlen,
+						 g_ss, c, g_sac)))
+      return errcode;
+    out[11 * c + 0] = qs; out[11 * c + 1] = qe; out[11 * c + 2] = (long long) rs; out[11 * c + 3] = (long long) re;
+    out[11 * c + 4] = bl; out[11 * c + 5] = br; out[11 * c + 6] = dqo; out[11 * c + 7] = dro;
+    out[11 * c + 8] = sx; out[11 * c + 9] = fl; out[11 * c + 10] = cov;
+  }
+  return 0;
+}

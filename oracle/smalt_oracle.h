@@ -153,6 +153,38 @@ int so_collect_hits_segment(so_hitlist *l, so_hitinfo *h, const so_index *ix,
 int so_collect_hits_cutoff(so_hitlist *l, const so_hitinfo *h, const so_index *ix,
 			   uint32_t max_nhit_per_tup);
 
+/* ------------------- candidate selection (segment.c) and score replay (rmap.c) ----------- */
+/* see smalt_oracle_cand.c */
+typedef struct so_cands_ so_cands;
+typedef struct {
+  uint32_t qs, qe;       /* read segment in the profiled orientation */
+  uint64_t rs, re;       /* window inside reference sequence sqidx */
+  int32_t band_l, band_r;
+  uint32_t dqo;
+  int32_t dro;
+  int32_t sqidx;
+  uint32_t cover;
+  uint8_t flags;         /* SEGCANDFLG_* (segment.h:51-55) */
+} so_cand;
+so_cands *so_cands_create(void);
+void so_cands_delete(so_cands *c);
+void so_cands_blank(so_cands *c);
+int so_cands_add_list(so_cands *c, const uint64_t *sqdat, int nhits, int is_reverse, uint32_t qlen,
+		      int ktup, int nskip, const uint8_t *qmask, uint32_t min_ktup, uint32_t mincover,
+		      int seqidx);
+int so_cands_stats(so_cands *c, uint32_t min_cover_below_max, uint32_t cover_deficit_f,
+		   uint32_t cover_deficit_r, int target_depth, int max_depth, int is_sensitive);
+uint32_t so_cands_count(const so_cands *c, uint32_t *max_cover, uint32_t *max2nd_cover, uint32_t *n_mincover,
+			uint32_t *n_all);
+int so_cands_offsets(const so_cands *c, uint32_t scidx, int edgelen, uint32_t qlen, const uint64_t *soffs,
+		     int nseq, int termchar, so_cand *out);
+int so_score_replay(int ncand, const uint32_t *cover, const uint8_t *rev, const int32_t *score,
+		    const int32_t *cand_band_l, const int32_t *cand_band_r,
+		    const uint32_t cover_deficit[2], uint32_t qlen, int ktup, int nskip, int matchscor,
+		    int mismatchscor, int gapinitscor, int gapextscor, int min_swatscor, int min_swatscor_below_max,
+		    int best, int *nscored, int *max1scor, int *max2scor, int *min_swatscor_out,
+		    int *scorlen_min_out, int *bandwidth_min_out, uint8_t *align, int32_t *band_l, int32_t *band_r);
+
 #ifdef __cplusplus
 }
 #endif

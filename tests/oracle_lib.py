@@ -65,6 +65,12 @@ class SoHitInfo(C.Structure):
                 ("frame_cnt", u32p), ("frame_ix", u32p), ("n_alloc", C.c_uint32)]
 
 
+class SoCand(C.Structure):
+    _fields_ = [("qs", C.c_uint32), ("qe", C.c_uint32), ("rs", C.c_uint64), ("re", C.c_uint64),
+                ("band_l", C.c_int32), ("band_r", C.c_int32), ("dqo", C.c_uint32), ("dro", C.c_int32),
+                ("sqidx", C.c_int32), ("cover", C.c_uint32), ("flags", C.c_uint8)]
+
+
 class SoHitList(C.Structure):
     _fields_ = [("nhits", C.c_int), ("nhits_max", C.c_int), ("nhits_alloc", C.c_int),
                 ("status", C.c_uint8), ("sqdat", u64p), ("qmask", u8p), ("qlen", C.c_uint32)]
@@ -200,6 +206,94 @@ class Oracle:
         qm = np.ctypeslib.as_array(hl.contents.qmask, (hl.contents.qlen,)).copy()
         return err, dat, qm, hl
 
+    # ---- candidate selection (segment.c) + score replay (rmap.c) ----
+    def candidates(self, ix, read, seq_offs, termchar=1, min_cover=0, min_swatscor_below_max=-1, best=False,
+                   target_depth=200, max_depth=8000, sensitive=False, nhit_max=10000, maxhit_total=16384,
+                   qual=None, basq=0):
+        """mapSingleRead between the seed tables and the scoring (rmap.c:1258-1337) on the oracle's own K1:
+        -> err, stats dict, list of candidate dicts (segAliCandsCalcSegmentOffsets with edgelen 0)"""
+        lib = self.lib
+        lib.so_cands_create.restype = C.c_void_p
+        lib.so_cands_count.restype = C.c_uint32
+        qlen = len(read)
+        k, nskip = ix.wordlen, ix.nskip
+        mm = self.sc.match - self.sc.mismatch
+        min_ktup = (min_cover - k) // nskip if min_cover >= k + nskip else 1
+        min_cover = (min_ktup - 1) * nskip + k
+        if min_swatscor_below_max < 0:
+            below = qlen - 1
+        else:
+            below = (min_swatscor_below_max // mm) * nskip
+            if below < k or best:
+                below = k + 2 * (nskip - 1)
+        cands = C.c_void_p(lib.so_cands_create())
+        lib.so_cands_blank(cands)
+        soffs = np.ascontiguousarray(seq_offs, np.uint64)
+        nseq = len(soffs) - 1
+        hs, cd, nh, nh_tot = [], [], 0, 0
+        err = 0
+        try:
+            for st in (0, 1):
+                e, d, h = self.hitinfo(ix, read, qual, st, 1, nhit_max, maxhit_total, basq)
+                hs.append(h)
+                if e:
+                    return e, None, None
+                cd.append(d["cover_deficit"])
+                nh += d["nhit_rank"]
+                nh_tot += d["nhit_tot"]
+            for st in (0, 1):
+                for s in range(nseq):
+                    e, hits, hl = self.hitlist_segment(ix, hs[st], int(soffs[s]), int(soffs[s + 1]), nhit_max, 1)
+                    lib.so_hitlist_delete(hl)
+                    if e and e != 32:
+                        return e, None, None
+                    hits = np.ascontiguousarray(hits, np.uint64)
+                    err = lib.so_cands_add_list(cands, _p(hits, u64p), len(hits), st, C.c_uint32(qlen), k, nskip, None,
+                                                C.c_uint32(min_ktup), C.c_uint32(min_cover), s)
+                    if err:
+                        return err, None, None
+            err = lib.so_cands_stats(cands, C.c_uint32(below), C.c_uint32(cd[0]), C.c_uint32(cd[1]), target_depth,
+                                     max_depth, int(sensitive))
+            if err:
+                return err, None, None
+            v = [C.c_uint32(0) for _ in range(4)]
+            n = lib.so_cands_count(cands, *[C.byref(x) for x in v])
+            stats = dict(n_sort=n, max_cover=v[0].value, max2nd_cover=v[1].value, n_mincover=v[2].value,
+                         n_all=v[3].value, cover_deficit=(cd[0], cd[1]), nhit=nh, nhit_tot=nh_tot)
+            out = []
+            for c in range(n):
+                sc = SoCand()
+                err = lib.so_cands_offsets(cands, C.c_uint32(c), 0, C.c_uint32(qlen), _p(soffs, u64p), nseq, termchar,
+                                           C.byref(sc))
+                if err:
+                    return err, stats, out
+                out.append(dict(qs=sc.qs, qe=sc.qe, rs=sc.rs, re=sc.re, band_l=sc.band_l, band_r=sc.band_r,
+                                dqo=sc.dqo, dro=sc.dro, sqidx=sc.sqidx, flags=sc.flags, cover=sc.cover))
+            return 0, stats, out
+        finally:
+            for h in hs:
+                lib.so_hitinfo_delete(h)
+            lib.so_cands_delete(cands)
+
+    def score_replay(self, cover, rev, score, band_l, band_r, cover_deficit, qlen, ktup, nskip, min_swatscor,
+                     min_swatscor_below_max, best):
+        n = len(cover)
+        cover = np.ascontiguousarray(cover, np.uint32)
+        rev = np.ascontiguousarray(rev, np.uint8)
+        score = np.ascontiguousarray(score, np.int32)
+        bl = np.ascontiguousarray(band_l, np.int32)
+        br = np.ascontiguousarray(band_r, np.int32)
+        cdf = np.ascontiguousarray(cover_deficit, np.uint32)
+        o = [C.c_int(0) for _ in range(6)]
+        align = np.zeros(max(n, 1), np.uint8)
+        obl = np.zeros(max(n, 1), np.int32)
+        obr = np.zeros(max(n, 1), np.int32)
+        err = self.lib.so_score_replay(n, _p(cover, u32p), _p(rev, u8p), _p(score, i32p), _p(bl, i32p), _p(br, i32p),
+                                       _p(cdf, u32p), C.c_uint32(qlen), ktup, nskip, self.sc.match, self.sc.mismatch,
+                                       -self.sc.gap_init, -self.sc.gap_ext, min_swatscor, min_swatscor_below_max,
+                                       int(best), *[C.byref(x) for x in o], _p(align, u8p), _p(obl, i32p), _p(obr, i32p))
+        return err, dict(nscored=o[0].value, max1=o[1].value, max2=o[2].value, min_swatscor=o[3].value,
+                         scorlen_min=o[4].value, bandwidth_min=o[5].value, align=align[:n], band_l=obl[:n], band_r=obr[:n])
 
 class RefLib:
     """The real reference (oracle/_ref/libsmalt_ref.so)."""
@@ -285,3 +379,25 @@ class RefLib:
                                     int(use_short), maxhits, C.byref(n), _p(dat, u64p),
                                     qlen, qm.ctypes.data_as(C.c_char_p))
         return err, dat[:n.value].copy(), qm
+
+    def candidates(self, read, qual=None, min_cover=0, min_swatscor_below_max=-1, mismatchdiff=3, best=False,
+                   target_depth=200, max_depth=8000, sensitive=False, nhit_max=10000, maxhit_total=16384, basq=0,
+                   maxcand=8192):
+        """the reference's own segment.c on the reference's own seed tables and hit lists (refh_candidates)"""
+        for st in (0, 1):
+            e, _ = self.hitinfo(read, qual, st, 1, nhit_max, maxhit_total, basq)
+            if e:
+                return e, None, None
+        stats = np.zeros(8, np.uint32)
+        out = np.zeros(11 * maxcand, np.int64)
+        err = self.lib.refh_candidates(C.c_uint(nhit_max), C.c_uint(min_cover), int(min_swatscor_below_max),
+                                       int(mismatchdiff), int(best), int(target_depth), int(max_depth), int(sensitive),
+                                       C.c_uint(len(read)), maxcand, _p(stats, u32p),
+                                       out.ctypes.data_as(C.POINTER(C.c_longlong)))
+        if err:
+            return err, None, None
+        st = dict(n_sort=int(stats[0]), n_mincover=int(stats[1]), max_cover=int(stats[2]), max2nd_cover=int(stats[3]),
+                  cover_deficit=(int(stats[4]), int(stats[5])), nhit=int(stats[6]), nhit_tot=int(stats[7]))
+        keys = ("qs", "qe", "rs", "re", "band_l", "band_r", "dqo", "dro", "sqidx", "flags", "cover")
+        cands = [dict(zip(keys, (int(x) for x in out[11 * c:11 * c + 11]))) for c in range(min(st["n_sort"], maxcand))]
+        return 0, st, cands
