@@ -285,6 +285,92 @@ int smb_hits_batch(smb_ctx *ctx, const smb_hit_req *req, int nreq, uint32_t nhit
  * HITQUAL_NOHIT like the reference's.  segLstFillHits (segment.c:782-788) consumes the mask. */
 int smb_hits_qmask(smb_ctx *ctx, uint8_t *qmask, size_t max_bytes, uint64_t *qmask_first);
 
+/* ---------------- resident block: hit lists -> candidates -> K2 -> replay -> K3 ----------------
+ * A block of reads stays on the device from the seed tables (smb_seed_batch / _tables) to the
+ * alignments: nothing but the jobs goes up, nothing but the per-read summaries, the aligned
+ * candidates and their alignments comes down.  Replaces, for every job (one mapSingleRead pass,
+ * rmap.c:1228-1433):
+ *   collectHits / collectHitsFromInterVal           rmap.c:273-318, :438-493   (hit lists, as smb_hits_batch)
+ *   segLstFillHits + segAliCandsAddFast             segment.c:763-810, :1530-1557 (:396-584, :1140-1223)
+ *   segAliCandsStats                                segment.c:1616-1785 (NR quicksort ties, sort.c:233-330)
+ *   segAliCandsCalcSegmentOffsets                   segment.c:1861-1985 (makeRMAPCANDfromSegment, rmap.c:535)
+ *   scoreRMAPCAND                                   rmap.c:660-786  (K2 / K2' of every candidate + the sequential
+ *                                                   early-break bookkeeping)
+ *   the thresholds of mapSingleRead                 rmap.c:1373-1400
+ *   alignRMAPCANDFull up to aliSmiWatInBand         rmap.c:820-911 with the INITIAL threshold (the rising
+ *                                                   threshold of BEST mode is replayed by the caller on the
+ *                                                   results, see DESIGN.md "threshold replay")
+ * calcTotalHitNumStats (rmap.c:1086) fills nhit / nhit_tot. */
+typedef struct {
+  uint32_t seed_read;    /* read in the last seed batch */
+  int32_t niv;           /* < 0: hit lists of every reference sequence; else number of intervals */
+  uint32_t iv_first;     /* first interval of the job in `ivals` */
+  uint32_t min_cover;    /* min_cover argument of mapSingleRead (before calcMinKtup, rmap.c:240-247) */
+  int32_t min_swatscor;  /* absolute score threshold argument */
+  uint32_t reserved;
+} smb_block_job;
+
+typedef struct {         /* hit lists restricted to [lo, hi) of the concatenated set, candidates labelled seqidx */
+  uint64_t lo, hi;
+  int32_t seqidx;
+  int32_t reserved;
+} smb_block_ival;
+
+typedef struct {
+  uint32_t nhit_max;               /* ktuple_maxhit */
+  int32_t min_swatscor_below_max;  /* relative threshold argument (< 0: none) */
+  int32_t target_depth, max_depth; /* as passed to segAliCandsStats (shorts converted like SEGNUM_t) */
+  uint8_t best;                    /* RMAPFLG_BEST */
+  uint8_t sensitive;               /* RMAPFLG_SENSITIVE */
+  uint8_t termchar;                /* a terminator follows every sequence in seq_offs (SEQSET_TERMCHAR) */
+  uint8_t reserved;
+} smb_block_params;
+
+typedef struct {                   /* per job */
+  int32_t errcode;                 /* error that ends the mapping of this read (ERRCODE_*) or 0 */
+  uint8_t reached_stats;           /* got as far as resultSetAlignmentStats (rmap.c:1338) */
+  uint8_t do_align;                /* max1scor >= 1 */
+  uint8_t reserved[2];
+  int32_t nseg, nseg_tot;          /* n_sort, n_mincover */
+  uint32_t nhit, nhit_tot;
+  uint32_t ncand, nscored;
+  int32_t max1scor, max2scor;
+  int32_t min_swatscor, scorlen_min, bandwidth_min;
+  uint32_t k3_first, nk3;          /* aligned candidates of this job in `cands` */
+  uint32_t reserved2;
+} smb_block_read;
+
+typedef struct {                   /* one candidate that went to K3 (RMAPCAND fields resultSetAddFromAli needs) */
+  uint64_t rs;                     /* window start inside the reference sequence */
+  int32_t sqidx;
+  int32_t swscor;
+  uint32_t reflen;
+  int32_t band_l, band_r;          /* the (widened) band of the K3 task */
+  uint8_t reverse;
+  uint8_t reserved[3];
+} smb_block_cand;
+
+typedef struct {
+  uint64_t nhits, ncand, nk2, nk2_band, nk3, nresults, ndiffbytes;
+  uint64_t k2_cells, k2_cells_ref, k2_tasks_ref, k3_cells;   /* cells of all candidates / of those the reference scores */
+  float ms_hits, ms_cand, ms_k2, ms_k3;                      /* device times (CUDA events on the context's stream) */
+  int32_t launches;
+  int32_t reserved;
+} smb_block_sizes;
+
+/* Runs the block on the seed tables of the last seed batch and leaves the outputs on the device;
+ * `sizes` tells the caller how much room smb_block_fetch needs. */
+int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job *jobs, int njobs,
+		  const smb_block_ival *ivals, int nivals, smb_block_sizes *sizes);
+/* reads[njobs]; cands[nk3], errs[nk3], first_result[nk3 + 1]; results[nresults]; diffstr[ndiffbytes]
+ * (results / diffstr as smb_band_align_batch, task = index into cands). */
+int smb_block_fetch(smb_ctx *ctx, smb_block_read *reads, smb_block_cand *cands, int32_t *errs,
+		    uint32_t *first_result, smb_ali_result *results, uint8_t *diffstr);
+/* Test access: the candidate list of the last smb_block_run, all jobs, in scoring order
+ * (cand_first[njobs + 1]); swscor = K2 / K2' score of every candidate (also the over-computed ones). */
+int smb_block_debug_cands(smb_ctx *ctx, uint64_t *cand_first, smb_block_cand *cands, uint32_t *cover,
+			  uint32_t *qs_qe, size_t max_cands);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,24 @@ INDEX_INFO_DTYPE = np.dtype([("npos", "<u4"), ("nwords", "<u4"), ("nkeys", "<u4"
 ALI_RESULT_DTYPE = np.dtype([("score", "<i4"), ("qs", "<i4"), ("qe", "<i4"), ("rs", "<i4"),
                              ("re", "<i4"), ("diff_off", "<u4"), ("diff_len", "<u4"),
                              ("task", "<u4")])
+BLOCK_JOB_DTYPE = np.dtype([("seed_read", "<u4"), ("niv", "<i4"), ("iv_first", "<u4"), ("min_cover", "<u4"),
+                            ("min_swatscor", "<i4"), ("reserved", "<u4")])
+BLOCK_IVAL_DTYPE = np.dtype([("lo", "<u8"), ("hi", "<u8"), ("seqidx", "<i4"), ("reserved", "<i4")])
+BLOCK_PARAMS_DTYPE = np.dtype([("nhit_max", "<u4"), ("min_swatscor_below_max", "<i4"), ("target_depth", "<i4"),
+                               ("max_depth", "<i4"), ("best", "u1"), ("sensitive", "u1"), ("termchar", "u1"),
+                               ("reserved", "u1")])
+BLOCK_READ_DTYPE = np.dtype([("errcode", "<i4"), ("reached_stats", "u1"), ("do_align", "u1"), ("reserved", "u1", (2,)),
+                             ("nseg", "<i4"), ("nseg_tot", "<i4"), ("nhit", "<u4"), ("nhit_tot", "<u4"),
+                             ("ncand", "<u4"), ("nscored", "<u4"), ("max1scor", "<i4"), ("max2scor", "<i4"),
+                             ("min_swatscor", "<i4"), ("scorlen_min", "<i4"), ("bandwidth_min", "<i4"),
+                             ("k3_first", "<u4"), ("nk3", "<u4"), ("reserved2", "<u4")])
+BLOCK_CAND_DTYPE = np.dtype([("rs", "<u8"), ("sqidx", "<i4"), ("swscor", "<i4"), ("reflen", "<u4"), ("band_l", "<i4"),
+                             ("band_r", "<i4"), ("reverse", "u1"), ("reserved", "u1", (3,))])
+BLOCK_SIZES_DTYPE = np.dtype([(k, "<u8") for k in ("nhits", "ncand", "nk2", "nk2_band", "nk3", "nresults", "ndiffbytes",
+                                                    "k2_cells", "k2_cells_ref", "k2_tasks_ref", "k3_cells")] +
+                             [(k, "<f4") for k in ("ms_hits", "ms_cand", "ms_k2", "ms_k3")] +
+                             [("launches", "<i4"), ("reserved", "<i4")])
+assert BLOCK_READ_DTYPE.itemsize == 64 and BLOCK_CAND_DTYPE.itemsize == 32 and BLOCK_JOB_DTYPE.itemsize == 24
 assert SW_TASK_DTYPE.itemsize == C.sizeof(SwTask)
 assert BAND_TASK_DTYPE.itemsize == C.sizeof(BandTask), (BAND_TASK_DTYPE.itemsize, C.sizeof(BandTask))
 assert ALI_RESULT_DTYPE.itemsize == C.sizeof(AliResult)
@@ -108,6 +126,9 @@ def load_library():
     lib.smb_seed_batch_tables.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
                                           C.c_void_p]
+    lib.smb_block_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.smb_block_fetch.argtypes = [C.c_void_p] * 7
+    lib.smb_block_debug_cands.argtypes = [C.c_void_p] * 5 + [C.c_size_t]
     _lib = lib
     return lib
 
@@ -308,6 +329,44 @@ class Context:
                 continue
             self._check(rc)
             return res[:nres.value], first, diff[:ndiff.value], errs, cells.value
+
+
+    # ---- resident block (hit lists -> candidates -> K2 -> replay -> K3 on the device) ----
+    def block_run(self, jobs, ivals=None, nhit_max=10000, min_swatscor_below_max=-1, target_depth=200, max_depth=8000,
+                  best=False, sensitive=False, termchar=False):
+        """-> sizes (BLOCK_SIZES_DTYPE scalar) of the block run on the last seed batch"""
+        jobs = np.ascontiguousarray(jobs, BLOCK_JOB_DTYPE)
+        ivals = np.zeros(0, BLOCK_IVAL_DTYPE) if ivals is None else np.ascontiguousarray(ivals, BLOCK_IVAL_DTYPE)
+        prm = np.zeros(1, BLOCK_PARAMS_DTYPE)
+        prm[0] = (nhit_max, min_swatscor_below_max, target_depth, max_depth, int(best), int(sensitive), int(termchar), 0)
+        sizes = np.zeros(1, BLOCK_SIZES_DTYPE)
+        self._check(self.lib.smb_block_run(self._h, _vp(prm), _vp(jobs), len(jobs), _vp(ivals), len(ivals), _vp(sizes)))
+        self._block_n = (len(jobs), sizes[0])
+        return sizes[0]
+
+    def block_fetch(self):
+        """-> (reads[BLOCK_READ_DTYPE], cands[BLOCK_CAND_DTYPE], errs, first_result, results, diffstr)"""
+        n, sz = self._block_n
+        nk3, nres, nd = int(sz["nk3"]), int(sz["nresults"]), int(sz["ndiffbytes"])
+        reads = np.zeros(n, BLOCK_READ_DTYPE)
+        cands = np.zeros(nk3, BLOCK_CAND_DTYPE)
+        errs = np.zeros(nk3, np.int32)
+        first = np.zeros(nk3 + 1, np.uint32)
+        res = np.zeros(nres, ALI_RESULT_DTYPE)
+        diff = np.zeros(max(nd, 1), np.uint8)
+        self._check(self.lib.smb_block_fetch(self._h, _vp(reads), _vp(cands), _vp(errs), _vp(first), _vp(res), _vp(diff)))
+        return reads, cands, errs, first, res, diff[:nd]
+
+    def block_debug_cands(self):
+        """-> (cand_first[n+1], cands[BLOCK_CAND_DTYPE] with swscor = K2 score, cover, qs_qe[n, 2]) of ALL candidates"""
+        n, sz = self._block_n
+        nc = int(sz["ncand"])
+        first = np.zeros(n + 1, np.uint64)
+        cands = np.zeros(nc, BLOCK_CAND_DTYPE)
+        cover = np.zeros(nc, np.uint32)
+        qsqe = np.zeros((nc, 2), np.uint32)
+        self._check(self.lib.smb_block_debug_cands(self._h, _vp(first), _vp(cands), _vp(cover), _vp(qsqe), nc))
+        return first, cands, cover, qsqe
 
 
 def pack_sequences(seqs):

@@ -1,137 +1,11 @@
 // api.cu - the C ABI of include/smalt_b200.h: context, device buffers, batch entry points.
-#include "common.cuh"
-#include "band.h"
-#include <atomic>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
+#include "ctx.h"
+#include "block.cuh"
 #include <cmath>
 #include <new>
-#include <string>
-#include <vector>
 
-using namespace smb;
-
-namespace {
-
-struct DevBuf {  // grow-only device buffer
-  void *p = nullptr;
-  size_t cap = 0;
-  cudaError_t ensure(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    size_t want = bytes + bytes / 4 + 4096;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-  template <class T> T *as() const { return (T *)p; }
-};
-
-struct HostBuf {  // grow-only pinned host staging buffer
-  void *p = nullptr;
-  size_t cap = 0;
-  cudaError_t ensure(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
-    size_t want = bytes + bytes / 4 + 4096;
-    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() {
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
-  }
-  template <class T> T *as() const { return (T *)p; }
-};
-
-}  // namespace
-
-struct smb_ctx {
-  int device = 0;
-  int sm_count = 148;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaEvent_t ev_done = nullptr;  // blocking-sync event: waiting host threads sleep instead of spinning
-  BandSide side;                  // K3: stream of the small launches beside the packed kernel
-  HostBuf stage;                  // pinned staging for the library's own host-side arrays
-  DevBuf cmp;                     // K3 output compaction scratch
-  DevBuf ticket;                  // work counters of persistent kernels
-  Scoring sc;
-  SeqSrc src{nullptr, nullptr, 0};
-  DevBuf arena, packed, tasks, out_a, out_b, scratch, dirs, diff, offs;
-  DevBuf index, qualbuf, seed_meta, seed_u32, seed_u8;
-  Index ix{};
-  bool have_index = false;
-  // device-resident seed tables of the last smb_seed_batch (consumed by smb_hits_batch)
-  int seed_nreads = 0;
-  SeedArgs seed_args{};
-  uint32_t seed_maxlen = 0;
-  DevBuf hit_meta, hit_data, hit_qmask, aux_index;
-  IndexBuildOut built{};               // arrays left on the device by smb_index_build
-  int built_typ = 0;
-  Index seed_ix{};                     // index (template) of the last seed batch: what smb_hits_batch reads
-  std::vector<uint32_t> seed_len;      // host copy of the read lengths of the last smb_seed_batch
-  std::vector<uint64_t> hit_qmask_first;  // per request of the last smb_hits_batch
-  bool hit_qmask_valid = false;
-  uint64_t seed_slots = 0;
-  size_t arena_bytes = 0;
-  std::vector<uint64_t> seq_offs;
-  float last_ms = 0.f;
-  int last_launches = 0;
-  long long total_launches = 0;
-  std::string err;
-};
-
-// process-wide traffic counters (all contexts): what bench.py reports as h2d/d2h bytes and launches
-static std::atomic<unsigned long long> g_h2d_bytes{0}, g_d2h_bytes{0};
-static std::atomic<long long> g_launches{0};
-
-static inline cudaError_t h2d(void *dst, const void *src, size_t bytes, cudaStream_t st) {
-  g_h2d_bytes += bytes;
-  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
-}
-static inline cudaError_t d2h(void *dst, const void *src, size_t bytes, cudaStream_t st) {
-  g_d2h_bytes += bytes;
-  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
-}
-
-static int fail(smb_ctx *c, int code, const char *fmt, ...) {
-  char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof buf, fmt, ap);
-  va_end(ap);
-  if (c) c->err = buf;
-  return code;
-}
-
-#define CU(call)                                                                         \
-  do {                                                                                   \
-    cudaError_t e_ = (call);                                                             \
-    if (e_ != cudaSuccess)                                                               \
-      return fail(ctx, SMB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
-                  __FILE__, __LINE__);                                                   \
-  } while (0)
-
-// Waits for the context's stream.  Uses a blocking-sync event so that a host worker thread
-// yields its core while the GPU works (one context per host thread, more threads than cores).
-static cudaError_t ctx_sync(smb_ctx *ctx) {
-  cudaError_t e = cudaEventRecord(ctx->ev_done, ctx->stream);
-  if (e != cudaSuccess) return e;
-  return cudaEventSynchronize(ctx->ev_done);
-}
+std::atomic<unsigned long long> g_h2d_bytes{0}, g_d2h_bytes{0};
+std::atomic<long long> g_launches{0};
 
 static void make_scoring(Scoring &sc, int match, int mismatch, int gapopen, int gapext) {
   sc.match = match;
@@ -158,7 +32,7 @@ int smb_device_warmup(int device) {
   if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) return SMB_ERR_CUDA;
   if (warm_sw() != cudaSuccess || warm_band() != cudaSuccess || warm_band_warp() != cudaSuccess || warm_band_wide() != cudaSuccess || warm_band_pack() != cudaSuccess ||
       warm_seed() != cudaSuccess ||
-      warm_compact() != cudaSuccess)
+      warm_compact() != cudaSuccess || warm_block() != cudaSuccess)
     return SMB_ERR_CUDA;
   return SMB_OK;
 }
@@ -199,8 +73,11 @@ void smb_ctx_destroy(smb_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf *bufs[] = {&ctx->arena, &ctx->packed, &ctx->tasks, &ctx->out_a, &ctx->out_b,
                     &ctx->scratch, &ctx->dirs, &ctx->diff, &ctx->offs, &ctx->index, &ctx->qualbuf,
-                    &ctx->seed_meta, &ctx->seed_u32, &ctx->seed_u8, &ctx->hit_meta, &ctx->hit_data, &ctx->cmp, &ctx->ticket, &ctx->hit_qmask, &ctx->aux_index};
+                    &ctx->seed_meta, &ctx->seed_u32, &ctx->seed_u8, &ctx->hit_meta, &ctx->hit_data, &ctx->cmp, &ctx->ticket, &ctx->hit_qmask, &ctx->aux_index,
+                    &ctx->seq_offs_buf, &ctx->blk_jobs, &ctx->blk_scr, &ctx->blk_cand, &ctx->blk_k3};
   for (DevBuf *b : bufs) b->release();
+  for (cudaEvent_t &e : ctx->blk_ev) if (e) cudaEventDestroy(e);
+  block_state_free(ctx);
   if (ctx->built.block) cudaFree(ctx->built.block);
   ctx->stage.release();
   if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
@@ -253,6 +130,7 @@ int smb_ctx_share_index(smb_ctx *dst, const smb_ctx *src) {
   dst->src.packed = src->src.packed;
   dst->src.packed_nbases = src->src.packed_nbases;
   dst->seq_offs = src->seq_offs;
+  dst->d_seq_offs = src->d_seq_offs;
   return SMB_OK;
 }
 
@@ -300,20 +178,27 @@ int smb_refseq_upload(smb_ctx *ctx, const uint32_t *words, size_t nwords, uint64
   ctx->src.packed = ctx->packed.as<uint32_t>();
   ctx->src.packed_nbases = nbases;
   ctx->seq_offs.clear();
-  if (seq_offs && nseq > 0) ctx->seq_offs.assign(seq_offs, seq_offs + nseq + 1);
+  ctx->d_seq_offs = nullptr;
+  if (seq_offs && nseq > 0) {
+    ctx->seq_offs.assign(seq_offs, seq_offs + nseq + 1);
+    CU(ctx->seq_offs_buf.ensure(((size_t)nseq + 1) * sizeof(uint64_t)));
+    CU(h2d(ctx->seq_offs_buf.p, seq_offs, ((size_t)nseq + 1) * sizeof(uint64_t), ctx->stream));
+    CU(ctx_sync(ctx));
+    ctx->d_seq_offs = ctx->seq_offs_buf.as<uint64_t>();
+  }
   return SMB_OK;
 }
 
 static int check_seq_ranges(smb_ctx *ctx, uint64_t read_off, uint32_t read_len, uint64_t ref_off,
                             uint32_t ref_len, uint32_t flags, int i) {
-  if (read_off + read_len > ctx->arena_bytes)
+  if (read_off > ctx->arena_bytes || read_len > ctx->arena_bytes - read_off)
     return fail(ctx, SMB_ERR_ARG, "task %d: read [%llu,+%u) outside the arena (%zu bytes)", i,
                 (unsigned long long)read_off, read_len, ctx->arena_bytes);
   if (flags & SMB_TASK_REF_PACKED) {
     if (!ctx->src.packed) return fail(ctx, SMB_ERR_STATE, "task %d: no packed reference uploaded", i);
-    if (ref_off + ref_len > ctx->src.packed_nbases)
+    if (ref_off > ctx->src.packed_nbases || ref_len > ctx->src.packed_nbases - ref_off)
       return fail(ctx, SMB_ERR_ARG, "task %d: window outside the packed reference", i);
-  } else if (ref_off + ref_len > ctx->arena_bytes) {
+  } else if (ref_off > ctx->arena_bytes || ref_len > ctx->arena_bytes - ref_off) {
     return fail(ctx, SMB_ERR_ARG, "task %d: window outside the arena", i);
   }
   return SMB_OK;
@@ -616,36 +501,14 @@ static int band_align_fast(smb_ctx *ctx, const smb_band_task *tasks, int ntasks,
   return SMB_OK;
 }
 
-int smb_band_align_batch(smb_ctx *ctx, const smb_band_task *tasks, int ntasks, smb_ali_result *results,
-                         size_t max_results, size_t *nresults, uint32_t *first_result, uint8_t *diffstr,
-                         size_t max_diffbytes, size_t *ndiffbytes, int32_t *errs, uint64_t *ncells) {
-  if (!ctx || ntasks < 0 || !nresults || !ndiffbytes || (ntasks && (!tasks || !first_result || !errs)))
-    return SMB_ERR_ARG;
-  ctx->last_ms = 0.f;
-  ctx->last_launches = 0;
-  *nresults = 0;
-  *ndiffbytes = 0;
-  if (ncells) *ncells = 0;
-  if (first_result) first_result[0] = 0;
-  if (!ntasks) return SMB_OK;
-  if (!ctx->src.arena) return fail(ctx, SMB_ERR_STATE, "smb_arena_upload() first");
-  for (int i = 0; i < ntasks; ++i) {
-    int rcode = check_seq_ranges(ctx, tasks[i].read_off, tasks[i].read_len, tasks[i].ref_off,
-                                 tasks[i].ref_len, tasks[i].flags, i);
-    if (rcode) return rcode;
-  }
-  cudaSetDevice(ctx->device);
-  {
-    const int rcode = band_align_fast(ctx, tasks, ntasks, results, max_results, nresults, first_result, diffstr,
-                                      max_diffbytes, ndiffbytes, errs, ncells);
-    if (rcode != 1) return rcode;
-    *nresults = 0;
-    *ndiffbytes = 0;
-    if (ncells) *ncells = 0;
-    first_result[0] = 0;
-  }
+}  // extern "C"
 
-  // per task: results and diff bytes collected from (possibly several) passes
+// Multi-pass path of K3 for batches in which a task ran out of its slot capacity (more than four
+// results, long DiffStrs) or whose direction strips exceed one pass: growing capacities, results
+// assembled on the host.  Outputs in task order.
+int band_align_multipass(smb_ctx *ctx, const smb_band_task *tasks, int ntasks, std::vector<smb_ali_result> &results,
+                         std::vector<uint32_t> &first_result, std::vector<uint8_t> &diffstr,
+                         std::vector<int32_t> &errs, uint64_t *ncells) {
   struct TaskOut { std::vector<smb_ali_result> res; std::vector<uint8_t> diff; int32_t err = 0; };
   std::vector<TaskOut> outs((size_t)ntasks);
   std::vector<int> todo((size_t)ntasks);
@@ -674,11 +537,9 @@ int smb_band_align_batch(smb_ctx *ctx, const smb_band_task *tasks, int ntasks, s
       std::vector<int32_t> h_errs;
       std::vector<uint8_t> h_diff;
       std::vector<uint64_t> doff;
-      const unsigned long long cells_before = cells;
       int rcode = band_align_pass(ctx, tasks, chunk, max_res, diff_scale, h_res, h_nres, h_errs, h_diff,
                                   doff, &cells, &ms, &nl);
       if (rcode) return rcode;
-      (void)cells_before;
       for (size_t k = 0; k < chunk.size(); ++k) {
         const int ti = chunk[k];
         TaskOut &o = outs[(size_t)ti];
@@ -705,25 +566,70 @@ int smb_band_align_batch(smb_ctx *ctx, const smb_band_task *tasks, int ntasks, s
   ctx->total_launches += nl;
   g_launches += nl;
   if (ncells) *ncells = cells;
-  size_t nr = 0, nd = 0;
-  for (int i = 0; i < ntasks; ++i) { nr += outs[(size_t)i].res.size(); nd += outs[(size_t)i].diff.size(); }
+  results.clear();
+  diffstr.clear();
+  first_result.assign((size_t)ntasks + 1, 0);
+  errs.assign((size_t)ntasks, 0);
+  for (int i = 0; i < ntasks; ++i) {
+    TaskOut &o = outs[(size_t)i];
+    first_result[(size_t)i] = (uint32_t)results.size();
+    errs[(size_t)i] = o.err;
+    const uint32_t nd = (uint32_t)diffstr.size();
+    for (smb_ali_result rr : o.res) {
+      rr.diff_off += nd;
+      results.push_back(rr);
+    }
+    diffstr.insert(diffstr.end(), o.diff.begin(), o.diff.end());
+  }
+  first_result[(size_t)ntasks] = (uint32_t)results.size();
+  return SMB_OK;
+}
+
+extern "C" {
+
+int smb_band_align_batch(smb_ctx *ctx, const smb_band_task *tasks, int ntasks, smb_ali_result *results,
+                         size_t max_results, size_t *nresults, uint32_t *first_result, uint8_t *diffstr,
+                         size_t max_diffbytes, size_t *ndiffbytes, int32_t *errs, uint64_t *ncells) {
+  if (!ctx || ntasks < 0 || !nresults || !ndiffbytes || (ntasks && (!tasks || !first_result || !errs)))
+    return SMB_ERR_ARG;
+  ctx->last_ms = 0.f;
+  ctx->last_launches = 0;
+  *nresults = 0;
+  *ndiffbytes = 0;
+  if (ncells) *ncells = 0;
+  if (first_result) first_result[0] = 0;
+  if (!ntasks) return SMB_OK;
+  if (!ctx->src.arena) return fail(ctx, SMB_ERR_STATE, "smb_arena_upload() first");
+  for (int i = 0; i < ntasks; ++i) {
+    int rcode = check_seq_ranges(ctx, tasks[i].read_off, tasks[i].read_len, tasks[i].ref_off,
+                                 tasks[i].ref_len, tasks[i].flags, i);
+    if (rcode) return rcode;
+  }
+  cudaSetDevice(ctx->device);
+  {
+    const int rcode = band_align_fast(ctx, tasks, ntasks, results, max_results, nresults, first_result, diffstr,
+                                      max_diffbytes, ndiffbytes, errs, ncells);
+    if (rcode != 1) return rcode;
+    *nresults = 0;
+    *ndiffbytes = 0;
+    if (ncells) *ncells = 0;
+    first_result[0] = 0;
+  }
+  std::vector<smb_ali_result> v_res;
+  std::vector<uint32_t> v_first;
+  std::vector<uint8_t> v_diff;
+  std::vector<int32_t> v_errs;
+  const int rcode = band_align_multipass(ctx, tasks, ntasks, v_res, v_first, v_diff, v_errs, ncells);
+  if (rcode) return rcode;
+  const size_t nr = v_res.size(), nd = v_diff.size();
   *nresults = nr;
   *ndiffbytes = nd;
   if (nr > max_results || nd > max_diffbytes || (nr && !results) || (nd && !diffstr))
     return fail(ctx, SMB_ERR_CAPACITY, "need %zu results and %zu diffstr bytes", nr, nd);
-  nr = nd = 0;
-  for (int i = 0; i < ntasks; ++i) {
-    TaskOut &o = outs[(size_t)i];
-    first_result[i] = (uint32_t)nr;
-    errs[i] = o.err;
-    for (smb_ali_result rr : o.res) {
-      rr.diff_off += (uint32_t)nd;
-      results[nr++] = rr;
-    }
-    if (!o.diff.empty()) memcpy(diffstr + nd, o.diff.data(), o.diff.size());
-    nd += o.diff.size();
-  }
-  first_result[ntasks] = (uint32_t)nr;
+  if (nr) memcpy(results, v_res.data(), nr * sizeof(smb_ali_result));
+  if (nd) memcpy(diffstr, v_diff.data(), nd);
+  memcpy(first_result, v_first.data(), ((size_t)ntasks + 1) * sizeof(uint32_t));
+  memcpy(errs, v_errs.data(), (size_t)ntasks * sizeof(int32_t));
   return SMB_OK;
 }
 
@@ -733,8 +639,9 @@ int smb_index_upload(smb_ctx *ctx, int typ, int wordlen, int nskip, int nbits_ke
                      uint32_t npos, uint32_t nwords, const uint32_t *idx, const uint32_t *pos,
                      const uint32_t *wordidx, const uint32_t *posidx) {
   if (!ctx || !idx || (npos && !pos) || (typ != 0 && (!wordidx || !posidx))) return SMB_ERR_ARG;
-  if (wordlen < 1 || wordlen > 31 || nskip < 1 || nskip > 32 || nbits_key > 32 || (typ != 0 && nbits_lo >= nbits_key))
-    return fail(ctx, SMB_ERR_ARG, "index parameters out of range (k=%d nskip=%d)", wordlen, nskip);
+  if (wordlen < 1 || wordlen > 31 || nskip < 1 || nskip > 32 || nbits_key > 32 || (typ != 0 && nbits_lo >= nbits_key) ||
+      (typ == 0 && wordlen > 15))   // perfect hash: 4^k keys must fit 32 bits (as smb_index_build)
+    return fail(ctx, SMB_ERR_ARG, "index parameters out of range (k=%d nskip=%d typ=%d)", wordlen, nskip, typ);
   cudaSetDevice(ctx->device);
   Index ix{};
   ix.typ = typ; ix.wordlen = wordlen; ix.nskip = nskip; ix.nbits_key = nbits_key; ix.nbits_lo = nbits_lo;
@@ -824,12 +731,16 @@ static int seed_batch_impl(smb_ctx *ctx, const Index &ixt, const IndexTab *d_tab
   ctx->last_ms = 0.f;
   ctx->last_launches = 0;
   if (!nreads) return SMB_OK;
+  // the buffers of the previous batch may be reallocated below: its state is gone from here on and
+  // the new one is published only on success
+  ctx->seed_nreads = 0;
+  ctx->hit_qmask_valid = false;
   if (!d_tab && !ctx->have_index) return fail(ctx, SMB_ERR_STATE, "smb_index_upload() first");
   if (!ctx->src.arena) return fail(ctx, SMB_ERR_STATE, "smb_arena_upload() first");
   if (basq_thresh < 0 || basq_thresh + 0x21 > 255) return fail(ctx, 67 /* ERRCODE_QUALVAL */, "quality threshold");
   std::vector<uint64_t> slot((size_t)nreads + 1, 0);
   for (int i = 0; i < nreads; ++i) {
-    if (read_off[i] + read_len[i] > ctx->arena_bytes)
+    if (read_off[i] > ctx->arena_bytes || read_len[i] > ctx->arena_bytes - read_off[i])
       return fail(ctx, SMB_ERR_ARG, "read %d outside the arena", i);
     slot[(size_t)i + 1] = slot[(size_t)i] + 2ull * read_len[i];
   }

@@ -1,0 +1,509 @@
+// api_block.cu - smb_block_run / smb_block_fetch: a block of reads resident on the device from the
+// seed tables to the alignments (include/smalt_b200.h, "resident block").  Host work per block:
+// sizing buffers from a few counters read back at four points, launch grids from class histograms.
+#include "ctx.h"
+#include "block.cuh"
+#include <cmath>
+
+namespace {
+
+// what smb_block_fetch needs from the last smb_block_run
+struct Pending {
+  bool valid = false, multipass = false;
+  int njobs = 0;
+  size_t ncand = 0, nk3 = 0, nres = 0, ndiff = 0;
+  // fast path: device pointers for the gather
+  smb_ali_result *d_res = nullptr;
+  uint32_t *d_nres = nullptr, *d_dused = nullptr, *d_first = nullptr;
+  int32_t *d_errs = nullptr;
+  uint64_t *d_diff_off = nullptr;
+  unsigned long long *d_diff_first = nullptr;
+  smb_block_read *d_rd = nullptr;
+  smb_block_cand *d_k3c = nullptr;
+  int max_res = 4;
+  // debug access
+  BlockArgs args{};
+  // multi-pass path: results assembled on the host
+  std::vector<smb_ali_result> v_res;
+  std::vector<uint32_t> v_first;
+  std::vector<uint8_t> v_diff;
+  std::vector<int32_t> v_errs;
+};
+
+inline size_t al256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+struct Carver {   // carves aligned arrays out of one device buffer
+  char *base;
+  size_t off = 0;
+  explicit Carver(void *p) : base((char *)p) {}
+  template <class T> T *take(size_t n) {
+    T *r = (T *)(base ? base + off : nullptr);
+    off += al256(n * sizeof(T));
+    return r;
+  }
+};
+
+}  // namespace
+
+struct BlockState { Pending p; };
+
+void block_state_free(smb_ctx *ctx) {
+  delete ctx->blk;
+  ctx->blk = nullptr;
+}
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+  return ms;
+}
+
+extern "C" {
+
+int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job *jobs, int njobs,
+                  const smb_block_ival *ivals, int nivals, smb_block_sizes *sizes) {
+  if (!ctx || !prm || !sizes || njobs < 0 || nivals < 0 || (njobs && !jobs) || (nivals && !ivals)) return SMB_ERR_ARG;
+  memset(sizes, 0, sizeof *sizes);
+  ctx->last_ms = 0.f;
+  ctx->last_launches = 0;
+  if (!ctx->blk) ctx->blk = new (std::nothrow) BlockState();
+  if (!ctx->blk) return SMB_ERRCODE_NOMEM;
+  Pending &P = ctx->blk->p;
+  P.valid = false;
+  if (!njobs) { P = Pending(); P.valid = true; return SMB_OK; }
+  if (!ctx->seed_nreads) return fail(ctx, SMB_ERR_STATE, "smb_seed_batch() first");
+  if (!ctx->src.packed || !ctx->d_seq_offs || ctx->seq_offs.size() < 2)
+    return fail(ctx, SMB_ERR_STATE, "smb_refseq_upload() with sequence offsets first");
+  const int nseq = (int)ctx->seq_offs.size() - 1;
+  const Scoring &sc = ctx->sc;
+  if (sc.match - sc.mismatch < 1 || sc.gap_ext <= 0 || sc.mismatch >= 0 || sc.match - (-sc.gap_init) < 1)
+    return fail(ctx, SMB_ERRCODE_ASSERT, "penalties outside the range mapSingleRead accepts (rmap.c:1266, :639)");
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  for (cudaEvent_t &e : ctx->blk_ev)
+    if (!e) CU(cudaEventCreate(&e));
+
+  // requests of every job: 2 strands x (sequences | intervals)
+  const size_t nj = (size_t)njobs;
+  const size_t stage_need = al256((nj + 1) * 4) + al256(sizeof(BlockCounters)) + 1024;
+  CU(ctx->stage.ensure(stage_need));
+  uint32_t *h_job_req = ctx->stage.as<uint32_t>();
+  BlockCounters *h_cnt = (BlockCounters *)((char *)ctx->stage.p + al256((nj + 1) * 4));
+  unsigned long long *h_tot = (unsigned long long *)(h_cnt + 1);   // a few totals read back
+  uint64_t nreq64 = 0;
+  uint32_t maxlen = 0;
+  for (int j = 0; j < njobs; ++j) {
+    if (jobs[j].seed_read >= (uint32_t)ctx->seed_nreads) return fail(ctx, SMB_ERR_ARG, "job %d: read %u out of range", j, jobs[j].seed_read);
+    if (jobs[j].niv >= 0 && (uint64_t)jobs[j].iv_first + (uint64_t)jobs[j].niv > (uint64_t)nivals)
+      return fail(ctx, SMB_ERR_ARG, "job %d: intervals out of range", j);
+    h_job_req[j] = (uint32_t)nreq64;
+    nreq64 += 2ull * (uint64_t)(jobs[j].niv < 0 ? nseq : jobs[j].niv);
+    const uint32_t l = ctx->seed_len[jobs[j].seed_read];
+    if (l > maxlen) maxlen = l;
+  }
+  if (nreq64 > 0x7fffffffull) return fail(ctx, SMB_ERR_ARG, "too many hit-list requests in one block");
+  h_job_req[njobs] = (uint32_t)nreq64;
+  const int nreq = (int)nreq64;
+  const size_t nr = (size_t)nreq;
+  for (int k = 0; k < nivals; ++k)
+    if (ivals[k].seqidx < 0 || ivals[k].seqidx >= nseq) return fail(ctx, SMB_ERR_ARG, "interval %d: sequence out of range", k);
+
+  // ---- per-job arrays ----
+  const int jtiles = compact_tiles(njobs > nreq ? njobs : (nreq > 0 ? nreq : 1)) + 1;
+  {
+    Carver c(nullptr);
+    c.take<smb_block_job>(nj); c.take<uint32_t>(nj + 1); c.take<smb_block_ival>((size_t)nivals + 1);
+    c.take<uint32_t>(nj); c.take<uint32_t>(nj); c.take<uint32_t>(2 * nj); c.take<smb_block_read>(nj);
+    c.take<unsigned long long>(nj + 1); c.take<unsigned long long>(nj + 1); c.take<unsigned long long>((size_t)jtiles);
+    c.take<BlockCounters>(1); c.take<int>(64);
+    CU(ctx->blk_jobs.ensure(c.off));
+  }
+  BlockArgs a{};
+  Carver cj(ctx->blk_jobs.p);
+  smb_block_job *d_jobs = cj.take<smb_block_job>(nj);
+  uint32_t *d_job_req = cj.take<uint32_t>(nj + 1);
+  smb_block_ival *d_ivals = cj.take<smb_block_ival>((size_t)nivals + 1);
+  a.n_sort = cj.take<uint32_t>(nj);
+  a.nk3 = cj.take<uint32_t>(nj);
+  a.cover_deficit = cj.take<uint32_t>(2 * nj);
+  a.rd = cj.take<smb_block_read>(nj);
+  unsigned long long *d_cand_first = cj.take<unsigned long long>(nj + 1);
+  unsigned long long *d_k3_first = cj.take<unsigned long long>(nj + 1);
+  unsigned long long *d_tile = cj.take<unsigned long long>((size_t)jtiles);
+  a.cnt = cj.take<BlockCounters>(1);
+  int *d_k2_tickets = cj.take<int>(64);
+  a.jobs = d_jobs; a.njobs = njobs; a.ivals = d_ivals; a.prm = *prm;
+  a.ktup = ctx->seed_ix.wordlen; a.nskip = ctx->seed_ix.nskip; a.nseq = nseq;
+  a.match = sc.match; a.mismatch = sc.mismatch; a.gap_init = sc.gap_init; a.gap_ext = sc.gap_ext;
+  a.seq_offs = ctx->d_seq_offs;
+  a.seed = ctx->seed_args;
+  a.job_req = d_job_req;
+  a.cand_first = d_cand_first;
+  a.k3_first = d_k3_first;
+  CU(h2d(d_jobs, jobs, nj * sizeof(smb_block_job), st));
+  CU(h2d(d_job_req, h_job_req, (nj + 1) * 4, st));
+  if (nivals) CU(h2d(d_ivals, ivals, (size_t)nivals * sizeof(smb_block_ival), st));
+  CU(cudaMemsetAsync(a.cnt, 0, sizeof(BlockCounters), st));
+
+  // ---- hit lists (as smb_hits_batch, lists stay on the device) ----
+  uint32_t nhits_alloc;
+  {
+    const double ql = (double)ctx->seed_maxlen;
+    double target = ql > 1 ? ql * log(ql) * 32.0 : 0.0;
+    if (target > 2147483647.0) target = 2147483647.0;
+    if (target < 8192.0) target = 8192.0;
+    const size_t t = (size_t)target;
+    nhits_alloc = 16384;
+    if (t > nhits_alloc) nhits_alloc = (uint32_t)((t + 16383) / 16384 * 16384);
+  }
+  {
+    Carver c(nullptr);
+    c.take<smb_hit_req>(nr + 1); c.take<uint64_t>(nr + 2); c.take<uint32_t>(nr + 1); c.take<uint32_t>(nr + 1);
+    c.take<int32_t>(nr + 1); c.take<int32_t>(nr + 1);
+    CU(ctx->hit_meta.ensure(c.off));
+  }
+  Carver ch(ctx->hit_meta.p);
+  smb_hit_req *d_req = ch.take<smb_hit_req>(nr + 1);
+  uint64_t *d_off = ch.take<uint64_t>(nr + 2);
+  uint32_t *d_count = ch.take<uint32_t>(nr + 1);
+  uint32_t *d_used = ch.take<uint32_t>(nr + 1);
+  int32_t *d_rerrs = ch.take<int32_t>(nr + 1);
+  int32_t *d_rseq = ch.take<int32_t>(nr + 1);
+  a.req = d_req; a.req_seqidx = d_rseq; a.hit_off = d_off; a.req_err = d_rerrs;
+  ctx->hit_qmask_valid = false;
+  HitArgs ha{};
+  ha.seed = ctx->seed_args; ha.req = d_req; ha.nreq = nreq; ha.nhits_alloc = nhits_alloc;
+  ha.count = d_count; ha.maxhit_used = d_used; ha.errs = d_rerrs; ha.offset = d_off; ha.sqdat = nullptr;
+  ha.list_qmask = nullptr; ha.qmask_off = nullptr;
+  int nl = 0;
+  CU(cudaEventRecord(ctx->blk_ev[0], st));
+  CU(launch_block_reqs(a, st, &nl));
+  uint64_t total_hits = 0;
+  if (nreq > 0) {
+    CU(launch_hits(ctx->seed_ix, ha, false, st, &nl));
+    CU(launch_scan_counts(d_count, nreq, (unsigned long long *)d_off, d_tile, st, &nl));
+    CU(d2h(h_tot, d_off + nreq, 8, st));
+    CU(ctx_sync(ctx));                                                          // sync 1: total hits
+    total_hits = h_tot[0];
+  } else {
+    CU(cudaMemsetAsync(d_off, 0, 16, st));
+  }
+  CU(ctx->hit_data.ensure((size_t)(total_hits + 1) * 8));
+  ha.sqdat = ctx->hit_data.as<uint64_t>();
+  a.sqdat = ha.sqdat;
+  if (nreq > 0 && total_hits) CU(launch_hits(ctx->seed_ix, ha, true, st, &nl));
+  CU(cudaEventRecord(ctx->blk_ev[1], st));
+
+  // ---- candidate selection ----
+  const size_t H = (size_t)total_hits + 1;
+  a.mask_words = (maxlen + 31u) / 32u + 1u;
+  {
+    Carver c(nullptr);
+    c.take<uint64_t>(H); c.take<int32_t>(H); c.take<uint32_t>(H); c.take<int32_t>(H); c.take<uint32_t>(H);
+    c.take<SegCand>(H); c.take<uint32_t>(H); c.take<uint32_t>(H); c.take<uint32_t>(nj * a.mask_words);
+    CU(ctx->blk_scr.ensure(c.off));
+  }
+  Carver cs(ctx->blk_scr.p);
+  a.sd_sqo = cs.take<uint64_t>(H); a.sd_len = cs.take<int32_t>(H); a.sg_ix = cs.take<uint32_t>(H);
+  a.sg_nseed = cs.take<int32_t>(H); a.sg_cover = cs.take<uint32_t>(H); a.cand = cs.take<SegCand>(H);
+  a.sort_key = cs.take<uint32_t>(H); a.sort_idx = cs.take<uint32_t>(H); a.mask = cs.take<uint32_t>(nj * a.mask_words);
+  CU(launch_block_cands(a, st, &nl));
+  CU(launch_scan_counts(a.n_sort, njobs, d_cand_first, d_tile, st, &nl));
+  CU(d2h(h_tot, d_cand_first + njobs, 8, st));
+  CU(d2h(h_cnt, a.cnt, sizeof(BlockCounters), st));
+  CU(ctx_sync(ctx));                                                            // sync 2: candidates, K2 classes
+  const size_t ncand = (size_t)h_tot[0];
+  const size_t NC = ncand + 1;
+  unsigned int nsw = 0;
+  for (int b = 0; b < BLK_K2_BINS; ++b) a.k2_start[b] = 0;
+  for (int b = 1; b <= 16; ++b) { a.k2_start[b] = nsw; nsw += h_cnt->k2_hist[b]; }
+  const unsigned int nbf = h_cnt->k2_hist[17];
+  if ((size_t)nsw + nbf != ncand) return fail(ctx, SMB_ERRCODE_ASSERT, "block: candidate classes do not add up");
+  {
+    Carver c(nullptr);
+    c.take<DCand>(NC); c.take<uint32_t>(NC); c.take<smb_sw_task>(NC); c.take<int32_t>(NC); c.take<int32_t>(NC);
+    c.take<int32_t>(NC); c.take<uint8_t>(NC); c.take<int>(NC); c.take<int>(NC); c.take<smb_band_task>(NC);
+    CU(ctx->blk_cand.ensure(c.off));
+  }
+  Carver cc(ctx->blk_cand.p);
+  a.dc = cc.take<DCand>(NC); a.dc_job = cc.take<uint32_t>(NC); a.swt = cc.take<smb_sw_task>(NC);
+  a.score = cc.take<int32_t>(NC); a.serr = cc.take<int32_t>(NC); a.k3rank = cc.take<int32_t>(NC);
+  a.k3cls = cc.take<uint8_t>(NC); a.k2_order = cc.take<int>(NC); a.bf_order = cc.take<int>(NC);
+  a.bft = cc.take<smb_band_task>(NC);
+  CU(launch_block_emit_k2(a, ncand, st, &nl));
+  CU(cudaEventRecord(ctx->blk_ev[2], st));
+
+  // ---- K2 (and K2' for the candidates outside the SIMD predicate) ----
+  if (nsw) {
+    SwPlan plan;
+    for (int c = 0; c <= 16; ++c) { plan.count[c] = c ? (int)h_cnt->k2_hist[c] : 0; plan.start[c] = (int)a.k2_start[c]; }
+    plan.max_grid = ctx->sm_count * 8;
+    plan.bstride = (h_cnt->max_rlen_multi + 31u) & ~31u;
+    plan.strip_bytes = (size_t)plan.max_grid * 4u * 2u * plan.bstride * sizeof(int2);   // SW_WARPS = 4 (sw_score.cu)
+    CU(ctx->scratch.ensure(plan.strip_bytes + 256));
+    CU(launch_sw_score(sc, ctx->src, a.swt, plan, d_k2_tickets, a.k2_order, ctx->scratch.p, a.score, a.serr, st, &nl));
+  }
+  // K2' of a list of candidates (indices in h_bf): planned on the host like smb_band_score_batch
+  auto run_band_fast = [&](const std::vector<int> &h_bf) -> int {
+    const int n = (int)h_bf.size();
+    if (!n) return SMB_OK;
+    std::vector<smb_band_task> all(ncand), sub((size_t)n);
+    CU(d2h(all.data(), a.bft, ncand * sizeof(smb_band_task), st));
+    CU(ctx_sync(ctx));
+    for (int i = 0; i < n; ++i) sub[(size_t)i] = all[(size_t)h_bf[(size_t)i]];
+    BandPlan plan;
+    plan_band(sub.data(), n, false, sc, plan);
+    std::vector<int> order((size_t)n);
+    for (int i = 0; i < n; ++i) order[(size_t)i] = h_bf[(size_t)plan.order[(size_t)i]];
+    const size_t gring_words = band_gring_words(plan);
+    CU(ctx->scratch.ensure(gring_words * sizeof(uint32_t) + 512));
+    CU(h2d(a.bf_order, order.data(), (size_t)n * sizeof(int), st));
+    CU(ctx_sync(ctx));   // `order` goes out of scope
+    unsigned long long *d_cells = &a.cnt->k2_cells_ref;   // (cells of K2' are not reported; any 8-byte slot)
+    BandOut bo{nullptr, nullptr, nullptr, a.serr, d_cells, nullptr};
+    CU(launch_band(sc, ctx->src, a.bft, plan, a.bf_order, false, a.score, bo, 0, nullptr, nullptr, nullptr, nullptr,
+                   ctx->scratch.as<uint32_t>(), ctx->ticket.as<int>(), ctx->sm_count, st, &nl));
+    return SMB_OK;
+  };
+  if (nbf) {
+    std::vector<int> h_bf((size_t)nbf);
+    CU(d2h(h_bf.data(), a.bf_order, (size_t)nbf * sizeof(int), st));
+    CU(ctx_sync(ctx));
+    const int rc = run_band_fast(h_bf);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(&a.cnt->k2_cells_ref, 0, 8, st));
+  }
+  CU(cudaEventRecord(ctx->blk_ev[3], st));
+
+  // ---- replay of the sequential score bookkeeping, K3 task list ----
+  size_t nk3 = 0;
+  for (int round = 0;; ++round) {
+    CU(launch_block_replay(a, st, &nl));
+    CU(launch_scan_counts(a.nk3, njobs, d_k3_first, d_tile, st, &nl));
+    CU(d2h(h_tot, d_k3_first + njobs, 8, st));
+    CU(d2h(h_cnt, a.cnt, sizeof(BlockCounters), st));
+    CU(ctx_sync(ctx));                                                          // sync 3: K3 classes and sizes
+    nk3 = (size_t)h_tot[0];
+    if (!h_cnt->n_exceed) break;
+    if (round) return fail(ctx, SMB_ERRCODE_ASSERT, "block: SWATEXCEED after the banded fallback");
+    // ERRCODE_SWATEXCEED -> banded fast variant (rmap.c:730-744), then the replay again
+    CU(cudaMemsetAsync(&a.cnt->bf_cursor, 0, sizeof(unsigned int), st));
+    CU(launch_block_exceed(a, ncand, st, &nl));
+    CU(d2h(h_cnt, a.cnt, sizeof(BlockCounters), st));
+    CU(ctx_sync(ctx));
+    std::vector<int> h_bf((size_t)h_cnt->bf_cursor);
+    if (!h_bf.empty()) {
+      CU(d2h(h_bf.data(), a.bf_order, h_bf.size() * sizeof(int), st));
+      CU(ctx_sync(ctx));
+      const int rc = run_band_fast(h_bf);
+      if (rc) return rc;
+    }
+    BlockCounters z = *h_cnt;   // counters of the replay start again; the K2 histogram is history
+    memset(z.k3_hist, 0, sizeof z.k3_hist);
+    z.pack_maxrows = z.pack_maxread = z.n_exceed = 0;
+    z.dir_words = z.diff_bytes = z.k2_cells_ref = z.k2_tasks_ref = 0;
+    *h_cnt = z;
+    CU(h2d(a.cnt, h_cnt, sizeof(BlockCounters), st));
+    CU(ctx_sync(ctx));
+  }
+  sizes->nhits = total_hits;
+  sizes->ncand = ncand;
+  sizes->nk2 = nsw;
+  sizes->nk2_band = nbf;
+  sizes->nk3 = nk3;
+  sizes->k2_cells = h_cnt->k2_cells;
+  sizes->k2_cells_ref = h_cnt->k2_cells_ref;
+  sizes->k2_tasks_ref = h_cnt->k2_tasks_ref;
+
+  P = Pending();
+  P.njobs = njobs;
+  P.ncand = ncand;
+  P.nk3 = nk3;
+  P.d_rd = a.rd;
+  P.args = a;
+  const int max_res = 4;
+  P.max_res = max_res;
+  float ms_k3 = 0.f;
+  if (nk3) {
+    if (nk3 > 0x7fffffffull) return fail(ctx, SMB_ERR_ARG, "too many alignment tasks in one block");
+    const int n3 = (int)nk3;
+    BandPlan plan;
+    unsigned int pos = 0;
+    for (int b = 0; b < BLK_K3_BINS; ++b) { a.k3_start[b] = pos; pos += h_cnt->k3_hist[b]; }
+    if (pos != nk3) return fail(ctx, SMB_ERRCODE_ASSERT, "block: alignment classes do not add up");
+    for (int b = 0; b < BAND_CLS_PACK8; ++b)
+      if (h_cnt->k3_hist[b]) plan.classes.push_back(BandPlan::Class{32 << b, (int)a.k3_start[b], (int)h_cnt->k3_hist[b]});
+    plan.wide_start = (int)a.k3_start[BAND_CLS_WIDE]; plan.wide_count = (int)h_cnt->k3_hist[BAND_CLS_WIDE];
+    plan.pack_start = (int)a.k3_start[BAND_CLS_PACK]; plan.pack_count = (int)h_cnt->k3_hist[BAND_CLS_PACK];
+    plan.half_start = (int)a.k3_start[BAND_CLS_HALF]; plan.half_count = (int)h_cnt->k3_hist[BAND_CLS_HALF];
+    plan.warp_start = (int)a.k3_start[BAND_CLS_WARP]; plan.warp_count = (int)h_cnt->k3_hist[BAND_CLS_WARP];
+    plan.pack_maxrows = (int)h_cnt->pack_maxrows; plan.pack_maxread = (int)h_cnt->pack_maxread;
+    const size_t N3 = nk3 + 1;
+    const int ntiles = compact_tiles(n3);
+    {
+      Carver c(nullptr);
+      c.take<smb_band_task>(N3); c.take<smb_block_cand>(N3); c.take<uint32_t>(N3); c.take<uint32_t>(N3); c.take<uint32_t>(N3);
+      c.take<int>(N3); c.take<uint64_t>(N3 + 1); c.take<uint64_t>(N3 + 1); c.take<unsigned long long>((size_t)ntiles + 1);
+      CU(ctx->blk_k3.ensure(c.off));
+    }
+    Carver c3(ctx->blk_k3.p);
+    a.bat = c3.take<smb_band_task>(N3); a.k3c = c3.take<smb_block_cand>(N3); a.dir_words_arr = c3.take<uint32_t>(N3);
+    a.diff_cap = c3.take<uint32_t>(N3); a.diff_stride = c3.take<uint32_t>(N3); a.k3_order = c3.take<int>(N3);
+    uint64_t *d_dir_off = c3.take<uint64_t>(N3 + 1);
+    uint64_t *d_diff_off = c3.take<uint64_t>(N3 + 1);
+    unsigned long long *d_tile3 = c3.take<unsigned long long>((size_t)ntiles + 1);
+    P.d_k3c = a.k3c;
+    P.args = a;
+    const bool too_big = h_cnt->dir_words > ((uint64_t)1 << 30);   // long-read sized: chunked multi-pass path
+    const size_t res_bytes = (size_t)n3 * max_res * sizeof(smb_ali_result);
+    CU(launch_block_emit_k3(a, ncand, st, &nl));
+    bool multipass = too_big;
+    if (!too_big) {
+      const size_t outa = res_bytes + (size_t)n3 * (2 * sizeof(uint32_t) + sizeof(int32_t)) + 64;
+      CU(ctx->out_b.ensure(outa));
+      CU(ctx->dirs.ensure((size_t)(h_cnt->dir_words + 4) * sizeof(uint32_t)));
+      CU(ctx->diff.ensure((size_t)h_cnt->diff_bytes + 64));
+      CU(launch_scan_counts(a.dir_words_arr, n3, (unsigned long long *)d_dir_off, d_tile3, st, &nl));
+      CU(launch_scan_counts(a.diff_stride, n3, (unsigned long long *)d_diff_off, d_tile3, st, &nl));
+      char *ob = ctx->out_b.as<char>();
+      smb_ali_result *d_res = (smb_ali_result *)ob;
+      uint32_t *d_nres = (uint32_t *)(ob + res_bytes);
+      uint32_t *d_dused = d_nres + n3;
+      int32_t *d_errs = (int32_t *)(d_dused + n3);
+      unsigned long long *d_cells = (unsigned long long *)(((uintptr_t)(d_errs + n3) + 15) & ~(uintptr_t)15);
+      CU(cudaMemsetAsync(d_cells, 0, sizeof(unsigned long long), st));
+      BandOut bo{d_res, d_nres, ctx->diff.as<uint8_t>(), d_errs, d_cells, d_dused};
+      const size_t gring_words = band_gring_words(plan);
+      CU(ctx->scratch.ensure(gring_words * sizeof(uint32_t) + 512));
+      const size_t cmp_bytes = (size_t)ntiles * 2 * 8 + 64 + (size_t)(n3 + 1) * 4 + 64 + (size_t)n3 * 8 + 64;
+      CU(ctx->cmp.ensure(cmp_bytes));
+      char *cb = ctx->cmp.as<char>();
+      unsigned long long *d_tile_res = (unsigned long long *)cb;
+      unsigned long long *d_tile_diff = d_tile_res + ntiles;
+      CompactTotals *d_tot = (CompactTotals *)(d_tile_diff + ntiles);
+      unsigned long long *d_diff_first = (unsigned long long *)(((uintptr_t)(d_tot + 1) + 63) & ~(uintptr_t)63);
+      uint32_t *d_first = (uint32_t *)(d_diff_first + n3);
+      CU(cudaEventRecord(ctx->blk_ev[4], st));
+      CU(launch_band(sc, ctx->src, a.bat, plan, a.k3_order, true, nullptr, bo, max_res, d_dir_off, ctx->dirs.as<uint32_t>(),
+                     d_diff_off, a.diff_cap, ctx->scratch.as<uint32_t>(), ctx->ticket.as<int>(), ctx->sm_count, st, &nl,
+                     &ctx->side));
+      CU(launch_compact_scan(d_nres, d_dused, d_errs, n3, d_tile_res, d_tile_diff, d_tot, d_first, d_diff_first, st, &nl));
+      CU(cudaEventRecord(ctx->blk_ev[5], st));
+      CompactTotals *h_ct = (CompactTotals *)(h_tot + 2);
+      unsigned long long *h_cells = (unsigned long long *)(h_ct + 1);
+      CU(d2h(h_ct, d_tot, sizeof(CompactTotals), st));
+      CU(d2h(h_cells, d_cells, sizeof(unsigned long long), st));
+      CU(ctx_sync(ctx));                                                        // sync 4: result sizes
+      ms_k3 = ev_ms(ctx->blk_ev[4], ctx->blk_ev[5]);
+      if (h_ct->capacity_flag || h_ct->ndiff > 0xffffffffull) multipass = true;
+      else {
+        P.nres = (size_t)h_ct->nresults;
+        P.ndiff = (size_t)h_ct->ndiff;
+        P.d_res = d_res; P.d_nres = d_nres; P.d_dused = d_dused; P.d_first = d_first; P.d_errs = d_errs;
+        P.d_diff_off = d_diff_off; P.d_diff_first = d_diff_first;
+        sizes->k3_cells = *h_cells;
+      }
+    }
+    if (multipass) {
+      std::vector<smb_band_task> h_bat(nk3);
+      CU(d2h(h_bat.data(), a.bat, nk3 * sizeof(smb_band_task), st));
+      CU(ctx_sync(ctx));
+      uint64_t cells = 0;
+      const float keep_ms = ctx->last_ms;
+      ctx->last_ms = 0.f;
+      const int rc = band_align_multipass(ctx, h_bat.data(), n3, P.v_res, P.v_first, P.v_diff, P.v_errs, &cells);
+      if (rc) return rc;
+      ms_k3 += ctx->last_ms;
+      ctx->last_ms = keep_ms;
+      P.multipass = true;
+      P.nres = P.v_res.size();
+      P.ndiff = P.v_diff.size();
+      sizes->k3_cells = cells;
+    }
+  }
+  sizes->nresults = P.nres;
+  sizes->ndiffbytes = P.ndiff;
+  sizes->ms_hits = ev_ms(ctx->blk_ev[0], ctx->blk_ev[1]);
+  sizes->ms_cand = ev_ms(ctx->blk_ev[1], ctx->blk_ev[2]);
+  sizes->ms_k2 = ev_ms(ctx->blk_ev[2], ctx->blk_ev[3]);
+  sizes->ms_k3 = ms_k3;
+  sizes->launches = nl;
+  ctx->last_ms = sizes->ms_hits + sizes->ms_cand + sizes->ms_k2 + sizes->ms_k3;
+  ctx->last_launches += nl;
+  ctx->total_launches += nl;
+  g_launches += nl;
+  P.valid = true;
+  return SMB_OK;
+}
+
+int smb_block_fetch(smb_ctx *ctx, smb_block_read *reads, smb_block_cand *cands, int32_t *errs, uint32_t *first_result,
+                    smb_ali_result *results, uint8_t *diffstr) {
+  if (!ctx) return SMB_ERR_ARG;
+  if (!ctx->blk || !ctx->blk->p.valid) return fail(ctx, SMB_ERR_STATE, "smb_block_run() first");
+  Pending &P = ctx->blk->p;
+  if (!P.njobs) return SMB_OK;
+  if (!reads || (P.nk3 && (!cands || !errs || !first_result)) || (P.nres && !results) || (P.ndiff && !diffstr))
+    return SMB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  int nl = 0;
+  CU(d2h(reads, P.d_rd, (size_t)P.njobs * sizeof(smb_block_read), st));
+  if (P.nk3) {
+    CU(d2h(cands, P.d_k3c, P.nk3 * sizeof(smb_block_cand), st));
+    if (P.multipass) {
+      memcpy(errs, P.v_errs.data(), P.nk3 * sizeof(int32_t));
+      memcpy(first_result, P.v_first.data(), (P.nk3 + 1) * sizeof(uint32_t));
+      if (P.nres) memcpy(results, P.v_res.data(), P.nres * sizeof(smb_ali_result));
+      if (P.ndiff) memcpy(diffstr, P.v_diff.data(), P.ndiff);
+    } else {
+      // dense arrays reuse the direction-strip buffer (no longer needed)
+      const size_t dense_bytes = P.nres * sizeof(smb_ali_result) + P.ndiff + 64;
+      CU(ctx->dirs.ensure(dense_bytes));
+      smb_ali_result *d_dense = ctx->dirs.as<smb_ali_result>();
+      uint8_t *d_ddiff = (uint8_t *)(d_dense + P.nres);
+      CU(launch_compact_gather(P.d_res, P.d_nres, ctx->diff.as<uint8_t>(), P.d_diff_off, P.d_dused, (int)P.nk3, P.max_res,
+                               P.d_first, P.d_diff_first, d_dense, d_ddiff, st, &nl));
+      if (P.nres) CU(d2h(results, d_dense, P.nres * sizeof(smb_ali_result), st));
+      if (P.ndiff) CU(d2h(diffstr, d_ddiff, P.ndiff, st));
+      CU(d2h(first_result, P.d_first, (P.nk3 + 1) * sizeof(uint32_t), st));
+      CU(d2h(errs, P.d_errs, P.nk3 * sizeof(int32_t), st));
+    }
+  }
+  CU(ctx_sync(ctx));
+  ctx->last_launches += nl;
+  ctx->total_launches += nl;
+  g_launches += nl;
+  return SMB_OK;
+}
+
+int smb_block_debug_cands(smb_ctx *ctx, uint64_t *cand_first, smb_block_cand *cands, uint32_t *cover, uint32_t *qs_qe,
+                          size_t max_cands) {
+  if (!ctx || !cand_first) return SMB_ERR_ARG;
+  if (!ctx->blk || !ctx->blk->p.valid) return fail(ctx, SMB_ERR_STATE, "smb_block_run() first");
+  const Pending &P = ctx->blk->p;
+  if (!P.njobs) return SMB_OK;
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = ctx->stream;
+  CU(d2h(cand_first, P.args.cand_first, ((size_t)P.njobs + 1) * sizeof(uint64_t), st));
+  CU(ctx_sync(ctx));
+  if (P.ncand > max_cands) return fail(ctx, SMB_ERR_CAPACITY, "need room for %zu candidates", P.ncand);
+  if (!P.ncand) return SMB_OK;
+  std::vector<DCand> dc(P.ncand);
+  std::vector<int32_t> score(P.ncand);
+  CU(d2h(dc.data(), P.args.dc, P.ncand * sizeof(DCand), st));
+  CU(d2h(score.data(), P.args.score, P.ncand * sizeof(int32_t), st));
+  CU(ctx_sync(ctx));
+  for (size_t i = 0; i < P.ncand; ++i) {
+    if (cands) {
+      smb_block_cand &o = cands[i];
+      memset(&o, 0, sizeof o);
+      o.rs = dc[i].rs; o.sqidx = dc[i].sqidx; o.swscor = score[i]; o.reflen = dc[i].reflen;
+      o.band_l = dc[i].band_l; o.band_r = dc[i].band_r; o.reverse = dc[i].rev;
+    }
+    if (cover) cover[i] = dc[i].cover;
+    if (qs_qe) { qs_qe[2 * i] = dc[i].qs; qs_qe[2 * i + 1] = dc[i].qe; }
+  }
+  return SMB_OK;
+}
+
+}  // extern "C"

@@ -95,3 +95,45 @@ SMB_HD bool band_warp_eligible(int l_edge, int r_edge, int p_left, int p_right, 
   return band_warp_lanes(l_edge, r_edge, p_left, p_right, read_len, u_left, u_right, ref_len) != 0;
 }
 }  // namespace smb
+
+// ---- thread-per-task band_kernel (band_dp.cu): ring capacity classes ----
+namespace smb {
+// band cells a row of the task can hold (the H/E ring of band_kernel); `fast` = score-only variant
+SMB_HD int band_ring_need(int l_edge, int r_edge, int p_left, int p_right, int read_len, int u_left, int u_right,
+                          int ref_len, bool fast) {
+  Band b;
+  if (band_init(b, l_edge, r_edge, p_left, p_right, read_len, u_left, u_right, ref_len)) return 1;
+  const int bw0 = r_edge - l_edge + 1;
+  int full = b.q_len - b.q_left;
+  if (full < 1) full = 1;
+  const int w = (bw0 <= 0 || (fast && b.q_left > b.l_edge)) ? full : (bw0 < full ? bw0 : full);
+  return w < 1 ? 1 : w;
+}
+SMB_HD int band_pow2_at_least(int v) {
+  int p = 32;
+  while (p < v) p <<= 1;
+  return p;
+}
+// class of a thread-per-task launch: ring capacity 32 << class
+SMB_HD int band_ring_class(int need) {
+  const int wcap = band_pow2_at_least(need + 1);
+  int c = 0;
+  while ((32 << c) < wcap) ++c;
+  return c;
+}
+// pseudo classes of the warp kernels (last in BandPlan.order)
+constexpr int BAND_CLS_WARP = 31, BAND_CLS_HALF = 30, BAND_CLS_PACK = 29, BAND_CLS_WIDE = 28, BAND_CLS_PACK8 = 27;
+// direction words a task needs in the HBM strip of band_kernel<true> (2 for the warp kernels)
+SMB_HD unsigned long long band_dir_words(int l_edge, int r_edge, int p_left, int p_right, int read_len, int u_left,
+                                         int u_right, int ref_len) {
+  Band b;
+  if (band_warp_eligible(l_edge, r_edge, p_left, p_right, read_len, u_left, u_right, ref_len) ||
+      band_wide_eligible(l_edge, r_edge, p_left, p_right, read_len, u_left, u_right, ref_len) ||
+      band_init(b, l_edge, r_edge, p_left, p_right, read_len, u_left, u_right, ref_len))
+    return 2;
+  const int bw0 = r_edge - l_edge + 1;
+  int w = (bw0 <= 0) ? (b.q_len - b.q_left) : bw0;
+  if (w < 1) w = 1;
+  return ((unsigned long long)w * (unsigned long long)ref_len) / 16u + 4u;
+}
+}  // namespace smb

@@ -302,24 +302,6 @@ band_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__restrict_
 // ------------------------------------------------------------------------------------
 // host side planning
 // ------------------------------------------------------------------------------------
-static int ring_need(const smb_band_task &t, bool fast) {
-  Band b;
-  if (band_init(b, t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
-                (int)t.ref_len))
-    return 1;
-  const int bw0 = t.r_edge - t.l_edge + 1;
-  int full = b.q_len - b.q_left;
-  if (full < 1) full = 1;
-  int w = (bw0 <= 0 || (fast && b.q_left > b.l_edge)) ? full : std::min(bw0, full);
-  return w < 1 ? 1 : w;
-}
-
-static int pow2_at_least(int v) {
-  int p = 32;
-  while (p < v) p <<= 1;
-  return p;
-}
-
 // Host-side plan: tasks bucketed by ring capacity (one launch per class), input order kept
 // inside a class (neighbouring tasks come from the same read / candidate list and have
 // similar geometry, so the threads of a warp stay balanced without a full sort).
@@ -328,8 +310,8 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, const Scori
   plan.classes.clear();
   std::vector<int> wc((size_t)ntasks);
   int count[32] = {0};
-  auto cls = [](int wcap) { int c = 0; while ((32 << c) < wcap) ++c; return c; };
-  constexpr int WARP_CLS = 31, HALF_CLS = 30, PACK_CLS = 29, WIDE_CLS = 28, PACK8_CLS = 27;  // pseudo classes of the warp kernels (last in `order`)
+  constexpr int WARP_CLS = BAND_CLS_WARP, HALF_CLS = BAND_CLS_HALF, PACK_CLS = BAND_CLS_PACK, WIDE_CLS = BAND_CLS_WIDE,
+                PACK8_CLS = BAND_CLS_PACK8;
   // packed 16-bit kernel: scores must stay far below 2^15 (band_pack.cu)
   const bool pen16 = sc.match > 0 && sc.match < 128 && sc.mismatch <= 0 && sc.mismatch > -128 && sc.gap_init > 0 &&
                      sc.gap_init < 4000 && sc.gap_ext >= 0 && sc.gap_ext < 4000 && sc.S[5] == 0 && sc.S[5 * 8] == 0 &&
@@ -361,8 +343,8 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, const Scori
                                   (int)t.ref_len)) {
       wc[(size_t)i] = WIDE_CLS;
     } else {
-      const int need = ring_need(t, !align);
-      wc[(size_t)i] = cls(pow2_at_least(need + 1));
+      wc[(size_t)i] = band_ring_class(band_ring_need(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left,
+                                                      t.u_right, (int)t.ref_len, !align));
     }
     count[wc[(size_t)i]]++;
   }
@@ -393,13 +375,10 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
                         const uint64_t *d_diff_off, const uint32_t *d_diff_cap,
                         uint32_t *d_gring, int *d_ticket, int sm_count, cudaStream_t main_st, int *nlaunch,
                         const BandSide *side) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(band_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(band_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
+  static std::atomic<unsigned long long> smem_done_a{0}, smem_done_f{0};
   cudaError_t e;
+  if ((e = ensure_dyn_smem(band_kernel<true>, 200 * 1024, smem_done_a)) != cudaSuccess) return e;
+  if ((e = ensure_dyn_smem(band_kernel<false>, 200 * 1024, smem_done_f)) != cudaSuccess) return e;
   // the packed kernels take (nearly) all tasks of a short-read batch; whatever else the batch holds goes
   // to the side stream
   const bool packed_any = align && (plan.pack_count || plan.pack8_count);

@@ -559,12 +559,10 @@ static cudaError_t launch_pack_t(const Scoring &sc, const SeqSrc &src, const smb
                                  int ntasks, int max_rows, int max_read, int *d_ticket, BandOut out, int max_res,
                                  const uint64_t *d_diff_off, const uint32_t *d_diff_cap, int sm_count, cudaStream_t st,
                                  int *nlaunch) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(band_pack_kernel<LANES, ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set = true;
-  }
-  cudaError_t e = cudaMemsetAsync(d_ticket, 0, sizeof(int), st);
+  static std::atomic<unsigned long long> smem_done{0};
+  cudaError_t e = ensure_dyn_smem(band_pack_kernel<LANES, ND>, 200 * 1024, smem_done);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(d_ticket, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
   PackLayout lay{(max_rows + 31) & ~31, (max_read + 15) & ~15, LANES, 8 / ND};
   if (lay.R < 32) lay.R = 32;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <atomic>
 #include <vector>
 #include "../../include/smalt_b200.h"
 
@@ -42,6 +43,20 @@ __device__ __forceinline__ uint32_t read_base(const uint8_t *__restrict__ arena,
   uint32_t c = __ldg(arena + off + (rc ? (len - 1u - j) : j)) & 7u;
   if (rc && c < 4u) c = 3u - c;
   return c;
+}
+
+// Opt-in to large dynamic shared memory, once per DEVICE (the attribute is per device; contexts of
+// several GPUs can live in one process and worker threads race here harmlessly).
+template <class F>
+inline cudaError_t ensure_dyn_smem(F *func, int bytes, std::atomic<unsigned long long> &done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
 }
 
 struct Timer {

@@ -20,6 +20,7 @@
 // unchanged inside that thread, which keeps them bit-identical by construction.
 // Per-strand tables live in HBM in SoA form (read_len slots per strand).
 #include "common.cuh"
+#include "sort2.cuh"
 #include <vector>
 
 namespace smb {
@@ -73,48 +74,6 @@ __device__ __forceinline__ uint32_t fetch_positions(const Index &ix, uint32_t po
     return __ldg(ix.posidx + posidx + 1) - s;
   }
   return 0;
-}
-
-// sort2UINTarraysByQuickSort (sort.c:233-330): median-of-three quicksort, insertion sort
-// below 7 elements, explicit stack, smaller partition first.  Unstable; the exchange
-// sequence is reproduced so that ties end up in the reference's order.
-__device__ int sort2(int n, uint32_t *key, uint32_t *val) {
-  int lo = 0, hi = n - 1, sp = 0, i, j;
-  int stack[62];
-#define XC(a, b) do { uint32_t t_ = (a); (a) = (b); (b) = t_; } while (0)
-  for (;;) {
-    if (hi - lo < 7) {
-      for (j = lo + 1; j <= hi; ++j) {
-        const uint32_t k = key[j], v = val[j];
-        for (i = j - 1; i >= lo && key[i] > k; --i) { key[i + 1] = key[i]; val[i + 1] = val[i]; }
-        key[i + 1] = k; val[i + 1] = v;
-      }
-      if (!sp) return 0;
-      hi = stack[sp--];
-      lo = stack[sp--];
-    } else {
-      const int mid = (lo + hi) >> 1;
-      XC(key[mid], key[lo + 1]); XC(val[mid], val[lo + 1]);
-      if (key[lo] > key[hi]) { XC(key[lo], key[hi]); XC(val[lo], val[hi]); }
-      if (key[lo + 1] > key[hi]) { XC(key[lo + 1], key[hi]); XC(val[lo + 1], val[hi]); }
-      if (key[lo] > key[lo + 1]) { XC(key[lo], key[lo + 1]); XC(val[lo], val[lo + 1]); }
-      i = lo + 1; j = hi;
-      const uint32_t pk = key[lo + 1], pv = val[lo + 1];
-      for (;;) {
-        do ++i; while (key[i] < pk);
-        do --j; while (key[j] > pk);
-        if (j < i) break;
-        XC(key[i], key[j]); XC(val[i], val[j]);
-      }
-      key[lo + 1] = key[j]; val[lo + 1] = val[j];
-      key[j] = pk; val[j] = pv;
-      sp += 2;
-      if (sp > 60) return 34;  // ERRCODE_SORTSTACK
-      if (hi - i + 1 >= j - lo) { stack[sp] = hi; stack[sp - 1] = i; hi = j - 1; }
-      else { stack[sp] = j - 1; stack[sp - 1] = lo; lo = i; }
-    }
-  }
-#undef XC
 }
 
 // The same sort by all lanes of a warp.  The result of sort2 for a sub-array depends on nothing but
@@ -649,11 +608,9 @@ cudaError_t launch_seed(const Index &ix, const uint8_t *arena, const SeedArgs &a
   SeedWarpLayout lay{(int)((a.maxlen + 63u) & ~63u)};
   const size_t smem = lay.bytes() * SEEDW_WARPS;
   if (a.is_short && a.maxlen > 0 && a.maxlen <= 2048u && ix.nskip <= 32 && ix.wordlen <= 31 && smem <= 200 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(seed_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_set = true;
-    }
+    static std::atomic<unsigned long long> smem_done{0};
+    const cudaError_t ea = ensure_dyn_smem(seed_warp_kernel, 200 * 1024, smem_done);
+    if (ea != cudaSuccess) return ea;
     seed_warp_kernel<<<(n + SEEDW_WARPS - 1) / SEEDW_WARPS, SEEDW_WARPS * 32, smem, st>>>(ix, arena, a, lay);
   } else {
     seed_kernel<<<(n + 127) / 128, 128, 0, st>>>(ix, arena, a);

@@ -101,7 +101,7 @@ enum { PST_END = 0, PST_SECOND_UNRESTRICTED = 3, PST_RESCUE_MAIN = 4, PST_RESCUE
 typedef struct { void *p; size_t cap; } WBUF;
 enum { WB_ARENA, WB_QUAL, WB_READ_OFF, WB_READ_LEN, WB_INFO, WB_INFO4, WB_REQ, WB_LIST_FIRST, WB_REQ_ERR, WB_SQDAT,
        WB_SWT, WB_SW_SCORE, WB_SW_ERR, WB_BFT, WB_BF_SCORE, WB_BF_ERR, WB_BAT, WB_BA_ERR, WB_RES,
-       WB_RES_FIRST, WB_DIFF, WB_COUNT };
+       WB_RES_FIRST, WB_DIFF, WB_BJOB, WB_BIVAL, WB_BRD, WB_BCAND, WB_COUNT };
 
 struct RmapWave_ {
   smb_ctx *ctx;
@@ -159,6 +159,7 @@ struct RmapWave_ {
   double wall_res[3]; /* inside results: add alignments, sort/MAPQ/filter, emit (report + format) */
   double cpu[8];      /* thread CPU seconds of the same eight stages (wall minus waiting for the GPU) */
   uint64_t cells_k2, cells_k3, n_k2, n_k3, n_reads;
+  double ms_cand;     /* part of ms_k1: candidate selection + task lists on the device */
 };
 
 static void *wbuf_need(WBUF *b, size_t bytes)
@@ -320,6 +321,192 @@ static int wave_seed(ErrMsg *errmsgp, RmapWave *w, int n, SeqFastq **reads, int 
   return ERRCODE_SUCCESS;
 }
 
+/* SMALT_B200_HOSTCAND: candidate selection with the reference's segment.c on the host (the first
+ * version of this driver) instead of on the device - kept for comparing the two */
+static int wave_host_cand(void)
+{
+  static int state = -1;
+  if (state < 0) state = getenv("SMALT_B200_HOSTCAND") != NULL;
+  return state;
+}
+
+/* waves 1b-3 with the block resident on the device (smb_block_run / smb_block_fetch): hit lists,
+ * candidate selection (segment.c), K2, the score replay (rmap.c:745-786, :1373-1400) and K3 run
+ * back to back on the GPU; the host gets the per-read summaries, the aligned candidates and their
+ * alignments and replays alignRMAPCANDFull's result handling (rmap.c:881-926) with results.c. */
+static int wave_pass_dev(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, const WJOB *jobs, const smb_seed_info *info,
+			 int ktuple_maxhit, int min_swatscor_below_max_arg, short target_depth, short max_depth,
+			 RMAPFLG_t rmapflg, const ScoreMatrix *scormtxp,
+			 const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
+			 WAVE_DONEF *donef, void *user)
+{
+  int errcode = ERRCODE_SUCCESS, rc, i;
+  UCHAR nskip;
+  const UCHAR ktup = hashTableGetKtupLen(htp, &nskip);
+  const SETSIZ_t *soffs;
+  const SEQNUM_t nseq = seqSetGetOffsets(ssp, &soffs);
+  RMAPBUFF *bufp = rmp->bfp;
+  short matchscor = 0, mismatchscor = 0, gapinitscor = 0, gapextscor = 0;
+  smb_block_job *bj;
+  smb_block_ival *biv;
+  smb_block_read *brd;
+  smb_block_cand *bc;
+  smb_block_params prm;
+  smb_block_sizes sz;
+  double tw = wnow(), tc = cnow(), tres;
+  size_t k;
+
+  (void) ktup;
+  if (n < 1) return ERRCODE_SUCCESS;
+  WGROW(w->rd, w->n_alloc, n, WREAD);
+  /* penalties are those of the score matrix, identical for every read (rmap.c:1258-1266) */
+  for (i = 0; i < n; i++)
+    if (!info[2 * jobs[i].seed_read].err && !info[2 * jobs[i].seed_read + 1].err) break;
+  if (i < n) {
+    short mismatchdiff;
+    if ((errcode = scoreMakeProfileFromSequence(w->prof, jobs[i].readp, scormtxp))) return errcode;
+    matchscor = scoreProfileGetAvgPenalties(&mismatchscor, &gapinitscor, &gapextscor, w->prof);
+    if ((rc = smbShimSetScoring(w->ctx, w->prof))) return gpu_fail(errmsgp, w, rc);
+    mismatchdiff = (short) (matchscor - mismatchscor);
+    if (mismatchdiff < 0 || gapextscor >= 0 || mismatchscor >= 0) return ERRCODE_ASSERT;
+    if ((short) (matchscor - mismatchscor) < 1 || (short) (matchscor - gapinitscor) < 1) return ERRCODE_ASSERT;
+  }
+  WPIN(bj, WB_BJOB, n, smb_block_job);
+  WPIN(biv, WB_BIVAL, w->niv + 1, smb_block_ival);
+  for (i = 0; i < n; i++) {
+    const WJOB *jb = jobs + i;
+    memset(bj + i, 0, sizeof(*bj));
+    bj[i].seed_read = jb->seed_read;
+    bj[i].niv = jb->niv < 0 ? -1 : jb->niv;
+    bj[i].iv_first = jb->niv < 0 ? 0 : jb->iv_first;
+    bj[i].min_cover = jb->min_cover;
+    bj[i].min_swatscor = jb->min_swatscor;
+  }
+  for (k = 0; k < w->niv; k++) {
+    biv[k].lo = w->iv[k].lo; biv[k].hi = w->iv[k].hi; biv[k].seqidx = w->iv[k].sx; biv[k].reserved = 0;
+  }
+  memset(&prm, 0, sizeof(prm));
+  prm.nhit_max = (uint32_t) ktuple_maxhit;
+  prm.min_swatscor_below_max = min_swatscor_below_max_arg;
+  prm.target_depth = (int32_t) target_depth;
+  prm.max_depth = (int32_t) max_depth;
+  prm.best = (uint8_t) ((rmapflg & RMAPFLG_BEST) != 0);
+  prm.sensitive = (uint8_t) ((rmapflg & RMAPFLG_SENSITIVE) != 0);
+  {
+    SETSIZ_t roffs;
+    const SEQLEN_t rlen0 = nseq > 0 ? seqSetGetSeqDatByIndex(&roffs, NULL, 0, ssp) : 0;
+    prm.termchar = (uint8_t) (nseq > 0 && (SETSIZ_t) rlen0 != soffs[1] - soffs[0]);
+  }
+  WTICK(3);
+  if ((rc = smb_block_run(w->ctx, &prm, bj, n, biv, (int) w->niv, &sz))) return gpu_fail(errmsgp, w, rc);
+  w->ms_k1 += sz.ms_hits + sz.ms_cand;
+  w->ms_cand += sz.ms_cand;
+  w->ms_k2 += sz.ms_k2;
+  w->ms_k3 += sz.ms_k3;
+  w->n_k2 += sz.k2_tasks_ref;
+  w->cells_k2 += sz.k2_cells_ref;
+  w->n_k3 += sz.nk3;
+  w->cells_k3 += sz.k3_cells;
+  WPIN(brd, WB_BRD, n, smb_block_read);
+  WPIN(bc, WB_BCAND, sz.nk3 + 1, smb_block_cand);
+  WPIN(w->ba_err, WB_BA_ERR, sz.nk3 + 1, int32_t);
+  WPIN(w->res_first, WB_RES_FIRST, sz.nk3 + 2, uint32_t);
+  if (w->res_alloc < sz.nresults + 1) {
+    WPIN(w->res, WB_RES, sz.nresults + sz.nresults / 2 + 64, smb_ali_result);
+    w->res_alloc = w->wb[WB_RES].cap / sizeof(smb_ali_result);
+  }
+  if (w->diff_alloc < sz.ndiffbytes + 1) {
+    WPIN(w->diff, WB_DIFF, sz.ndiffbytes + sz.ndiffbytes / 2 + 4096, uint8_t);
+    w->diff_alloc = w->wb[WB_DIFF].cap;
+  }
+  if ((rc = smb_block_fetch(w->ctx, brd, bc, w->ba_err, w->res_first, w->res, w->diff))) return gpu_fail(errmsgp, w, rc);
+  WTICK(6);
+
+  /* host: replay of alignRMAPCANDFull (rmap.c:820-926) on the alignments, then results.c as in the reference */
+  tres = wnow();
+  for (i = 0; i < n; i++) {
+    WREAD *rd = w->rd + i;
+    const smb_block_read *b = brd + i;
+    ResultSet *rsp = jobs[i].rsp;
+    SeqFastq *readp = jobs[i].readp;
+    memset(rd, 0, sizeof(*rd));
+    rd->qlen = w->read_len[jobs[i].read];
+    rd->errcode = b->errcode;
+    rd->reached_stats = b->reached_stats;
+    rd->do_align = b->do_align;
+    rd->nseg = b->nseg; rd->nseg_tot = b->nseg_tot; rd->nhit = b->nhit; rd->nhit_tot = b->nhit_tot;
+    rd->ncand = b->ncand; rd->nscored = b->nscored;
+    rd->max1scor = b->max1scor; rd->max2scor = b->max2scor;
+    rd->min_swatscor = b->min_swatscor; rd->scorlen_min = b->scorlen_min; rd->bandwidth_min = b->bandwidth_min;
+    if (jobs[i].blank) resultSetBlank(rsp);
+    if (rd->errcode == ERRCODE_SHORTSEQ) { /* too short to be hashed (rmap.c:1273-1275) */
+      if (donef && (errcode = (*donef)(user, i, ERRCODE_SHORTSEQ, rsp))) return errcode;
+      continue;
+    }
+    if (rd->errcode) ERRMSGNO(errmsgp, rd->errcode);
+    if (rd->reached_stats)
+      resultSetAlignmentStats(rsp, rd->nseg, rd->nseg_tot, max_depth, rd->nhit, rd->nhit_tot);
+    if (wave_debug())
+      fprintf(stderr, "DBG read %d ncand %u nscored %u max1 %d max2 %d min_swatscor %d scorlen_min %d bw_min %d nseg %d/%d nhit %u/%u\n",
+	      i, rd->ncand, rd->nscored, rd->max1scor, rd->max2scor, rd->min_swatscor, rd->scorlen_min, rd->bandwidth_min,
+	      rd->nseg, rd->nseg_tot, rd->nhit, rd->nhit_tot);
+    if (!rd->errcode && rd->do_align) {
+      int min_swatscor = rd->min_swatscor;
+      SWATSCOR swatscor_2ndmax = 0;
+      uint32_t c;
+      for (c = 0; c < b->nk3 && !rd->errcode; c++) {
+	const size_t t = (size_t) b->k3_first + c;
+	const smb_block_cand *cp = bc + t;
+	int minscorlen = rd->scorlen_min;
+	uint32_t pos, end;
+	if (rmapflg & RMAPFLG_BEST) {
+	  resultSetGetMaxSwat(rsp, &swatscor_2ndmax);
+	  if (swatscor_2ndmax > min_swatscor) min_swatscor = swatscor_2ndmax;
+	}
+	if (w->ba_err[t]) { rd->errcode = w->ba_err[t]; break; }
+	aliRsltSetReset(bufp->alirsltp);
+	/* aliSmiWatInBand (alignment.c:1569-1575) with the current threshold */
+	if (min_swatscor < 1 || matchscor <= 0) { rd->errcode = ERRCODE_ASSERT; break; }
+	if (minscorlen * matchscor < min_swatscor) minscorlen = min_swatscor / matchscor;
+	if (minscorlen < 5) { rd->errcode = ERRCODE_ASSERT; break; }
+	pos = w->res_first[t];
+	end = w->res_first[t + 1];
+	if ((errcode = prune_results(bufp->alirsltp, w->res, w->diff, &pos, end, 0, (int) cp->reflen - 1,
+				     min_swatscor, minscorlen, 1)))
+	  return errcode;
+	if (wave_debug()) {
+	  short k_, n_ = aliRsltSetGetSize(bufp->alirsltp);
+	  fprintf(stderr, "DBG  cand swscor %d rev %d rs %llu band %d %d minscore %d minscorlen %d raw %u kept %d:",
+		  cp->swscor, (int) cp->reverse, (unsigned long long) cp->rs, cp->band_l, cp->band_r, min_swatscor,
+		  minscorlen, w->res_first[t + 1] - w->res_first[t], (int) n_);
+	  for (k_ = 0; k_ < n_; k_++) {
+	    int sc_, a_, b_, c_, d_;
+	    aliRsltSetFetchData(bufp->alirsltp, k_, &sc_, &a_, &b_, &c_, &d_, NULL);
+	    fprintf(stderr, " (%d q%d-%d r%d-%d)", sc_, a_, b_, c_, d_);
+	  }
+	  fputc('\n', stderr);
+	}
+	errcode = resultSetAddFromAli(rsp, bufp->alirsltp, (SETSIZ_t) cp->rs, 0, rd->qlen, (SEQNUM_t) cp->sqidx,
+				      (char) (cp->reverse ? RMAPCANDFLG_REVERSE : 0));
+	if (errcode) { rd->errcode = errcode; break; }
+      }
+      { const double t_ = wnow(); w->wall_res[0] += t_ - tres; tres = t_; }
+      if (rd->errcode) ERRMSGNO(errmsgp, rd->errcode);
+      else {
+	/* (the read's profiles are only dereferenced for results without a sequence index, which the
+	 * sequence-by-sequence mode never produces: results.c:1715, :1742-1756) */
+	errcode = resultSetSortAndAssignSequence(rsp, bufp->sqbfp, 0, readp, w->prof, w->profRC, ssp, codecp);
+	if (errcode) { rd->errcode = errcode; ERRMSGNO(errmsgp, errcode); }
+      }
+    }
+    if (donef && (errcode = (*donef)(user, i, rd->errcode, rsp))) return errcode;
+    tres = wnow();
+  }
+  WTICK(7);
+  w->n_reads += (uint64_t) n;
+  return ERRCODE_SUCCESS;
+}
+
 /* waves 1b-3 for a list of jobs on the reads of the current seed batch */
 static int wave_pass(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, const WJOB *jobs, const smb_seed_info *info,
 		     int ktuple_maxhit, int min_swatscor_below_max_arg, short target_depth, short max_depth,
@@ -341,6 +528,9 @@ static int wave_pass(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, const WJOB 
   double tw = wnow(), tc = cnow(), tres;
 
   if (n < 1) return ERRCODE_SUCCESS;
+  if (!wave_host_cand())
+    return wave_pass_dev(errmsgp, rmp, w, n, jobs, info, ktuple_maxhit, min_swatscor_below_max_arg, target_depth, max_depth,
+			 rmapflg, scormtxp, htp, ssp, codecp, donef, user);
   WGROW(w->rd, w->n_alloc, n, WREAD);
   for (i = 0; i < n; i++) nreq_max += 2 * (size_t) (jobs[i].niv < 0 ? nseq : jobs[i].niv);
 

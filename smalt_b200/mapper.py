@@ -57,6 +57,18 @@ def load_map_library():
     return lib
 
 
+def _as_pointer(text):
+    """bytes / bytearray / memoryview / numpy uint8 array -> (void pointer, length, object to keep alive)"""
+    if isinstance(text, bytes):
+        return C.cast(C.c_char_p(text), C.c_void_p), len(text), text
+    mv = memoryview(text).cast("B")
+    if mv.readonly or not mv.contiguous:
+        data = bytes(mv)
+        return C.cast(C.c_char_p(data), C.c_void_p), len(data), data
+    arr = (C.c_char * len(mv)).from_buffer(mv)
+    return C.cast(arr, C.c_void_p), len(mv), (arr, mv)
+
+
 class Mapper:
     """`smalt map -n nthreads -O [options] index_prefix` held open in this process."""
 
@@ -73,11 +85,11 @@ class Mapper:
 
     def map_fastq(self, text):
         """text: bytes-like FASTQ/FASTA -> SAM records (bytes, no header) in input order."""
-        buf = (C.c_char * len(text)).from_buffer_copy(text) if not isinstance(text, (bytes, bytearray)) else text
+        p, nbytes, keep = _as_pointer(text)
         sam = C.c_void_p()
         n = C.c_size_t(0)
-        p = C.cast(C.c_char_p(bytes(buf)) if isinstance(buf, bytearray) else C.c_char_p(buf), C.c_void_p)
-        rc = self.lib.smbm_map_fastq(self._h, p, len(text), C.byref(sam), C.byref(n), C.byref(self.stats))
+        rc = self.lib.smbm_map_fastq(self._h, p, nbytes, C.byref(sam), C.byref(n), C.byref(self.stats))
+        del keep
         if rc:
             raise SmbError(rc, "smbm_map_fastq failed")
         return C.string_at(sam, n.value)
