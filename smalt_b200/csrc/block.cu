@@ -694,6 +694,7 @@ __global__ void __launch_bounds__(128) block_emit_k3_kernel(const BlockArgs a, c
     const smb_block_job jb = a.jobs[j];
     const DCand d = a.dc[ci];
     k = a.k3_first[j] + (unsigned long long)a.k3rank[ci];
+    if (a.k3rank[ci] == 0) a.rd[j].k3_first = (uint32_t)a.k3_first[j];
     smb_band_task t;
     k3_task_of(a, d, rd, a.seed.read_off[jb.seed_read], a.seed.read_len[jb.seed_read], t);
     a.bat[k] = t;
