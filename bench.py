@@ -1,28 +1,37 @@
 #!/usr/bin/env python
 """bench.py - headline benchmark of the B200-native SMALT hot path.
 
-Metric (BASELINE.json): mapped reads/s (and SW GCUPS) on config C2 - 5 Mb synthetic genome,
-1 M single-end 150 bp reads, smalt index -k 13 -s 6 - next to the reference's own CPU `smalt`
+Metric (BASELINE.json): mapped reads/s (and SW GCUPS) next to the reference's own CPU `smalt`
 timed on this box's host cores.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2|c1|c3|c4|c5] [--reads R]
   python bench.py --impl reference ...      # the reference CPU arm (oracle/_ref/smalt map)
 
-One "step" = one pass of the mapping path over one batch of R reads per GPU (default 1 M):
-FASTQ text in host memory -> SAM text in host memory through the in-process driver
-(include/smalt_b200_map.h: the reference's unmodified candidate selection / results / SAM
-writer around K1 seed lookup + hit lists, K2 SW score, K3 banded DP + backtrace on the GPU).
+Workloads (genome = uniform ACGT from numpy PCG64 seeded with the config number,
+reads from the reference's own misc/simread with the seeds fixed there):
+  c2 (default, the configuration the metric is quoted on): 5 Mb genome, 1 M single-end 150 bp reads per
+      GPU, 2 % error, smalt index -k 13 -s 6
+  c1  1 Mb, 10 k x 100 bp (the reference's CPU-runnable case)
+  c3  100 Mb (4 x 25 Mb), pairs of 2 x 150 bp, insert 400, `smalt sample` + `map -g`
+  c4  3.1 Gb (24 sequences), k = 20 s = 13, pairs of 2 x 150 bp
+  c5  100 Mb, reads of 5-10 kb with 12 % indel-dominated error
+c1/c3/c4/c5 are builder-run lines (profiles/), the driver runs c2.
 
-  e2e    reads/s of that call, wall clock (host buffers in, host buffers out; every H2D/D2H
-         copy and all host stages inside the timed region) - the headline;
-  value  reads/s with inputs resident in HBM: reads / sum of the device times of all kernels
-         of a step (CUDA events on the launching stream, measured in a pass with ONE host
-         worker so that no two streams overlap);
-  roofline / roofline_k2 / roofline_k1: per kernel, against the measured integer-issue peak
-         (DP kernels; no tensor/HBM bound applies) or the measured HBM bandwidth (seed lookup).
+One "step" = one pass of the mapping path over one batch of reads per GPU: FASTQ text in host memory ->
+SAM text in host memory through the in-process driver (include/smalt_b200_map.h).
 
-Multi-GPU: one process per GPU (torchrun), reads sharded by rank, index + reference
-replicated, no collective on the data path (weak scaling); host cores are split between ranks.
+  value = e2e  reads/s of that call, wall clock over exactly K steps between barriers (host buffers in,
+         host buffers out; every H2D/D2H copy and all host stages inside), max over ranks - the headline;
+  device_value  reads / sum of the device times of all kernels of a step (CUDA events on the launching
+         stream, a pass with ONE host worker so that no two streams overlap): explains the e2e figure;
+  roofline / roofline_k1 / _k2 / _k3  per kernel, against the measured integer-issue peak (DP kernels;
+         no tensor/HBM bound applies) or the measured HBM bandwidth (seed lookup);
+  parity  SAM of a prefix of THIS run's reads from a one-worker run of the product, compared byte for
+         byte with the reference's own `smalt map` on the same prefix (per rank when N > 1).
+
+Multi-GPU: one process per GPU (torchrun), reads sharded by rank, index + reference replicated, no
+collective on the data path (weak scaling); host cores are split between ranks; the per-rank SAM texts are
+merged in input order by offset writes into one shared file (smalt_b200/shard.py), inside the timed region.
 """
 import argparse
 import json
@@ -38,65 +47,178 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GENOME_LEN = 5_000_000
-READ_LEN = 150
-K, NSKIP = 13, 6
-ERR = 0.02
-# integer instructions per DP cell of the recurrences as restated for two 16-bit lanes per
-# register ("rooflines"): K2 6.5 ALU-pipe instructions per cell pair (LOP3, PRMT, 3 x VIADDMNMX,
-# 1.5 x VIMNMX3; the eighth, H - gap_init, is an IMAD on the FMA pipe); K3: ALU-pipe instructions per
-# iteration of the DP loop in the SASS (62, loop overhead included) / 4 cells (two packed cell pairs)
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+SMALT_REF = os.path.join(REF_DIR, "smalt")
+SIMREAD = os.path.join(REF_DIR, "simread")
+SMALT_B200 = os.path.join(ROOT, "smalt_b200", "bin", "smalt_b200")
+
+# seeds and simread arguments of SURVEY.md 8(d)
+CONFIGS = {
+    "c1": dict(name="C1", seqs=[1_000_000], gseed=1, k=13, s=6, qlen=100, units=10_000, err=1.0, insert=0, std=0,
+               simseed=42, paired=False),
+    "c2": dict(name="C2", seqs=[5_000_000], gseed=2, k=13, s=6, qlen=150, units=1_000_000, err=2.0, insert=0, std=0,
+               simseed=43, paired=False),
+    "c3": dict(name="C3", seqs=[25_000_000] * 4, gseed=3, k=13, s=6, qlen=150, units=1_000_000, err=2.0, insert=400,
+               std=0.1, simseed=44, paired=True),
+    "c4": dict(name="C4", seqs=[129_166_667] * 24, gseed=4, k=20, s=13, qlen=150, units=500_000, err=2.0, insert=400,
+               std=0.1, simseed=45, paired=True),
+    "c5": dict(name="C5", seqs=[25_000_000] * 4, gseed=3, k=13, s=6, qlen=0, units=512, err=12.0, insert=0, std=0,
+               simseed=46, paired=False, long_reads=(5000, 10000)),
+}
+# integer instructions per DP cell of the recurrences as restated for two 16-bit lanes per register
+# (DESIGN.md, "rooflines"): K2 6.5 ALU-pipe instructions per cell pair (LOP3, PRMT, 3 x VIADDMNMX, 1.5 x
+# VIMNMX3; the eighth, H - gap_init, is an IMAD on the FMA pipe).  K3: the ALGORITHMIC minimum of the
+# restricted recurrence on the ALU pipe per packed cell pair - h (VIADD), m = max(E, F) (VIMNMX), the
+# comparison h <= m as a mask (3), t (VIADDMNMX.RELU + LOP3), E', F' (2 x VIADDMNMX), H' (VIMNMX), the running
+# maximum key (VIMNMX), the direction code (4) = 16 per pair = 8 per cell; everything above that
+# (staging, backtrace, band masks, lanes outside the band) is overhead the fraction exposes.
 K2_OPS_PER_CELL = 3.25
-K3_OPS_PER_CELL = 15.5
+K3_OPS_PER_CELL = 8.0
 
 
-def make_genome(seed=2, n=GENOME_LEN):
-    return np.random.default_rng(seed).integers(0, 4, n).astype(np.uint8)
+# --------------------------------------------------------------------------------------------------
+# workloads
+# --------------------------------------------------------------------------------------------------
+def make_genome(cfg):
+    rng = np.random.default_rng(cfg["gseed"])
+    return [rng.integers(0, 4, n).astype(np.uint8) for n in cfg["seqs"]]
 
 
-def simulate_reads(genome, n, seed, qlen=READ_LEN, err=ERR):
-    """Seeded, vectorised read simulator: substitutions (80 % of errors) and short indels
-    (20 %), random strand.  -> reads[n, qlen] codes, pos[n], strand[n], span[n]"""
+def write_index(tmp, cfg, seqs, device=0, tag="idx"):
+    """.smi/.sma of the genome (byte-identical to `smalt index -k K -s S`, tests/test_indexer.py,
+    test_gpu_index_build.py).  Genomes beyond 20 Mb are indexed on the GPU (smb_index_build)."""
+    from smalt_b200 import indexer
+    pref = os.path.join(tmp, tag)
+    total = sum(len(s) for s in seqs)
+    if total > 20_000_000:
+        from smalt_b200.capi import Context
+        ctx = Context(device)
+        try:
+            ix = indexer.build_index_gpu(ctx, seqs, cfg["k"], cfg["s"])
+        finally:
+            ctx.close()
+    else:
+        ix = indexer.build_index(seqs, cfg["k"], cfg["s"])
+    indexer.write_smi(pref, ix)
+    indexer.write_sma(pref, ["chr%d" % (i + 1) for i in range(len(seqs))], seqs)
+    return pref, {"nwords": int(ix["nwords"]), "nkeys": int(ix["nkeys"]), "npos": int(ix["npos"]), "typ": int(ix["typ"])}
+
+
+def simread(pref, cfg, n, seed, out, name_prefix):
+    """reads of the reference's own simulator (misc/simread.c:738-755; drand48 seeded -> deterministic)
+    -> list of FASTQ files (two for pairs)"""
+    cmd = [SIMREAD, pref, str(cfg["qlen"]), str(n), "%g" % cfg["err"], "y", str(cfg["insert"]), "%g" % cfg["std"],
+           str(seed), name_prefix, out]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if r.returncode != 0:
+        raise RuntimeError("simread failed: " + r.stdout.decode()[-300:])
+    if cfg["paired"]:
+        return [out + "_1.fq", out + "_2.fq"]
+    return [out + ".fq"]
+
+
+def simulate_long_reads(seqs, n, seed, lo, hi, err):
+    """C5: misc/simread only makes fixed lengths and substitution-dominated errors, so the
+    long reads come from this seeded simulator: length uniform in [lo, hi], `err` % errors of which 80 %
+    are indels of 1-3 bases, random strand -> FASTQ text"""
     rng = np.random.default_rng(seed)
-    G = len(genome)
-    pos = rng.integers(0, G - qlen - 64, n)
-    ev = rng.random((n, qlen))
-    p_indel = err * 0.2
-    is_del = ev < p_indel / 2
-    is_ins = (ev >= p_indel / 2) & (ev < p_indel)
-    is_sub = (ev >= p_indel) & (ev < p_indel + err * 0.8)
-    step = np.ones((n, qlen), np.int64)
-    step[is_del] += rng.integers(1, 4, int(is_del.sum()))
-    step[is_ins] = 0
-    step[:, 0] = 0
-    idx = pos[:, None] + np.cumsum(step, axis=1)
-    reads = genome[idx]
-    rnd = rng.integers(0, 4, (n, qlen)).astype(np.uint8)
-    reads[is_ins] = rnd[is_ins]
-    reads[is_sub] = (reads[is_sub] + 1 + rnd[is_sub] % 3) & 3
-    span = idx[:, -1] - pos + 1
-    strand = rng.integers(0, 2, n).astype(np.uint8)
-    rc = strand == 1
-    reads[rc] = 3 - reads[rc][:, ::-1]
-    return np.ascontiguousarray(reads), pos, strand, span
-
-
-def fastq_text(reads, first=0):
-    """4-line FASTQ text of the code matrix reads[n, qlen] (names r<first+i>, quality 'I')."""
-    n, qlen = reads.shape
     let = np.frombuffer(b"ACGT", np.uint8)
-    names = np.char.add("@r", np.arange(first, first + n).astype(str)).astype("S")
-    w = names.dtype.itemsize
-    rec = np.full((n, w + 1 + qlen + 3 + qlen + 1), ord("\n"), np.uint8)
-    nm = np.frombuffer(names.tobytes(), np.uint8).reshape(n, w)
-    rec[:, :w] = nm                       # padded with NULs, removed below
-    rec[:, w + 1:w + 1 + qlen] = let[reads]
-    rec[:, w + 2 + qlen] = ord("+")
-    rec[:, w + 4 + qlen:w + 4 + 2 * qlen] = ord("I")
-    flat = rec.reshape(-1)
-    return flat[flat != 0].tobytes()
+    out = []
+    p = err / 100.0
+    for i in range(n):
+        L = int(rng.integers(lo, hi + 1))
+        s = seqs[int(rng.integers(0, len(seqs)))]
+        st = int(rng.integers(0, len(s) - 2 * L))
+        ev = rng.random(L)
+        is_del = ev < 0.4 * p
+        is_ins = (ev >= 0.4 * p) & (ev < 0.8 * p)
+        is_sub = (ev >= 0.8 * p) & (ev < p)
+        step = np.ones(L, np.int64)
+        step[is_del] += rng.integers(1, 4, int(is_del.sum()))
+        step[is_ins] = 0
+        step[0] = 0
+        idx = st + np.cumsum(step)
+        rd = s[np.minimum(idx, len(s) - 1)].copy()
+        rnd = rng.integers(0, 4, L).astype(np.uint8)
+        rd[is_ins] = rnd[is_ins]
+        rd[is_sub] = (rd[is_sub] + 1 + rnd[is_sub] % 3) & 3
+        if rng.integers(0, 2):
+            rd = 3 - rd[::-1]
+        out.append(b"@lr%d\n" % i + let[rd].tobytes() + b"\n+\n" + b"5" * L + b"\n")
+    return b"".join(out)
 
 
+def nth_record(text, n):
+    """byte offset behind the n-th 4-line record of a FASTQ text"""
+    p = 0
+    for _ in range(4 * n):
+        p = text.find(b"\n", p) + 1
+        if p == 0:
+            return len(text)
+    return p
+
+
+class Workload:
+    """index files + the reads of one rank (texts in memory and files on disk)"""
+
+    def __init__(self, tmp, cfg, units, rank=0, device=0):
+        self.cfg, self.units, self.tmp = cfg, units, tmp
+        t0 = time.time()
+        seqs = make_genome(cfg)
+        self.pref, self.ixinfo = write_index(tmp, cfg, seqs, device)
+        self.t_index = time.time() - t0
+        t0 = time.time()
+        seed = cfg["simseed"] + 1000 * rank       # rank r maps its own reads (weak scaling)
+        if cfg.get("long_reads"):
+            lo, hi = cfg["long_reads"]
+            text = simulate_long_reads(seqs, units, seed, lo, hi, cfg["err"])
+            f = os.path.join(tmp, "reads.fq")
+            with open(f, "wb") as fh:
+                fh.write(text)
+            self.files, self.texts = [f], [text]
+            self.generator = "own seeded simulator (lengths %d-%d, %g %% errors, 80 %% of them indels)" % (lo, hi, cfg["err"])
+        else:
+            if not os.path.exists(SIMREAD):
+                raise RuntimeError("oracle/_ref/simread not built")
+            self.files = simread(self.pref, cfg, units, seed, os.path.join(tmp, "reads"), "r%d" % rank)
+            self.texts = [open(f, "rb").read() for f in self.files]
+            self.generator = "misc/simread %d %d %g y %d %g %d" % (cfg["qlen"], units, cfg["err"], cfg["insert"],
+                                                                  cfg["std"], seed)
+        self.t_reads = time.time() - t0
+        self.nreads = units * (2 if cfg["paired"] else 1)
+        del seqs
+
+    def prefix_files(self, n, tag):
+        """the first n units as files"""
+        out = []
+        for i, t in enumerate(self.texts):
+            f = os.path.join(self.tmp, "%s_%d.fq" % (tag, i + 1))
+            with open(f, "wb") as fh:
+                fh.write(t[:nth_record(t, n)])
+            out.append(f)
+        return out
+
+
+def workload_config(cfg, units, world=1):
+    what = "%s: %s synthetic genome (uniform ACGT, numpy PCG64 seed %d)" % (
+        cfg["name"], " + ".join("%d" % n for n in sorted(set(cfg["seqs"]))) + (" x %d" % len(cfg["seqs"]) if len(cfg["seqs"]) > 1 else "") + " bp",
+        cfg["gseed"])
+    if cfg.get("long_reads"):
+        reads = "%d reads of %d-%d bp per GPU, %g%% indel-dominated error" % ((units,) + cfg["long_reads"] + (cfg["err"],))
+    elif cfg["paired"]:
+        reads = "%d pairs of 2 x %d bp per GPU, insert %d, %g%% error (misc/simread seed %d + 1000 x rank)" % (
+            units, cfg["qlen"], cfg["insert"], cfg["err"], cfg["simseed"])
+    else:
+        reads = "%d single-end %d bp reads per GPU, %g%% error (misc/simread seed %d + 1000 x rank)" % (
+            units, cfg["qlen"], cfg["err"], cfg["simseed"])
+    return {"workload": "%s, %s, smalt index -k %d -s %d" % (what, reads, cfg["k"], cfg["s"]),
+            "reads_per_gpu": units * (2 if cfg["paired"] else 1), "gpus": world,
+            "l2": "inputs larger than L2 (FASTQ text, task lists and outputs of a step are > 126 MB)"}
+
+
+# --------------------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -141,122 +263,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def simulate_at(genome, pos, rc, seed, qlen=READ_LEN, err=ERR):
-    """like simulate_reads, but at given positions / strands (rc[i]: read i is the reverse complement of
-    genome[pos[i] ...]) -> reads[n, qlen]"""
-    rng = np.random.default_rng(seed)
-    n = len(pos)
-    ev = rng.random((n, qlen))
-    p_indel = err * 0.2
-    is_del = ev < p_indel / 2
-    is_ins = (ev >= p_indel / 2) & (ev < p_indel)
-    is_sub = (ev >= p_indel) & (ev < p_indel + err * 0.8)
-    step = np.ones((n, qlen), np.int64)
-    step[is_del] += rng.integers(1, 4, int(is_del.sum()))
-    step[is_ins] = 0
-    step[:, 0] = 0
-    idx = pos[:, None] + np.cumsum(step, axis=1)
-    reads = genome[np.minimum(idx, len(genome) - 1)]
-    rnd = rng.integers(0, 4, (n, qlen)).astype(np.uint8)
-    reads[is_ins] = rnd[is_ins]
-    reads[is_sub] = (reads[is_sub] + 1 + rnd[is_sub] % 3) & 3
-    reads[rc] = 3 - reads[rc][:, ::-1]
-    return np.ascontiguousarray(reads)
-
-
-def paired_workload(tmp, npairs, nseq=4, seqlen=5_000_000, seed=3):
-    """C3 scaled down (BASELINE.json configs[2]: 100 Mb genome, 5 M pairs): nseq x seqlen bases, pairs of
-    2 x 150 bp from fragments of 400 +- 40 bases (forward/reverse), 2 % error, 2 % of the mates random"""
-    from smalt_b200 import indexer
-    rng = np.random.default_rng(seed)
-    seqs = [rng.integers(0, 4, seqlen).astype(np.uint8) for _ in range(nseq)]
-    genome = np.concatenate(seqs)
-    pref = os.path.join(tmp, "c3")
-    indexer.write_smi(pref, indexer.build_index(seqs, K, NSKIP))
-    indexer.write_sma(pref, ["chr%d" % (i + 1) for i in range(nseq)], seqs)
-    ins = np.clip(rng.normal(400, 40, npairs), 200, 600).astype(np.int64)
-    chrom = rng.integers(0, nseq, npairs)
-    start = chrom * seqlen + (rng.random(npairs) * (seqlen - 700)).astype(np.int64)
-    flip = rng.integers(0, 2, npairs).astype(bool)      # which mate is the forward one
-    r_fwd = simulate_at(genome, start, np.zeros(npairs, bool), seed + 1)
-    r_rev = simulate_at(genome, start + ins - READ_LEN - 8, np.ones(npairs, bool), seed + 2)
-    junk = rng.random(npairs) < 0.02
-    r_rev[junk] = rng.integers(0, 4, (int(junk.sum()), READ_LEN)).astype(np.uint8)
-    r1 = np.where(flip[:, None], r_rev, r_fwd)
-    r2 = np.where(flip[:, None], r_fwd, r_rev)
-    return pref, fastq_text(r1), fastq_text(r2)
-
-
-def run_paired(tmp, threads, cores, npairs, ref_pairs, steps, warmup):
-    """paired-end throughput through the in-process driver (smbm_map_fastq_pairs) + the reference's CPU
-    `smalt map` on a sample of the same pairs"""
-    from smalt_b200.mapper import Mapper
-    pref, t1, t2 = paired_workload(tmp, npairs)
-    opts = ["-i", "600", "-j", "200"]
-    m = Mapper(pref, threads, options=opts, paired=True)
-    for _ in range(warmup):
-        m.map_fastq_pairs(t1, t2, copy=False)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        nb = m.map_fastq_pairs(t1, t2, copy=False)
-    wall = (time.perf_counter() - t0) / steps
-    st = m.stats.as_dict()
-    sam = m.map_fastq_pairs(t1[:_nth_record(t1, 20000)], t2[:_nth_record(t2, 20000)])
-    m.close()
-    proper = sum(1 for ln in sam.split(b"\n") if ln and ln[:1] != b"@" and int(ln.split(b"\t", 2)[1]) & 2)
-    out = {"workload": "C3 scaled to 4 x 5 Mb: %d pairs of 2 x %d bp per step, fragments 400 +- 40, %.0f%% error, 2%% random "
-                       "mates, smalt index -k %d -s %d, map -i 600 -j 200" % (npairs, READ_LEN, ERR * 100, K, NSKIP),
-           "e2e": {"value": 2 * npairs / wall, "unit": "reads/s", "ms_per_step": 1e3 * wall, "sam_bytes_per_step": int(nb)},
-           "kernel_ms": {"k1": st["k1_ms"], "k2": st["k2_ms"], "k3": st["k3_ms"]},
-           "proper_pair_fraction_sample": proper / 40000.0, "host_workers": threads}
-    smalt = os.path.join(ROOT, "oracle", "_ref", "smalt")
-    if os.path.exists(smalt):
-        f1, f2 = os.path.join(tmp, "p1.fq"), os.path.join(tmp, "p2.fq")
-        with open(f1, "wb") as f:
-            f.write(t1[:_nth_record(t1, ref_pairs)])
-        with open(f2, "wb") as f:
-            f.write(t2[:_nth_record(t2, ref_pairs)])
-        t0 = time.time()
-        r = subprocess.run([smalt, "map", "-n", str(cores), "-O"] + opts + ["-o", os.path.join(tmp, "pref.sam"), pref, f1, f2],
-                           stdout=subprocess.PIPE, stderr=subprocess.PIPE)
-        dt = time.time() - t0
-        out["cpu_baseline"] = ({"value": 2 * ref_pairs / dt, "unit": "reads/s", "cores": cores, "kind": "reference",
-                                "sample": "first %d pairs, whole `oracle/_ref/smalt map -n %d -O -i 600 -j 200` program "
-                                          "(%.1f s)" % (ref_pairs, cores, dt)}
-                               if r.returncode == 0 else {"value": None, "sample": "unavailable: reference failed"})
-    return out
-
-
-def _nth_record(text, n):
-    """byte offset behind the n-th 4-line record of a FASTQ text"""
-    p = 0
-    for _ in range(4 * n):
-        p = text.find(b"\n", p) + 1
-        if p == 0:
-            return len(text)
-    return p
-
-
-def write_index_files(tmp, genome):
-    """index files (own builder, byte-identical to `smalt index -k 13 -s 6`)"""
-    from smalt_b200 import indexer
-    pref = os.path.join(tmp, "c2")
-    ix = indexer.build_index([genome], K, NSKIP)
-    indexer.write_smi(pref, ix)
-    indexer.write_sma(pref, ["chr1"], [genome])
-    return pref, ix
-
-
-def write_workload_files(tmp, genome, reads):
-    pref, ix = write_index_files(tmp, genome)
-    fq = os.path.join(tmp, "reads.fq")
-    with open(fq, "wb") as f:
-        f.write(fastq_text(reads))
-    return pref, fq, ix
-
-
-def count_mapped(sam_path_or_bytes):
-    data = sam_path_or_bytes if isinstance(sam_path_or_bytes, bytes) else open(sam_path_or_bytes, "rb").read()
+def count_mapped(data):
     mapped = total = 0
     for ln in data.split(b"\n"):
         if not ln or ln[:1] == b"@":
@@ -267,13 +274,12 @@ def count_mapped(sam_path_or_bytes):
     return mapped, total
 
 
-def run_cli(exe, threads, pref, fq, out, env=None):
-    cmd = [exe, "map", "-n", str(threads), "-O", "-o", out, pref, fq]
+def run_program(exe, args, env=None):
     t0 = time.time()
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    r = subprocess.run([exe] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
     dt = time.time() - t0
     if r.returncode != 0:
-        return None, "%s failed: %s" % (os.path.basename(exe), r.stderr.decode()[-200:])
+        return None, "%s failed: %s" % (os.path.basename(exe), r.stderr.decode()[-300:])
     return dt, None
 
 
@@ -298,66 +304,140 @@ def dist_setup():
     return rank, world, local, dist
 
 
-def workload_config(nreads, world=1):
-    return {"workload": "C2: 5 Mb synthetic genome (uniform ACGT, seed 2), %d single-end %d bp reads per GPU, "
-                        "%.0f%% error, smalt index -k %d -s %d" % (nreads, READ_LEN, ERR * 100, K, NSKIP),
-            "reads_per_gpu": nreads, "gpus": world,
-            "l2": "inputs larger than L2 (FASTQ text, task lists and outputs of a step are > 126 MB)"}
+def sam_records(path):
+    with open(path, "rb") as f:
+        return [ln for ln in f.read().split(b"\n") if ln and ln[:1] != b"@"]
 
 
+def map_options(cfg, hist=None):
+    if not cfg["paired"]:
+        return []
+    return ["-g", hist] if hist else ["-i", "600", "-j", "200"]
+
+
+def parity_check(wl, n, device, hist):
+    """SAM of the first n units: one-worker `smalt_b200 map -r 7` (this product, this GPU) against the
+    reference's own `smalt map -r 7` (fixed seed: by default the reference draws among equally good
+    placements with a calendar-seeded drand48) - every record, byte for byte"""
+    if not os.path.exists(SMALT_REF) or not os.path.exists(SMALT_B200):
+        return {"checked": False, "why": "oracle/_ref/smalt or smalt_b200/bin/smalt_b200 not built"}
+    n = min(n, wl.units)
+    files = wl.prefix_files(n, "par")
+    opts = ["map", "-r", "7"] + map_options(wl.cfg, hist)
+    ref_out, own_out = os.path.join(wl.tmp, "par_ref.sam"), os.path.join(wl.tmp, "par_own.sam")
+    dt_r, err = run_program(SMALT_REF, opts + ["-o", ref_out, wl.pref] + files)
+    if dt_r is None:
+        return {"checked": False, "why": err}
+    env = dict(os.environ, SMALT_B200_DEVICE=str(device))
+    dt_o, err = run_program(SMALT_B200, opts + ["-o", own_out, wl.pref] + files, env=env)
+    if dt_o is None:
+        return {"checked": False, "why": err}
+    a, b = sam_records(ref_out), sam_records(own_out)
+    ndiff = sum(1 for x, y in zip(a, b) if x != y) + abs(len(a) - len(b))
+    return {"checked": True, "units": n, "sam_records": len(a), "differing_records": ndiff, "identical": ndiff == 0,
+            "how": "first %d %s of this rank's input, `map -r 7` one worker, all records compared with the "
+                   "reference's own program" % (n, "pairs" if wl.cfg["paired"] else "reads")}
+
+
+def reference_rate(wl, n, threads, hist, tag="ref"):
+    """whole `oracle/_ref/smalt map -n threads -O` program on the first n units -> (reads/s, seconds)"""
+    files = wl.prefix_files(n, tag) if n < wl.units else wl.files
+    out = os.path.join(wl.tmp, tag + ".sam")
+    dt, err = run_program(SMALT_REF, ["map", "-n", str(threads), "-O"] + map_options(wl.cfg, hist) + ["-o", out, wl.pref] + files)
+    if dt is None:
+        return None, err, None
+    return n * (2 if wl.cfg["paired"] else 1) / dt, dt, out
+
+
+def sample_histogram(wl, exe, threads, device=None, skip=100):
+    """insert-size estimation: `smalt sample` on every skip-th pair -> histogram file for `map -g`
+    (smalt.c:838-878, :1288, :1397; insert.c)"""
+    out = os.path.join(wl.tmp, "insert_%s.hist" % os.path.basename(exe))
+    env = dict(os.environ, SMALT_B200_DEVICE=str(device)) if device is not None else None
+    dt, err = run_program(exe, ["sample", "-u", str(skip), "-n", str(threads), "-o", out, wl.pref] + wl.files, env=env)
+    return (out, dt, None) if dt is not None else (None, None, err)
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm
+# --------------------------------------------------------------------------------------------------
 def run_reference_arm(args):
-    """the reference's own CPU `smalt map` on this box's host cores (rank 0 only)"""
+    """the reference's own CPU `smalt map` on this box's host cores (rank 0 only), same workload and
+    read count as the product's arm"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    smalt = os.path.join(ROOT, "oracle", "_ref", "smalt")
-    if not os.path.exists(smalt):
+    if not os.path.exists(SMALT_REF):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/smalt not built"}))
         return
-    genome = make_genome()
-    nsample = args.ref_sample
-    reads, _, _, _ = simulate_reads(genome, nsample, seed=43)
-    threads = host_threads()
-    rates, mapped = [], 0
+    cfg = CONFIGS[args.config]
+    units = args.reads or cfg["units"]
+    nsample = min(args.ref_sample or units, units)
+    cores = host_threads()
     with tempfile.TemporaryDirectory() as tmp:
-        pref, fq, _ = write_workload_files(tmp, genome, reads)
-        out = os.path.join(tmp, "out.sam")
-        for it in range(args.warmup + args.steps):
-            dt, err = run_cli(smalt, threads, pref, fq, out)
-            if dt is None:
+        try:
+            wl = Workload(tmp, cfg, units)
+        except Exception as exc:
+            print(json.dumps({"impl": "reference", "unavailable": repr(exc)[:200]}))
+            return
+        hist = None
+        if cfg["paired"]:
+            hist, _, err = sample_histogram(wl, SMALT_REF, cores)
+            if hist is None:
                 print(json.dumps({"impl": "reference", "unavailable": err}))
                 return
-            if it >= args.warmup:
-                rates.append(nsample / dt)
-        mapped, _ = count_mapped(out)
+        # the reference does not scale past ~16 PROC threads (VERDICT r1: slower at -n 32 than at -n 16):
+        # one untimed run per candidate thread count, the timed steps use the faster
+        cands = sorted({cores, min(cores, 16)})
+        trial = {}
+        for t in cands:
+            v, dt, _ = reference_rate(wl, nsample, t, hist)
+            if v is None:
+                print(json.dumps({"impl": "reference", "unavailable": dt}))
+                return
+            trial[t] = v
+        threads = max(trial, key=trial.get)
+        rates, out = [], None
+        for it in range(max(0, args.warmup - len(cands)) + args.steps):
+            v, dt, out = reference_rate(wl, nsample, threads, hist)
+            if it >= max(0, args.warmup - len(cands)):
+                rates.append(v)
+        mapped, total = count_mapped(open(out, "rb").read())
     v = float(np.mean(rates))
-    sample = ("first %d reads of the C2 read set per step; whole `smalt map -n %d -O` program (index load, FASTQ "
-              "parsing, SAM output)" % (nsample, threads))
+    nreads = nsample * (2 if cfg["paired"] else 1)
+    sample = ("%s %d %s of the workload per step; whole `smalt map -n %d -O` program (index load, FASTQ parsing, "
+              "SAM output); reads/s at the thread counts tried: %s"
+              % ("all" if nsample == units else "first", nsample, "pairs" if cfg["paired"] else "reads", threads,
+                 ", ".join("-n %d: %.0f" % (t, r) for t, r in sorted(trial.items()))))
     print(json.dumps({
         "impl": "reference", "metric": "mapped reads/sec", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * nsample / v, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * nreads / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/i16 (SSE2)", "data": "synthetic",
-        "config": workload_config(nsample),
+        "config": workload_config(cfg, units, args.gpus),
         "cpu_baseline": {"value": v, "unit": "reads/s", "cores": threads, "kind": "reference", "sample": sample,
-                         "mapped_fraction": mapped / nsample},
+                         "host_cores": cores, "mapped_fraction": mapped / max(total, 1)},
         "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+# --------------------------------------------------------------------------------------------------
+# the product's arm
+# --------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--reads", type=int, default=0, help="reads (pairs) per GPU per step (0: the config's size)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ref-sample", type=int, default=250_000)
-    ap.add_argument("--cpu-sample", type=int, default=250_000)
+    ap.add_argument("--ref-sample", type=int, default=0, help="reference arm: units per step (0: all, same job)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="cpu_baseline: units of the sample (0: config default)")
     ap.add_argument("--threads", type=int, default=0, help="host worker threads per GPU (0: 2 x cores / GPUs)")
     ap.add_argument("--device-block", type=int, default=32000, help="reads per launch of the device-time pass")
+    ap.add_argument("--parity", type=int, default=20000, help="units of the SAM parity check (0: none)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cli", action="store_true")
-    ap.add_argument("--no-paired", action="store_true")
-    ap.add_argument("--pairs", type=int, default=250_000, help="pairs per step of the paired-end section")
+    ap.add_argument("--no-device-pass", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -366,170 +446,211 @@ def main():
     rank, world, local, dist = dist_setup()
     from smalt_b200.capi import Context
     from smalt_b200.mapper import Mapper
+    from smalt_b200 import shard
 
-    n = args.reads
+    cfg = CONFIGS[args.config]
+    units = args.reads or cfg["units"]
     cores = host_threads()
     threads = args.threads or max(1, int(round(2.0 * cores / world)))
-    genome = make_genome()
-    # reads are sharded by rank: rank r maps reads [r*n, (r+1)*n) of the job
-    reads, pos, strand, span = simulate_reads(genome, n, seed=43 + 1000 * rank)
-    text = fastq_text(reads, first=rank * n)
     tmpdir = tempfile.TemporaryDirectory()
     tmp = tmpdir.name
-    pref, ix = write_index_files(tmp, genome)
+    wl = Workload(tmp, cfg, units, rank, local)
+    nreads = wl.nreads
+    paired = cfg["paired"]
 
     def barrier():
         if dist is not None:
             dist.barrier()
 
-    # ---- pass 1: device-resident kernel times, ONE host worker (no overlapping streams) ----
-    # (blocks of DEVICE_BLOCK reads per launch: with one stream nothing else fills the tail of a launch,
-    # which the e2e pass does with the launches of its other workers' streams)
-    os.environ["SMALT_B200_BLOCK"] = str(args.device_block)
-    m = Mapper(pref, 1)
-    m.map_fastq_nocopy(fastq_text(reads[:max(1, n // 8)]))   # warm-up of this mapper
-    m.map_fastq_nocopy(text)
-    s1 = m.stats.as_dict()
-    m.close()
-    del os.environ["SMALT_B200_BLOCK"]
-    dev_ms = s1["k1_ms"] + s1["k2_ms"] + s1["k3_ms"]
+    # insert-size estimation (paired configs): `sample` on this rank's pairs; the histograms of the ranks
+    # (every 100th pair; with several ranks the sampled pairs of all ranks are merged on the host and sampled
+    # once - the only cross-read state of the reference, smalt.c:838-878)
+    hist, t_sample = None, None
+    if paired:
+        t0 = time.time()
+        if dist is None:
+            hist, _, err = sample_histogram(wl, SMALT_B200, max(1, cores // world), device=local)
+            if hist is None:
+                raise RuntimeError("sample failed: " + err)
+        else:
+            hist = shard.sample_insert_sizes(dist, SMALT_B200, wl.pref, wl.texts[0], wl.texts[1], 100,
+                                             "/dev/shm/smalt_b200_bench_%s.hist" % os.environ.get("MASTER_PORT", "0"), cores,
+                                             env=dict(os.environ, SMALT_B200_DEVICE=str(local)))
+        t_sample = time.time() - t0
+    opts = map_options(cfg, hist)
 
-    # ---- pass 2: e2e through the in-process driver, all host workers ----
-    m = Mapper(pref, threads)
+    def run_step(m, copy=False):
+        if paired:
+            return m.map_fastq_pairs(wl.texts[0], wl.texts[1], copy=copy)
+        return m.map_fastq(wl.texts[0]) if copy else m.map_fastq_nocopy(wl.texts[0])
+
+    # ---- pass 1: device-resident kernel times, ONE host worker (no overlapping streams), large launches ----
+    s1 = None
+    if not args.no_device_pass:
+        os.environ["SMALT_B200_BLOCK"] = str(args.device_block)
+        m = Mapper(wl.pref, 1, options=opts, paired=paired)
+        run_step(m)   # warm-up of this mapper (buffers, kernels)
+        run_step(m)
+        s1 = m.stats.as_dict()
+        m.close()
+        del os.environ["SMALT_B200_BLOCK"]
+
+    # ---- pass 2: e2e through the in-process driver, all host workers; per-rank SAM merged in input order ----
+    m = Mapper(wl.pref, threads, options=opts, paired=paired)
+    merged = os.path.join(os.environ.get("SMALT_B200_MERGE_DIR", "/dev/shm"), "smalt_b200_bench_%s.sam" % os.environ.get("MASTER_PORT", "0"))
     for _ in range(args.warmup):
-        m.map_fastq_nocopy(text)
+        run_step(m)
     c0 = m.stats.as_dict()
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
     t0 = time.perf_counter()
-    sam_bytes = 0
+    sam_bytes = merged_bytes = 0
     for _ in range(args.steps):
-        sam_bytes = m.map_fastq_nocopy(text)
+        if dist is None:
+            sam_bytes = run_step(m)
+        else:
+            sam = run_step(m, copy=True)
+            sam_bytes = len(sam)
+            merged_bytes = shard.merge_to_file(dist, sam, merged)   # offset writes, ends with a barrier
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     c1 = m.stats.as_dict()
-    sam = m.map_fastq(fastq_text(reads[:max(1, n // 50)]))
-    mapped, total = count_mapped(sam)
+    sam = run_step(m, copy=True) if units <= 50_000 else None
     m.close()
+    if dist is not None and rank == 0 and os.path.exists(merged):
+        os.unlink(merged)
+    mapped_fraction = None
+    if sam is not None:
+        mp, tot = count_mapped(sam)
+        mapped_fraction = mp / max(tot, 1)
+
+    # ---- parity: SAM of a prefix against the reference, on every rank ----
+    parity = parity_check(wl, args.parity, local, hist) if args.parity else {"checked": False, "why": "--parity 0"}
 
     wall_ms = 1e3 * wall / args.steps
+    dev_ms = (s1["k1_ms"] + s1["k2_ms"] + s1["k3_ms"]) if s1 else 0.0
+    par_ok = 1.0 if parity.get("identical") else 0.0
+    par_checked = 1.0 if parity.get("checked") else 0.0
     if dist is not None:
         import torch
-        t = torch.tensor([dev_ms, wall_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([dev_ms, wall_ms, -par_ok, -par_checked], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, wall_ms = float(t[0]), float(t[1])
+        parity["all_ranks_identical"] = bool(-float(t[2]) > 0.5)
+        parity["all_ranks_checked"] = bool(-float(t[3]) > 0.5)
     if rank != 0:
         return
 
-    value = world * n / (dev_ms * 1e-3)
-    e2e = world * n / (wall_ms * 1e-3)
+    e2e = world * nreads / (wall_ms * 1e-3)
     launches = (c1["gpu_launches"] - c0["gpu_launches"]) // args.steps
     h2d = (c1["h2d_bytes"] - c0["h2d_bytes"]) // args.steps
     d2h = (c1["d2h_bytes"] - c0["d2h_bytes"]) // args.steps
-    k2_gcups = s1["k2_cells"] / (s1["k2_ms"] * 1e-3) / 1e9
-    k3_gcups = s1["k3_cells"] / (s1["k3_ms"] * 1e-3) / 1e9
-    ctx = Context(local)
-    # giga thread-instructions/s: VIADDMNMX, VIMNMX3, IADD+IMNMX pairs (ops), VIADDMNMX.S16x2, VIMNMX3.S16x2
-    peaks = ctx.int_peak()
-    ctx.close()
-    k2_peak = peaks[3] / K2_OPS_PER_CELL
-    k3_peak = peaks[3] / K3_OPS_PER_CELL
-    try:
-        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-        peak_src = "MEASURED_PEAKS.json"
-    except Exception:
-        hbm_peak, peak_src = 6650.0, "fallback of B200_PROFILING.md"
-    # K1 algorithmic bytes: per lookup 8 (idx pair) + 4*ceil(log2(bucket+1)) (wordidx probes) +
-    # 8 (posidx pair); per hit 4 (pos) + 8 (sqdat) + 16 (sort)
-    nlook = 2 * n * (READ_LEN - K + 1)
-    bucket = max(1.0, ix["nwords"] / ix["nkeys"])
-    k1_bytes = nlook * (8 + 4 * np.ceil(np.log2(bucket + 1)) + 8)
-    k1_gbs = k1_bytes / (s1["k1_ms"] * 1e-3) / 1e9
-    kernel_ms = {"k1_seed_hits": s1["k1_ms"], "k2_sw_score": s1["k2_ms"], "k3_band_align": s1["k3_ms"]}
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch (one block of 32000 reads) from the
-    # ncu --set full captures under profiles/ (r1c_ncu_full_k1/k2/k3_raw_selected.csv) - K2 and K3 are
-    # bound by the integer ALU pipe (sm__pipe_alu_cycles_active 93 % / 72 %), not by memory
-    roof_k3 = {"kernel": "band_pack_kernel (K3: banded DP + backtrace, 4 tasks per warp)", "bound": "alu",
-               "achieved": k3_gcups, "peak": k3_peak, "unit": "GCUPS", "frac": k3_gcups / k3_peak if k3_peak else None,
-               "traffic": 13.1e6,
-               "note": "integer-issue bound (no tensor/HBM bound applies to this DP): peak = measured VIADDMNMX.S16x2 "
-                       "issue rate %.0f G thread-instr/s / %.1f ALU-pipe instructions per cell (62 per DP-loop iteration "
-                       "of two packed cell pairs in the SASS); cells include staging and backtrace time" % (peaks[3], K3_OPS_PER_CELL)}
-    roof_k2 = {"kernel": "sw_score2_kernel (K2: SW score, 2 tasks per warp)", "bound": "alu", "achieved": k2_gcups,
-               "peak": k2_peak, "unit": "GCUPS", "frac": k2_gcups / k2_peak if k2_peak else None, "traffic": 11.8e6,
-               "note": "DPX issue bound: peak = measured VIADDMNMX.S16x2 issue rate %.0f G thread-instr/s / %.1f "
-                       "ALU-pipe instructions per cell (6.5 per packed cell pair)" % (peaks[3], K2_OPS_PER_CELL)}
-    roof_k1 = {"kernel": "seed_kernel + hits_kernel (K1)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak,
-               "unit": "GB/s", "frac": k1_gbs / hbm_peak, "traffic": 37.3e6, "peak_source": peak_src,
-               "note": "dependent 4-byte index probes (latency bound); the 5 Mb index (11 MB) is L2 resident"}
-    dominant = max(kernel_ms, key=kernel_ms.get)
     line = {
-        "metric": "mapped reads/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+        "metric": "mapped reads/sec", "value": e2e, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": wall_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "i16x2 DPX (K2, K3), u32/u64 (K1)", "data": "synthetic",
-        "config": dict(workload_config(n, world), host_workers_per_gpu=threads, host_cores=cores),
-        "timing": "value: reads / sum of CUDA-event kernel times of a step (one host worker = one stream, "
-                  "inputs resident, %d reads per launch); " % args.device_block +
-                  "e2e: wall clock of smbm_map_fastq (FASTQ text in host memory -> SAM text in host memory), "
-                  "max over ranks",
-        "device_ms_per_step": dev_ms, "kernel_ms": kernel_ms, "sw_gcups": k2_gcups, "band_gcups": k3_gcups,
-        "tasks_per_step": {"k2_tasks": s1["k2_tasks"], "k2_cells": s1["k2_cells"], "k3_tasks": s1["k3_tasks"],
-                           "k3_cells": s1["k3_cells"]},
+        "config": workload_config(cfg, units, world),
+        "run": {"host_workers_per_gpu": threads, "host_cores": cores, "reads_generator": wl.generator,
+                "index_s": wl.t_index, "reads_s": wl.t_reads, "index": wl.ixinfo},
+        "timing": "value = e2e: reads of all ranks / wall clock of K calls of smbm_map_fastq%s (FASTQ text in host "
+                  "memory -> SAM text in host memory%s), barriers on both sides, max over ranks; device_value: reads "
+                  "/ sum of CUDA-event kernel times of a step (one host worker = one stream, inputs resident, %d reads "
+                  "per launch)" % ("_pairs" if paired else "", ", per-rank SAM merged into one file in input order" if world > 1 else "",
+                                   args.device_block),
         "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": wall_ms, "sam_bytes_per_step": int(sam_bytes),
+                "ms_per_step": wall_ms, "sam_bytes_per_step": int(sam_bytes), "merged_sam_bytes_per_step": int(merged_bytes),
                 "host_stage_wall_s": c1["host_stage_s"], "host_stage_cpu_s": c1["host_cpu_s"]},
-        "gpu_launches": int(launches), "clocks": clocks,
-        "int_peaks_ginstr": {"viaddmnmx": peaks[0], "vimnmx3": peaks[1], "iadd_imnmx_ops": peaks[2],
-                             "viaddmnmx_s16x2": peaks[3], "vimnmx3_s16x2": peaks[4]},
-        "roofline": {"k3_band_align": roof_k3, "k2_sw_score": roof_k2, "k1_seed_hits": roof_k1}[dominant],
-        "roofline_k2": roof_k2, "roofline_k3": roof_k3, "roofline_k1": roof_k1,
-        "mapped_fraction": mapped / max(total, 1),
+        "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
     }
+    if mapped_fraction is not None:
+        line["mapped_fraction"] = mapped_fraction
+    if t_sample is not None:
+        line["sample_s"] = t_sample
+    if s1:
+        ctx = Context(local)
+        # giga thread-instructions/s: VIADDMNMX, VIMNMX3, IADD+IMNMX pairs (ops), VIADDMNMX.S16x2, VIMNMX3.S16x2
+        peaks = ctx.int_peak()
+        ctx.close()
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            peak_src = "MEASURED_PEAKS.json"
+        except Exception:
+            hbm_peak, peak_src = 6650.0, "fallback of B200_PROFILING.md"
+        k2_gcups = s1["k2_cells"] / (s1["k2_ms"] * 1e-3) / 1e9 if s1["k2_ms"] else 0.0
+        k3_gcups = s1["k3_cells"] / (s1["k3_ms"] * 1e-3) / 1e9 if s1["k3_ms"] else 0.0
+        k2_peak, k3_peak = peaks[3] / K2_OPS_PER_CELL, peaks[3] / K3_OPS_PER_CELL
+        # K1 algorithmic bytes: per lookup 8 (idx pair) + 4*ceil(log2(bucket+1)) (wordidx probes) + 8
+        # (posidx pair); lookups = 2 strands x (qlen - k + 1) per read
+        qlen_mean = (sum(len(t) for t in wl.texts) / max(1, nreads) - 8) / 2 if cfg.get("long_reads") else cfg["qlen"]
+        nlook = 2 * nreads * max(1.0, qlen_mean - cfg["k"] + 1)
+        bucket = max(1.0, wl.ixinfo["nwords"] / max(1, wl.ixinfo["nkeys"])) if wl.ixinfo["typ"] else 1.0
+        probes = float(np.ceil(np.log2(bucket + 1))) if wl.ixinfo["typ"] else 0.0
+        k1_bytes = nlook * (8 + 4 * probes + 8)
+        k1_gbs = k1_bytes / (s1["k1_ms"] * 1e-3) / 1e9 if s1["k1_ms"] else 0.0
+        kernel_ms = {"k1_seed_hits_candidates": s1["k1_ms"], "k2_sw_score": s1["k2_ms"], "k3_band_align": s1["k3_ms"]}
+        roof_k3 = {"kernel": "K3 banded DP + backtrace (band_pack_kernel for short reads)", "bound": "alu", "achieved": k3_gcups,
+                   "peak": k3_peak, "unit": "GCUPS", "frac": k3_gcups / k3_peak if k3_peak else None, "traffic": 13.1e6,
+                   "note": "integer-issue bound (no tensor/HBM bound applies to this DP): peak = measured VIADDMNMX.S16x2 issue "
+                           "rate %.0f G thread-instr/s / %.1f ALU-pipe instructions per cell, the algorithmic minimum of the "
+                           "restricted recurrence with directions (16 per packed cell pair, bench.py K3_OPS_PER_CELL); staging, "
+                           "backtrace and lanes outside the band count against the fraction" % (peaks[3], K3_OPS_PER_CELL)}
+        roof_k2 = {"kernel": "K2 SW score (sw_score2_kernel, 2 tasks per 16 lanes)", "bound": "alu", "achieved": k2_gcups,
+                   "peak": k2_peak, "unit": "GCUPS", "frac": k2_gcups / k2_peak if k2_peak else None, "traffic": 11.8e6,
+                   "note": "DPX issue bound: peak = measured VIADDMNMX.S16x2 issue rate %.0f G thread-instr/s / %.2f "
+                           "ALU-pipe instructions per cell (6.5 per packed cell pair)" % (peaks[3], K2_OPS_PER_CELL)}
+        roof_k1 = {"kernel": "K1 seed tables + hit lists + candidate selection", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak,
+                   "unit": "GB/s", "frac": k1_gbs / hbm_peak, "traffic": 37.3e6, "peak_source": peak_src,
+                   "note": "algorithmic bytes of the index probes only (%.0f B per lookup, %.1f wordidx probes); dependent "
+                           "4-byte loads, latency bound; the time includes hit lists and candidate selection" % (8 + 4 * probes + 8, probes)}
+        dominant = max(kernel_ms, key=kernel_ms.get)
+        line.update({
+            "device_value": world * nreads / (dev_ms * 1e-3) if dev_ms else None, "device_ms_per_step": dev_ms,
+            "kernel_ms": kernel_ms, "sw_gcups": k2_gcups, "band_gcups": k3_gcups,
+            "tasks_per_step": {"k2_tasks": s1["k2_tasks"], "k2_cells": s1["k2_cells"], "k3_tasks": s1["k3_tasks"],
+                               "k3_cells": s1["k3_cells"]},
+            "int_peaks_ginstr": {"viaddmnmx": peaks[0], "vimnmx3": peaks[1], "iadd_imnmx_ops": peaks[2],
+                                 "viaddmnmx_s16x2": peaks[3], "vimnmx3_s16x2": peaks[4]},
+            "roofline": {"k3_band_align": roof_k3, "k2_sw_score": roof_k2, "k1_seed_hits_candidates": roof_k1}[dominant],
+            "roofline_k2": roof_k2, "roofline_k3": roof_k3, "roofline_k1": roof_k1})
     if world == 1 and not args.no_cli:
-        # the same job as a whole program, like the reference arm runs it (process start, CUDA
-        # start-up, index load, file I/O included)
-        fq = os.path.join(tmp, "reads.fq")
-        with open(fq, "wb") as f:
-            f.write(text)
-        exe = os.path.join(ROOT, "smalt_b200", "bin", "smalt_b200")
-        # (the driver is still tearing down the contexts of the passes above when this process's mappers
-        # are closed: a program started right then waits seconds in CUDA start-up; two runs, the faster)
-        runs = []
+        # the same job as a whole program, like the reference arm runs it (process start, CUDA start-up, index
+        # load, file I/O included); two runs, the faster (a program started while the driver tears down the
+        # contexts of the passes above waits seconds in CUDA start-up)
+        runs, err = [], None
         for _ in range(2):
             time.sleep(2.0)
-            dt, err = run_cli(exe, cores, pref, fq, os.path.join(tmp, "cli.sam"))
+            dt, err = run_program(SMALT_B200, ["map", "-n", str(cores), "-O"] + opts + ["-o", os.path.join(tmp, "cli.sam"), wl.pref] + wl.files)
             if not dt:
                 break
             runs.append(dt)
         dt = min(runs) if runs else None
-        line["e2e_cli"] = ({"value": n / dt, "unit": "reads/s", "seconds": dt, "runs_seconds": runs,
-                            "what": "whole `smalt_b200 map -n %d -O` program on the same %d reads" % (cores, n)}
+        line["e2e_cli"] = ({"value": nreads / dt, "unit": "reads/s", "seconds": dt, "runs_seconds": runs,
+                            "what": "whole `smalt_b200 map -n %d -O` program on the same reads" % cores}
                            if dt else {"value": None, "unavailable": err})
     if world == 1 and not args.no_cpu_baseline:
-        ns = min(args.cpu_sample, n)
-        smalt = os.path.join(ROOT, "oracle", "_ref", "smalt")
-        fq = os.path.join(tmp, "sample.fq")
-        with open(fq, "wb") as f:
-            f.write(fastq_text(reads[:ns]))
-        dt, err = run_cli(smalt, cores, pref, fq, os.path.join(tmp, "ref.sam")) if os.path.exists(smalt) else \
-            (None, "oracle/_ref/smalt not built")
-        if dt:
-            line["cpu_baseline"] = {"value": ns / dt, "unit": "reads/s", "cores": cores, "kind": "reference",
-                                    "sample": "first %d reads of this workload, whole `oracle/_ref/smalt map -n %d "
-                                              "-O` program (%.1f s)" % (ns, cores, dt)}
+        ns = min(args.cpu_sample or units, units)
+        if cfg.get("long_reads"):
+            ns = min(ns, args.cpu_sample or 64)
+        if os.path.exists(SMALT_REF):
+            ref_hist = hist
+            t_best, best = None, None
+            for t in sorted({cores, min(cores, 16)}):
+                v, dt, _ = reference_rate(wl, ns, t, ref_hist, tag="cpu")
+                if v is not None and (best is None or v > best):
+                    best, t_best, dt_best = v, t, dt
+            if best is not None:
+                line["cpu_baseline"] = {"value": best, "unit": "reads/s", "cores": t_best, "host_cores": cores, "kind": "reference",
+                                        "sample": "%s %d %s of this workload, whole `oracle/_ref/smalt map -n %d -O` "
+                                                  "program (%.1f s)" % ("all" if ns == units else "first", ns,
+                                                                        "pairs" if paired else "reads", t_best, dt_best)}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": cores, "kind": "reference",
+                                        "sample": "unavailable: " + str(dt)}
         else:
             line["cpu_baseline"] = {"value": None, "unit": "reads/s", "cores": cores, "kind": "reference",
-                                    "sample": "unavailable: " + err}
-    if world == 1 and not args.no_paired:
-        # configs[2] of BASELINE.json (paired-end, insert sizes) scaled to one GPU and a few seconds: not the
-        # headline metric, reported next to it
-        try:
-            time.sleep(2.0)   # (let the driver finish tearing down the whole-program runs above)
-            line["paired"] = run_paired(tmp, threads, cores, args.pairs, min(50_000, args.pairs), 3, 3)
-        except Exception as exc:   # the headline line must not be lost
-            line["paired"] = {"unavailable": repr(exc)[:300]}
+                                    "sample": "unavailable: oracle/_ref/smalt not built"}
     print(json.dumps(line))
 
 

@@ -1,5 +1,5 @@
 """`python -m smalt_b200.mapreads` - multi-GPU `smalt map` of a FASTQ file: one process per
-GPU (launch with torchrun), reads sharded by rank, SAM merged in input order on rank 0.
+GPU (launch with torchrun), reads sharded by rank, SAM merged in input order by offset writes into the output file.
 
   torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 -m smalt_b200.mapreads \
       [-n threads_per_gpu] [-i max_insert -j min_insert] -o out.sam <index_prefix> <reads.fq> [<mates.fq>]
@@ -24,7 +24,7 @@ def main(argv=None):
     ap.add_argument("mates", nargs="?", default=None)
     args = ap.parse_args(argv)
     from .mapper import Mapper
-    from .shard import gather_in_order, pair_shard_of, shard_of
+    from .shard import merge_to_file, pair_shard_of, shard_of
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     dist = None
@@ -56,13 +56,15 @@ def main(argv=None):
         header = m.sam_header() if rank == 0 else b""
         sam = m.map_fastq_pairs(mine1, mine2) if mine1 else b""
     m.close()
-    out = gather_in_order(dist, sam) if dist is not None else sam
-    if rank == 0:
+    if dist is None:
         with open(args.o, "wb") as f:
             f.write(header)
-            f.write(out)
-    if dist is not None:
+            f.write(sam)
+    else:
+        if rank == 0 and os.path.exists(args.o):
+            os.unlink(args.o)
         dist.barrier()
+        merge_to_file(dist, sam, args.o, header=header)   # every rank writes its records at its offset
         dist.destroy_process_group()
     return 0
 

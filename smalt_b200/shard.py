@@ -1,9 +1,13 @@
 """Multi-GPU read sharding: reads are independent, so rank r of N maps one contiguous
 range of the input records with its own GPU (index + packed reference replicated per GPU) and
-the per-rank SAM texts are concatenated in rank order - the input order, exactly what the
-reference's OUTPUT task restores with `-O` (smalt.c:966-1000).  No collective on the data
-path; the only communication is the final gather of the SAM text on the host side."""
+the per-rank SAM texts are merged in rank order - the input order, what the reference's OUTPUT
+task restores with `-O` (smalt.c:966-1000) - by offset writes into one file (merge_to_file).  No
+collective on the data path; the ranks exchange the lengths of their texts (8 bytes each).
+The merged text equals a single-process run except where the reference draws among equally good
+placements: every rank starts its own drand48 sequence (results.c:2298), like every run of the
+reference with another seed."""
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -66,23 +70,71 @@ def pair_shard_of(text1, text2, rank, world):
     return text1[p1[rank]:p1[rank + 1]], text2[p2[rank]:p2[rank + 1]]
 
 
-def gather_in_order(dist, local_bytes, dst=0):
-    """Concatenates the per-rank outputs in rank order on `dst` (None elsewhere).  Works with any
-    torch.distributed backend: sizes by all_gather, payloads as uint8 tensors."""
+def merge_to_file(dist, local_bytes, path, header=b""):
+    """Host merge of the per-rank outputs in rank (= input) order, as the reference's OUTPUT task
+    orders its blocks by read number (smalt.c:966-1000): every rank writes its text at its offset
+    into ONE file - `header` (rank 0), then rank 0's records, rank 1's, ... - with pwrite; the offsets
+    are the exclusive scan of the text lengths, the only thing the ranks exchange (8 bytes each).
+    Put `path` on /dev/shm for a merge through shared memory.  Ends with a barrier; -> total bytes."""
     import torch
-    world = dist.get_world_size()
-    rank = dist.get_rank()
+    world, rank = dist.get_world_size(), dist.get_rank()
     dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-    size = torch.tensor([len(local_bytes)], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, size)
-    sizes = [int(s.item()) for s in sizes]
-    mx = max(sizes + [1])
-    buf = torch.zeros(mx, dtype=torch.uint8, device=dev)
-    if local_bytes:
-        buf[:len(local_bytes)] = torch.frombuffer(bytearray(local_bytes), dtype=torch.uint8).to(dev)
-    bufs = [torch.zeros(mx, dtype=torch.uint8, device=dev) for _ in range(world)]
-    dist.all_gather(bufs, buf)
-    if rank != dst:
-        return None
-    return b"".join(bytes(np.asarray(b[:s].cpu().numpy()).tobytes()) for b, s in zip(bufs, sizes))
+    mine = len(local_bytes) + (len(header) if rank == 0 else 0)
+    sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+    sizes[rank] = mine
+    dist.all_reduce(sizes)
+    sizes = [int(x) for x in sizes.cpu().tolist()]
+    off = sum(sizes[:rank])
+    fd = os.open(path, os.O_WRONLY | os.O_CREAT, 0o644)
+    try:
+        if rank == 0:
+            os.ftruncate(fd, sum(sizes))
+            if header:
+                os.pwrite(fd, header, 0)
+                off = len(header)
+        mv, done = memoryview(local_bytes), 0
+        while done < len(mv):                      # (pwrite may write less than asked for)
+            done += os.pwrite(fd, mv[done:done + (1 << 30)], off + done)
+    finally:
+        os.close(fd)
+    dist.barrier()
+    return sum(sizes)
+
+
+def every_nth_record(text, n, phase=0):
+    """records phase, phase + n, phase + 2n, ... of a 4-line FASTQ text"""
+    a = np.frombuffer(text, np.uint8)
+    nl = np.flatnonzero(a == 10)
+    starts = np.concatenate([[0], nl + 1])
+    nrec = (len(nl) + (0 if not len(text) or text[-1:] == b"\n" else 1)) // 4
+    out = []
+    for r in range(phase, nrec, n):
+        b = int(starts[4 * r])
+        e = int(starts[4 * r + 4]) if 4 * r + 4 < len(starts) else len(text)
+        out.append(text[b:e])
+    return b"".join(out)
+
+
+def sample_insert_sizes(dist, exe, index_prefix, text1, text2, skip, hist_path, threads, env=None):
+    """Insert-size estimation for sharded pairs.  The reference samples every skip-th pair of the input and
+    builds ONE histogram from the sampled insert sizes (smalt.c:838-878, :1288-1300: the only cross-read state
+    of the path).  Here every rank contributes every skip-th pair of its shard, the subsamples are merged in
+    rank order on the host (merge_to_file) and rank 0 runs `sample -u 1` on them; all ranks then read the
+    same histogram file.  -> hist_path"""
+    import subprocess
+    rank = dist.get_rank()
+    f1, f2 = hist_path + ".s1.fq", hist_path + ".s2.fq"
+    merge_to_file(dist, every_nth_record(text1, skip), f1)
+    merge_to_file(dist, every_nth_record(text2, skip), f2)
+    err = b""
+    if rank == 0:
+        r = subprocess.run([exe, "sample", "-u", "1", "-n", str(threads), "-o", hist_path, index_prefix, f1, f2],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+        if r.returncode != 0:
+            err = r.stderr[-300:]
+        os.unlink(f1)
+        os.unlink(f2)
+    dist.barrier()
+    if not os.path.exists(hist_path):
+        raise RuntimeError("sample failed on rank 0: " + err.decode(errors="replace"))
+    return hist_path

