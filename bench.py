@@ -81,26 +81,28 @@ K3_OPS_PER_CELL = 8.0
 # --------------------------------------------------------------------------------------------------
 def make_genome(cfg):
     rng = np.random.default_rng(cfg["gseed"])
-    return [rng.integers(0, 4, n).astype(np.uint8) for n in cfg["seqs"]]
+    return [rng.integers(0, 4, n, dtype=np.uint8) for n in cfg["seqs"]]
 
 
 def write_index(tmp, cfg, seqs, device=0, tag="idx"):
     """.smi/.sma of the genome (byte-identical to `smalt index -k K -s S`, tests/test_indexer.py,
     test_gpu_index_build.py).  Genomes beyond 20 Mb are indexed on the GPU (smb_index_build)."""
     from smalt_b200 import indexer
+    from smalt_b200.seqpack import pack3
     pref = os.path.join(tmp, tag)
     total = sum(len(s) for s in seqs)
+    words = pack3(np.concatenate(list(seqs) + [np.array([7], np.uint8)]))
     if total > 20_000_000:
         from smalt_b200.capi import Context
         ctx = Context(device)
         try:
-            ix = indexer.build_index_gpu(ctx, seqs, cfg["k"], cfg["s"])
+            ix = indexer.build_index_gpu(ctx, seqs, cfg["k"], cfg["s"], words=words)
         finally:
             ctx.close()
     else:
         ix = indexer.build_index(seqs, cfg["k"], cfg["s"])
     indexer.write_smi(pref, ix)
-    indexer.write_sma(pref, ["chr%d" % (i + 1) for i in range(len(seqs))], seqs)
+    indexer.write_sma(pref, ["chr%d" % (i + 1) for i in range(len(seqs))], seqs, words=words)
     return pref, {"nwords": int(ix["nwords"]), "nkeys": int(ix["nkeys"]), "npos": int(ix["npos"]), "typ": int(ix["typ"])}
 
 
@@ -283,6 +285,13 @@ def run_program(exe, args, env=None):
     return dt, None
 
 
+def scaled_config(args):
+    cfg = dict(CONFIGS[args.config])
+    if args.genome_scale != 1.0:
+        cfg["seqs"] = [max(1000, int(n * args.genome_scale)) for n in cfg["seqs"]]
+    return cfg
+
+
 def host_threads():
     try:
         return max(1, min(len(os.sched_getaffinity(0)), 64))
@@ -370,7 +379,7 @@ def run_reference_arm(args):
     if not os.path.exists(SMALT_REF):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/smalt not built"}))
         return
-    cfg = CONFIGS[args.config]
+    cfg = scaled_config(args)
     units = args.reads or cfg["units"]
     nsample = min(args.ref_sample or units, units)
     cores = host_threads()
@@ -438,6 +447,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cli", action="store_true")
     ap.add_argument("--no-device-pass", action="store_true")
+    ap.add_argument("--genome-scale", type=float, default=1.0, help="scale the sequence lengths of the config (trial runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -448,7 +458,7 @@ def main():
     from smalt_b200.mapper import Mapper
     from smalt_b200 import shard
 
-    cfg = CONFIGS[args.config]
+    cfg = scaled_config(args)
     units = args.reads or cfg["units"]
     cores = host_threads()
     threads = args.threads or max(1, int(round(2.0 * cores / world)))

@@ -52,11 +52,32 @@ void block_state_free(smb_ctx *ctx) {
   ctx->blk = nullptr;
 }
 
-static float ev_ms(cudaEvent_t a, cudaEvent_t b) {
-  float ms = 0.f;
-  if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0.f; }
-  return ms;
-}
+// Device time of a block: spans of GPU work between two events on the stream, none of them across a
+// host synchronisation (the gaps in which the device waits for the host are not kernel time).
+enum { SPAN_HITS = 0, SPAN_CAND = 1, SPAN_K2 = 2, SPAN_K3 = 3, SPAN_KINDS = 4 };
+struct Spans {
+  smb_ctx *ctx;
+  int n = 0;
+  int kind[SMB_BLK_EVENTS / 2];
+  explicit Spans(smb_ctx *c) : ctx(c) {}
+  cudaError_t begin(int k) {
+    if (n >= SMB_BLK_EVENTS / 2) return cudaSuccess;   // (more spans than events: the rest goes untimed)
+    kind[n] = k;
+    return cudaEventRecord(ctx->blk_ev[2 * n], ctx->stream);
+  }
+  cudaError_t end() {
+    if (n >= SMB_BLK_EVENTS / 2) return cudaSuccess;
+    return cudaEventRecord(ctx->blk_ev[2 * n++ + 1], ctx->stream);
+  }
+  void sum(float ms[SPAN_KINDS]) const {   // after a synchronisation of the stream
+    for (int k = 0; k < SPAN_KINDS; ++k) ms[k] = 0.f;
+    for (int i = 0; i < n; ++i) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, ctx->blk_ev[2 * i], ctx->blk_ev[2 * i + 1]) == cudaSuccess) ms[kind[i]] += t;
+      else cudaGetLastError();
+    }
+  }
+};
 
 extern "C" {
 
@@ -159,7 +180,7 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
   {
     Carver c(nullptr);
     c.take<smb_hit_req>(nr + 1); c.take<uint64_t>(nr + 2); c.take<uint32_t>(nr + 1); c.take<uint32_t>(nr + 1);
-    c.take<int32_t>(nr + 1); c.take<int32_t>(nr + 1);
+    c.take<int32_t>(nr + 1); c.take<int32_t>(nr + 1); c.take<uint32_t>(nr + 1);
     CU(ctx->hit_meta.ensure(c.off));
   }
   Carver ch(ctx->hit_meta.p);
@@ -169,6 +190,7 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
   uint32_t *d_used = ch.take<uint32_t>(nr + 1);
   int32_t *d_rerrs = ch.take<int32_t>(nr + 1);
   int32_t *d_rseq = ch.take<int32_t>(nr + 1);
+  a.req_ncand = ch.take<uint32_t>(nr + 1);
   a.req = d_req; a.req_seqidx = d_rseq; a.hit_off = d_off; a.req_err = d_rerrs;
   ctx->hit_qmask_valid = false;
   HitArgs ha{};
@@ -176,39 +198,46 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
   ha.count = d_count; ha.maxhit_used = d_used; ha.errs = d_rerrs; ha.offset = d_off; ha.sqdat = nullptr;
   ha.list_qmask = nullptr; ha.qmask_off = nullptr;
   int nl = 0;
-  CU(cudaEventRecord(ctx->blk_ev[0], st));
+  Spans sp(ctx);
+  CU(sp.begin(SPAN_HITS));
   CU(launch_block_reqs(a, st, &nl));
   uint64_t total_hits = 0;
   if (nreq > 0) {
     CU(launch_hits(ctx->seed_ix, ha, false, st, &nl));
     CU(launch_scan_counts(d_count, nreq, (unsigned long long *)d_off, d_tile, st, &nl));
+    CU(sp.end());
     CU(d2h(h_tot, d_off + nreq, 8, st));
     CU(ctx_sync(ctx));                                                          // sync 1: total hits
     total_hits = h_tot[0];
   } else {
     CU(cudaMemsetAsync(d_off, 0, 16, st));
+    CU(sp.end());
   }
   CU(ctx->hit_data.ensure((size_t)(total_hits + 1) * 8));
   ha.sqdat = ctx->hit_data.as<uint64_t>();
   a.sqdat = ha.sqdat;
-  if (nreq > 0 && total_hits) CU(launch_hits(ctx->seed_ix, ha, true, st, &nl));
-  CU(cudaEventRecord(ctx->blk_ev[1], st));
 
   // ---- candidate selection ----
   const size_t H = (size_t)total_hits + 1;
   a.mask_words = (maxlen + 31u) / 32u + 1u;
+  const size_t mask_total = a.mask_words > 8u ? nj * 32u * a.mask_words : 64;   // (CW_MASKW words per lane live in shared memory)
   {
     Carver c(nullptr);
     c.take<uint64_t>(H); c.take<int32_t>(H); c.take<uint32_t>(H); c.take<int32_t>(H); c.take<uint32_t>(H);
-    c.take<SegCand>(H); c.take<uint32_t>(H); c.take<uint32_t>(H); c.take<uint32_t>(nj * a.mask_words);
+    c.take<SegCand>(H); c.take<uint32_t>(H); c.take<uint32_t>(H); c.take<uint32_t>(mask_total);
     CU(ctx->blk_scr.ensure(c.off));
   }
   Carver cs(ctx->blk_scr.p);
   a.sd_sqo = cs.take<uint64_t>(H); a.sd_len = cs.take<int32_t>(H); a.sg_ix = cs.take<uint32_t>(H);
   a.sg_nseed = cs.take<int32_t>(H); a.sg_cover = cs.take<uint32_t>(H); a.cand = cs.take<SegCand>(H);
-  a.sort_key = cs.take<uint32_t>(H); a.sort_idx = cs.take<uint32_t>(H); a.mask = cs.take<uint32_t>(nj * a.mask_words);
+  a.sort_key = cs.take<uint32_t>(H); a.sort_idx = cs.take<uint32_t>(H); a.mask = cs.take<uint32_t>(mask_total);
+  CU(sp.begin(SPAN_HITS));
+  if (nreq > 0 && total_hits) CU(launch_hits(ctx->seed_ix, ha, true, st, &nl));
+  CU(sp.end());
+  CU(sp.begin(SPAN_CAND));
   CU(launch_block_cands(a, st, &nl));
   CU(launch_scan_counts(a.n_sort, njobs, d_cand_first, d_tile, st, &nl));
+  CU(sp.end());
   CU(d2h(h_tot, d_cand_first + njobs, 8, st));
   CU(d2h(h_cnt, a.cnt, sizeof(BlockCounters), st));
   CU(ctx_sync(ctx));                                                            // sync 2: candidates, K2 classes
@@ -230,8 +259,9 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
   a.score = cc.take<int32_t>(NC); a.serr = cc.take<int32_t>(NC); a.k3rank = cc.take<int32_t>(NC);
   a.k3cls = cc.take<uint8_t>(NC); a.k2_order = cc.take<int>(NC); a.bf_order = cc.take<int>(NC);
   a.bft = cc.take<smb_band_task>(NC);
+  CU(sp.begin(SPAN_CAND));
   CU(launch_block_emit_k2(a, ncand, st, &nl));
-  CU(cudaEventRecord(ctx->blk_ev[2], st));
+  CU(sp.end());
 
   // ---- K2 (and K2' for the candidates outside the SIMD predicate) ----
   if (nsw) {
@@ -241,7 +271,9 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
     plan.bstride = (h_cnt->max_rlen_multi + 31u) & ~31u;
     plan.strip_bytes = (size_t)plan.max_grid * 4u * 2u * plan.bstride * sizeof(int2);   // SW_WARPS = 4 (sw_score.cu)
     CU(ctx->scratch.ensure(plan.strip_bytes + 256));
+    CU(sp.begin(SPAN_K2));
     CU(launch_sw_score(sc, ctx->src, a.swt, plan, d_k2_tickets, a.k2_order, ctx->scratch.p, a.score, a.serr, st, &nl));
+    CU(sp.end());
   }
   // K2' of a list of candidates (indices in h_bf): planned on the host like smb_band_score_batch
   auto run_band_fast = [&](const std::vector<int> &h_bf) -> int {
@@ -261,8 +293,10 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
     CU(ctx_sync(ctx));   // `order` goes out of scope
     unsigned long long *d_cells = &a.cnt->k2_cells_ref;   // (cells of K2' are not reported; any 8-byte slot)
     BandOut bo{nullptr, nullptr, nullptr, a.serr, d_cells, nullptr};
+    CU(sp.begin(SPAN_K2));
     CU(launch_band(sc, ctx->src, a.bft, plan, a.bf_order, false, a.score, bo, 0, nullptr, nullptr, nullptr, nullptr,
                    ctx->scratch.as<uint32_t>(), ctx->ticket.as<int>(), ctx->sm_count, st, &nl));
+    CU(sp.end());
     return SMB_OK;
   };
   if (nbf) {
@@ -273,13 +307,14 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
     if (rc) return rc;
     CU(cudaMemsetAsync(&a.cnt->k2_cells_ref, 0, 8, st));
   }
-  CU(cudaEventRecord(ctx->blk_ev[3], st));
 
   // ---- replay of the sequential score bookkeeping, K3 task list ----
   size_t nk3 = 0;
   for (int round = 0;; ++round) {
+    CU(sp.begin(SPAN_CAND));
     CU(launch_block_replay(a, st, &nl));
     CU(launch_scan_counts(a.nk3, njobs, d_k3_first, d_tile, st, &nl));
+    CU(sp.end());
     CU(d2h(h_tot, d_k3_first + njobs, 8, st));
     CU(d2h(h_cnt, a.cnt, sizeof(BlockCounters), st));
     CU(ctx_sync(ctx));                                                          // sync 3: K3 classes and sizes
@@ -356,15 +391,19 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
     P.args = a;
     const bool too_big = h_cnt->dir_words > ((uint64_t)1 << 30);   // long-read sized: chunked multi-pass path
     const size_t res_bytes = (size_t)n3 * max_res * sizeof(smb_ali_result);
+    CU(sp.begin(SPAN_CAND));
     CU(launch_block_emit_k3(a, ncand, st, &nl));
+    CU(sp.end());
     bool multipass = too_big;
     if (!too_big) {
       const size_t outa = res_bytes + (size_t)n3 * (2 * sizeof(uint32_t) + sizeof(int32_t)) + 64;
       CU(ctx->out_b.ensure(outa));
       CU(ctx->dirs.ensure((size_t)(h_cnt->dir_words + 4) * sizeof(uint32_t)));
       CU(ctx->diff.ensure((size_t)h_cnt->diff_bytes + 64));
+      CU(sp.begin(SPAN_CAND));
       CU(launch_scan_counts(a.dir_words_arr, n3, (unsigned long long *)d_dir_off, d_tile3, st, &nl));
       CU(launch_scan_counts(a.diff_stride, n3, (unsigned long long *)d_diff_off, d_tile3, st, &nl));
+      CU(sp.end());
       char *ob = ctx->out_b.as<char>();
       smb_ali_result *d_res = (smb_ali_result *)ob;
       uint32_t *d_nres = (uint32_t *)(ob + res_bytes);
@@ -383,18 +422,17 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
       CompactTotals *d_tot = (CompactTotals *)(d_tile_diff + ntiles);
       unsigned long long *d_diff_first = (unsigned long long *)(((uintptr_t)(d_tot + 1) + 63) & ~(uintptr_t)63);
       uint32_t *d_first = (uint32_t *)(d_diff_first + n3);
-      CU(cudaEventRecord(ctx->blk_ev[4], st));
+      CU(sp.begin(SPAN_K3));
       CU(launch_band(sc, ctx->src, a.bat, plan, a.k3_order, true, nullptr, bo, max_res, d_dir_off, ctx->dirs.as<uint32_t>(),
                      d_diff_off, a.diff_cap, ctx->scratch.as<uint32_t>(), ctx->ticket.as<int>(), ctx->sm_count, st, &nl,
                      &ctx->side));
       CU(launch_compact_scan(d_nres, d_dused, d_errs, n3, d_tile_res, d_tile_diff, d_tot, d_first, d_diff_first, st, &nl));
-      CU(cudaEventRecord(ctx->blk_ev[5], st));
+      CU(sp.end());
       CompactTotals *h_ct = (CompactTotals *)(h_tot + 2);
       unsigned long long *h_cells = (unsigned long long *)(h_ct + 1);
       CU(d2h(h_ct, d_tot, sizeof(CompactTotals), st));
       CU(d2h(h_cells, d_cells, sizeof(unsigned long long), st));
       CU(ctx_sync(ctx));                                                        // sync 4: result sizes
-      ms_k3 = ev_ms(ctx->blk_ev[4], ctx->blk_ev[5]);
       if (h_ct->capacity_flag || h_ct->ndiff > 0xffffffffull) multipass = true;
       else {
         P.nres = (size_t)h_ct->nresults;
@@ -423,10 +461,14 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
   }
   sizes->nresults = P.nres;
   sizes->ndiffbytes = P.ndiff;
-  sizes->ms_hits = ev_ms(ctx->blk_ev[0], ctx->blk_ev[1]);
-  sizes->ms_cand = ev_ms(ctx->blk_ev[1], ctx->blk_ev[2]);
-  sizes->ms_k2 = ev_ms(ctx->blk_ev[2], ctx->blk_ev[3]);
-  sizes->ms_k3 = ms_k3;
+  {
+    float ms[SPAN_KINDS];
+    sp.sum(ms);
+    sizes->ms_hits = ms[SPAN_HITS];
+    sizes->ms_cand = ms[SPAN_CAND];
+    sizes->ms_k2 = ms[SPAN_K2];
+    sizes->ms_k3 = ms[SPAN_K3] + ms_k3;
+  }
   sizes->launches = nl;
   ctx->last_ms = sizes->ms_hits + sizes->ms_cand + sizes->ms_k2 + sizes->ms_k3;
   ctx->last_launches += nl;

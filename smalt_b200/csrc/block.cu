@@ -2,7 +2,7 @@
 //
 //   block_reqs_kernel     the hit-list requests of every job (read x strand x sequence | interval),
 //                         what collectHits / collectHitsFromInterVal ask for (rmap.c:283-318, :438-493)
-//   block_cands_kernel    candidate selection, one thread per job: hit regions, seeds, constant-shift
+//   block_cands_kernel    candidate selection, one warp per job and one lane per hit list: hit regions, seeds, constant-shift
 //                         segments (segLstFillHits, segment.c:763-810 with :396-584), candidates by coverage
 //                         (segAliCandsAddFast -> addCandsFast / derriveSEGCAND, :1140-1223, :929-1059),
 //                         threshold + sort + depth cut (segAliCandsStats, :1616-1785; the reference's
@@ -13,8 +13,8 @@
 //                         mapSingleRead (:1373-1400) on the scores, which candidates go to K3
 //   block_emit_k3_kernel  K3 tasks (widened bands, rmap.c:888-896) grouped by kernel class
 //
-// Integer work on small per-read lists (a few dozen hits, a handful of candidates): one thread walks
-// one read's lists exactly in the reference's order, 32-bit and 64-bit quantities as there.
+// Integer work on small per-read lists (a few dozen hits, a handful of candidates): one lane walks
+// one hit list exactly in the reference's order, 32-bit and 64-bit quantities as there.
 #include "block.cuh"
 #include "band.h"
 #include "sort2.cuh"
@@ -34,6 +34,18 @@ constexpr int MINLEN_QUERY_STRIPED = 32, BWSCAL_QLEN = 48;   // rmap.c:83-84
 constexpr int SW2_MAXROWS_ = 512;                   // sw_score.cu: staged window rows of the paired kernel
 
 __device__ __forceinline__ uint64_t shiftpart(uint64_t x) { return x & ~((uint64_t)HALFMASK); }
+
+// Division by the sampling step.  Every dividend on this path is a read offset or a seed length
+// (< 2^26), for which floor(x / d) = umulhi(x, ceil(2^32 / d)) exactly (d <= 255: the error term
+// x * (d - 1) / 2^32 stays below 1); a hardware-free replacement of the ~20-instruction runtime divide
+// that sits in the innermost hit loops.
+struct StepDiv {
+  uint32_t d, m;
+  __device__ __forceinline__ explicit StepDiv(int step) : d((uint32_t)step), m(step > 1 ? (uint32_t)(0x100000000ull / (uint32_t)step) + 1u : 0u) {}
+  __device__ __forceinline__ uint32_t div(uint32_t x) const { return d > 1u ? (x < (1u << 26) ? __umulhi(x, m) : x / d) : x; }
+  __device__ __forceinline__ uint32_t mod(uint32_t x) const { return x - div(x) * d; }
+  __device__ __forceinline__ int divs(int x) const { return x >= 0 ? (int)div((uint32_t)x) : -(int)div((uint32_t)(-x)); }   // C truncation
+};
 
 // sets bits [q0, q0 + len) of the coverage mask, returns how many of them were clear
 __device__ __forceinline__ uint32_t mask_cover(uint32_t *mask, uint32_t q0, uint32_t len) {
@@ -62,25 +74,25 @@ struct SegView {   // the seeds / segments of the current hit region (per job sc
 
 // calcSegmentBoundaries (segment.c:635-668)
 __device__ __forceinline__ void seg_bounds(uint32_t &qs, uint32_t &qe, uint32_t &rs, uint32_t &re, const SegView &v,
-                                           int sg, int ktup, int nskip, bool is_reverse) {
+                                           int sg, int ktup, const StepDiv &nskip, bool is_reverse) {
   const uint32_t i0 = v.sg_ix[sg], i1 = i0 + (uint32_t)v.sg_nseed[sg] - 1u;
   const uint64_t s0 = v.sd_sqo[i0], s1 = v.sd_sqo[i1];
   const int32_t l1 = v.sd_len[i1];
   qs = (uint32_t)(s0 & HALFMASK);
   qe = (uint32_t)(s1 & HALFMASK) + (uint32_t)l1 - 1u;
   if (is_reverse) {
-    rs = (uint32_t)(((s1 >> HALFBIT) - (s1 & HALFMASK) / (uint32_t)nskip) & SOFFSMASK);
-    rs -= (uint32_t)((l1 - ktup) / nskip);
-    re = (uint32_t)(((s0 >> HALFBIT) - qs / (uint32_t)nskip) & SOFFSMASK);
+    rs = (uint32_t)(((s1 >> HALFBIT) - nskip.div((uint32_t)(s1 & HALFMASK))) & SOFFSMASK);
+    rs -= (uint32_t)nskip.divs(l1 - ktup);
+    re = (uint32_t)(((s0 >> HALFBIT) - nskip.div(qs)) & SOFFSMASK);
   } else {
-    rs = (uint32_t)(((s0 >> HALFBIT) + qs / (uint32_t)nskip) & SOFFSMASK);
-    re = (uint32_t)(((s1 >> HALFBIT) + (s1 & HALFMASK) / (uint32_t)nskip) & SOFFSMASK);
-    re += (uint32_t)((l1 - ktup) / nskip);
+    rs = (uint32_t)(((s0 >> HALFBIT) + nskip.div(qs)) & SOFFSMASK);
+    re = (uint32_t)(((s1 >> HALFBIT) + nskip.div((uint32_t)(s1 & HALFMASK))) & SOFFSMASK);
+    re += (uint32_t)nskip.divs(l1 - ktup);
   }
 }
 
 // derriveSEGCAND (segment.c:929-1059) for segments [first, first + nseg) of the region
-__device__ int derive_cand(SegCand &cd, int first, int nseg, const SegView &v, int ktup, int nskip, uint32_t cover,
+__device__ int derive_cand(SegCand &cd, int first, int nseg, const SegView &v, int ktup, const StepDiv &nskip, uint32_t cover,
                            uint32_t mincover_noindel, bool is_reverse) {
   if (v.sg_nseed[first] < 0) return ERR_ASSERT;
   uint32_t cqs, cqe, crs, cre;
@@ -109,9 +121,9 @@ __device__ int derive_cand(SegCand &cd, int first, int nseg, const SegView &v, i
   long long shift_start;
   if (is_reverse) {
     flag |= CANDFLG_REVERSE;
-    shift_start = ((long long)crs) + (long long)((cqe - (uint32_t)ktup + 1u) / (uint32_t)nskip);
+    shift_start = ((long long)crs) + (long long)nskip.div(cqe - (uint32_t)ktup + 1u);
   } else {
-    shift_start = (long long)(((unsigned long long)crs) | (1ull << (HALFBIT + 1))) - (long long)(cqs / (uint32_t)nskip);
+    shift_start = (long long)(((unsigned long long)crs) | (1ull << (HALFBIT + 1))) - (long long)nskip.div(cqs);
   }
   const unsigned long long shift_range =
       (unsigned long long)(((long long)(v.sd_sqo[v.sg_ix[last]] >> HALFBIT)) - shift_min);
@@ -138,13 +150,14 @@ __device__ int derive_cand(SegCand &cd, int first, int nseg, const SegView &v, i
 
 // One hit list -> candidates appended to cand[ncand...].
 __device__ int add_list(const uint64_t *__restrict__ sqdat, int nhits, bool is_reverse, uint32_t qlen, int ktup,
-                        int nskip, uint32_t min_ktup, uint32_t mincover, int seqidx, const SegView &v,
+                        int nskip_, uint32_t min_ktup, uint32_t mincover, int seqidx, const SegView &v,
                         uint32_t *mask, uint32_t mask_words, SegCand *cand, uint32_t &ncand, uint32_t &max_cover,
                         uint32_t &max2nd_cover) {
   if (nhits < 1) return 0;
+  const StepDiv nskip(nskip_);
   // defineHitRegions (segment.c:396-453)
-  uint32_t max_dshift = (uint32_t)(ktup * SEGMENTING_DIFFSHIFT / nskip) & 0xffffu;
-  const uint32_t ds = (qlen - (uint32_t)ktup) / (uint32_t)nskip + 1u;
+  uint32_t max_dshift = (uint32_t)(ktup * SEGMENTING_DIFFSHIFT / nskip_) & 0xffffu;
+  const uint32_t ds = (qlen - (uint32_t)ktup) / (uint32_t)nskip_ + 1u;
   if (ds < max_dshift) max_dshift = ds & 0xffffu;
   const uint64_t dsthresh = ((uint64_t)max_dshift) << HALFBIT;
   int i = 0;
@@ -169,7 +182,7 @@ __device__ int add_list(const uint64_t *__restrict__ sqdat, int nhits, bool is_r
           const uint64_t h = sqdat[b];
           if (shiftpart(h) != shift) break;
           const uint32_t qo = (uint32_t)(h & HALFMASK);
-          if (qo > lastq || ((qo - qoffs) % (uint32_t)nskip)) break;
+          if (qo > lastq || nskip.mod(qo - qoffs)) break;
           lastq = qo + (uint32_t)ktup;
         }
         v.sd_sqo[nseed] = sqo;
@@ -187,7 +200,7 @@ __device__ int add_list(const uint64_t *__restrict__ sqdat, int nhits, bool is_r
         int b = a + 1;
         for (; b < nseed; ++b) {
           const uint64_t s2 = v.sd_sqo[b];
-          if (shiftpart(s2) != shift || (((uint32_t)(s2 & HALFMASK)) - qoffs) % (uint32_t)nskip) break;
+          if (shiftpart(s2) != shift || nskip.mod(((uint32_t)(s2 & HALFMASK)) - qoffs)) break;
           cover += (uint32_t)v.sd_len[b];
         }
         v.sg_ix[nsegm] = (uint32_t)a;
@@ -343,21 +356,60 @@ __global__ void __launch_bounds__(128) block_reqs_kernel(const BlockArgs a) {
 }
 
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) block_cands_kernel(const BlockArgs a) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+// ONE WARP PER JOB, ONE LANE PER HIT LIST.  The hit lists of a job (read x strand x sequence | interval)
+// are independent until segAliCandsStats: every lane runs the reference's sequential segmentation on its
+// own list (regions, seeds, segments, candidates by coverage) with its scratch in shared memory, the
+// candidates of the lists are then numbered in list order (the order candr has in the reference), the two
+// largest distinct covers are merged, the threshold filter keeps that order, lane 0 runs the reference's
+// quicksort and depth cut on the (few) keys, and the windows of the selected candidates are checked by all
+// lanes.  Jobs whose lists do not fit the shared scratch (more than CW_HITS hits, reads beyond 32 * CW_MASKW
+// bases) use the per-job scratch in HBM with the same code.
+constexpr int CW_WARPS = 4;      // jobs per CTA
+constexpr int CW_HITS = 192;     // hits of a job whose seeds / segments fit the shared scratch
+constexpr int CW_MASKW = 8;      // coverage mask words per lane in shared memory (reads of <= 256 bases)
+
+struct CandSmem {
+  unsigned long long sd_sqo[CW_HITS];
+  int sd_len[CW_HITS];
+  unsigned int sg_ix[CW_HITS];
+  int sg_nseed[CW_HITS];
+  unsigned int sg_cover[CW_HITS];
+  unsigned int mask[32 * CW_MASKW];
+};
+
+// the two largest distinct values of two (max, second) pairs
+__device__ __forceinline__ void merge_top2(uint32_t &m, uint32_t &s, uint32_t m2, uint32_t s2) {
+  const uint32_t M = max(m, m2);
+  uint32_t S = 0;
+  if (m < M && m > S) S = m;
+  if (m2 < M && m2 > S) S = m2;
+  if (s < M && s > S) S = s;
+  if (s2 < M && s2 > S) S = s2;
+  m = M;
+  s = S;
+}
+
+__global__ void __launch_bounds__(CW_WARPS * 32) block_cands_kernel(const BlockArgs a) {
+  __shared__ CandSmem s_all[CW_WARPS];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * CW_WARPS + (threadIdx.x >> 5);
   if (j >= a.njobs) return;
+  CandSmem &sm = s_all[threadIdx.x >> 5];
   const smb_block_job jb = a.jobs[j];
   smb_block_read rd;
   memset(&rd, 0, sizeof rd);
-  a.n_sort[j] = 0;
-  a.nk3[j] = 0;
   const uint32_t r = jb.seed_read;
   const uint32_t qlen = a.seed.read_len[r];
   const smb_seed_info inf0 = a.seed.info[2 * r], inf1 = a.seed.info[2 * r + 1];
   rd.errcode = inf0.err ? inf0.err : inf1.err;
-  a.cover_deficit[2 * j] = inf0.cover_deficit;
-  a.cover_deficit[2 * j + 1] = inf1.cover_deficit;
-  if (rd.errcode) { a.rd[j] = rd; return; }
+  if (lane == 0) {
+    a.n_sort[j] = 0;
+    a.nk3[j] = 0;
+    a.cover_deficit[2 * j] = inf0.cover_deficit;
+    a.cover_deficit[2 * j + 1] = inf1.cover_deficit;
+  }
+  if (rd.errcode) { if (lane == 0) a.rd[j] = rd; return; }
   const int ktup = a.ktup, nskip = a.nskip;
   // calcMinKtup (rmap.c:240-247) and the prelude of mapSingleRead (:1282-1288)
   uint32_t min_cover = jb.min_cover;
@@ -376,27 +428,49 @@ __global__ void __launch_bounds__(64) block_cands_kernel(const BlockArgs a) {
   if (min_ktup >= 2u) min_ktup = (min_ktup - 1u > qlen) ? min_ktup - qlen : 1u;
 
   const int nlist = jb.niv < 0 ? a.nseq : jb.niv;
+  const int nl = 2 * nlist;
   const uint32_t rq0 = a.job_req[j];
   const uint64_t base = a.hit_off[rq0];
-  SegView v{a.sd_sqo + base, a.sd_len + base, a.sg_ix + base, a.sg_nseed + base, a.sg_cover + base};
-  SegCand *cand = a.cand + base;
-  uint32_t *mask = a.mask + (size_t)j * a.mask_words;
+  const uint64_t H = a.hit_off[rq0 + nl] - base;
   const uint32_t mask_words = (qlen + 31u) / 32u;
-  uint32_t ncand = 0, max_cover = 0, max2nd_cover = 0;
-  uint32_t rq = rq0;
-  for (int st = 0; st < 2 && !rd.errcode; ++st)
-    for (int c = 0; c < nlist; ++c, ++rq) {
-      if (rd.errcode) continue;
-      const int e = a.req_err[rq];
-      if (e && e != SMB_ERRCODE_ALLOCBOUNDARY) { rd.errcode = e; continue; }
-      const uint64_t f0 = a.hit_off[rq], f1 = a.hit_off[rq + 1];
-      const int e2 = add_list(a.sqdat + f0, (int)(f1 - f0), st != 0, qlen, ktup, nskip, min_ktup, min_cover,
-                              a.req_seqidx[rq], v, mask, mask_words, cand, ncand, max_cover, max2nd_cover);
-      if (e2) rd.errcode = e2;
-    }
-  if (rd.errcode) { a.rd[j] = rd; return; }
+  const bool in_smem = H <= (uint64_t)CW_HITS && mask_words <= (uint32_t)CW_MASKW;
+  uint32_t *mask = mask_words <= (uint32_t)CW_MASKW ? sm.mask + lane * CW_MASKW : a.mask + ((size_t)j * 32u + lane) * a.mask_words;
 
-  // segAliCandsStats (segment.c:1616-1785)
+  // ---- phase 1: the lists, 32 at a time ----
+  uint32_t max_cover = 0, max2nd_cover = 0, ncand_all = 0;
+  for (int l0 = 0; l0 < nl && !rd.errcode; l0 += 32) {
+    const int l = l0 + lane;
+    int e = 0;
+    uint32_t nc = 0, mc = 0, m2 = 0;
+    if (l < nl) {
+      const uint32_t rq = rq0 + (uint32_t)l;
+      e = a.req_err[rq];
+      if (e == SMB_ERRCODE_ALLOCBOUNDARY) e = 0;
+      if (!e) {
+        const uint64_t f0 = a.hit_off[rq], f1 = a.hit_off[rq + 1];
+        const uint64_t o = f0 - base;
+        SegView v;
+        if (in_smem) v = SegView{(uint64_t *)sm.sd_sqo + o, sm.sd_len + o, sm.sg_ix + o, sm.sg_nseed + o, sm.sg_cover + o};
+        else v = SegView{a.sd_sqo + f0, a.sd_len + f0, a.sg_ix + f0, a.sg_nseed + f0, a.sg_cover + f0};
+        e = add_list(a.sqdat + f0, (int)(f1 - f0), l >= nlist, qlen, ktup, nskip, min_ktup, min_cover, a.req_seqidx[rq], v,
+                     mask, mask_words, a.cand + f0, nc, mc, m2);
+      }
+      a.req_ncand[rq] = nc;
+    }
+    // the first list (in order) with an error ends the job
+    const unsigned bad = __ballot_sync(FULL, e != 0);
+    if (bad) { rd.errcode = __shfl_sync(FULL, e, __ffs(bad) - 1); break; }
+    for (int o = 16; o > 0; o >>= 1) {
+      const uint32_t om = __shfl_xor_sync(FULL, mc, o), o2 = __shfl_xor_sync(FULL, m2, o);
+      merge_top2(mc, m2, om, o2);
+      nc += __shfl_xor_sync(FULL, nc, o);
+    }
+    merge_top2(max_cover, max2nd_cover, mc, m2);
+    ncand_all += nc;
+  }
+  if (rd.errcode) { if (lane == 0) a.rd[j] = rd; return; }
+
+  // ---- phase 2: segAliCandsStats (segment.c:1616-1785): threshold filter in list order ----
   uint32_t max_depth = (uint32_t)a.prm.max_depth, target_depth = (uint32_t)a.prm.target_depth;   // SEGNUM_t
   if (max_depth < 1u || max_depth > (uint32_t)MAXIMUM_DEPTH) max_depth = MAXIMUM_DEPTH;
   if (target_depth < 1u) target_depth = DEFAULT_TARGET_DEPTH;
@@ -406,68 +480,117 @@ __global__ void __launch_bounds__(64) block_cands_kernel(const BlockArgs a) {
   const uint32_t cda = inf0.cover_deficit > cdf ? inf0.cover_deficit - cdf : 0u;   // both strands: FORWARD deficit (:1674)
   uint32_t *skey = a.sort_key + base, *sidx = a.sort_idx + base;
   uint32_t nk = 0;
-  for (uint32_t i = 0; i < ncand; ++i) {
-    const uint32_t cov = cand[i].cover;
-    if (cov + cda < thr) continue;
-    if (cov > max_cover) { rd.errcode = ERR_ASSERT; break; }
-    skey[nk] = max_cover - cov;
-    sidx[nk] = i;
-    ++nk;
+  for (int l0 = 0; l0 < nl; l0 += 32) {
+    const int l = l0 + lane;
+    uint32_t cnt = 0, nc = 0;
+    uint64_t f0 = 0;
+    if (l < nl) {
+      const uint32_t rq = rq0 + (uint32_t)l;
+      nc = a.req_ncand[rq];
+      f0 = a.hit_off[rq];
+      for (uint32_t i = 0; i < nc; ++i) cnt += (a.cand[f0 + i].cover + cda >= thr);
+    }
+    uint32_t pos = cnt;   // inclusive scan over the lanes
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL, pos, o);
+      if (lane >= o) pos += t;
+    }
+    const uint32_t tot = __shfl_sync(FULL, pos, 31);
+    pos = nk + pos - cnt;
+    for (uint32_t i = 0; i < nc; ++i) {
+      const uint32_t cov = a.cand[f0 + i].cover;
+      if (cov + cda < thr) continue;
+      skey[pos] = max_cover - cov;
+      sidx[pos] = (uint32_t)(f0 - base) + i;
+      ++pos;
+    }
+    nk += tot;
   }
-  if (!rd.errcode) {
-    const int e = sort2((int)nk, skey, sidx);
-    if (e) rd.errcode = e;
-  }
-  if (rd.errcode) { a.rd[j] = rd; return; }
+  __syncwarp();
+  // ---- phase 3: the reference's quicksort and the depth cut, lane 0 (in shared memory if the keys fit) ----
   const uint32_t n_mincover = nk;
-  if (nk > target_depth) {
-    const uint32_t maxj = (nk < max_depth) ? nk : max_depth;
-    if (a.prm.sensitive) {
+  uint32_t *wk = skey, *wi = sidx;
+  const bool sort_smem = nk <= (uint32_t)CW_HITS;   // (the seed scratch is free again)
+  if (sort_smem) {
+    wk = (uint32_t *)sm.sd_sqo;
+    wi = wk + CW_HITS;
+    for (uint32_t i = lane; i < nk; i += 32) { wk[i] = skey[i]; wi[i] = sidx[i]; }
+    __syncwarp();
+  }
+  int serr = 0;
+  if (lane == 0) {
+    serr = sort2((int)nk, wk, wi);
+    if (!serr && nk > target_depth) {
+      const uint32_t maxj = (nk < max_depth) ? nk : max_depth;
       uint32_t t = target_depth;
-      for (; t < maxj; ++t)
-        if (skey[t] >= cda) break;            // (the reference indexes candr by t here, both strands share cda)
-      for (; t < n_mincover && skey[t] < (uint32_t)nskip; ++t);
-      nk = t;
-    } else {
-      uint32_t cov = skey[nk / 2];
-      if (cov < (uint32_t)nskip) cov = (uint32_t)nskip;
-      uint32_t t = target_depth;
-      for (; t < maxj && skey[t] < cov; ++t);
+      if (a.prm.sensitive) {
+        for (; t < maxj; ++t)
+          if (wk[t] >= cda) break;            // (the reference indexes candr by t here, both strands share cda)
+        for (; t < n_mincover && wk[t] < (uint32_t)nskip; ++t);
+      } else {
+        uint32_t cov = wk[nk / 2];
+        if (cov < (uint32_t)nskip) cov = (uint32_t)nskip;
+        for (; t < maxj && wk[t] < cov; ++t);
+      }
       nk = t;
     }
   }
-  if (nk > 0x7fffffffu || n_mincover > 0x7fffffffu) { rd.errcode = ERR_ASSERT; a.rd[j] = rd; return; }
+  serr = __shfl_sync(FULL, serr, 0);
+  nk = __shfl_sync(FULL, nk, 0);
+  if (sort_smem) {
+    __syncwarp();
+    for (uint32_t i = lane; i < n_mincover; i += 32) { skey[i] = wk[i]; sidx[i] = wi[i]; }
+  }
+  if (!serr && (nk > 0x7fffffffu || n_mincover > 0x7fffffffu)) serr = ERR_ASSERT;
+  if (serr) { rd.errcode = serr; if (lane == 0) a.rd[j] = rd; return; }
   rd.nseg = (int32_t)nk;
   rd.nseg_tot = (int32_t)n_mincover;
   rd.nhit = inf0.nhit_rank + inf1.nhit_rank;      // calcTotalHitNumStats (rmap.c:1086-1094)
   rd.nhit_tot = inf0.nhit_tot + inf1.nhit_tot;
   rd.reached_stats = 1;
-  // windows of the selected candidates: errors end the read (rmap.c:669-671), bins of the K2 launches
-  unsigned int nbin[BLK_K2_BINS];
-  for (int b = 0; b < BLK_K2_BINS; ++b) nbin[b] = 0;
+  // ---- phase 4: windows of the selected candidates (errors end the read, rmap.c:669-671), K2 launch bins ----
+  // (two passes: the bins are only counted for reads all of whose windows are valid)
   unsigned int multi = 0;
   unsigned long long cells = 0;
-  for (uint32_t c = 0; c < nk; ++c) {
-    Offsets o;
-    const int e = cand_offsets(o, cand[sidx[c]], qlen, ktup, nskip, a.seq_offs, a.nseq, a.prm.termchar != 0);
-    if (e) { rd.errcode = e; break; }
-    const uint32_t reflen = (uint32_t)(o.re - o.rs + 1u);
-    if (simd_pred(qlen, o)) {
-      ++nbin[k2_bin(a, qlen, reflen)];
-      if (qlen > 256u && reflen > multi) multi = reflen;
-      cells += (unsigned long long)qlen * reflen;
-    } else {
-      ++nbin[17];
+  for (int pass = 0; pass < 2 && !rd.errcode; ++pass)
+    for (uint32_t c0 = 0; c0 < nk; c0 += 32) {
+      const uint32_t c = c0 + lane;
+      int e = 0, bin = -1;
+      if (c < nk) {
+        Offsets o;
+        const uint32_t ix = sort_smem ? wi[c] : sidx[c];
+        e = cand_offsets(o, a.cand[base + ix], qlen, ktup, nskip, a.seq_offs, a.nseq, a.prm.termchar != 0);
+        if (!e && pass) {
+          const uint32_t reflen = (uint32_t)(o.re - o.rs + 1u);
+          if (simd_pred(qlen, o)) {
+            bin = k2_bin(a, qlen, reflen);
+            if (qlen > 256u && reflen > multi) multi = reflen;
+            cells += (unsigned long long)qlen * reflen;
+          } else {
+            bin = 17;
+          }
+        }
+      }
+      if (!pass) {
+        const unsigned bad = __ballot_sync(FULL, e != 0);
+        if (bad) { rd.errcode = __shfl_sync(FULL, e, __ffs(bad) - 1); break; }
+      } else {   // one atomic per warp and bin
+        const unsigned peers = __match_any_sync(FULL, bin);
+        if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&a.cnt->k2_hist[bin], (unsigned int)__popc(peers));
+      }
     }
+  if (rd.errcode) { if (lane == 0) a.rd[j] = rd; return; }   // (no candidates: the wave driver drops them too)
+  for (int o = 16; o > 0; o >>= 1) {
+    cells += __shfl_xor_sync(FULL, cells, o);
+    multi = max(multi, __shfl_xor_sync(FULL, multi, o));
   }
-  if (rd.errcode) { a.rd[j] = rd; return; }   // (no candidates: the wave driver drops them too)
-  rd.ncand = nk;
-  a.n_sort[j] = nk;
-  for (int b = 1; b < BLK_K2_BINS; ++b)
-    if (nbin[b]) atomicAdd(&a.cnt->k2_hist[b], nbin[b]);
-  if (multi) atomicMax(&a.cnt->max_rlen_multi, multi);
-  if (cells) atomicAdd(&a.cnt->k2_cells, cells);
-  a.rd[j] = rd;
+  if (lane == 0) {
+    rd.ncand = nk;
+    a.n_sort[j] = nk;
+    if (multi) atomicMax(&a.cnt->max_rlen_multi, multi);
+    if (cells) atomicAdd(&a.cnt->k2_cells, cells);
+    a.rd[j] = rd;
+  }
 }
 
 // ------------------------------------------------------------------------------------
@@ -721,7 +844,7 @@ cudaError_t launch_block_reqs(const BlockArgs &a, cudaStream_t st, int *nlaunch)
 }
 cudaError_t launch_block_cands(const BlockArgs &a, cudaStream_t st, int *nlaunch) {
   if (a.njobs <= 0) return cudaSuccess;
-  block_cands_kernel<<<(a.njobs + 63) / 64, 64, 0, st>>>(a);
+  block_cands_kernel<<<(a.njobs + CW_WARPS - 1) / CW_WARPS, CW_WARPS * 32, 0, st>>>(a);
   ++*nlaunch;
   return cudaGetLastError();
 }

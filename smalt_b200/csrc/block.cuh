@@ -62,12 +62,13 @@ struct BlockArgs {
   const uint64_t *hit_off;          // [nreq + 1]
   const uint64_t *sqdat;
   const int32_t *req_err;
+  uint32_t *req_ncand;              // [nreq] candidates of every list
   // candidate scratch (indexed by hit offset of the job)
   uint64_t *sd_sqo; int32_t *sd_len;                      // seeds of the current hit region
   uint32_t *sg_ix; int32_t *sg_nseed; uint32_t *sg_cover; // segments of the current hit region
   SegCand *cand;
   uint32_t *sort_key, *sort_idx;
-  uint32_t *mask; uint32_t mask_words;                    // coverage mask, mask_words per job
+  uint32_t *mask; uint32_t mask_words;                    // coverage masks in HBM: 32 per job, mask_words each
   // per job
   smb_block_read *rd;
   uint32_t *n_sort;                 // [njobs]  (scanned into cand_first)

@@ -196,9 +196,48 @@ scan1_apply(const uint32_t *__restrict__ in, int n, const unsigned long long *__
   if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) out[n] = o;
 }
 
+// the same scan for short arrays in ONE launch: one CTA, every thread sums a run of consecutive items,
+// the thread sums are scanned through the warps (a block of reads has a few thousand jobs / requests)
+constexpr int SCAN1_SMALL_THREADS = 1024;
+constexpr int SCAN1_SMALL_MAX = SCAN1_SMALL_THREADS * 32;
+__global__ void __launch_bounds__(SCAN1_SMALL_THREADS)
+scan1_small(const uint32_t *__restrict__ in, int n, unsigned long long *__restrict__ out) {
+  __shared__ unsigned long long s_warp[32];
+  const int per = (n + SCAN1_SMALL_THREADS - 1) / SCAN1_SMALL_THREADS;
+  const int b = threadIdx.x * per, e = min(n, b + per);
+  unsigned long long a = 0;
+  for (int i = b; i < e; ++i) a += in[i];
+  unsigned long long incl = a;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    const unsigned long long v = s_warp[lane];
+    unsigned long long iw = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, iw, o);
+      if (lane >= o) iw += t;
+    }
+    s_warp[lane] = iw - v;   // exclusive over the warps
+  }
+  __syncthreads();
+  unsigned long long run = s_warp[w] + incl - a;
+  for (int i = b; i < e; ++i) { out[i] = run; run += in[i]; }
+  if (threadIdx.x == SCAN1_SMALL_THREADS - 1) out[n] = run;
+}
+
 // out has n + 1 entries (out[n] = total); tile: compact_tiles(n) scratch words
 cudaError_t launch_scan_counts(const uint32_t *in, int n, unsigned long long *out, unsigned long long *tile,
                                cudaStream_t st, int *nlaunch) {
+  if (n <= SCAN1_SMALL_MAX) {
+    scan1_small<<<1, SCAN1_SMALL_THREADS, 0, st>>>(in, n, out);
+    *nlaunch += 1;
+    return cudaGetLastError();
+  }
   const int ntiles = compact_tiles(n);
   scan1_tiles<<<ntiles, SCAN_THREADS, 0, st>>>(in, n, tile);
   scan1_top<<<1, 32, 0, st>>>(tile, ntiles);

@@ -53,6 +53,8 @@ struct HostBuf {  // grow-only pinned host staging buffer
   template <class T> T *as() const { return (T *)p; }
 };
 
+constexpr int SMB_BLK_EVENTS = 48;   // event pairs of the timed spans of a block (api_block.cu)
+
 struct smb_ctx {
   int device = 0;
   int sm_count = 148;
@@ -87,7 +89,7 @@ struct smb_ctx {
   const uint64_t *d_seq_offs = nullptr;
   // resident block pipeline (api_block.cu)
   DevBuf blk_jobs, blk_scr, blk_cand, blk_k3;
-  cudaEvent_t blk_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t blk_ev[SMB_BLK_EVENTS] = {};
   struct BlockState *blk = nullptr;
   float last_ms = 0.f;
   int last_launches = 0;

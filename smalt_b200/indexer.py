@@ -161,16 +161,18 @@ def kmer_grid(seqs, k, nskip):
     return grid, tuplectr
 
 
-def build_index_gpu(ctx, seqs, k=13, nskip=6, upload=True):
-    """build_index on the GPU (csrc/index_build.cu through smb_index_build): same dict, same bytes."""
+def build_index_gpu(ctx, seqs, k=13, nskip=6, upload=True, words=None):
+    """build_index on the GPU (csrc/index_build.cu through smb_index_build): same dict, same bytes.
+    words: the 3-bit packed set (pack3 of all sequences + one terminator) if the caller has it already."""
     from .seqpack import pack3
     totlen = int(sum(len(s) for s in seqs))
     typ, nbits_key, nbits_lo = select_hash_type(k, nskip, totlen)
     grid, tuplectr = kmer_grid(seqs, k, nskip)
     if upload:
-        allc = np.concatenate([np.asarray(s, np.uint8) & 7 for s in seqs] + [np.array([7], np.uint8)])
+        if words is None:
+            words = pack3(np.concatenate([np.asarray(s, np.uint8) & 7 for s in seqs] + [np.array([7], np.uint8)]))
         offs = np.concatenate([[0], np.cumsum([len(s) for s in seqs])]).astype(np.uint64)
-        ctx.refseq_upload(pack3(allc), totlen, offs)
+        ctx.refseq_upload(words, totlen, offs)
     r = ctx.index_build(k, nskip, typ, nbits_key if typ else 2 * k, nbits_lo, grid)
     maxpos = tuplectr - 1 if tuplectr > 0 else 0
     return dict(typ=typ, wordlen=k, nskip=nskip, nbits_key=nbits_key if typ else 2 * k, nbits_lo=nbits_lo if typ else 0,
@@ -208,14 +210,14 @@ def write_smi(prefix, ix):
             f.write(ix["posidx"].astype("<u4").tobytes())
 
 
-def write_sma(prefix, names, seqs, flags=2):
+def write_sma(prefix, names, seqs, flags=2, words=None):
     """sequence.c:2448-2519; the sequences are stored back to back (no terminators between
     them with the driver's default flags), one terminator code at the very end."""
     nseq = len(seqs)
     nam = b"".join(n.encode() + b"\0" for n in names)
-    allc = np.concatenate([np.asarray(s, np.uint8) & 7 for s in seqs])
-    seqsiz = len(allc)
-    words = pack3(np.concatenate([allc, np.array([7], np.uint8)]))
+    seqsiz = int(sum(len(s) for s in seqs))
+    if words is None:
+        words = pack3(np.concatenate([np.asarray(s, np.uint8) & 7 for s in seqs] + [np.array([7], np.uint8)]))
     assert len(words) == seqsiz // 10 + 1
     hd = np.array([nseq & 0xFFFFFFFF, nseq >> 32, len(nam) & 0xFFFFFFFF, len(nam) >> 32,
                    seqsiz & 0xFFFFFFFF, seqsiz >> 32, flags, 0], "<u4")

@@ -12,11 +12,16 @@ def pack3(codes):
     codes = np.asarray(codes, np.uint8)
     n = len(codes)
     nw = (n + 9) // 10
-    padded = np.zeros(nw * 10, np.uint32)
-    padded[:n] = codes & 7
-    padded = padded.reshape(nw, 10)
+    out = np.empty(nw, np.uint32)
     shifts = (3 * (9 - np.arange(10))).astype(np.uint32)
-    return (padded << shifts).sum(axis=1, dtype=np.uint64).astype(np.uint32)
+    CH = 1 << 23                       # words per slice: human-scale sets without tens of GB of temporaries
+    for w0 in range(0, nw, CH):
+        w1 = min(nw, w0 + CH)
+        part = codes[10 * w0:min(n, 10 * w1)]
+        padded = np.zeros((w1 - w0) * 10, np.uint32)
+        padded[:len(part)] = part & 7
+        out[w0:w1] = (padded.reshape(w1 - w0, 10) << shifts).sum(axis=1, dtype=np.uint32)
+    return out
 
 
 def unpack3(words, n):

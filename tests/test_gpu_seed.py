@@ -105,7 +105,7 @@ def test_hits_batch_vs_oracle(ctx, k, nskip, kind):
                     req[n]["read"], req[n]["nhit_max"], req[n]["strand"], req[n]["use_short"] = r, nhit_max, s, 1
                     n += 1
         sq, first, errs = ctx.hits_batch(req, nhits_alloc=32768)
-        assert ctx.last_kernel_launches == 5      # COUNT, 3-phase device scan of the list sizes, FILL
+        assert ctx.last_kernel_launches in (3, 5)   # COUNT, device scan of the list sizes (one launch for short arrays, else three), FILL
         n = 0
         big = 0
         for r, rd in enumerate(reads):
