@@ -359,11 +359,21 @@ def reference_rate(wl, n, threads, hist, tag="ref"):
 
 
 def sample_histogram(wl, exe, threads, device=None, skip=100):
-    """insert-size estimation: `smalt sample` on every skip-th pair -> histogram file for `map -g`
-    (smalt.c:838-878, :1288, :1397; insert.c)"""
+    """insert-size estimation: `smalt sample` on every skip-th pair (pairs 0, skip, 2 skip, ... - the pairs
+    insIsInSample picks with a sampling interval of `skip`, insert.c:215-218) -> histogram file for `map -g`
+    (smalt.c:838-878, :1288, :1397; insert.c).  The sampled pairs are cut out of the input first, so that the
+    program does not read the other 99 %."""
+    from smalt_b200.shard import every_nth_record
     out = os.path.join(wl.tmp, "insert_%s.hist" % os.path.basename(exe))
+    sub = []
+    for i, t in enumerate(wl.texts):
+        f = os.path.join(wl.tmp, "sampled_%d.fq" % (i + 1))
+        if not os.path.exists(f):
+            with open(f, "wb") as fh:
+                fh.write(every_nth_record(t, skip))
+        sub.append(f)
     env = dict(os.environ, SMALT_B200_DEVICE=str(device)) if device is not None else None
-    dt, err = run_program(exe, ["sample", "-u", str(skip), "-n", str(threads), "-o", out, wl.pref] + wl.files, env=env)
+    dt, err = run_program(exe, ["sample", "-u", "1", "-n", str(threads), "-o", out, wl.pref] + sub, env=env)
     return (out, dt, None) if dt is not None else (None, None, err)
 
 

@@ -30,7 +30,7 @@ int smb_device_warmup(int device) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return SMB_ERR_NODEVICE;
   if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) return SMB_ERR_CUDA;
-  if (warm_sw() != cudaSuccess || warm_band() != cudaSuccess || warm_band_warp() != cudaSuccess || warm_band_wide() != cudaSuccess || warm_band_pack() != cudaSuccess ||
+  if (warm_sw() != cudaSuccess || warm_band() != cudaSuccess || warm_band_warp() != cudaSuccess || warm_band_wide() != cudaSuccess || warm_band_long() != cudaSuccess || warm_band_pack() != cudaSuccess ||
       warm_seed() != cudaSuccess ||
       warm_compact() != cudaSuccess || warm_block() != cudaSuccess)
     return SMB_ERR_CUDA;
@@ -300,15 +300,8 @@ static int band_align_pass(smb_ctx *ctx, const smb_band_task *tasks, const std::
   for (int i = 0; i < n; ++i) {
     const smb_band_task &t = tasks[idx[(size_t)i]];
     sub[(size_t)i] = t;
-    Band b;
-    uint64_t words = 2;
-    if (!band_init(b, t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
-                   (int)t.ref_len)) {
-      const int bw0 = t.r_edge - t.l_edge + 1;
-      int w = (bw0 <= 0) ? (b.q_len - b.q_left) : bw0;
-      if (w < 1) w = 1;
-      words = ((uint64_t)w * (uint64_t)t.ref_len) / 16u + 4u;
-    }
+    const uint64_t words = band_dir_words(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
+                                          (int)t.ref_len);
     dir_off[(size_t)i + 1] = dir_off[(size_t)i] + words;
     const uint32_t cap = (uint32_t)diff_scale * (t.read_len + t.ref_len + 64u);
     diff_cap[(size_t)i] = cap;
@@ -384,19 +377,8 @@ static int band_align_fast(smb_ctx *ctx, const smb_band_task *tasks, int ntasks,
   dir_off[0] = diff_off[0] = 0;
   for (int i = 0; i < n; ++i) {
     const smb_band_task &t = tasks[i];
-    Band b;
-    uint64_t words = 2;
-    if (!band_warp_eligible(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
-                            (int)t.ref_len) &&
-        !band_wide_eligible(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
-                            (int)t.ref_len) &&
-        !band_init(b, t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
-                   (int)t.ref_len)) {
-      const int bw0 = t.r_edge - t.l_edge + 1;
-      int w = (bw0 <= 0) ? (b.q_len - b.q_left) : bw0;
-      if (w < 1) w = 1;
-      words = ((uint64_t)w * (uint64_t)t.ref_len) / 16u + 4u;
-    }
+    const uint64_t words = band_dir_words(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
+                                          (int)t.ref_len);
     dir_off[i + 1] = dir_off[i] + words;
     // final DiffStr area: one byte per aligned column at most, plus slack for several results
     const uint32_t cap = t.read_len + t.ref_len + 64u;
@@ -526,8 +508,8 @@ int band_align_multipass(smb_ctx *ctx, const smb_band_task *tasks, int ntasks, s
       uint64_t words = 0;
       while (pos < todo.size()) {
         const smb_band_task &t = tasks[todo[pos]];
-        const int bw0 = t.r_edge - t.l_edge + 1;
-        const uint64_t w = (uint64_t)(bw0 <= 0 ? t.read_len : (uint32_t)bw0) * t.ref_len / 16u + 4u;
+        const uint64_t w = band_dir_words(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
+                                          (int)t.ref_len);
         if (!chunk.empty() && words + w > DIR_WORDS_MAX) break;
         words += w;
         chunk.push_back(todo[pos++]);

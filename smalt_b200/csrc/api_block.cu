@@ -366,8 +366,10 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
     unsigned int pos = 0;
     for (int b = 0; b < BLK_K3_BINS; ++b) { a.k3_start[b] = pos; pos += h_cnt->k3_hist[b]; }
     if (pos != nk3) return fail(ctx, SMB_ERRCODE_ASSERT, "block: alignment classes do not add up");
-    for (int b = 0; b < BAND_CLS_PACK8; ++b)
+    for (int b = 0; b < BAND_CLS_THREAD_END; ++b)
       if (h_cnt->k3_hist[b]) plan.classes.push_back(BandPlan::Class{32 << b, (int)a.k3_start[b], (int)h_cnt->k3_hist[b]});
+    plan.long16_start = (int)a.k3_start[BAND_CLS_LONG16]; plan.long16_count = (int)h_cnt->k3_hist[BAND_CLS_LONG16];
+    plan.long32_start = (int)a.k3_start[BAND_CLS_LONG32]; plan.long32_count = (int)h_cnt->k3_hist[BAND_CLS_LONG32];
     plan.wide_start = (int)a.k3_start[BAND_CLS_WIDE]; plan.wide_count = (int)h_cnt->k3_hist[BAND_CLS_WIDE];
     plan.pack_start = (int)a.k3_start[BAND_CLS_PACK]; plan.pack_count = (int)h_cnt->k3_hist[BAND_CLS_PACK];
     plan.half_start = (int)a.k3_start[BAND_CLS_HALF]; plan.half_count = (int)h_cnt->k3_hist[BAND_CLS_HALF];

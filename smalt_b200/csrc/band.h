@@ -121,8 +121,25 @@ SMB_HD int band_ring_class(int need) {
   while ((32 << c) < wcap) ++c;
   return c;
 }
-// pseudo classes of the warp kernels (last in BandPlan.order)
-constexpr int BAND_CLS_WARP = 31, BAND_CLS_HALF = 30, BAND_CLS_PACK = 29, BAND_CLS_WIDE = 28, BAND_CLS_PACK8 = 27;
+// pseudo classes of the warp / CTA kernels (last in BandPlan.order)
+constexpr int BAND_CLS_WARP = 31, BAND_CLS_HALF = 30, BAND_CLS_PACK = 29, BAND_CLS_WIDE = 28, BAND_CLS_PACK8 = 27,
+              BAND_CLS_LONG16 = 26, BAND_CLS_LONG32 = 25;
+constexpr int BAND_CLS_THREAD_END = 25;   // classes below: thread-per-task launches by ring capacity
+// band_long_kernel<D> (band_long.cu): one CTA of BAND_LONG_THREADS threads per task, D diagonals per thread
+constexpr int BAND_LONG_THREADS = 128;
+constexpr int BAND_LONG_MAXDIM = 1 << 20;   // rows / columns (21-bit fields of the maximum key)
+// 0: not a task of band_long_kernel, else the diagonals per thread (16 or 32)
+SMB_HD int band_long_dpt(int l_edge, int r_edge, int p_left, int p_right, int read_len, int u_left, int u_right,
+                         int ref_len) {
+  if (ref_len > BAND_LONG_MAXDIM || read_len > BAND_LONG_MAXDIM || ref_len < 1 || read_len < 1) return 0;
+  Band b;
+  if (band_init(b, l_edge, r_edge, p_left, p_right, read_len, u_left, u_right, ref_len)) return 0;
+  const int bw0 = r_edge - l_edge + 1;
+  const int bw = (bw0 <= 0) ? (b.q_len - b.q_left) : bw0;     // bound of every DP pass of the task
+  if (bw <= 16 * BAND_LONG_THREADS) return 16;
+  if (bw <= 32 * BAND_LONG_THREADS) return 32;
+  return 0;
+}
 // direction words a task needs in the HBM strip of band_kernel<true> (2 for the warp kernels)
 SMB_HD unsigned long long band_dir_words(int l_edge, int r_edge, int p_left, int p_right, int read_len, int u_left,
                                          int u_right, int ref_len) {
@@ -131,6 +148,11 @@ SMB_HD unsigned long long band_dir_words(int l_edge, int r_edge, int p_left, int
       band_wide_eligible(l_edge, r_edge, p_left, p_right, read_len, u_left, u_right, ref_len) ||
       band_init(b, l_edge, r_edge, p_left, p_right, read_len, u_left, u_right, ref_len))
     return 2;
+  {   // band_long_kernel: one unit of dpt / 16 words per thread and iteration, rows + threads iterations
+    const int dpt = band_long_dpt(l_edge, r_edge, p_left, p_right, read_len, u_left, u_right, ref_len);
+    if (dpt)
+      return ((unsigned long long)ref_len + BAND_LONG_THREADS) * BAND_LONG_THREADS * (unsigned long long)(dpt / 16) + 8u;
+  }
   const int bw0 = r_edge - l_edge + 1;
   int w = (bw0 <= 0) ? (b.q_len - b.q_left) : bw0;
   if (w < 1) w = 1;

@@ -342,6 +342,9 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, const Scori
                band_wide_eligible(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
                                   (int)t.ref_len)) {
       wc[(size_t)i] = WIDE_CLS;
+    } else if (const int dpt = align ? band_long_dpt(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
+                                                     (int)t.ref_len) : 0) {
+      wc[(size_t)i] = dpt == 16 ? BAND_CLS_LONG16 : BAND_CLS_LONG32;
     } else {
       wc[(size_t)i] = band_ring_class(band_ring_need(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left,
                                                       t.u_right, (int)t.ref_len, !align));
@@ -354,8 +357,12 @@ void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, const Scori
   int fill[32];
   for (int c = 0; c < 32; ++c) fill[c] = start[c];
   for (int i = 0; i < ntasks; ++i) plan.order[(size_t)fill[wc[(size_t)i]]++] = i;
-  for (int c = 0; c < PACK8_CLS; ++c)
+  for (int c = 0; c < BAND_CLS_THREAD_END; ++c)
     if (count[c]) plan.classes.push_back(BandPlan::Class{32 << c, start[c], count[c]});
+  plan.long16_start = start[BAND_CLS_LONG16];
+  plan.long16_count = count[BAND_CLS_LONG16];
+  plan.long32_start = start[BAND_CLS_LONG32];
+  plan.long32_count = count[BAND_CLS_LONG32];
   plan.wide_start = start[WIDE_CLS];
   plan.wide_count = count[WIDE_CLS];
   plan.pack8_start = start[PACK8_CLS];
@@ -382,7 +389,7 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
   // the packed kernels take (nearly) all tasks of a short-read batch; whatever else the batch holds goes
   // to the side stream
   const bool packed_any = align && (plan.pack_count || plan.pack8_count);
-  const bool other_any = !plan.classes.empty() || (align && (plan.wide_count || plan.half_count || plan.warp_count));
+  const bool other_any = !plan.classes.empty() || (align && (plan.wide_count || plan.half_count || plan.warp_count || plan.long16_count || plan.long32_count));
   static const bool no_side = getenv("SMB_NO_SIDE") != nullptr;
   const bool fork = side && side->stream && packed_any && other_any && !no_side;
   cudaStream_t st = main_st;
@@ -408,6 +415,14 @@ cudaError_t launch_band(const Scoring &sc, const SeqSrc &src, const smb_band_tas
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     ++*nlaunch;
   }
+  if (align && plan.long32_count &&
+      (e = launch_band_long(sc, src, d_tasks, d_order + plan.long32_start, plan.long32_count, 32, d_ticket + 5, out, max_res,
+                            d_dir_off, d_dirs, d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)
+    return e;
+  if (align && plan.long16_count &&
+      (e = launch_band_long(sc, src, d_tasks, d_order + plan.long16_start, plan.long16_count, 16, d_ticket + 6, out, max_res,
+                            d_dir_off, d_dirs, d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)
+    return e;
   if (align && plan.wide_count &&
       (e = launch_band_wide(sc, src, d_tasks, d_order + plan.wide_start, plan.wide_count, d_ticket + 3, out, max_res,
                             d_diff_off, d_diff_cap, sm_count, st, nlaunch)) != cudaSuccess)

@@ -685,6 +685,10 @@ __device__ __forceinline__ int k3_class(const BlockArgs &a, const smb_band_task 
   if (wl) return wl == 16 ? BAND_CLS_HALF : BAND_CLS_WARP;
   if (band_wide_eligible(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right, (int)t.ref_len))
     return BAND_CLS_WIDE;
+  {
+    const int dpt = band_long_dpt(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right, (int)t.ref_len);
+    if (dpt) return dpt == 16 ? BAND_CLS_LONG16 : BAND_CLS_LONG32;
+  }
   return band_ring_class(band_ring_need(t.l_edge, t.r_edge, t.p_left, t.p_right, (int)t.read_len, t.u_left, t.u_right,
                                         (int)t.ref_len, false));
 }

@@ -112,6 +112,7 @@ struct BandPlan {
   int pack_start = 0, pack_count = 0, pack_maxrows = 0, pack_maxread = 0;   // band_pack_kernel<16, 2> (four tasks per warp, s16x2)
   int pack8_start = 0, pack8_count = 0, pack8_maxrows = 0, pack8_maxread = 0;   // band_pack_kernel<8, 3> (eight tasks per warp)
   int wide_start = 0, wide_count = 0;   // band_wide_kernel (band_wide.cu: bands <= 128 diagonals, windows <= 512 rows)
+  int long16_start = 0, long16_count = 0, long32_start = 0, long32_count = 0;   // band_long_kernel<16 | 32> (band_long.cu)
 };
 void plan_band(const smb_band_task *h_tasks, int ntasks, bool align, const Scoring &sc, BandPlan &plan);
 size_t band_gring_words(const BandPlan &plan);
@@ -138,6 +139,11 @@ cudaError_t launch_band_wide(const Scoring &sc, const SeqSrc &src, const smb_ban
                              const uint64_t *d_diff_off, const uint32_t *d_diff_cap, int sm_count,
                              cudaStream_t st, int *nlaunch);
 cudaError_t warm_band_wide();
+cudaError_t launch_band_long(const Scoring &sc, const SeqSrc &src, const smb_band_task *d_tasks, const int *d_order,
+                             int ntasks, int dpt, int *d_ticket, BandOut out, int max_res, const uint64_t *d_dir_off,
+                             uint32_t *d_dirs, const uint64_t *d_diff_off, const uint32_t *d_diff_cap, int sm_count,
+                             cudaStream_t st, int *nlaunch);
+cudaError_t warm_band_long();
 cudaError_t launch_band_pack(const Scoring &sc, const SeqSrc &src, const smb_band_task *d_tasks,
                              const int *d_order, int ntasks, int lanes, int max_rows, int max_read, int *d_ticket, BandOut out, int max_res,
                              const uint64_t *d_diff_off, const uint32_t *d_diff_cap, int sm_count,

@@ -374,6 +374,57 @@ def test_band_align_wide_kernel_geometry(ctx, orc):
     assert nmulti > 5
 
 
+def test_band_align_long_kernel_geometry(ctx, orc):
+    """Geometries of the CTA-per-task long-read kernel (band_long.cu): bands of 129..4096 diagonals (16 or 32
+    per thread; beyond: thread-per-task kernel), windows of 513..4000 rows, reads of up to 4000 bases with
+    indel-rich errors, several local alignments per window (recursion), sub-ranges of read and window."""
+    from seqgen import mutate
+    rng = np.random.default_rng(107)
+    pairs, args = [], []
+    for rows, bw in ((600, 129), (513, 300), (700, 64), (1500, 700), (2000, 2047), (2000, 2048), (2100, 2049),
+                     (1800, 3000), (2600, 4096), (1000, 4097), (3000, 1500), (4000, 900), (900, 130), (520, 2500)):
+        qlen = int(rng.integers(rows // 2, rows - 20))
+        rd = random_seq(rng, qlen)
+        off = int(rng.integers(0, max(1, rows - qlen)))
+        win = random_seq(rng, rows)
+        m = mutate(rng, rd.copy(), p_sub=0.03, p_ins=0.04, p_del=0.04)[:rows - off]
+        win[off:off + len(m)] = m
+        if (rows + bw) % 3 == 0:          # two separate pieces: several results, recursion left/right
+            cut = len(m) // 2
+            win[off + cut:off + cut + 40] = random_seq(rng, min(40, rows - off - cut))
+        if (rows + bw) % 5 == 0:
+            win[int(rng.integers(0, rows))] = 5
+            rd[int(rng.integers(0, qlen))] = 5
+        pairs.append((rd, win))
+        l = -off - bw // 2 + int(rng.integers(-6, 7))
+        if rows == 3000:                  # sub-ranges of the read segment and of the window
+            args.append((l, l + bw - 1, 50, qlen - 80, 30, rows - 100))
+        else:
+            args.append((l, l + bw - 1, 0, qlen - 1, 0, rows - 1))
+    minscore = [int(x) for x in rng.integers(20, 60, len(pairs))]
+    minscorlen = [int(x) for x in rng.integers(10, 40, len(pairs))]
+    arena, offs = _arena(pairs)
+    ctx.arena_upload(arena)
+    nmulti = 0
+    for sel in (slice(None), slice(3, 4)):
+        idx = list(range(len(pairs)))[sel]
+        sub_pairs = [pairs[i] for i in idx]
+        sub_offs = np.concatenate([[offs[2 * i], offs[2 * i + 1]] for i in idx] + [[0]])
+        t = _band_tasks(sub_pairs, sub_offs, [args[i] for i in idx], [minscore[i] for i in idx],
+                        [minscorlen[i] for i in idx])
+        res, first, diff, errs, cells = ctx.band_align(t)
+        ocells = 0
+        for k, i in enumerate(idx):
+            rd, win = pairs[i]
+            e, want, c = orc.band_align(rd, win, *args[i], minscore[i], minscorlen[i])
+            ocells += c
+            assert int(errs[k]) == e, (i, args[i])
+            assert _unpack(res, first, diff, k) == want, (i, len(rd), len(win), args[i], minscore[i], minscorlen[i])
+            nmulti += len(want) > 1
+        assert cells == ocells
+    assert nmulti >= 2
+
+
 @pytest.mark.parametrize("pen", [(2, -1, -1, -1), (1, -3, -9, -1), (3, -2, -5, -4), (1, -1, -2, 0)])
 def test_dp_kernels_other_penalties(pen):
     """K2 and K3 under other penalty sets than the default (match, mismatch, gap open, gap extension):
