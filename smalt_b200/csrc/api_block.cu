@@ -246,6 +246,7 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
   unsigned int nsw = 0;
   for (int b = 0; b < BLK_K2_BINS; ++b) a.k2_start[b] = 0;
   for (int b = 1; b <= 16; ++b) { a.k2_start[b] = nsw; nsw += h_cnt->k2_hist[b]; }
+  a.k2_start[18] = nsw; nsw += h_cnt->k2_hist[18];   // long reads, paired
   const unsigned int nbf = h_cnt->k2_hist[17];
   if ((size_t)nsw + nbf != ncand) return fail(ctx, SMB_ERRCODE_ASSERT, "block: candidate classes do not add up");
   {
@@ -267,6 +268,8 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
   if (nsw) {
     SwPlan plan;
     for (int c = 0; c <= 16; ++c) { plan.count[c] = c ? (int)h_cnt->k2_hist[c] : 0; plan.start[c] = (int)a.k2_start[c]; }
+    plan.count[SW_SLOT_LONG2] = (int)h_cnt->k2_hist[18];
+    plan.start[SW_SLOT_LONG2] = (int)a.k2_start[18];
     plan.max_grid = ctx->sm_count * 8;
     plan.bstride = (h_cnt->max_rlen_multi + 31u) & ~31u;
     plan.strip_bytes = (size_t)plan.max_grid * 4u * 2u * plan.bstride * sizeof(int2);   // SW_WARPS = 4 (sw_score.cu)

@@ -307,7 +307,9 @@ __device__ __forceinline__ bool pen16_k2(const BlockArgs &a) {   // plan_sw (sw_
 __device__ __forceinline__ int k2_bin(const BlockArgs &a, uint32_t qlen, uint32_t reflen) {
   int c = (int)((qlen + 31u) / 32u);
   c = c < 1 ? 1 : (c > 8 ? 8 : c);
-  const bool pair16 = pen16_k2(a) && qlen <= 256u && reflen <= (uint32_t)SW2_MAXROWS_ && (long long)qlen * a.match <= 16000;
+  const bool fits16 = pen16_k2(a) && (long long)qlen * a.match <= 16000;
+  if (fits16 && qlen > 256u) return 18;   // long reads, paired (sw_long2_kernel)
+  const bool pair16 = fits16 && qlen <= 256u && reflen <= (uint32_t)SW2_MAXROWS_;
   return pair16 ? c + 8 : c;
 }
 __device__ __forceinline__ bool simd_pred(uint32_t qlen, const Offsets &o) {   // rmap.c:715-718

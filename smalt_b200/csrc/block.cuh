@@ -28,7 +28,7 @@ struct DCand {
 };
 static_assert(sizeof(DCand) == 48, "layout");
 
-constexpr int BLK_K2_BINS = 20;   // [1..8] 32-bit classes, [9..16] paired 16-bit classes, [17] band-fast tasks
+constexpr int BLK_K2_BINS = 20;   // [1..8] 32-bit classes, [9..16] paired 16-bit classes, [17] band-fast tasks, [18] long reads paired
 constexpr int BLK_K3_BINS = 32;   // BandPlan classes (band.h)
 
 // counters of a block on the device (zeroed per block)

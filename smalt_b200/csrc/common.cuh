@@ -64,9 +64,10 @@ struct Timer {
 };
 
 // ---- K2 ----
+constexpr int SW_SLOT_LONG2 = 17, SW_SLOTS = 18;
 struct SwPlan {
   std::vector<int> order;   // task indices grouped by columns-per-lane class
-  int count[17], start[17]; // [1..8] 32-bit classes, [9..16] paired 16-bit classes
+  int count[SW_SLOTS], start[SW_SLOTS]; // [1..8] 32-bit classes, [9..16] paired 16-bit classes, [17] long reads paired
   int max_grid;
   uint32_t bstride;         // rows of the boundary strips (multi-block reads), 0 if none
   size_t strip_bytes;

@@ -355,6 +355,156 @@ sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restri
   }
 }
 
+// ------------------------------------------------------------------------------------
+// sw_long2_kernel: the packed recurrence of sw_score2_kernel for LONG reads (more columns than a warp
+// holds in registers): two tasks per warp in the 16-bit halves (scores <= qlen * match <= 16000), the
+// read cut into column blocks of 32 lanes x C columns, every block streaming all window rows through
+// the systolic array.  What a block's last column leaves for the next one - H and F of every row,
+// both tasks packed - goes through a strip in HBM / L2 (8 bytes per row, written and read 32 rows at a
+// time).  Window rows are staged in shared memory RCH steps at a time as PRMT selectors, with the
+// zero-scoring padding rows in front of and behind the window that let every lane compute in every
+// step (see sw_score2_kernel).  swSIMDAlignStriped (swsimd.c:868-933) on 5-10 kb reads: ~36 such tasks
+// per read with 7 * 10^7 cells each.
+// ------------------------------------------------------------------------------------
+constexpr int SWL_RCH = 512;     // steps per staged chunk of window rows
+
+template <int C>
+__global__ void __launch_bounds__(SW_WARPS * 32)
+sw_long2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restrict__ tasks,
+                const SwClassArgs cls, int32_t *__restrict__ scores, int32_t *__restrict__ errs,
+                uint2 *__restrict__ bscratch, const uint32_t bstride) {
+  __shared__ uint32_t s_row[SW_WARPS][SWL_RCH + 32];
+  __shared__ unsigned short s_raw[SW_WARPS][SWL_RCH + 32];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  uint32_t *const srow = s_row[threadIdx.x >> 5];
+  unsigned short *const sraw = s_raw[threadIdx.x >> 5];
+  const int gwarp = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
+  uint2 *const strip0 = bscratch + (size_t)gwarp * 2u * bstride;
+  const uint32_t nge2 = (uint32_t)((-sc.gap_ext) & 0xffff) * 0x10001u;
+  __shared__ uint32_t s_konst[2];
+  if (threadIdx.x == 0) {
+    s_konst[0] = (uint32_t)(sc.match & 0xff) | ((uint32_t)(sc.mismatch & 0xff) * 0x01010100u);
+    s_konst[1] = (uint32_t)(sc.gap_init & 0xffff) * 0x10001u;
+  }
+  __syncthreads();
+  const uint32_t T0 = ((volatile uint32_t *)s_konst)[0], gi2 = ((volatile uint32_t *)s_konst)[1];
+  const int npairs = (cls.ntasks + 1) >> 1;
+
+  for (;;) {
+    int k = 0;
+    if (lane == 0) k = atomicAdd(cls.counter, 1);
+    k = __shfl_sync(FULL, k, 0);
+    if (k >= npairs) break;
+    const int tixA = __ldg(cls.order + 2 * k);
+    const bool haveB = 2 * k + 1 < cls.ntasks;
+    const int tixB = haveB ? __ldg(cls.order + 2 * k + 1) : tixA;
+    const smb_sw_task ta = tasks[tixA], tb = tasks[tixB];
+    const int qlenA = (int)ta.read_len, qlenB = (int)tb.read_len;
+    const int rlenA = (int)ta.ref_len, rlenB = (int)tb.ref_len;
+    const int rlen = max(rlenA, rlenB), qlen = max(qlenA, qlenB);
+    const bool rcA = (ta.flags & SMB_TASK_READ_REVCOMP) != 0, rcB = (tb.flags & SMB_TASK_READ_REVCOMP) != 0;
+    const bool pkA = (ta.flags & SMB_TASK_REF_PACKED) != 0, pkB = (tb.flags & SMB_TASK_REF_PACKED) != 0;
+    const int nblk = (qlen + 32 * C - 1) / (32 * C);
+    const int nsteps = rlen + 31;
+    uint32_t best = gi2;
+    // X (the mismatch-against-everything code) anywhere in the reads or windows: per-cell table path
+    bool hasX = false;
+    for (int x = lane; x < max(rlen, qlen); x += 32) {
+      if (x < rlenA) hasX |= ref_base(src, pkA, ta.ref_off, (uint32_t)x) == 4u;
+      if (x < rlenB) hasX |= ref_base(src, pkB, tb.ref_off, (uint32_t)x) == 4u;
+      if (x < qlenA) hasX |= read_base(src.arena, ta.read_off, (uint32_t)qlenA, rcA, (uint32_t)x) == 4u;
+      if (x < qlenB) hasX |= read_base(src.arena, tb.read_off, (uint32_t)qlenB, rcB, (uint32_t)x) == 4u;
+    }
+    const bool general = __any_sync(FULL, hasX);
+
+    for (int b = 0; b < nblk; ++b) {
+      uint32_t qsel[C], qraw[C], H[C], E[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int j = b * 32 * C + lane * C + c;
+        const uint32_t qa = (j < qlenA) ? read_base(src.arena, ta.read_off, (uint32_t)qlenA, rcA, (uint32_t)j) : 7u;
+        const uint32_t qb = (j < qlenB) ? read_base(src.arena, tb.read_off, (uint32_t)qlenB, rcB, (uint32_t)j) : 7u;
+        const uint32_t ia = qa < 4u ? qa : 4u, ib = qb < 4u ? qb : 4u;
+        qsel[c] = (ia | ((ia | 8u) << 4) | (ib << 8) | ((ib | 8u) << 12)) ^ 0x4444u;
+        qraw[c] = qa | (qb << 8);
+        H[c] = gi2;
+        E[c] = gi2;
+      }
+      uint32_t hdiag = gi2, hout = gi2, fout = gi2;
+      uint2 bin = make_uint2(gi2, gi2), keep = make_uint2(gi2, gi2);
+      const uint2 *bin_strip = strip0 + (size_t)((b & 1) ^ 1) * bstride;
+      uint2 *bout_strip = strip0 + (size_t)(b & 1) * bstride;
+      const bool has_in = b > 0, has_out = b < nblk - 1;
+
+      for (int base = 0; base < nsteps; base += SWL_RCH) {
+        // rows base - 31 .. base + RCH - 1 of both windows as selectors (padding outside the windows)
+        __syncwarp();
+        for (int x = lane; x < SWL_RCH + 31; x += 32) {
+          const int i = base - 31 + x;
+          const uint32_t a = (i >= 0 && i < rlenA) ? ref_base(src, pkA, ta.ref_off, (uint32_t)i) : 7u;
+          const uint32_t bb = (i >= 0 && i < rlenB) ? ref_base(src, pkB, tb.ref_off, (uint32_t)i) : 7u;
+          sraw[x] = (unsigned short)(a | (bb << 8));
+          srow[x] = (a < 4u ? a * 0x11u : 0x00440000u) | (bb < 4u ? bb * 0x1100u : 0x44000000u);
+        }
+        __syncwarp();
+        const int tend = min(nsteps, base + SWL_RCH);
+        const uint32_t *rowp = srow + (31 - lane) - base;
+        const unsigned short *rawp = sraw + (31 - lane) - base;
+        for (int t = base; t < tend; ++t) {
+          if ((t & 31) == 0 && has_in) {
+            const int i = t + lane;
+            bin = (i < rlen) ? __ldcg(bin_strip + i) : make_uint2(gi2, gi2);
+          }
+          uint32_t hl = __shfl_up_sync(FULL, hout, 1);
+          uint32_t F = __shfl_up_sync(FULL, fout, 1);
+          if (has_in) {
+            const uint32_t hb = __shfl_sync(FULL, bin.x, t & 31), fb = __shfl_sync(FULL, bin.y, t & 31);
+            if (lane == 0) { hl = hb; F = fb; }
+          } else if (lane == 0) {
+            hl = gi2;
+            F = gi2;
+          }
+          uint32_t diag = hdiag;
+          hdiag = hl;
+          if (!general) {
+            const uint32_t w = rowp[t];
+            const uint32_t wm = w >> 16;
+            SW2_STEP(prmt(0u, T0, (qsel[c] ^ w) & ~wm));
+          } else {
+            const uint32_t r2 = (uint32_t)rawp[t];
+            const uint32_t ra = r2 & 0xffu, rb = r2 >> 8;
+            SW2_STEP((((uint32_t)(int)sc.S[ra * 8u + (qraw[c] & 0xffu)]) & 0xffffu) |
+                     ((uint32_t)(int)sc.S[rb * 8u + (qraw[c] >> 8)] << 16));
+          }
+          hout = H[C - 1];
+          fout = F;
+          if (has_out) {   // the block's last column (lane 31, row t - 31) for the next column block
+            const uint32_t ho = __shfl_sync(FULL, hout, 31), fo = __shfl_sync(FULL, fout, 31);
+            const int i31 = t - 31;
+            if (i31 >= 0) {
+              if (lane == (i31 & 31)) keep = make_uint2(ho, fo);
+              if ((i31 & 31) == 31 || i31 == rlen - 1) {
+                const int rb0 = i31 & ~31;
+                if (rb0 + lane <= i31) __stcg(bout_strip + rb0 + lane, keep);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    int bA = (int)(short)(best & 0xffffu) - sc.gap_init, bB = (int)(short)(best >> 16) - sc.gap_init;
+    bA = __reduce_max_sync(FULL, bA);
+    bB = __reduce_max_sync(FULL, bB);
+    if (lane == 0) {
+      scores[tixA] = bA;
+      errs[tixA] = SMB_OK;
+      if (haveB) { scores[tixB] = bB; errs[tixB] = SMB_OK; }
+    }
+  }
+}
+
 // C: columns per lane of the 32-lane form (ceil(qlen / 32)); the half-warp form owns 2C per lane
 template <int C>
 static cudaError_t launch_class2(const Scoring &sc, const SeqSrc &src, const smb_sw_task *d_tasks,
@@ -382,27 +532,32 @@ void plan_sw(const smb_sw_task *h_tasks, int ntasks, int sm_count, const Scoring
     return pen16 && t.read_len <= 32u * NCLS && t.ref_len <= (uint32_t)SW2_MAXROWS &&
            (long long)t.read_len * sc.match <= 16000;
   };
-  // slots 1..8: 32-bit classes, 9..16: paired 16-bit classes
-  for (int c = 0; c <= 2 * NCLS; ++c) plan.count[c] = plan.start[c] = 0;
+  // long reads in 16-bit pairs (sw_long2_kernel)
+  auto long16 = [&](const smb_sw_task &t) {
+    return pen16 && t.read_len > 32u * NCLS && (long long)t.read_len * sc.match <= 16000;
+  };
+  // slots 1..8: 32-bit classes, 9..16: paired 16-bit classes, 17: long reads, paired
+  auto slot_of = [&](const smb_sw_task &t) {
+    const int c = cls_of(t.read_len);
+    return long16(t) ? SW_SLOT_LONG2 : (pair16(t) ? c + NCLS : c);
+  };
+  for (int c = 0; c < SW_SLOTS; ++c) plan.count[c] = plan.start[c] = 0;
   for (int i = 0; i < ntasks; ++i) {
-    const int c = cls_of(h_tasks[i].read_len);
-    plan.count[pair16(h_tasks[i]) ? c + NCLS : c]++;
+    plan.count[slot_of(h_tasks[i])]++;
     if (h_tasks[i].read_len > 32u * NCLS) max_rlen_multi = std::max(max_rlen_multi, h_tasks[i].ref_len);
   }
-  for (int c = 1; c <= 2 * NCLS; ++c) plan.start[c] = plan.start[c - 1] + plan.count[c - 1];
-  int fill[2 * NCLS + 1];
-  for (int c = 0; c <= 2 * NCLS; ++c) fill[c] = plan.start[c];
-  for (int i = 0; i < ntasks; ++i) {
-    const int c = cls_of(h_tasks[i].read_len);
-    plan.order[(size_t)fill[pair16(h_tasks[i]) ? c + NCLS : c]++] = i;
-  }
-  // long reads first inside the multi-block class (largest tasks start earliest)
+  for (int c = 1; c < SW_SLOTS; ++c) plan.start[c] = plan.start[c - 1] + plan.count[c - 1];
+  int fill[SW_SLOTS];
+  for (int c = 0; c < SW_SLOTS; ++c) fill[c] = plan.start[c];
+  for (int i = 0; i < ntasks; ++i) plan.order[(size_t)fill[slot_of(h_tasks[i])]++] = i;
+  // long reads first inside the multi-block classes (largest tasks start earliest)
   if (max_rlen_multi)
-    std::stable_sort(plan.order.begin() + plan.start[NCLS], plan.order.begin() + plan.start[NCLS] + plan.count[NCLS],
-                     [&](int a, int b) {
-                       return (uint64_t)h_tasks[a].read_len * h_tasks[a].ref_len >
-                              (uint64_t)h_tasks[b].read_len * h_tasks[b].ref_len;
-                     });
+    for (const int c : {NCLS, (int)SW_SLOT_LONG2})
+      std::stable_sort(plan.order.begin() + plan.start[c], plan.order.begin() + plan.start[c] + plan.count[c],
+                       [&](int a, int b) {
+                         return (uint64_t)h_tasks[a].read_len * h_tasks[a].ref_len >
+                                (uint64_t)h_tasks[b].read_len * h_tasks[b].ref_len;
+                       });
   plan.max_grid = sm_count * 8;
   plan.bstride = (max_rlen_multi + 31u) & ~31u;
   plan.strip_bytes = (size_t)plan.max_grid * SW_WARPS * 2u * plan.bstride * sizeof(int2);
@@ -415,6 +570,15 @@ cudaError_t launch_sw_score(const Scoring &sc, const SeqSrc &src, const smb_sw_t
   constexpr int NCLS = 8;
   cudaError_t e;
   if ((e = cudaMemsetAsync(d_counters, 0, 32 * sizeof(int), st)) != cudaSuccess) return e;
+  if (plan.count[SW_SLOT_LONG2]) {    // long reads, two tasks per warp
+    const int n = plan.count[SW_SLOT_LONG2];
+    SwClassArgs cls{d_order + plan.start[SW_SLOT_LONG2], n, d_counters + SW_SLOT_LONG2};
+    int grid = ((n + 1) / 2 + SW_WARPS - 1) / SW_WARPS;
+    if (grid > plan.max_grid) grid = plan.max_grid;
+    sw_long2_kernel<16><<<grid, SW_WARPS * 32, 0, st>>>(sc, src, d_tasks, cls, d_scores, d_errs, (uint2 *)d_strips, plan.bstride);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    ++*nlaunch;
+  }
   for (int c = 1; c <= NCLS; ++c) {   // paired 16-bit classes
     const int n = plan.count[c + NCLS];
     if (!n) continue;
@@ -455,6 +619,11 @@ cudaError_t launch_sw_score(const Scoring &sc, const SeqSrc &src, const smb_sw_t
     ++*nlaunch;
   }
   return cudaSuccess;
+}
+
+cudaError_t warm_sw_long() {
+  cudaFuncAttributes a;
+  return cudaFuncGetAttributes(&a, sw_long2_kernel<16>);
 }
 
 cudaError_t warm_sw() {
