@@ -28,6 +28,13 @@
  *   smb_hits_batch        <- hashCollectHitsForSegment (hashhit.c:1691) / hashCollectHitsUsingCutoff
  *                            (:1593) + hashGetHitListData (:1867)
  * The reference-side binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Not covered (the reference's symbols on top of this ABI, hostc/shim_hot.c, print one message and
+ * fail with ERRCODE_ARGINVAL / a NULL constructor result instead of computing on the CPU):
+ *   map -w   complexity-weighted scores: scaleALICPLX (alignment.c:268-305) rescoring in floating point
+ *            inside aliSmiWatInBand
+ *   map -p   split reads: hashCollectHitInfo on a read segment (hashhit.c:987 with seq_start / seq_end)
+ *   HashHitFilter arguments of hashCollectHitsForSegment (no caller in the smalt driver passes one)
  */
 #ifndef SMALT_B200_H
 #define SMALT_B200_H

@@ -19,8 +19,9 @@ int smbShimIndexFetch(uint32_t *idx, uint32_t *pos, uint32_t *wordidx, uint32_t 
 
 /* hashTableSetUp (hashidx.c:829-998).  The index of a whole sequence set (`smalt index`) is
  * built on the GPU (csrc/index_build.cu) into the same arrays with the same allocation rules, so
- * that hashTableWrite produces the same `.smi` bytes; the on-the-fly index of a few intervals
- * (rmap.c:495-517), a box without a GPU and SMALT_B200_CPU_INDEX=1 use the reference's builder. */
+ * that hashTableWrite produces the same `.smi` bytes.  The on-the-fly k=5 index of a few intervals
+ * (rmap.c:495-517, ~12 KB per pair) is the reference's own builder, as is SMALT_B200_CPU_INDEX=1 (an
+ * explicit switch for comparing the two); without a CUDA device the call fails. */
 int hashTableSetUp(HashTable *htp, SeqFastq *sqbufp, const SeqSet *ssp, const InterVal *ivp,
 		   const SeqCodec *codecp, uint32_t *npos_max, char verbose)
 {
@@ -37,8 +38,10 @@ int hashTableSetUp(HashTable *htp, SeqFastq *sqbufp, const SeqSet *ssp, const In
   }
   if (smbShimIndexBuild(ssp, codecp, htp->wordlen, htp->nskip, htp->typ, htp->nbits_key, htp->nbits_lo,
 			&npos, &nwords, &tuplectr, &ms) < 0) {
-    if (verbose) fprintf(stderr, "# (index construction on the CPU)\n");
-    return hashTableSetUp_cpu(htp, sqbufp, ssp, ivp, codecp, npos_max, verbose);
+    /* no silent fallback: the index of a sequence set is built on the GPU or not at all
+     * (SMALT_B200_CPU_INDEX=1 asks for the reference's builder explicitly, e.g. to compare the two) */
+    fprintf(stderr, "smalt_b200: index construction needs a CUDA device (there is no CPU fallback)\n");
+    return ERRCODE_FAILURE;
   }
   if (verbose) fprintf(stderr, "# Hash index built on the GPU (%u positions, %u words, %.1f ms).\n", npos, nwords, ms);
   if (npos_max != NULL) {   /* hashidx.c:881-887 */

@@ -66,6 +66,14 @@ static double shim_now(void)
 }
 #define SHIM_TIMING(what, t0) do { if (getenv("SMALT_B200_TIMING")) fprintf(stderr, "smalt_b200 timing: %s %.3f s\n", what, shim_now() - (t0)); } while (0)
 
+/* a feature of the reference interface that the device path does not implement: one message, then the
+ * call fails with an error code the caller handles like any other failure (no abort, no CPU fallback) */
+static void shim_unsupported(const char *what)
+{
+  static int said;
+  if (!said++) fprintf(stderr, "smalt_b200: %s is not implemented on the B200 path (include/smalt_b200.h, \"not covered\")\n", what);
+}
+
 static void shim_die(const char *what)
 {
   fprintf(stderr, "smalt_b200: %s\n", what);
@@ -282,8 +290,10 @@ AliRsltSet *aliRsltSetCreate(const ScoreMatrix *smp, short blksz, short diffblks
 {
   AliRsltSet *p;
   (void) blksz; (void) diffblksz; (void) track_blksz; (void) track_thresh;
-  if (smp != NULL)
-    shim_die("complexity-weighted Smith-Waterman scores (-w) are not supported by the B200 path");
+  if (smp != NULL) {   /* scaleALICPLX (alignment.c:268-305): floating-point rescoring inside K3 - not on the device */
+    shim_unsupported("complexity-weighted Smith-Waterman scores (map -w)");
+    return NULL;       /* constructors report failure as NULL; the caller ends with its own error message */
+  }
   p = (AliRsltSet *) calloc(1, sizeof(*p));
   return p;
 }
@@ -657,8 +667,10 @@ static int collect_info(HashHitInfo *h, int is_reverse, int is_short, uint32_t m
 int hashCollectHitInfo(HashHitInfo *hhip, unsigned char is_reverse, unsigned char basq_thresh,
 		       SEQLEN_t seq_start, SEQLEN_t seq_end, const SeqFastq *seqp, const HashTable *htp)
 {
-  if (seq_start != 0 || seq_end != 0)
-    shim_die("hashCollectHitInfo on a read segment (split-read mode -p) is not supported by the B200 path");
+  if (seq_start != 0 || seq_end != 0) {   /* seed tables of a read segment (hashhit.c:538-548): split reads, map -p */
+    shim_unsupported("seed tables of a read segment (split-read mode, map -p)");
+    return ERRCODE_ARGINVAL;
+  }
   return collect_info(hhip, is_reverse, 0, 0, 0, basq_thresh, seqp, htp);
 }
 
@@ -769,7 +781,10 @@ int hashCollectHitsForSegment(HashHitList *hlp, SETSIZ_t segmoffs_lo, SETSIZ_t s
 			      const HashHitInfo *hhip, const HashTable *htp, const HashHitFilter *hhfp)
 {
   (void) htp;
-  if (hhfp) shim_die("hit filters (HashHitFilter) are not supported by the B200 path");
+  if (hhfp) {   /* (no caller in the smalt driver passes a filter) */
+    shim_unsupported("hit filters (HashHitFilter)");
+    return ERRCODE_ARGINVAL;
+  }
   return collect_hits(hlp, segmoffs_lo, segmoffs_hi, nhit_max, use_short_hitinfo ? 1 : 0, (HashHitInfo *) hhip);
 }
 
