@@ -94,6 +94,25 @@ class Mapper:
             raise SmbError(rc, "smbm_map_fastq failed")
         return C.string_at(sam, n.value)
 
+    def map_fastq_view(self, text, mates=None):
+        """like map_fastq / map_fastq_pairs, but returns a memoryview of the SAM records in the mapper's own
+        buffer (valid until the next call): no copy on the Python side"""
+        sam = C.c_void_p()
+        n = C.c_size_t(0)
+        p, nbytes, keep = _as_pointer(text)
+        if mates is None:
+            rc = self.lib.smbm_map_fastq(self._h, p, nbytes, C.byref(sam), C.byref(n), C.byref(self.stats))
+        else:
+            p2, nbytes2, keep2 = _as_pointer(mates)
+            rc = self.lib.smbm_map_fastq_pairs(self._h, p, nbytes, p2, nbytes2, C.byref(sam), C.byref(n), C.byref(self.stats))
+            del keep2
+        del keep
+        if rc:
+            raise SmbError(rc, "smbm_map_fastq failed")
+        if not n.value:
+            return memoryview(b"")
+        return memoryview((C.c_char * n.value).from_address(sam.value)).cast("B")
+
     def map_fastq_nocopy(self, text):
         """like map_fastq but returns only the length of the SAM text (bench: no Python copy)"""
         sam = C.c_void_p()

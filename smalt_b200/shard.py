@@ -70,12 +70,14 @@ def pair_shard_of(text1, text2, rank, world):
     return text1[p1[rank]:p1[rank + 1]], text2[p2[rank]:p2[rank + 1]]
 
 
-def merge_to_file(dist, local_bytes, path, header=b""):
+def merge_to_file(dist, local_bytes, path, header=b"", writers=4):
     """Host merge of the per-rank outputs in rank (= input) order, as the reference's OUTPUT task
     orders its blocks by read number (smalt.c:966-1000): every rank writes its text at its offset
     into ONE file - `header` (rank 0), then rank 0's records, rank 1's, ... - with pwrite; the offsets
     are the exclusive scan of the text lengths, the only thing the ranks exchange (8 bytes each).
-    Put `path` on /dev/shm for a merge through shared memory.  Ends with a barrier; -> total bytes."""
+    Put `path` on /dev/shm for a merge through shared memory (a file that is overwritten keeps its pages:
+    later merges into the same path are plain copies).  `writers` threads share the copy of a large text.
+    Ends with a barrier; -> total bytes."""
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
@@ -92,9 +94,23 @@ def merge_to_file(dist, local_bytes, path, header=b""):
             if header:
                 os.pwrite(fd, header, 0)
                 off = len(header)
-        mv, done = memoryview(local_bytes), 0
-        while done < len(mv):                      # (pwrite may write less than asked for)
-            done += os.pwrite(fd, mv[done:done + (1 << 30)], off + done)
+        mv = memoryview(local_bytes).cast("B")
+
+        def put(lo, hi):
+            while lo < hi:                         # (pwrite may write less than asked for)
+                lo += os.pwrite(fd, mv[lo:min(hi, lo + (1 << 28))], off + lo)
+
+        nthr = max(1, min(writers, len(mv) >> 24))   # a writer per 16 MB, the copy is the whole cost
+        if nthr == 1:
+            put(0, len(mv))
+        else:
+            import threading
+            step = (len(mv) + nthr - 1) // nthr
+            ths = [threading.Thread(target=put, args=(k * step, min(len(mv), (k + 1) * step))) for k in range(nthr)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
     finally:
         os.close(fd)
     dist.barrier()
