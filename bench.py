@@ -531,14 +531,19 @@ def main():
     barrier()
     t0 = time.perf_counter()
     sam_bytes = merged_bytes = 0
+    t_map = t_merge = 0.0
     for _ in range(args.steps):
         if dist is None:
             sam_bytes = run_step(m)
         else:
+            ta = time.perf_counter()
             sam = m.map_fastq_view(wl.texts[0], wl.texts[1] if paired else None)   # the mapper's own buffer, no copy
+            tb = time.perf_counter()
             sam_bytes = len(sam)
             merged_bytes = shard.merge_to_file(dist, sam, merged)   # offset writes, ends with a barrier
             del sam
+            t_map += tb - ta
+            t_merge += time.perf_counter() - tb
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -587,6 +592,7 @@ def main():
                                    args.device_block),
         "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": wall_ms, "sam_bytes_per_step": int(sam_bytes), "merged_sam_bytes_per_step": int(merged_bytes),
+                "rank0_map_ms_per_step": 1e3 * t_map / args.steps, "rank0_merge_ms_per_step": 1e3 * t_merge / args.steps,
                 "host_stage_wall_s": c1["host_stage_s"], "host_stage_cpu_s": c1["host_cpu_s"]},
         "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
     }
