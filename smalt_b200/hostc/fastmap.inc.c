@@ -85,6 +85,10 @@ typedef struct {
 
 static FmWorker *g_fm_workers;
 static int g_fm_nworkers;
+/* device batches shared by the workers of the single-end pipeline (rmap_wave.c, WaveCombiner);
+ * SMALT_B200_COMBINE=0: every worker maps its block on its own stream; SMALT_B200_BATCH: reads per batch */
+static WaveCombiner *g_fm_comb;
+static FmWorker g_fm_comb_stats[8];   /* the batch slots' waves, for fm_collect_stats */
 
 /* ---- block boundaries ---------------------------------------------------------------- */
 
@@ -429,7 +433,7 @@ static int fm_map_block(FmWorker *w, size_t c)
     const int nb = (int) ((n - pos < 32000) ? n - pos : 32000);
     SeqFastq **save = w->reads;
     w->reads += pos; /* fm_emit indexes relative to the sub-block */
-    errcode = rmapSingleWave(w->errmsgp, fm->maps[w->id].rmp, w->wave, nb, w->reads, w->mincov + pos,
+    errcode = rmapSingleWaveCombined(w->errmsgp, fm->maps[w->id].rmp, w->wave, g_fm_comb, nb, w->reads, w->mincov + pos,
 			     macop->nhitmax_tuple, (int) macop->min_swatscor, macop->swatscordiff, macop->minbasq,
 			     SMALT_TARGET_DEPTH, SMALT_MAX_DEPTH, (RMAPFLG_t) (macop->rmapflg & ~RMAPFLG_ALLPAIR),
 			     macop->scormtxp, macop->rfp, macop->htp, macop->ssp, macop->codecp, fm_emit, &em);
@@ -773,6 +777,14 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
       fprintf(stderr, "smalt_b200 timing: fastmap set-up of %d workers %.3f s (at %.3f s); %zu blocks of ~%zu reads\n",
 	      nworkers, t1 - t0, t1 - g_t0, fm.nchunks, block);
   }
+  if (!errcode && !dataB && nworkers > 1 && !g_fm_comb) {
+    const char *ce = getenv("SMALT_B200_COMBINE"), *be = getenv("SMALT_B200_BATCH");
+    if (!ce || atoi(ce) != 0) {
+      g_fm_comb = waveCombinerCreate(macop->htp, macop->ssp, macop->codecp, macop->scormtxp, 4,
+				     (be && atoi(be) > 0) ? atoi(be) : 32768);
+      if (!g_fm_comb) errcode = ERRCODE_FAILURE;
+    }
+  }
   if (!errcode) {
     if (nworkers == 1) {
       fm_worker_main(g_fm_workers);
@@ -785,6 +797,15 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
     errcode = fm.errcode;
   }
   for (i = 0; i < nworkers; i++) fm_collect_stats(g_fm_workers + i);
+  if (g_fm_comb) {
+    RmapWave *waves[8];
+    uint64_t cc[2];
+    const int ns = waveCombinerSlots(g_fm_comb, waves, cc);
+    for (i = 0; i < ns && i < 8; i++) { g_fm_comb_stats[i].wave = waves[i]; fm_collect_stats(g_fm_comb_stats + i); }
+    if (getenv("SMALT_B200_TIMING"))
+      fprintf(stderr, "smalt_b200 timing: %llu device batches, %.0f reads each\n", (unsigned long long) cc[0],
+	      cc[0] ? (double) cc[1] / (double) cc[0] : 0.0);
+  }
   for (p = 0; p < fm.nchunks; p++) free(fm.out[p].buf);
   free(fm.out);
   fm_lines_free(fm.linesA);
@@ -818,4 +839,7 @@ static void fastmap_cleanup(void)
   free(g_fm_workers);
   g_fm_workers = NULL;
   g_fm_nworkers = 0;
+  waveCombinerDelete(g_fm_comb);
+  g_fm_comb = NULL;
+  memset(g_fm_comb_stats, 0, sizeof(g_fm_comb_stats));
 }

@@ -337,6 +337,106 @@ static int wave_skip_results(void)
   return state;
 }
 
+/* host side of a block whose device outputs are in `bw` (the worker's own wave or the shared wave of a
+ * combined batch): replay of alignRMAPCANDFull (rmap.c:820-926) on the alignments of reads first .. first+n-1
+ * of the batch, then results.c as in the reference.  `w` = the calling worker's wave (profiles, timers). */
+static int dev_results(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, WREAD *rdarr, const RmapWave *bw, const smb_block_read *brd,
+		       const smb_block_cand *bc, size_t first, int n, const WJOB *jobs, short max_depth, RMAPFLG_t rmapflg,
+		       short matchscor, const SeqSet *ssp, const SeqCodec *codecp, WAVE_DONEF *donef, void *user)
+{
+  int errcode = ERRCODE_SUCCESS, i;
+  RMAPBUFF *bufp = rmp->bfp;
+  double tres;
+  tres = wnow();
+  if (wave_skip_results()) {   /* diagnostic: device + transfer side alone, every read reported unmapped */
+    for (i = 0; i < n; i++) {
+      if (rdarr) memset(rdarr + i, 0, sizeof(WREAD));
+      if (jobs[i].blank) resultSetBlank(jobs[i].rsp);
+      if (donef && (errcode = (*donef)(user, i, 0, jobs[i].rsp))) return errcode;
+    }
+    return ERRCODE_SUCCESS;
+  }
+  for (i = 0; i < n; i++) {
+    WREAD rd_local, *rd = rdarr ? rdarr + i : &rd_local;
+    const smb_block_read *b = brd + first + i;
+    ResultSet *rsp = jobs[i].rsp;
+    SeqFastq *readp = jobs[i].readp;
+    memset(rd, 0, sizeof(*rd));
+    rd->qlen = bw->read_len[jobs[i].read];
+    rd->errcode = b->errcode;
+    rd->reached_stats = b->reached_stats;
+    rd->do_align = b->do_align;
+    rd->nseg = b->nseg; rd->nseg_tot = b->nseg_tot; rd->nhit = b->nhit; rd->nhit_tot = b->nhit_tot;
+    rd->ncand = b->ncand; rd->nscored = b->nscored;
+    rd->max1scor = b->max1scor; rd->max2scor = b->max2scor;
+    rd->min_swatscor = b->min_swatscor; rd->scorlen_min = b->scorlen_min; rd->bandwidth_min = b->bandwidth_min;
+    if (jobs[i].blank) resultSetBlank(rsp);
+    if (rd->errcode == ERRCODE_SHORTSEQ) { /* too short to be hashed (rmap.c:1273-1275) */
+      if (donef && (errcode = (*donef)(user, i, ERRCODE_SHORTSEQ, rsp))) return errcode;
+      continue;
+    }
+    if (rd->errcode) ERRMSGNO(errmsgp, rd->errcode);
+    if (rd->reached_stats)
+      resultSetAlignmentStats(rsp, rd->nseg, rd->nseg_tot, max_depth, rd->nhit, rd->nhit_tot);
+    if (wave_debug())
+      fprintf(stderr, "DBG read %d ncand %u nscored %u max1 %d max2 %d min_swatscor %d scorlen_min %d bw_min %d nseg %d/%d nhit %u/%u\n",
+	      i, rd->ncand, rd->nscored, rd->max1scor, rd->max2scor, rd->min_swatscor, rd->scorlen_min, rd->bandwidth_min,
+	      rd->nseg, rd->nseg_tot, rd->nhit, rd->nhit_tot);
+    if (!rd->errcode && rd->do_align) {
+      int min_swatscor = rd->min_swatscor;
+      SWATSCOR swatscor_2ndmax = 0;
+      uint32_t c;
+      for (c = 0; c < b->nk3 && !rd->errcode; c++) {
+	const size_t t = (size_t) b->k3_first + c;
+	const smb_block_cand *cp = bc + t;
+	int minscorlen = rd->scorlen_min;
+	uint32_t pos, end;
+	if (rmapflg & RMAPFLG_BEST) {
+	  resultSetGetMaxSwat(rsp, &swatscor_2ndmax);
+	  if (swatscor_2ndmax > min_swatscor) min_swatscor = swatscor_2ndmax;
+	}
+	if (bw->ba_err[t]) { rd->errcode = bw->ba_err[t]; break; }
+	aliRsltSetReset(bufp->alirsltp);
+	/* aliSmiWatInBand (alignment.c:1569-1575) with the current threshold */
+	if (min_swatscor < 1 || matchscor <= 0) { rd->errcode = ERRCODE_ASSERT; break; }
+	if (minscorlen * matchscor < min_swatscor) minscorlen = min_swatscor / matchscor;
+	if (minscorlen < 5) { rd->errcode = ERRCODE_ASSERT; break; }
+	pos = bw->res_first[t];
+	end = bw->res_first[t + 1];
+	if ((errcode = prune_results(bufp->alirsltp, bw->res, bw->diff, &pos, end, 0, (int) cp->reflen - 1,
+				     min_swatscor, minscorlen, 1)))
+	  return errcode;
+	if (wave_debug()) {
+	  short k_, n_ = aliRsltSetGetSize(bufp->alirsltp);
+	  fprintf(stderr, "DBG  cand swscor %d rev %d rs %llu band %d %d minscore %d minscorlen %d raw %u kept %d:",
+		  cp->swscor, (int) cp->reverse, (unsigned long long) cp->rs, cp->band_l, cp->band_r, min_swatscor,
+		  minscorlen, bw->res_first[t + 1] - bw->res_first[t], (int) n_);
+	  for (k_ = 0; k_ < n_; k_++) {
+	    int sc_, a_, b_, c_, d_;
+	    aliRsltSetFetchData(bufp->alirsltp, k_, &sc_, &a_, &b_, &c_, &d_, NULL);
+	    fprintf(stderr, " (%d q%d-%d r%d-%d)", sc_, a_, b_, c_, d_);
+	  }
+	  fputc('\n', stderr);
+	}
+	errcode = resultSetAddFromAli(rsp, bufp->alirsltp, (SETSIZ_t) cp->rs, 0, rd->qlen, (SEQNUM_t) cp->sqidx,
+				      (char) (cp->reverse ? RMAPCANDFLG_REVERSE : 0));
+	if (errcode) { rd->errcode = errcode; break; }
+      }
+      { const double t_ = wnow(); w->wall_res[0] += t_ - tres; tres = t_; }
+      if (rd->errcode) ERRMSGNO(errmsgp, rd->errcode);
+      else {
+	/* (the read's profiles are only dereferenced for results without a sequence index, which the
+	 * sequence-by-sequence mode never produces: results.c:1715, :1742-1756) */
+	errcode = resultSetSortAndAssignSequence(rsp, bufp->sqbfp, 0, readp, w->prof, w->profRC, ssp, codecp);
+	if (errcode) { rd->errcode = errcode; ERRMSGNO(errmsgp, errcode); }
+      }
+    }
+    if (donef && (errcode = (*donef)(user, i, rd->errcode, rsp))) return errcode;
+    tres = wnow();
+  }
+  return ERRCODE_SUCCESS;
+}
+
 /* waves 1b-3 with the block resident on the device (smb_block_run / smb_block_fetch): hit lists,
  * candidate selection (segment.c), K2, the score replay (rmap.c:745-786, :1373-1400) and K3 run
  * back to back on the GPU; the host gets the per-read summaries, the aligned candidates and their
@@ -430,95 +530,8 @@ static int wave_pass_dev(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, const W
   WTICK(6);
 
   /* host: replay of alignRMAPCANDFull (rmap.c:820-926) on the alignments, then results.c as in the reference */
-  tres = wnow();
-  if (wave_skip_results()) {   /* diagnostic: device + transfer side alone, every read reported unmapped */
-    for (i = 0; i < n; i++) {
-      memset(w->rd + i, 0, sizeof(WREAD));
-      if (jobs[i].blank) resultSetBlank(jobs[i].rsp);
-      if (donef && (errcode = (*donef)(user, i, 0, jobs[i].rsp))) return errcode;
-    }
-    WTICK(7);
-    w->n_reads += (uint64_t) n;
-    return ERRCODE_SUCCESS;
-  }
-  for (i = 0; i < n; i++) {
-    WREAD *rd = w->rd + i;
-    const smb_block_read *b = brd + i;
-    ResultSet *rsp = jobs[i].rsp;
-    SeqFastq *readp = jobs[i].readp;
-    memset(rd, 0, sizeof(*rd));
-    rd->qlen = w->read_len[jobs[i].read];
-    rd->errcode = b->errcode;
-    rd->reached_stats = b->reached_stats;
-    rd->do_align = b->do_align;
-    rd->nseg = b->nseg; rd->nseg_tot = b->nseg_tot; rd->nhit = b->nhit; rd->nhit_tot = b->nhit_tot;
-    rd->ncand = b->ncand; rd->nscored = b->nscored;
-    rd->max1scor = b->max1scor; rd->max2scor = b->max2scor;
-    rd->min_swatscor = b->min_swatscor; rd->scorlen_min = b->scorlen_min; rd->bandwidth_min = b->bandwidth_min;
-    if (jobs[i].blank) resultSetBlank(rsp);
-    if (rd->errcode == ERRCODE_SHORTSEQ) { /* too short to be hashed (rmap.c:1273-1275) */
-      if (donef && (errcode = (*donef)(user, i, ERRCODE_SHORTSEQ, rsp))) return errcode;
-      continue;
-    }
-    if (rd->errcode) ERRMSGNO(errmsgp, rd->errcode);
-    if (rd->reached_stats)
-      resultSetAlignmentStats(rsp, rd->nseg, rd->nseg_tot, max_depth, rd->nhit, rd->nhit_tot);
-    if (wave_debug())
-      fprintf(stderr, "DBG read %d ncand %u nscored %u max1 %d max2 %d min_swatscor %d scorlen_min %d bw_min %d nseg %d/%d nhit %u/%u\n",
-	      i, rd->ncand, rd->nscored, rd->max1scor, rd->max2scor, rd->min_swatscor, rd->scorlen_min, rd->bandwidth_min,
-	      rd->nseg, rd->nseg_tot, rd->nhit, rd->nhit_tot);
-    if (!rd->errcode && rd->do_align) {
-      int min_swatscor = rd->min_swatscor;
-      SWATSCOR swatscor_2ndmax = 0;
-      uint32_t c;
-      for (c = 0; c < b->nk3 && !rd->errcode; c++) {
-	const size_t t = (size_t) b->k3_first + c;
-	const smb_block_cand *cp = bc + t;
-	int minscorlen = rd->scorlen_min;
-	uint32_t pos, end;
-	if (rmapflg & RMAPFLG_BEST) {
-	  resultSetGetMaxSwat(rsp, &swatscor_2ndmax);
-	  if (swatscor_2ndmax > min_swatscor) min_swatscor = swatscor_2ndmax;
-	}
-	if (w->ba_err[t]) { rd->errcode = w->ba_err[t]; break; }
-	aliRsltSetReset(bufp->alirsltp);
-	/* aliSmiWatInBand (alignment.c:1569-1575) with the current threshold */
-	if (min_swatscor < 1 || matchscor <= 0) { rd->errcode = ERRCODE_ASSERT; break; }
-	if (minscorlen * matchscor < min_swatscor) minscorlen = min_swatscor / matchscor;
-	if (minscorlen < 5) { rd->errcode = ERRCODE_ASSERT; break; }
-	pos = w->res_first[t];
-	end = w->res_first[t + 1];
-	if ((errcode = prune_results(bufp->alirsltp, w->res, w->diff, &pos, end, 0, (int) cp->reflen - 1,
-				     min_swatscor, minscorlen, 1)))
-	  return errcode;
-	if (wave_debug()) {
-	  short k_, n_ = aliRsltSetGetSize(bufp->alirsltp);
-	  fprintf(stderr, "DBG  cand swscor %d rev %d rs %llu band %d %d minscore %d minscorlen %d raw %u kept %d:",
-		  cp->swscor, (int) cp->reverse, (unsigned long long) cp->rs, cp->band_l, cp->band_r, min_swatscor,
-		  minscorlen, w->res_first[t + 1] - w->res_first[t], (int) n_);
-	  for (k_ = 0; k_ < n_; k_++) {
-	    int sc_, a_, b_, c_, d_;
-	    aliRsltSetFetchData(bufp->alirsltp, k_, &sc_, &a_, &b_, &c_, &d_, NULL);
-	    fprintf(stderr, " (%d q%d-%d r%d-%d)", sc_, a_, b_, c_, d_);
-	  }
-	  fputc('\n', stderr);
-	}
-	errcode = resultSetAddFromAli(rsp, bufp->alirsltp, (SETSIZ_t) cp->rs, 0, rd->qlen, (SEQNUM_t) cp->sqidx,
-				      (char) (cp->reverse ? RMAPCANDFLG_REVERSE : 0));
-	if (errcode) { rd->errcode = errcode; break; }
-      }
-      { const double t_ = wnow(); w->wall_res[0] += t_ - tres; tres = t_; }
-      if (rd->errcode) ERRMSGNO(errmsgp, rd->errcode);
-      else {
-	/* (the read's profiles are only dereferenced for results without a sequence index, which the
-	 * sequence-by-sequence mode never produces: results.c:1715, :1742-1756) */
-	errcode = resultSetSortAndAssignSequence(rsp, bufp->sqbfp, 0, readp, w->prof, w->profRC, ssp, codecp);
-	if (errcode) { rd->errcode = errcode; ERRMSGNO(errmsgp, errcode); }
-      }
-    }
-    if (donef && (errcode = (*donef)(user, i, rd->errcode, rsp))) return errcode;
-    tres = wnow();
-  }
+  if ((errcode = dev_results(errmsgp, rmp, w, w->rd, w, brd, bc, 0, n, jobs, max_depth, rmapflg, matchscor, ssp, codecp, donef, user)))
+    return errcode;
   WTICK(7);
   w->n_reads += (uint64_t) n;
   return ERRCODE_SUCCESS;
@@ -1034,6 +1047,305 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
   sd.w = w; sd.errmsgp = errmsgp; sd.rsfp = rsfp; sd.jobs = w->jobs; sd.emitf = emitf; sd.user = user;
   return wave_pass(errmsgp, rmp, w, n, w->jobs, w->info, ktuple_maxhit, min_swatscor_below_max_arg, target_depth, max_depth,
 		   rmapflg, scormtxp, htp, ssp, codecp, single_done, &sd);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* combined device batches                                                                */
+/* ------------------------------------------------------------------------------------ */
+/* The host stages want small blocks (parse and results.c of ~8000 reads per worker thread keep all cores
+ * busy and the output in order), the device wants large batches: the kernels of an 8192-read block are
+ * short and latency bound, and since the persistent K2 / K3 kernels fill the machine the blocks of different
+ * worker streams run one after the other (104 ms of device time per 1 M reads at 8192-read launches, 74 ms
+ * at 32000).  A WaveCombiner joins the blocks of several workers into ONE device batch: a worker copies its
+ * reads into the shared staging of the open batch and waits; the batch closes when it is full or as soon as
+ * the device is free, its last member to arrive drives the GPU for everybody (seed tables, smb_block_run,
+ * smb_block_fetch), then every member runs results.c on its own reads.  Batch size follows the load: a lone
+ * worker maps its block at once, a saturated device gets batches of `target` reads. */
+#include <pthread.h>
+enum { CS_FREE = 0, CS_OPEN, CS_CLOSED, CS_RUNNING, CS_DONE };
+enum { COMB_MAXSLOTS = 6 };
+typedef struct {
+  RmapWave *bw;              /* device context + page-locked staging / outputs of the batch */
+  int state, nmembers, ncopied, ndone, nreads, leader, any_qual, errcode;
+  size_t bytes;
+  smb_block_job *jobs;
+  smb_block_read *brd;
+  smb_block_cand *bc;
+  int have_pen;
+} CombSlot;
+struct WaveCombiner_ {
+  pthread_mutex_t lock;
+  pthread_cond_t cond;
+  int nslots, target, cap_reads, open, nrunning;
+  size_t cap_bytes;
+  CombSlot slot[COMB_MAXSLOTS];
+  uint64_t nbatches, nbatch_reads;
+};
+
+WaveCombiner *waveCombinerCreate(const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
+				 const ScoreMatrix *scormtxp, int nslots, int target_reads)
+{
+  WaveCombiner *wc = (WaveCombiner *) calloc(1, sizeof(*wc));
+  int k;
+  if (!wc) return NULL;
+  if (nslots < 2) nslots = 2;
+  if (nslots > COMB_MAXSLOTS) nslots = COMB_MAXSLOTS;
+  if (target_reads < 1024) target_reads = 1024;
+  wc->nslots = nslots; wc->target = target_reads; wc->cap_reads = 2 * target_reads;
+  wc->cap_bytes = (size_t) wc->cap_reads * 320;
+  wc->open = -1;
+  pthread_mutex_init(&wc->lock, NULL);
+  pthread_cond_init(&wc->cond, NULL);
+  for (k = 0; k < nslots; k++) {
+    RmapWave *bw = rmapWaveCreate(htp, ssp, codecp, scormtxp);
+    CombSlot *b = wc->slot + k;
+    if (!bw) { waveCombinerDelete(wc); return NULL; }
+    b->bw = bw;
+    bw->read_off = (uint64_t *) wbuf_need(&bw->wb[WB_READ_OFF], (size_t) wc->cap_reads * sizeof(uint64_t));
+    bw->read_len = (uint32_t *) wbuf_need(&bw->wb[WB_READ_LEN], (size_t) wc->cap_reads * sizeof(uint32_t));
+    bw->info = (smb_seed_info *) wbuf_need(&bw->wb[WB_INFO], 2 * (size_t) wc->cap_reads * sizeof(smb_seed_info));
+    bw->arena = (uint8_t *) wbuf_need(&bw->wb[WB_ARENA], wc->cap_bytes + 16);
+    bw->qual = (uint8_t *) wbuf_need(&bw->wb[WB_QUAL], wc->cap_bytes + 16);
+    b->jobs = (smb_block_job *) wbuf_need(&bw->wb[WB_BJOB], (size_t) wc->cap_reads * sizeof(smb_block_job));
+    if (!bw->read_off || !bw->read_len || !bw->info || !bw->arena || !bw->qual || !b->jobs) { waveCombinerDelete(wc); return NULL; }
+  }
+  return wc;
+}
+
+void waveCombinerDelete(WaveCombiner *wc)
+{
+  int k;
+  if (!wc) return;
+  for (k = 0; k < COMB_MAXSLOTS; k++) rmapWaveDelete(wc->slot[k].bw);
+  pthread_mutex_destroy(&wc->lock);
+  pthread_cond_destroy(&wc->cond);
+  free(wc);
+}
+
+int waveCombinerSlots(const WaveCombiner *wc, RmapWave **waves, uint64_t counts[2])
+{
+  int k;
+  for (k = 0; k < wc->nslots; k++) waves[k] = wc->slot[k].bw;
+  counts[0] = wc->nbatches; counts[1] = wc->nbatch_reads;
+  return wc->nslots;
+}
+
+/* closes the open batch if the device is free and every member has delivered its reads (lock held) */
+static void comb_try_close(WaveCombiner *wc)
+{
+  if (wc->open >= 0 && wc->nrunning == 0) {
+    CombSlot *b = wc->slot + wc->open;
+    if (b->state == CS_OPEN && b->nmembers > 0 && b->ncopied == b->nmembers) {
+      b->state = CS_CLOSED;
+      wc->open = -1;
+      pthread_cond_broadcast(&wc->cond);
+    }
+  }
+}
+
+/* the leader's part: the whole batch through the device */
+static int comb_run_gpu(ErrMsg *errmsgp, RmapWave *lw, CombSlot *b, int ktuple_maxhit, int min_swatscor_below_max_arg,
+			UCHAR min_basqval, short target_depth, short max_depth, RMAPFLG_t rmapflg,
+			const ScoreMatrix *scormtxp, SeqFastq *any_read, const SeqSet *ssp)
+{
+  RmapWave *w = b->bw;
+  const int n = b->nreads;
+  int rc, errcode;
+  smb_block_params prm;
+  smb_block_sizes sz;
+  const SETSIZ_t *soffs;
+  const SEQNUM_t nseq = seqSetGetOffsets(ssp, &soffs);
+  (void) lw;
+  if (!b->have_pen) {
+    if ((errcode = scoreMakeProfileFromSequence(w->prof, any_read, scormtxp))) return errcode;
+    if ((rc = smbShimSetScoring(w->ctx, w->prof))) return gpu_fail(errmsgp, w, rc);
+    b->have_pen = 1;
+  }
+  if ((rc = smb_arena_upload(w->ctx, w->arena, b->bytes))) return gpu_fail(errmsgp, w, rc);
+  if ((rc = smb_seed_batch(w->ctx, w->read_off, w->read_len, n, b->any_qual ? w->qual : NULL,
+			   (uint32_t) ktuple_maxhit, HASH_MAXNHITS, min_basqval, 1, w->info,
+			   NULL, NULL, NULL, NULL, NULL, NULL)))
+    return gpu_fail(errmsgp, w, rc);
+  w->ms_k1 += smb_last_kernel_ms(w->ctx);
+  memset(&prm, 0, sizeof(prm));
+  prm.nhit_max = (uint32_t) ktuple_maxhit;
+  prm.min_swatscor_below_max = min_swatscor_below_max_arg;
+  prm.target_depth = (int32_t) target_depth;
+  prm.max_depth = (int32_t) max_depth;
+  prm.best = (uint8_t) ((rmapflg & RMAPFLG_BEST) != 0);
+  prm.sensitive = (uint8_t) ((rmapflg & RMAPFLG_SENSITIVE) != 0);
+  {
+    SETSIZ_t roffs;
+    const SEQLEN_t rlen0 = nseq > 0 ? seqSetGetSeqDatByIndex(&roffs, NULL, 0, ssp) : 0;
+    prm.termchar = (uint8_t) (nseq > 0 && (SETSIZ_t) rlen0 != soffs[1] - soffs[0]);
+  }
+  if ((rc = smb_block_run(w->ctx, &prm, b->jobs, n, NULL, 0, &sz))) return gpu_fail(errmsgp, w, rc);
+  w->ms_k1 += sz.ms_hits + sz.ms_cand;
+  w->ms_cand += sz.ms_cand;
+  w->ms_k2 += sz.ms_k2;
+  w->ms_k3 += sz.ms_k3;
+  w->n_k2 += sz.k2_tasks_ref;
+  w->cells_k2 += sz.k2_cells_ref;
+  w->n_k3 += sz.nk3;
+  w->cells_k3 += sz.k3_cells;
+  WPIN(b->brd, WB_BRD, n, smb_block_read);
+  WPIN(b->bc, WB_BCAND, sz.nk3 + 1, smb_block_cand);
+  WPIN(w->ba_err, WB_BA_ERR, sz.nk3 + 1, int32_t);
+  WPIN(w->res_first, WB_RES_FIRST, sz.nk3 + 2, uint32_t);
+  if (w->res_alloc < sz.nresults + 1) {
+    WPIN(w->res, WB_RES, sz.nresults + sz.nresults / 2 + 64, smb_ali_result);
+    w->res_alloc = w->wb[WB_RES].cap / sizeof(smb_ali_result);
+  }
+  if (w->diff_alloc < sz.ndiffbytes + 1) {
+    WPIN(w->diff, WB_DIFF, sz.ndiffbytes + sz.ndiffbytes / 2 + 4096, uint8_t);
+    w->diff_alloc = w->wb[WB_DIFF].cap;
+  }
+  if ((rc = smb_block_fetch(w->ctx, b->brd, b->bc, w->ba_err, w->res_first, w->res, w->diff))) return gpu_fail(errmsgp, w, rc);
+  w->n_reads += (uint64_t) n;
+  return ERRCODE_SUCCESS;
+}
+
+int rmapSingleWaveCombined(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, WaveCombiner *wc, int n, SeqFastq **reads,
+			   const uint32_t *min_cover_arr, int ktuple_maxhit, int min_swatscor_arg,
+			   int min_swatscor_below_max_arg, UCHAR min_basqval, short target_depth, short max_depth,
+			   RMAPFLG_t rmapflg, const ScoreMatrix *scormtxp, const ResultFilter *rsfp,
+			   const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
+			   RMAPWAVE_EMITF *emitf, void *user)
+{
+  int errcode = ERRCODE_SUCCESS, i, any_qual = 0, s, first, valid = -1;
+  size_t tot = 0, off;
+  CombSlot *b;
+  SINGLEDONE sd;
+  double tw = wnow(), tc = cnow();
+  UCHAR nskip;
+  const UCHAR ktup = hashTableGetKtupLen(htp, &nskip);
+  short matchscor = 0, mismatchscor = 0, gapinitscor = 0, gapextscor = 0;
+
+  if (n < 1) return ERRCODE_SUCCESS;
+  for (i = 0; i < n; i++) {
+    SEQLEN_t len;
+    char cod;
+    seqFastqGetConstSequence(reads[i], &len, &cod);
+    if (cod != SEQCOD_MANGLED) return ERRCODE_SEQCODE;
+    if (valid < 0 && len >= ktup) valid = i;
+    tot += len;
+    if (seqFastqGetConstQualityFactors(reads[i], NULL, NULL)) any_qual = 1;
+  }
+  if (!wc || wave_host_cand() || !(rmapflg & RMAPFLG_SEQBYSEQ) || (rmapflg & (RMAPFLG_NOSHRTINFO | RMAPFLG_SPLIT | RMAPFLG_CMPLXW)) ||
+      valid < 0 || n > wc->cap_reads / 2 || tot > wc->cap_bytes / 2)
+    return rmapSingleWave(errmsgp, rmp, w, n, reads, min_cover_arr, ktuple_maxhit, min_swatscor_arg, min_swatscor_below_max_arg,
+			  min_basqval, target_depth, max_depth, rmapflg, scormtxp, rsfp, htp, ssp, codecp, emitf, user);
+  /* penalties are those of the score matrix (rmap.c:1258-1266) */
+  if ((errcode = scoreMakeProfileFromSequence(w->prof, reads[valid], scormtxp))) return errcode;
+  matchscor = scoreProfileGetAvgPenalties(&mismatchscor, &gapinitscor, &gapextscor, w->prof);
+  if ((short) (matchscor - mismatchscor) < 1 || gapextscor >= 0 || mismatchscor >= 0 || (short) (matchscor - gapinitscor) < 1)
+    return ERRCODE_ASSERT;
+
+  /* ---- join the open batch ---- */
+  pthread_mutex_lock(&wc->lock);
+  for (;;) {
+    s = wc->open;
+    if (s >= 0) {
+      b = wc->slot + s;
+      if (b->nreads + n <= wc->cap_reads && b->bytes + tot <= wc->cap_bytes) break;
+      b->state = CS_CLOSED;   /* no room for this block: the batch goes as it is */
+      wc->open = -1;
+      pthread_cond_broadcast(&wc->cond);
+      continue;
+    }
+    for (s = 0; s < wc->nslots; s++)
+      if (wc->slot[s].state == CS_FREE) break;
+    if (s < wc->nslots) {
+      b = wc->slot + s;
+      b->state = CS_OPEN;
+      b->nmembers = b->ncopied = b->ndone = b->nreads = b->leader = b->any_qual = b->errcode = 0;
+      b->bytes = 0;
+      wc->open = s;
+      break;
+    }
+    pthread_cond_wait(&wc->cond, &wc->lock);
+  }
+  first = b->nreads;
+  off = b->bytes;
+  b->nreads += n;
+  b->bytes += tot;
+  b->nmembers++;
+  if (b->nreads >= wc->target) { b->state = CS_CLOSED; wc->open = -1; }
+  pthread_mutex_unlock(&wc->lock);
+
+  /* ---- deliver the reads ---- */
+  {
+    RmapWave *bw = b->bw;
+    size_t o = off;
+    for (i = 0; i < n; i++) {
+      SEQLEN_t len;
+      const char *p = seqFastqGetConstSequence(reads[i], &len, NULL);
+      const char *q = seqFastqGetConstQualityFactors(reads[i], NULL, NULL);
+      smb_block_job *jb = b->jobs + first + i;
+      bw->read_off[first + i] = o;
+      bw->read_len[first + i] = len;
+      memcpy(bw->arena + o, p, len);
+      if (q) memcpy(bw->qual + o, q, len);
+      else memset(bw->qual + o, 0xff, len); /* FASTA read: never below the threshold */
+      o += len;
+      memset(jb, 0, sizeof(*jb));
+      jb->seed_read = (uint32_t) (first + i);
+      jb->niv = -1;
+      jb->min_cover = min_cover_arr[i];
+      jb->min_swatscor = min_swatscor_arg;
+    }
+  }
+  WTICK(0);
+  pthread_mutex_lock(&wc->lock);
+  b->ncopied++;
+  if (any_qual) b->any_qual = 1;
+  comb_try_close(wc);
+  for (;;) {
+    if (b->state == CS_CLOSED && b->ncopied == b->nmembers && !b->leader) {
+      int rc;
+      b->leader = 1;
+      b->state = CS_RUNNING;
+      wc->nrunning++;
+      wc->nbatches++;
+      wc->nbatch_reads += (uint64_t) b->nreads;
+      pthread_mutex_unlock(&wc->lock);
+      rc = comb_run_gpu(errmsgp, w, b, ktuple_maxhit, min_swatscor_below_max_arg, min_basqval, target_depth, max_depth,
+			rmapflg, scormtxp, reads[valid], ssp);
+      pthread_mutex_lock(&wc->lock);
+      wc->nrunning--;
+      b->errcode = rc;
+      b->state = CS_DONE;
+      comb_try_close(wc);
+      pthread_cond_broadcast(&wc->cond);
+      break;
+    }
+    if (b->state == CS_DONE) break;
+    pthread_cond_wait(&wc->cond, &wc->lock);
+  }
+  errcode = b->errcode;
+  pthread_mutex_unlock(&wc->lock);
+  WTICK(6);
+
+  /* ---- results of the own reads ---- */
+  if (!errcode) {
+    WGROW(w->jobs, w->jobs_alloc, n, WJOB);
+    for (i = 0; i < n; i++) {
+      WJOB *jb = w->jobs + i;
+      jb->read = jb->seed_read = (uint32_t) (first + i); jb->min_cover = min_cover_arr[i]; jb->min_swatscor = min_swatscor_arg;
+      jb->readp = reads[i]; jb->rsp = rmp->rsrp; jb->niv = -1; jb->iv_first = 0; jb->blank = 1;
+    }
+    sd.w = w; sd.errmsgp = errmsgp; sd.rsfp = rsfp; sd.jobs = w->jobs; sd.emitf = emitf; sd.user = user;
+    errcode = dev_results(errmsgp, rmp, w, NULL, b->bw, b->brd, b->bc, (size_t) first, n, w->jobs, max_depth, rmapflg,
+			  matchscor, ssp, codecp, single_done, &sd);
+  }
+  WTICK(7);
+  pthread_mutex_lock(&wc->lock);
+  if (++b->ndone == b->nmembers) {
+    b->state = CS_FREE;
+    pthread_cond_broadcast(&wc->cond);
+  }
+  pthread_mutex_unlock(&wc->lock);
+  return errcode;
 }
 
 /* ------------------------------------------------------------------------------------ */
