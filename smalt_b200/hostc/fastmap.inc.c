@@ -780,7 +780,7 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
   if (!errcode && !dataB && nworkers > 1 && !g_fm_comb) {
     const char *ce = getenv("SMALT_B200_COMBINE"), *be = getenv("SMALT_B200_BATCH");
     if (!ce || atoi(ce) != 0) {
-      g_fm_comb = waveCombinerCreate(macop->htp, macop->ssp, macop->codecp, macop->scormtxp, 4,
+      g_fm_comb = waveCombinerCreate(macop->htp, macop->ssp, macop->codecp, macop->scormtxp, 6,
 				     (be && atoi(be) > 0) ? atoi(be) : 32768);
       if (!g_fm_comb) errcode = ERRCODE_FAILURE;
     }

@@ -1076,7 +1076,7 @@ typedef struct {
 struct WaveCombiner_ {
   pthread_mutex_t lock;
   pthread_cond_t cond;
-  int nslots, target, cap_reads, open, nrunning;
+  int nslots, target, cap_reads, open, nrunning, max_running;
   size_t cap_bytes;
   CombSlot slot[COMB_MAXSLOTS];
   uint64_t nbatches, nbatch_reads;
@@ -1094,6 +1094,8 @@ WaveCombiner *waveCombinerCreate(const HashTable *htp, const SeqSet *ssp, const 
   wc->nslots = nslots; wc->target = target_reads; wc->cap_reads = 2 * target_reads;
   wc->cap_bytes = (size_t) wc->cap_reads * 320;
   wc->open = -1;
+  wc->max_running = getenv("SMALT_B200_BATCHES") ? atoi(getenv("SMALT_B200_BATCHES")) : 2;
+  if (wc->max_running < 1) wc->max_running = 1;
   pthread_mutex_init(&wc->lock, NULL);
   pthread_cond_init(&wc->cond, NULL);
   for (k = 0; k < nslots; k++) {
@@ -1130,10 +1132,12 @@ int waveCombinerSlots(const WaveCombiner *wc, RmapWave **waves, uint64_t counts[
   return wc->nslots;
 }
 
-/* closes the open batch if the device is free and every member has delivered its reads (lock held) */
+/* closes the open batch if fewer than max_running batches are on the device (two, so that the copies and
+ * host synchronisations of one overlap the kernels of the other) and every member has delivered its reads
+ * (lock held) */
 static void comb_try_close(WaveCombiner *wc)
 {
-  if (wc->open >= 0 && wc->nrunning == 0) {
+  if (wc->open >= 0 && wc->nrunning < wc->max_running) {
     CombSlot *b = wc->slot + wc->open;
     if (b->state == CS_OPEN && b->nmembers > 0 && b->ncopied == b->nmembers) {
       b->state = CS_CLOSED;

@@ -21,9 +21,9 @@ B200 = os.path.join(ROOT, "smalt_b200", "bin", "smalt_b200")
 @pytest.mark.skipif(ref_binary("smalt") is None or not os.path.exists(B200), reason="needs oracle/_ref and smalt_b200/bin")
 def test_c2_full_size(tmp_path):
     n = 1_000_000
-    genome = bench.make_genome()
-    reads, pos, strand, span = bench.simulate_reads(genome, n, seed=43)
-    pref, fq, _ = bench.write_workload_files(str(tmp_path), genome, reads)
+    wl = bench.Workload(str(tmp_path), bench.CONFIGS["c2"], n)     # misc/simread 150 1000000 2.0 y 0 0 43
+    pref, fq = wl.pref, wl.files[0]
+    names = [ln[1:] for ln in wl.texts[0].split(b"\n")[0::4] if ln]
     cores = bench.host_threads()
     sams = {}
     for tag, exe in (("ref", ref_binary("smalt")), ("b200", B200)):
@@ -43,14 +43,16 @@ def test_c2_full_size(tmp_path):
     for k in range(n):
         a, b = ref[hdr + k], got[hdr + k]
         fa, fb = a.split("\t", 5), b.split("\t", 5)
-        assert fb[0] == "r%d" % k                      # every read once, in input order
+        assert fb[0].encode() == names[k]              # every read once, in input order
         if a == b:
             nsame += 1
         elif int(fa[4]) > 6 or int(fb[4]) > 6:
             ndiff += 1
         if not int(fb[1]) & 4:
             mapped += 1
-            near += abs(int(fb[3]) - 1 - int(pos[k])) <= 20 and bool(int(fb[1]) & 16) == bool(strand[k])
+            # simread names carry the origin: r_<no>_<sequence>_<position>_<mate>_<F|R>_<edits>
+            f = fb[0].split("_")
+            near += abs(int(fb[3]) - int(f[3])) <= 25 and bool(int(fb[1]) & 16) == (f[5] == "R")
     assert ndiff == 0, "%d records with MAPQ > 6 differ from the reference" % ndiff
     assert nsame > 0.999 * n
     assert mapped > 0.999 * n and near > 0.995 * n     # the simulated origins are found
@@ -58,13 +60,13 @@ def test_c2_full_size(tmp_path):
 
 @pytest.mark.skipif(ref_binary("smalt") is None or not os.path.exists(B200), reason="needs oracle/_ref and smalt_b200/bin")
 def test_c3_scaled_pairs(tmp_path):
-    """configs[2] scaled to one GPU and a few seconds (4 x 5 Mb, 250 k pairs of 2 x 150 bp, the bench's
-    paired workload): whole program against the reference's, pair by pair"""
+    """configs[2] with the genome scaled to 4 x 5 Mb and 250 k pairs of 2 x 150 bp (misc/simread, insert 400):
+    whole program against the reference's, pair by pair"""
     npairs = 250_000
-    pref, t1, t2 = bench.paired_workload(str(tmp_path), npairs)
-    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
-    open(f1, "wb").write(t1)
-    open(f2, "wb").write(t2)
+    cfg = dict(bench.CONFIGS["c3"], seqs=[5_000_000] * 4)
+    wl = bench.Workload(str(tmp_path), cfg, npairs)
+    pref, (f1, f2) = wl.pref, wl.files
+    names = [ln[1:] for ln in wl.texts[0].split(b"\n")[0::4] if ln]
     cores = bench.host_threads()
     sams = {}
     for tag, exe in (("ref", ref_binary("smalt")), ("b200", B200)):
@@ -80,7 +82,7 @@ def test_c3_scaled_pairs(tmp_path):
         same = ref[k] == got[k] and ref[k + 1] == got[k + 1]
         nsame += same
         f = [x.split("\t", 5) for x in (ref[k], ref[k + 1], got[k], got[k + 1])]
-        assert f[2][0] == f[3][0] == "r%d" % (k // 2)
+        assert f[2][0] == f[0][0] and f[3][0] == f[1][0] and names[k // 2].startswith(f[2][0].encode())   # input order
         proper += bool(int(f[2][1]) & 2)
         # a pair is comparable when no placement in it was a random draw among equals on either side
         if not same and min(int(x[4]) for x in f) > 6:
