@@ -451,7 +451,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ref-sample", type=int, default=0, help="reference arm: units per step (0: all, same job)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="cpu_baseline: units of the sample (0: config default)")
-    ap.add_argument("--threads", type=int, default=0, help="host worker threads per GPU (0: 2 x cores / GPUs)")
+    ap.add_argument("--threads", type=int, default=0, help="host worker threads per GPU (0: chosen from the cores per GPU)")
     ap.add_argument("--device-block", type=int, default=32000, help="reads per launch of the device-time pass")
     ap.add_argument("--parity", type=int, default=20000, help="units of the SAM parity check (0: none)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -471,7 +471,14 @@ def main():
     cfg = scaled_config(args)
     units = args.reads or cfg["units"]
     cores = host_threads()
-    threads = args.threads or max(1, int(round(2.0 * cores / world)))
+    # host worker threads per GPU: the paired path keeps a device stream per worker and hides device latency with
+    # twice as many workers as cores; the single-end path (workers never wait for the device, two polling device
+    # threads) wants one worker per remaining core
+    per_rank = cores / world
+    if cfg["paired"] or cfg.get("long_reads"):
+        threads = args.threads or max(1, int(round(2.0 * per_rank)))
+    else:
+        threads = args.threads or max(2, int(per_rank) - (2 if per_rank >= 8 else 0))
     tmpdir = tempfile.TemporaryDirectory()
     tmp = tmpdir.name
     wl = Workload(tmp, cfg, units, rank, local)

@@ -101,6 +101,11 @@ void smb_process_counters(unsigned long long *launches, unsigned long long *h2d_
 void *smb_host_alloc(size_t nbytes);
 void smb_host_free(void *p);
 
+/* How the calling thread waits for the device inside the batch calls: 0 (default) = it sleeps on a
+ * blocking-sync event (one context per worker thread, more threads than cores); 1 = it polls, for a thread
+ * that drives the device for many others and must not wait for a time slice on a busy host. */
+int smb_ctx_set_spin(smb_ctx *ctx, int spin);
+
 /* Makes `dst` use the index and packed reference already uploaded to `src`
  * (same device) instead of holding its own copy: one resident copy per GPU,
  * one context (stream + scratch buffers) per host worker thread. */

@@ -50,6 +50,7 @@ int smb_ctx_create(smb_ctx **out, int device) {
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_done, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_spin, cudaEventDisableTiming) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->side.stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->side.fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->side.join, cudaEventDisableTiming) != cudaSuccess) {
@@ -81,6 +82,7 @@ void smb_ctx_destroy(smb_ctx *ctx) {
   if (ctx->built.block) cudaFree(ctx->built.block);
   ctx->stage.release();
   if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+  if (ctx->ev_spin) cudaEventDestroy(ctx->ev_spin);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->side.fork) cudaEventDestroy(ctx->side.fork);
@@ -120,6 +122,12 @@ int smb_set_scoring(smb_ctx *ctx, int match, int mismatch, int gapopen, int gape
       gapext > 0 || gapext < -127 || mismatch - match < -127)
     return fail(ctx, SMB_ERRCODE_SWATEXCEED, "penalty out of range");
   make_scoring(ctx->sc, match, mismatch, gapopen, gapext);
+  return SMB_OK;
+}
+
+int smb_ctx_set_spin(smb_ctx *ctx, int spin) {
+  if (!ctx) return SMB_ERR_ARG;
+  ctx->spin = spin != 0;
   return SMB_OK;
 }
 

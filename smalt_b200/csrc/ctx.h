@@ -61,6 +61,8 @@ struct smb_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_done = nullptr;  // blocking-sync event: waiting host threads sleep instead of spinning
+  cudaEvent_t ev_spin = nullptr;  // polled event (smb_ctx_set_spin)
+  bool spin = false;
   BandSide side;                  // K3: stream of the small launches beside the packed kernel
   HostBuf stage;                  // pinned staging for the library's own host-side arrays
   DevBuf cmp;                     // K3 output compaction scratch
@@ -131,6 +133,16 @@ static inline int fail(smb_ctx *c, int code, const char *fmt, ...) {
 // Waits for the context's stream.  Uses a blocking-sync event so that a host worker thread
 // yields its core while the GPU works (one context per host thread, more threads than cores).
 static inline cudaError_t ctx_sync(smb_ctx *ctx) {
+  if (ctx->spin && ctx->ev_spin) {   // the calling thread polls: no wake-up latency on a busy host (smb_ctx_set_spin)
+    cudaError_t e = cudaEventRecord(ctx->ev_spin, ctx->stream);
+    if (e != cudaSuccess) return e;
+    while ((e = cudaEventQuery(ctx->ev_spin)) == cudaErrorNotReady) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    return e;
+  }
   cudaError_t e = cudaEventRecord(ctx->ev_done, ctx->stream);
   if (e != cudaSuccess) return e;
   return cudaEventSynchronize(ctx->ev_done);

@@ -32,6 +32,17 @@ typedef struct {
   int done;
 } FmBlockOut;
 
+/* a block of reads on its way through the pipelined single-end path: parsed by one worker, mapped in a
+ * device batch together with the blocks of other workers, turned into results by whichever worker is free */
+typedef struct FmBlock_ {
+  SeqFastq **reads;
+  uint32_t *mincov;
+  size_t n_alloc, n, chunk;
+  WaveTicket tk;
+  int inflight;
+  struct FmBlock_ *next;
+} FmBlock;
+
 typedef struct FastMap_ {
   const SmaltMapConst *macop;
   SmaltMapArgs *maps;        /* one per worker (threadsGetMem(THRTASK_PROC)) */
@@ -54,6 +65,10 @@ typedef struct FastMap_ {
   FmBlockOut *out;
   int errcode;
   uint64_t n_reads;
+  /* pipelined path */
+  pthread_cond_t cond;
+  FmBlock *blocks, *free_blk, *ready;
+  int nblocks, outstanding;
 } FastMap;
 
 typedef struct {
@@ -87,6 +102,8 @@ static FmWorker *g_fm_workers;
 static int g_fm_nworkers;
 /* device batches shared by the workers of the single-end pipeline (rmap_wave.c, WaveCombiner);
  * SMALT_B200_COMBINE=0: every worker maps its block on its own stream; SMALT_B200_BATCH: reads per batch */
+static struct FmBlock_ *g_fm_blocks;   /* block objects of the pipelined path (their read buffers persist) */
+static int g_fm_nblocks;
 static WaveCombiner *g_fm_comb;
 static FmWorker g_fm_comb_stats[8];   /* the batch slots' waves, for fm_collect_stats */
 
@@ -372,6 +389,7 @@ static int fm_parse_block(FmWorker *w, const char *data, size_t start, size_t en
   return errcode;
 }
 
+static int fm_map_parsed(FmWorker *w, size_t c, size_t n);
 static int fm_map_block(FmWorker *w, size_t c)
 {
   FastMap *fm = w->fm;
@@ -407,7 +425,21 @@ static int fm_map_block(FmWorker *w, size_t c)
     w->mincov[i] = covermin_tuple;
   }
   if (errcode) { fm_publish(fm, c, NULL, 0, errcode); return errcode; }
+  return fm_map_parsed(w, c, n);
+}
 
+/* maps the n parsed reads of w->reads (block c) on the worker's own stream and publishes the block */
+static int fm_map_parsed(FmWorker *w, size_t c, size_t n)
+{
+  FastMap *fm = w->fm;
+  const SmaltMapConst *macop = fm->macop;
+  size_t pos, buflen = 0;
+  char *buf = NULL;
+  int errcode = ERRCODE_SUCCESS;
+  FmEmit em;
+  FILE *fp;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
   /* Formatted records are captured from the reference's fprintf calls (fastprintf.h) for the
    * line-oriented formats; explicit alignment output (-a) also writes by other means and
    * goes through a memory stream. */
@@ -433,7 +465,7 @@ static int fm_map_block(FmWorker *w, size_t c)
     const int nb = (int) ((n - pos < 32000) ? n - pos : 32000);
     SeqFastq **save = w->reads;
     w->reads += pos; /* fm_emit indexes relative to the sub-block */
-    errcode = rmapSingleWaveCombined(w->errmsgp, fm->maps[w->id].rmp, w->wave, g_fm_comb, nb, w->reads, w->mincov + pos,
+    errcode = rmapSingleWave(w->errmsgp, fm->maps[w->id].rmp, w->wave, nb, w->reads, w->mincov + pos,
 			     macop->nhitmax_tuple, (int) macop->min_swatscor, macop->swatscordiff, macop->minbasq,
 			     SMALT_TARGET_DEPTH, SMALT_MAX_DEPTH, (RMAPFLG_t) (macop->rmapflg & ~RMAPFLG_ALLPAIR),
 			     macop->scormtxp, macop->rfp, macop->htp, macop->ssp, macop->codecp, fm_emit, &em);
@@ -457,6 +489,226 @@ static int fm_map_block(FmWorker *w, size_t c)
 	    (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec), t1.tv_sec + 1e-9 * t1.tv_nsec - g_t0);
   }
   return errcode;
+}
+
+/* ---- pipelined single-end path ------------------------------------------------------------ */
+/* Workers never wait for the device: a worker parses a block and delivers its reads to the open device batch
+ * (rmap_wave.c, WaveCombiner), then takes the next piece of work - preferably the results of a block whose
+ * batch has come back, else the next block to parse.  Two device threads run the batches.  Blocks are
+ * published in input order as before. */
+static void fm_block_swap_in(FmWorker *w, FmBlock *b, SeqFastq ***sr, uint32_t **sm, size_t *sa)
+{
+  *sr = w->reads; *sm = w->mincov; *sa = w->n_alloc;
+  w->reads = b->reads; w->mincov = b->mincov; w->n_alloc = b->n_alloc;
+}
+static void fm_block_swap_out(FmWorker *w, FmBlock *b, SeqFastq **sr, uint32_t *sm, size_t sa)
+{
+  b->reads = w->reads; b->mincov = w->mincov; b->n_alloc = w->n_alloc;
+  w->reads = sr; w->mincov = sm; w->n_alloc = sa;
+}
+
+static void fm_block_release(FastMap *fm, FmBlock *b)
+{
+  pthread_mutex_lock(&fm->lock);
+  b->inflight = 0;
+  b->tk.slot = -1;
+  b->next = fm->free_blk;
+  fm->free_blk = b;
+  fm->outstanding--;
+  pthread_cond_broadcast(&fm->cond);
+  pthread_mutex_unlock(&fm->lock);
+}
+
+/* results + formatting of a block whose batch is back */
+static int fm_block_results(FmWorker *w, FmBlock *b)
+{
+  FastMap *fm = w->fm;
+  const SmaltMapConst *macop = fm->macop;
+  SeqFastq **sr; uint32_t *sm; size_t sa, buflen = 0;
+  char *buf = NULL;
+  FILE *fp = NULL;
+  FmEmit em;
+  int errcode = ERRCODE_SUCCESS;
+  const int capture = !(macop->oumodflg & REPORTMODIF_ALIOUT) &&
+    (macop->outform == REPORTFMT_SAM || macop->outform == REPORTFMT_CIGAR || macop->outform == REPORTFMT_SSAHA);
+  fm_block_swap_in(w, b, &sr, &sm, &sa);
+  if (capture) {
+    if (!w->keyfp && !(w->keyfp = open_memstream(&w->keybuf, &w->keylen))) errcode = ERRCODE_NOMEM;
+    else { smbFastCaptureBegin(w->keyfp); smbShimReportWriterSetStream(w->writer, w->keyfp); }
+  } else {
+    if (!(fp = open_memstream(&buf, &buflen))) errcode = ERRCODE_NOMEM;
+    else smbShimReportWriterSetStream(w->writer, fp);
+  }
+  if (!errcode) {
+    em.w = w; em.fp = fp; em.n = b->n;
+    errcode = waveCombinerResults(w->errmsgp, fm->maps[w->id].rmp, w->wave, g_fm_comb, &b->tk, w->reads, w->mincov,
+				  (int) macop->min_swatscor, SMALT_MAX_DEPTH, (RMAPFLG_t) (macop->rmapflg & ~RMAPFLG_ALLPAIR),
+				  macop->scormtxp, macop->rfp, macop->ssp, macop->codecp, fm_emit, &em);
+    smbShimReportWriterSetStream(w->writer, NULL);
+    if (fp) {
+      if (fclose(fp) && !errcode) errcode = ERRCODE_FILEIO;
+    } else {
+      if (smbFastCaptureEnd(&buf, &buflen) && !errcode) errcode = ERRCODE_NOMEM;
+      if (fflush(w->keyfp) || w->keylen != 0) { if (!errcode) errcode = ERRCODE_ASSERT; }
+    }
+  }
+  pthread_mutex_lock(&g_stats_lock);
+  fm->n_reads += b->n;
+  pthread_mutex_unlock(&g_stats_lock);
+  fm_block_swap_out(w, b, sr, sm, sa);
+  fm_publish(fm, b->chunk, buf, buflen, errcode);
+  fm_block_release(fm, b);
+  return errcode;
+}
+
+/* parse block b->chunk and deliver it to the device batches (or map it directly when the combiner does not
+ * take it); while no batch slot is free the worker finishes blocks that are back */
+static int fm_block_parse_deliver(FmWorker *w, FmBlock *b)
+{
+  FastMap *fm = w->fm;
+  const SmaltMapConst *macop = fm->macop;
+  const size_t c = b->chunk;
+  const size_t start = fm_record_start(fm, c * fm->chunk_bytes);
+  const size_t end = (c + 1 == fm->nchunks) ? fm->len : fm_record_start(fm, (c + 1) * fm->chunk_bytes);
+  SeqFastq **sr; uint32_t *sm; size_t sa, n = 0, i;
+  int errcode, takes;
+  struct timespec t0, t1;
+  fm_block_swap_in(w, b, &sr, &sm, &sa);
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  errcode = fm_parse_block(w, fm->data, start, end, &n);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  pthread_mutex_lock(&g_stats_lock);
+  g_fm_parse_s += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+  pthread_mutex_unlock(&g_stats_lock);
+  for (i = 0; i < n && !errcode; i++) { /* per-read preparation of processMapArgs (smalt.c:1106-1127) */
+    uint32_t covermin_tuple;
+    if ((errcode = seqFastqEncode(w->reads[i], macop->codecp))) break;
+    if (macop->tupcovmin < 1.01) {
+      uint32_t readlen;
+      seqFastqGetConstSequence(w->reads[i], &readlen, NULL);
+      covermin_tuple = (uint32_t) (macop->tupcovmin * readlen);
+      if (covermin_tuple > readlen) covermin_tuple = readlen;
+    } else {
+      covermin_tuple = (uint32_t) macop->tupcovmin;
+    }
+    w->mincov[i] = covermin_tuple;
+  }
+  b->n = n;
+  takes = !errcode && n > 0 && n <= 32000 &&
+    waveCombinerTakes(g_fm_comb, (int) n, w->reads, (RMAPFLG_t) (macop->rmapflg & ~RMAPFLG_ALLPAIR), macop->htp);
+  fm_block_swap_out(w, b, sr, sm, sa);
+  if (errcode || !n) {
+    fm_publish(fm, c, NULL, 0, errcode);
+    fm_block_release(fm, b);
+    return errcode;
+  }
+  if (!takes) {   /* long reads, other modes: the block is mapped by this worker on its own stream */
+    FmBlock *keep = b;
+    SeqFastq **r2; uint32_t *m2; size_t a2;
+    fm_block_swap_in(w, keep, &r2, &m2, &a2);
+    errcode = fm_map_parsed(w, c, n);
+    fm_block_swap_out(w, keep, r2, m2, a2);
+    fm_block_release(fm, keep);
+    return errcode;
+  }
+  b->tk.slot = -1;
+  b->inflight = 1;
+  for (;;) {
+    const int rc = waveCombinerDeliver(g_fm_comb, (int) n, b->reads, b->mincov, (int) macop->min_swatscor, macop->scormtxp,
+				       macop->htp, &b->tk);
+    FmBlock *other = NULL;
+    if (rc == 0) break;
+    if (rc != 1) { fm_publish(fm, c, NULL, 0, rc); fm_block_release(fm, b); return rc; }
+    /* every batch slot is busy: finish a block that is back, or wait for one */
+    pthread_mutex_lock(&fm->lock);
+    if (fm->ready) { other = fm->ready; fm->ready = other->next; }
+    else {
+      struct timespec ts;
+      clock_gettime(CLOCK_REALTIME, &ts);
+      ts.tv_nsec += 500000;
+      if (ts.tv_nsec >= 1000000000) { ts.tv_sec++; ts.tv_nsec -= 1000000000; }
+      pthread_cond_timedwait(&fm->cond, &fm->lock, &ts);
+    }
+    pthread_mutex_unlock(&fm->lock);
+    if (other && (errcode = fm_block_results(w, other))) return errcode;
+  }
+  return ERRCODE_SUCCESS;
+}
+
+static void *fm_worker_pipe(void *arg)
+{
+  FmWorker *w = (FmWorker *) arg;
+  FastMap *fm = w->fm;
+  int rc = (pregrow_arena(), fm_worker_setup(w, fm, w->id));
+  if (rc) {
+    pthread_mutex_lock(&fm->lock);
+    if (!fm->errcode) fm->errcode = rc;
+    pthread_cond_broadcast(&fm->cond);
+    pthread_mutex_unlock(&fm->lock);
+    return NULL;
+  }
+  for (;;) {
+    FmBlock *b = NULL;
+    int mode = 0;   /* 1 results, 2 parse, 3 exit */
+    pthread_mutex_lock(&fm->lock);
+    for (;;) {
+      if (fm->ready) { b = fm->ready; fm->ready = b->next; mode = 1; break; }
+      if (!fm->errcode && fm->next_chunk < fm->nchunks && fm->free_blk) {
+	b = fm->free_blk; fm->free_blk = b->next;
+	b->chunk = fm->next_chunk++;
+	fm->outstanding++;
+	mode = 2;
+	break;
+      }
+      if ((fm->errcode || fm->next_chunk >= fm->nchunks) && fm->outstanding == 0) { mode = 3; break; }
+      pthread_cond_wait(&fm->cond, &fm->lock);
+    }
+    pthread_mutex_unlock(&fm->lock);
+    if (mode == 3) break;
+    rc = (mode == 1) ? fm_block_results(w, b) : fm_block_parse_deliver(w, b);
+    if (rc) {
+      pthread_mutex_lock(&fm->lock);
+      if (!fm->errcode) fm->errcode = rc;
+      pthread_cond_broadcast(&fm->cond);
+      pthread_mutex_unlock(&fm->lock);
+    }
+  }
+  pthread_mutex_lock(&fm->lock);
+  pthread_cond_broadcast(&fm->cond);
+  pthread_mutex_unlock(&fm->lock);
+  return NULL;
+}
+
+/* a device thread: runs closed batches, hands their blocks to the workers */
+static void *fm_device_main(void *arg)
+{
+  FastMap *fm = (FastMap *) arg;
+  const SmaltMapConst *macop = fm->macop;
+  ErrMsg *errmsgp;
+  ERRMSG_CREATE(errmsgp);
+  for (;;) {
+    int errcode = 0, k;
+    const int s = waveCombinerRunNext(errmsgp, g_fm_comb, macop->nhitmax_tuple, macop->swatscordiff, macop->minbasq,
+				      SMALT_TARGET_DEPTH, SMALT_MAX_DEPTH, (RMAPFLG_t) (macop->rmapflg & ~RMAPFLG_ALLPAIR),
+				      macop->scormtxp, NULL, macop->ssp, &errcode);
+    if (s < 0) break;
+    pthread_mutex_lock(&fm->lock);
+    if (errcode && !fm->errcode) fm->errcode = errcode;
+    for (k = 0; k < fm->nblocks; k++) {
+      FmBlock *b = fm->blocks + k;
+      if (b->inflight == 1 && b->tk.slot == s) {
+	FmBlock **pp = &fm->ready;
+	b->inflight = 2;
+	while (*pp && (*pp)->chunk < b->chunk) pp = &(*pp)->next;   /* earlier blocks first: the output is flushed in order */
+	b->next = *pp;
+	*pp = b;
+      }
+    }
+    pthread_cond_broadcast(&fm->cond);
+    pthread_mutex_unlock(&fm->lock);
+  }
+  ERRMSG_END(errmsgp);
+  return NULL;
 }
 
 /* ---- paired input ---------------------------------------------------------------------- */
@@ -697,6 +949,10 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
   int i, errcode = ERRCODE_SUCCESS;
   size_t p = 0, block = 8192, rec_bytes;
   const char *e = getenv("SMALT_B200_BLOCK");
+  {   /* pipelined single-end path (device batches are made of several blocks): smaller host blocks */
+    const char *ce = getenv("SMALT_B200_COMBINE");
+    if (!dataB && nworkers > 1 && (!ce || atoi(ce) != 0)) block = 4096;
+  }
 
   memset(&fm, 0, sizeof(fm));
   while (p < len && isspace((unsigned char) data[p])) p++;
@@ -781,11 +1037,44 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
     const char *ce = getenv("SMALT_B200_COMBINE"), *be = getenv("SMALT_B200_BATCH");
     if (!ce || atoi(ce) != 0) {
       g_fm_comb = waveCombinerCreate(macop->htp, macop->ssp, macop->codecp, macop->scormtxp, 6,
-				     (be && atoi(be) > 0) ? atoi(be) : 32768);
+				     (be && atoi(be) > 0) ? atoi(be) : 16384, nworkers >= 8);
       if (!g_fm_comb) errcode = ERRCODE_FAILURE;
     }
   }
-  if (!errcode) {
+  if (!errcode && g_fm_comb && !dataB && nworkers > 1) {
+    /* pipelined path: workers parse / deliver / finish blocks, two device threads run the combined batches */
+    const int nblk = 2 * nworkers + 8, ndev = 2;
+    pthread_t dev[2];
+    int k;
+    if (g_fm_nblocks < nblk) {
+      FmBlock *hp = (FmBlock *) realloc(g_fm_blocks, (size_t) nblk * sizeof(FmBlock));
+      if (!hp) errcode = ERRCODE_NOMEM;
+      else {
+	memset(hp + g_fm_nblocks, 0, (size_t) (nblk - g_fm_nblocks) * sizeof(FmBlock));
+	g_fm_blocks = hp;
+	g_fm_nblocks = nblk;
+      }
+    }
+    if (!errcode) {
+      pthread_cond_init(&fm.cond, NULL);
+      fm.blocks = g_fm_blocks; fm.nblocks = g_fm_nblocks;
+      fm.free_blk = fm.ready = NULL;
+      for (k = g_fm_nblocks - 1; k >= 0; k--) {
+	g_fm_blocks[k].inflight = 0; g_fm_blocks[k].tk.slot = -1;
+	g_fm_blocks[k].next = fm.free_blk; fm.free_blk = g_fm_blocks + k;
+      }
+      waveCombinerRestart(g_fm_comb);
+      tid = (pthread_t *) calloc((size_t) nworkers, sizeof(pthread_t));
+      for (k = 0; k < ndev; k++) pthread_create(dev + k, NULL, fm_device_main, &fm);
+      for (i = 0; i < nworkers; i++) pthread_create(tid + i, NULL, fm_worker_pipe, g_fm_workers + i);
+      for (i = 0; i < nworkers; i++) pthread_join(tid[i], NULL);
+      waveCombinerFlush(g_fm_comb, 1);
+      for (k = 0; k < ndev; k++) pthread_join(dev[k], NULL);
+      free(tid);
+      pthread_cond_destroy(&fm.cond);
+      errcode = fm.errcode;
+    }
+  } else if (!errcode) {
     if (nworkers == 1) {
       fm_worker_main(g_fm_workers);
     } else {
@@ -841,5 +1130,14 @@ static void fastmap_cleanup(void)
   g_fm_nworkers = 0;
   waveCombinerDelete(g_fm_comb);
   g_fm_comb = NULL;
+  for (i = 0; i < g_fm_nblocks; i++) {
+    size_t k;
+    for (k = 0; k < g_fm_blocks[i].n_alloc; k++) seqFastqDelete(g_fm_blocks[i].reads[k]);
+    free(g_fm_blocks[i].reads);
+    free(g_fm_blocks[i].mincov);
+  }
+  free(g_fm_blocks);
+  g_fm_blocks = NULL;
+  g_fm_nblocks = 0;
   memset(g_fm_comb_stats, 0, sizeof(g_fm_comb_stats));
 }

@@ -330,6 +330,13 @@ static int wave_host_cand(void)
   return state;
 }
 
+static int wave_timing(void)
+{
+  static int state = -1;
+  if (state < 0) state = getenv("SMALT_B200_TIMING") != NULL;
+  return state;
+}
+
 static int wave_skip_results(void)
 {
   static int state = -1;
@@ -1071,19 +1078,19 @@ typedef struct {
   smb_block_job *jobs;
   smb_block_read *brd;
   smb_block_cand *bc;
-  int have_pen;
+  int have_pen, have_prof;
 } CombSlot;
 struct WaveCombiner_ {
   pthread_mutex_t lock;
   pthread_cond_t cond;
-  int nslots, target, cap_reads, open, nrunning, max_running;
+  int nslots, target, cap_reads, open, nrunning, max_running, flush, stop;
   size_t cap_bytes;
   CombSlot slot[COMB_MAXSLOTS];
   uint64_t nbatches, nbatch_reads;
 };
 
 WaveCombiner *waveCombinerCreate(const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
-				 const ScoreMatrix *scormtxp, int nslots, int target_reads)
+				 const ScoreMatrix *scormtxp, int nslots, int target_reads, int spin)
 {
   WaveCombiner *wc = (WaveCombiner *) calloc(1, sizeof(*wc));
   int k;
@@ -1103,6 +1110,9 @@ WaveCombiner *waveCombinerCreate(const HashTable *htp, const SeqSet *ssp, const 
     CombSlot *b = wc->slot + k;
     if (!bw) { waveCombinerDelete(wc); return NULL; }
     b->bw = bw;
+    /* the leader of a batch drives the device for several workers: it polls instead of sleeping, so that it
+     * does not wait for a time slice after every synchronisation while the cores run results.c */
+    if (spin && !getenv("SMALT_B200_NOSPIN")) smb_ctx_set_spin(bw->ctx, 1);
     bw->read_off = (uint64_t *) wbuf_need(&bw->wb[WB_READ_OFF], (size_t) wc->cap_reads * sizeof(uint64_t));
     bw->read_len = (uint32_t *) wbuf_need(&bw->wb[WB_READ_LEN], (size_t) wc->cap_reads * sizeof(uint32_t));
     bw->info = (smb_seed_info *) wbuf_need(&bw->wb[WB_INFO], 2 * (size_t) wc->cap_reads * sizeof(smb_seed_info));
@@ -1160,11 +1170,12 @@ static int comb_run_gpu(ErrMsg *errmsgp, RmapWave *lw, CombSlot *b, int ktuple_m
   const SETSIZ_t *soffs;
   const SEQNUM_t nseq = seqSetGetOffsets(ssp, &soffs);
   (void) lw;
-  if (!b->have_pen) {
-    if ((errcode = scoreMakeProfileFromSequence(w->prof, any_read, scormtxp))) return errcode;
+  if (!b->have_pen) {   /* (the profile was made by the first worker that delivered reads to this slot) */
+    if (!b->have_prof) return ERRCODE_ASSERT;
     if ((rc = smbShimSetScoring(w->ctx, w->prof))) return gpu_fail(errmsgp, w, rc);
     b->have_pen = 1;
   }
+  (void) any_read; (void) scormtxp; (void) errcode;
   if ((rc = smb_arena_upload(w->ctx, w->arena, b->bytes))) return gpu_fail(errmsgp, w, rc);
   if ((rc = smb_seed_batch(w->ctx, w->read_off, w->read_len, n, b->any_qual ? w->qual : NULL,
 			   (uint32_t) ktuple_maxhit, HASH_MAXNHITS, min_basqval, 1, w->info,
@@ -1209,43 +1220,44 @@ static int comb_run_gpu(ErrMsg *errmsgp, RmapWave *lw, CombSlot *b, int ktuple_m
   return ERRCODE_SUCCESS;
 }
 
-int rmapSingleWaveCombined(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, WaveCombiner *wc, int n, SeqFastq **reads,
-			   const uint32_t *min_cover_arr, int ktuple_maxhit, int min_swatscor_arg,
-			   int min_swatscor_below_max_arg, UCHAR min_basqval, short target_depth, short max_depth,
-			   RMAPFLG_t rmapflg, const ScoreMatrix *scormtxp, const ResultFilter *rsfp,
-			   const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
-			   RMAPWAVE_EMITF *emitf, void *user)
+/* can this block go through the combiner?  (flags of the wave path, sizes inside the staging of a batch) */
+int waveCombinerTakes(const WaveCombiner *wc, int n, SeqFastq **reads, RMAPFLG_t rmapflg, const HashTable *htp)
 {
-  int errcode = ERRCODE_SUCCESS, i, any_qual = 0, s, first, valid = -1;
-  size_t tot = 0, off;
-  CombSlot *b;
-  SINGLEDONE sd;
-  double tw = wnow(), tc = cnow();
+  size_t tot = 0;
+  int i, valid = 0;
   UCHAR nskip;
   const UCHAR ktup = hashTableGetKtupLen(htp, &nskip);
-  short matchscor = 0, mismatchscor = 0, gapinitscor = 0, gapextscor = 0;
-
-  if (n < 1) return ERRCODE_SUCCESS;
+  if (!wc || wave_host_cand() || n < 1 || !(rmapflg & RMAPFLG_SEQBYSEQ) ||
+      (rmapflg & (RMAPFLG_NOSHRTINFO | RMAPFLG_SPLIT | RMAPFLG_CMPLXW)))
+    return 0;
   for (i = 0; i < n; i++) {
     SEQLEN_t len;
     char cod;
     seqFastqGetConstSequence(reads[i], &len, &cod);
-    if (cod != SEQCOD_MANGLED) return ERRCODE_SEQCODE;
+    if (cod != SEQCOD_MANGLED) return 0;
+    if (len >= ktup) valid = 1;
+    tot += len;
+  }
+  return valid && n <= wc->cap_reads / 2 && tot <= wc->cap_bytes / 2;
+}
+
+/* A worker hands the reads of its block to the open batch (never blocks on the device): 0 and the ticket,
+ * or 1 when no batch can take the block right now (all slots busy: the caller finishes other work first). */
+int waveCombinerDeliver(WaveCombiner *wc, int n, SeqFastq **reads, const uint32_t *min_cover_arr, int min_swatscor_arg,
+			const ScoreMatrix *scormtxp, const HashTable *htp, WaveTicket *tk)
+{
+  int i, any_qual = 0, s, first, valid = -1;
+  size_t tot = 0, off;
+  CombSlot *b;
+  UCHAR nskip;
+  const UCHAR ktup = hashTableGetKtupLen(htp, &nskip);
+  for (i = 0; i < n; i++) {
+    SEQLEN_t len;
+    seqFastqGetConstSequence(reads[i], &len, NULL);
     if (valid < 0 && len >= ktup) valid = i;
     tot += len;
     if (seqFastqGetConstQualityFactors(reads[i], NULL, NULL)) any_qual = 1;
   }
-  if (!wc || wave_host_cand() || !(rmapflg & RMAPFLG_SEQBYSEQ) || (rmapflg & (RMAPFLG_NOSHRTINFO | RMAPFLG_SPLIT | RMAPFLG_CMPLXW)) ||
-      valid < 0 || n > wc->cap_reads / 2 || tot > wc->cap_bytes / 2)
-    return rmapSingleWave(errmsgp, rmp, w, n, reads, min_cover_arr, ktuple_maxhit, min_swatscor_arg, min_swatscor_below_max_arg,
-			  min_basqval, target_depth, max_depth, rmapflg, scormtxp, rsfp, htp, ssp, codecp, emitf, user);
-  /* penalties are those of the score matrix (rmap.c:1258-1266) */
-  if ((errcode = scoreMakeProfileFromSequence(w->prof, reads[valid], scormtxp))) return errcode;
-  matchscor = scoreProfileGetAvgPenalties(&mismatchscor, &gapinitscor, &gapextscor, w->prof);
-  if ((short) (matchscor - mismatchscor) < 1 || gapextscor >= 0 || mismatchscor >= 0 || (short) (matchscor - gapinitscor) < 1)
-    return ERRCODE_ASSERT;
-
-  /* ---- join the open batch ---- */
   pthread_mutex_lock(&wc->lock);
   for (;;) {
     s = wc->open;
@@ -1259,15 +1271,17 @@ int rmapSingleWaveCombined(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, WaveCombiner
     }
     for (s = 0; s < wc->nslots; s++)
       if (wc->slot[s].state == CS_FREE) break;
-    if (s < wc->nslots) {
-      b = wc->slot + s;
-      b->state = CS_OPEN;
-      b->nmembers = b->ncopied = b->ndone = b->nreads = b->leader = b->any_qual = b->errcode = 0;
-      b->bytes = 0;
-      wc->open = s;
-      break;
-    }
-    pthread_cond_wait(&wc->cond, &wc->lock);
+    if (s >= wc->nslots) { pthread_mutex_unlock(&wc->lock); return 1; }
+    b = wc->slot + s;
+    b->state = CS_OPEN;
+    b->nmembers = b->ncopied = b->ndone = b->nreads = b->leader = b->any_qual = b->errcode = 0;
+    b->bytes = 0;
+    wc->open = s;
+    break;
+  }
+  if (!b->have_prof && valid >= 0) {   /* penalties are those of the score matrix (rmap.c:1258-1266): any read gives them */
+    if (scoreMakeProfileFromSequence(b->bw->prof, reads[valid], scormtxp)) { pthread_mutex_unlock(&wc->lock); return ERRCODE_ASSERT; }
+    b->have_prof = 1;
   }
   first = b->nreads;
   off = b->bytes;
@@ -1275,9 +1289,8 @@ int rmapSingleWaveCombined(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, WaveCombiner
   b->bytes += tot;
   b->nmembers++;
   if (b->nreads >= wc->target) { b->state = CS_CLOSED; wc->open = -1; }
+  tk->slot = (int) (b - wc->slot); tk->first = first; tk->n = n;   /* (before the batch can possibly run) */
   pthread_mutex_unlock(&wc->lock);
-
-  /* ---- deliver the reads ---- */
   {
     RmapWave *bw = b->bw;
     size_t o = off;
@@ -1299,48 +1312,115 @@ int rmapSingleWaveCombined(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, WaveCombiner
       jb->min_swatscor = min_swatscor_arg;
     }
   }
-  WTICK(0);
   pthread_mutex_lock(&wc->lock);
   b->ncopied++;
   if (any_qual) b->any_qual = 1;
   comb_try_close(wc);
+  pthread_cond_broadcast(&wc->cond);
+  pthread_mutex_unlock(&wc->lock);
+  return 0;
+}
+
+/* end of the input: whatever the open batch holds goes to the device */
+void waveCombinerFlush(WaveCombiner *wc, int stop)
+{
+  pthread_mutex_lock(&wc->lock);
+  wc->flush = 1;
+  if (stop) wc->stop = 1;
+  if (wc->open >= 0 && wc->slot[wc->open].nmembers > 0) {
+    wc->slot[wc->open].state = CS_CLOSED;
+    wc->open = -1;
+  }
+  pthread_cond_broadcast(&wc->cond);
+  pthread_mutex_unlock(&wc->lock);
+}
+
+void waveCombinerRestart(WaveCombiner *wc)
+{
+  pthread_mutex_lock(&wc->lock);
+  wc->flush = wc->stop = 0;
+  pthread_mutex_unlock(&wc->lock);
+}
+
+/* A device thread: waits for the next closed batch whose members have all delivered, runs it (seed tables,
+ * smb_block_run, smb_block_fetch) and returns its slot (>= 0), or -1 when the combiner is stopped.  *errcode
+ * = the error of the batch (its members see it in waveCombinerResults too). */
+int waveCombinerRunNext(ErrMsg *errmsgp, WaveCombiner *wc, int ktuple_maxhit, int min_swatscor_below_max_arg,
+			UCHAR min_basqval, short target_depth, short max_depth, RMAPFLG_t rmapflg,
+			const ScoreMatrix *scormtxp, SeqFastq *any_read, const SeqSet *ssp, int *errcode)
+{
+  int s, rc;
+  CombSlot *b = NULL;
+  pthread_mutex_lock(&wc->lock);
   for (;;) {
-    if (b->state == CS_CLOSED && b->ncopied == b->nmembers && !b->leader) {
-      int rc;
-      b->leader = 1;
-      b->state = CS_RUNNING;
-      wc->nrunning++;
-      wc->nbatches++;
-      wc->nbatch_reads += (uint64_t) b->nreads;
-      pthread_mutex_unlock(&wc->lock);
-      rc = comb_run_gpu(errmsgp, w, b, ktuple_maxhit, min_swatscor_below_max_arg, min_basqval, target_depth, max_depth,
-			rmapflg, scormtxp, reads[valid], ssp);
-      pthread_mutex_lock(&wc->lock);
-      wc->nrunning--;
-      b->errcode = rc;
-      b->state = CS_DONE;
-      comb_try_close(wc);
-      pthread_cond_broadcast(&wc->cond);
-      break;
+    for (s = 0; s < wc->nslots; s++) {
+      b = wc->slot + s;
+      if (b->state == CS_CLOSED && b->ncopied == b->nmembers && !b->leader) break;
     }
-    if (b->state == CS_DONE) break;
+    if (s < wc->nslots) break;
+    if (wc->stop) { pthread_mutex_unlock(&wc->lock); return -1; }
+    /* an open batch with all members in and an idle device thread: take it now (latency), do not wait for it to fill */
+    if (wc->open >= 0 && wc->slot[wc->open].nmembers > 0 && wc->slot[wc->open].ncopied == wc->slot[wc->open].nmembers) {
+      wc->slot[wc->open].state = CS_CLOSED;
+      wc->open = -1;
+      continue;
+    }
     pthread_cond_wait(&wc->cond, &wc->lock);
   }
-  errcode = b->errcode;
+  b->leader = 1;
+  b->state = CS_RUNNING;
+  wc->nrunning++;
+  wc->nbatches++;
+  wc->nbatch_reads += (uint64_t) b->nreads;
   pthread_mutex_unlock(&wc->lock);
-  WTICK(6);
+  {
+    const double t0_ = wnow();
+    rc = comb_run_gpu(errmsgp, NULL, b, ktuple_maxhit, min_swatscor_below_max_arg, min_basqval, target_depth, max_depth,
+		      rmapflg, scormtxp, any_read, ssp);
+    if (wave_timing())
+      fprintf(stderr, "smalt_b200 timing: batch slot %d: %d blocks, %d reads, device round trip %.3f ms, at %.3f s\n",
+	      s, b->nmembers, b->nreads, 1e3 * (wnow() - t0_), wnow());
+  }
+  pthread_mutex_lock(&wc->lock);
+  wc->nrunning--;
+  b->errcode = rc;
+  b->state = CS_DONE;
+  pthread_cond_broadcast(&wc->cond);
+  pthread_mutex_unlock(&wc->lock);
+  *errcode = rc;
+  return s;
+}
 
-  /* ---- results of the own reads ---- */
+/* A worker turns the device outputs of ITS reads of a finished batch into results (results.c, emitf per read
+ * in order) and gives its share of the batch back. */
+int waveCombinerResults(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, WaveCombiner *wc, const WaveTicket *tk, SeqFastq **reads,
+			const uint32_t *min_cover_arr, int min_swatscor_arg, short max_depth, RMAPFLG_t rmapflg,
+			const ScoreMatrix *scormtxp, const ResultFilter *rsfp, const SeqSet *ssp, const SeqCodec *codecp,
+			RMAPWAVE_EMITF *emitf, void *user)
+{
+  CombSlot *b = wc->slot + tk->slot;
+  const int n = tk->n, first = tk->first;
+  int errcode = b->errcode, i;
+  SINGLEDONE sd;
+  double tw = wnow(), tc = cnow();
   if (!errcode) {
-    WGROW(w->jobs, w->jobs_alloc, n, WJOB);
-    for (i = 0; i < n; i++) {
-      WJOB *jb = w->jobs + i;
-      jb->read = jb->seed_read = (uint32_t) (first + i); jb->min_cover = min_cover_arr[i]; jb->min_swatscor = min_swatscor_arg;
-      jb->readp = reads[i]; jb->rsp = rmp->rsrp; jb->niv = -1; jb->iv_first = 0; jb->blank = 1;
+    short matchscor, mismatchscor = 0, gapinitscor = 0, gapextscor = 0;
+    /* penalties are those of the score matrix (rmap.c:1258-1266): the batch's profile was made from one of its reads */
+    matchscor = scoreProfileGetAvgPenalties(&mismatchscor, &gapinitscor, &gapextscor, b->bw->prof);
+    if ((short) (matchscor - mismatchscor) < 1 || gapextscor >= 0 || mismatchscor >= 0 || (short) (matchscor - gapinitscor) < 1)
+      errcode = ERRCODE_ASSERT;
+    (void) scormtxp;
+    if (!errcode) {
+      WGROW(w->jobs, w->jobs_alloc, n, WJOB);
+      for (i = 0; i < n; i++) {
+	WJOB *jb = w->jobs + i;
+	jb->read = jb->seed_read = (uint32_t) (first + i); jb->min_cover = min_cover_arr[i]; jb->min_swatscor = min_swatscor_arg;
+	jb->readp = reads[i]; jb->rsp = rmp->rsrp; jb->niv = -1; jb->iv_first = 0; jb->blank = 1;
+      }
+      sd.w = w; sd.errmsgp = errmsgp; sd.rsfp = rsfp; sd.jobs = w->jobs; sd.emitf = emitf; sd.user = user;
+      errcode = dev_results(errmsgp, rmp, w, NULL, b->bw, b->brd, b->bc, (size_t) first, n, w->jobs, max_depth, rmapflg,
+			    matchscor, ssp, codecp, single_done, &sd);
     }
-    sd.w = w; sd.errmsgp = errmsgp; sd.rsfp = rsfp; sd.jobs = w->jobs; sd.emitf = emitf; sd.user = user;
-    errcode = dev_results(errmsgp, rmp, w, NULL, b->bw, b->brd, b->bc, (size_t) first, n, w->jobs, max_depth, rmapflg,
-			  matchscor, ssp, codecp, single_done, &sd);
   }
   WTICK(7);
   pthread_mutex_lock(&wc->lock);

@@ -23,20 +23,30 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
 		   const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
 		   RMAPWAVE_EMITF *emitf, void *user);
 /* Device batches shared by several worker threads (rmap_wave.c, "combined device batches"): nslots batches
- * in flight, a batch closes at target_reads reads or as soon as the device is free. */
+ * in flight, a batch closes at target_reads reads or as soon as a device thread is free; spin: the device
+ * threads poll instead of sleeping (worth a core each when there are many). */
 typedef struct WaveCombiner_ WaveCombiner;
 WaveCombiner *waveCombinerCreate(const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
-				 const ScoreMatrix *scormtxp, int nslots, int target_reads);
+				 const ScoreMatrix *scormtxp, int nslots, int target_reads, int spin);
 void waveCombinerDelete(WaveCombiner *wc);
 /* the waves of the batch slots (for the statistics) -> number of slots; counts: batches run, reads in them */
 int waveCombinerSlots(const WaveCombiner *wc, RmapWave **waves, uint64_t counts[2]);
-/* rmapSingleWave through the combiner (wc == NULL or a block the combiner does not take: rmapSingleWave itself) */
-int rmapSingleWaveCombined(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, WaveCombiner *wc, int n, SeqFastq **reads,
-			   const uint32_t *min_cover_arr, int ktuple_maxhit, int min_swatscor,
-			   int min_swatscor_below_max, unsigned char min_basqval, short target_depth, short max_depth,
-			   RMAPFLG_t rmapflg, const ScoreMatrix *scormtxp, const ResultFilter *rsfp,
-			   const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
-			   RMAPWAVE_EMITF *emitf, void *user);
+/* The three stages of a block that goes through the combiner (see rmap_wave.c): a worker delivers its reads
+ * (waveCombinerDeliver, 1 = no slot free right now), a device thread runs closed batches (waveCombinerRunNext ->
+ * slot or -1 after waveCombinerFlush(stop)), a worker turns its share of a finished batch into results. */
+typedef struct { int slot, first, n; } WaveTicket;
+int waveCombinerTakes(const WaveCombiner *wc, int n, SeqFastq **reads, RMAPFLG_t rmapflg, const HashTable *htp);
+int waveCombinerDeliver(WaveCombiner *wc, int n, SeqFastq **reads, const uint32_t *min_cover_arr, int min_swatscor,
+			const ScoreMatrix *scormtxp, const HashTable *htp, WaveTicket *tk);
+void waveCombinerFlush(WaveCombiner *wc, int stop);
+void waveCombinerRestart(WaveCombiner *wc);
+int waveCombinerRunNext(ErrMsg *errmsgp, WaveCombiner *wc, int ktuple_maxhit, int min_swatscor_below_max,
+			unsigned char min_basqval, short target_depth, short max_depth, RMAPFLG_t rmapflg,
+			const ScoreMatrix *scormtxp, SeqFastq *any_read, const SeqSet *ssp, int *errcode);
+int waveCombinerResults(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, WaveCombiner *wc, const WaveTicket *tk, SeqFastq **reads,
+			const uint32_t *min_cover_arr, int min_swatscor, short max_depth, RMAPFLG_t rmapflg,
+			const ScoreMatrix *scormtxp, const ResultFilter *rsfp, const SeqSet *ssp, const SeqCodec *codecp,
+			RMAPWAVE_EMITF *emitf, void *user);
 /* Paired reads: reads[2p] / reads[2p+1] = read and mate of pair p (mincov likewise).  On return
  * status[p] is RMAPPAIR_DONE (finish with rmapPairWaveFinish) or RMAPPAIR_FALLBACK (map the pair
  * with the reference's rmapPair).  ERRCODE_ARGINVAL: flag combination not handled here. */
