@@ -36,6 +36,7 @@ typedef struct {
   double host_stage_s[12];   /* summed over worker threads: staging, seed, hits, candidates, score,
 				replay, align, results, parse, and inside results: add, sort+filter, emit */
   double host_cpu_s[8];      /* thread CPU seconds of the first eight stages (no waiting for the GPU) */
+  double cand_ms;            /* the part of k1_ms spent in candidate selection / task lists / score replay */
 } smbm_stats;
 
 /* Loads <index_prefix>.smi/.sma (hashTableRead hashidx.c:1257, seqSetReadBinFil sequence.c:2521),

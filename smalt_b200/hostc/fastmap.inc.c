@@ -94,7 +94,7 @@ typedef struct {
   char *keybuf;
   size_t keylen;
   ErrMsg *errmsgp;
-  double ms_prev[3], wall_prev[11], cpu_prev[8];
+  double ms_prev[3], wall_prev[11], cpu_prev[8], cand_prev;
   uint64_t counts_prev[5];
 } FmWorker;
 
@@ -935,6 +935,7 @@ static void fm_collect_stats(FmWorker *w)
   pthread_mutex_lock(&g_stats_lock);
   for (i = 0; i < 11; i++) { g_wall[i] += wall[i] - w->wall_prev[i]; w->wall_prev[i] = wall[i]; }
   for (i = 0; i < 3; i++) { g_ms[i] += ms[i] - w->ms_prev[i]; w->ms_prev[i] = ms[i]; }
+  { const double c = rmapWaveGetCandMs(w->wave); g_ms_cand += c - w->cand_prev; w->cand_prev = c; }
   for (i = 0; i < 5; i++) { g_counts[i] += counts[i] - w->counts_prev[i]; w->counts_prev[i] = counts[i]; }
   pthread_mutex_unlock(&g_stats_lock);
 }

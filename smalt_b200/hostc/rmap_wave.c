@@ -239,6 +239,7 @@ static double cnow(void)
 #define WTICK(k) do { const double t_ = wnow(), c_ = cnow(); w->wall[k] += t_ - tw; tw = t_; \
     w->cpu[k] += c_ - tc; tc = c_; } while (0)
 void rmapWaveGetCpu(const RmapWave *w, double cpu[8]) { memcpy(cpu, w->cpu, sizeof(w->cpu)); }
+double rmapWaveGetCandMs(const RmapWave *w) { return w->ms_cand; }
 
 static int gpu_fail(ErrMsg *errmsgp, const RmapWave *w, int rc)
 {

@@ -11,6 +11,8 @@ void rmapWaveDelete(RmapWave *w);
 void rmapWaveGetStats(const RmapWave *w, double ms[3], uint64_t counts[5]);
 /* host wall-clock seconds per stage: staging, seed, hits, candidates, score, replay, align, results */
 void rmapWaveGetWall(const RmapWave *w, double wall[11]);
+/* the part of ms[0] spent in candidate selection, task lists and the score replay (block.cu) */
+double rmapWaveGetCandMs(const RmapWave *w);
 /* thread CPU seconds of the eight stages */
 void rmapWaveGetCpu(const RmapWave *w, double cpu[8]);
 /* Maps reads[0..n) (SEQCOD_MANGLED) like n calls of rmapSingle (rmap.c:1648) would and calls

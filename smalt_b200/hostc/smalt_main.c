@@ -157,7 +157,7 @@ static struct smbm_mapper *g_lib;
 static int g_fm_pairs_ok = 1;   /* paired input may use the block-parallel pipeline (SMALT_B200_PAIRS_REFIO=1: not) */
 static short g_blocksz = 2048;  /* reads per block of the reference queue path */
 static pthread_mutex_t g_stats_lock = PTHREAD_MUTEX_INITIALIZER;
-static double g_ms[3];
+static double g_ms[3], g_ms_cand;
 static uint64_t g_counts[5];
 static double g_wall[11], g_cpu[8], g_wall_enc, g_t0;
 static double g_fm_parse_s, g_fm_format_s;
@@ -724,6 +724,7 @@ static int fastmap_eligible(const SmaltMapConst *macop, const char **reason)
 static void fm_stats_reset(void)
 {
   memset(g_ms, 0, sizeof(g_ms));
+  g_ms_cand = 0;
   memset(g_counts, 0, sizeof(g_counts));
   memset(g_wall, 0, sizeof(g_wall));
   memset(g_cpu, 0, sizeof(g_cpu));
@@ -765,6 +766,7 @@ int __wrap_threadsRun(void)
 	m->stats.n_reads = nr;
 	m->stats.wall_s = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 	m->stats.k1_ms = g_ms[0]; m->stats.k2_ms = g_ms[1]; m->stats.k3_ms = g_ms[2];
+	m->stats.cand_ms = g_ms_cand;
 	m->stats.k2_tasks = g_counts[1]; m->stats.k2_cells = g_counts[2];
 	m->stats.k3_tasks = g_counts[3]; m->stats.k3_cells = g_counts[4];
 	{
