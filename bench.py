@@ -530,7 +530,7 @@ def main():
             run_step(m)
         else:   # the merge is part of a step: its file is written once before the timed region
             sam = m.map_fastq_view(wl.texts[0], wl.texts[1] if paired else None)
-            shard.merge_to_file(dist, sam, merged)
+            shard.merge_to_file(dist, sam, merged, final_size=False)
             del sam
     c0 = m.stats.as_dict()
     sampler = ClockSampler(local)
@@ -547,7 +547,7 @@ def main():
             sam = m.map_fastq_view(wl.texts[0], wl.texts[1] if paired else None)   # the mapper's own buffer, no copy
             tb = time.perf_counter()
             sam_bytes = len(sam)
-            merged_bytes = shard.merge_to_file(dist, sam, merged)   # offset writes, ends with a barrier
+            merged_bytes = shard.merge_to_file(dist, sam, merged, final_size=False)   # copies at the ranks' offsets, ends with a barrier
             del sam
             t_map += tb - ta
             t_merge += time.perf_counter() - tb

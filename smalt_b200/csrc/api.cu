@@ -896,6 +896,7 @@ int smb_hits_batch(smb_ctx *ctx, const smb_hit_req *req, int nreq, uint32_t nhit
   HitArgs ha{};
   ha.seed = ctx->seed_args; ha.req = d_req; ha.nreq = nreq; ha.nhits_alloc = nhits_alloc;
   ha.count = d_count; ha.maxhit_used = d_used; ha.errs = d_errs; ha.offset = d_off; ha.sqdat = nullptr;
+  ha.req_skip = nullptr;
   ha.list_qmask = want_qmask ? ctx->hit_qmask.as<uint8_t>() : nullptr;
   ha.qmask_off = d_qoff;
   int nl = 0;

@@ -180,7 +180,8 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
   {
     Carver c(nullptr);
     c.take<smb_hit_req>(nr + 1); c.take<uint64_t>(nr + 2); c.take<uint32_t>(nr + 1); c.take<uint32_t>(nr + 1);
-    c.take<int32_t>(nr + 1); c.take<int32_t>(nr + 1); c.take<uint32_t>(nr + 1);
+    c.take<int32_t>(nr + 1); c.take<int32_t>(nr + 1); c.take<uint32_t>(nr + 1); c.take<uint8_t>(nr + 1);
+    c.take<unsigned long long>(2 * nj + 1);
     CU(ctx->hit_meta.ensure(c.off));
   }
   Carver ch(ctx->hit_meta.p);
@@ -191,15 +192,21 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
   int32_t *d_rerrs = ch.take<int32_t>(nr + 1);
   int32_t *d_rseq = ch.take<int32_t>(nr + 1);
   a.req_ncand = ch.take<uint32_t>(nr + 1);
+  a.req_skip = ch.take<uint8_t>(nr + 1);
+  // with several reference sequences most requests are empty: mark them from the seeds' positions first
+  a.seqmask = (nseq >= 3 && nseq <= 64 && !ctx->seed_args.tab) ? ch.take<unsigned long long>(2 * nj + 1) : nullptr;
+  a.ix = ctx->seed_ix;
   a.req = d_req; a.req_seqidx = d_rseq; a.hit_off = d_off; a.req_err = d_rerrs;
   ctx->hit_qmask_valid = false;
   HitArgs ha{};
   ha.seed = ctx->seed_args; ha.req = d_req; ha.nreq = nreq; ha.nhits_alloc = nhits_alloc;
   ha.count = d_count; ha.maxhit_used = d_used; ha.errs = d_rerrs; ha.offset = d_off; ha.sqdat = nullptr;
   ha.list_qmask = nullptr; ha.qmask_off = nullptr;
+  ha.req_skip = a.req_skip;
   int nl = 0;
   Spans sp(ctx);
   CU(sp.begin(SPAN_HITS));
+  CU(launch_block_seqmask(a, st, &nl));
   CU(launch_block_reqs(a, st, &nl));
   uint64_t total_hits = 0;
   if (nreq > 0) {

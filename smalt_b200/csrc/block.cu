@@ -332,6 +332,46 @@ __device__ __forceinline__ unsigned int warp_ticket(unsigned int *cursor, int bi
 }  // namespace
 
 // ------------------------------------------------------------------------------------
+// With many reference sequences nearly all hit lists of a read are empty (collectHits asks for one list
+// per sequence and strand, rmap.c:293-318: 48 requests per read on a 24-sequence genome, ~1 of them with
+// hits).  One warp per job x strand marks the sequences that hold a position of any ranked seed; the request
+// of every other sequence is answered "empty" without looking at the seeds again.
+__global__ void __launch_bounds__(128) block_seqmask_kernel(const BlockArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (g >= 2 * a.njobs) return;
+  const smb_block_job jb = a.jobs[g >> 1];
+  const uint32_t rd = jb.seed_read, st = (uint32_t)(g & 1);
+  const uint32_t qlen = a.seed.read_len[rd];
+  const uint64_t slot = a.seed.slot_off[rd] + (st ? qlen : 0u);
+  const smb_seed_info inf = a.seed.info[2 * rd + st];
+  unsigned long long m = 0;
+  if (jb.niv >= 0 || inf.err) m = ~0ull;   // (interval searches take all seeds: not pruned)
+  else {
+    const uint32_t ns = inf.seed_rank > 0 ? inf.seed_rank : inf.n_seeds;
+    const uint32_t *posidx = a.seed.posidx + slot, *sidx = a.seed.sidx + slot;
+    for (uint32_t n = lane; n < ns; n += 32) {
+      const uint32_t *posp;
+      const uint32_t nh = fetch_positions(a.ix, posidx[sidx[n]], posp);
+      if (!posp) continue;
+      if (nh > 256u) { m = ~0ull; continue; }   // very frequent word: every sequence may hold it
+      for (uint32_t i = 0; i < nh; ++i) {
+        const uint64_t p = __ldg(posp + i);
+        int lo = 0, hi = a.nseq;                // last s with seq_offs[s] / nskip <= p
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (a.seq_offs[mid] / (uint64_t)a.nskip <= p) lo = mid; else hi = mid;
+        }
+        m |= 1ull << lo;
+        // a position on the boundary may count for the previous sequence too (hi of s == lo of s + 1 after the division)
+        if (lo > 0 && a.seq_offs[lo] / (uint64_t)a.nskip == p) m |= 1ull << (lo - 1);
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+  if (lane == 0) a.seqmask[g] = m;
+}
+
 __global__ void __launch_bounds__(128) block_reqs_kernel(const BlockArgs a) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= a.njobs) return;
@@ -354,6 +394,7 @@ __global__ void __launch_bounds__(128) block_reqs_kernel(const BlockArgs a) {
       rq.nhits_max = 0;
       a.req[r] = rq;
       a.req_seqidx[r] = sx;
+      if (a.req_skip) a.req_skip[r] = (a.seqmask && jb.niv < 0 && !((a.seqmask[2 * j + st] >> c) & 1ull)) ? 1 : 0;
     }
 }
 
@@ -842,6 +883,12 @@ __global__ void __launch_bounds__(128) block_emit_k3_kernel(const BlockArgs a, c
 }
 
 // ------------------------------------------------------------------------------------
+cudaError_t launch_block_seqmask(const BlockArgs &a, cudaStream_t st, int *nlaunch) {
+  if (a.njobs <= 0 || !a.seqmask) return cudaSuccess;
+  block_seqmask_kernel<<<(2 * a.njobs + 3) / 4, 128, 0, st>>>(a);
+  ++*nlaunch;
+  return cudaGetLastError();
+}
 cudaError_t launch_block_reqs(const BlockArgs &a, cudaStream_t st, int *nlaunch) {
   if (a.njobs <= 0) return cudaSuccess;
   block_reqs_kernel<<<(a.njobs + 127) / 128, 128, 0, st>>>(a);
@@ -882,6 +929,7 @@ cudaError_t launch_block_emit_k3(const BlockArgs &a, unsigned long long ncand, c
 cudaError_t warm_block() {
   cudaFuncAttributes f;
   cudaError_t e = cudaFuncGetAttributes(&f, block_reqs_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_seqmask_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_cands_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_emit_k2_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_exceed_kernel);

@@ -55,6 +55,9 @@ struct BlockArgs {
   int ktup, nskip, nseq, match, mismatch, gap_init, gap_ext;
   const uint64_t *seq_offs;         // [nseq + 1]
   SeedArgs seed;                    // seed tables of the last seed batch
+  Index ix;                         // its index
+  unsigned long long *seqmask;      // [2 * njobs] sequences that hold a seed position of job x strand (nullptr: not computed)
+  uint8_t *req_skip;                // [nreq] requests known to be empty
   // hit lists
   smb_hit_req *req;                 // [nreq]
   const uint32_t *job_req;          // [njobs + 1] first request of every job
@@ -97,6 +100,7 @@ struct BlockArgs {
   BlockCounters *cnt;
 };
 
+cudaError_t launch_block_seqmask(const BlockArgs &a, cudaStream_t st, int *nlaunch);
 cudaError_t launch_block_reqs(const BlockArgs &a, cudaStream_t st, int *nlaunch);
 cudaError_t launch_block_cands(const BlockArgs &a, cudaStream_t st, int *nlaunch);
 cudaError_t launch_block_emit_k2(const BlockArgs &a, unsigned long long ncand, cudaStream_t st, int *nlaunch);

@@ -159,6 +159,23 @@ struct Index {
   const uint32_t *idx, *pos, *wordidx, *posidx;
 };
 
+// hashTableFetchHitPositions (hashidx.c:1193-1212): the positions of a k-mer word found by lookup()
+__device__ __forceinline__ uint32_t fetch_positions(const Index &ix, uint32_t posidx, const uint32_t *&posp) {
+  posp = nullptr;
+  if (ix.typ == 0) {
+    if (posidx < ix.nkeys) {
+      const uint32_t s = __ldg(ix.idx + posidx);
+      posp = ix.pos + s;
+      return __ldg(ix.idx + posidx + 1) - s;
+    }
+  } else if (posidx < ix.npos) {
+    const uint32_t s = __ldg(ix.posidx + posidx);
+    posp = ix.pos + s;
+    return __ldg(ix.posidx + posidx + 1) - s;
+  }
+  return 0;
+}
+
 // per-read tables of a multi-table seed batch (smb_seed_batch_tables): perfect-hash indexes that
 // share word length and sampling step and differ in their arrays only
 struct IndexTab {
@@ -204,6 +221,7 @@ struct HitArgs {
   uint64_t *sqdat;
   uint8_t *list_qmask;        // HITQUAL mask of every list (read_len bytes each) or nullptr
   const uint64_t *qmask_off;  // [nreq] start of each list's mask
+  const uint8_t *req_skip;    // [nreq] 1: the list is known to be empty (nullptr: no such knowledge)
 };
 cudaError_t launch_hits(const Index &ix, const HitArgs &a, bool fill, cudaStream_t st, int *nlaunch);
 

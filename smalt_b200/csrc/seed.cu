@@ -59,22 +59,6 @@ __device__ __forceinline__ uint32_t lookup(const Index &ix, uint64_t word, uint3
   return 0;
 }
 
-// hashTableFetchHitPositions
-__device__ __forceinline__ uint32_t fetch_positions(const Index &ix, uint32_t posidx, const uint32_t *&posp) {
-  posp = nullptr;
-  if (ix.typ == 0) {
-    if (posidx < ix.nkeys) {
-      const uint32_t s = __ldg(ix.idx + posidx);
-      posp = ix.pos + s;
-      return __ldg(ix.idx + posidx + 1) - s;
-    }
-  } else if (posidx < ix.npos) {
-    const uint32_t s = __ldg(ix.posidx + posidx);
-    posp = ix.pos + s;
-    return __ldg(ix.posidx + posidx + 1) - s;
-  }
-  return 0;
-}
 
 // The same sort by all lanes of a warp.  The result of sort2 for a sub-array depends on nothing but
 // the sub-array, and the two parts a partitioning step leaves are disjoint - so they can be sorted
@@ -761,6 +745,10 @@ __global__ void __launch_bounds__(HITW_WARPS * 32) hits_warp_kernel(const Index 
   const int lane = threadIdx.x & 31;
   const int g = blockIdx.x * HITW_WARPS + (threadIdx.x >> 5);
   if (g >= a.nreq) return;
+  if (a.req_skip && a.req_skip[g]) {   // no seed position of this read x strand lies in the request's sequence (block.cu)
+    if (!FILL && lane == 0) { a.count[g] = 0; a.maxhit_used[g] = 0x80000000u; a.errs[g] = 0; }
+    return;
+  }
   unsigned long long *srt = s_sort[threadIdx.x >> 5];
   const smb_hit_req rq = a.req[g];
   const uint32_t rd = rq.read;

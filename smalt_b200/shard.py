@@ -70,14 +70,37 @@ def pair_shard_of(text1, text2, rank, world):
     return text1[p1[rank]:p1[rank + 1]], text2[p2[rank]:p2[rank + 1]]
 
 
-def merge_to_file(dist, local_bytes, path, header=b"", writers=4):
+_MERGE_MAPS = {}   # path -> (fd, mmap, size): the shared mapping of a merge target is kept between merges
+
+
+def _merge_map(path, need):
+    """shared read-write mapping of `path` with room for `need` bytes (grown in 256 MB steps, kept open)"""
+    import mmap
+    ent = _MERGE_MAPS.get(path)
+    if ent is not None and ent[2] >= need:
+        return ent[1]
+    if ent is not None:
+        ent[1].close()
+        os.close(ent[0])
+    size = max(1 << 20, (need + (1 << 28) - 1) >> 28 << 28)
+    fd = os.open(path, os.O_RDWR | os.O_CREAT, 0o644)
+    if os.fstat(fd).st_size < size:
+        os.ftruncate(fd, size)       # sparse: pages appear when written
+    mm = mmap.mmap(fd, size, mmap.MAP_SHARED, mmap.PROT_READ | mmap.PROT_WRITE)
+    _MERGE_MAPS[path] = (fd, mm, size)
+    return mm
+
+
+def merge_to_file(dist, local_bytes, path, header=b"", writers=8, final_size=True):
     """Host merge of the per-rank outputs in rank (= input) order, as the reference's OUTPUT task
-    orders its blocks by read number (smalt.c:966-1000): every rank writes its text at its offset
-    into ONE file - `header` (rank 0), then rank 0's records, rank 1's, ... - with pwrite; the offsets
-    are the exclusive scan of the text lengths, the only thing the ranks exchange (8 bytes each).
-    Put `path` on /dev/shm for a merge through shared memory (a file that is overwritten keeps its pages:
-    later merges into the same path are plain copies).  `writers` threads share the copy of a large text.
+    orders its blocks by read number (smalt.c:966-1000): every rank copies its text to its offset
+    in ONE file - `header` (rank 0), then rank 0's records, rank 1's, ... - through a shared mapping of
+    the file; the offsets are the exclusive scan of the text lengths, the only thing the ranks
+    exchange (8 bytes each).  Put `path` on /dev/shm for a merge through shared memory; the mapping is
+    kept between calls, so that repeated merges into the same path are plain memory copies shared by
+    `writers` threads.  final_size: rank 0 cuts the file to the merged length (after the barrier).
     Ends with a barrier; -> total bytes."""
+    import ctypes
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
@@ -86,35 +109,48 @@ def merge_to_file(dist, local_bytes, path, header=b"", writers=4):
     sizes[rank] = mine
     dist.all_reduce(sizes)
     sizes = [int(x) for x in sizes.cpu().tolist()]
+    total = sum(sizes)
     off = sum(sizes[:rank])
-    fd = os.open(path, os.O_WRONLY | os.O_CREAT, 0o644)
-    try:
-        if rank == 0:
-            os.ftruncate(fd, sum(sizes))
-            if header:
-                os.pwrite(fd, header, 0)
-                off = len(header)
-        mv = memoryview(local_bytes).cast("B")
-
-        def put(lo, hi):
-            while lo < hi:                         # (pwrite may write less than asked for)
-                lo += os.pwrite(fd, mv[lo:min(hi, lo + (1 << 28))], off + lo)
-
-        nthr = max(1, min(writers, len(mv) >> 24))   # a writer per 16 MB, the copy is the whole cost
+    mm = _merge_map(path, total)
+    dst = (ctypes.c_char * len(mm)).from_buffer(mm)
+    base = ctypes.addressof(dst)
+    if rank == 0 and header:
+        ctypes.memmove(base, header, len(header))
+        off = len(header)
+    mv = memoryview(local_bytes).cast("B")
+    n = len(mv)
+    if n:
+        src = (ctypes.c_char * n).from_buffer_copy(mv) if mv.readonly and not isinstance(local_bytes, (bytes, bytearray)) else None
+        if isinstance(local_bytes, bytes):
+            src_addr = ctypes.cast(ctypes.c_char_p(local_bytes), ctypes.c_void_p).value
+        elif src is not None:
+            src_addr = ctypes.addressof(src)
+        else:
+            src_addr = ctypes.addressof((ctypes.c_char * n).from_buffer(mv))
+        nthr = max(1, min(writers, n >> 24))     # a writer per 16 MB: the copy is the whole cost
         if nthr == 1:
-            put(0, len(mv))
+            ctypes.memmove(base + off, src_addr, n)
         else:
             import threading
-            step = (len(mv) + nthr - 1) // nthr
-            ths = [threading.Thread(target=put, args=(k * step, min(len(mv), (k + 1) * step))) for k in range(nthr)]
+            step = (n + nthr - 1) // nthr
+            ths = [threading.Thread(target=ctypes.memmove, args=(base + off + k * step, src_addr + k * step,
+                                                                 min(step, n - k * step))) for k in range(nthr)]
             for t in ths:
                 t.start()
             for t in ths:
                 t.join()
-    finally:
-        os.close(fd)
+    del dst
     dist.barrier()
-    return sum(sizes)
+    if final_size and rank == 0:
+        os.truncate(path, total)
+        ent = _MERGE_MAPS.pop(path)
+        ent[1].close()
+        os.close(ent[0])
+    elif final_size:
+        ent = _MERGE_MAPS.pop(path)
+        ent[1].close()
+        os.close(ent[0])
+    return total
 
 
 def every_nth_record(text, n, phase=0):
