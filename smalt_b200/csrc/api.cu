@@ -180,7 +180,7 @@ int smb_refseq_upload(smb_ctx *ctx, const uint32_t *words, size_t nwords, uint64
                       const uint64_t *seq_offs, int nseq) {
   if (!ctx || !words || nwords * 10u < nbases) return SMB_ERR_ARG;
   cudaSetDevice(ctx->device);
-  CU(ctx->packed.ensure(nwords * sizeof(uint32_t) + 16));
+  CU(ctx->packed.ensure(nwords * sizeof(uint32_t) + 1040));   // (slack: the K3 long-read kernel stages whole 512-byte chunks)
   CU(h2d(ctx->packed.p, words, nwords * sizeof(uint32_t), ctx->stream));
   CU(ctx_sync(ctx));
   ctx->src.packed = ctx->packed.as<uint32_t>();

@@ -194,7 +194,7 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
   a.req_ncand = ch.take<uint32_t>(nr + 1);
   a.req_skip = ch.take<uint8_t>(nr + 1);
   // with several reference sequences most requests are empty: mark them from the seeds' positions first
-  a.seqmask = (nseq >= 3 && nseq <= 64 && !ctx->seed_args.tab) ? ch.take<unsigned long long>(2 * nj + 1) : nullptr;
+  a.seqmask = (nseq >= 8 && nseq <= 64 && !ctx->seed_args.tab) ? ch.take<unsigned long long>(2 * nj + 1) : nullptr;
   a.ix = ctx->seed_ix;
   a.req = d_req; a.req_seqidx = d_rseq; a.hit_off = d_off; a.req_err = d_rerrs;
   ctx->hit_qmask_valid = false;

@@ -31,8 +31,32 @@ namespace smb {
 constexpr int BL_T = BAND_LONG_THREADS;
 constexpr int BL_STACK = 64;
 
+constexpr int BL_CH = 1024;          // window rows per staged chunk of the packed reference
+constexpr int BL_CHW = 128;          // words per chunk buffer (1024 bases = 103 words + alignment), one 512-byte bulk copy
+
+// ---- TMA (bulk async copy) staging of the packed reference window: cp.async.bulk global -> shared, completion
+// on an mbarrier (one elected thread issues, every thread waits on the barrier's phase) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t phase) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+  } while (!ok);
+}
+
 template <int D>
 struct LongSmem {
+  alignas(16) uint32_t wbuf[2][BL_CHW];   // two chunks of the packed window (TMA destinations)
+  alignas(8) unsigned long long bar[2];   // their mbarriers
   int xF[BL_T];                 // F of every thread's last diagonal, previous iteration
   int xE[BL_T];                 // E of every thread's first diagonal, this iteration
   unsigned long long red[BL_T / 32];
@@ -60,9 +84,16 @@ band_long_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
     for (int q = 0; q < 8; ++q) v |= (unsigned long long)(unsigned char)sc.S[t * 8 + q] << (q * 8);
     s_S64[t] = v;
   }
+  if (t == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   const int gi = sc.gap_init, ge = sc.gap_ext;
   unsigned long long ncell_tot = 0;
+  uint32_t phase[2] = {0u, 0u};     // parity of the next completion of each chunk barrier (uniform over the CTA)
+  const uint64_t packed_words = src.packed_nbases / 10u + 1u;
 
   for (;;) {
     if (t == 0) sm.task = atomicAdd(ticket, 1);
@@ -123,13 +154,47 @@ band_long_kernel(const Scoring sc, const SeqSrc src, const smb_band_task *__rest
       }
       sm.xF[t] = 0;
       sm.xE[t] = 0;
+      // packed windows are staged by TMA, BL_CH rows per chunk, chunk c in buffer c & 1: rows it - 127 .. it are
+      // in use in iteration it, so chunk c + 1 is requested at it = c * BL_CH + 128 (its buffer, that of chunk
+      // c - 1, is dead by then) and awaited at it = (c + 1) * BL_CH
+      const uint64_t B0 = tk.ref_off + (uint64_t)b.s_left;         // packed base index of window row 0 of this pass
+      const uint32_t w0 = (uint32_t)(B0 / 10u), dg0 = (uint32_t)(B0 - (uint64_t)w0 * 10u);
+      const int nchunks = packed ? (nrows + BL_CH - 1) / BL_CH : 0;
+      auto chunk_word = [&](int c) { return (w0 + (dg0 + (uint32_t)c * BL_CH) / 10u) & ~3u; };
+      auto chunk_issue = [&](int c) {
+        const uint32_t wl = chunk_word(c);
+        uint64_t nw = packed_words > wl ? packed_words - wl : 0;
+        if (nw > BL_CHW) nw = BL_CHW;
+        nw &= ~(uint64_t)3;                                           // whole 16-byte units
+        if (nw < 4) nw = 4;
+        bulk_load(sm.wbuf[c & 1], src.packed + wl, (uint32_t)nw * 4u, &sm.bar[c & 1]);
+      };
+      if (t == 0 && nchunks > 0) {
+        chunk_issue(0);
+        if (nchunks > 1) chunk_issue(1);
+      }
       __syncthreads();
       for (int it = 0; it < iters; ++it) {
         const int r = it - t;
         const bool rowok = r >= 0 && r < nrows && t < nthr;
+        if (nchunks > 0) {
+          const int k = it / BL_CH, ph = it - k * BL_CH;
+          if (ph == 0 && k < nchunks) { mbar_wait(&sm.bar[k & 1], phase[k & 1]); phase[k & 1] ^= 1u; }
+          if (t == 0 && ph == 128 && k >= 1 && k + 1 < nchunks) chunk_issue(k + 1);
+        }
         const int Fin = (t > 0) ? sm.xF[t - 1] : 0;       // F(r, d0-1): left neighbour, previous iteration
         const int j0 = jbase + it;
-        const int refc = rowok ? (int)ref_base(src, packed, tk.ref_off, (uint32_t)(b.s_left + r)) : 0;
+        int refc = 0;
+        if (rowok) {
+          if (packed) {
+            const uint32_t x = dg0 + (uint32_t)r, wq = x / 10u, dig = x - wq * 10u;
+            const int c = r / BL_CH;
+            const uint32_t word = sm.wbuf[c & 1][w0 + wq - chunk_word(c)];
+            refc = (int)((word >> (3u * (9u - dig))) & 7u);
+          } else {
+            refc = (int)ref_base(src, false, tk.ref_off, (uint32_t)(b.s_left + r));
+          }
+        }
         const unsigned long long srow = s_S64[refc];
         uint32_t dw[W];
 #pragma unroll

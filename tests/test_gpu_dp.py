@@ -374,8 +374,10 @@ def test_band_align_wide_kernel_geometry(ctx, orc):
     assert nmulti > 5
 
 
-def test_band_align_long_kernel_geometry(ctx, orc):
-    """Geometries of the CTA-per-task long-read kernel (band_long.cu): bands of 129..4096 diagonals (16 or 32
+@pytest.mark.parametrize("packed", [False, True])
+def test_band_align_long_kernel_geometry(ctx, orc, packed):
+    """(packed: the windows lie in the 3-bit packed reference store, which the kernel stages by bulk async
+    copies in chunks of 1024 rows; else in the byte arena.)  Geometries of the CTA-per-task long-read kernel (band_long.cu): bands of 129..4096 diagonals (16 or 32
     per thread; beyond: thread-per-task kernel), windows of 513..4000 rows, reads of up to 4000 bases with
     indel-rich errors, several local alignments per window (recursion), sub-ranges of read and window."""
     from seqgen import mutate
@@ -405,6 +407,17 @@ def test_band_align_long_kernel_geometry(ctx, orc):
     minscorlen = [int(x) for x in rng.integers(10, 40, len(pairs))]
     arena, offs = _arena(pairs)
     ctx.arena_upload(arena)
+    if packed:
+        from smalt_b200.capi import SMB_TASK_REF_PACKED
+        from smalt_b200.seqpack import pack3
+        woff, parts, pos = [], [], 0
+        for i, (rd, win) in enumerate(pairs):        # windows back to back behind gaps of 0..12 bases: every word phase
+            gap = random_seq(rng, (7 * i) % 13)
+            parts += [gap, win]
+            woff.append(pos + len(gap))
+            pos += len(gap) + len(win)
+        codes = np.concatenate(parts)
+        ctx.refseq_upload(pack3(codes), len(codes), np.array([0, len(codes)], np.uint64))
     nmulti = 0
     for sel in (slice(None), slice(3, 4)):
         idx = list(range(len(pairs)))[sel]
@@ -412,6 +425,10 @@ def test_band_align_long_kernel_geometry(ctx, orc):
         sub_offs = np.concatenate([[offs[2 * i], offs[2 * i + 1]] for i in idx] + [[0]])
         t = _band_tasks(sub_pairs, sub_offs, [args[i] for i in idx], [minscore[i] for i in idx],
                         [minscorlen[i] for i in idx])
+        if packed:
+            for k, i in enumerate(idx):
+                t[k]["ref_off"] = woff[i]
+                t[k]["flags"] = SMB_TASK_REF_PACKED
         res, first, diff, errs, cells = ctx.band_align(t)
         ocells = 0
         for k, i in enumerate(idx):
