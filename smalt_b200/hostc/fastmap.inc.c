@@ -50,6 +50,7 @@ typedef struct FastMap_ {
   const char *data;
   size_t len;
   int is_fasta;
+  int refparse;              /* SMALT_B200_REFPARSE: every block through the reference's own parser */
   /* paired input: second file, cut at the same record numbers */
   const char *dataB;
   size_t lenB;
@@ -88,8 +89,8 @@ typedef struct {
   PairWorker pw;
   int memfd;
   char fdpath[64];
-  char *scratch;             /* NUL-terminated copies of the lines of one record */
-  size_t scratch_alloc;
+  char *scratch, *scratch2;  /* names of a record whose header lines hold white space */
+  size_t scratch_alloc, scratch2_alloc;
   FILE *keyfp;               /* stream handed to the report writer while its output is captured */
   char *keybuf;
   size_t keylen;
@@ -260,19 +261,22 @@ static size_t fm_header_name(char *dst, const char *line, size_t len)
 
 /* white space (' ', 9..13) in a sequence / quality line?  Eight bytes at a time: any byte below '!'
  * counts (control characters other than white space also send the block to the reference parser,
- * which is always right). */
-static int fm_has_space(const char *p, size_t len)
+ * which is always right); with `high` also any byte beyond 0x7f. */
+static int fm_has_space(const char *p, size_t len, int high)
 {
   size_t i = 0;
-  uint64_t acc = 0;
+  uint64_t acc = 0, hi = 0;
   for (; i + 8 <= len; i += 8) {
     uint64_t w;
     memcpy(&w, p + i, 8);
     acc |= (w - 0x2121212121212121ULL) & ~w;
+    hi |= w;
   }
-  acc &= 0x8080808080808080ULL;
-  for (; i < len; i++) acc |= (uint64_t) ((unsigned char) p[i] < 0x21u);
-  return acc != 0;
+  for (; i < len; i++) {
+    acc |= (uint64_t) ((unsigned char) p[i] < 0x21u) << 7;
+    hi |= (unsigned char) p[i];
+  }
+  return ((acc | (high ? hi : 0)) & 0x8080808080808080ULL) != 0;
 }
 
 static int fm_reads_reserve(FmWorker *w, size_t n)
@@ -298,46 +302,61 @@ static int fm_reads_reserve(FmWorker *w, size_t n)
  * reference's own parser for the whole block. */
 static int fm_parse_block_fast(FmWorker *w, const char *d, size_t start, size_t end, size_t *nreads)
 {
+  const SmaltMapConst *macop = w->fm->macop;
   size_t p = start, n = 0;
   int errcode;
   *nreads = 0;
   while (p < end) {
-    const char *l[4];
+    const char *l[4], *nl;
     size_t ll[4], need;
-    int k;
-    char *name, *seq, *qnam, *qual;
-    for (k = 0; k < 4; k++) {
-      const char *nl = (p < end) ? (const char *) memchr(d + p, '\n', end - p) : NULL;
-      if (!nl) return 1;
-      l[k] = d + p;
-      ll[k] = (size_t) (nl - (d + p));
-      p = (size_t) (nl - d) + 1;
-    }
-    if (ll[0] < 1 || l[0][0] != '@' || ll[2] < 1 || l[2][0] != '+' || ll[1] < 1 || ll[1] != ll[3] ||
-	fm_has_space(l[1], ll[1]) || fm_has_space(l[3], ll[3]))
+    char *name, *qnam;
+    size_t nl_, ql_;
+    /* header and bases: up to the next line feed; '+' line: usually bare; qualities: as long as the bases */
+    if (!(nl = (const char *) memchr(d + p, '\n', end - p))) return 1;
+    l[0] = d + p; ll[0] = (size_t) (nl - l[0]); p += ll[0] + 1;
+    if (p >= end || !(nl = (const char *) memchr(d + p, '\n', end - p))) return 1;
+    l[1] = d + p; ll[1] = (size_t) (nl - l[1]); p += ll[1] + 1;
+    if (p + 1 < end && d[p] == '+' && d[p + 1] == '\n') nl = d + p + 1;
+    else if (p >= end || !(nl = (const char *) memchr(d + p, '\n', end - p))) return 1;
+    l[2] = d + p; ll[2] = (size_t) (nl - l[2]); p += ll[2] + 1;
+    l[3] = d + p; ll[3] = ll[1];
+    if (p + ll[3] >= end || d[p + ll[3]] != '\n') return 1;      /* (a shorter line shows as a line feed inside, below) */
+    p += ll[3] + 1;
+    if (ll[0] < 1 || l[0][0] != '@' || ll[2] < 1 || l[2][0] != '+' || ll[1] < 1 ||
+	fm_has_space(l[1], ll[1], 1) || fm_has_space(l[3], ll[3], 0))
       return 1;
-    need = ll[0] + ll[1] + ll[2] + ll[3] + 8;
-    if (need > w->scratch_alloc) {
-      char *hp = (char *) realloc(w->scratch, 2 * need);
-      if (!hp) return ERRCODE_NOMEM;
-      w->scratch = hp;
-      w->scratch_alloc = 2 * need;
-    }
-    name = w->scratch;
-    seq = name + ll[0] + 1;
-    qnam = seq + ll[1] + 1;
-    qual = qnam + ll[2] + 1;
-    {
-      size_t nl_ = fm_header_name(name, l[0], ll[0]), ql_ = fm_header_name(qnam, l[2], ll[2]);
+    if ((errcode = fm_reads_reserve(w, n))) return errcode;
+    if (!fm_has_space(l[0] + 1, ll[0] - 1, 0)) {   /* the usual header: one word */
+      name = (char *) l[0] + 1; nl_ = ll[0] - 1;
+    } else {
+      need = ll[0] + 8;
+      if (need > w->scratch_alloc) {
+	char *hp = (char *) realloc(w->scratch, 2 * need);
+	if (!hp) return ERRCODE_NOMEM;
+	w->scratch = hp;
+	w->scratch_alloc = 2 * need;
+      }
+      name = w->scratch;
+      nl_ = fm_header_name(name, l[0], ll[0]);
       /* setSeq (sequence.c:780-803) also strips white space at both ends of what it is given */
       while (nl_ > 0 && isspace((unsigned char) name[nl_ - 1])) nl_--;
-      while (ql_ > 0 && isspace((unsigned char) qnam[ql_ - 1])) ql_--;
-      (void) seq; (void) qual;
-      if ((errcode = fm_reads_reserve(w, n))) return errcode;
-      seqFastqBlank(w->reads[n]);
-      if ((errcode = smbShimSeqFastqLoad(w->reads[n], name, nl_, l[1], ll[1], qnam, ql_, l[3], ll[3])))
-	return errcode;
     }
+    if (ll[2] == 1) { qnam = (char *) l[2]; ql_ = 0; }
+    else {
+      need = ll[2] + 8;
+      if (need > w->scratch2_alloc) {
+	char *hp = (char *) realloc(w->scratch2, 2 * need);
+	if (!hp) return ERRCODE_NOMEM;
+	w->scratch2 = hp;
+	w->scratch2_alloc = 2 * need;
+      }
+      qnam = w->scratch2;
+      ql_ = fm_header_name(qnam, l[2], ll[2]);
+      while (ql_ > 0 && isspace((unsigned char) qnam[ql_ - 1])) ql_--;
+    }
+    /* bases stored encoded (seqFastqEncode of the per-read preparation, smalt.c:1106-1127) */
+    if ((errcode = smbShimSeqFastqLoad(w->reads[n], name, nl_, l[1], ll[1], qnam, ql_, l[3], ll[3], macop->codecp)))
+      return errcode;
     n++;
   }
   *nreads = n;
@@ -352,20 +371,20 @@ static int fm_parse_block(FmWorker *w, const char *data, size_t start, size_t en
   SeqIO *sio;
   *nreads = 0;
   if (end <= start) return ERRCODE_SUCCESS;
-  if (!fm->is_fasta && (errcode = fm_check_fastq(data, start, end, &nrec_expect))) {
-    fprintf(stderr, "smalt_b200: the read file is not plain 4-line FASTQ near byte %zu; "
-	    "rerun with SMALT_B200_REFIO=1 (the reference's own reader)\n", start);
-    return errcode;
-  }
-  if (!fm->is_fasta && !getenv("SMALT_B200_REFPARSE")) {
+  if (!fm->is_fasta && !fm->refparse) {
+    /* the fast parser accepts whole 4-line records only, so a block it accepts needs no other check */
     errcode = fm_parse_block_fast(w, data, start, end, &n);
     if (errcode != 1) {
-      if (!errcode && n != nrec_expect) errcode = ERRCODE_FASTA;
       *nreads = n;
       return errcode;
     }
     errcode = ERRCODE_SUCCESS;
     n = 0;
+  }
+  if (!fm->is_fasta && (errcode = fm_check_fastq(data, start, end, &nrec_expect))) {
+    fprintf(stderr, "smalt_b200: the read file is not plain 4-line FASTQ near byte %zu; "
+	    "rerun with SMALT_B200_REFIO=1 (the reference's own reader)\n", start);
+    return errcode;
   }
   if (ftruncate(w->memfd, 0)) return ERRCODE_FILEIO;
   for (off = start; off < end;) {
@@ -961,6 +980,7 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
   fm.macop = macop; fm.maps = maps; fm.proto = proto;
   fm.data = data + p; fm.len = len - p;
   fm.is_fasta = data[p] == '>';
+  fm.refparse = getenv("SMALT_B200_REFPARSE") != NULL;
   fm.nworkers = nworkers;
   fm.sinkf = sinkf; fm.sink_user = sink_user;
   if (dataB) { /* paired: blocks of whole records, the same record numbers in both files */
@@ -1124,6 +1144,7 @@ static void fastmap_cleanup(void)
     if (w->memfd > 0) close(w->memfd);
     if (w->keyfp) { fclose(w->keyfp); free(w->keybuf); }
     free(w->scratch);
+    free(w->scratch2);
     if (w->errmsgp) { ERRMSG_END(w->errmsgp); }
   }
   free(g_fm_workers);

@@ -55,7 +55,7 @@ int smbFiberSelfTest(int nfibers, int nitems, int *order_out, int *draws_out, in
 
 /* FASTQ record -> SeqFastq by memcpy (shim_sequence.c) */
 int smbShimSeqFastqLoad(SeqFastq *sqp, const char *name, size_t nlen, const char *seq, size_t slen,
-			const char *qnam, size_t qnlen, const char *qual, size_t qlen);
+			const char *qnam, size_t qnlen, const char *qual, size_t qlen, const SeqCodec *codep);
 
 /* per-worker report writers of the block-parallel driver (shim_report.c) */
 #include "report.h"

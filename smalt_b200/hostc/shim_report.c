@@ -65,6 +65,21 @@ int smbShimWriteSAMHeader(FILE *fp, const SeqSet *ssp, const char *prognam, cons
 extern int smbShimSeqFastqDecodeSegment(char *seq, char *qual, int *has_qual, const SeqFastq *sqp,
 					SEQLEN_t start, SEQLEN_t len, int reverse, const SeqCodec *codep);
 
+/* length of a name as copyReadNamStrToREPSTR (report.c:434-461) copies it: up to the first white space,
+ * without the "/1", "/2" mate extension if is_stripped */
+static size_t samNameLen(const char *namp, int is_stripped)
+{
+  size_t i = 0;
+  for (;; i++) {
+    const unsigned char c = (unsigned char) namp[i];
+    if (!c || c == ' ' || (c >= 9 && c <= 13)) break;
+  }
+  if (is_stripped && i > 2 && namp[i - 2] == OUFMT_NAMSTR_MATESEP &&
+      (namp[i - 1] == OUFMT_NAMSTR_MATE1 || namp[i - 1] == OUFMT_NAMSTR_MATE2))
+    i -= 2;
+  return i;
+}
+
 static __thread char *t_seqbuf;
 static __thread size_t t_seqbuf_alloc;
 
@@ -87,9 +102,6 @@ static int samRecordSingle(const ReportWriter *wrp, const REPALI *rrp, const Dif
     seqSetGetSeqDatByIndex(NULL, &s_nam, rrp->s_idx, ssp);
     diffstr = rdfsp->dstrp + rrp->dfo;
   }
-  if ((errcode = copyReadNamStrToREPSTR(&wrp->nambufp->ref_nam, 0, s_nam)) ||
-      (errcode = copyReadNameToREPSTR(&wrp->nambufp->q_nam, 1, q_sqp)))
-    return errcode;
   seqFastqGetConstSequence(q_sqp, &qlen, &cod);
 
   if (is_mapped) {
@@ -140,8 +152,9 @@ static int samRecordSingle(const ReportWriter *wrp, const REPALI *rrp, const Dif
   /* OUFMT_SAM_BEFORE "%s\t%hu\t%s\t%i\t%hi\t" (report.c:192), written field by field when the stream
    * is this thread's capture buffer */
   {
-    const char *qn = wrp->nambufp->q_nam.strp, *rn = is_mapped ? wrp->nambufp->ref_nam.strp : OUFMT_SAM_NULLSTR;
-    const size_t lq = strlen(qn), lr = strlen(rn);
+    /* the names straight from their strings (the reference copies them into REPSTR buffers first) */
+    const char *qn = q_sqp ? seqFastqGetSeqName(q_sqp) : OUFMT_SAM_NULLSTR, *rn = is_mapped ? s_nam : OUFMT_SAM_NULLSTR;
+    const size_t lq = samNameLen(qn, 1), lr = samNameLen(rn, 0);
     char *o = smbFastReserve(fp, lq + lr + 64);
     if (o) {
       char *p = o;
@@ -152,7 +165,7 @@ static int samRecordSingle(const ReportWriter *wrp, const REPALI *rrp, const Dif
       p += smbFastPutInt(p, (short) rrp->mapscor); *p++ = '\t';
       smbFastCommit((size_t) (p - o));
     } else
-      fprintf(fp, OUFMT_SAM_BEFORE, qn, samflg, rn, pos, rrp->mapscor);
+      fprintf(fp, "%.*s\t%hu\t%.*s\t%i\t%hi\t", (int) lq, qn, samflg, (int) lr, rn, pos, rrp->mapscor);
   }
   if (is_mapped) {
     errcode = diffStrPrintf(fp, diffstr,
@@ -164,7 +177,8 @@ static int samRecordSingle(const ReportWriter *wrp, const REPALI *rrp, const Dif
   }
   /* OUFMT_SAM_AFTER "\t%s\t%i\t%i\t%s\t%s\tNM:i:%i\tAS:i:%i\n" (report.c:194) */
   {
-    const size_t ls = strlen(seqstr), lq = strlen(qualstr);
+    const size_t ls = (want_seq && qseg_len > 0) ? (size_t) qseg_len : strlen(seqstr);
+    const size_t lq = (want_seq && has_qual && qseg_len > 0) ? (size_t) qseg_len : strlen(qualstr);
     char *o = smbFastReserve(fp, ls + lq + 96);
     if (o) {
       char *p = o;

@@ -146,7 +146,8 @@ def test_mapreads_two_gpus(tmp_path):
 @needs
 def test_fast_record_loader_equals_reference_parser(tmp_path):
     """read names with comments, tabs and runs of blanks, '+name' separator lines, quality lines
-    that start with '@' or '+', CRLF records (those fall back to the reference parser)"""
+    that start with '@' or '+', lower-case and ambiguous bases (encoded while they are loaded),
+    CRLF records (those fall back to the reference parser)"""
     from smalt_b200.mapper import Mapper
     rng = np.random.default_rng(31)
     g = random_seq(rng, 80_000)
@@ -158,6 +159,11 @@ def test_fast_record_loader_equals_reference_parser(tmp_path):
         L = int(rng.integers(40, 130))
         st = int(rng.integers(0, len(g) - L))
         sq = LET[mutate(rng, g[st:st + L].copy(), p_sub=0.02, p_ins=0.002, p_del=0.002)].tobytes().decode()
+        if i % 7 == 0:
+            sq = sq.lower()                   # lower case, N, other IUPAC letters: the encoder's table
+        if i % 11 == 0:
+            k = int(rng.integers(0, len(sq)))
+            sq = sq[:k] + "NnRy"[i % 4] + sq[k + 1:]
         q = "".join(chr(int(x)) for x in rng.integers(40, 74, len(sq)))
         if i % 3 == 0:
             q = "@" + q[1:]
