@@ -971,7 +971,7 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
   const char *e = getenv("SMALT_B200_BLOCK");
   {   /* pipelined single-end path (device batches are made of several blocks): smaller host blocks */
     const char *ce = getenv("SMALT_B200_COMBINE");
-    if (!dataB && nworkers > 1 && (!ce || atoi(ce) != 0)) block = 4096;
+    if (!dataB && nworkers > 1 && (!ce || atoi(ce) != 0)) block = nworkers >= 8 ? 2048 : 4096;
   }
 
   memset(&fm, 0, sizeof(fm));
@@ -1057,14 +1057,16 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
   if (!errcode && !dataB && nworkers > 1 && !g_fm_comb) {
     const char *ce = getenv("SMALT_B200_COMBINE"), *be = getenv("SMALT_B200_BATCH");
     if (!ce || atoi(ce) != 0) {
+      const char *se = getenv("SMALT_B200_SPIN");   /* device threads poll instead of blocking (SMALT_B200_SPIN=0: block):
+						     * faster at every core count measured (2 .. 16, tools/core_sweep.py) */
       g_fm_comb = waveCombinerCreate(macop->htp, macop->ssp, macop->codecp, macop->scormtxp, 6,
-				     (be && atoi(be) > 0) ? atoi(be) : 16384, nworkers >= 8);
+				     (be && atoi(be) > 0) ? atoi(be) : 16384, se ? atoi(se) != 0 : 1);
       if (!g_fm_comb) errcode = ERRCODE_FAILURE;
     }
   }
   if (!errcode && g_fm_comb && !dataB && nworkers > 1) {
     /* pipelined path: workers parse / deliver / finish blocks, two device threads run the combined batches */
-    const int nblk = 2 * nworkers + 8, ndev = 2;
+    const int nblk = 2 * nworkers + 8, ndev = (getenv("SMALT_B200_DEVTHREADS") && atoi(getenv("SMALT_B200_DEVTHREADS")) == 1) ? 1 : 2;
     pthread_t dev[2];
     int k;
     if (g_fm_nblocks < nblk) {

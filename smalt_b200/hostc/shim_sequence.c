@@ -23,16 +23,125 @@ static int shim_load(SEQSEQ *sp, const char *s, size_t len)
 /* the bases of a record encoded while they are loaded: what seqFastqEncode (encodeSeq, sequence.c:1337-1357)
  * makes of the ASCII string - every character through codtab (the caller has made sure that there are
  * neither 0 characters nor characters beyond 0x7f, which the reference looks up with a negative index) */
-static void shim_encode_bytes(char *dst, const char *src, size_t len, const UCHAR_t *codtab)
+static void shim_encode_scalar(char *dst, const char *src, size_t len, const UCHAR_t *codtab)
 {
   size_t i;
   for (i = 0; i < len; i++) dst[i] = (char) codtab[(unsigned char) src[i]];
 }
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define SHIM_SIMD 1
+/* what the SIMD paths assume of a codec, checked once per codec and thread: the code of A, C, G, T in either
+ * case is (x ^ x >> 1) & 3 of bits 1, 2 of the letter plus (upper-case letter - 64) << 3 (make3BitMangledCodec,
+ * sequence.c:287-318), every code the encoder can produce decodes to 64 + (code >> 3), and the complement
+ * of a standard code c is codtab_complement[c & 3].  Anything else: the table loops. */
+typedef struct {
+  const SeqCodec *codec;
+  int ok;
+  char rc4[16];     /* letter of the complement of the standard code v (entries 0..3) */
+} ShimSimd;
+static __thread ShimSimd t_simd;
+
+static const ShimSimd *shim_simd(const SeqCodec *codep)
+{
+  if (t_simd.codec != codep) {
+    int i, ok = __builtin_cpu_supports("ssse3") != 0;
+    static const char acgt[] = "ACGTacgt";
+    for (i = 0; i < 8 && ok; i++) {
+      const unsigned c = (unsigned char) acgt[i], up = c & 0xDFu;
+      const unsigned code = (((up >> 1) ^ (up >> 2)) & 3u) | ((up - 64u) << 3);
+      if (codep->codtab[c] != code) ok = 0;
+    }
+    for (i = 1; i < SIZE_CODTAB && ok; i++) {
+      const unsigned code = codep->codtab[i];
+      if ((unsigned char) codep->decodtab[code] != 64u + (code >> 3)) ok = 0;
+    }
+    memset(t_simd.rc4, 0, sizeof(t_simd.rc4));
+    for (i = 0; i < 4; i++) t_simd.rc4[i] = codep->decodtab[codep->codtab_complement[i]];
+    t_simd.ok = ok;
+    t_simd.codec = codep;
+  }
+  return &t_simd;
+}
+
+__attribute__((target("ssse3")))
+static void shim_encode_simd(char *dst, const char *src, size_t len, const UCHAR_t *codtab)
+{
+  const __m128i up_mask = _mm_set1_epi8((char) 0xDF), three = _mm_set1_epi8(3), c64 = _mm_set1_epi8(64);
+  /* ACGT test: the letter must equal the table entry selected by its own low nibble ('A' 1, 'C' 3, 'D'..: 4 'T', 7 'G') */
+  const __m128i letters = _mm_setr_epi8(0, 'A', 0, 'C', 'T', 0, 0, 'G', 0, 0, 0, 0, 0, 0, 0, 0);
+  size_t i = 0;
+  for (; i + 16 <= len; i += 16) {
+    const __m128i x = _mm_loadu_si128((const __m128i *) (src + i));
+    const __m128i up = _mm_and_si128(x, up_mask);
+    const __m128i good = _mm_cmpeq_epi8(_mm_shuffle_epi8(letters, _mm_and_si128(up, _mm_set1_epi8(15))), up);
+    if (_mm_movemask_epi8(good) != 0xffff) {
+      shim_encode_scalar(dst + i, src + i, 16, codtab);
+      continue;
+    }
+    {
+      const __m128i h1 = _mm_and_si128(_mm_srli_epi16(up, 1), _mm_set1_epi8(0x7f));
+      const __m128i h2 = _mm_and_si128(_mm_srli_epi16(up, 2), _mm_set1_epi8(0x3f));
+      const __m128i a = _mm_and_si128(_mm_xor_si128(h1, h2), three);
+      const __m128i offs = _mm_sub_epi8(up, c64);                                   /* 1 .. 20 */
+      const __m128i hi = _mm_and_si128(_mm_slli_epi16(offs, 3), _mm_set1_epi8((char) 0xF8));
+      _mm_storeu_si128((__m128i *) (dst + i), _mm_or_si128(a, hi));
+    }
+  }
+  if (i < len) shim_encode_scalar(dst + i, src + i, len - i, codtab);
+}
+
+/* decoded letters of len codes; reverse: of the reverse complement (source read backwards) */
+__attribute__((target("ssse3")))
+static void shim_decode_simd(char *dst, const unsigned char *src, size_t len, int reverse, const ShimSimd *sd,
+			     const char *fwd_tab, const char *rc_tab)
+{
+  const __m128i c64 = _mm_set1_epi8(64), m1f = _mm_set1_epi8(0x1f), three = _mm_set1_epi8(3), four = _mm_set1_epi8(4);
+  const __m128i rev = _mm_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+  const __m128i rc4 = _mm_loadu_si128((const __m128i *) sd->rc4);
+  size_t i = 0;
+  if (!reverse) {
+    for (; i + 16 <= len; i += 16) {
+      const __m128i x = _mm_loadu_si128((const __m128i *) (src + i));
+      _mm_storeu_si128((__m128i *) (dst + i), _mm_add_epi8(_mm_and_si128(_mm_srli_epi16(x, 3), m1f), c64));
+    }
+    for (; i < len; i++) dst[i] = fwd_tab[src[i]];
+  } else {
+    for (; i + 16 <= len; i += 16) {
+      const __m128i x = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *) (src + len - 16 - i)), rev);
+      const __m128i own = _mm_add_epi8(_mm_and_si128(_mm_srli_epi16(x, 3), m1f), c64);
+      const __m128i comp = _mm_shuffle_epi8(rc4, _mm_and_si128(x, three));
+      const __m128i nonstd = _mm_cmpeq_epi8(_mm_and_si128(x, four), four);
+      _mm_storeu_si128((__m128i *) (dst + i), _mm_or_si128(_mm_and_si128(nonstd, own), _mm_andnot_si128(nonstd, comp)));
+    }
+    for (; i < len; i++) dst[i] = rc_tab[src[len - 1 - i]];
+  }
+}
+
+__attribute__((target("ssse3")))
+static void shim_reverse_bytes(char *dst, const char *src, size_t len)
+{
+  const __m128i rev = _mm_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
+  size_t i = 0;
+  for (; i + 16 <= len; i += 16)
+    _mm_storeu_si128((__m128i *) (dst + i), _mm_shuffle_epi8(_mm_loadu_si128((const __m128i *) (src + len - 16 - i)), rev));
+  for (; i < len; i++) dst[i] = src[len - 1 - i];
+}
+#endif
+
+static void shim_encode_bytes(char *dst, const char *src, size_t len, const SeqCodec *codep)
+{
+#ifdef SHIM_SIMD
+  if (shim_simd(codep)->ok) { shim_encode_simd(dst, src, len, codep->codtab); return; }
+#endif
+  shim_encode_scalar(dst, src, len, codep->codtab);
+}
+
 static int shim_load_encoded(SEQSEQ *sp, const char *s, size_t len, const SeqCodec *codep)
 {
   if (len + 2 >= sp->alloc_size && reallocSeqBlocks(sp, len + 2)) return ERRCODE_NOMEM;
-  shim_encode_bytes(sp->basep, s, len, codep->codtab);
+  shim_encode_bytes(sp->basep, s, len, codep);
   sp->basep[len] = '\0';
   sp->size = (SETSIZ_t) len;
   sp->code = SEQCOD_MANGLED;
@@ -91,6 +200,11 @@ int smbShimSeqFastqDecodeSegment(char *seq, char *qual, int *has_qual, const Seq
   if (start > dp->size || start + len > dp->size) return ERRCODE_ARGRANGE;
   if (SIZE_DECODTAB < 256) return ERRCODE_ASSERT;
   cp = (const unsigned char *) dp->basep + start;
+#ifdef SHIM_SIMD
+  if (shim_simd(codep)->ok) {
+    shim_decode_simd(seq, cp, len, reverse, shim_simd(codep), codep->decodtab, reverse ? shim_rc_table(codep) : NULL);
+  } else
+#endif
   if (reverse) {
     const char *rct = shim_rc_table(codep);
     const unsigned char *ep = cp + len - 1;
@@ -105,8 +219,11 @@ int smbShimSeqFastqDecodeSegment(char *seq, char *qual, int *has_qual, const Seq
   if (*has_qual && qp->size != dp->size) return ERRCODE_QUALLEN;
   if (*has_qual) {
     const char *qc = qp->basep + start;
-    if (reverse) for (i = 0; i < len; i++) qual[i] = qc[len - 1 - i];
-    else memcpy(qual, qc, len);
+    if (!reverse) memcpy(qual, qc, len);
+#ifdef SHIM_SIMD
+    else if (shim_simd(codep)->ok) shim_reverse_bytes(qual, qc, len);
+#endif
+    else for (i = 0; i < len; i++) qual[i] = qc[len - 1 - i];
     qual[len] = '\0';
   } else {
     qual[0] = '\0';

@@ -31,8 +31,11 @@ for spec in sys.argv[1:]:
     env = dict(os.environ)
     if len(f) > 2 and f[2] == "1":
         env["SMALT_B200_NOSPIN"] = "1"
-    if len(f) > 3:
+    if len(f) > 3 and f[3] != "0":
         env["SMALT_B200_BLOCK"] = f[3]
+    for kv in f[4:]:                      # further fields: NAME=value environment settings
+        k, v = kv.split("=")
+        env[k] = v
     cmd = ["taskset", "-c", "0-%d" % (cores - 1), sys.executable, __file__, "--child", tmp.name, str(workers)]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     res = [l for l in out.stdout.splitlines() if l.startswith("RESULT")]
