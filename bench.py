@@ -601,7 +601,8 @@ def main():
         "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": wall_ms, "sam_bytes_per_step": int(sam_bytes), "merged_sam_bytes_per_step": int(merged_bytes),
                 "rank0_map_ms_per_step": 1e3 * t_map / args.steps, "rank0_merge_ms_per_step": 1e3 * t_merge / args.steps,
-                "host_stage_wall_s": c1["host_stage_s"], "host_stage_cpu_s": c1["host_cpu_s"]},
+                "host_stage_wall_s": {k: v for k, v in c1["host_stage_s"].items() if v},   # (results.*: only with SMALT_B200_TIMING)
+                "host_stage_cpu_s": c1["host_cpu_s"]},
         "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
     }
     if mapped_fraction is not None:
@@ -633,14 +634,19 @@ def main():
         k1_only = s1["k1_ms"] - s1["cand_ms"]
         kernel_ms = {"k1_seed_hits": k1_only, "candidates_replay": s1["cand_ms"], "k2_sw_score": s1["k2_ms"],
                      "k3_band_align": s1["k3_ms"]}
-        roof_k3 = {"kernel": "K3 banded DP + backtrace (band_pack_kernel for short reads)", "bound": "alu", "achieved": k3_gcups,
-                   "peak": k3_peak, "unit": "GCUPS", "frac": k3_gcups / k3_peak if k3_peak else None, "traffic": 13.1e6,
+        longr = bool(cfg.get("long_reads"))
+        roof_k3 = {"kernel": "K3 banded DP + backtrace (%s)" % ("band_long_kernel<16|32>, one CTA per task, TMA-staged windows" if longr
+                                                               else "band_pack_kernel for short reads"), "bound": "alu", "achieved": k3_gcups,
+                   "peak": k3_peak, "unit": "GCUPS", "frac": k3_gcups / k3_peak if k3_peak else None,
+                   "traffic": 1143.7e6 if longr else 13.1e6,
                    "note": "integer-issue bound (no tensor/HBM bound applies to this DP): peak = measured VIADDMNMX.S16x2 issue "
                            "rate %.0f G thread-instr/s / %.1f ALU-pipe instructions per cell, the algorithmic minimum of the "
                            "restricted recurrence with directions (16 per packed cell pair, bench.py K3_OPS_PER_CELL); staging, "
                            "backtrace and lanes outside the band count against the fraction" % (peaks[3], K3_OPS_PER_CELL)}
-        roof_k2 = {"kernel": "K2 SW score (sw_score2_kernel, 2 tasks per 16 lanes)", "bound": "alu", "achieved": k2_gcups,
-                   "peak": k2_peak, "unit": "GCUPS", "frac": k2_gcups / k2_peak if k2_peak else None, "traffic": 11.8e6,
+        roof_k2 = {"kernel": "K2 SW score (%s)" % ("sw_long2_kernel, 512-column blocks, strips in HBM" if longr
+                                                    else "sw_score2_kernel, 2 tasks per 16 lanes"), "bound": "alu", "achieved": k2_gcups,
+                   "peak": k2_peak, "unit": "GCUPS", "frac": k2_gcups / k2_peak if k2_peak else None,
+                   "traffic": 9.68e9 if longr else 11.8e6,
                    "note": "DPX issue bound: peak = measured VIADDMNMX.S16x2 issue rate %.0f G thread-instr/s / %.2f "
                            "ALU-pipe instructions per cell (6.5 per packed cell pair)" % (peaks[3], K2_OPS_PER_CELL)}
         roof_k1 = {"kernel": "K1 seed tables + hit lists (seed_warp_kernel, hits_warp_kernel)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak,
@@ -669,13 +675,13 @@ def main():
         runs, err = [], None
         for _ in range(2):
             time.sleep(2.0)
-            dt, err = run_program(SMALT_B200, ["map", "-n", str(cores), "-O"] + opts + ["-o", os.path.join(tmp, "cli.sam"), wl.pref] + wl.files)
+            dt, err = run_program(SMALT_B200, ["map", "-n", str(threads), "-O"] + opts + ["-o", os.path.join(tmp, "cli.sam"), wl.pref] + wl.files)
             if not dt:
                 break
             runs.append(dt)
         dt = min(runs) if runs else None
         line["e2e_cli"] = ({"value": nreads / dt, "unit": "reads/s", "seconds": dt, "runs_seconds": runs,
-                            "what": "whole `smalt_b200 map -n %d -O` program on the same reads" % cores}
+                            "what": "whole `smalt_b200 map -n %d -O` program on the same reads" % threads}
                            if dt else {"value": None, "unavailable": err})
     if world == 1 and not args.no_cpu_baseline:
         ns = min(args.cpu_sample or units, units)
