@@ -473,13 +473,14 @@ def main():
     cores = host_threads()
     # host worker threads per GPU: the paired path keeps a device stream per worker and hides device latency with
     # twice as many workers as cores; the single-end path (workers never wait for the device, two polling device
-    # threads) wants a worker per core up to 8 cores, three cores left to the device threads beyond, and no more
-    # than 13 workers (they saturate one GPU; measured with tools/core_sweep.py: 16 cores 13 > 12 > 14 > 15 workers)
+    # threads that sleep between polls) wants a worker per core on 4 cores, one core less from 6 cores, and no more
+    # than 14 workers (they saturate one GPU; tools/core_sweep.py: 4 cores 4 > 5 > 6 workers, 8 cores 7 > 8, 16 cores
+    # 14 ~ 13 > 16)
     per_rank = cores / world
     if cfg["paired"] or cfg.get("long_reads"):
         threads = args.threads or max(1, int(round(2.0 * per_rank)))
     else:
-        threads = args.threads or min(13, max(2, int(per_rank) - (3 if per_rank >= 12 else 0)))
+        threads = args.threads or min(14, max(2, int(per_rank) - (1 if per_rank >= 6 else 0)))
     tmpdir = tempfile.TemporaryDirectory()
     tmp = tmpdir.name
     wl = Workload(tmp, cfg, units, rank, local)

@@ -103,7 +103,9 @@ void smb_host_free(void *p);
 
 /* How the calling thread waits for the device inside the batch calls: 0 (default) = it sleeps on a
  * blocking-sync event (one context per worker thread, more threads than cores); 1 = it polls, for a thread
- * that drives the device for many others and must not wait for a time slice on a busy host. */
+ * that drives the device for many others and must not wait for a time slice on a busy host; 2 = it polls
+ * with sleeps of 20 us in between (n > 2: of n us), which costs next to no CPU time - call it from the
+ * thread that will wait (the timer slack of that thread is lowered). */
 int smb_ctx_set_spin(smb_ctx *ctx, int spin);
 
 /* Makes `dst` use the index and packed reference already uploaded to `src`

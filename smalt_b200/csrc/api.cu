@@ -1,5 +1,8 @@
 // api.cu - the C ABI of include/smalt_b200.h: context, device buffers, batch entry points.
 #include "ctx.h"
+#if defined(__linux__)
+#include <sys/prctl.h>
+#endif
 #include "block.cuh"
 #include <cmath>
 #include <new>
@@ -127,7 +130,13 @@ int smb_set_scoring(smb_ctx *ctx, int match, int mismatch, int gapopen, int gape
 
 int smb_ctx_set_spin(smb_ctx *ctx, int spin) {
   if (!ctx) return SMB_ERR_ARG;
-  ctx->spin = spin != 0;
+  ctx->spin = spin < 0 ? 0 : (spin >= 2 ? 2 : spin);
+  if (spin > 2) ctx->poll_ns = (long)spin * 1000L;   // 3 and more: the sleep between polls in microseconds
+  if (ctx->spin == 2) {
+#if defined(__linux__)
+    prctl(PR_SET_TIMERSLACK, 1000UL, 0UL, 0UL, 0UL);   // of the calling thread: sleeps of tens of microseconds mean what they say
+#endif
+  }
   return SMB_OK;
 }
 

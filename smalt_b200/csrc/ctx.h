@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -62,7 +63,8 @@ struct smb_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_done = nullptr;  // blocking-sync event: waiting host threads sleep instead of spinning
   cudaEvent_t ev_spin = nullptr;  // polled event (smb_ctx_set_spin)
-  bool spin = false;
+  int spin = 0;                   // 0 block, 1 poll, 2 poll with sleeps of poll_ns (smb_ctx_set_spin)
+  long poll_ns = 20000;
   BandSide side;                  // K3: stream of the small launches beside the packed kernel
   HostBuf stage;                  // pinned staging for the library's own host-side arrays
   DevBuf cmp;                     // K3 output compaction scratch
@@ -136,6 +138,11 @@ static inline cudaError_t ctx_sync(smb_ctx *ctx) {
   if (ctx->spin && ctx->ev_spin) {   // the calling thread polls: no wake-up latency on a busy host (smb_ctx_set_spin)
     cudaError_t e = cudaEventRecord(ctx->ev_spin, ctx->stream);
     if (e != cudaSuccess) return e;
+    if (ctx->spin == 2) {   // poll with short sleeps: the latency of a poll interval, next to no CPU time
+      struct timespec ts = {0, ctx->poll_ns > 0 ? ctx->poll_ns : 20000};
+      while ((e = cudaEventQuery(ctx->ev_spin)) == cudaErrorNotReady) nanosleep(&ts, nullptr);
+      return e;
+    }
     while ((e = cudaEventQuery(ctx->ev_spin)) == cudaErrorNotReady) {
 #if defined(__x86_64__)
       __builtin_ia32_pause();

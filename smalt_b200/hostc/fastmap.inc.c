@@ -1057,10 +1057,12 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
   if (!errcode && !dataB && nworkers > 1 && !g_fm_comb) {
     const char *ce = getenv("SMALT_B200_COMBINE"), *be = getenv("SMALT_B200_BATCH");
     if (!ce || atoi(ce) != 0) {
-      const char *se = getenv("SMALT_B200_SPIN");   /* device threads poll instead of blocking (SMALT_B200_SPIN=0: block):
-						     * faster at every core count measured (2 .. 16, tools/core_sweep.py) */
+      /* the device threads poll with 50 us sleeps instead of blocking in the driver (SMALT_B200_SPIN: 0 block, 1 spin,
+       * 2 poll with 20 us sleeps, n > 2 with n us): as fast as spinning on 16 cores, 15-25 % faster on 4 and 8, where
+       * spinning threads take the workers' cores; blocking costs a third of the throughput (tools/core_sweep.py) */
+      const char *se = getenv("SMALT_B200_SPIN");
       g_fm_comb = waveCombinerCreate(macop->htp, macop->ssp, macop->codecp, macop->scormtxp, 6,
-				     (be && atoi(be) > 0) ? atoi(be) : 16384, se ? atoi(se) != 0 : 1);
+				     (be && atoi(be) > 0) ? atoi(be) : 16384, se ? atoi(se) : 50);
       if (!g_fm_comb) errcode = ERRCODE_FAILURE;
     }
   }

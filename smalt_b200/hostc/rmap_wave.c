@@ -1120,7 +1120,7 @@ WaveCombiner *waveCombinerCreate(const HashTable *htp, const SeqSet *ssp, const 
     b->bw = bw;
     /* the leader of a batch drives the device for several workers: it polls instead of sleeping, so that it
      * does not wait for a time slice after every synchronisation while the cores run results.c */
-    if (spin && !getenv("SMALT_B200_NOSPIN")) smb_ctx_set_spin(bw->ctx, 1);
+    if (spin && !getenv("SMALT_B200_NOSPIN")) smb_ctx_set_spin(bw->ctx, spin);
     bw->read_off = (uint64_t *) wbuf_need(&bw->wb[WB_READ_OFF], (size_t) wc->cap_reads * sizeof(uint64_t));
     bw->read_len = (uint32_t *) wbuf_need(&bw->wb[WB_READ_LEN], (size_t) wc->cap_reads * sizeof(uint32_t));
     bw->info = (smb_seed_info *) wbuf_need(&bw->wb[WB_INFO], 2 * (size_t) wc->cap_reads * sizeof(smb_seed_info));
