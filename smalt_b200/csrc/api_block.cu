@@ -113,12 +113,14 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
   unsigned long long *h_tot = (unsigned long long *)(h_cnt + 1);   // a few totals read back
   uint64_t nreq64 = 0;
   uint32_t maxlen = 0;
+  int max_lists = 0;   // hit lists of the job with the most: group size of the candidate kernel
   for (int j = 0; j < njobs; ++j) {
     if (jobs[j].seed_read >= (uint32_t)ctx->seed_nreads) return fail(ctx, SMB_ERR_ARG, "job %d: read %u out of range", j, jobs[j].seed_read);
     if (jobs[j].niv >= 0 && (uint64_t)jobs[j].iv_first + (uint64_t)jobs[j].niv > (uint64_t)nivals)
       return fail(ctx, SMB_ERR_ARG, "job %d: intervals out of range", j);
     h_job_req[j] = (uint32_t)nreq64;
     nreq64 += 2ull * (uint64_t)(jobs[j].niv < 0 ? nseq : jobs[j].niv);
+    max_lists = std::max(max_lists, 2 * (jobs[j].niv < 0 ? nseq : jobs[j].niv));
     const uint32_t l = ctx->seed_len[jobs[j].seed_read];
     if (l > maxlen) maxlen = l;
   }
@@ -242,7 +244,7 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
   if (nreq > 0 && total_hits) CU(launch_hits(ctx->seed_ix, ha, true, st, &nl));
   CU(sp.end());
   CU(sp.begin(SPAN_CAND));
-  CU(launch_block_cands(a, st, &nl));
+  CU(launch_block_cands(a, max_lists, st, &nl));
   CU(launch_scan_counts(a.n_sort, njobs, d_cand_first, d_tile, st, &nl));
   CU(sp.end());
   CU(d2h(h_tot, d_cand_first + njobs, 8, st));

@@ -407,18 +407,14 @@ __global__ void __launch_bounds__(128) block_reqs_kernel(const BlockArgs a) {
 // quicksort and depth cut on the (few) keys, and the windows of the selected candidates are checked by all
 // lanes.  Jobs whose lists do not fit the shared scratch (more than CW_HITS hits, reads beyond 32 * CW_MASKW
 // bases) use the per-job scratch in HBM with the same code.
-constexpr int CW_WARPS = 4;      // jobs per CTA
-constexpr int CW_HITS = 192;     // hits of a job whose seeds / segments fit the shared scratch
+// Few lists per job (one or two sequences): G = 2 .. 16 lanes per job and 32 / G jobs per warp, otherwise most
+// lanes of the warp would idle (5.6 of 32 busy on a one-sequence genome, profiles/r2_ncu_full_cands_*).
+constexpr int CW_WARPS = 2;      // warps per CTA
 constexpr int CW_MASKW = 8;      // coverage mask words per lane in shared memory (reads of <= 256 bases)
-
-struct CandSmem {
-  unsigned long long sd_sqo[CW_HITS];
-  int sd_len[CW_HITS];
-  unsigned int sg_ix[CW_HITS];
-  int sg_nseed[CW_HITS];
-  unsigned int sg_cover[CW_HITS];
-  unsigned int mask[32 * CW_MASKW];
-};
+// hits of a job whose seeds / segments fit the shared scratch, by group size
+__host__ __device__ constexpr int cw_hits(int G) { return G >= 32 ? 192 : G >= 16 ? 160 : G >= 8 ? 128 : G >= 4 ? 96 : 64; }
+__host__ __device__ constexpr size_t cw_job_bytes(int G) { return (size_t)cw_hits(G) * 24u; }     // u64 + 4 x 32 bit per hit
+__host__ __device__ constexpr size_t cw_warp_bytes(int G) { return (size_t)(32 / G) * cw_job_bytes(G) + 32u * CW_MASKW * 4u; }
 
 // the two largest distinct values of two (max, second) pairs
 __device__ __forceinline__ void merge_top2(uint32_t &m, uint32_t &s, uint32_t m2, uint32_t s2) {
@@ -432,13 +428,27 @@ __device__ __forceinline__ void merge_top2(uint32_t &m, uint32_t &s, uint32_t m2
   s = S;
 }
 
+template <int G>
 __global__ void __launch_bounds__(CW_WARPS * 32) block_cands_kernel(const BlockArgs a) {
-  __shared__ CandSmem s_all[CW_WARPS];
-  const unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int j = blockIdx.x * CW_WARPS + (threadIdx.x >> 5);
+  extern __shared__ __align__(16) unsigned char s_cw[];
+  constexpr int CW_HITS = cw_hits(G);
+  constexpr int JPW = 32 / G;
+  const int wlane = threadIdx.x & 31;                 // lane of the warp
+  const int lane = wlane & (G - 1);                   // lane of the job's group
+  const unsigned FULL = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (wlane - lane));   // the group's lanes
+  const int j = (blockIdx.x * CW_WARPS + (threadIdx.x >> 5)) * JPW + wlane / G;
   if (j >= a.njobs) return;
-  CandSmem &sm = s_all[threadIdx.x >> 5];
+  unsigned char *const wbase = s_cw + (size_t)(threadIdx.x >> 5) * cw_warp_bytes(G);
+  unsigned char *const jbase = wbase + (size_t)(wlane / G) * cw_job_bytes(G);
+  struct {
+    unsigned long long *sd_sqo; int *sd_len; unsigned int *sg_ix; int *sg_nseed; unsigned int *sg_cover; unsigned int *mask;
+  } sm;
+  sm.sd_sqo = (unsigned long long *)jbase;
+  sm.sd_len = (int *)(jbase + (size_t)CW_HITS * 8u);
+  sm.sg_ix = (unsigned int *)(jbase + (size_t)CW_HITS * 12u);
+  sm.sg_nseed = (int *)(jbase + (size_t)CW_HITS * 16u);
+  sm.sg_cover = (unsigned int *)(jbase + (size_t)CW_HITS * 20u);
+  sm.mask = (unsigned int *)(wbase + (size_t)JPW * cw_job_bytes(G));
   const smb_block_job jb = a.jobs[j];
   smb_block_read rd;
   memset(&rd, 0, sizeof rd);
@@ -477,11 +487,11 @@ __global__ void __launch_bounds__(CW_WARPS * 32) block_cands_kernel(const BlockA
   const uint64_t H = a.hit_off[rq0 + nl] - base;
   const uint32_t mask_words = (qlen + 31u) / 32u;
   const bool in_smem = H <= (uint64_t)CW_HITS && mask_words <= (uint32_t)CW_MASKW;
-  uint32_t *mask = mask_words <= (uint32_t)CW_MASKW ? sm.mask + lane * CW_MASKW : a.mask + ((size_t)j * 32u + lane) * a.mask_words;
+  uint32_t *mask = mask_words <= (uint32_t)CW_MASKW ? sm.mask + wlane * CW_MASKW : a.mask + ((size_t)j * 32u + lane) * a.mask_words;
 
   // ---- phase 1: the lists, 32 at a time ----
   uint32_t max_cover = 0, max2nd_cover = 0, ncand_all = 0;
-  for (int l0 = 0; l0 < nl && !rd.errcode; l0 += 32) {
+  for (int l0 = 0; l0 < nl && !rd.errcode; l0 += G) {
     const int l = l0 + lane;
     int e = 0;
     uint32_t nc = 0, mc = 0, m2 = 0;
@@ -503,7 +513,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32) block_cands_kernel(const BlockA
     // the first list (in order) with an error ends the job
     const unsigned bad = __ballot_sync(FULL, e != 0);
     if (bad) { rd.errcode = __shfl_sync(FULL, e, __ffs(bad) - 1); break; }
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = G / 2; o > 0; o >>= 1) {
       const uint32_t om = __shfl_xor_sync(FULL, mc, o), o2 = __shfl_xor_sync(FULL, m2, o);
       merge_top2(mc, m2, om, o2);
       nc += __shfl_xor_sync(FULL, nc, o);
@@ -523,7 +533,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32) block_cands_kernel(const BlockA
   const uint32_t cda = inf0.cover_deficit > cdf ? inf0.cover_deficit - cdf : 0u;   // both strands: FORWARD deficit (:1674)
   uint32_t *skey = a.sort_key + base, *sidx = a.sort_idx + base;
   uint32_t nk = 0;
-  for (int l0 = 0; l0 < nl; l0 += 32) {
+  for (int l0 = 0; l0 < nl; l0 += G) {
     const int l = l0 + lane;
     uint32_t cnt = 0, nc = 0;
     uint64_t f0 = 0;
@@ -534,11 +544,11 @@ __global__ void __launch_bounds__(CW_WARPS * 32) block_cands_kernel(const BlockA
       for (uint32_t i = 0; i < nc; ++i) cnt += (a.cand[f0 + i].cover + cda >= thr);
     }
     uint32_t pos = cnt;   // inclusive scan over the lanes
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(FULL, pos, o);
+    for (int o = 1; o < G; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL, pos, o, G);
       if (lane >= o) pos += t;
     }
-    const uint32_t tot = __shfl_sync(FULL, pos, 31);
+    const uint32_t tot = __shfl_sync(FULL, pos, G - 1, G);
     pos = nk + pos - cnt;
     for (uint32_t i = 0; i < nc; ++i) {
       const uint32_t cov = a.cand[f0 + i].cover;
@@ -549,7 +559,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32) block_cands_kernel(const BlockA
     }
     nk += tot;
   }
-  __syncwarp();
+  __syncwarp(FULL);
   // ---- phase 3: the reference's quicksort and the depth cut, lane 0 (in shared memory if the keys fit) ----
   const uint32_t n_mincover = nk;
   uint32_t *wk = skey, *wi = sidx;
@@ -557,8 +567,8 @@ __global__ void __launch_bounds__(CW_WARPS * 32) block_cands_kernel(const BlockA
   if (sort_smem) {
     wk = (uint32_t *)sm.sd_sqo;
     wi = wk + CW_HITS;
-    for (uint32_t i = lane; i < nk; i += 32) { wk[i] = skey[i]; wi[i] = sidx[i]; }
-    __syncwarp();
+    for (uint32_t i = lane; i < nk; i += G) { wk[i] = skey[i]; wi[i] = sidx[i]; }
+    __syncwarp(FULL);
   }
   int serr = 0;
   if (lane == 0) {
@@ -578,11 +588,11 @@ __global__ void __launch_bounds__(CW_WARPS * 32) block_cands_kernel(const BlockA
       nk = t;
     }
   }
-  serr = __shfl_sync(FULL, serr, 0);
-  nk = __shfl_sync(FULL, nk, 0);
+  serr = __shfl_sync(FULL, serr, 0, G);
+  nk = __shfl_sync(FULL, nk, 0, G);
   if (sort_smem) {
-    __syncwarp();
-    for (uint32_t i = lane; i < n_mincover; i += 32) { skey[i] = wk[i]; sidx[i] = wi[i]; }
+    __syncwarp(FULL);
+    for (uint32_t i = lane; i < n_mincover; i += G) { skey[i] = wk[i]; sidx[i] = wi[i]; }
   }
   if (!serr && (nk > 0x7fffffffu || n_mincover > 0x7fffffffu)) serr = ERR_ASSERT;
   if (serr) { rd.errcode = serr; if (lane == 0) a.rd[j] = rd; return; }
@@ -596,7 +606,7 @@ __global__ void __launch_bounds__(CW_WARPS * 32) block_cands_kernel(const BlockA
   unsigned int multi = 0;
   unsigned long long cells = 0;
   for (int pass = 0; pass < 2 && !rd.errcode; ++pass)
-    for (uint32_t c0 = 0; c0 < nk; c0 += 32) {
+    for (uint32_t c0 = 0; c0 < nk; c0 += G) {
       const uint32_t c = c0 + lane;
       int e = 0, bin = -1;
       if (c < nk) {
@@ -619,11 +629,11 @@ __global__ void __launch_bounds__(CW_WARPS * 32) block_cands_kernel(const BlockA
         if (bad) { rd.errcode = __shfl_sync(FULL, e, __ffs(bad) - 1); break; }
       } else {   // one atomic per warp and bin
         const unsigned peers = __match_any_sync(FULL, bin);
-        if (bin >= 0 && lane == __ffs(peers) - 1) atomicAdd(&a.cnt->k2_hist[bin], (unsigned int)__popc(peers));
+        if (bin >= 0 && wlane == __ffs(peers) - 1) atomicAdd(&a.cnt->k2_hist[bin], (unsigned int)__popc(peers));
       }
     }
   if (rd.errcode) { if (lane == 0) a.rd[j] = rd; return; }   // (no candidates: the wave driver drops them too)
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = G / 2; o > 0; o >>= 1) {
     cells += __shfl_xor_sync(FULL, cells, o);
     multi = max(multi, __shfl_xor_sync(FULL, multi, o));
   }
@@ -895,11 +905,25 @@ cudaError_t launch_block_reqs(const BlockArgs &a, cudaStream_t st, int *nlaunch)
   ++*nlaunch;
   return cudaGetLastError();
 }
-cudaError_t launch_block_cands(const BlockArgs &a, cudaStream_t st, int *nlaunch) {
-  if (a.njobs <= 0) return cudaSuccess;
-  block_cands_kernel<<<(a.njobs + CW_WARPS - 1) / CW_WARPS, CW_WARPS * 32, 0, st>>>(a);
-  ++*nlaunch;
+template <int G>
+static cudaError_t launch_block_cands_g(const BlockArgs &a, cudaStream_t st) {
+  static std::atomic<unsigned long long> smem_done{0};
+  const size_t smem = cw_warp_bytes(G) * CW_WARPS;
+  const cudaError_t e = ensure_dyn_smem(block_cands_kernel<G>, (int)smem, smem_done);
+  if (e != cudaSuccess) return e;
+  const int per_cta = CW_WARPS * (32 / G);
+  block_cands_kernel<G><<<(a.njobs + per_cta - 1) / per_cta, CW_WARPS * 32, smem, st>>>(a);
   return cudaGetLastError();
+}
+// max_lists: the largest number of hit lists (2 x sequences or intervals) of a job of the block
+cudaError_t launch_block_cands(const BlockArgs &a, int max_lists, cudaStream_t st, int *nlaunch) {
+  if (a.njobs <= 0) return cudaSuccess;
+  ++*nlaunch;
+  if (max_lists <= 2) return launch_block_cands_g<2>(a, st);
+  if (max_lists <= 4) return launch_block_cands_g<4>(a, st);
+  if (max_lists <= 8) return launch_block_cands_g<8>(a, st);
+  if (max_lists <= 16) return launch_block_cands_g<16>(a, st);
+  return launch_block_cands_g<32>(a, st);
 }
 cudaError_t launch_block_emit_k2(const BlockArgs &a, unsigned long long ncand, cudaStream_t st, int *nlaunch) {
   if (!ncand) return cudaSuccess;
@@ -930,7 +954,9 @@ cudaError_t warm_block() {
   cudaFuncAttributes f;
   cudaError_t e = cudaFuncGetAttributes(&f, block_reqs_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_seqmask_kernel);
-  if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_cands_kernel);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_cands_kernel<2>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_cands_kernel<8>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_cands_kernel<32>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_emit_k2_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_exceed_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_replay_kernel);

@@ -200,20 +200,18 @@ scan1_apply(const uint32_t *__restrict__ in, int n, const unsigned long long *__
 // the thread sums are scanned through the warps (a block of reads has a few thousand jobs / requests)
 constexpr int SCAN1_SMALL_THREADS = 1024;
 constexpr int SCAN1_SMALL_MAX = SCAN1_SMALL_THREADS * 32;
+// one CTA: warp w scans the contiguous chunk [w * per, (w + 1) * per) with coalesced accesses (32 elements per
+// step: a warp scan, the running total carried in a register); chunk totals are scanned in between
 __global__ void __launch_bounds__(SCAN1_SMALL_THREADS)
 scan1_small(const uint32_t *__restrict__ in, int n, unsigned long long *__restrict__ out) {
   __shared__ unsigned long long s_warp[32];
-  const int per = (n + SCAN1_SMALL_THREADS - 1) / SCAN1_SMALL_THREADS;
-  const int b = threadIdx.x * per, e = min(n, b + per);
-  unsigned long long a = 0;
-  for (int i = b; i < e; ++i) a += in[i];
-  unsigned long long incl = a;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) s_warp[w] = incl;
+  const int per = (((n + 31) / 32) + 31) & ~31;          // elements per warp, a multiple of 32
+  const int b = w * per, e = min(n, b + per);
+  unsigned long long a = 0;
+  for (int i = b + lane; i < e; i += 32) a += in[i];
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) s_warp[w] = a;
   __syncthreads();
   if (w == 0) {
     const unsigned long long v = s_warp[lane];
@@ -225,9 +223,19 @@ scan1_small(const uint32_t *__restrict__ in, int n, unsigned long long *__restri
     s_warp[lane] = iw - v;   // exclusive over the warps
   }
   __syncthreads();
-  unsigned long long run = s_warp[w] + incl - a;
-  for (int i = b; i < e; ++i) { out[i] = run; run += in[i]; }
-  if (threadIdx.x == SCAN1_SMALL_THREADS - 1) out[n] = run;
+  unsigned long long run = s_warp[w];
+  for (int i0 = b; i0 < e; i0 += 32) {
+    const int i = i0 + lane;
+    const unsigned long long v = i < e ? in[i] : 0u;
+    unsigned long long incl = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (i < e) out[i] = run + incl - v;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (w == 31 && lane == 0) out[n] = run;
 }
 
 // out has n + 1 entries (out[n] = total); tile: compact_tiles(n) scratch words

@@ -10,16 +10,22 @@ if len(sys.argv) > 2 and sys.argv[1] == "--child":
     wl = bench.Workload(tmpdir, bench.CONFIGS["c2"], 1_000_000)
     text = wl.texts[0]
     m = Mapper(wl.pref, workers)
+    steps = []
     for _ in range(2):
+        t0 = time.perf_counter()
         m.map_fastq_nocopy(text)
+        steps.append(time.perf_counter() - t0)
     c0 = time.process_time()
     t0 = time.perf_counter()
     for _ in range(3):
+        t1 = time.perf_counter()
         m.map_fastq_nocopy(text)
+        steps.append(time.perf_counter() - t1)
     dt = (time.perf_counter() - t0) / 3
     cpu = (time.process_time() - c0) / 3
     m.close()
-    print("RESULT %.1f ms  %.2f M reads/s  cpu %.2f core-s per step" % (1e3 * dt, wl.nreads / dt / 1e6, cpu), flush=True)
+    print("RESULT %.1f ms  %.2f M reads/s  cpu %.2f core-s per step  steps(ms) %s" % (
+        1e3 * dt, wl.nreads / dt / 1e6, cpu, " ".join("%.0f" % (1e3 * x) for x in steps)), flush=True)
     sys.exit(0)
 
 tmp = tempfile.TemporaryDirectory()
