@@ -1061,15 +1061,18 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
        * 2 poll with 20 us sleeps, n > 2 with n us): as fast as spinning on 16 cores, 15-25 % faster on 4 and 8, where
        * spinning threads take the workers' cores; blocking costs a third of the throughput (tools/core_sweep.py) */
       const char *se = getenv("SMALT_B200_SPIN");
-      g_fm_comb = waveCombinerCreate(macop->htp, macop->ssp, macop->codecp, macop->scormtxp, 6,
+      g_fm_comb = waveCombinerCreate(macop->htp, macop->ssp, macop->codecp, macop->scormtxp, 8,
 				     (be && atoi(be) > 0) ? atoi(be) : 16384, se ? atoi(se) : 50);
       if (!g_fm_comb) errcode = ERRCODE_FAILURE;
     }
   }
   if (!errcode && g_fm_comb && !dataB && nworkers > 1) {
     /* pipelined path: workers parse / deliver / finish blocks, two device threads run the combined batches */
-    const int nblk = 2 * nworkers + 8, ndev = (getenv("SMALT_B200_DEVTHREADS") && atoi(getenv("SMALT_B200_DEVTHREADS")) == 1) ? 1 : 2;
-    pthread_t dev[2];
+    const char *de = getenv("SMALT_B200_DEVTHREADS");
+    /* three device threads = three batches on the device: the third fills the gaps the host synchronisations of the
+     * other two leave (1 M C2 reads, 14 workers: 91 ms with two, 85 ms with three) */
+    const int nblk = 2 * nworkers + 8, ndev = (de && atoi(de) >= 1 && atoi(de) <= 4) ? atoi(de) : 3;
+    pthread_t dev[4];
     int k;
     if (g_fm_nblocks < nblk) {
       FmBlock *hp = (FmBlock *) realloc(g_fm_blocks, (size_t) nblk * sizeof(FmBlock));
@@ -1089,6 +1092,7 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
 	g_fm_blocks[k].next = fm.free_blk; fm.free_blk = g_fm_blocks + k;
       }
       waveCombinerRestart(g_fm_comb);
+      waveCombinerSetRunning(g_fm_comb, ndev);
       tid = (pthread_t *) calloc((size_t) nworkers, sizeof(pthread_t));
       for (k = 0; k < ndev; k++) pthread_create(dev + k, NULL, fm_device_main, &fm);
       for (i = 0; i < nworkers; i++) pthread_create(tid + i, NULL, fm_worker_pipe, g_fm_workers + i);

@@ -1109,7 +1109,7 @@ WaveCombiner *waveCombinerCreate(const HashTable *htp, const SeqSet *ssp, const 
   wc->nslots = nslots; wc->target = target_reads; wc->cap_reads = 2 * target_reads;
   wc->cap_bytes = (size_t) wc->cap_reads * 320;
   wc->open = -1;
-  wc->max_running = getenv("SMALT_B200_BATCHES") ? atoi(getenv("SMALT_B200_BATCHES")) : 2;
+  wc->max_running = getenv("SMALT_B200_BATCHES") ? atoi(getenv("SMALT_B200_BATCHES")) : 3;
   if (wc->max_running < 1) wc->max_running = 1;
   pthread_mutex_init(&wc->lock, NULL);
   pthread_cond_init(&wc->cond, NULL);
@@ -1148,6 +1148,12 @@ int waveCombinerSlots(const WaveCombiner *wc, RmapWave **waves, uint64_t counts[
   for (k = 0; k < wc->nslots; k++) waves[k] = wc->slot[k].bw;
   counts[0] = wc->nbatches; counts[1] = wc->nbatch_reads;
   return wc->nslots;
+}
+
+/* batches on the device at a time = device threads of the caller (unless SMALT_B200_BATCHES says otherwise) */
+void waveCombinerSetRunning(WaveCombiner *wc, int n)
+{
+  if (wc && n >= 1 && !getenv("SMALT_B200_BATCHES")) wc->max_running = n;
 }
 
 /* closes the open batch if fewer than max_running batches are on the device (two, so that the copies and

@@ -32,6 +32,7 @@ WaveCombiner *waveCombinerCreate(const HashTable *htp, const SeqSet *ssp, const 
 				 const ScoreMatrix *scormtxp, int nslots, int target_reads, int spin);
 void waveCombinerDelete(WaveCombiner *wc);
 /* the waves of the batch slots (for the statistics) -> number of slots; counts: batches run, reads in them */
+void waveCombinerSetRunning(WaveCombiner *wc, int n);
 int waveCombinerSlots(const WaveCombiner *wc, RmapWave **waves, uint64_t counts[2]);
 /* The three stages of a block that goes through the combiner (see rmap_wave.c): a worker delivers its reads
  * (waveCombinerDeliver, 1 = no slot free right now), a device thread runs closed batches (waveCombinerRunNext ->
