@@ -471,13 +471,15 @@ def main():
     cfg = scaled_config(args)
     units = args.reads or cfg["units"]
     cores = host_threads()
-    # host worker threads per GPU: the paired path keeps a device stream per worker and hides device latency with
-    # twice as many workers as cores; the single-end path (workers never wait for the device, two polling device
+    # host worker threads per GPU: the paired and long-read paths keep a device stream per worker (long reads: twice as
+    # many workers as cores hide the device latency); the single-end path (workers never wait for the device, two polling device
     # threads that sleep between polls) wants a worker per core on 4 cores, one core less from 6 cores, and no more
     # than 14 workers (they saturate one GPU; tools/core_sweep.py: 4 cores 4 > 5 > 6 workers, 8 cores 7 > 8, 16 cores
     # 14 ~ 13 > 16)
     per_rank = cores / world
-    if cfg["paired"] or cfg.get("long_reads"):
+    if cfg["paired"]:
+        threads = args.threads or max(1, int(per_rank))         # blocks of 4096 pairs: one worker per core (C3: 16 > 24 > 32 > 12)
+    elif cfg.get("long_reads"):
         threads = args.threads or max(1, int(round(2.0 * per_rank)))
     else:
         threads = args.threads or min(14, max(2, int(per_rank) - (1 if per_rank >= 6 else 0)))

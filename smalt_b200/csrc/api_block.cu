@@ -244,7 +244,7 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
   if (nreq > 0 && total_hits) CU(launch_hits(ctx->seed_ix, ha, true, st, &nl));
   CU(sp.end());
   CU(sp.begin(SPAN_CAND));
-  CU(launch_block_cands(a, max_lists, st, &nl));
+  CU(launch_block_cands(a, max_lists, (double)total_hits / (double)njobs, st, &nl));
   CU(launch_scan_counts(a.n_sort, njobs, d_cand_first, d_tile, st, &nl));
   CU(sp.end());
   CU(d2h(h_tot, d_cand_first + njobs, 8, st));

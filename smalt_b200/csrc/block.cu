@@ -16,6 +16,7 @@
 // Integer work on small per-read lists (a few dozen hits, a handful of candidates): one lane walks
 // one hit list exactly in the reference's order, 32-bit and 64-bit quantities as there.
 #include "block.cuh"
+#include <cstdlib>
 #include "band.h"
 #include "sort2.cuh"
 
@@ -407,12 +408,12 @@ __global__ void __launch_bounds__(128) block_reqs_kernel(const BlockArgs a) {
 // quicksort and depth cut on the (few) keys, and the windows of the selected candidates are checked by all
 // lanes.  Jobs whose lists do not fit the shared scratch (more than CW_HITS hits, reads beyond 32 * CW_MASKW
 // bases) use the per-job scratch in HBM with the same code.
-// Few lists per job (one or two sequences): G = 2 .. 16 lanes per job and 32 / G jobs per warp, otherwise most
+// Few lists per job (one or two sequences): G = 4 .. 16 lanes per job and 32 / G jobs per warp, otherwise most
 // lanes of the warp would idle (5.6 of 32 busy on a one-sequence genome, profiles/r2_ncu_full_cands_*).
 constexpr int CW_WARPS = 2;      // warps per CTA
 constexpr int CW_MASKW = 8;      // coverage mask words per lane in shared memory (reads of <= 256 bases)
 // hits of a job whose seeds / segments fit the shared scratch, by group size
-__host__ __device__ constexpr int cw_hits(int G) { return G >= 32 ? 192 : G >= 16 ? 160 : G >= 8 ? 128 : G >= 4 ? 96 : 64; }
+__host__ __device__ constexpr int cw_hits(int G) { return G >= 32 ? 320 : G >= 16 ? 256 : G >= 8 ? 192 : 112; }
 __host__ __device__ constexpr size_t cw_job_bytes(int G) { return (size_t)cw_hits(G) * 24u; }     // u64 + 4 x 32 bit per hit
 __host__ __device__ constexpr size_t cw_warp_bytes(int G) { return (size_t)(32 / G) * cw_job_bytes(G) + 32u * CW_MASKW * 4u; }
 
@@ -915,14 +916,20 @@ static cudaError_t launch_block_cands_g(const BlockArgs &a, cudaStream_t st) {
   block_cands_kernel<G><<<(a.njobs + per_cta - 1) / per_cta, CW_WARPS * 32, smem, st>>>(a);
   return cudaGetLastError();
 }
-// max_lists: the largest number of hit lists (2 x sequences or intervals) of a job of the block
-cudaError_t launch_block_cands(const BlockArgs &a, int max_lists, cudaStream_t st, int *nlaunch) {
+// max_lists: the largest number of hit lists (2 x sequences or intervals) of a job of the block; hits_per_job: mean
+// number of hits of a job.  Group size: a lane per list, at least four (C2, 32000 jobs: 2 lanes 0.36, 4 lanes 0.34,
+// 8 lanes 0.38, 32 lanes 0.44 ms for the candidate stage), and more when the jobs' hits would not fit the shared
+// scratch of a smaller group (the restricted passes of paired reads take all seeds: long lists, 2.7 x slower
+// with 2 lanes per job than with a warp per job).
+cudaError_t launch_block_cands(const BlockArgs &a, int max_lists, double hits_per_job, cudaStream_t st, int *nlaunch) {
   if (a.njobs <= 0) return cudaSuccess;
   ++*nlaunch;
-  if (max_lists <= 2) return launch_block_cands_g<2>(a, st);
-  if (max_lists <= 4) return launch_block_cands_g<4>(a, st);
-  if (max_lists <= 8) return launch_block_cands_g<8>(a, st);
-  if (max_lists <= 16) return launch_block_cands_g<16>(a, st);
+  static const int force = getenv("SMALT_B200_CANDG") ? atoi(getenv("SMALT_B200_CANDG")) : 0;   // (A/B measurements)
+  int G = 4;
+  while (G < 32 && (G < max_lists || G < force || (double)cw_hits(G) < 2.0 * hits_per_job)) G *= 2;
+  if (G <= 4) return launch_block_cands_g<4>(a, st);
+  if (G <= 8) return launch_block_cands_g<8>(a, st);
+  if (G <= 16) return launch_block_cands_g<16>(a, st);
   return launch_block_cands_g<32>(a, st);
 }
 cudaError_t launch_block_emit_k2(const BlockArgs &a, unsigned long long ncand, cudaStream_t st, int *nlaunch) {
@@ -954,7 +961,7 @@ cudaError_t warm_block() {
   cudaFuncAttributes f;
   cudaError_t e = cudaFuncGetAttributes(&f, block_reqs_kernel);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_seqmask_kernel);
-  if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_cands_kernel<2>);
+  if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_cands_kernel<4>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_cands_kernel<8>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_cands_kernel<32>);
   if (e == cudaSuccess) e = cudaFuncGetAttributes(&f, block_emit_k2_kernel);

@@ -102,7 +102,7 @@ struct BlockArgs {
 
 cudaError_t launch_block_seqmask(const BlockArgs &a, cudaStream_t st, int *nlaunch);
 cudaError_t launch_block_reqs(const BlockArgs &a, cudaStream_t st, int *nlaunch);
-cudaError_t launch_block_cands(const BlockArgs &a, int max_lists, cudaStream_t st, int *nlaunch);
+cudaError_t launch_block_cands(const BlockArgs &a, int max_lists, double hits_per_job, cudaStream_t st, int *nlaunch);
 cudaError_t launch_block_emit_k2(const BlockArgs &a, unsigned long long ncand, cudaStream_t st, int *nlaunch);
 cudaError_t launch_block_exceed(const BlockArgs &a, unsigned long long ncand, cudaStream_t st, int *nlaunch);
 cudaError_t launch_block_replay(const BlockArgs &a, cudaStream_t st, int *nlaunch);

@@ -258,6 +258,7 @@ int smbShimWorkerCtx(smb_ctx **ctxp, const ScoreMatrix *scormtxp)
   }
   if (errcode) return ERRCODE_FAILURE;
   if ((errcode = smb_ctx_share_index(*ctxp, g_root))) return errcode;
+  if (getenv("SMALT_B200_WSPIN")) smb_ctx_set_spin(*ctxp, atoi(getenv("SMALT_B200_WSPIN")));   /* how worker threads wait */
   (void) scormtxp; /* penalties are set per block from the read profiles (smbShimSetScoring) */
   return ERRCODE_SUCCESS;
 }

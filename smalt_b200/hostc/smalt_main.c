@@ -134,17 +134,19 @@ static void keep_heaps(void)
   done = 1;
   mallopt(M_TRIM_THRESHOLD, 1 << 30);
   mallopt(M_MMAP_THRESHOLD, 32 << 20);
+  if (getenv("SMALT_B200_TOPPAD")) mallopt(M_TOP_PAD, atoi(getenv("SMALT_B200_TOPPAD")) << 20);
 }
 
 /* ... and let a worker thread grow its arena ONCE: glibc extends a thread arena page by page with
  * mprotect (arena.c grow_heap) - thousands of calls under the mmap lock while 16-32 workers fill
  * their first blocks (21 % of the samples of a 1 M read run).  One large request, freed again,
  * leaves the heap mapped (trimming is off). */
+static size_t g_pregrow_mb = 28;   /* paired blocks keep two result sets of >= 24 KB per pair: 96 (fastmap_run) */
 static void pregrow_arena(void)
 {
   static __thread int done;
   if (!done && !(getenv("SMALT_B200_NOPREGROW") && atoi(getenv("SMALT_B200_NOPREGROW")))) {
-    void *p = malloc((size_t) 28 << 20);
+    void *p = malloc(g_pregrow_mb << 20);
     done = 1;
     if (p) { *(volatile char *) p = 0; free(p); }
   }
