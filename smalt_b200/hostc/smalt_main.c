@@ -127,6 +127,9 @@ static void prof_start(void)
  * next block: mprotect + page faults under the process-wide mmap lock, which made 16 workers
  * slower than 4 (69 % of the samples of a paired run in __mprotect).  Keep the heaps. */
 #include <malloc.h>
+#if defined(__linux__)
+#include <sys/prctl.h>
+#endif
 static void keep_heaps(void)
 {
   static int done;
