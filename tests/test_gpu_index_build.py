@@ -30,6 +30,7 @@ CASES = [
     (20, 13, [400_000, 300_001], 0.0005),
     (13, 13, [100_000], 0.0),
     (8, 5, [1_000_003], 0.0),          # perfect hash with sampling step
+    (13, 3, [9_000_000, 4_000_001], 0.0001),   # 4.3 M positions: three levels of the scan, 1058 sort tiles
 ]
 
 
