@@ -337,8 +337,18 @@ typedef struct {
   uint8_t best;                    /* RMAPFLG_BEST */
   uint8_t sensitive;               /* RMAPFLG_SENSITIVE */
   uint8_t termchar;                /* a terminator follows every sequence in seq_offs (SEQSET_TERMCHAR) */
-  uint8_t reserved;
+  uint8_t cigar;                   /* SMB_CIGAR_* flags: CIGAR text + edit distance of every alignment (0: none) */
 } smb_block_params;
+
+/* Output stage on the device: what fprintREPALIsam (report.c:832-898) derives from the alignment
+ * string of a reported alignment - the CIGAR field (writeDiffStrCIGAR, diffstr.c:298-367, through
+ * diffStrPrintf with DIFFSTRFORM_CIGEXT / _XMISMATCH, :1066-1075) and the NM:i: edit distance
+ * (diffStrGetLevenshteinDistance, diffstr.c:1496-1510). */
+enum smb_cigar_flags {
+  SMB_CIGAR_ON = 1,          /* run the stage (smb_block_params.cigar) */
+  SMB_CIGAR_SOFTCLIP = 2,    /* clips as 'S' (REPORTMODIF_SOFTCLIP) instead of 'H' */
+  SMB_CIGAR_XMISMATCH = 4    /* mismatches as 'X' runs (REPORTMODIF_XMISMATCH) instead of inside 'M' */
+};
 
 typedef struct {                   /* per job */
   int32_t errcode;                 /* error that ends the mapping of this read (ERRCODE_*) or 0 */
@@ -370,6 +380,7 @@ typedef struct {
   float ms_hits, ms_cand, ms_k2, ms_k3;                      /* device times (CUDA events on the context's stream) */
   int32_t launches;
   int32_t reserved;
+  uint64_t ncigarbytes;                                      /* CIGAR text of all alignments (smb_block_params.cigar) */
 } smb_block_sizes;
 
 /* Runs the block on the seed tables of the last seed batch and leaves the outputs on the device;
@@ -380,6 +391,20 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
  * (results / diffstr as smb_band_align_batch, task = index into cands). */
 int smb_block_fetch(smb_ctx *ctx, smb_block_read *reads, smb_block_cand *cands, int32_t *errs,
 		    uint32_t *first_result, smb_ali_result *results, uint8_t *diffstr);
+/* smb_block_fetch plus the output stage (smb_block_params.cigar & SMB_CIGAR_ON): alignment i of `results` has
+ * the CIGAR text cigar[cigar_first[i] .. cigar_first[i + 1]) (no terminator; cigar_first has nresults + 1 entries,
+ * cigar holds sizes.ncigarbytes) with clip_start = qs, clip_end = read length - 1 - qe (report.c:832-843 for
+ * either strand) and the edit distance nm[i]; nm[i] < 0 where the reference's function fails on the string
+ * (-1 = ERRCODE_FAILURE, -59 = -ERRCODE_DIFFSTR; no text then). */
+int smb_block_fetch_cigar(smb_ctx *ctx, smb_block_read *reads, smb_block_cand *cands, int32_t *errs,
+			  uint32_t *first_result, smb_ali_result *results, uint8_t *diffstr,
+			  uint32_t *cigar_first, int32_t *nm, char *cigar);
+/* The same stage for a batch of alignment strings given explicitly: string i starts at diffstr[diff_off[i]]
+ * (0-terminated); text[cigar_first[i] .. cigar_first[i + 1]).  Returns SMB_ERR_CAPACITY with *ntext = required
+ * size if max_text is too small. */
+int smb_cigar_batch(smb_ctx *ctx, const uint8_t *diffstr, size_t ndiffbytes, const uint32_t *diff_off,
+		    const uint32_t *clip_start, const uint32_t *clip_end, int n, int flags,
+		    uint32_t *cigar_first, int32_t *nm, char *text, size_t max_text, size_t *ntext);
 /* Test access: the candidate list of the last smb_block_run, all jobs, in scoring order
  * (cand_first[njobs + 1]); swscor = K2 / K2' score of every candidate (also the over-computed ones). */
 int smb_block_debug_cands(smb_ctx *ctx, uint64_t *cand_first, smb_block_cand *cands, uint32_t *cover,

@@ -185,6 +185,9 @@ int so_score_replay(int ncand, const uint32_t *cover, const uint8_t *rev, const 
 		    int best, int *nscored, int *max1scor, int *max2scor, int *min_swatscor_out,
 		    int *scorlen_min_out, int *bandwidth_min_out, uint8_t *align, int32_t *band_l, int32_t *band_r);
 
+/* smalt_oracle_cigar.c: CIGAR text + edit distance of an alignment string (diffstr.c:298-367, :1496-1510) */
+int so_cigar(const unsigned char *diffstr, int clip_start, int clip_end, int flags, char *out, int maxout, int *nm);
+
 #ifdef __cplusplus
 }
 #endif

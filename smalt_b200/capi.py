@@ -58,7 +58,7 @@ BLOCK_JOB_DTYPE = np.dtype([("seed_read", "<u4"), ("niv", "<i4"), ("iv_first", "
 BLOCK_IVAL_DTYPE = np.dtype([("lo", "<u8"), ("hi", "<u8"), ("seqidx", "<i4"), ("reserved", "<i4")])
 BLOCK_PARAMS_DTYPE = np.dtype([("nhit_max", "<u4"), ("min_swatscor_below_max", "<i4"), ("target_depth", "<i4"),
                                ("max_depth", "<i4"), ("best", "u1"), ("sensitive", "u1"), ("termchar", "u1"),
-                               ("reserved", "u1")])
+                               ("cigar", "u1")])
 BLOCK_READ_DTYPE = np.dtype([("errcode", "<i4"), ("reached_stats", "u1"), ("do_align", "u1"), ("reserved", "u1", (2,)),
                              ("nseg", "<i4"), ("nseg_tot", "<i4"), ("nhit", "<u4"), ("nhit_tot", "<u4"),
                              ("ncand", "<u4"), ("nscored", "<u4"), ("max1scor", "<i4"), ("max2scor", "<i4"),
@@ -69,7 +69,8 @@ BLOCK_CAND_DTYPE = np.dtype([("rs", "<u8"), ("sqidx", "<i4"), ("swscor", "<i4"),
 BLOCK_SIZES_DTYPE = np.dtype([(k, "<u8") for k in ("nhits", "ncand", "nk2", "nk2_band", "nk3", "nresults", "ndiffbytes",
                                                     "k2_cells", "k2_cells_ref", "k2_tasks_ref", "k3_cells")] +
                              [(k, "<f4") for k in ("ms_hits", "ms_cand", "ms_k2", "ms_k3")] +
-                             [("launches", "<i4"), ("reserved", "<i4")])
+                             [("launches", "<i4"), ("reserved", "<i4"), ("ncigarbytes", "<u8")])
+CIGAR_ON, CIGAR_SOFTCLIP, CIGAR_XMISMATCH = 1, 2, 4
 assert BLOCK_READ_DTYPE.itemsize == 64 and BLOCK_CAND_DTYPE.itemsize == 32 and BLOCK_JOB_DTYPE.itemsize == 24
 assert SW_TASK_DTYPE.itemsize == C.sizeof(SwTask)
 assert BAND_TASK_DTYPE.itemsize == C.sizeof(BandTask), (BAND_TASK_DTYPE.itemsize, C.sizeof(BandTask))
@@ -129,6 +130,9 @@ def load_library():
     lib.smb_block_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.smb_block_fetch.argtypes = [C.c_void_p] * 7
     lib.smb_block_debug_cands.argtypes = [C.c_void_p] * 5 + [C.c_size_t]
+    lib.smb_block_fetch_cigar.argtypes = [C.c_void_p] * 10
+    lib.smb_cigar_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     _lib = lib
     return lib
 
@@ -333,12 +337,12 @@ class Context:
 
     # ---- resident block (hit lists -> candidates -> K2 -> replay -> K3 on the device) ----
     def block_run(self, jobs, ivals=None, nhit_max=10000, min_swatscor_below_max=-1, target_depth=200, max_depth=8000,
-                  best=False, sensitive=False, termchar=False):
-        """-> sizes (BLOCK_SIZES_DTYPE scalar) of the block run on the last seed batch"""
+                  best=False, sensitive=False, termchar=False, cigar=0):
+        """-> sizes (BLOCK_SIZES_DTYPE scalar) of the block run on the last seed batch; cigar = CIGAR_* flags"""
         jobs = np.ascontiguousarray(jobs, BLOCK_JOB_DTYPE)
         ivals = np.zeros(0, BLOCK_IVAL_DTYPE) if ivals is None else np.ascontiguousarray(ivals, BLOCK_IVAL_DTYPE)
         prm = np.zeros(1, BLOCK_PARAMS_DTYPE)
-        prm[0] = (nhit_max, min_swatscor_below_max, target_depth, max_depth, int(best), int(sensitive), int(termchar), 0)
+        prm[0] = (nhit_max, min_swatscor_below_max, target_depth, max_depth, int(best), int(sensitive), int(termchar), int(cigar))
         sizes = np.zeros(1, BLOCK_SIZES_DTYPE)
         self._check(self.lib.smb_block_run(self._h, _vp(prm), _vp(jobs), len(jobs), _vp(ivals), len(ivals), _vp(sizes)))
         self._block_n = (len(jobs), sizes[0])
@@ -356,6 +360,44 @@ class Context:
         diff = np.zeros(max(nd, 1), np.uint8)
         self._check(self.lib.smb_block_fetch(self._h, _vp(reads), _vp(cands), _vp(errs), _vp(first), _vp(res), _vp(diff)))
         return reads, cands, errs, first, res, diff[:nd]
+
+    def block_fetch_cigar(self):
+        """block_fetch() + (cigar_first[nresults + 1], nm[nresults], text bytes) of the output stage"""
+        n, sz = self._block_n
+        nk3, nres, nd, nc = int(sz["nk3"]), int(sz["nresults"]), int(sz["ndiffbytes"]), int(sz["ncigarbytes"])
+        reads = np.zeros(n, BLOCK_READ_DTYPE)
+        cands = np.zeros(nk3, BLOCK_CAND_DTYPE)
+        errs = np.zeros(nk3, np.int32)
+        first = np.zeros(nk3 + 1, np.uint32)
+        res = np.zeros(nres, ALI_RESULT_DTYPE)
+        diff = np.zeros(max(nd, 1), np.uint8)
+        cfirst = np.zeros(nres + 1, np.uint32)
+        nm = np.zeros(max(nres, 1), np.int32)
+        text = np.zeros(max(nc, 1), np.uint8)
+        self._check(self.lib.smb_block_fetch_cigar(self._h, _vp(reads), _vp(cands), _vp(errs), _vp(first), _vp(res),
+                                                   _vp(diff), _vp(cfirst), _vp(nm), _vp(text)))
+        return reads, cands, errs, first, res, diff[:nd], cfirst, nm[:nres], text[:nc].tobytes()
+
+    def cigar_batch(self, diffstr, diff_off, clip_start, clip_end, flags=0):
+        """CIGAR text + edit distance of explicit alignment strings -> (cigar_first[n + 1], nm[n], text bytes)"""
+        diffstr = np.ascontiguousarray(diffstr, np.uint8)
+        diff_off = np.ascontiguousarray(diff_off, np.uint32)
+        cs = np.ascontiguousarray(clip_start, np.uint32)
+        ce = np.ascontiguousarray(clip_end, np.uint32)
+        n = len(diff_off)
+        cfirst = np.zeros(n + 1, np.uint32)
+        nm = np.zeros(max(n, 1), np.int32)
+        cap = 64
+        while True:
+            text = np.zeros(cap, np.uint8)
+            nt = C.c_size_t(0)
+            rc = self.lib.smb_cigar_batch(self._h, _vp(diffstr), diffstr.size, _vp(diff_off), _vp(cs), _vp(ce), n,
+                                          int(flags), _vp(cfirst), _vp(nm), _vp(text), cap, C.byref(nt))
+            if rc == SMB_ERR_CAPACITY and nt.value > cap:
+                cap = nt.value
+                continue
+            self._check(rc)
+            return cfirst, nm[:n], text[:nt.value].tobytes()
 
     def block_debug_cands(self):
         """-> (cand_first[n+1], cands[BLOCK_CAND_DTYPE] with swscor = K2 score, cover, qs_qe[n, 2]) of ALL candidates"""

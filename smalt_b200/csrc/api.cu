@@ -78,7 +78,8 @@ void smb_ctx_destroy(smb_ctx *ctx) {
   DevBuf *bufs[] = {&ctx->arena, &ctx->packed, &ctx->tasks, &ctx->out_a, &ctx->out_b,
                     &ctx->scratch, &ctx->dirs, &ctx->diff, &ctx->offs, &ctx->index, &ctx->qualbuf,
                     &ctx->seed_meta, &ctx->seed_u32, &ctx->seed_u8, &ctx->hit_meta, &ctx->hit_data, &ctx->cmp, &ctx->ticket, &ctx->hit_qmask, &ctx->aux_index,
-                    &ctx->seq_offs_buf, &ctx->blk_jobs, &ctx->blk_scr, &ctx->blk_cand, &ctx->blk_k3};
+                    &ctx->seq_offs_buf, &ctx->blk_jobs, &ctx->blk_scr, &ctx->blk_cand, &ctx->blk_k3, &ctx->blk_cig,
+                    &ctx->blk_cigtext};
   for (DevBuf *b : bufs) b->release();
   for (cudaEvent_t &e : ctx->blk_ev) if (e) cudaEventDestroy(e);
   block_state_free(ctx);

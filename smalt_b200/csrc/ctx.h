@@ -92,7 +92,7 @@ struct smb_ctx {
   DevBuf seq_offs_buf;                 // device copy of seq_offs (owner context only)
   const uint64_t *d_seq_offs = nullptr;
   // resident block pipeline (api_block.cu)
-  DevBuf blk_jobs, blk_scr, blk_cand, blk_k3;
+  DevBuf blk_jobs, blk_scr, blk_cand, blk_k3, blk_cig, blk_cigtext;
   cudaEvent_t blk_ev[SMB_BLK_EVENTS] = {};
   struct BlockState *blk = nullptr;
   float last_ms = 0.f;

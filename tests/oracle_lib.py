@@ -275,6 +275,21 @@ class Oracle:
                 lib.so_hitinfo_delete(h)
             lib.so_cands_delete(cands)
 
+    def cigar(self, diffstr, clip_start=0, clip_end=0, softclip=True, xmismatch=False):
+        """-> (text bytes | None, nm | error) of so_cigar (oracle/smalt_oracle_cigar.c); error: -1 / -59"""
+        d = bytes(diffstr)
+        if not d.endswith(b"\0"):
+            d += b"\0"
+        cap = 6 * len(d) + 64
+        out = C.create_string_buffer(cap)
+        nm = C.c_int(0)
+        self.lib.so_cigar.restype = C.c_int
+        n = self.lib.so_cigar(d, int(clip_start), int(clip_end), (2 if softclip else 0) | (4 if xmismatch else 0),
+                              out, cap, C.byref(nm))
+        if n < 0:
+            return None, n
+        return out.raw[:n], nm.value
+
     def score_replay(self, cover, rev, score, band_l, band_r, cover_deficit, qlen, ktup, nskip, min_swatscor,
                      min_swatscor_below_max, best):
         n = len(cover)
@@ -379,6 +394,20 @@ class RefLib:
                                     int(use_short), maxhits, C.byref(n), _p(dat, u64p),
                                     qlen, qm.ctypes.data_as(C.c_char_p))
         return err, dat[:n.value].copy(), qm
+
+    def cigar(self, diffstr, clip_start=0, clip_end=0, softclip=True, xmismatch=False):
+        """the reference's diffStrPrintfStr (diffstr.c:1084-1121, DIFFSTRFORM_CIGEXT = 3 / _XMISMATCH = 4) and
+        diffStrGetLevenshteinDistance (:1496) -> (errcode, text bytes, nm)"""
+        d = bytes(diffstr)
+        if not d.endswith(b"\0"):
+            d += b"\0"
+        out = C.create_string_buffer(6 * len(d) + 64)
+        nchar = C.c_int(0)
+        self.lib.diffStrPrintfStr.restype = C.c_int
+        self.lib.diffStrGetLevenshteinDistance.restype = C.c_int
+        e = self.lib.diffStrPrintfStr(out, C.byref(nchar), d, C.c_char(4 if xmismatch else 3), int(clip_start),
+                                      int(clip_end), C.c_char(1 if softclip else 0))
+        return e, out.raw[:nchar.value], self.lib.diffStrGetLevenshteinDistance(d)
 
     def candidates(self, read, qual=None, min_cover=0, min_swatscor_below_max=-1, mismatchdiff=3, best=False,
                    target_depth=200, max_depth=8000, sensitive=False, nhit_max=10000, maxhit_total=16384, basq=0,
