@@ -983,6 +983,8 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
   while (p < len && isspace((unsigned char) data[p])) p++;
   if (p >= len) { if (n_reads) *n_reads = 0; return ERRCODE_SUCCESS; }
   fm.macop = macop; fm.maps = maps; fm.proto = proto;
+  /* single-end SAM: the device also emits CIGAR and NM of every alignment (SMALT_B200_HOSTCIGAR=1: host formats) */
+  rmapWaveSetCigarMode((dataB || getenv("SMALT_B200_HOSTCIGAR")) ? 0 : smbShimReportCigarFlags(proto));
   fm.data = data + p; fm.len = len - p;
   fm.is_fasta = data[p] == '>';
   fm.refparse = getenv("SMALT_B200_REFPARSE") != NULL;

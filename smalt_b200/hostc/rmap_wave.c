@@ -101,7 +101,7 @@ enum { PST_END = 0, PST_SECOND_UNRESTRICTED = 3, PST_RESCUE_MAIN = 4, PST_RESCUE
 typedef struct { void *p; size_t cap; } WBUF;
 enum { WB_ARENA, WB_QUAL, WB_READ_OFF, WB_READ_LEN, WB_INFO, WB_INFO4, WB_REQ, WB_LIST_FIRST, WB_REQ_ERR, WB_SQDAT,
        WB_SWT, WB_SW_SCORE, WB_SW_ERR, WB_BFT, WB_BF_SCORE, WB_BF_ERR, WB_BAT, WB_BA_ERR, WB_RES,
-       WB_RES_FIRST, WB_DIFF, WB_BJOB, WB_BIVAL, WB_BRD, WB_BCAND, WB_COUNT };
+       WB_RES_FIRST, WB_DIFF, WB_BJOB, WB_BIVAL, WB_BRD, WB_BCAND, WB_CIG_FIRST, WB_CIG_NM, WB_CIG_TEXT, WB_COUNT };
 
 struct RmapWave_ {
   smb_ctx *ctx;
@@ -132,6 +132,12 @@ struct RmapWave_ {
   uint32_t *res_first;
   uint8_t *diff;
   size_t res_alloc, diff_alloc;
+  /* output stage on the device (csrc/cigar.cu): CIGAR text + NM of every alignment in `res` */
+  int cigar_mode;        /* SMB_CIGAR_* flags of the next block run, 0 = off */
+  int have_cigar;        /* the arrays below describe the current `res` */
+  uint32_t *cig_first;
+  int32_t *cig_nm;
+  char *cig_text;
   ScoreProfile *prof, *profRC;
   SeqFastq *readRC;
   WJOB *jobs, *pjob;
@@ -338,6 +344,10 @@ static int wave_host_cand(void)
   return state;
 }
 
+/* SMB_CIGAR_* flags for the blocks of single-end reads (set by the driver from the report writer: SAM output) */
+static int g_cigar_mode = 0;
+void rmapWaveSetCigarMode(int flags) { g_cigar_mode = flags; }
+
 static int wave_timing(void)
 {
   static int state = -1;
@@ -446,7 +456,17 @@ static int dev_results(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, WREAD *rdarr, co
 	if (errcode) { rd->errcode = errcode; ERRMSGNO(errmsgp, errcode); }
       }
     }
-    if (donef && (errcode = (*donef)(user, i, rd->errcode, rsp))) return errcode;
+    if (bw->have_cigar && b->nk3) {   /* the output stage's text for the alignments of this read (shim_report.c) */
+      SmbCigarSource src;
+      src.cands = bc + b->k3_first; src.res_first = bw->res_first + b->k3_first; src.nk3 = b->nk3;
+      src.res = bw->res; src.diff = bw->diff;
+      src.cig_first = bw->cig_first; src.cig_nm = bw->cig_nm; src.cig_text = bw->cig_text;
+      src.qlen = rd->qlen;
+      smbShimSetCigarSource(&src);
+    }
+    errcode = donef ? (*donef)(user, i, rd->errcode, rsp) : ERRCODE_SUCCESS;
+    smbShimSetCigarSource(NULL);
+    if (errcode) return errcode;
     tres = rnow();
   }
   return ERRCODE_SUCCESS;
@@ -514,6 +534,7 @@ static int wave_pass_dev(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, const W
   prm.max_depth = (int32_t) max_depth;
   prm.best = (uint8_t) ((rmapflg & RMAPFLG_BEST) != 0);
   prm.sensitive = (uint8_t) ((rmapflg & RMAPFLG_SENSITIVE) != 0);
+  prm.cigar = (uint8_t) w->cigar_mode;
   {
     SETSIZ_t roffs;
     const SEQLEN_t rlen0 = nseq > 0 ? seqSetGetSeqDatByIndex(&roffs, NULL, 0, ssp) : 0;
@@ -541,7 +562,16 @@ static int wave_pass_dev(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, const W
     WPIN(w->diff, WB_DIFF, sz.ndiffbytes + sz.ndiffbytes / 2 + 4096, uint8_t);
     w->diff_alloc = w->wb[WB_DIFF].cap;
   }
-  if ((rc = smb_block_fetch(w->ctx, brd, bc, w->ba_err, w->res_first, w->res, w->diff))) return gpu_fail(errmsgp, w, rc);
+  w->have_cigar = 0;
+  if (prm.cigar) {
+    WPIN(w->cig_first, WB_CIG_FIRST, sz.nresults + 2, uint32_t);
+    WPIN(w->cig_nm, WB_CIG_NM, sz.nresults + 1, int32_t);
+    WPIN(w->cig_text, WB_CIG_TEXT, sz.ncigarbytes + 64, char);
+    if ((rc = smb_block_fetch_cigar(w->ctx, brd, bc, w->ba_err, w->res_first, w->res, w->diff, w->cig_first, w->cig_nm,
+				    w->cig_text)))
+      return gpu_fail(errmsgp, w, rc);
+    w->have_cigar = 1;
+  } else if ((rc = smb_block_fetch(w->ctx, brd, bc, w->ba_err, w->res_first, w->res, w->diff))) return gpu_fail(errmsgp, w, rc);
   WTICK(6);
 
   /* host: replay of alignRMAPCANDFull (rmap.c:820-926) on the alignments, then results.c as in the reference */
@@ -1052,6 +1082,7 @@ int rmapSingleWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, SeqFastq **re
   if (n < 1) return ERRCODE_SUCCESS;
   if (!(rmapflg & RMAPFLG_SEQBYSEQ) || (rmapflg & (RMAPFLG_NOSHRTINFO | RMAPFLG_SPLIT | RMAPFLG_CMPLXW)))
     return ERRCODE_ARGINVAL; /* caller runs the reference's own per-read code on fibers (still GPU) */
+  w->cigar_mode = g_cigar_mode;
   if ((errcode = wave_seed(errmsgp, w, n, reads, ktuple_maxhit, min_basqval))) return errcode;
   WGROW(w->jobs, w->jobs_alloc, n, WJOB);
   for (i = 0; i < n; i++) {
@@ -1203,6 +1234,7 @@ static int comb_run_gpu(ErrMsg *errmsgp, RmapWave *lw, CombSlot *b, int ktuple_m
   prm.max_depth = (int32_t) max_depth;
   prm.best = (uint8_t) ((rmapflg & RMAPFLG_BEST) != 0);
   prm.sensitive = (uint8_t) ((rmapflg & RMAPFLG_SENSITIVE) != 0);
+  prm.cigar = (uint8_t) g_cigar_mode;   /* (combined batches are single-end reads) */
   {
     SETSIZ_t roffs;
     const SEQLEN_t rlen0 = nseq > 0 ? seqSetGetSeqDatByIndex(&roffs, NULL, 0, ssp) : 0;
@@ -1229,7 +1261,16 @@ static int comb_run_gpu(ErrMsg *errmsgp, RmapWave *lw, CombSlot *b, int ktuple_m
     WPIN(w->diff, WB_DIFF, sz.ndiffbytes + sz.ndiffbytes / 2 + 4096, uint8_t);
     w->diff_alloc = w->wb[WB_DIFF].cap;
   }
-  if ((rc = smb_block_fetch(w->ctx, b->brd, b->bc, w->ba_err, w->res_first, w->res, w->diff))) return gpu_fail(errmsgp, w, rc);
+  w->have_cigar = 0;
+  if (prm.cigar) {
+    WPIN(w->cig_first, WB_CIG_FIRST, sz.nresults + 2, uint32_t);
+    WPIN(w->cig_nm, WB_CIG_NM, sz.nresults + 1, int32_t);
+    WPIN(w->cig_text, WB_CIG_TEXT, sz.ncigarbytes + 64, char);
+    if ((rc = smb_block_fetch_cigar(w->ctx, b->brd, b->bc, w->ba_err, w->res_first, w->res, w->diff, w->cig_first, w->cig_nm,
+				    w->cig_text)))
+      return gpu_fail(errmsgp, w, rc);
+    w->have_cigar = 1;
+  } else if ((rc = smb_block_fetch(w->ctx, b->brd, b->bc, w->ba_err, w->res_first, w->res, w->diff))) return gpu_fail(errmsgp, w, rc);
   w->n_reads += (uint64_t) n;
   return ERRCODE_SUCCESS;
 }
@@ -1505,6 +1546,7 @@ int rmapPairWave(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int npairs, SeqFastq *
       (rmapflg & (RMAPFLG_NOSHRTINFO | RMAPFLG_SPLIT | RMAPFLG_CMPLXW | RMAPFLG_ALLPAIR)) ||
       !rmp->mmp || !rmp->ivr || !rmp->pairp)
     return ERRCODE_ARGINVAL;
+  w->cigar_mode = 0;   /* pairs are reported by the reference's reportWrite */
   if ((size_t) npairs > w->ps_alloc) {
     const size_t na = (size_t) npairs + 64;
     struct PairState_ *hp = (struct PairState_ *) realloc(w->ps, na * sizeof(*hp));

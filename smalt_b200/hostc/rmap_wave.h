@@ -7,6 +7,9 @@ typedef int (RMAPWAVE_EMITF)(void *user, int i, const ResultSet *rsltp);
 RmapWave *rmapWaveCreate(const HashTable *htp, const SeqSet *ssp, const SeqCodec *codecp,
 			 const ScoreMatrix *scormtxp);
 void rmapWaveDelete(RmapWave *w);
+/* SMB_CIGAR_* flags (include/smalt_b200.h) for the blocks of single-end reads that follow: the device also
+ * emits the CIGAR text and the NM edit distance of every alignment (0: off) */
+void rmapWaveSetCigarMode(int flags);
 /* ms: device time of K1, K2(+K2'), K3; counts: reads, K2 tasks, K2 cells, K3 tasks, K3 cells */
 void rmapWaveGetStats(const RmapWave *w, double ms[3], uint64_t counts[5]);
 /* host wall-clock seconds per stage: staging, seed, hits, candidates, score, replay, align, results */

@@ -65,6 +65,22 @@ void smbShimReportWriterDelete(ReportWriter *p);
 /* reportWrite for single-end SAM records with the read decoded once (falls back to reportWrite) */
 int smbShimReportWriteSAM(const ReportWriter *wrp, const SeqFastq *readp, const SeqSet *ssp,
 			  const SeqCodec *codecp, const Report *rep);
+/* CIGAR text + NM of the alignments of the read that is being reported, computed by the device's output stage
+ * (csrc/cigar.cu); set per read by the wave orchestrator around the emit call (thread-local, NULL clears) */
+typedef struct {
+  const smb_block_cand *cands;       /* aligned candidates of the read [nk3] */
+  const uint32_t *res_first;         /* their alignments in res: res_first[t] .. res_first[t + 1] */
+  uint32_t nk3, qlen;
+  const smb_ali_result *res;
+  const uint8_t *diff;
+  const uint32_t *cig_first;
+  const int32_t *cig_nm;
+  const char *cig_text;
+} SmbCigarSource;
+void smbShimSetCigarSource(const SmbCigarSource *src);
+/* SMB_CIGAR_* flags that make the device's text equal what this writer prints (0: not a plain SAM writer) */
+int smbShimReportCigarFlags(const ReportWriter *wrp);
+void smbShimCigarCounters(unsigned long long *ndev, unsigned long long *nhost);
 int smbShimWriteSAMHeader(FILE *fp, const SeqSet *ssp, const char *prognam, const char *progversion,
 			  int narg, char * const *argv);
 #endif

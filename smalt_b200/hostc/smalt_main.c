@@ -772,6 +772,11 @@ int __wrap_threadsRun(void)
 	m->stats.wall_s = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 	m->stats.k1_ms = g_ms[0]; m->stats.k2_ms = g_ms[1]; m->stats.k3_ms = g_ms[2];
 	m->stats.cand_ms = g_ms_cand;
+	{
+	  unsigned long long cd, ch;
+	  smbShimCigarCounters(&cd, &ch);
+	  m->stats.cigar_dev = cd; m->stats.cigar_host = ch;
+	}
 	m->stats.k2_tasks = g_counts[1]; m->stats.k2_cells = g_counts[2];
 	m->stats.k3_tasks = g_counts[3]; m->stats.k3_cells = g_counts[4];
 	{

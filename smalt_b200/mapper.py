@@ -16,7 +16,8 @@ class MapStats(C.Structure):
                 ("k2_tasks", C.c_uint64), ("k2_cells", C.c_uint64),
                 ("k3_tasks", C.c_uint64), ("k3_cells", C.c_uint64),
                 ("gpu_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("host_stage_s", C.c_double * 12), ("host_cpu_s", C.c_double * 8), ("cand_ms", C.c_double)]
+                ("host_stage_s", C.c_double * 12), ("host_cpu_s", C.c_double * 8), ("cand_ms", C.c_double),
+                ("cigar_dev", C.c_uint64), ("cigar_host", C.c_uint64)]
 
     STAGES = ("staging", "seed", "hits", "candidates", "score", "replay", "align", "results", "parse",
               "results.add", "results.sort_filter", "results.emit")

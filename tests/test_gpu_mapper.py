@@ -69,6 +69,9 @@ def test_mapper_matches_reference(tmp_path):
         got = m.map_fastq(text).decode().splitlines()
         assert got == want
         assert m.stats.n_reads == 6000 and m.stats.k2_tasks > 0 and m.stats.k3_cells > 0
+        # CIGAR and NM of every mapped record came from the device's output stage (csrc/cigar.cu), none from diffstr.c
+        nmapped = sum(1 for l in want if l.split("\t")[5] != "*")
+        assert m.stats.cigar_dev == nmapped > 5000 and m.stats.cigar_host == 0
         # a second call on the same mapper, a sub-range of the reads
         cut = text.index(b"@q3000\n")
         assert m.map_fastq(text[cut:]).decode().splitlines() == want[3000:]
@@ -95,16 +98,20 @@ def test_mapper_matches_reference(tmp_path):
 
 
 @needs
-@pytest.mark.parametrize("opts", [["-d", "3"], ["-d", "-1"], ["-y", "0.9"], ["-q", "10"], ["-f", "cigar"], ["-f", "ssaha"]])
+@pytest.mark.parametrize("opts", [["-d", "3"], ["-d", "-1"], ["-y", "0.9"], ["-q", "10"], ["-f", "cigar"], ["-f", "ssaha"],
+                                  ["-f", "sam:x"], ["-f", "sam:clip"], ["-f", "sam:x,clip"]])
 def test_mapper_options(tmp_path, opts):
     """modes other than the default best-hit SAM: score range (-d), identity filter (-y), base
-    quality threshold for seeds (-q), other text formats (-f)"""
+    quality threshold for seeds (-q), other text formats (-f); the SAM variants (X-CIGAR, hard clips) take their
+    CIGAR / NM from the device's output stage"""
     from smalt_b200.mapper import Mapper
     pref, fq, text = _workload(tmp_path, 21, [150_000, 50_000], 13, 6, 2500, (60, 200), 0.03)
     _, want = _ref_sam(tmp_path, pref, fq, opts)
     m = Mapper(pref, 1, ["-r", "7"] + opts)
     try:
         got = m.map_fastq(text).decode().splitlines()
+        if opts[0] == "-f" and opts[1].startswith("sam"):
+            assert m.stats.cigar_dev > 2000 and m.stats.cigar_host == 0
     finally:
         m.close()
     assert got == want
