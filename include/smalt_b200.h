@@ -391,20 +391,24 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
  * (results / diffstr as smb_band_align_batch, task = index into cands). */
 int smb_block_fetch(smb_ctx *ctx, smb_block_read *reads, smb_block_cand *cands, int32_t *errs,
 		    uint32_t *first_result, smb_ali_result *results, uint8_t *diffstr);
-/* smb_block_fetch plus the output stage (smb_block_params.cigar & SMB_CIGAR_ON): alignment i of `results` has
- * the CIGAR text cigar[cigar_first[i] .. cigar_first[i + 1]) (no terminator; cigar_first has nresults + 1 entries,
- * cigar holds sizes.ncigarbytes) with clip_start = qs, clip_end = read length - 1 - qe (report.c:832-843 for
- * either strand) and the edit distance nm[i]; nm[i] < 0 where the reference's function fails on the string
- * (-1 = ERRCODE_FAILURE, -59 = -ERRCODE_DIFFSTR; no text then). */
+/* smb_block_fetch plus the output stage (smb_block_params.cigar & SMB_CIGAR_ON).  `cigar_blob` receives, in one
+ * copy, for the n = sizes.nresults alignments of `results`:
+ *     uint32_t first[n + 1]; int32_t nm[n]; char text[sizes.ncigarbytes];      (SMB_CIGAR_BLOB_BYTES)
+ * alignment i has the CIGAR text[first[i] .. first[i + 1]) (no terminator) with clip_start = qs, clip_end = read
+ * length - 1 - qe (report.c:832-843 for either strand) and the edit distance nm[i]; nm[i] < 0 where the
+ * reference's function fails on the string (-1 = ERRCODE_FAILURE, -59 = -ERRCODE_DIFFSTR; no text then). */
+#define SMB_CIGAR_BLOB_BYTES(n, ntext) ((2 * (size_t) (n) + 1) * 4 + (size_t) (ntext))
+#define SMB_CIGAR_FIRST(blob) ((const uint32_t *) (blob))
+#define SMB_CIGAR_NM(blob, n) ((const int32_t *) (blob) + (size_t) (n) + 1)
+#define SMB_CIGAR_TEXT(blob, n) ((const char *) (blob) + (2 * (size_t) (n) + 1) * 4)
 int smb_block_fetch_cigar(smb_ctx *ctx, smb_block_read *reads, smb_block_cand *cands, int32_t *errs,
-			  uint32_t *first_result, smb_ali_result *results, uint8_t *diffstr,
-			  uint32_t *cigar_first, int32_t *nm, char *cigar);
-/* The same stage for a batch of alignment strings given explicitly: string i starts at diffstr[diff_off[i]]
- * (0-terminated); text[cigar_first[i] .. cigar_first[i + 1]).  Returns SMB_ERR_CAPACITY with *ntext = required
- * size if max_text is too small. */
+			  uint32_t *first_result, smb_ali_result *results, uint8_t *diffstr, void *cigar_blob);
+/* The same stage for a batch of n alignment strings given explicitly: string i starts at diffstr[diff_off[i]]
+ * (0-terminated); the blob has the layout above with room for max_text bytes of text.  Returns SMB_ERR_CAPACITY
+ * with *ntext = required text size if max_text is too small. */
 int smb_cigar_batch(smb_ctx *ctx, const uint8_t *diffstr, size_t ndiffbytes, const uint32_t *diff_off,
 		    const uint32_t *clip_start, const uint32_t *clip_end, int n, int flags,
-		    uint32_t *cigar_first, int32_t *nm, char *text, size_t max_text, size_t *ntext);
+		    void *cigar_blob, size_t max_text, size_t *ntext);
 /* Test access: the candidate list of the last smb_block_run, all jobs, in scoring order
  * (cand_first[njobs + 1]); swscor = K2 / K2' score of every candidate (also the over-computed ones). */
 int smb_block_debug_cands(smb_ctx *ctx, uint64_t *cand_first, smb_block_cand *cands, uint32_t *cover,

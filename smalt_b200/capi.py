@@ -130,9 +130,9 @@ def load_library():
     lib.smb_block_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.smb_block_fetch.argtypes = [C.c_void_p] * 7
     lib.smb_block_debug_cands.argtypes = [C.c_void_p] * 5 + [C.c_size_t]
-    lib.smb_block_fetch_cigar.argtypes = [C.c_void_p] * 10
+    lib.smb_block_fetch_cigar.argtypes = [C.c_void_p] * 8
     lib.smb_cigar_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
-                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+                                    C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     _lib = lib
     return lib
 
@@ -371,12 +371,11 @@ class Context:
         first = np.zeros(nk3 + 1, np.uint32)
         res = np.zeros(nres, ALI_RESULT_DTYPE)
         diff = np.zeros(max(nd, 1), np.uint8)
-        cfirst = np.zeros(nres + 1, np.uint32)
-        nm = np.zeros(max(nres, 1), np.int32)
-        text = np.zeros(max(nc, 1), np.uint8)
+        blob = np.zeros((2 * nres + 1) * 4 + nc + 8, np.uint8)
         self._check(self.lib.smb_block_fetch_cigar(self._h, _vp(reads), _vp(cands), _vp(errs), _vp(first), _vp(res),
-                                                   _vp(diff), _vp(cfirst), _vp(nm), _vp(text)))
-        return reads, cands, errs, first, res, diff[:nd], cfirst, nm[:nres], text[:nc].tobytes()
+                                                   _vp(diff), _vp(blob)))
+        cfirst, nm, text = _split_cigar_blob(blob, nres, nc)
+        return reads, cands, errs, first, res, diff[:nd], cfirst, nm, text
 
     def cigar_batch(self, diffstr, diff_off, clip_start, clip_end, flags=0):
         """CIGAR text + edit distance of explicit alignment strings -> (cigar_first[n + 1], nm[n], text bytes)"""
@@ -385,19 +384,17 @@ class Context:
         cs = np.ascontiguousarray(clip_start, np.uint32)
         ce = np.ascontiguousarray(clip_end, np.uint32)
         n = len(diff_off)
-        cfirst = np.zeros(n + 1, np.uint32)
-        nm = np.zeros(max(n, 1), np.int32)
         cap = 64
         while True:
-            text = np.zeros(cap, np.uint8)
+            blob = np.zeros((2 * n + 1) * 4 + cap + 8, np.uint8)
             nt = C.c_size_t(0)
             rc = self.lib.smb_cigar_batch(self._h, _vp(diffstr), diffstr.size, _vp(diff_off), _vp(cs), _vp(ce), n,
-                                          int(flags), _vp(cfirst), _vp(nm), _vp(text), cap, C.byref(nt))
+                                          int(flags), _vp(blob), cap, C.byref(nt))
             if rc == SMB_ERR_CAPACITY and nt.value > cap:
                 cap = nt.value
                 continue
             self._check(rc)
-            return cfirst, nm[:n], text[:nt.value].tobytes()
+            return _split_cigar_blob(blob, n, nt.value)
 
     def block_debug_cands(self):
         """-> (cand_first[n+1], cands[BLOCK_CAND_DTYPE] with swscor = K2 score, cover, qs_qe[n, 2]) of ALL candidates"""
@@ -409,6 +406,14 @@ class Context:
         qsqe = np.zeros((nc, 2), np.uint32)
         self._check(self.lib.smb_block_debug_cands(self._h, _vp(first), _vp(cands), _vp(cover), _vp(qsqe), nc))
         return first, cands, cover, qsqe
+
+
+def _split_cigar_blob(blob, n, ntext):
+    """the blob of the output stage (SMB_CIGAR_BLOB_BYTES) -> (first[n + 1], nm[n], text bytes)"""
+    first = blob[:(n + 1) * 4].view(np.uint32).copy()
+    nm = blob[(n + 1) * 4:(2 * n + 1) * 4].view(np.int32).copy()
+    text = blob[(2 * n + 1) * 4:(2 * n + 1) * 4 + ntext].tobytes()
+    return first, nm, text
 
 
 def pack_sequences(seqs):

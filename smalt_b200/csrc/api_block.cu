@@ -29,10 +29,12 @@ struct Pending {
   std::vector<uint32_t> v_first;
   std::vector<uint8_t> v_diff;
   std::vector<int32_t> v_errs;
-  // output stage (SMB_CIGAR_ON): arguments of the count pass, total text bytes
+  // output stage (SMB_CIGAR_ON)
   bool cigar = false;
-  size_t ncig = 0;
-  CigarArgs cig{};
+  int cigar_flags = 0;
+  size_t ncig = 0;                             // text bytes
+  unsigned long long *d_cig_first = nullptr;   // fast path: per task, offset of its first alignment's text
+  CigarArgs cig{};                             // multi-pass path: dense results uploaded again
   unsigned long long *d_cig_off = nullptr;
 };
 
@@ -49,10 +51,12 @@ struct Carver {   // carves aligned arrays out of one device buffer
   }
 };
 
-// count pass of the output stage over `ca` (len / nm / off / tile carved out of blk_cig behind `extra` bytes the
-// caller uses for uploads); the total is copied to *h_total (valid after the next synchronisation)
-static int cigar_count_pass(smb_ctx *ctx, Pending &P, CigarArgs ca, size_t nscan, size_t extra, unsigned long long *h_total,
-                            cudaStream_t st, int *nl) {
+// count pass of the output stage over dense / explicit alignments `ca` (len / nm / off / tile carved out of blk_cig
+// behind `extra` bytes the caller uses for uploads); the total is copied to *h_total (valid after the next
+// synchronisation)
+static int cigar_count_pass(smb_ctx *ctx, CigarArgs *ca, unsigned long long **d_off_out, size_t extra,
+                            unsigned long long *h_total, cudaStream_t st, int *nl) {
+  const size_t nscan = (size_t)ca->n + 1;
   Carver c(nullptr);
   c.off = al256(extra);
   c.take<uint32_t>(nscan); c.take<int32_t>(nscan); c.take<unsigned long long>(nscan + 1);
@@ -60,15 +64,28 @@ static int cigar_count_pass(smb_ctx *ctx, Pending &P, CigarArgs ca, size_t nscan
   CU(ctx->blk_cig.ensure(c.off));
   Carver d(ctx->blk_cig.p);
   d.off = al256(extra);
-  ca.len = d.take<uint32_t>(nscan);
-  ca.nm = d.take<int32_t>(nscan);
+  ca->len = d.take<uint32_t>(nscan);
+  ca->nm = d.take<int32_t>(nscan);
   unsigned long long *d_off = d.take<unsigned long long>(nscan + 1);
   unsigned long long *d_tile = d.take<unsigned long long>((size_t)compact_tiles((int)nscan) + 2);
-  CU(cudaMemsetAsync(ca.len, 0, nscan * sizeof(uint32_t), st));
-  CU(launch_cigar_count(ca, nscan, d_off, d_tile, st, nl));
+  CU(launch_cigar_count(*ca, d_off, d_tile, st, nl));
   CU(d2h(h_total, d_off + (nscan - 1), 8, st));
-  P.cig = ca;
-  P.d_cig_off = d_off;
+  *d_off_out = d_off;
+  return SMB_OK;
+}
+
+// fill pass + one copy of the blob {first[n + 1], nm[n], text[ntext]} to the host
+static int cigar_fill_blob(smb_ctx *ctx, CigarArgs ca, const unsigned long long *d_off, size_t ntext, void *blob,
+                           cudaStream_t st, int *nl) {
+  const size_t n = (size_t)ca.n, head = (2 * n + 1) * 4;
+  CU(ctx->blk_cigtext.ensure(head + ntext + 64));
+  char *d_blob = ctx->blk_cigtext.as<char>();
+  ca.off = d_off;
+  ca.first_out = (uint32_t *)d_blob;
+  ca.text = d_blob + head;
+  CU(launch_cigar_fill(ca, st, nl));
+  CU(cudaMemcpyAsync(d_blob + (n + 1) * 4, ca.nm, n * 4, cudaMemcpyDeviceToDevice, st));
+  CU(d2h(blob, d_blob, head + ntext, st));
   return SMB_OK;
 }
 
@@ -393,6 +410,7 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
 
   P = Pending();
   P.cigar = (prm->cigar & SMB_CIGAR_ON) != 0;
+  P.cigar_flags = prm->cigar;
   P.njobs = njobs;
   P.ncand = ncand;
   P.nk3 = nk3;
@@ -470,17 +488,24 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
       CU(launch_band(sc, ctx->src, a.bat, plan, a.k3_order, true, nullptr, bo, max_res, d_dir_off, ctx->dirs.as<uint32_t>(),
                      d_diff_off, a.diff_cap, ctx->scratch.as<uint32_t>(), ctx->ticket.as<int>(), ctx->sm_count, st, &nl,
                      &ctx->side));
-      CU(launch_compact_scan(d_nres, d_dused, d_errs, n3, d_tile_res, d_tile_diff, d_tot, d_first, d_diff_first, st, &nl));
+      uint32_t *d_cig_task = nullptr;
+      unsigned long long *d_tile_cig = nullptr, *d_cig_first = nullptr;
+      if (P.cigar) {   // output stage: text bytes per task, scanned with the result and DiffStr counts
+        Carver c(nullptr);
+        c.take<uint32_t>((size_t)n3 + 1); c.take<unsigned long long>((size_t)ntiles + 1); c.take<unsigned long long>((size_t)n3 + 1);
+        CU(ctx->blk_cig.ensure(c.off));
+        Carver d(ctx->blk_cig.p);
+        d_cig_task = d.take<uint32_t>((size_t)n3 + 1);
+        d_tile_cig = d.take<unsigned long long>((size_t)ntiles + 1);
+        d_cig_first = d.take<unsigned long long>((size_t)n3 + 1);
+        CigarSlots cs{d_res, d_nres, d_diff_off, ctx->diff.as<uint8_t>(), a.bat, n3, max_res, (int)prm->cigar};
+        CU(launch_cigar_task_count(cs, d_cig_task, st, &nl));
+      }
+      CU(launch_compact_scan(d_nres, d_dused, d_errs, n3, d_tile_res, d_tile_diff, d_tot, d_first, d_diff_first, st, &nl,
+                             d_cig_task, d_tile_cig, d_cig_first));
+      CU(sp.end());
       CompactTotals *h_ct = (CompactTotals *)(h_tot + 2);
       unsigned long long *h_cells = (unsigned long long *)(h_ct + 1);
-      if (P.cigar) {   // output stage, count pass: text length + edit distance of every alignment in its slot
-        CigarArgs ca{};
-        ca.res = d_res; ca.nres = d_nres; ca.first = d_first; ca.diff_off_task = d_diff_off; ca.tasks = a.bat;
-        ca.diff = ctx->diff.as<uint8_t>(); ca.n = n3 * max_res; ca.max_res = max_res; ca.flags = prm->cigar;
-        const int rc = cigar_count_pass(ctx, P, ca, (size_t)n3 * max_res + 1, 0, h_cells + 1, st, &nl);
-        if (rc) return rc;
-      }
-      CU(sp.end());
       CU(d2h(h_ct, d_tot, sizeof(CompactTotals), st));
       CU(d2h(h_cells, d_cells, sizeof(unsigned long long), st));
       CU(ctx_sync(ctx));                                                        // sync 4: result sizes
@@ -491,7 +516,7 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
         P.d_res = d_res; P.d_nres = d_nres; P.d_dused = d_dused; P.d_first = d_first; P.d_errs = d_errs;
         P.d_diff_off = d_diff_off; P.d_diff_first = d_diff_first;
         sizes->k3_cells = *h_cells;
-        if (P.cigar) P.ncig = (size_t)h_cells[1];
+        if (P.cigar) { P.ncig = (size_t)h_ct->ncig; P.d_cig_first = d_cig_first; }
       }
     }
     if (multipass) {
@@ -511,10 +536,6 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
       sizes->k3_cells = cells;
       if (P.cigar && P.nres) {   // output stage on the dense results the multi-pass path assembled on the host
         const size_t rb = al256(P.nres * sizeof(smb_ali_result)), extra = rb + al256(P.ndiff + 1);
-        CU(ctx->blk_cig.ensure(extra));   // (grown again with the same prefix by cigar_count_pass: upload afterwards)
-        CigarArgs ca{};
-        ca.tasks = a.bat; ca.n = (int)P.nres; ca.max_res = 1; ca.flags = prm->cigar;
-        unsigned long long *h_cig = h_tot + 8;
         {   // size the buffer first so that the uploads land in the final allocation
           Carver c(nullptr);
           c.off = al256(extra);
@@ -526,10 +547,13 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
         uint8_t *d_mdiff = (uint8_t *)ctx->blk_cig.p + rb;
         CU(h2d(d_mres, P.v_res.data(), P.nres * sizeof(smb_ali_result), st));
         if (P.ndiff) CU(h2d(d_mdiff, P.v_diff.data(), P.ndiff, st));
-        ca.res = d_mres; ca.diff = d_mdiff;
-        const int rc2 = cigar_count_pass(ctx, P, ca, P.nres + 1, extra, h_cig, st, &nl);
+        CigarArgs ca{};
+        ca.res = d_mres; ca.diff = d_mdiff; ca.tasks = a.bat; ca.n = (int)P.nres; ca.flags = prm->cigar;
+        unsigned long long *h_cig = h_tot + 8;
+        const int rc2 = cigar_count_pass(ctx, &ca, &P.d_cig_off, extra, h_cig, st, &nl);
         if (rc2) return rc2;
         CU(ctx_sync(ctx));
+        P.cig = ca;
         P.ncig = (size_t)*h_cig;
       }
     }
@@ -555,13 +579,12 @@ int smb_block_run(smb_ctx *ctx, const smb_block_params *prm, const smb_block_job
 }
 
 static int block_fetch_impl(smb_ctx *ctx, smb_block_read *reads, smb_block_cand *cands, int32_t *errs, uint32_t *first_result,
-                            smb_ali_result *results, uint8_t *diffstr, bool want_cigar, uint32_t *cigar_first, int32_t *nm,
-                            char *cigar) {
+                            smb_ali_result *results, uint8_t *diffstr, bool want_cigar, void *cigar_blob) {
   if (!ctx) return SMB_ERR_ARG;
   if (!ctx->blk || !ctx->blk->p.valid) return fail(ctx, SMB_ERR_STATE, "smb_block_run() first");
   Pending &P = ctx->blk->p;
   if (!P.njobs) {
-    if (want_cigar && cigar_first) cigar_first[0] = 0;
+    if (want_cigar && cigar_blob) *(uint32_t *)cigar_blob = 0;
     return SMB_OK;
   }
   if (!reads || (P.nk3 && (!cands || !errs || !first_result)) || (P.nres && !results) || (P.ndiff && !diffstr))
@@ -583,30 +606,31 @@ static int block_fetch_impl(smb_ctx *ctx, smb_block_read *reads, smb_block_cand 
       CU(ctx->dirs.ensure(dense_bytes));
       smb_ali_result *d_dense = ctx->dirs.as<smb_ali_result>();
       uint8_t *d_ddiff = (uint8_t *)(d_dense + P.nres);
+      GatherCigar gc{};
+      const size_t head = (2 * P.nres + 1) * 4;
+      if (want_cigar && P.cigar && P.nres) {   // output stage: the gather also writes the blob {first, nm, text}
+        CU(ctx->blk_cigtext.ensure(head + P.ncig + 64));
+        char *d_blob = ctx->blk_cigtext.as<char>();
+        gc.tasks = P.args.bat; gc.cig_first = P.d_cig_first; gc.first_out = (uint32_t *)d_blob;
+        gc.nm = (int32_t *)(d_blob + (P.nres + 1) * 4); gc.text = d_blob + head; gc.flags = P.cigar_flags;
+        gc.nres_total = (uint32_t)P.nres; gc.ncig_total = P.ncig;
+      }
       CU(launch_compact_gather(P.d_res, P.d_nres, ctx->diff.as<uint8_t>(), P.d_diff_off, P.d_dused, (int)P.nk3, P.max_res,
-                               P.d_first, P.d_diff_first, d_dense, d_ddiff, st, &nl));
+                               P.d_first, P.d_diff_first, d_dense, d_ddiff, st, &nl, gc.text ? &gc : nullptr));
+      if (gc.text) CU(d2h(cigar_blob, gc.first_out, head + P.ncig, st));
       if (P.nres) CU(d2h(results, d_dense, P.nres * sizeof(smb_ali_result), st));
       if (P.ndiff) CU(d2h(diffstr, d_ddiff, P.ndiff, st));
       CU(d2h(first_result, P.d_first, (P.nk3 + 1) * sizeof(uint32_t), st));
       CU(d2h(errs, P.d_errs, P.nk3 * sizeof(int32_t), st));
     }
   }
-  if (want_cigar) {   // output stage, fill pass: the text at the scanned offsets
+  if (want_cigar) {
     if (!P.cigar) return fail(ctx, SMB_ERR_STATE, "smb_block_run() without SMB_CIGAR_ON");
-    if (!cigar_first || (P.nres && !nm) || (P.ncig && !cigar)) return SMB_ERR_ARG;
-    if (!P.nres || !P.nk3) cigar_first[0] = 0;
-    else {
-      const size_t fb = al256((P.nres + 1) * sizeof(uint32_t));
-      CU(ctx->blk_cigtext.ensure(fb + P.ncig + 64));
-      CigarArgs ca = P.cig;
-      ca.off = P.d_cig_off;
-      ca.ndense = P.nres;
-      ca.first_out = ctx->blk_cigtext.as<uint32_t>();
-      ca.text = ctx->blk_cigtext.as<char>() + fb;
-      CU(launch_cigar_fill(ca, st, &nl));
-      CU(d2h(cigar_first, ca.first_out, (P.nres + 1) * sizeof(uint32_t), st));
-      CU(d2h(nm, ca.nm, P.nres * sizeof(int32_t), st));
-      if (P.ncig) CU(d2h(cigar, ca.text, P.ncig, st));
+    if (!cigar_blob) return SMB_ERR_ARG;
+    if (!P.nres || !P.nk3) *(uint32_t *)cigar_blob = 0;
+    else if (P.multipass) {
+      const int rc = cigar_fill_blob(ctx, P.cig, P.d_cig_off, P.ncig, cigar_blob, st, &nl);
+      if (rc) return rc;
     }
   }
   CU(ctx_sync(ctx));
@@ -618,32 +642,29 @@ static int block_fetch_impl(smb_ctx *ctx, smb_block_read *reads, smb_block_cand 
 
 int smb_block_fetch(smb_ctx *ctx, smb_block_read *reads, smb_block_cand *cands, int32_t *errs, uint32_t *first_result,
                     smb_ali_result *results, uint8_t *diffstr) {
-  return block_fetch_impl(ctx, reads, cands, errs, first_result, results, diffstr, false, nullptr, nullptr, nullptr);
+  return block_fetch_impl(ctx, reads, cands, errs, first_result, results, diffstr, false, nullptr);
 }
 
 int smb_block_fetch_cigar(smb_ctx *ctx, smb_block_read *reads, smb_block_cand *cands, int32_t *errs, uint32_t *first_result,
-                          smb_ali_result *results, uint8_t *diffstr, uint32_t *cigar_first, int32_t *nm, char *cigar) {
-  return block_fetch_impl(ctx, reads, cands, errs, first_result, results, diffstr, true, cigar_first, nm, cigar);
+                          smb_ali_result *results, uint8_t *diffstr, void *cigar_blob) {
+  return block_fetch_impl(ctx, reads, cands, errs, first_result, results, diffstr, true, cigar_blob);
 }
 
 // the output stage for explicit alignment strings
 int smb_cigar_batch(smb_ctx *ctx, const uint8_t *diffstr, size_t ndiffbytes, const uint32_t *diff_off,
-                    const uint32_t *clip_start, const uint32_t *clip_end, int n, int flags, uint32_t *cigar_first,
-                    int32_t *nm, char *text, size_t max_text, size_t *ntext) {
-  if (!ctx || n < 0 || !cigar_first || !ntext) return SMB_ERR_ARG;
+                    const uint32_t *clip_start, const uint32_t *clip_end, int n, int flags, void *cigar_blob,
+                    size_t max_text, size_t *ntext) {
+  if (!ctx || n < 0 || !cigar_blob || !ntext) return SMB_ERR_ARG;
   *ntext = 0;
-  cigar_first[0] = 0;
+  *(uint32_t *)cigar_blob = 0;
   if (!n) return SMB_OK;
-  if (!diffstr || !ndiffbytes || !diff_off || !clip_start || !clip_end || !nm) return SMB_ERR_ARG;
+  if (!diffstr || !ndiffbytes || !diff_off || !clip_start || !clip_end) return SMB_ERR_ARG;
   if (diffstr[ndiffbytes - 1]) return fail(ctx, SMB_ERR_ARG, "alignment strings: the last byte must be the terminator");
   for (int i = 0; i < n; ++i)
     if (diff_off[i] >= ndiffbytes) return fail(ctx, SMB_ERR_ARG, "alignment string %d starts outside the buffer", i);
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
   int nl = 0;
-  if (!ctx->blk) ctx->blk = new (std::nothrow) BlockState();
-  if (!ctx->blk) return SMB_ERRCODE_NOMEM;
-  Pending S;   // scratch state of this call
   const size_t N = (size_t)n, ab = al256(N * 4), extra = al256(ndiffbytes) + 3 * ab;
   {
     Carver c(nullptr);
@@ -660,25 +681,17 @@ int smb_cigar_batch(smb_ctx *ctx, const uint8_t *diffstr, size_t ndiffbytes, con
   CU(h2d(d_cs, clip_start, N * 4, st));
   CU(h2d(d_ce, clip_end, N * 4, st));
   CigarArgs ca{};
-  ca.diff = d_diff; ca.x_off = d_xoff; ca.x_cs = d_cs; ca.x_ce = d_ce; ca.n = n; ca.max_res = 1; ca.flags = flags;
+  ca.diff = d_diff; ca.x_off = d_xoff; ca.x_cs = d_cs; ca.x_ce = d_ce; ca.n = n; ca.flags = flags;
   CU(ctx->stage.ensure(64));
   unsigned long long *h_total = ctx->stage.as<unsigned long long>();
-  const int rc = cigar_count_pass(ctx, S, ca, N + 1, extra, h_total, st, &nl);
+  unsigned long long *d_off = nullptr;
+  int rc = cigar_count_pass(ctx, &ca, &d_off, extra, h_total, st, &nl);
   if (rc) return rc;
   CU(ctx_sync(ctx));
   *ntext = (size_t)*h_total;
-  if (*ntext > max_text || (*ntext && !text)) return SMB_ERR_CAPACITY;
-  const size_t fb = al256((N + 1) * sizeof(uint32_t));
-  CU(ctx->blk_cigtext.ensure(fb + *ntext + 64));
-  ca = S.cig;
-  ca.off = S.d_cig_off;
-  ca.ndense = N;
-  ca.first_out = ctx->blk_cigtext.as<uint32_t>();
-  ca.text = ctx->blk_cigtext.as<char>() + fb;
-  CU(launch_cigar_fill(ca, st, &nl));
-  CU(d2h(cigar_first, ca.first_out, (N + 1) * sizeof(uint32_t), st));
-  CU(d2h(nm, ca.nm, N * sizeof(int32_t), st));
-  if (*ntext) CU(d2h(text, ca.text, *ntext, st));
+  if (*ntext > max_text) return SMB_ERR_CAPACITY;
+  rc = cigar_fill_blob(ctx, ca, d_off, *ntext, cigar_blob, st, &nl);
+  if (rc) return rc;
   CU(ctx_sync(ctx));
   ctx->last_launches = nl;
   ctx->total_launches += nl;

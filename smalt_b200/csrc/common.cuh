@@ -90,18 +90,23 @@ struct BandOut {        // device buffers of smb_band_align_batch
 struct CompactTotals {
   unsigned long long nresults, ndiff;
   int capacity_flag, pad;
+  unsigned long long ncig;   // CIGAR text bytes (output stage on)
 };
+struct GatherCigar;   // cigar.cuh
 int compact_tiles(int n);
 cudaError_t launch_compact_scan(const uint32_t *nres, const uint32_t *dused, const int32_t *errs, int n,
                                 unsigned long long *tile_res, unsigned long long *tile_diff,
                                 CompactTotals *tot, uint32_t *first_result,
-                                unsigned long long *diff_first, cudaStream_t st, int *nlaunch);
+                                unsigned long long *diff_first, cudaStream_t st, int *nlaunch,
+                                const uint32_t *cig = nullptr, unsigned long long *tile_cig = nullptr,
+                                unsigned long long *cig_first = nullptr);
 cudaError_t launch_scan_counts(const uint32_t *in, int n, unsigned long long *out, unsigned long long *tile,
                                cudaStream_t st, int *nlaunch);
 cudaError_t launch_compact_gather(const smb_ali_result *slots, const uint32_t *nres, const uint8_t *diff_slots,
                                   const uint64_t *diff_off, const uint32_t *dused, int n, int max_res,
                                   const uint32_t *first_result, const unsigned long long *diff_first,
-                                  smb_ali_result *out_res, uint8_t *out_diff, cudaStream_t st, int *nlaunch);
+                                  smb_ali_result *out_res, uint8_t *out_diff, cudaStream_t st, int *nlaunch,
+                                  const GatherCigar *cg = nullptr);
 
 constexpr int BAND_SMEM_WCAP_MAX = 512;  // 512 slots * 64 threads * 4 B = 128 KB of shared memory
 struct BandPlan {

@@ -101,7 +101,7 @@ enum { PST_END = 0, PST_SECOND_UNRESTRICTED = 3, PST_RESCUE_MAIN = 4, PST_RESCUE
 typedef struct { void *p; size_t cap; } WBUF;
 enum { WB_ARENA, WB_QUAL, WB_READ_OFF, WB_READ_LEN, WB_INFO, WB_INFO4, WB_REQ, WB_LIST_FIRST, WB_REQ_ERR, WB_SQDAT,
        WB_SWT, WB_SW_SCORE, WB_SW_ERR, WB_BFT, WB_BF_SCORE, WB_BF_ERR, WB_BAT, WB_BA_ERR, WB_RES,
-       WB_RES_FIRST, WB_DIFF, WB_BJOB, WB_BIVAL, WB_BRD, WB_BCAND, WB_CIG_FIRST, WB_CIG_NM, WB_CIG_TEXT, WB_COUNT };
+       WB_RES_FIRST, WB_DIFF, WB_BJOB, WB_BIVAL, WB_BRD, WB_BCAND, WB_CIG_BLOB, WB_COUNT };
 
 struct RmapWave_ {
   smb_ctx *ctx;
@@ -135,9 +135,10 @@ struct RmapWave_ {
   /* output stage on the device (csrc/cigar.cu): CIGAR text + NM of every alignment in `res` */
   int cigar_mode;        /* SMB_CIGAR_* flags of the next block run, 0 = off */
   int have_cigar;        /* the arrays below describe the current `res` */
-  uint32_t *cig_first;
-  int32_t *cig_nm;
-  char *cig_text;
+  uint8_t *cig_blob;     /* SMB_CIGAR_BLOB_BYTES: first[], nm[], text */
+  const uint32_t *cig_first;
+  const int32_t *cig_nm;
+  const char *cig_text;
   ScoreProfile *prof, *profRC;
   SeqFastq *readRC;
   WJOB *jobs, *pjob;
@@ -564,12 +565,12 @@ static int wave_pass_dev(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, int n, const W
   }
   w->have_cigar = 0;
   if (prm.cigar) {
-    WPIN(w->cig_first, WB_CIG_FIRST, sz.nresults + 2, uint32_t);
-    WPIN(w->cig_nm, WB_CIG_NM, sz.nresults + 1, int32_t);
-    WPIN(w->cig_text, WB_CIG_TEXT, sz.ncigarbytes + 64, char);
-    if ((rc = smb_block_fetch_cigar(w->ctx, brd, bc, w->ba_err, w->res_first, w->res, w->diff, w->cig_first, w->cig_nm,
-				    w->cig_text)))
+    WPIN(w->cig_blob, WB_CIG_BLOB, SMB_CIGAR_BLOB_BYTES(sz.nresults, sz.ncigarbytes) + 64, uint8_t);
+    if ((rc = smb_block_fetch_cigar(w->ctx, brd, bc, w->ba_err, w->res_first, w->res, w->diff, w->cig_blob)))
       return gpu_fail(errmsgp, w, rc);
+    w->cig_first = SMB_CIGAR_FIRST(w->cig_blob);
+    w->cig_nm = SMB_CIGAR_NM(w->cig_blob, sz.nresults);
+    w->cig_text = SMB_CIGAR_TEXT(w->cig_blob, sz.nresults);
     w->have_cigar = 1;
   } else if ((rc = smb_block_fetch(w->ctx, brd, bc, w->ba_err, w->res_first, w->res, w->diff))) return gpu_fail(errmsgp, w, rc);
   WTICK(6);
@@ -1263,12 +1264,12 @@ static int comb_run_gpu(ErrMsg *errmsgp, RmapWave *lw, CombSlot *b, int ktuple_m
   }
   w->have_cigar = 0;
   if (prm.cigar) {
-    WPIN(w->cig_first, WB_CIG_FIRST, sz.nresults + 2, uint32_t);
-    WPIN(w->cig_nm, WB_CIG_NM, sz.nresults + 1, int32_t);
-    WPIN(w->cig_text, WB_CIG_TEXT, sz.ncigarbytes + 64, char);
-    if ((rc = smb_block_fetch_cigar(w->ctx, b->brd, b->bc, w->ba_err, w->res_first, w->res, w->diff, w->cig_first, w->cig_nm,
-				    w->cig_text)))
+    WPIN(w->cig_blob, WB_CIG_BLOB, SMB_CIGAR_BLOB_BYTES(sz.nresults, sz.ncigarbytes) + 64, uint8_t);
+    if ((rc = smb_block_fetch_cigar(w->ctx, b->brd, b->bc, w->ba_err, w->res_first, w->res, w->diff, w->cig_blob)))
       return gpu_fail(errmsgp, w, rc);
+    w->cig_first = SMB_CIGAR_FIRST(w->cig_blob);
+    w->cig_nm = SMB_CIGAR_NM(w->cig_blob, sz.nresults);
+    w->cig_text = SMB_CIGAR_TEXT(w->cig_blob, sz.nresults);
     w->have_cigar = 1;
   } else if ((rc = smb_block_fetch(w->ctx, b->brd, b->bc, w->ba_err, w->res_first, w->res, w->diff))) return gpu_fail(errmsgp, w, rc);
   w->n_reads += (uint64_t) n;
