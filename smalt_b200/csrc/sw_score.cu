@@ -229,19 +229,66 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // ~200 steps) and the per-step instructions (two shuffles, two selects, one LDS) are shared by twice as
 // many cells.  The half-warps run in lockstep: full-warp shuffles of width 16, trip counts and staging
 // bounds are the maxima over the two halves.
+// What a window row contributes to a step, looked up by the pair of base codes (a, b) of the two tasks' rows
+// (the staged row is the BYTE OFFSET of its entry, so the two loads of a step need no arithmetic):
+//   tab   score bytes {s(q = 0..3, a)} of task A in .x, of task B in .y: the two sources of ONE PRMT per cell
+//         pair whose selector is a per-column constant {q_A, q_A | 8, 4 + q_B, (4 + q_B) | 8} (| 8: the sign of
+//         the selected byte, i.e. the high byte of the 16-bit score).  N / padding rows hold zeros.  This form
+//         has no spare byte for a read base that must score 0 against every row, so pairs with an N in a READ
+//         take the masked form below; padding COLUMNS (behind the read) only need a score <= 0 in every row
+//         - values there then never exceed the cell they came from - and select the sign of byte 0 twice
+//         (0 or -1).
+//   wsel  the row's selector nibbles and N / padding masks of the masked form: index into the table
+//         {match, mismatch x3 | 0 x4} = (read selector ^ row selector) & ~mask, one LOP3 + one PRMT per cell pair
+//   raw   the base codes for the per-cell table path (X anywhere in the pair's reads or windows)
+// Entry numbers: a * 4 + b for two standard bases (the 16 entries every in-window step reads lie in 32 different
+// banks as 8-byte elements: lanes that read different entries never conflict), 16 + a * 8 + b otherwise.
+constexpr int SW2_LUT_N = 16 + 64;
+__device__ __forceinline__ uint32_t sw2_lut_index(uint32_t a, uint32_t b) {
+  return (a < 4u && b < 4u) ? a * 4u + b : 16u + a * 8u + b;
+}
+
+__device__ __forceinline__ void sw2_build_lut(const Scoring &sc, uint2 *s_tab, uint32_t *s_wsel, uint32_t *s_rawc) {
+  if (threadIdx.x < 64) {   // (the caller synchronises the CTA)
+    const uint32_t a = threadIdx.x >> 3, b = threadIdx.x & 7u;
+    auto tab = [&](uint32_t x) {
+      uint32_t t = 0;
+      for (uint32_t q = 0; q < 4u; ++q) {
+        const int v = x < 4u ? (q == x ? sc.match : sc.mismatch) : (x == 4u ? sc.mismatch : 0);
+        t |= (uint32_t)(v & 0xff) << (8u * q);
+      }
+      return t;
+    };
+    const uint32_t e = sw2_lut_index(a, b);
+    s_tab[e] = make_uint2(tab(a), tab(b));
+    s_wsel[e] = (a < 4u ? a * 0x11u : 0x00440000u) | (b < 4u ? b * 0x1100u : 0x44000000u);
+    s_rawc[e] = a | (b << 8);
+  }
+}
+// the per-column PRMT selector of the row-table form; code 8 = padding column
+__device__ __forceinline__ uint32_t sw2_qsel_tab(uint32_t qa, uint32_t qb) {
+  return (qa < 4u ? (qa | ((qa | 8u) << 4)) : 0x88u) | ((qb < 4u ? ((qb | 4u) | ((qb | 12u) << 4)) : 0xCCu) << 8);
+}
+// ... of the masked form {qA, qA|8, qB, qB|8} (N, padding: 4), bit 2 flipped: the table is the SECOND source of
+// the PRMT (as first source ptxas overwrites it with the result and copies it afresh for every cell):
+// idx' = ((q ^ 4) ^ r) & ~mask
+__device__ __forceinline__ uint32_t sw2_qsel_masked(uint32_t qa, uint32_t qb) {
+  const uint32_t ia = qa < 4u ? qa : 4u, ib = qb < 4u ? qb : 4u;
+  return (ia | ((ia | 8u) << 4) | (ib << 8) | ((ib | 8u) << 12)) ^ 0x4444u;
+}
+
 template <int C, int LANES>
 __global__ void __launch_bounds__(SW_WARPS * 32)
 sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restrict__ tasks,
                  const SwClassArgs cls, int32_t *__restrict__ scores, int32_t *__restrict__ errs) {
   constexpr int GROUPS = 32 / LANES;
-  // per window row (SW2_PAD padding rows on either side): PRMT selector nibbles of both tasks in the
-  // low half, their N / padding masks in the high half; the raw codes for the general path
-  __shared__ uint32_t s_row[SW_WARPS * GROUPS][SW2_MAXROWS + 2 * SW2_PAD];
-  __shared__ unsigned short s_raw[SW_WARPS * GROUPS][SW2_MAXROWS + 2 * SW2_PAD];
+  // per window row (SW2_PAD padding rows on either side): byte offset of the row's entry in s_tab
+  __shared__ unsigned short s_po[SW_WARPS * GROUPS][SW2_MAXROWS + 2 * SW2_PAD];
+  __shared__ __align__(16) uint2 s_tab[SW2_LUT_N];
+  __shared__ uint32_t s_wsel[SW2_LUT_N], s_rawc[SW2_LUT_N];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & (LANES - 1);
-  uint32_t *const srow = s_row[threadIdx.x / LANES];
-  unsigned short *const sraw = s_raw[threadIdx.x / LANES];
+  unsigned short *const spo = s_po[threadIdx.x / LANES];
   const uint32_t nge2 = (uint32_t)((-sc.gap_ext) & 0xffff) * 0x10001u;
   // The table {match, mismatch x3 | 0 x4} and the bias are read back from shared memory so
   // that they live in (vector) registers: as kernel-uniform values ptxas keeps them in uniform
@@ -252,11 +299,10 @@ sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restri
     s_konst[0] = (uint32_t)(sc.match & 0xff) | ((uint32_t)(sc.mismatch & 0xff) * 0x01010100u);
     s_konst[1] = (uint32_t)(sc.gap_init & 0xffff) * 0x10001u;
   }
+  sw2_build_lut(sc, s_tab, s_wsel, s_rawc);
   __syncthreads();
   const uint32_t T0 = ((volatile uint32_t *)s_konst)[0], gi2 = ((volatile uint32_t *)s_konst)[1];
-  // PRMT takes the table as its SECOND source (bytes 4..7; the first source is the zero register):
-  // as first source ptxas overwrites it with the result and copies it afresh for every cell.  The
-  // selector nibbles are therefore kept with bit 2 flipped: idx' = ((q ^ 4) ^ r) & ~mask.
+  const char *const lutb = (const char *)s_tab, *const wselb = (const char *)s_wsel, *const rawb = (const char *)s_rawc;
   const int npairs = (cls.ntasks + 1) >> 1;
 
   for (;;) {
@@ -275,48 +321,70 @@ sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restri
     if (GROUPS > 1) rlen = max(rlen, __shfl_xor_sync(FULL, rlen, 16)); // ... of the warp: common trip count
     const bool rcA = (ta.flags & SMB_TASK_READ_REVCOMP) != 0, rcB = (tb.flags & SMB_TASK_READ_REVCOMP) != 0;
     const bool pkA = (ta.flags & SMB_TASK_REF_PACKED) != 0, pkB = (tb.flags & SMB_TASK_REF_PACKED) != 0;
-    bool hasX = false;
+    bool hasX = false, hasN = false;
     __syncwarp();
     for (int x = lane; x < rlen + 2 * SW2_PAD; x += LANES) {
       const int i = x - SW2_PAD;
       const uint32_t a = (i >= 0 && i < rlenA) ? ref_base(src, pkA, ta.ref_off, (uint32_t)i) : 7u;
       const uint32_t b = (i >= 0 && i < rlenB) ? ref_base(src, pkB, tb.ref_off, (uint32_t)i) : 7u;
       hasX |= (a == 4u) | (b == 4u);
-      sraw[x] = (unsigned short)(a | (b << 8));
-      srow[x] = (a < 4u ? a * 0x11u : 0x00440000u) | (b < 4u ? b * 0x1100u : 0x44000000u);
+      spo[x] = (unsigned short)(sw2_lut_index(a, b) * 8u);
     }
-    // per column: PRMT selector nibbles of the read bases {qA, qA|8, qB, qB|8} (N, padding: 4) and
-    // the raw codes for the general path
-    uint32_t qsel[C], qraw[C], H[C], E[C];
+    // per column: the PRMT selector of the row-table form {qA, qA | 8, 4 + qB, (4 + qB) | 8}; padding columns
+    // select the sign of byte 0 / byte 4 twice (a score of 0 or -1 in every row)
+    uint32_t qsel[C], H[C], E[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const int j = lane * C + c;
-      const uint32_t qa = (j < qlenA) ? read_base(src.arena, ta.read_off, (uint32_t)qlenA, rcA, (uint32_t)j) : 7u;
-      const uint32_t qb = (j < qlenB) ? read_base(src.arena, tb.read_off, (uint32_t)qlenB, rcB, (uint32_t)j) : 7u;
+      const uint32_t qa = (j < qlenA) ? read_base(src.arena, ta.read_off, (uint32_t)qlenA, rcA, (uint32_t)j) : 8u;
+      const uint32_t qb = (j < qlenB) ? read_base(src.arena, tb.read_off, (uint32_t)qlenB, rcB, (uint32_t)j) : 8u;
       hasX |= (qa == 4u) | (qb == 4u);
-      const uint32_t ia = qa < 4u ? qa : 4u, ib = qb < 4u ? qb : 4u;
-      qsel[c] = (ia | ((ia | 8u) << 4) | (ib << 8) | ((ib | 8u) << 12)) ^ 0x4444u;
-      qraw[c] = qa | (qb << 8);
+      hasN |= ((qa > 4u) & (qa < 8u)) | ((qb > 4u) & (qb < 8u));
+      qsel[c] = sw2_qsel_tab(qa, qb);
       H[c] = gi2;
       E[c] = gi2;
     }
     // X (the mismatch-against-everything code, score.c:138-173) in a read or a window: the warp's
-    // pairs take the per-cell table path
+    // pairs take the per-cell table path; an N in a read: the masked form
     const bool general = __any_sync(FULL, hasX);
+    const bool masked = __any_sync(FULL, hasN);
     __syncwarp();
     uint32_t hdiag = gi2, hout = gi2, fout = gi2, best = gi2;
     const int nsteps = rlen + LANES - 1;
-    if (!general) {
+    const unsigned short *rowp = spo + (SW2_PAD - lane);
+    if (!general && !masked) {
       // Every lane computes in every step: before its first and behind its last window row it
       // runs over the padding rows, which score 0 in every column - H stays 0 in front of the
       // window and cannot rise behind it, E and F only matter where they are positive - so the
       // maximum is that of the window rows alone and the loop needs no activity predicate.
-      const uint32_t *rowp = srow + (SW2_PAD - lane);
+      // (the row's table is fetched one step ahead: two dependent loads in front of the first PRMT otherwise;
+      // rowp[nsteps] is a staged padding row)
+      uint2 rt = *(const uint2 *)(lutb + rowp[0]);
+      for (int t = 0; t < nsteps; ++t) {
+        const uint2 rtn = *(const uint2 *)(lutb + rowp[t + 1]);
+        uint32_t hl = __shfl_up_sync(FULL, hout, 1, LANES);
+        uint32_t F = __shfl_up_sync(FULL, fout, 1, LANES);
+        if (lane == 0) { hl = gi2; F = gi2; }
+        uint32_t diag = hdiag;
+        hdiag = hl;
+        SW2_STEP(prmt(rt.x, rt.y, qsel[c]));
+        hout = H[C - 1];
+        fout = F;
+        rt = rtn;
+      }
+    } else if (!general) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int j = lane * C + c;
+        const uint32_t qa = (j < qlenA) ? read_base(src.arena, ta.read_off, (uint32_t)qlenA, rcA, (uint32_t)j) : 7u;
+        const uint32_t qb = (j < qlenB) ? read_base(src.arena, tb.read_off, (uint32_t)qlenB, rcB, (uint32_t)j) : 7u;
+        qsel[c] = sw2_qsel_masked(qa, qb);
+      }
       for (int t = 0; t < nsteps; ++t) {
         uint32_t hl = __shfl_up_sync(FULL, hout, 1, LANES);
         uint32_t F = __shfl_up_sync(FULL, fout, 1, LANES);
         if (lane == 0) { hl = gi2; F = gi2; }
-        const uint32_t w = rowp[t];
+        const uint32_t w = *(const uint32_t *)(wselb + (rowp[t] >> 1));
         const uint32_t wm = w >> 16;
         uint32_t diag = hdiag;
         hdiag = hl;
@@ -325,18 +393,25 @@ sw_score2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restri
         fout = F;
       }
     } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {   // raw base codes of the columns
+        const int j = lane * C + c;
+        const uint32_t qa = (j < qlenA) ? read_base(src.arena, ta.read_off, (uint32_t)qlenA, rcA, (uint32_t)j) : 7u;
+        const uint32_t qb = (j < qlenB) ? read_base(src.arena, tb.read_off, (uint32_t)qlenB, rcB, (uint32_t)j) : 7u;
+        qsel[c] = qa | (qb << 8);
+      }
       for (int t = 0; t < nsteps; ++t) {
         uint32_t hl = __shfl_up_sync(FULL, hout, 1, LANES);
         uint32_t F = __shfl_up_sync(FULL, fout, 1, LANES);
         if (lane == 0) { hl = gi2; F = gi2; }
         const int i = t - lane;
         if (i >= 0 && i < rlen) {
-          const uint32_t r2 = (uint32_t)sraw[i + SW2_PAD];
+          const uint32_t r2 = *(const uint32_t *)(rawb + (spo[i + SW2_PAD] >> 1));
           const uint32_t ra = r2 & 0xffu, rb = r2 >> 8;
           uint32_t diag = hdiag;
           hdiag = hl;
-          SW2_STEP((((uint32_t)(int)sc.S[ra * 8u + (qraw[c] & 0xffu)]) & 0xffffu) |
-                   ((uint32_t)(int)sc.S[rb * 8u + (qraw[c] >> 8)] << 16));
+          SW2_STEP((((uint32_t)(int)sc.S[ra * 8u + (qsel[c] & 0xffu)]) & 0xffffu) |
+                   ((uint32_t)(int)sc.S[rb * 8u + (qsel[c] >> 8)] << 16));
           hout = H[C - 1];
           fout = F;
         }
@@ -373,12 +448,12 @@ __global__ void __launch_bounds__(SW_WARPS * 32)
 sw_long2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restrict__ tasks,
                 const SwClassArgs cls, int32_t *__restrict__ scores, int32_t *__restrict__ errs,
                 uint2 *__restrict__ bscratch, const uint32_t bstride) {
-  __shared__ uint32_t s_row[SW_WARPS][SWL_RCH + 32];
-  __shared__ unsigned short s_raw[SW_WARPS][SWL_RCH + 32];
+  __shared__ unsigned short s_po[SW_WARPS][SWL_RCH + 32];   // rows as byte offsets into s_tab (see sw_score2_kernel)
+  __shared__ __align__(16) uint2 s_tab[SW2_LUT_N];
+  __shared__ uint32_t s_wsel[SW2_LUT_N], s_rawc[SW2_LUT_N];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  uint32_t *const srow = s_row[threadIdx.x >> 5];
-  unsigned short *const sraw = s_raw[threadIdx.x >> 5];
+  unsigned short *const spo = s_po[threadIdx.x >> 5];
   const int gwarp = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
   uint2 *const strip0 = bscratch + (size_t)gwarp * 2u * bstride;
   const uint32_t nge2 = (uint32_t)((-sc.gap_ext) & 0xffff) * 0x10001u;
@@ -387,8 +462,10 @@ sw_long2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restric
     s_konst[0] = (uint32_t)(sc.match & 0xff) | ((uint32_t)(sc.mismatch & 0xff) * 0x01010100u);
     s_konst[1] = (uint32_t)(sc.gap_init & 0xffff) * 0x10001u;
   }
+  sw2_build_lut(sc, s_tab, s_wsel, s_rawc);
   __syncthreads();
   const uint32_t T0 = ((volatile uint32_t *)s_konst)[0], gi2 = ((volatile uint32_t *)s_konst)[1];
+  const char *const lutb = (const char *)s_tab, *const wselb = (const char *)s_wsel, *const rawb = (const char *)s_rawc;
   const int npairs = (cls.ntasks + 1) >> 1;
 
   for (;;) {
@@ -409,25 +486,32 @@ sw_long2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restric
     const int nsteps = rlen + 31;
     uint32_t best = gi2;
     // X (the mismatch-against-everything code) anywhere in the reads or windows: per-cell table path
-    bool hasX = false;
+    // ... an N in a read: the masked form; else one PRMT over the row's score table per cell pair
+    bool hasX = false, hasN = false;
     for (int x = lane; x < max(rlen, qlen); x += 32) {
       if (x < rlenA) hasX |= ref_base(src, pkA, ta.ref_off, (uint32_t)x) == 4u;
       if (x < rlenB) hasX |= ref_base(src, pkB, tb.ref_off, (uint32_t)x) == 4u;
-      if (x < qlenA) hasX |= read_base(src.arena, ta.read_off, (uint32_t)qlenA, rcA, (uint32_t)x) == 4u;
-      if (x < qlenB) hasX |= read_base(src.arena, tb.read_off, (uint32_t)qlenB, rcB, (uint32_t)x) == 4u;
+      if (x < qlenA) {
+        const uint32_t q = read_base(src.arena, ta.read_off, (uint32_t)qlenA, rcA, (uint32_t)x);
+        hasX |= q == 4u; hasN |= q > 4u;
+      }
+      if (x < qlenB) {
+        const uint32_t q = read_base(src.arena, tb.read_off, (uint32_t)qlenB, rcB, (uint32_t)x);
+        hasX |= q == 4u; hasN |= q > 4u;
+      }
     }
     const bool general = __any_sync(FULL, hasX);
+    const int mode = general ? 2 : (__any_sync(FULL, hasN) ? 1 : 0);
 
     for (int b = 0; b < nblk; ++b) {
-      uint32_t qsel[C], qraw[C], H[C], E[C];
+      uint32_t qsel[C], H[C], E[C];   // qsel: the column's selector in the form of `mode` (raw codes for mode 2)
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const int j = b * 32 * C + lane * C + c;
-        const uint32_t qa = (j < qlenA) ? read_base(src.arena, ta.read_off, (uint32_t)qlenA, rcA, (uint32_t)j) : 7u;
-        const uint32_t qb = (j < qlenB) ? read_base(src.arena, tb.read_off, (uint32_t)qlenB, rcB, (uint32_t)j) : 7u;
-        const uint32_t ia = qa < 4u ? qa : 4u, ib = qb < 4u ? qb : 4u;
-        qsel[c] = (ia | ((ia | 8u) << 4) | (ib << 8) | ((ib | 8u) << 12)) ^ 0x4444u;
-        qraw[c] = qa | (qb << 8);
+        const uint32_t qa = (j < qlenA) ? read_base(src.arena, ta.read_off, (uint32_t)qlenA, rcA, (uint32_t)j) : 8u;
+        const uint32_t qb = (j < qlenB) ? read_base(src.arena, tb.read_off, (uint32_t)qlenB, rcB, (uint32_t)j) : 8u;
+        qsel[c] = mode == 0 ? sw2_qsel_tab(qa, qb)
+                            : (mode == 1 ? sw2_qsel_masked(qa, qb) : ((qa < 8u ? qa : 7u) | ((qb < 8u ? qb : 7u) << 8)));
         H[c] = gi2;
         E[c] = gi2;
       }
@@ -444,13 +528,11 @@ sw_long2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restric
           const int i = base - 31 + x;
           const uint32_t a = (i >= 0 && i < rlenA) ? ref_base(src, pkA, ta.ref_off, (uint32_t)i) : 7u;
           const uint32_t bb = (i >= 0 && i < rlenB) ? ref_base(src, pkB, tb.ref_off, (uint32_t)i) : 7u;
-          sraw[x] = (unsigned short)(a | (bb << 8));
-          srow[x] = (a < 4u ? a * 0x11u : 0x00440000u) | (bb < 4u ? bb * 0x1100u : 0x44000000u);
+          spo[x] = (unsigned short)(sw2_lut_index(a, bb) * 8u);
         }
         __syncwarp();
         const int tend = min(nsteps, base + SWL_RCH);
-        const uint32_t *rowp = srow + (31 - lane) - base;
-        const unsigned short *rawp = sraw + (31 - lane) - base;
+        const unsigned short *rowp = spo + (31 - lane) - base;
         for (int t = base; t < tend; ++t) {
           if ((t & 31) == 0 && has_in) {
             const int i = t + lane;
@@ -467,15 +549,18 @@ sw_long2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restric
           }
           uint32_t diag = hdiag;
           hdiag = hl;
-          if (!general) {
-            const uint32_t w = rowp[t];
+          if (mode == 0) {
+            const uint2 rt = *(const uint2 *)(lutb + rowp[t]);
+            SW2_STEP(prmt(rt.x, rt.y, qsel[c]));
+          } else if (mode == 1) {
+            const uint32_t w = *(const uint32_t *)(wselb + (rowp[t] >> 1));
             const uint32_t wm = w >> 16;
             SW2_STEP(prmt(0u, T0, (qsel[c] ^ w) & ~wm));
           } else {
-            const uint32_t r2 = (uint32_t)rawp[t];
+            const uint32_t r2 = *(const uint32_t *)(rawb + (rowp[t] >> 1));
             const uint32_t ra = r2 & 0xffu, rb = r2 >> 8;
-            SW2_STEP((((uint32_t)(int)sc.S[ra * 8u + (qraw[c] & 0xffu)]) & 0xffffu) |
-                     ((uint32_t)(int)sc.S[rb * 8u + (qraw[c] >> 8)] << 16));
+            SW2_STEP((((uint32_t)(int)sc.S[ra * 8u + (qsel[c] & 0xffu)]) & 0xffffu) |
+                     ((uint32_t)(int)sc.S[rb * 8u + (qsel[c] >> 8)] << 16));
           }
           hout = H[C - 1];
           fout = F;
@@ -509,10 +594,17 @@ sw_long2_kernel(const Scoring sc, const SeqSrc src, const smb_sw_task *__restric
 template <int C>
 static cudaError_t launch_class2(const Scoring &sc, const SeqSrc &src, const smb_sw_task *d_tasks,
                                  const SwClassArgs &cls, int32_t *d_scores, int32_t *d_errs, int grid,
-                                 cudaStream_t st) {
+                                 int sm_count, int ntasks_cls, cudaStream_t st) {
   static const bool lanes32 = getenv("SMB_SW_LANES32") != nullptr;
   if (lanes32) sw_score2_kernel<C, 32><<<grid, SW_WARPS * 32, 0, st>>>(sc, src, d_tasks, cls, d_scores, d_errs);
-  else sw_score2_kernel<2 * C, 16><<<(grid + 1) / 2, SW_WARPS * 32, 0, st>>>(sc, src, d_tasks, cls, d_scores, d_errs);
+  else {
+    // the half-warp form: 64 registers and 10 KB of shared memory per CTA leave room for 8 CTAs per SM; 6 measured
+    // best (26.4 ms per 1 M C2 reads; 4: 27.3, 8: 26.9 - more warps hide the step's loads, fewer end more evenly)
+    static const int ctas_per_sm = getenv("SMB_SW_CTAS_PER_SM") ? atoi(getenv("SMB_SW_CTAS_PER_SM")) : 6;
+    const int cap = sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 6);
+    const int want = (ntasks_cls + 3) / 4 / SW_WARPS + 1;   // four tasks per warp
+    sw_score2_kernel<2 * C, 16><<<want < cap ? want : cap, SW_WARPS * 32, 0, st>>>(sc, src, d_tasks, cls, d_scores, d_errs);
+  }
   return cudaGetLastError();
 }
 
@@ -586,14 +678,14 @@ cudaError_t launch_sw_score(const Scoring &sc, const SeqSrc &src, const smb_sw_t
     int grid = ((n + 1) / 2 + SW_WARPS - 1) / SW_WARPS;
     if (grid > plan.max_grid) grid = plan.max_grid;
     switch (c) {
-      case 1: e = launch_class2<1>(sc, src, d_tasks, cls, d_scores, d_errs, grid, st); break;
-      case 2: e = launch_class2<2>(sc, src, d_tasks, cls, d_scores, d_errs, grid, st); break;
-      case 3: e = launch_class2<3>(sc, src, d_tasks, cls, d_scores, d_errs, grid, st); break;
-      case 4: e = launch_class2<4>(sc, src, d_tasks, cls, d_scores, d_errs, grid, st); break;
-      case 5: e = launch_class2<5>(sc, src, d_tasks, cls, d_scores, d_errs, grid, st); break;
-      case 6: e = launch_class2<6>(sc, src, d_tasks, cls, d_scores, d_errs, grid, st); break;
-      case 7: e = launch_class2<7>(sc, src, d_tasks, cls, d_scores, d_errs, grid, st); break;
-      default: e = launch_class2<8>(sc, src, d_tasks, cls, d_scores, d_errs, grid, st); break;
+      case 1: e = launch_class2<1>(sc, src, d_tasks, cls, d_scores, d_errs, grid, plan.max_grid / 8, n, st); break;
+      case 2: e = launch_class2<2>(sc, src, d_tasks, cls, d_scores, d_errs, grid, plan.max_grid / 8, n, st); break;
+      case 3: e = launch_class2<3>(sc, src, d_tasks, cls, d_scores, d_errs, grid, plan.max_grid / 8, n, st); break;
+      case 4: e = launch_class2<4>(sc, src, d_tasks, cls, d_scores, d_errs, grid, plan.max_grid / 8, n, st); break;
+      case 5: e = launch_class2<5>(sc, src, d_tasks, cls, d_scores, d_errs, grid, plan.max_grid / 8, n, st); break;
+      case 6: e = launch_class2<6>(sc, src, d_tasks, cls, d_scores, d_errs, grid, plan.max_grid / 8, n, st); break;
+      case 7: e = launch_class2<7>(sc, src, d_tasks, cls, d_scores, d_errs, grid, plan.max_grid / 8, n, st); break;
+      default: e = launch_class2<8>(sc, src, d_tasks, cls, d_scores, d_errs, grid, plan.max_grid / 8, n, st); break;
     }
     if (e != cudaSuccess) return e;
     ++*nlaunch;
