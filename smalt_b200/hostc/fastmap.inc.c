@@ -1070,7 +1070,11 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
        * spinning threads take the workers' cores; blocking costs a third of the throughput (tools/core_sweep.py) */
       const char *se = getenv("SMALT_B200_SPIN");
       g_fm_comb = waveCombinerCreate(macop->htp, macop->ssp, macop->codecp, macop->scormtxp, 8,
-				     (be && atoi(be) > 0) ? atoi(be) : 16384, se ? atoi(se) : 50);
+				     /* reads per device batch: smaller batches shorten the fill and drain of a call's pipeline
+				      * when the device is the limit (16 cores: 12288 -> 11.7, 16384 -> 11.2-11.5, 24576 -> 10.3 M
+				      * reads/s per 1 M-read call), larger ones save launches when the host is (4 cores: 16384 ->
+				      * 5.3, 8192 -> 4.9 M reads/s); tools/core_sweep.py, tools/batch_sweep.sh */
+				     (be && atoi(be) > 0) ? atoi(be) : (nworkers >= 8 ? 12288 : 16384), se ? atoi(se) : 50);
       if (!g_fm_comb) errcode = ERRCODE_FAILURE;
     }
   }
