@@ -171,6 +171,7 @@ static int fm_check_fastq(const char *d, size_t start, size_t end, size_t *nrec)
 
 static void fm_publish(FastMap *fm, size_t c, char *buf, size_t len, int errcode)
 {
+  smbShimCigarFlush();   /* this worker's device- / host-formatted record counts of the block */
   pthread_mutex_lock(&fm->lock);
   fm->out[c].buf = buf;
   fm->out[c].len = len;

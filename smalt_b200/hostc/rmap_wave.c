@@ -467,10 +467,11 @@ static int dev_results(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, WREAD *rdarr, co
     }
     errcode = donef ? (*donef)(user, i, rd->errcode, rsp) : ERRCODE_SUCCESS;
     smbShimSetCigarSource(NULL);
-    if (errcode) return errcode;
+    if (errcode) break;
     tres = rnow();
   }
-  return ERRCODE_SUCCESS;
+  smbShimCigarFlush();
+  return errcode;
 }
 
 /* waves 1b-3 with the block resident on the device (smb_block_run / smb_block_fetch): hit lists,

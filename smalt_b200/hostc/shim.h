@@ -81,6 +81,7 @@ void smbShimSetCigarSource(const SmbCigarSource *src);
 /* SMB_CIGAR_* flags that make the device's text equal what this writer prints (0: not a plain SAM writer) */
 int smbShimReportCigarFlags(const ReportWriter *wrp);
 void smbShimCigarCounters(unsigned long long *ndev, unsigned long long *nhost);
+void smbShimCigarFlush(void);
 int smbShimWriteSAMHeader(FILE *fp, const SeqSet *ssp, const char *prognam, const char *progversion,
 			  int narg, char * const *argv);
 #endif

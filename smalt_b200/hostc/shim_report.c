@@ -81,15 +81,18 @@ static size_t samNameLen(const char *namp, int is_stripped)
 }
 
 /* ---- the device's output stage as the source of CIGAR and NM ---- */
-static __thread SmbCigarSource t_cig;
-static __thread int t_cig_set;
+static __thread const SmbCigarSource *t_cigp;   /* (the caller's struct stays valid until it clears the pointer) */
 static unsigned long long g_cig_dev, g_cig_host;   /* records served from the device / formatted on the host */
+static __thread unsigned long long t_cig_dev, t_cig_host;   /* ... of this thread since its last flush */
 
-void smbShimSetCigarSource(const SmbCigarSource *src)
+/* adds the calling thread's counts to the process totals (once per block, not per record: the totals share a line) */
+void smbShimCigarFlush(void)
 {
-  if (src) { t_cig = *src; t_cig_set = 1; }
-  else t_cig_set = 0;
+  if (t_cig_dev) { __atomic_fetch_add(&g_cig_dev, t_cig_dev, __ATOMIC_RELAXED); t_cig_dev = 0; }
+  if (t_cig_host) { __atomic_fetch_add(&g_cig_host, t_cig_host, __ATOMIC_RELAXED); t_cig_host = 0; }
 }
+
+void smbShimSetCigarSource(const SmbCigarSource *src) { t_cigp = src; }
 
 int smbShimReportCigarFlags(const ReportWriter *wrp)
 {
@@ -107,23 +110,23 @@ void smbShimCigarCounters(unsigned long long *ndev, unsigned long long *nhost)
 /* The alignment of the device's result list that the report entry `rrp` was made from: same candidate
  * (sequence, strand), same coordinates (results.c:1897-1907) and score, and the same alignment string bytes
  * (report.c:1700 copies them unchanged).  -> index into res / cig_first / cig_nm, or -1. */
-static long cigarLookup(const REPALI *rrp, const DIFFSTR_T *diffstr, SEQLEN_t qlen)
+static long cigarLookup(const SmbCigarSource *cs, const REPALI *rrp, const DIFFSTR_T *diffstr, SEQLEN_t qlen)
 {
   uint32_t t, i;
   const int is_rev = (rrp->status & REPMATEFLG_REVERSE) != 0;
-  if (!t_cig_set || t_cig.qlen != (uint32_t) qlen) return -1;
-  for (t = 0; t < t_cig.nk3; t++) {
-    const smb_block_cand *cp = t_cig.cands + t;
+  if (!cs || cs->qlen != (uint32_t) qlen) return -1;
+  for (t = 0; t < cs->nk3; t++) {
+    const smb_block_cand *cp = cs->cands + t;
     if ((SEQNUM_t) cp->sqidx != rrp->s_idx || (cp->reverse != 0) != is_rev) continue;
-    for (i = t_cig.res_first[t]; i < t_cig.res_first[t + 1]; i++) {
-      const smb_ali_result *r = t_cig.res + i;
+    for (i = cs->res_first[t]; i < cs->res_first[t + 1]; i++) {
+      const smb_ali_result *r = cs->res + i;
       const long long qs1 = is_rev ? (long long) qlen - r->qe : (long long) r->qs + 1;
       const long long qe1 = is_rev ? (long long) qlen - r->qs : (long long) r->qe + 1;
       if (r->score != rrp->swatscor || qs1 != (long long) rrp->q_start || qe1 != (long long) rrp->q_end ||
 	  (long long) cp->rs + r->rs + 1 != (long long) rrp->s_start ||
 	  (long long) cp->rs + r->re + 1 != (long long) rrp->s_end)
 	continue;
-      if (r->diff_len && !memcmp(t_cig.diff + r->diff_off, diffstr, r->diff_len)) return (long) i;
+      if (r->diff_len && !memcmp(cs->diff + r->diff_off, diffstr, r->diff_len)) return (long) i;
     }
   }
   return -1;
@@ -219,23 +222,24 @@ static int samRecordSingle(const ReportWriter *wrp, const REPALI *rrp, const Dif
   if (is_mapped) {
     /* CIGAR and NM from the device's output stage; the reference's functions where the record does not come
      * from a resident block (other drivers of this writer) or the stage reported the reference's error */
-    const long ci = cigarLookup(rrp, diffstr, qlen);
-    if (ci >= 0 && t_cig.cig_nm[ci] >= 0) {
-      const size_t lc = t_cig.cig_first[ci + 1] - t_cig.cig_first[ci];
+    const SmbCigarSource *cs = t_cigp;
+    const long ci = cigarLookup(cs, rrp, diffstr, qlen);
+    if (ci >= 0 && cs->cig_nm[ci] >= 0) {
+      const size_t lc = cs->cig_first[ci + 1] - cs->cig_first[ci];
       char *o = smbFastReserve(fp, lc + 8);
       if (o) {
-	memcpy(o, t_cig.cig_text + t_cig.cig_first[ci], lc);
+	memcpy(o, cs->cig_text + cs->cig_first[ci], lc);
 	smbFastCommit(lc);
       } else
-	fwrite(t_cig.cig_text + t_cig.cig_first[ci], 1, lc, fp);
-      editdist = t_cig.cig_nm[ci];
-      __atomic_fetch_add(&g_cig_dev, 1, __ATOMIC_RELAXED);
+	fwrite(cs->cig_text + cs->cig_first[ci], 1, lc, fp);
+      editdist = cs->cig_nm[ci];
+      t_cig_dev++;
     } else {
       errcode = diffStrPrintf(fp, diffstr,
 			      (char) ((oumodiflg & REPORTMODIF_XMISMATCH) ? DIFFSTRFORM_CIGEXT_XMISMATCH : DIFFSTRFORM_CIGEXT),
 			      clip_start, clip_end, (char) ((oumodiflg & REPORTMODIF_SOFTCLIP) != 0));
       if (!errcode) editdist = diffStrGetLevenshteinDistance(diffstr);
-      __atomic_fetch_add(&g_cig_host, 1, __ATOMIC_RELAXED);
+      t_cig_host++;
     }
   } else {
     fprintf(fp, OUFMT_SAM_NULLSTR);
