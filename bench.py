@@ -607,7 +607,11 @@ def main():
                 "ms_per_step": wall_ms, "sam_bytes_per_step": int(sam_bytes), "merged_sam_bytes_per_step": int(merged_bytes),
                 "rank0_map_ms_per_step": 1e3 * t_map / args.steps, "rank0_merge_ms_per_step": 1e3 * t_merge / args.steps,
                 "host_stage_wall_s": {k: v for k, v in c1["host_stage_s"].items() if v},   # (results.*: only with SMALT_B200_TIMING)
-                "host_stage_cpu_s": c1["host_cpu_s"]},
+                "host_stage_cpu_s": c1["host_cpu_s"],
+                # who formatted CIGAR / NM of the SAM records of the timed steps: the device's output stage
+                # (csrc/cigar.cu; default up to 8 host workers, SMALT_B200_DEVCIGAR=1 forces it) or diffstr.c on the host
+                "cigar_records_device_per_step": int((c1["cigar_dev"] - c0["cigar_dev"]) // args.steps),
+                "cigar_records_host_per_step": int((c1["cigar_host"] - c0["cigar_host"]) // args.steps)},
         "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
     }
     if mapped_fraction is not None:

@@ -984,8 +984,16 @@ static int fastmap_run(const SmaltMapConst *macop, SmaltMapArgs *maps, int nwork
   while (p < len && isspace((unsigned char) data[p])) p++;
   if (p >= len) { if (n_reads) *n_reads = 0; return ERRCODE_SUCCESS; }
   fm.macop = macop; fm.maps = maps; fm.proto = proto;
-  /* single-end SAM: the device also emits CIGAR and NM of every alignment (SMALT_B200_HOSTCIGAR=1: host formats) */
-  rmapWaveSetCigarMode((dataB || getenv("SMALT_B200_HOSTCIGAR")) ? 0 : smbShimReportCigarFlags(proto));
+  /* Single-end SAM: the device can also emit CIGAR and NM of every alignment (csrc/cigar.cu).  The stage follows
+   * the bottleneck: it takes ~5 % of the workers' CPU time away and lengthens every device batch by one small
+   * kernel and one copy - measured on one box (tools/core_sweep.py, 1 M C2 reads per call): 4 cores 5.5 M reads/s
+   * with it, 5.2 M without; 16 cores 11.7 M with it, 12.2 M without (there the device batches are the critical path).
+   * Default: on up to 8 workers (host-bound), off above; SMALT_B200_DEVCIGAR=1 / 0 forces it. */
+  {
+    const char *dc = getenv("SMALT_B200_DEVCIGAR");
+    const int on = dc ? atoi(dc) != 0 : (nworkers <= 8 && !getenv("SMALT_B200_HOSTCIGAR"));
+    rmapWaveSetCigarMode((dataB || !on) ? 0 : smbShimReportCigarFlags(proto));
+  }
   fm.data = data + p; fm.len = len - p;
   fm.is_fasta = data[p] == '>';
   fm.refparse = getenv("SMALT_B200_REFPARSE") != NULL;

@@ -118,6 +118,37 @@ def test_mapper_options(tmp_path, opts):
 
 
 @needs
+@pytest.mark.parametrize("workers,force", [(1, "0"), (12, "1"), (12, None)])
+def test_cigar_stage_placement(tmp_path, monkeypatch, workers, force):
+    """the CIGAR / NM stage runs on the device up to 8 workers and on the host above (it follows the bottleneck,
+    fastmap.inc.c); SMALT_B200_DEVCIGAR forces either - the records are the reference's in every case"""
+    from smalt_b200.mapper import Mapper
+    if force is None:
+        monkeypatch.delenv("SMALT_B200_DEVCIGAR", raising=False)
+    else:
+        monkeypatch.setenv("SMALT_B200_DEVCIGAR", force)
+    pref, fq, text = _workload(tmp_path, 31, [200_000], 13, 6, 20000, (80, 200), 0.03)
+    _, want = _ref_sam(tmp_path, pref, fq)
+    m = Mapper(pref, workers, ["-r", "7"])
+    try:
+        got = m.map_fastq(text).decode().splitlines()
+        dev, host = m.stats.cigar_dev, m.stats.cigar_host
+    finally:
+        m.close()
+    nmapped = sum(1 for l in got if l.split("\t")[5] != "*")
+    if force == "1":
+        assert dev == nmapped > 15000 and host == 0
+    else:
+        assert host == nmapped > 15000 and dev == 0
+    assert len(got) == len(want)
+    if workers == 1:
+        assert got == want
+    else:   # several workers: the draws among equally good hits are scheduling dependent (see above)
+        diff = [(a, b) for a, b in zip(got, want) if a != b and (int(a.split("\t")[4]) > 6 or int(b.split("\t")[4]) > 6)]
+        assert not diff, diff[0]
+
+
+@needs
 def test_mapreads_entry_point(tmp_path):
     """the multi-GPU entry point with world size 1 (sharding and merge are tested on CPU)"""
     pref, fq, text = _workload(tmp_path, 13, [200_000], 13, 6, 2000, (100, 101), 0.01)
