@@ -610,8 +610,8 @@ def main():
                 "host_stage_cpu_s": c1["host_cpu_s"],
                 # who formatted CIGAR / NM of the SAM records of the timed steps: the device's output stage
                 # (csrc/cigar.cu; default up to 8 host workers, SMALT_B200_DEVCIGAR=1 forces it) or diffstr.c on the host
-                "cigar_records_device_per_step": int((c1["cigar_dev"] - c0["cigar_dev"]) // args.steps),
-                "cigar_records_host_per_step": int((c1["cigar_host"] - c0["cigar_host"]) // args.steps)},
+                "cigar_records_device_per_step": int(c1["cigar_dev"]),   # (of the last timed step)
+                "cigar_records_host_per_step": int(c1["cigar_host"])},
         "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
     }
     if mapped_fraction is not None:

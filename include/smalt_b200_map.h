@@ -37,7 +37,7 @@ typedef struct {
 				replay, align, results, parse, and inside results: add, sort+filter, emit */
   double host_cpu_s[8];      /* thread CPU seconds of the first eight stages (no waiting for the GPU) */
   double cand_ms;            /* the part of k1_ms spent in candidate selection / task lists / score replay */
-  uint64_t cigar_dev, cigar_host; /* SAM records of this process so far whose CIGAR / NM came from the device's
+  uint64_t cigar_dev, cigar_host; /* SAM records of the last call whose CIGAR / NM came from the device's
 				     output stage / were formatted by the reference's diffstr.c on the host */
 } smbm_stats;
 

@@ -762,7 +762,9 @@ int __wrap_threadsRun(void)
       {
 	struct timespec t0, t1;
 	uint64_t nr = 0;
+	unsigned long long cd0, ch0;
 	fm_stats_reset();
+	smbShimCigarCounters(&cd0, &ch0);
 	m->out_len = 0;
 	clock_gettime(CLOCK_MONOTONIC, &t0);
 	errcode = fastmap_run(macop, maps, nworkers, dop->writerp, m->req_data, m->req_len, m->req_dataB, m->req_lenB,
@@ -775,7 +777,7 @@ int __wrap_threadsRun(void)
 	{
 	  unsigned long long cd, ch;
 	  smbShimCigarCounters(&cd, &ch);
-	  m->stats.cigar_dev = cd; m->stats.cigar_host = ch;
+	  m->stats.cigar_dev = cd - cd0; m->stats.cigar_host = ch - ch0;
 	}
 	m->stats.k2_tasks = g_counts[1]; m->stats.k2_cells = g_counts[2];
 	m->stats.k3_tasks = g_counts[3]; m->stats.k3_cells = g_counts[4];
