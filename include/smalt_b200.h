@@ -405,7 +405,8 @@ int smb_block_fetch_cigar(smb_ctx *ctx, smb_block_read *reads, smb_block_cand *c
 			  uint32_t *first_result, smb_ali_result *results, uint8_t *diffstr, void *cigar_blob);
 /* The same stage for a batch of n alignment strings given explicitly: string i starts at diffstr[diff_off[i]]
  * (0-terminated); the blob has the layout above with room for max_text bytes of text.  Returns SMB_ERR_CAPACITY
- * with *ntext = required text size if max_text is too small. */
+ * with *ntext = required text size if max_text is too small.  (Shares device buffers with the stage of a block:
+ * call it after smb_block_fetch_cigar, not between smb_block_run and the fetch.) */
 int smb_cigar_batch(smb_ctx *ctx, const uint8_t *diffstr, size_t ndiffbytes, const uint32_t *diff_off,
 		    const uint32_t *clip_start, const uint32_t *clip_end, int n, int flags,
 		    void *cigar_blob, size_t max_text, size_t *ntext);

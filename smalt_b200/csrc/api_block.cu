@@ -665,6 +665,9 @@ int smb_cigar_batch(smb_ctx *ctx, const uint8_t *diffstr, size_t ndiffbytes, con
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
   int nl = 0;
+  // this call reuses the buffers the output stage of a block keeps between smb_block_run and smb_block_fetch_cigar:
+  // a block that is still pending loses its text (its fetch then fails with SMB_ERR_STATE instead of reading them)
+  if (ctx->blk && ctx->blk->p.valid) ctx->blk->p.cigar = false;
   const size_t N = (size_t)n, ab = al256(N * 4), extra = al256(ndiffbytes) + 3 * ab;
   {
     Carver c(nullptr);
