@@ -1,6 +1,7 @@
 """Times smb_index_build (csrc/index_build.cu) stage by stage on a random genome:
     python tools/index_probe.py [Mb] [k] [nskip]
-SMB_INDEX_DEBUG=1 makes the library print the stage times; the second build is the warm one."""
+SMB_INDEX_DEBUG=1 makes the library print the stage times; the second build is the warm one.  The table is
+checked with smalt_b200/indexcheck.py (structure of every array, sampled grid positions found under their words)."""
 import os
 import sys
 import time
@@ -24,5 +25,8 @@ for it in range(2):
     t = time.time()
     ix = indexer.build_index_gpu(ctx, seqs, k, nskip)
     print("build %d: %.3f s  npos %d nwords %d" % (it, time.time() - t, ix["npos"], ix["nwords"]), flush=True)
-pos, idx = ix["pos"], ix["idx"]
-print("idx monotone:", bool(np.all(np.diff(idx.astype(np.int64)) >= 0)), " idx[-1]:", int(idx[-1]))
+from smalt_b200 import indexcheck  # noqa: E402
+t = time.time()
+indexcheck.check_structure(ix)
+n = indexcheck.check_samples(ix, seqs, k, nskip, nsample=20000)
+print("structure ok, %d sampled grid positions found under their words (%.1f s)" % (n, time.time() - t))
