@@ -54,6 +54,21 @@ def test_index_build_gpu_equals_host_builder(ctx, tmp_path, k, nskip, lens, p_n)
     assert want["npos"] > 0
 
 
+def test_index_build_gpu_large_genome_invariants(ctx):
+    """120 Mb, 20 M positions (5000 sort tiles, three scan levels): too large for the numpy host builder, checked
+    through the size-independent properties of smalt_b200/indexcheck.py (pinned against the host builder on CPU,
+    tests/test_indexcheck.py): every offset array monotone and complete, words ascending inside a key, positions
+    ascending inside a word (= the stable order of the sort), sampled grid positions found under their own words"""
+    from smalt_b200 import indexcheck
+    rng = np.random.default_rng(77)
+    seqs = [rng.integers(0, 4, n, dtype=np.uint8) for n in (70_000_003, 49_999_999)]
+    seqs[0][rng.integers(0, len(seqs[0]), 5000)] = 5
+    ix = indexer.build_index_gpu(ctx, seqs, 13, 6)
+    assert ix["typ"] == 1 and ix["npos"] > 19_000_000
+    indexcheck.check_structure(ix)
+    assert indexcheck.check_samples(ix, seqs, 13, 6, nsample=20000) > 19000
+
+
 def _fasta(path, seqs):
     let = np.frombuffer(b"ACGTNN", np.uint8)
     with open(path, "w") as f:
