@@ -371,6 +371,7 @@ static int dev_results(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, WREAD *rdarr, co
 		       short matchscor, const SeqSet *ssp, const SeqCodec *codecp, WAVE_DONEF *donef, void *user)
 {
   int errcode = ERRCODE_SUCCESS, i;
+  SmbCigarSource src;
   RMAPBUFF *bufp = rmp->bfp;
   double tres;
   tres = rnow();
@@ -458,7 +459,7 @@ static int dev_results(ErrMsg *errmsgp, RMap *rmp, RmapWave *w, WREAD *rdarr, co
       }
     }
     if (bw->have_cigar && b->nk3) {   /* the output stage's text for the alignments of this read (shim_report.c) */
-      SmbCigarSource src;
+      /* (`src` lives at function scope: the writer keeps a pointer to it until it is cleared below) */
       src.cands = bc + b->k3_first; src.res_first = bw->res_first + b->k3_first; src.nk3 = b->nk3;
       src.res = bw->res; src.diff = bw->diff;
       src.cig_first = bw->cig_first; src.cig_nm = bw->cig_nm; src.cig_text = bw->cig_text;
