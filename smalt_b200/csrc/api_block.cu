@@ -589,6 +589,8 @@ static int block_fetch_impl(smb_ctx *ctx, smb_block_read *reads, smb_block_cand 
   }
   if (!reads || (P.nk3 && (!cands || !errs || !first_result)) || (P.nres && !results) || (P.ndiff && !diffstr))
     return SMB_ERR_ARG;
+  if (want_cigar && !P.cigar) return fail(ctx, SMB_ERR_STATE, "smb_block_run() without SMB_CIGAR_ON");
+  if (want_cigar && !cigar_blob) return SMB_ERR_ARG;
   cudaSetDevice(ctx->device);
   cudaStream_t st = ctx->stream;
   int nl = 0;
@@ -625,8 +627,6 @@ static int block_fetch_impl(smb_ctx *ctx, smb_block_read *reads, smb_block_cand 
     }
   }
   if (want_cigar) {
-    if (!P.cigar) return fail(ctx, SMB_ERR_STATE, "smb_block_run() without SMB_CIGAR_ON");
-    if (!cigar_blob) return SMB_ERR_ARG;
     if (!P.nres || !P.nk3) *(uint32_t *)cigar_blob = 0;
     else if (P.multipass) {
       const int rc = cigar_fill_blob(ctx, P.cig, P.d_cig_off, P.ncig, cigar_blob, st, &nl);
