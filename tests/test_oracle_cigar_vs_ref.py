@@ -4,6 +4,7 @@ diffStrGetLevenshteinDistance (diffstr.c:1496-1510) of oracle/_ref/libsmalt_ref.
 answers of the reference's own test/bam_cigar_test.py."""
 import numpy as np
 import pytest
+from hypothesis import given, settings, strategies as st
 
 from diffgen import encode_columns, random_bytes_string, random_columns
 from golden_io import load_bam_cigar, parse_record
@@ -80,3 +81,17 @@ def test_cigar_known_answers(orc):
                         found = True
             assert found, (rd[key], sam)
             assert fld[5] == rd[key] and rd["nm"] in fld
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@settings(max_examples=400, deadline=None)
+@given(body=st.binary(min_size=0, max_size=60).map(lambda b: bytes(x or 1 for x in b)),
+       last=st.integers(0, 63), cs=st.integers(0, 500), ce=st.integers(0, 20000), soft=st.booleans(), xm=st.booleans())
+def test_cigar_fuzz_against_reference(body, last, cs, ce, soft, xm):
+    """arbitrary non-zero bytes closed by an S byte: text, edit distance and error code of the restatement equal
+    the reference's for strings no aligner writes"""
+    orc, ref = Oracle(), RefLib()
+    d = body + bytes([(3 << 6) | last, 0])
+    e, text, nm = ref.cigar(d, cs, ce, soft, xm)
+    got_text, got_nm = orc.cigar(d, cs, ce, soft, xm)
+    assert e == 0 and got_text == text and got_nm == nm
