@@ -94,6 +94,7 @@ def write_index(tmp, cfg, seqs, device=0, tag="idx"):
     pref = os.path.join(tmp, tag)
     total = sum(len(s) for s in seqs)
     words = pack3(np.concatenate(list(seqs) + [np.array([7], np.uint8)]))
+    check = None
     if total > 20_000_000:
         from smalt_b200.capi import Context
         ctx = Context(device)
@@ -101,11 +102,28 @@ def write_index(tmp, cfg, seqs, device=0, tag="idx"):
             ix = indexer.build_index_gpu(ctx, seqs, cfg["k"], cfg["s"], words=words)
         finally:
             ctx.close()
+        check = index_invariants(ix, seqs, cfg["k"], cfg["s"])
     else:
         ix = indexer.build_index(seqs, cfg["k"], cfg["s"])
     indexer.write_smi(pref, ix)
     indexer.write_sma(pref, ["chr%d" % (i + 1) for i in range(len(seqs))], seqs, words=words)
-    return pref, {"nwords": int(ix["nwords"]), "nkeys": int(ix["nkeys"]), "npos": int(ix["npos"]), "typ": int(ix["typ"])}
+    info = {"nwords": int(ix["nwords"]), "nkeys": int(ix["nkeys"]), "npos": int(ix["npos"]), "typ": int(ix["typ"])}
+    if check:
+        info["check"] = check
+    return pref, info
+
+
+def index_invariants(ix, seqs, k, nskip, nsample=5000):
+    """a GPU-built index is too large for the host builder: the size-independent checks of smalt_b200/indexcheck.py
+    (pinned against the host builder in tests/test_indexcheck.py); raises if one fails"""
+    from smalt_b200 import indexcheck
+    what = []
+    if int(ix["npos"]) <= 100_000_000:   # (the array-wide passes take ~16 bytes per position of host memory)
+        indexcheck.check_structure(ix)
+        what.append("offset arrays monotone and complete, words / positions in order")
+    n = indexcheck.check_samples(ix, seqs, k, nskip, nsample=nsample)
+    what.append("%d sampled grid positions found under their words" % n)
+    return "; ".join(what)
 
 
 def simread(pref, cfg, n, seed, out, name_prefix):

@@ -49,24 +49,24 @@ def check_structure(ix):
 def lookup(ix, words):
     """-> (nhits, first position index) per 2k-bit word"""
     words = np.asarray(words, np.uint64)
-    idx = ix["idx"].astype(np.int64)
+    idx = ix["idx"]                     # (gathers only: the arrays of a 3 Gb genome are not converted as a whole)
     if ix["typ"] == 0:
-        lo = idx[words.astype(np.int64)]
-        return idx[words.astype(np.int64) + 1] - lo, lo
+        lo = idx[words.astype(np.int64)].astype(np.int64)
+        return idx[words.astype(np.int64) + 1].astype(np.int64) - lo, lo
     nbl = np.uint64(ix["nbits_lo"])
     hi = (words >> nbl).astype(np.uint64)
     keymod = np.uint64(1 << (ix["nbits_key"] - ix["nbits_lo"]))
     key = ((hash32mix(hi) % keymod) << nbl) + (words & ((np.uint64(1) << nbl) - np.uint64(1)))
     key = key.astype(np.int64)
-    a, b = idx[key], idx[key + 1]
-    widx, pidx = ix["wordidx"], ix["posidx"].astype(np.int64)
+    a, b = idx[key].astype(np.int64), idx[key + 1].astype(np.int64)
+    widx, pidx = ix["wordidx"], ix["posidx"]
     nh = np.zeros(len(words), np.int64)
     first = np.zeros(len(words), np.int64)
     for i in range(len(words)):   # binary search in the key's words (a few entries)
         j = a[i] + np.searchsorted(widx[a[i]:b[i]], np.uint32(hi[i]))
         if j < b[i] and widx[j] == np.uint32(hi[i]):
-            first[i] = pidx[j]
-            nh[i] = pidx[j + 1] - pidx[j]
+            first[i] = int(pidx[j])
+            nh[i] = int(pidx[j + 1]) - int(pidx[j])
     return nh, first
 
 
