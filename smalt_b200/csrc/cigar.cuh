@@ -7,7 +7,7 @@
 
 namespace smb {
 
-__device__ __forceinline__ int cg_put(char *out, const int pos, uint32_t count, const char op, const bool write) {
+__host__ __device__ __forceinline__ int cg_put(char *out, const int pos, uint32_t count, const char op, const bool write) {
   int nd = 1;
   for (uint32_t v = count; v >= 10u; v /= 10u) ++nd;
   if (write) {
@@ -19,8 +19,10 @@ __device__ __forceinline__ int cg_put(char *out, const int pos, uint32_t count, 
 
 // returns the text length; *nm = edit distance, or < 0 where the reference fails (then length 0):
 // -1 = ERRCODE_FAILURE (empty string), -59 = -ERRCODE_DIFFSTR (the string does not end with an S byte)
+// (__host__ too: tests/test_cigar_walk_host.py compiles this very function for the CPU and checks it against the
+// reference's functions without a GPU)
 template <bool WRITE>
-__device__ __forceinline__ int cg_walk(const uint8_t *__restrict__ d, const uint32_t clip_start, const uint32_t clip_end,
+__host__ __device__ __forceinline__ int cg_walk(const uint8_t *__restrict__ d, const uint32_t clip_start, const uint32_t clip_end,
                                        const int flags, char *out, int *nm) {
   const bool silent_mm = !(flags & SMB_CIGAR_XMISMATCH);
   const char clipc = (flags & SMB_CIGAR_SOFTCLIP) ? 'S' : 'H';
