@@ -53,3 +53,26 @@ def test_row_table_prmt_gives_both_scores(match, mismatch):
                     assert got == 0
                 else:
                     assert got == (match if q == r else mismatch)
+
+
+def qsel_masked(qa, qb):              # sw2_qsel_masked: N and padding columns read the zero half of the table
+    ia, ib = (qa if qa < 4 else 4), (qb if qb < 4 else 4)
+    return (ia | ((ia | 8) << 4) | (ib << 8) | ((ib | 8) << 12)) ^ 0x4444
+
+
+def wsel(a, b):                       # sw2_build_lut: row selector nibbles + N / padding masks of the masked form
+    return (a * 0x11 if a < 4 else 0x00440000) | (b * 0x1100 if b < 4 else 0x44000000)
+
+
+@pytest.mark.parametrize("match,mismatch", [(1, -2), (3, -5), (127, -127)])
+def test_masked_form_scores_zero_for_n_in_reads_and_rows(match, mismatch):
+    """the form pairs with an N in a READ take (short and long kernel): table {match, mismatch x3 | 0 x4} as the
+    second PRMT source, index = (read selector ^ row selector) & ~row mask"""
+    t0 = (match & 0xFF) | ((mismatch & 0xFF) * 0x01010100)
+    for a, b in itertools.product((0, 1, 2, 3, 5, 6, 7), repeat=2):
+        w = wsel(a, b)
+        for qa, qb in itertools.product((0, 1, 2, 3, 5, 7, 8), repeat=2):
+            s2 = prmt(0, t0, (qsel_masked(qa, qb) ^ w) & ~(w >> 16) & 0xFFFF)
+            for q, r, got in ((qa, a, s16(s2 & 0xFFFF)), (qb, b, s16(s2 >> 16))):
+                want = 0 if (q >= 4 or r >= 4) else (match if q == r else mismatch)
+                assert got == want, (a, b, qa, qb, got, want)
