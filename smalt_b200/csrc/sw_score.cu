@@ -28,6 +28,8 @@
 #include <algorithm>
 #include <vector>
 
+#include "sw2_lut.cuh"
+
 namespace smb {
 
 constexpr int SW_WARPS = 4;  // warps per CTA
@@ -243,38 +245,15 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 //   raw   the base codes for the per-cell table path (X anywhere in the pair's reads or windows)
 // Entry numbers: a * 4 + b for two standard bases (the 16 entries every in-window step reads lie in 32 different
 // banks as 8-byte elements: lanes that read different entries never conflict), 16 + a * 8 + b otherwise.
-constexpr int SW2_LUT_N = 16 + 64;
-__device__ __forceinline__ uint32_t sw2_lut_index(uint32_t a, uint32_t b) {
-  return (a < 4u && b < 4u) ? a * 4u + b : 16u + a * 8u + b;
-}
-
+// (sw2_lut.cuh: sw2_lut_index, sw2_tab_word, sw2_wsel_word, sw2_qsel_tab, sw2_qsel_masked - host + device)
 __device__ __forceinline__ void sw2_build_lut(const Scoring &sc, uint2 *s_tab, uint32_t *s_wsel, uint32_t *s_rawc) {
   if (threadIdx.x < 64) {   // (the caller synchronises the CTA)
     const uint32_t a = threadIdx.x >> 3, b = threadIdx.x & 7u;
-    auto tab = [&](uint32_t x) {
-      uint32_t t = 0;
-      for (uint32_t q = 0; q < 4u; ++q) {
-        const int v = x < 4u ? (q == x ? sc.match : sc.mismatch) : (x == 4u ? sc.mismatch : 0);
-        t |= (uint32_t)(v & 0xff) << (8u * q);
-      }
-      return t;
-    };
     const uint32_t e = sw2_lut_index(a, b);
-    s_tab[e] = make_uint2(tab(a), tab(b));
-    s_wsel[e] = (a < 4u ? a * 0x11u : 0x00440000u) | (b < 4u ? b * 0x1100u : 0x44000000u);
+    s_tab[e] = make_uint2(sw2_tab_word(a, sc.match, sc.mismatch), sw2_tab_word(b, sc.match, sc.mismatch));
+    s_wsel[e] = sw2_wsel_word(a, b);
     s_rawc[e] = a | (b << 8);
   }
-}
-// the per-column PRMT selector of the row-table form; code 8 = padding column
-__device__ __forceinline__ uint32_t sw2_qsel_tab(uint32_t qa, uint32_t qb) {
-  return (qa < 4u ? (qa | ((qa | 8u) << 4)) : 0x88u) | ((qb < 4u ? ((qb | 4u) | ((qb | 12u) << 4)) : 0xCCu) << 8);
-}
-// ... of the masked form {qA, qA|8, qB, qB|8} (N, padding: 4), bit 2 flipped: the table is the SECOND source of
-// the PRMT (as first source ptxas overwrites it with the result and copies it afresh for every cell):
-// idx' = ((q ^ 4) ^ r) & ~mask
-__device__ __forceinline__ uint32_t sw2_qsel_masked(uint32_t qa, uint32_t qb) {
-  const uint32_t ia = qa < 4u ? qa : 4u, ib = qb < 4u ? qb : 4u;
-  return (ia | ((ia | 8u) << 4) | (ib << 8) | ((ib | 8u) << 12)) ^ 0x4444u;
 }
 
 template <int C, int LANES>
