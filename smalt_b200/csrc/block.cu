@@ -36,14 +36,15 @@ constexpr int SW2_MAXROWS_ = 512;                   // sw_score.cu: staged windo
 
 __device__ __forceinline__ uint64_t shiftpart(uint64_t x) { return x & ~((uint64_t)HALFMASK); }
 
-// Division by the sampling step.  Every dividend on this path is a read offset or a seed length
-// (< 2^26), for which floor(x / d) = umulhi(x, ceil(2^32 / d)) exactly (d <= 255: the error term
-// x * (d - 1) / 2^32 stays below 1); a hardware-free replacement of the ~20-instruction runtime divide
-// that sits in the innermost hit loops.
+// Division by the sampling step.  Every dividend on this path is a read offset or a seed length; for
+// x < 2^24 and d <= 255, floor(x / d) = umulhi(x, floor(2^32 / d) + 1) exactly (the error term x * e / 2^32 with
+// e <= 1 stays below 1 / d; checked exhaustively in tests/test_stepdiv_model.py - beyond 2^24 the first wrong
+// quotient is at x = 16 909 559, d = 255), anything larger takes the hardware divide; a replacement of the
+// ~20-instruction runtime divide that sits in the innermost hit loops.
 struct StepDiv {
   uint32_t d, m;
   __device__ __forceinline__ explicit StepDiv(int step) : d((uint32_t)step), m(step > 1 ? (uint32_t)(0x100000000ull / (uint32_t)step) + 1u : 0u) {}
-  __device__ __forceinline__ uint32_t div(uint32_t x) const { return d > 1u ? (x < (1u << 26) ? __umulhi(x, m) : x / d) : x; }
+  __device__ __forceinline__ uint32_t div(uint32_t x) const { return d > 1u ? (x < (1u << 24) ? __umulhi(x, m) : x / d) : x; }
   __device__ __forceinline__ uint32_t mod(uint32_t x) const { return x - div(x) * d; }
   __device__ __forceinline__ int divs(int x) const { return x >= 0 ? (int)div((uint32_t)x) : -(int)div((uint32_t)(-x)); }   // C truncation
 };
